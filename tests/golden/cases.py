@@ -1,0 +1,60 @@
+"""Golden-case definitions shared by make_golden.py (generator) and the tests (consumers).
+
+Inputs are drawn from numpy's PCG64 streams (stable across platforms), never from /root/reference,
+so every test can rebuild them on the GPU box.
+"""
+import numpy as np
+import torch
+
+# name -> (d_model, headdim, d_state, batch, grid)   [SURVEY.md §8(c): the four fp64-verified configs + a 128^2 one]
+MIXER_CASES = {
+    "mixer_d32_p4_n16_g16": (32, 4, 16, 2, 16),
+    "mixer_d128_p4_n16_g8": (128, 4, 16, 2, 8),
+    "mixer_d32_p4_n64_g8": (32, 4, 64, 2, 8),
+    "mixer_d64_p8_n128_g6": (64, 8, 128, 2, 6),
+    "mixer_d32_p4_n16_g128": (32, 4, 16, 1, 128),   # refiner shape at a 128x128 token grid; stored subsampled
+}
+SUBSAMPLE_STRIDE = 61  # token stride used to store `out`/`du` of the 128^2 case
+
+# name -> (C, k, levels, batch, H, W, bias)   [instances of models/ADNMUNet.py at reduced size + the odd-size pad path]
+WTCONV_CASES = {
+    "wtconv_c5_k5_l3_64": (5, 5, 3, 2, 64, 64, True),
+    "wtconv_c32_k5_l2_32": (32, 5, 2, 2, 32, 32, True),
+    "wtconv_c64_k5_l1_16": (64, 5, 1, 1, 16, 16, True),
+    "wtconv_c32_k5_l3_33": (32, 5, 3, 1, 33, 33, True),     # odd sizes at every level (models/WTConv2d.py:114-116)
+    "wtconv_c8_k3_l2_20x28": (8, 3, 2, 2, 20, 28, False),   # non-square, k=3, no bias
+}
+
+METRIC_CASE = ("metrics_counts", (3, 20, 64, 64))
+
+
+def rng_normal(seed, shape, dtype=torch.float64):
+    return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape)).to(dtype)
+
+
+def rng_uniform(seed, shape, dtype=torch.float64):
+    return torch.from_numpy(np.random.default_rng(seed).random(shape)).to(dtype)
+
+
+def mixer_inputs(name, dtype=torch.float64):
+    D, P, N, B, g = MIXER_CASES[name]
+    seed = 1000 + sorted(MIXER_CASES).index(name)
+    u = rng_normal(seed, (B, g * g, D), dtype)
+    dout = rng_normal(seed + 500, (B, g * g, D), dtype)
+    return u, dout
+
+
+def wtconv_inputs(name, dtype=torch.float64):
+    C, k, L, B, H, W, bias = WTCONV_CASES[name]
+    seed = 2000 + sorted(WTCONV_CASES).index(name)
+    return rng_normal(seed, (B, C, H, W), dtype), rng_normal(seed + 500, (B, C, H, W), dtype)
+
+
+def metric_inputs():
+    shape = METRIC_CASE[1]
+    # uniform in [-0.1, 1.1]: exercises the clip, every threshold (20..40)/90, and values at exact k/90 boundaries
+    obs = rng_uniform(3000, shape, torch.float32) * 1.2 - 0.1
+    sim = rng_uniform(3001, shape, torch.float32) * 1.2 - 0.1
+    obs.view(-1)[::97] = torch.tensor([20, 30, 35, 40], dtype=torch.float32).repeat(obs.numel())[: obs.view(-1)[::97].numel()] / 90
+    sim.view(-1)[::89] = torch.tensor([40, 35, 30, 20], dtype=torch.float32).repeat(sim.numel())[: sim.view(-1)[::89].numel()] / 90
+    return obs.numpy(), sim.numpy()

@@ -1,0 +1,96 @@
+"""Pins the CPU oracle (oracle/*.py) to golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import adnssd_oracle as AO
+from oracle import metrics_oracle as MO
+from oracle import wtconv_oracle as WO
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64)
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
+
+
+def load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    params = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")}
+    grads = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad/")}
+    return z, params, grads
+
+
+@pytest.mark.parametrize("name", sorted(cases.MIXER_CASES))
+def test_mixer_oracle_matches_reference_fp64(golden_dir, name):
+    D, P, N, B, g = cases.MIXER_CASES[name]
+    z, params, grads = load(golden_dir, name)
+    p = {k: v.double() for k, v in params.items()}
+    u, dout = cases.mixer_inputs(name, torch.float32)
+    if "u" in z.files:  # inputs stored explicitly for the small cases: the PCG64 rebuild must agree bit for bit
+        assert np.array_equal(z["u"], u.numpy()) and np.array_equal(z["dout"], dout.numpy())
+    u, dout = u.double(), dout.double()
+    s = cases.SUBSAMPLE_STRIDE if g >= 64 else 1
+    out = AO.mixer_forward(p, u, g, g, P, N)
+    du, og = AO.mixer_backward(p, u, g, g, P, N, dout)
+    assert rel(out[:, ::s], z["out"]) < 1e-12
+    assert rel(du[:, ::s], z["du"]) < 1e-12
+    assert set(grads) == set(AO.PARAM_NAMES) - set(AO.UNUSED_PARAMS)
+    for k, ref in grads.items():
+        assert rel(og[k].reshape(ref.shape), ref) < 1e-11, k
+
+
+def test_mixer_oracle_explicit_backward_equals_autograd():
+    D, P, N, g = 16, 4, 8, 5
+    p = AO.init_params(D, P, N, seed=3, perturb=0.3, dtype=torch.float64)
+    q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    u = cases.rng_normal(5, (2, g * g, D)).requires_grad_(True)
+    dout = cases.rng_normal(6, (2, g * g, D))
+    AO.mixer_forward(q, u, g, g, P, N).backward(dout)
+    du, og = AO.mixer_backward(p, u.detach(), g, g, P, N, dout)
+    assert rel(du, u.grad) < 1e-12
+    for k in AO.PARAM_NAMES:
+        if k in AO.UNUSED_PARAMS:
+            assert q[k].grad is None
+        else:
+            assert rel(og[k].reshape(q[k].shape), q[k].grad) < 1e-11, k
+
+
+@pytest.mark.parametrize("name", sorted(cases.WTCONV_CASES))
+def test_wtconv_oracle_matches_reference_fp64(golden_dir, name):
+    C, k, L, B, H, W, bias = cases.WTCONV_CASES[name]
+    z, params, grads = load(golden_dir, name)
+    p = {n: v.double() for n, v in params.items()}
+    x, dy = cases.wtconv_inputs(name, torch.float32)
+    assert np.array_equal(z["x"], x.numpy()) and np.array_equal(z["dy"], dy.numpy())
+    out, dx, og = WO.wtconv_forward_backward(p, x.double(), L, dy.double())
+    assert rel(out, z["out"]) < 1e-12
+    assert rel(dx, z["dx"]) < 1e-12
+    assert set(grads) == set(og)
+    for n, ref in grads.items():
+        assert rel(og[n], ref) < 1e-11, n
+
+
+def test_haar_filters_match_reference_parameters(golden_dir):
+    z, params, _ = load(golden_dir, "wtconv_c5_k5_l3_64")
+    wt, iwt = WO.haar_filters(5)
+    assert torch.allclose(params["wt_filter"], wt, atol=1e-7) and torch.allclose(params["iwt_filter"], iwt, atol=1e-7)
+    x = cases.rng_normal(1, (1, 3, 8, 10))
+    assert rel(WO.haar_idwt(WO.haar_dwt(x)), x) < 1e-14  # orthonormal round trip
+
+
+def test_metric_counts_match_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, cases.METRIC_CASE[0] + ".npz"))
+    obs, sim = cases.metric_inputs()
+    table = MO.counts(obs, sim)
+    assert np.array_equal(table, z["table"])
+    assert int(MO.float2int(obs).astype(np.int64).sum()) == int(z["obs_int_checksum"])
+    assert (table.sum(1) == obs.size).all()
+    sc = MO.scores(table)
+    assert np.allclose(sc["CSI"], table[:, 0] / (table[:, 0] + table[:, 1] + table[:, 2]))
+    # CSI and HSS are symmetric under the FP<->FN swap the reference's call order introduces
+    sw = MO.scores(table[:, [0, 2, 1, 3]])
+    assert np.allclose(sw["CSI"], sc["CSI"]) and np.allclose(sw["HSS"], sc["HSS"])
