@@ -1,0 +1,11 @@
+"""adnm-unet_b200: B200-native (sm_100a) ADN-SSD token mixer, Haar WTConv2d and threshold counts behind the
+reference's own module API (kanyu369/ADNM-UNet: models/ADNssd.py::Mamba2, models/WTConv2d.py::WTConv2d,
+datasets/Shanghai_metrics.py).  All compute goes through the C ABI in include/adnb200.h (ctypes); there is no
+CPU or PyTorch fallback - calling an op without the built CUDA library or without a GPU raises."""
+from adnm_unet_b200 import _lib  # noqa: F401
+from adnm_unet_b200.mixer import Mamba2, adnssd_mixer  # noqa: F401
+from adnm_unet_b200.wtconv import WTConv2d, wtconv2d  # noqa: F401
+from adnm_unet_b200.metrics import threshold_counts, csi_hss  # noqa: F401
+from adnm_unet_b200.inject import install_into_reference  # noqa: F401
+
+__all__ = ["Mamba2", "adnssd_mixer", "WTConv2d", "wtconv2d", "threshold_counts", "csi_hss", "install_into_reference"]

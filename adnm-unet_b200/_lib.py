@@ -1,0 +1,112 @@
+"""ctypes binding of include/adnb200.h.  The library is built in-tree by `adnm_unet_b200.build` (nvcc, sm_100a).
+There is deliberately no fallback: a missing library or a non-CUDA tensor raises."""
+import ctypes as C
+import os
+
+import torch
+
+ADN_F32, ADN_BF16 = 0, 1
+WT_MAX_LEVELS = 8
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libadnb200.so")
+_lib = None
+
+fp = C.POINTER(C.c_float)
+
+MIXER_FIELDS = ("dt_bias", "A_log", "D", "scale", "shift", "alpha1", "alpha2", "in_proj_w",
+                "conv_13_x1_w", "conv_31_x1_w", "conv_13_x2_w", "conv_31_x2_w",
+                "conv_13_bc1_w", "conv_31_bc1_w", "conv_13_bc2_w", "conv_31_bc2_w",
+                "conv2d_w", "norm_w", "norm_b", "conv2d_z_w", "out_proj_w")
+
+
+class AdnShape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "H", "W", "D", "Di", "P", "G", "N", "dtype", "flags")]
+
+
+class AdnWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in MIXER_FIELDS]
+
+
+class AdnWeightGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in MIXER_FIELDS]
+
+
+class WtShape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "C", "H", "W", "k", "levels", "has_bias", "dtype")]
+
+
+class WtWeights(C.Structure):
+    _fields_ = [("base_conv_w", C.c_void_p), ("base_conv_b", C.c_void_p), ("base_scale_w", C.c_void_p),
+                ("wavelet_conv_w", C.c_void_p * WT_MAX_LEVELS), ("wavelet_scale_w", C.c_void_p * WT_MAX_LEVELS)]
+
+
+class WtWeightGrads(C.Structure):
+    _fields_ = WtWeights._fields_
+
+
+EXPORTS = {
+    "adnssd_workspace_bytes": (C.c_int, [C.POINTER(AdnShape)] + [C.POINTER(C.c_size_t)] * 3),
+    "adnssd_forward": (C.c_int, [C.POINTER(AdnShape), C.POINTER(AdnWeights)] + [C.c_void_p] * 5),
+    "adnssd_backward": (C.c_int, [C.POINTER(AdnShape), C.POINTER(AdnWeights), C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.POINTER(AdnWeightGrads), C.c_void_p, C.c_void_p]),
+    "wtconv_workspace_bytes": (C.c_int, [C.POINTER(WtShape)] + [C.POINTER(C.c_size_t)] * 3),
+    "wtconv_forward": (C.c_int, [C.POINTER(WtShape), C.POINTER(WtWeights)] + [C.c_void_p] * 5),
+    "wtconv_backward": (C.c_int, [C.POINTER(WtShape), C.POINTER(WtWeights), C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.POINTER(WtWeightGrads), C.c_void_p, C.c_void_p]),
+    "adn_threshold_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.c_int32, C.c_float,
+                                       C.c_void_p, C.c_void_p]),
+    "adn_last_error": (C.c_char_p, []),
+    "adn_abi_version": (C.c_int, []),
+    "adn_device_supported": (C.c_int, []),
+}
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the CUDA library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(_LIB_PATH):
+            raise ImportError(f"{_LIB_PATH} not found: run `python -m adnm_unet_b200.build` (nvcc, sm_100a). "
+                              "adnm-unet_b200 has no CPU / PyTorch fallback.")
+        lib = C.CDLL(_LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.adn_abi_version() != 1:
+            raise ImportError("libadnb200.so ABI version mismatch; rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"adnb200 {what} failed (code {rc}): {load().adn_last_error().decode()}")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return ADN_F32
+    if t.dtype == torch.bfloat16:
+        return ADN_BF16
+    raise RuntimeError(f"adnb200: unsupported activation dtype {t.dtype} (float32 or bfloat16)")
+
+
+def require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"adnb200: `{name}` is on {t.device}; the sm_100a library is the only implementation "
+                           "(no CPU fallback)")
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def scratch(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

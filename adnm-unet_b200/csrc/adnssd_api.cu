@@ -1,0 +1,118 @@
+// C-ABI entry points of the ADN-SSD mixer (include/adnb200.h).  Validates the shape, carves the caller's
+// buffers and enqueues the kernels on the caller's stream.  No allocation, no host sync, no CPU fallback.
+#include <stdarg.h>
+#include <string.h>
+
+#include "adn_common.cuh"
+#include "adnssd_generic.cuh"
+#include "adnssd_sm100.cuh"
+
+namespace adn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int validate(const AdnShape* s) {
+  ADN_REQUIRE(s != nullptr, ADN_ERR_NULL, "AdnShape is NULL");
+  ADN_REQUIRE(s->B > 0 && s->H > 0 && s->W > 0 && s->D > 0, ADN_ERR_SHAPE, "B/H/W/D must be positive (got %d,%d,%d,%d)",
+              s->B, s->H, s->W, s->D);
+  ADN_REQUIRE(s->G == 2, ADN_ERR_SHAPE, "only ngroups == 2 is supported (the branch models/ADNssd.py:278 takes); got %d",
+              s->G);
+  ADN_REQUIRE(s->Di > 0 && s->Di % 4 == 0, ADN_ERR_SHAPE, "d_inner must be a positive multiple of 4 (got %d)", s->Di);
+  ADN_REQUIRE(s->P > 0 && s->Di % s->P == 0, ADN_ERR_SHAPE, "d_inner %% headdim != 0 (%d, %d)", s->Di, s->P);
+  ADN_REQUIRE(s->N > 0 && (s->G * s->N) % 4 == 0, ADN_ERR_SHAPE, "ngroups*d_state must be a multiple of 4 (got %d)",
+              s->G * s->N);
+  ADN_REQUIRE(s->dtype == ADN_F32 || s->dtype == ADN_BF16, ADN_ERR_DTYPE, "unsupported dtype %d", s->dtype);
+  ADN_REQUIRE(s->flags == 0, ADN_ERR_SHAPE, "flags must be 0");
+  ADN_REQUIRE((long long)s->B * s->H * s->W < (1LL << 31) / 4, ADN_ERR_SHAPE, "too many tokens");
+  return ADN_OK;
+}
+
+static int check_weights(const AdnWeights* w) {
+  ADN_REQUIRE(w != nullptr, ADN_ERR_NULL, "AdnWeights is NULL");
+  const void* req[] = {w->dt_bias, w->A_log, w->D, w->alpha1, w->in_proj_w, w->conv_13_x1_w, w->conv_31_x1_w,
+                       w->conv_13_x2_w, w->conv_31_x2_w, w->conv_13_bc1_w, w->conv_31_bc1_w, w->conv_13_bc2_w,
+                       w->conv_31_bc2_w, w->conv2d_w, w->norm_w, w->norm_b, w->conv2d_z_w, w->out_proj_w};
+  for (size_t i = 0; i < sizeof(req) / sizeof(req[0]); ++i)
+    ADN_REQUIRE(req[i] != nullptr, ADN_ERR_NULL, "AdnWeights: required tensor #%zu is NULL", i);
+  return ADN_OK;
+}
+
+}  // namespace adn
+
+using namespace adn;
+
+extern "C" {
+
+const char* adn_last_error(void) { return adn::g_err; }
+int adn_abi_version(void) { return ADNB200_ABI_VERSION; }
+
+int adn_device_supported(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+int adnssd_workspace_bytes(const AdnShape* s, size_t* saved_bytes, size_t* fwd_ws, size_t* bwd_ws) {
+  int rc = validate(s);
+  if (rc) return rc;
+  MixerDims d = make_dims(*s);
+  size_t sv, fw, bw;
+  if (s->dtype == ADN_F32) {
+    sv = SavedBufs<float>(d, nullptr).bytes;
+    fw = FwdWs<float>(d, nullptr).bytes;
+    bw = BwdWs<float>(d, nullptr).bytes;
+  } else {
+    sv = SavedBufs<bf16>(d, nullptr).bytes;
+    fw = FwdWs<bf16>(d, nullptr).bytes;
+    bw = BwdWs<bf16>(d, nullptr).bytes;
+    size_t fw2 = 0, bw2 = 0;
+    sm100_workspace_bytes(d, &fw2, &bw2);
+    fw = fw > fw2 ? fw : fw2;
+    bw = bw > bw2 ? bw : bw2;
+  }
+  if (saved_bytes) *saved_bytes = sv;
+  if (fwd_ws) *fwd_ws = fw;
+  if (bwd_ws) *bwd_ws = bw;
+  return ADN_OK;
+}
+
+int adnssd_forward(const AdnShape* s, const AdnWeights* w, const void* u, void* out, void* saved, void* workspace,
+                   void* stream) {
+  int rc = validate(s);
+  if (rc) return rc;
+  rc = check_weights(w);
+  if (rc) return rc;
+  ADN_REQUIRE(u && out && workspace, ADN_ERR_NULL, "u / out / workspace must not be NULL");
+  MixerDims d = make_dims(*s);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s->dtype == ADN_F32) return generic_forward<float>(d, *w, (const float*)u, (float*)out, saved, workspace, st);
+  if (sm100_supported(d)) return sm100_forward(d, *w, (const bf16*)u, (bf16*)out, saved, workspace, st);
+  return generic_forward<bf16>(d, *w, (const bf16*)u, (bf16*)out, saved, workspace, st);
+}
+
+int adnssd_backward(const AdnShape* s, const AdnWeights* w, const void* u, const void* saved, const void* dout,
+                    void* du, const AdnWeightGrads* g, void* workspace, void* stream) {
+  int rc = validate(s);
+  if (rc) return rc;
+  rc = check_weights(w);
+  if (rc) return rc;
+  ADN_REQUIRE(u && saved && dout && du && g && workspace, ADN_ERR_NULL,
+              "u / saved / dout / du / grads / workspace must not be NULL");
+  MixerDims d = make_dims(*s);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s->dtype == ADN_F32)
+    return generic_backward<float>(d, *w, (const float*)u, saved, (const float*)dout, (float*)du, *g, workspace, st);
+  if (sm100_supported(d))
+    return sm100_backward(d, *w, (const bf16*)u, saved, (const bf16*)dout, (bf16*)du, *g, workspace, st);
+  return generic_backward<bf16>(d, *w, (const bf16*)u, saved, (const bf16*)dout, (bf16*)du, *g, workspace, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,21 @@
+"""Make the unmodified reference network use the B200 kernels: rebind the two module globals the reference
+resolves at construction time: `models.ADNMUNet.Mamba2` (looked up inside `create_block`,
+models/ADNMUNet.py:277) and `models.model_untils.WTConv2d` (models/model_untils.py:17,101).  No reference file is
+edited; call this before `create_ADNMUNet(...)`."""
+import importlib
+
+
+def install_into_reference(adnmunet_module="models.ADNMUNet", untils_module="models.model_untils",
+                           mixer=True, wtconv=True):
+    from adnm_unet_b200.mixer import Mamba2
+    from adnm_unet_b200.wtconv import WTConv2d
+    done = []
+    if mixer:
+        m = importlib.import_module(adnmunet_module)
+        m.Mamba2 = Mamba2
+        done.append(adnmunet_module + ".Mamba2")
+    if wtconv:
+        m = importlib.import_module(untils_module)
+        m.WTConv2d = WTConv2d
+        done.append(untils_module + ".WTConv2d")
+    return done

@@ -1,0 +1,157 @@
+/*
+ * adnb200.h - C ABI of the B200-native (sm_100a) ADN-SSD token mixer, Haar WTConv2d and
+ * threshold-count kernels.  Plain pointers and sizes only; no torch / CUDA types in signatures
+ * (`stream` is a cudaStream_t passed as void*).
+ *
+ * The reference (kanyu369/ADNM-UNet) is pure Python and has no FFI; each entry point below
+ * replaces the body of one reference Python method, and the reference-side binding a maintainer
+ * would add is the ctypes stub shown in INTEGRATION.md.
+ *
+ *   adnssd_forward / adnssd_backward   <- models/ADNssd.py:302-462  Mamba2.forward (+ its autograd)
+ *   wtconv_forward / wtconv_backward   <- models/WTConv2d.py:100-153 WTConv2d.forward (+ its autograd)
+ *   adn_threshold_counts               <- datasets/Shanghai_metrics.py:45-47,105-114 float2int + _cal_frame
+ *
+ * Conventions:
+ *  - every pointer is a DEVICE pointer on the current CUDA device unless stated otherwise;
+ *  - the caller owns every buffer; the library allocates nothing, keeps no pointer after return;
+ *  - work is enqueued on `stream` with no host synchronisation (CUDA-graph capturable);
+ *  - parameters and parameter gradients are float32 in the reference's native state_dict layout;
+ *    gradient buffers are OVERWRITTEN, never accumulated into;
+ *  - return 0 on success, non-zero ADN_ERR_* otherwise, message via adn_last_error() (thread-local).
+ *    Unsupported shapes are errors: there is no CPU fallback and no alternative backend.
+ */
+#ifndef ADNB200_H_
+#define ADNB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADNB200_ABI_VERSION 1
+
+enum { ADN_OK = 0, ADN_ERR_SHAPE = 1, ADN_ERR_DTYPE = 2, ADN_ERR_NULL = 3, ADN_ERR_CUDA = 4, ADN_ERR_ARCH = 5 };
+
+/* Activation dtype at the seam (u, out, dout, du, x, y, ...).  ADN_F32 is the "check mode": every
+ * intermediate and every contraction in fp32 (tolerance 1e-4 vs the reference).  ADN_BF16: bf16 I/O and
+ * saved intermediates, bf16 tensor-core operands, fp32 accumulation / statistics / parameter gradients. */
+enum { ADN_F32 = 0, ADN_BF16 = 1 };
+
+/* ------------------------------------------------------------------ ADN-SSD mixer ---------- */
+
+typedef struct AdnShape {
+  int32_t B;      /* batch                                                                        */
+  int32_t H, W;   /* token grid, L = H*W (the reference only ever passes H == W, ADNMUNet.py:120) */
+  int32_t D;      /* d_model                                                                      */
+  int32_t Di;     /* d_inner = expand * d_model          (models/ADNssd.py:84), Di % 4 == 0       */
+  int32_t P;      /* headdim, Di % P == 0                (:85,:90-91)                             */
+  int32_t G;      /* ngroups; only 2 is supported (the branch taken at :278)                      */
+  int32_t N;      /* d_state                             (:86), (G*N) % 4 == 0                    */
+  int32_t dtype;  /* ADN_F32 | ADN_BF16                                                           */
+  int32_t flags;  /* reserved, must be 0                                                          */
+} AdnShape;
+
+/* The 21 state_dict tensors of one Mamba2 mixer (models/ADNssd.py:100-248), float32, native layout.
+ * scale / shift / alpha2 are declared by the reference but never read (:227-228,:246); they may be NULL. */
+typedef struct AdnWeights {
+  const float* dt_bias;        /* (nh)                 nh = Di / P                     */
+  const float* A_log;          /* (nh)                                                 */
+  const float* D;              /* (nh)                                                 */
+  const float* scale;          /* ()   unused                                          */
+  const float* shift;          /* ()   unused                                          */
+  const float* alpha1;         /* ()                                                   */
+  const float* alpha2;         /* ()   unused                                          */
+  const float* in_proj_w;      /* (2Di + 2GN + nh, D)  rows ordered [z | x | B | C | dt] */
+  const float* conv_13_x1_w;   /* (Di/4, 1, 1, 3)                                      */
+  const float* conv_31_x1_w;   /* (Di/4, 1, 3, 1)                                      */
+  const float* conv_13_x2_w;   /* (Di/4, 1, 1, 3)                                      */
+  const float* conv_31_x2_w;   /* (Di/4, 1, 3, 1)                                      */
+  const float* conv_13_bc1_w;  /* (GN/2, 1, 1, 3)                                      */
+  const float* conv_31_bc1_w;  /* (GN/2, 1, 3, 1)                                      */
+  const float* conv_13_bc2_w;  /* (GN/2, 1, 1, 3)                                      */
+  const float* conv_31_bc2_w;  /* (GN/2, 1, 3, 1)                                      */
+  const float* conv2d_w;       /* ((Di + 2GN)/2, 1, 3, 3)                              */
+  const float* norm_w;         /* (Di)                                                 */
+  const float* norm_b;         /* (Di)                                                 */
+  const float* conv2d_z_w;     /* (Di, 1, 3, 3)                                        */
+  const float* out_proj_w;     /* (D, 2Di)                                             */
+} AdnWeights;
+
+/* Same field order and shapes; every non-NULL pointer receives that parameter's gradient (overwritten).
+ * scale / shift / alpha2 are ignored (the reference leaves their .grad None). */
+typedef struct AdnWeightGrads {
+  float* dt_bias; float* A_log; float* D; float* scale; float* shift; float* alpha1; float* alpha2;
+  float* in_proj_w;
+  float* conv_13_x1_w; float* conv_31_x1_w; float* conv_13_x2_w; float* conv_31_x2_w;
+  float* conv_13_bc1_w; float* conv_31_bc1_w; float* conv_13_bc2_w; float* conv_31_bc2_w;
+  float* conv2d_w; float* norm_w; float* norm_b; float* conv2d_z_w; float* out_proj_w;
+} AdnWeightGrads;
+
+/* Sizes (bytes) of the caller-allocated `saved` (forward -> backward) and `workspace` (scratch, may be
+ * shared between calls on one stream; must hold max(fwd, bwd)) buffers.  256-byte alignment required. */
+int adnssd_workspace_bytes(const AdnShape* s, size_t* saved_bytes, size_t* fwd_workspace_bytes,
+                           size_t* bwd_workspace_bytes);
+
+/* out(B,L,D) = Mamba2.forward(u(B,L,D), H, W).  `saved` may be NULL for inference (no backward). */
+int adnssd_forward(const AdnShape* s, const AdnWeights* w, const void* u, void* out, void* saved,
+                   void* workspace, void* stream);
+
+/* du(B,L,D) and all parameter gradients from dout(B,L,D); `saved` is what adnssd_forward wrote. */
+int adnssd_backward(const AdnShape* s, const AdnWeights* w, const void* u, const void* saved,
+                    const void* dout, void* du, const AdnWeightGrads* g, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------ WTConv2d --------------- */
+
+#define ADN_WT_MAX_LEVELS 8
+
+typedef struct WtShape {
+  int32_t B, C, H, W;   /* NCHW input == output shape (stride 1, in_channels == out_channels, WTConv2d.py:67) */
+  int32_t k;            /* odd depthwise kernel size (5 or 3 in ADNM-UNet)                                   */
+  int32_t levels;       /* wt_levels, 1..ADN_WT_MAX_LEVELS                                                    */
+  int32_t has_bias;     /* base_conv.bias present                                                             */
+  int32_t dtype;        /* ADN_F32 | ADN_BF16 (activations); parameters float32                               */
+} WtShape;
+
+/* state_dict of one WTConv2d minus the frozen Haar filters wt_filter / iwt_filter (fixed db1 butterflies,
+ * models/WTConv2d.py:9-29; the host module keeps them as non-trainable Parameters for checkpoint parity). */
+typedef struct WtWeights {
+  const float* base_conv_w;                       /* (C,1,k,k)  */
+  const float* base_conv_b;                       /* (C) | NULL */
+  const float* base_scale_w;                      /* (1,C,1,1)  */
+  const float* wavelet_conv_w[ADN_WT_MAX_LEVELS]; /* (4C,1,k,k) */
+  const float* wavelet_scale_w[ADN_WT_MAX_LEVELS];/* (1,4C,1,1) */
+} WtWeights;
+
+typedef struct WtWeightGrads {
+  float* base_conv_w; float* base_conv_b; float* base_scale_w;
+  float* wavelet_conv_w[ADN_WT_MAX_LEVELS]; float* wavelet_scale_w[ADN_WT_MAX_LEVELS];
+} WtWeightGrads;
+
+int wtconv_workspace_bytes(const WtShape* s, size_t* saved_bytes, size_t* fwd_workspace_bytes,
+                           size_t* bwd_workspace_bytes);
+int wtconv_forward(const WtShape* s, const WtWeights* w, const void* x, void* y, void* saved,
+                   void* workspace, void* stream);
+int wtconv_backward(const WtShape* s, const WtWeights* w, const void* x, const void* saved, const void* dy,
+                    void* dx, const WtWeightGrads* g, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------ threshold counts ------- */
+
+/* table[t*4 + {0,1,2,3}] = TP, FN, FP, TN over n float32 elements with
+ * q(v) = (uint16)(clamp(v,0,1) * value_scale), event = q >= thresholds[t]   (Shanghai_metrics.py:45-47,105-114).
+ * `thresholds` is a HOST pointer (n_thresholds <= 8); `table` is a DEVICE int64 buffer, overwritten. */
+int adn_threshold_counts(const float* obs, const float* sim, int64_t n, const int32_t* thresholds,
+                         int32_t n_thresholds, float value_scale, int64_t* table, void* stream);
+
+/* ------------------------------------------------------------------ misc ------------------- */
+
+const char* adn_last_error(void);
+int adn_abi_version(void);
+/* 1 if the current device is compute capability 10.x (the only target this library is built for). */
+int adn_device_supported(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADNB200_H_ */

@@ -15,8 +15,8 @@ import torch.nn.functional as F
 
 def param_names(levels, bias=True):
     names = ["wt_filter", "iwt_filter", "base_conv.weight"] + (["base_conv.bias"] if bias else []) + ["base_scale.weight"]
-    for i in range(levels):
-        names += [f"wavelet_convs.{i}.weight", f"wavelet_scale.{i}.weight"]
+    names += [f"wavelet_convs.{i}.weight" for i in range(levels)]        # models/WTConv2d.py:85-91 (ModuleList order)
+    names += [f"wavelet_scale.{i}.weight" for i in range(levels)]
     return names
 
 

@@ -1,0 +1,122 @@
+"""GPU parity of the ADN-SSD mixer (CUDA library through the C ABI) against the golden vectors produced by the
+reference and against the CPU oracle.  Tolerances (BASELINE.json north_star), measured per tensor as
+max|a-b| / max|b|:  1e-4 in fp32 check mode, 2e-2 in bf16."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import adnssd_oracle as AO
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), torch.as_tensor(b).double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def load_case(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    params = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")}
+    grads = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad/")}
+    return z, params, grads
+
+
+def run_cuda(params, u, dout, g_h, g_w, P, N, dtype):
+    import adnm_unet_b200 as A
+    dev = torch.device("cuda:0")
+    p = {k: v.to(dev).float().requires_grad_(k not in AO.UNUSED_PARAMS) for k, v in params.items()}
+    ud = u.to(dev, dtype).requires_grad_(True)
+    out = A.adnssd_mixer(ud, g_h, g_w, p, headdim=P, d_state=N)
+    out.backward(dout.to(dev, dtype))
+    torch.cuda.synchronize()
+    return out, ud.grad, {k: v.grad for k, v in p.items() if v.grad is not None}
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("name", sorted(cases.MIXER_CASES))
+def test_mixer_matches_reference_golden(golden_dir, name, dtype):
+    D, P, N, B, g = cases.MIXER_CASES[name]
+    z, params, grads = load_case(golden_dir, name)
+    u, dout = cases.mixer_inputs(name, torch.float32)
+    out, du, pg = run_cuda(params, u, dout, g, g, P, N, dtype)
+    s = cases.SUBSAMPLE_STRIDE if g >= 64 else 1
+    tol = TOL[dtype]
+    errs = {"out": rel(out[:, ::s], z["out"]), "du": rel(du[:, ::s], z["du"])}
+    assert set(pg) == set(grads)
+    for k, ref in grads.items():
+        errs[k] = rel(pg[k].reshape(ref.shape), ref)
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, f"{name} {dtype}: {bad} (all: {errs})"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("cfg", [(16, 4, 8, 3, 5, 9), (32, 4, 16, 1, 33, 17), (48, 8, 16, 2, 7, 7), (256, 4, 16, 2, 4, 4)],
+                         ids=lambda c: "D%d_P%d_N%d_B%d_%dx%d" % c)
+def test_mixer_matches_oracle_ragged_shapes(cfg, dtype):
+    """Non-square and odd token grids, tiny and large d_model: compared with the CPU oracle in fp64."""
+    D, P, N, B, H, W = cfg
+    params = AO.init_params(D, P, N, seed=7, perturb=0.3, dtype=torch.float32)
+    u = cases.rng_normal(11, (B, H * W, D), torch.float32)
+    dout = cases.rng_normal(12, (B, H * W, D), torch.float32)
+    p64 = {k: v.double() for k, v in params.items()}
+    ref_out = AO.mixer_forward(p64, u.double(), H, W, P, N)
+    ref_du, ref_g = AO.mixer_backward(p64, u.double(), H, W, P, N, dout.double())
+    out, du, pg = run_cuda(params, u, dout, H, W, P, N, dtype)
+    tol = TOL[dtype]
+    errs = {"out": rel(out, ref_out), "du": rel(du, ref_du)}
+    for k, ref in ref_g.items():
+        errs[k] = rel(pg[k].reshape(ref.shape), ref)
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, f"{cfg} {dtype}: {bad}"
+
+
+def test_module_is_a_drop_in(golden_dir):
+    """Strict state_dict load of reference-shaped weights, forward(u, H, W), grads land on the same 18 parameters."""
+    import adnm_unet_b200 as A
+    name = "mixer_d32_p4_n16_g16"
+    D, P, N, B, g = cases.MIXER_CASES[name]
+    z, params, grads = load_case(golden_dir, name)
+    m = A.Mamba2(d_model=D, headdim=P, d_state=N, layer_idx=3, linear_attn_duality=True)
+    missing = m.load_state_dict(params, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert list(m.state_dict()) == list(AO.PARAM_NAMES)
+    m = m.cuda()
+    u, dout = cases.mixer_inputs(name, torch.float32)
+    ud = u.cuda().requires_grad_(True)
+    out = m(ud, g, g)
+    assert out.shape == ud.shape and out.is_contiguous()
+    out.backward(dout.cuda())
+    assert rel(out, z["out"]) < 1e-4 and rel(ud.grad, z["du"]) < 1e-4
+    for k, p in m.named_parameters():
+        if k in AO.UNUSED_PARAMS:
+            assert p.grad is None, k
+        else:
+            assert rel(p.grad, grads[k]) < 1e-4, k
+    # inference path (no saved buffers) gives the same output
+    with torch.no_grad():
+        out2 = m(u.cuda(), g, g)
+    assert torch.equal(out2, out.detach())
+    # autocast -> bf16 compute
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out3 = m(u.cuda(), g, g)
+    assert out3.dtype == torch.bfloat16 and rel(out3, z["out"]) < 2e-2
+
+
+def test_errors_are_loud():
+    import adnm_unet_b200 as A
+    params = AO.init_params(32, 4, 16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        A.adnssd_mixer(torch.zeros(1, 16, 32), 4, 4, params, headdim=4, d_state=16)
+    pc = {k: v.cuda() for k, v in params.items()}
+    with pytest.raises(RuntimeError, match="H\\*W"):
+        A.adnssd_mixer(torch.zeros(1, 16, 32, device="cuda"), 4, 5, pc, headdim=4, d_state=16)
+    with pytest.raises(RuntimeError, match="ngroups"):
+        A.adnssd_mixer(torch.zeros(1, 16, 32, device="cuda"), 4, 4, pc, headdim=4, d_state=16, ngroups=4)
+    with pytest.raises(RuntimeError, match="dtype"):
+        A.adnssd_mixer(torch.zeros(1, 16, 32, device="cuda", dtype=torch.float16), 4, 4, pc, headdim=4, d_state=16)
