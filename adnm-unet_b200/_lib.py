@@ -57,6 +57,10 @@ EXPORTS = {
     "adn_last_error": (C.c_char_p, []),
     "adn_abi_version": (C.c_int, []),
     "adn_device_supported": (C.c_int, []),
+    "adn_launch_count": (C.c_ulonglong, []),
+    "adn_prof_enable": (C.c_int, [C.c_int]),
+    "adn_prof_count": (C.c_int, []),
+    "adn_prof_get": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
 }
 
 
@@ -110,3 +114,26 @@ def stream_ptr():
 
 def scratch(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def launch_count() -> int:
+    return int(load().adn_launch_count())
+
+
+class profile:
+    """with _lib.profile() as p: ...; p.records -> [(kernel name, ms)], after synchronising the device."""
+
+    def __enter__(self):
+        load().adn_prof_enable(1)
+        self.records = []
+        return self
+
+    def __exit__(self, *exc):
+        lib = load()
+        torch.cuda.synchronize()
+        name, ms = C.c_char_p(), C.c_float()
+        for i in range(lib.adn_prof_count()):
+            check(lib.adn_prof_get(i, C.byref(name), C.byref(ms)), "adn_prof_get")
+            self.records.append((name.value.decode(), ms.value))
+        lib.adn_prof_enable(0)
+        return False

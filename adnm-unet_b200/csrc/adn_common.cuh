@@ -32,6 +32,18 @@ void set_error(const char* fmt, ...);
     }                                 \
   } while (0)
 
+// Diagnostics (include/adnb200.h: adn_prof_*): every kernel launch of the library goes through one ProfScope, which
+// counts the launch and, when profiling is enabled, brackets it with CUDA events on the launching stream.
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  ProfScope(const char* name, cudaStream_t stream);
+  ~ProfScope();
+};
+#define ADN_CAT2(a, b) a##b
+#define ADN_CAT(a, b) ADN_CAT2(a, b)
+#define ADN_KERNEL(name, st) adn::ProfScope ADN_CAT(_adn_prof_, __LINE__)(name, st)
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

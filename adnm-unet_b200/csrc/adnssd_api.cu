@@ -18,6 +18,31 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- diagnostics: launch counter + optional per-launch CUDA-event timing
+constexpr int PROF_CAP = 4096;
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static ProfRec g_prof[PROF_CAP];
+static int g_prof_n = 0, g_prof_events = 0;
+static bool g_prof_on = false;
+static unsigned long long g_launches = 0;
+
+ProfScope::ProfScope(const char* name, cudaStream_t stream) : slot(-1), st(stream) {
+  __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED);
+  if (g_prof_on && g_prof_n < PROF_CAP) {
+    slot = g_prof_n++;
+    if (slot >= g_prof_events) {
+      cudaEventCreate(&g_prof[slot].e0);
+      cudaEventCreate(&g_prof[slot].e1);
+      g_prof_events = slot + 1;
+    }
+    g_prof[slot].name = name;
+    cudaEventRecord(g_prof[slot].e0, st);
+  }
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].e1, st);
+}
+
 static int validate(const AdnShape* s) {
   ADN_REQUIRE(s != nullptr, ADN_ERR_NULL, "AdnShape is NULL");
   ADN_REQUIRE(s->B > 0 && s->H > 0 && s->W > 0 && s->D > 0, ADN_ERR_SHAPE, "B/H/W/D must be positive (got %d,%d,%d,%d)",
@@ -52,6 +77,21 @@ extern "C" {
 
 const char* adn_last_error(void) { return adn::g_err; }
 int adn_abi_version(void) { return ADNB200_ABI_VERSION; }
+
+unsigned long long adn_launch_count(void) { return adn::g_launches; }
+int adn_prof_enable(int on) {
+  adn::g_prof_on = on != 0;
+  adn::g_prof_n = 0;
+  return ADN_OK;
+}
+int adn_prof_count(void) { return adn::g_prof_n; }
+int adn_prof_get(int i, const char** name, float* ms) {
+  ADN_REQUIRE(i >= 0 && i < adn::g_prof_n && name && ms, ADN_ERR_SHAPE, "adn_prof_get: bad index %d", i);
+  ADN_CHECK_CUDA(cudaEventSynchronize(adn::g_prof[i].e1));
+  ADN_CHECK_CUDA(cudaEventElapsedTime(ms, adn::g_prof[i].e0, adn::g_prof[i].e1));
+  *name = adn::g_prof[i].name;
+  return ADN_OK;
+}
 
 int adn_device_supported(void) {
   int dev = 0, major = 0;

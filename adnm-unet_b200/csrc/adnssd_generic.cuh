@@ -129,8 +129,8 @@ static inline void launch_gemm(cudaStream_t st, const TA* A, long long lda, long
                                long long ldw, long long w_bs, TC* C, long long ldc, long long c_bs, int M, int N,
                                int K, int batches, const float* alpha_ptr, int accumulate) {
   dim3 grid(cdiv(M, 64), cdiv(N, 64), batches);  // M (tokens) on grid.x: no 65535 limit
-  k_gemm<TA, TC, W_NK><<<grid, 256, 0, st>>>(A, lda, a_bs, Wt, ldw, w_bs, C, ldc, c_bs, M, N, K, alpha_ptr,
-                                              accumulate);
+  { ADN_KERNEL("k_gemm", st); k_gemm<TA, TC, W_NK><<<grid, 256, 0, st>>>(A, lda, a_bs, Wt, ldw, w_bs, C, ldc, c_bs, M, N, K, alpha_ptr,
+                                              accumulate); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -201,7 +201,7 @@ static inline void launch_reduce_gemm(cudaStream_t st, const TX* X, long long ld
   int chunk = cdiv(cdiv(L, splits), 16) * 16;
   splits = cdiv(L, chunk);
   dim3 grid(cdiv(N2, 64), cdiv(N1, 64), B * splits);
-  k_reduce_gemm<TX, TY><<<grid, 256, 0, st>>>(X, ldx, Y, ldy, Out, ldo, o_bs, N1, N2, L, chunk, splits, parity_mask);
+  { ADN_KERNEL("k_reduce_gemm", st); k_reduce_gemm<TX, TY><<<grid, 256, 0, st>>>(X, ldx, Y, ldy, Out, ldo, o_bs, N1, N2, L, chunk, splits, parity_mask); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -683,17 +683,17 @@ int generic_forward(const MixerDims& d, const AdnWeights& w, const T* u, T* out,
   SavedBufs<T> S = saved ? SavedBufs<T>(d, saved) : W.tmp;
   const bool training = saved != nullptr;
   const long long Tt = d.T;
-  k_assemble_conv<<<cdiv(d.CC, 128), 128, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC);
+  { ADN_KERNEL("k_assemble_conv", st); k_assemble_conv<<<cdiv(d.CC, 128), 128, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC); }
   // (1) in_proj  (models/ADNssd.py:309)
   launch_gemm<T, T, true>(st, u, d.D, 0, w.in_proj_w, d.D, 0, S.raw, d.ldr, 0, (int)Tt, d.dip, d.D, 1, nullptr, 0);
   // (2) depthwise 3x3 + SiLU over [z | x | B | C]
   {
     dim3 grid(cdiv(d.CC / 4, 8), cdiv(d.W, 32), d.B * cdiv(d.H, CONV_ROWS)), block(8, 32);
-    k_conv_fwd<T><<<grid, block, 0, st>>>(S.raw, d.ldr, W.Kc, training ? S.pre : nullptr, S.act, d.H, d.W, d.CC);
+    { ADN_KERNEL("k_conv_fwd", st); k_conv_fwd<T><<<grid, block, 0, st>>>(S.raw, d.ldr, W.Kc, training ? S.pre : nullptr, S.act, d.H, d.W, d.CC); }
   }
   // (3) decay weights and w*x
-  k_decay_wx<T><<<cdiv(Tt * d.nh, 256), 256, 0, st>>>(S.raw, d.ldr, S.act, w.dt_bias, w.A_log, S.wdec, W.bufA, Tt,
-                                                      d.nh, d.P, d.Di, d.CC);
+  { ADN_KERNEL("k_decay_wx", st); k_decay_wx<T><<<cdiv(Tt * d.nh, 256), 256, 0, st>>>(S.raw, d.ldr, S.act, w.dt_bias, w.A_log, S.wdec, W.bufA, Tt,
+                                                      d.nh, d.P, d.Di, d.CC); }
   // (4a) state S'[b] = mask . Bc^T (w x)
   ADN_CHECK_CUDA(cudaMemsetAsync(S.S, 0, (size_t)d.B * d.GN * d.Di * sizeof(float), st));
   launch_reduce_gemm<T, T>(st, S.act + 2 * d.Di, d.CC, W.bufA, d.Di, S.S, d.Di, (long long)d.GN * d.Di, d.GN, d.Di,
@@ -703,7 +703,7 @@ int generic_forward(const MixerDims& d, const AdnWeights& w, const T* u, T* out,
                            (long long)d.GN * d.Di, W.bufA, d.Di, (long long)d.L * d.Di, d.L, d.Di, d.GN, d.B, nullptr,
                            0);
   // (5) D-skip + LayerNorm, then out = alpha1 * (yn Wy^T + zc Wz^T)
-  k_ln_fwd<T><<<cdiv(Tt, 8), 256, 0, st>>>(W.bufA, S.act, w.D, w.norm_w, w.norm_b, W.bufB, Tt, d.Di, d.P, d.CC);
+  { ADN_KERNEL("k_ln_fwd", st); k_ln_fwd<T><<<cdiv(Tt, 8), 256, 0, st>>>(W.bufA, S.act, w.D, w.norm_w, w.norm_b, W.bufB, Tt, d.Di, d.P, d.CC); }
   launch_gemm<T, T, true>(st, W.bufB, d.Di, 0, w.out_proj_w, 2 * d.Di, 0, out, d.D, 0, (int)Tt, d.D, d.Di, 1,
                           w.alpha1, 0);
   launch_gemm<T, T, true>(st, S.act, d.CC, 0, w.out_proj_w + d.Di, 2 * d.Di, 0, out, d.D, 0, (int)Tt, d.D, d.Di, 1,
@@ -720,7 +720,7 @@ int generic_backward(const MixerDims& d, const AdnWeights& w, const T* u, const 
   const long long Tt = d.T;
   const long long sS = (long long)d.GN * d.Di;
   ADN_CHECK_CUDA(cudaMemsetAsync(W.zero_begin, 0, W.zero_bytes, st));
-  k_assemble_conv<<<cdiv(d.CC, 128), 128, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC);
+  { ADN_KERNEL("k_assemble_conv", st); k_assemble_conv<<<cdiv(d.CC, 128), 128, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC); }
   // ---- phase B1
   launch_gemm<T, T, false>(st, dout, d.D, 0, w.out_proj_w, 2 * d.Di, 0, W.g, 2 * d.Di, 0, (int)Tt, 2 * d.Di, d.D, 1,
                            nullptr, 0);
@@ -728,9 +728,9 @@ int generic_backward(const MixerDims& d, const AdnWeights& w, const T* u, const 
                            (long long)d.L * d.Di, d.L, d.Di, d.GN, d.B, nullptr, 0);
   {
     int tpw = 4;
-    k_ln_bwd<T><<<cdiv(Tt, 8 * tpw), 256, 2 * d.Di * sizeof(float), st>>>(
+    { ADN_KERNEL("k_ln_bwd", st); k_ln_bwd<T><<<cdiv(Tt, 8 * tpw), 256, 2 * d.Di * sizeof(float), st>>>(
         W.ybuf, S.act, W.g, w.D, w.norm_w, w.norm_b, w.alpha1, W.ynbuf, W.dact, W.acc.dgamma, W.acc.dbeta,
-        W.acc.dalpha1, Tt, tpw, d.Di, d.P, d.CC);
+        W.acc.dalpha1, Tt, tpw, d.Di, d.P, d.CC); }
   }
   launch_reduce_gemm<T, T>(st, dout, d.D, W.ynbuf, d.Di, W.acc.dWout, 2 * d.Di, 0, d.D, d.Di, (int)Tt, 1, 0);
   launch_reduce_gemm<T, T>(st, dout, d.D, S.act, d.CC, W.acc.dWout + d.Di, 2 * d.Di, 0, d.D, d.Di, (int)Tt, 1, 0);
@@ -744,20 +744,20 @@ int generic_backward(const MixerDims& d, const AdnWeights& w, const T* u, const 
   {
     int tpt = 8;
     dim3 grid(cdiv(d.nh, 32), cdiv(Tt, 8 * tpt)), block(32, 8);
-    k_bwd_heads<T><<<grid, block, 0, st>>>(S.raw, d.ldr, S.act, S.wdec, w.dt_bias, w.A_log, w.D, W.dact, W.ybuf,
-                                           W.draw, W.acc.dD, W.acc.dAlog, W.acc.ddtb, Tt, tpt, d.nh, d.P, d.Di, d.CC);
+    { ADN_KERNEL("k_bwd_heads", st); k_bwd_heads<T><<<grid, block, 0, st>>>(S.raw, d.ldr, S.act, S.wdec, w.dt_bias, w.A_log, w.D, W.dact, W.ybuf,
+                                           W.draw, W.acc.dD, W.acc.dAlog, W.acc.ddtb, Tt, tpt, d.nh, d.P, d.Di, d.CC); }
   }
   launch_gemm<T, T, true>(st, W.ybuf, d.Di, (long long)d.L * d.Di, W.dS, d.Di, sS, W.dact + 2 * d.Di, d.CC,
                           (long long)d.L * d.CC, d.L, d.GN, d.Di, d.B, nullptr, 0);
   // ---- conv backward
   {
     dim3 grid(cdiv(d.CC / 4, 8), cdiv(d.W, 32), d.B * cdiv(d.H, CONV_ROWS)), block(8, 32);
-    k_conv_bwd<T><<<grid, block, 0, st>>>(W.dact, S.pre, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.H, d.W, d.CC);
+    { ADN_KERNEL("k_conv_bwd", st); k_conv_bwd<T><<<grid, block, 0, st>>>(W.dact, S.pre, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.H, d.W, d.CC); }
   }
   // ---- in_proj backward
   launch_gemm<T, T, false>(st, W.draw, d.ldr, 0, w.in_proj_w, d.D, 0, du, d.D, 0, (int)Tt, d.D, d.dip, 1, nullptr, 0);
   launch_reduce_gemm<T, T>(st, W.draw, d.ldr, u, d.D, W.acc.dWin, d.D, 0, d.dip, d.D, (int)Tt, 1, 0);
-  k_finalize<<<148, 256, 0, st>>>(W.acc, w, g, d.D, d.Di, d.GN, d.nh, d.dip);
+  { ADN_KERNEL("k_finalize", st); k_finalize<<<148, 256, 0, st>>>(W.acc, w, g, d.D, d.Di, d.GN, d.nh, d.dip); }
   ADN_CHECK_LAUNCH();
   return ADN_OK;
 }

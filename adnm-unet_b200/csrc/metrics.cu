@@ -83,7 +83,7 @@ k_threshold_counts(const float* __restrict__ obs, const float* __restrict__ sim,
 extern "C" int adn_threshold_counts(const float* obs, const float* sim, int64_t n, const int32_t* thresholds,
                                     int32_t n_thresholds, float value_scale, int64_t* table, void* stream) {
   using namespace adn;
-  ADN_REQUIRE(obs && sim && table && thresholds, ADN_ERR_NULL, "adn_threshold_counts: NULL argument");
+  ADN_REQUIRE(table && thresholds && ((obs && sim) || n == 0), ADN_ERR_NULL, "adn_threshold_counts: NULL argument");
   ADN_REQUIRE(n >= 0 && n_thresholds > 0 && n_thresholds <= MAX_THR, ADN_ERR_SHAPE,
               "adn_threshold_counts: n >= 0 and 1..%d thresholds required", MAX_THR);
   ADN_REQUIRE(((uintptr_t)obs % 16 == 0) && ((uintptr_t)sim % 16 == 0), ADN_ERR_SHAPE,
@@ -97,7 +97,7 @@ extern "C" int adn_threshold_counts(const float* obs, const float* sim, int64_t 
   // each thread may count at most 2^32 events: 148*8 blocks x 256 threads x 4 => fine up to 2^50 elements
   long long blocks = (n / 4 + 255) / 256;
   int grid = (int)(blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks));
-  k_threshold_counts<<<grid, 256, 0, st>>>(obs, sim, n, thr, value_scale, (unsigned long long*)table);
+  { ADN_KERNEL("k_threshold_counts", st); k_threshold_counts<<<grid, 256, 0, st>>>(obs, sim, n, thr, value_scale, (unsigned long long*)table); }
   ADN_CHECK_LAUNCH();
   return ADN_OK;
 }

@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py - ADN-SSD mixer fwd+bwd tokens/s (BASELINE.json configs[1]) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--d-model 32]
+
+One "step" = one forward + backward of one ADN-SSD mixer (models/ADNssd.py::Mamba2 of the reference) over a
+synthetic batch B=16 of 128x128 token grids (262 144 tokens per GPU), bf16 I/O, random-init weights.
+  value  : tokens/s with u / dout already resident in HBM (CUDA events, max over ranks)
+  e2e    : the same through the public module call (adnm_unet_b200.Mamba2) with HOST buffers: pinned-host u and
+           dout copied H2D and out / du copied D2H inside the timed region, every step
+  roofline : dominant kernel of the step, timed per launch with CUDA events inside the library
+           (adn_prof_*), algorithmic bytes / time vs MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle port (oracle/adnssd_oracle.py, PyTorch fp32, all host threads) on a bounded sample
+N > 1 (torchrun): batch-sharded data parallel, one process per GPU, weak scaling; the mixer's parameter
+gradients are all-reduced over NCCL every step (the only exchange the path has).
+`--impl reference` times the reference's CPU algorithm (the oracle port; the reference is pure Python and
+/root/reference does not exist on the GPU box) on the host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "adnssd_fwd_bwd_tokens_per_s"
+UNIT = "tokens/s"
+B_PER_GPU, GRID = 16, 128
+HEADDIM, D_STATE = 4, 16
+N_INPUT_SETS = 8   # rotating (u, dout) sets: 8 x 33.5 MB (bf16) > L2, on top of ~1 GB of intermediates rewritten each step
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # under load = upper half of the samples (the sampler also sees the idle edges of the region)
+        med = sm[(len(sm) * 3) // 4] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_step_fn(d_model, batch, threads):
+    """The CPU algorithm of the reference (oracle port), fwd + autograd bwd, fp32."""
+    import torch
+    from oracle import adnssd_oracle as AO
+    torch.set_num_threads(threads)
+    p = {k: v.clone().requires_grad_(k not in AO.UNUSED_PARAMS) for k, v in AO.init_params(d_model, HEADDIM, D_STATE, seed=0).items()}
+    g = torch.Generator().manual_seed(1234)
+    u = torch.randn(batch, GRID * GRID, d_model, generator=g).requires_grad_(True)
+    dout = torch.randn(batch, GRID * GRID, d_model, generator=g)
+
+    def step():
+        for v in p.values():
+            v.grad = None
+        u.grad = None
+        AO.mixer_forward(p, u, GRID, GRID, HEADDIM, D_STATE).backward(dout)
+    return step
+
+
+def time_cpu(d_model, batch, steps, warmup):
+    threads = os.cpu_count() or 1
+    step = oracle_step_fn(d_model, batch, threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return batch * GRID * GRID / dt, dt, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 1
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    val, dt, threads = time_cpu(args.d_model, batch, steps, warmup)
+    sample = f"oracle port (PyTorch fp32 CPU), B={batch} x {GRID}x{GRID} tokens per step, {steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"ADN-SSD mixer fwd+bwd, D={args.d_model}, headdim={HEADDIM}, d_state={D_STATE}, "
+                               f"{GRID}x{GRID} tokens (CPU sample B={batch}; GPU arm B={B_PER_GPU}/GPU)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import adnm_unet_b200 as A
+    from adnm_unet_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    assert lib.adn_device_supported() == 1
+
+    D = args.d_model
+    torch.manual_seed(0)                                  # identical weights on every rank
+    mixer = A.Mamba2(d_model=D, headdim=HEADDIM, d_state=D_STATE).to(dev)
+    params = [p for n, p in mixer.named_parameters() if n not in ("scale", "shift", "alpha2")]
+    B, L = B_PER_GPU, GRID * GRID
+    tokens = B * L
+    g = torch.Generator().manual_seed(1234 + rank)        # per-rank data shard
+    host_u = [torch.randn(B, L, D, generator=g).bfloat16().pin_memory() for _ in range(N_INPUT_SETS)]
+    host_g = [torch.randn(B, L, D, generator=g).bfloat16().pin_memory() for _ in range(N_INPUT_SETS)]
+    dev_u = [t.to(dev) for t in host_u]
+    dev_g = [t.to(dev) for t in host_g]
+    host_out = torch.empty(B, L, D, dtype=torch.bfloat16).pin_memory()
+    host_du = torch.empty(B, L, D, dtype=torch.bfloat16).pin_memory()
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+
+    def allreduce_grads():
+        if world > 1:
+            torch.cat([p.grad.reshape(-1) for p in params], out=flat)
+            dist.all_reduce(flat)
+            flat.mul_(1.0 / world)
+
+    def step_resident(i):
+        u = dev_u[i % N_INPUT_SETS].requires_grad_(True)
+        u.grad = None
+        for p in params:
+            p.grad = None
+        out = mixer(u, GRID, GRID)
+        out.backward(dev_g[i % N_INPUT_SETS])
+        allreduce_grads()
+        return out, u.grad
+
+    def step_e2e(i):
+        u = host_u[i % N_INPUT_SETS].to(dev, non_blocking=True).requires_grad_(True)
+        go = host_g[i % N_INPUT_SETS].to(dev, non_blocking=True)
+        for p in params:
+            p.grad = None
+        out = mixer(u, GRID, GRID)
+        out.backward(go)
+        allreduce_grads()
+        host_out.copy_(out.detach(), non_blocking=True)
+        host_du.copy_(u.grad, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+        step_e2e(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-kernel device times (CUDA events recorded by the library on the launching stream), a few extra steps
+    barrier()
+    with _lib.profile() as prof:
+        for i in range(min(args.steps, 5)):
+            step_resident(i)
+    per = {}
+    for name, t in prof.records:
+        a = per.setdefault(name, [0.0, 0])
+        a[0] += t; a[1] += 1
+    nprof = min(args.steps, 5)
+    tot = sum(v[0] for v in per.values())
+    top = max(per, key=lambda k: per[k][0])
+    hbm_peak, tf_peak, peak_src = load_peaks()
+    # algorithmic bytes of the whole mixer fwd+bwd: 10*D bytes per token: u, out, dout, u, du in bf16
+    alg_bytes_step = 10 * D * tokens
+    step_ms = ms / args.steps
+    kernels = {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] / nprof, "share": v[0] / tot} for k, v in per.items()}
+
+    if rank == 0:
+        top_ms = per[top][0] / per[top][1]
+        # dominant kernel: achieved = bytes it must move per launch / its mean launch time
+        top_bytes = KERNEL_ALG_BYTES.get(top, lambda D, T: None)(D, tokens)
+        roof = {"bound": "hbm", "kernel": top, "achieved": (top_bytes / (top_ms * 1e-3) / 1e9) if top_bytes else None,
+                "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "kernel_ms_per_launch": top_ms, "kernel_share_of_step": per[top][0] / tot,
+                "step_achieved": alg_bytes_step / (step_ms * 1e-3) / 1e9, "step_algorithmic_bytes": alg_bytes_step}
+        roof["frac"] = (roof["achieved"] / hbm_peak) if roof["achieved"] else None
+        roof["step_frac"] = roof["step_achieved"] / hbm_peak
+        cpu_val, cpu_dt, cpu_threads = time_cpu(D, 1, 3, 1) if world == 1 and not args.no_cpu else (None, None, None)
+        line = {
+            "metric": METRIC, "value": world * tokens * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"ADN-SSD mixer fwd+bwd (BASELINE configs[1]): D={D}, headdim={HEADDIM}, d_state={D_STATE}, "
+                                   f"B={B}/GPU, {GRID}x{GRID} tokens", "global_batch": B * world, "tokens_per_step": tokens * world,
+                       "parallelism": f"dp{world}", "l2": f"{N_INPUT_SETS} rotating input sets (> L2) + ~1 GB of intermediates rewritten per step"},
+            "e2e": {"value": world * tokens * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": 2 * tokens * D * 2, "d2h_bytes_per_step": 2 * tokens * D * 2,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
+        }
+        if cpu_val is not None:
+            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                                    "sample": f"oracle port, B=1 x {GRID}x{GRID} tokens, 3 steps after 1 warm-up, {cpu_dt:.2f} s/step"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# algorithmic HBM bytes per launch of each kernel (bf16 elements = 2 bytes), D = d_model, T = tokens; see DESIGN.md
+def _dims(D):
+    Di = 2 * D
+    GN = 2 * D_STATE
+    nh = Di // HEADDIM
+    CC = 2 * Di + 2 * GN
+    return Di, GN, nh, CC, CC + nh
+
+
+KERNEL_ALG_BYTES = {
+    "k_conv_fwd": lambda D, T: T * 2 * (3 * _dims(D)[3]),                      # read raw[:, :CC], write pre + act
+    "k_conv_bwd": lambda D, T: T * 2 * (4 * _dims(D)[3]),                      # read dact, pre, raw ; write draw
+    "k_gemm": lambda D, T: None,
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--d-model", type=int, default=32)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -151,6 +151,18 @@ int adn_abi_version(void);
 /* 1 if the current device is compute capability 10.x (the only target this library is built for). */
 int adn_device_supported(void);
 
+
+/* ------------------------------------------------------------------ diagnostics ------------ */
+
+/* Number of CUDA kernels this library has launched in this process (all entry points, all threads). */
+unsigned long long adn_launch_count(void);
+/* Per-launch device timing: while enabled, every launch is bracketed by CUDA events on its stream (not
+ * thread-safe; for bench.py / profiling only).  adn_prof_enable(1) clears the log; after a stream sync,
+ * adn_prof_get(i, &name, &ms) returns the i-th launch's kernel name (static string) and duration. */
+int adn_prof_enable(int on);
+int adn_prof_count(void);
+int adn_prof_get(int i, const char** name, float* ms);
+
 #ifdef __cplusplus
 }
 #endif
