@@ -271,8 +271,8 @@ k_conv_fwd(const T* __restrict__ raw, long long ldr, const float* __restrict__ K
 }
 
 // conv backward: draw[:, :CC] = convT( dact * silu'(pre) ), dK[c][a][b] += raw[y,x,c] * dpre[y-a+1, x-b+1, c]
-template <typename T>
-__device__ __forceinline__ void load_dpre_row3(const T* __restrict__ dact, const T* __restrict__ pre, long long ld,
+template <typename TW, typename T>
+__device__ __forceinline__ void load_dpre_row3(const TW* __restrict__ dact, const T* __restrict__ pre, long long ld,
                                                int W, int y, int H, int x, float (&r)[3][4]) {
 #pragma unroll
   for (int s = 0; s < 3; ++s) {
@@ -291,10 +291,10 @@ __device__ __forceinline__ void load_dpre_row3(const T* __restrict__ dact, const
   }
 }
 
-template <typename T>
+template <typename T, typename TW>
 __global__ void __launch_bounds__(256)
-k_conv_bwd(const T* __restrict__ dact, const T* __restrict__ pre, const T* __restrict__ raw, long long ldr,
-           const float* __restrict__ Kc, T* __restrict__ draw, float* __restrict__ dK, int H, int W, int CC) {
+k_conv_bwd(const TW* __restrict__ dact, const T* __restrict__ pre, const T* __restrict__ raw, long long ldr,
+           const float* __restrict__ Kc, TW* __restrict__ draw, float* __restrict__ dK, int H, int W, int CC) {
   __shared__ float red[8][36];
   const int CV = CC >> 2;
   const int cv = blockIdx.x * 8 + threadIdx.x;
@@ -314,7 +314,7 @@ k_conv_bwd(const T* __restrict__ dact, const T* __restrict__ pre, const T* __res
 #pragma unroll
       for (int t = 0; t < 9; ++t) k[t][i] = Kc[(c0 + i) * 9 + t];
     const long long boff = (long long)b * H * W;
-    const T* g = dact + boff * CC + c0;
+    const TW* g = dact + boff * CC + c0;
     const T* p = pre + boff * CC + c0;
     float win[3][3][4];
     load_dpre_row3(g, p, CC, W, y0 - 1, H, x, win[0]);
@@ -366,10 +366,10 @@ k_conv_bwd(const T* __restrict__ dact, const T* __restrict__ pre, const T* __res
 // decay weights: w[t,h] = softplus(raw_dt + dt_bias) * exp(A_log)  (models/ADNssd.py:318,:310,:267-270)
 // and wx[t,c] = w[t,hd(c)] * xc[t,c].   thread = (token, head)
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, typename TW>
 __global__ void k_decay_wx(const T* __restrict__ raw, long long ldr, const T* __restrict__ act,
                            const float* __restrict__ dt_bias, const float* __restrict__ A_log,
-                           float* __restrict__ wdec, T* __restrict__ wx, long long Ttok, int nh, int P, int Di, int CC) {
+                           float* __restrict__ wdec, TW* __restrict__ wx, long long Ttok, int nh, int P, int Di, int CC) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Ttok * nh) return;
   long long t = idx / nh;
@@ -386,15 +386,15 @@ __global__ void k_decay_wx(const T* __restrict__ raw, long long ldr, const T* __
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over Di of y = ygemm + D[hd(c)] * xc  (models/ADNssd.py:283,:456), one warp per token
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, typename TW>
 __global__ void __launch_bounds__(256)
-k_ln_fwd(const T* __restrict__ ygemm, const T* __restrict__ act, const float* __restrict__ Dp,
-         const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ yn, long long Ttok,
+k_ln_fwd(const TW* __restrict__ ygemm, const T* __restrict__ act, const float* __restrict__ Dp,
+         const float* __restrict__ gamma, const float* __restrict__ beta, TW* __restrict__ yn, long long Ttok,
          int Di, int P, int CC) {
   long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (t >= Ttok) return;
-  const T* yg = ygemm + t * Di;
+  const TW* yg = ygemm + t * Di;
   const T* xc = act + t * CC + Di;
   float s = 0.f;
   for (int c = lane; c < Di; c += 32) s += ldf(yg + c) + Dp[head_of_channel(c, P)] * ldf(xc + c);
@@ -413,11 +413,11 @@ k_ln_fwd(const T* __restrict__ ygemm, const T* __restrict__ act, const float* __
 
 // backward of: out = alpha1 * [LN(y) | zc] @ W_out^T.  g = dout @ W_out (no alpha1).  Writes yn (for dW_out),
 // dy -> dact[:, Di:2Di], dzc -> dact[:, :Di]; accumulates dgamma, dbeta, dalpha1.
-template <typename T>
+template <typename T, typename TW>
 __global__ void __launch_bounds__(256)
-k_ln_bwd(const T* __restrict__ ygemm, const T* __restrict__ act, const T* __restrict__ g,
+k_ln_bwd(const TW* __restrict__ ygemm, const T* __restrict__ act, const TW* __restrict__ g,
          const float* __restrict__ Dp, const float* __restrict__ gamma, const float* __restrict__ beta,
-         const float* __restrict__ alpha1p, T* __restrict__ yn, T* __restrict__ dact, float* __restrict__ dgamma,
+         const float* __restrict__ alpha1p, TW* __restrict__ yn, TW* __restrict__ dact, float* __restrict__ dgamma,
          float* __restrict__ dbeta, float* __restrict__ dalpha1, long long Ttok, int tokens_per_warp, int Di, int P,
          int CC) {
   extern __shared__ float sm[];  // [2*Di] block-local dgamma / dbeta
@@ -430,11 +430,11 @@ k_ln_bwd(const T* __restrict__ ygemm, const T* __restrict__ act, const T* __rest
   long long t0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * tokens_per_warp;
   float da = 0.f;
   for (long long t = t0; t < min(Ttok, t0 + tokens_per_warp); ++t) {
-    const T* yg = ygemm + t * Di;
+    const TW* yg = ygemm + t * Di;
     const T* zc = act + t * CC;
     const T* xc = zc + Di;
-    const T* gy = g + t * 2 * Di;
-    const T* gz = gy + Di;
+    const TW* gy = g + t * 2 * Di;
+    const TW* gz = gy + Di;
     float s = 0.f;
     for (int c = lane; c < Di; c += 32) s += ldf(yg + c) + Dp[head_of_channel(c, P)] * ldf(xc + c);
     float mu = warp_sum(s) / Di;
@@ -478,11 +478,11 @@ k_ln_bwd(const T* __restrict__ ygemm, const T* __restrict__ act, const T* __rest
 
 // per (token, head): dxc = D*dy + w*G (in place over dact x block), wx = w*xc (in place over G),
 // ddt -> draw[:, CC+h]; accumulates dD, dA_log, ddt_bias.   block (32 heads, 8 tokens)
-template <typename T>
+template <typename T, typename TW>
 __global__ void __launch_bounds__(256)
 k_bwd_heads(const T* __restrict__ raw, long long ldr, const T* __restrict__ act, const float* __restrict__ wdec,
             const float* __restrict__ dt_bias, const float* __restrict__ A_log, const float* __restrict__ Dp,
-            T* __restrict__ dact, T* __restrict__ Gwx, T* __restrict__ draw, float* __restrict__ dD,
+            TW* __restrict__ dact, TW* __restrict__ Gwx, TW* __restrict__ draw, float* __restrict__ dD,
             float* __restrict__ dAlog, float* __restrict__ ddtb, long long Ttok, int tokens_per_thread, int nh, int P,
             int Di, int CC) {
   __shared__ float red[3][8][32];
@@ -614,17 +614,20 @@ struct SavedBufs {
   }
 };
 
+// Workspace (never saved) intermediates are fp32 in both modes: bf16 rounding is confined to the I/O and saved tensors.
+typedef float TWs;
+
 template <typename T>
 struct FwdWs {
   float* Kc;
-  T *bufA, *bufB;  // (T, Di) each: wx then y-gemm ; yn
+  TWs *bufA, *bufB;  // (T, Di) each: wx then y-gemm ; yn
   SavedBufs<T> tmp;  // used when the caller passes saved == NULL (inference)
   size_t bytes;
   FwdWs(const MixerDims& d, void* p) : tmp(d, nullptr) {
     Carver c(p);
     Kc = c.take<float>((size_t)d.CC * 9);
-    bufA = c.take<T>((size_t)d.T * d.Di);
-    bufB = c.take<T>((size_t)d.T * d.Di);
+    bufA = c.take<TWs>((size_t)d.T * d.Di);
+    bufB = c.take<TWs>((size_t)d.T * d.Di);
     size_t here = c.off;
     tmp = SavedBufs<T>(d, p ? (char*)p + here : nullptr);
     bytes = here + tmp.bytes;
@@ -638,7 +641,7 @@ struct BwdWs {
   GradAcc acc;
   float* dS;
   size_t zero_bytes;
-  T *g, *ybuf, *ynbuf, *dact, *draw;
+  TWs *g, *ybuf, *ynbuf, *dact, *draw;
   size_t bytes;
   BwdWs(const MixerDims& d, void* p) {
     Carver c(p);
@@ -656,11 +659,11 @@ struct BwdWs {
     acc.dK = c.take<float>((size_t)d.CC * 9);
     dS = c.take<float>((size_t)d.B * d.GN * d.Di);
     zero_bytes = c.off - z0;
-    g = c.take<T>((size_t)d.T * 2 * d.Di);
-    ybuf = c.take<T>((size_t)d.T * d.Di);
-    ynbuf = c.take<T>((size_t)d.T * d.Di);
-    dact = c.take<T>((size_t)d.T * d.CC);
-    draw = c.take<T>((size_t)d.T * d.ldr);
+    g = c.take<TWs>((size_t)d.T * 2 * d.Di);
+    ybuf = c.take<TWs>((size_t)d.T * d.Di);
+    ynbuf = c.take<TWs>((size_t)d.T * d.Di);
+    dact = c.take<TWs>((size_t)d.T * d.CC);
+    draw = c.take<TWs>((size_t)d.T * d.ldr);
     bytes = c.off;
   }
 };
@@ -692,19 +695,19 @@ int generic_forward(const MixerDims& d, const AdnWeights& w, const T* u, T* out,
     { ADN_KERNEL("k_conv_fwd", st); k_conv_fwd<T><<<grid, block, 0, st>>>(S.raw, d.ldr, W.Kc, training ? S.pre : nullptr, S.act, d.H, d.W, d.CC); }
   }
   // (3) decay weights and w*x
-  { ADN_KERNEL("k_decay_wx", st); k_decay_wx<T><<<cdiv(Tt * d.nh, 256), 256, 0, st>>>(S.raw, d.ldr, S.act, w.dt_bias, w.A_log, S.wdec, W.bufA, Tt,
+  { ADN_KERNEL("k_decay_wx", st); k_decay_wx<T, TWs><<<cdiv(Tt * d.nh, 256), 256, 0, st>>>(S.raw, d.ldr, S.act, w.dt_bias, w.A_log, S.wdec, W.bufA, Tt,
                                                       d.nh, d.P, d.Di, d.CC); }
   // (4a) state S'[b] = mask . Bc^T (w x)
   ADN_CHECK_CUDA(cudaMemsetAsync(S.S, 0, (size_t)d.B * d.GN * d.Di * sizeof(float), st));
-  launch_reduce_gemm<T, T>(st, S.act + 2 * d.Di, d.CC, W.bufA, d.Di, S.S, d.Di, (long long)d.GN * d.Di, d.GN, d.Di,
+  launch_reduce_gemm<T, TWs>(st, S.act + 2 * d.Di, d.CC, W.bufA, d.Di, S.S, d.Di, (long long)d.GN * d.Di, d.GN, d.Di,
                            d.L, d.B, 1);
   // (4b) readout y = Cc S'  (D-skip is added inside the LayerNorm kernel)
-  launch_gemm<T, T, false>(st, S.act + 2 * d.Di + d.GN, d.CC, (long long)d.L * d.CC, S.S, d.Di,
+  launch_gemm<T, TWs, false>(st, S.act + 2 * d.Di + d.GN, d.CC, (long long)d.L * d.CC, S.S, d.Di,
                            (long long)d.GN * d.Di, W.bufA, d.Di, (long long)d.L * d.Di, d.L, d.Di, d.GN, d.B, nullptr,
                            0);
   // (5) D-skip + LayerNorm, then out = alpha1 * (yn Wy^T + zc Wz^T)
-  { ADN_KERNEL("k_ln_fwd", st); k_ln_fwd<T><<<cdiv(Tt, 8), 256, 0, st>>>(W.bufA, S.act, w.D, w.norm_w, w.norm_b, W.bufB, Tt, d.Di, d.P, d.CC); }
-  launch_gemm<T, T, true>(st, W.bufB, d.Di, 0, w.out_proj_w, 2 * d.Di, 0, out, d.D, 0, (int)Tt, d.D, d.Di, 1,
+  { ADN_KERNEL("k_ln_fwd", st); k_ln_fwd<T, TWs><<<cdiv(Tt, 8), 256, 0, st>>>(W.bufA, S.act, w.D, w.norm_w, w.norm_b, W.bufB, Tt, d.Di, d.P, d.CC); }
+  launch_gemm<TWs, T, true>(st, W.bufB, d.Di, 0, w.out_proj_w, 2 * d.Di, 0, out, d.D, 0, (int)Tt, d.D, d.Di, 1,
                           w.alpha1, 0);
   launch_gemm<T, T, true>(st, S.act, d.CC, 0, w.out_proj_w + d.Di, 2 * d.Di, 0, out, d.D, 0, (int)Tt, d.D, d.Di, 1,
                           w.alpha1, 1);
@@ -722,41 +725,41 @@ int generic_backward(const MixerDims& d, const AdnWeights& w, const T* u, const 
   ADN_CHECK_CUDA(cudaMemsetAsync(W.zero_begin, 0, W.zero_bytes, st));
   { ADN_KERNEL("k_assemble_conv", st); k_assemble_conv<<<cdiv(d.CC, 128), 128, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC); }
   // ---- phase B1
-  launch_gemm<T, T, false>(st, dout, d.D, 0, w.out_proj_w, 2 * d.Di, 0, W.g, 2 * d.Di, 0, (int)Tt, 2 * d.Di, d.D, 1,
+  launch_gemm<T, TWs, false>(st, dout, d.D, 0, w.out_proj_w, 2 * d.Di, 0, W.g, 2 * d.Di, 0, (int)Tt, 2 * d.Di, d.D, 1,
                            nullptr, 0);
-  launch_gemm<T, T, false>(st, S.act + 2 * d.Di + d.GN, d.CC, (long long)d.L * d.CC, S.S, d.Di, sS, W.ybuf, d.Di,
+  launch_gemm<T, TWs, false>(st, S.act + 2 * d.Di + d.GN, d.CC, (long long)d.L * d.CC, S.S, d.Di, sS, W.ybuf, d.Di,
                            (long long)d.L * d.Di, d.L, d.Di, d.GN, d.B, nullptr, 0);
   {
     int tpw = 4;
-    { ADN_KERNEL("k_ln_bwd", st); k_ln_bwd<T><<<cdiv(Tt, 8 * tpw), 256, 2 * d.Di * sizeof(float), st>>>(
+    { ADN_KERNEL("k_ln_bwd", st); k_ln_bwd<T, TWs><<<cdiv(Tt, 8 * tpw), 256, 2 * d.Di * sizeof(float), st>>>(
         W.ybuf, S.act, W.g, w.D, w.norm_w, w.norm_b, w.alpha1, W.ynbuf, W.dact, W.acc.dgamma, W.acc.dbeta,
         W.acc.dalpha1, Tt, tpw, d.Di, d.P, d.CC); }
   }
-  launch_reduce_gemm<T, T>(st, dout, d.D, W.ynbuf, d.Di, W.acc.dWout, 2 * d.Di, 0, d.D, d.Di, (int)Tt, 1, 0);
+  launch_reduce_gemm<T, TWs>(st, dout, d.D, W.ynbuf, d.Di, W.acc.dWout, 2 * d.Di, 0, d.D, d.Di, (int)Tt, 1, 0);
   launch_reduce_gemm<T, T>(st, dout, d.D, S.act, d.CC, W.acc.dWout + d.Di, 2 * d.Di, 0, d.D, d.Di, (int)Tt, 1, 0);
-  launch_reduce_gemm<T, T>(st, S.act + 2 * d.Di + d.GN, d.CC, W.dact + d.Di, d.CC, W.dS, d.Di, sS, d.GN, d.Di, d.L,
+  launch_reduce_gemm<T, TWs>(st, S.act + 2 * d.Di + d.GN, d.CC, W.dact + d.Di, d.CC, W.dS, d.Di, sS, d.GN, d.Di, d.L,
                            d.B, 1);
-  launch_gemm<T, T, true>(st, W.dact + d.Di, d.CC, (long long)d.L * d.CC, S.S, d.Di, sS, W.dact + 2 * d.Di + d.GN,
+  launch_gemm<TWs, TWs, true>(st, W.dact + d.Di, d.CC, (long long)d.L * d.CC, S.S, d.Di, sS, W.dact + 2 * d.Di + d.GN,
                           d.CC, (long long)d.L * d.CC, d.L, d.GN, d.Di, d.B, nullptr, 0);
   // ---- phase B2
-  launch_gemm<T, T, false>(st, S.act + 2 * d.Di, d.CC, (long long)d.L * d.CC, W.dS, d.Di, sS, W.ybuf, d.Di,
+  launch_gemm<T, TWs, false>(st, S.act + 2 * d.Di, d.CC, (long long)d.L * d.CC, W.dS, d.Di, sS, W.ybuf, d.Di,
                            (long long)d.L * d.Di, d.L, d.Di, d.GN, d.B, nullptr, 0);
   {
     int tpt = 8;
     dim3 grid(cdiv(d.nh, 32), cdiv(Tt, 8 * tpt)), block(32, 8);
-    { ADN_KERNEL("k_bwd_heads", st); k_bwd_heads<T><<<grid, block, 0, st>>>(S.raw, d.ldr, S.act, S.wdec, w.dt_bias, w.A_log, w.D, W.dact, W.ybuf,
+    { ADN_KERNEL("k_bwd_heads", st); k_bwd_heads<T, TWs><<<grid, block, 0, st>>>(S.raw, d.ldr, S.act, S.wdec, w.dt_bias, w.A_log, w.D, W.dact, W.ybuf,
                                            W.draw, W.acc.dD, W.acc.dAlog, W.acc.ddtb, Tt, tpt, d.nh, d.P, d.Di, d.CC); }
   }
-  launch_gemm<T, T, true>(st, W.ybuf, d.Di, (long long)d.L * d.Di, W.dS, d.Di, sS, W.dact + 2 * d.Di, d.CC,
+  launch_gemm<TWs, TWs, true>(st, W.ybuf, d.Di, (long long)d.L * d.Di, W.dS, d.Di, sS, W.dact + 2 * d.Di, d.CC,
                           (long long)d.L * d.CC, d.L, d.GN, d.Di, d.B, nullptr, 0);
   // ---- conv backward
   {
     dim3 grid(cdiv(d.CC / 4, 8), cdiv(d.W, 32), d.B * cdiv(d.H, CONV_ROWS)), block(8, 32);
-    { ADN_KERNEL("k_conv_bwd", st); k_conv_bwd<T><<<grid, block, 0, st>>>(W.dact, S.pre, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.H, d.W, d.CC); }
+    { ADN_KERNEL("k_conv_bwd", st); k_conv_bwd<T, TWs><<<grid, block, 0, st>>>(W.dact, S.pre, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.H, d.W, d.CC); }
   }
   // ---- in_proj backward
-  launch_gemm<T, T, false>(st, W.draw, d.ldr, 0, w.in_proj_w, d.D, 0, du, d.D, 0, (int)Tt, d.D, d.dip, 1, nullptr, 0);
-  launch_reduce_gemm<T, T>(st, W.draw, d.ldr, u, d.D, W.acc.dWin, d.D, 0, d.dip, d.D, (int)Tt, 1, 0);
+  launch_gemm<TWs, T, false>(st, W.draw, d.ldr, 0, w.in_proj_w, d.D, 0, du, d.D, 0, (int)Tt, d.D, d.dip, 1, nullptr, 0);
+  launch_reduce_gemm<TWs, T>(st, W.draw, d.ldr, u, d.D, W.acc.dWin, d.D, 0, d.dip, d.D, (int)Tt, 1, 0);
   { ADN_KERNEL("k_finalize", st); k_finalize<<<148, 256, 0, st>>>(W.acc, w, g, d.D, d.Di, d.GN, d.nh, d.dip); }
   ADN_CHECK_LAUNCH();
   return ADN_OK;

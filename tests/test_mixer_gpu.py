@@ -101,7 +101,7 @@ def test_module_is_a_drop_in(golden_dir):
     # inference path (no saved buffers) gives the same output
     with torch.no_grad():
         out2 = m(u.cuda(), g, g)
-    assert torch.equal(out2, out.detach())
+    assert rel(out2, out.detach().cpu()) < 1e-5   # fp32 atomics in the state reduction: not bit-reproducible
     # autocast -> bf16 compute
     with torch.autocast("cuda", dtype=torch.bfloat16):
         out3 = m(u.cuda(), g, g)
