@@ -61,6 +61,7 @@ EXPORTS = {
     "adn_prof_enable": (C.c_int, [C.c_int]),
     "adn_prof_count": (C.c_int, []),
     "adn_prof_get": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
+    "adn_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -162,6 +162,10 @@ unsigned long long adn_launch_count(void);
 int adn_prof_enable(int on);
 int adn_prof_count(void);
 int adn_prof_get(int i, const char** name, float* ms);
+/* Hardware self-test of the tcgen05 building blocks (one 128 x N x K bf16 GEMM through shared-memory descriptors
+ * and TMEM).  mode 0: A[128][K], B[N][K] (K-major operands); mode 1: A[K][128], B[K][N] (MN-major operands).
+ * C is float[128][N]; *status (device int) is set to 1 if the MMA completion barrier timed out. */
+int adn_selftest_umma(int mode, int N, int K, const void* A, const void* B, float* C, int* status, void* stream);
 
 #ifdef __cplusplus
 }

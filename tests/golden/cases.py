@@ -58,3 +58,17 @@ def metric_inputs():
     obs.view(-1)[::97] = torch.tensor([20, 30, 35, 40], dtype=torch.float32).repeat(obs.numel())[: obs.view(-1)[::97].numel()] / 90
     sim.view(-1)[::89] = torch.tensor([40, 35, 30, 20], dtype=torch.float32).repeat(sim.numel())[: sim.view(-1)[::89].numel()] / 90
     return obs.numpy(), sim.numpy()
+
+# bf16 parity regime: the model's own initialisation scale with a mild perturbation so that
+# no term vanishes.  name -> (d_model, headdim, d_state, batch, grid, perturb)
+MIXER_BF16_CASES = {
+    "mixerinit_d32_p4_n16_g32": (32, 4, 16, 2, 32, 0.1),
+    "mixerinit_d128_p4_n16_g16": (128, 4, 16, 2, 16, 0.1),
+    "mixerinit_d32_p4_n64_g16": (32, 4, 64, 1, 16, 0.05),
+}
+
+
+def mixer_bf16_inputs(name, dtype=torch.float64):
+    D, P, N, B, g, _ = MIXER_BF16_CASES[name]
+    seed = 4000 + sorted(MIXER_BF16_CASES).index(name)
+    return rng_normal(seed, (B, g * g, D), dtype), rng_normal(seed + 500, (B, g * g, D), dtype)

@@ -50,6 +50,25 @@ def mixer_case(ref, name):
     save(name, **arrays)
 
 
+def mixer_bf16_case(ref, name):
+    """Model-scale parameters (init_params mirrors the reference init, models/ADNssd.py:201-222 + ADNMUNet.py:294-323)."""
+    D, P, N, B, g, perturb = cases.MIXER_BF16_CASES[name]
+    p32 = adnssd_oracle.init_params(D, P, N, seed=13, perturb=perturb, dtype=torch.float32)
+    m = ref.ADNssd.Mamba2(d_model=D, headdim=P, d_state=N).double()
+    m.load_state_dict({k: v.double() for k, v in p32.items()}, strict=True)
+    u32, g32 = cases.mixer_bf16_inputs(name, torch.float32)
+    u = u32.double().requires_grad_(True)
+    with cuda_to_is_noop():
+        out = m(u, g, g)
+    out.backward(g32.double())
+    arrays = {"param/" + k: v.numpy() for k, v in p32.items()}
+    arrays.update(out=out.detach().float().numpy(), du=u.grad.float().numpy())
+    for k, v in m.named_parameters():
+        if v.grad is not None:
+            arrays["grad/" + k] = v.grad.float().numpy()
+    save(name, **arrays)
+
+
 def wtconv_case(ref, name):
     C, k, L, B, H, W, bias = cases.WTCONV_CASES[name]
     p32 = wtconv_oracle.init_params(C, k, L, bias=bias, seed=21, dtype=torch.float32)
@@ -96,6 +115,9 @@ def main():
     for name in cases.MIXER_CASES:
         if not only or name in only:
             mixer_case(ref, name)
+    for name in cases.MIXER_BF16_CASES:
+        if not only or name in only:
+            mixer_bf16_case(ref, name)
     for name in cases.WTCONV_CASES:
         if not only or name in only:
             wtconv_case(ref, name)

@@ -17,3 +17,13 @@ for name in sorted(cases.MIXER_CASES):
         for k, ref in grads.items():
             errs[k] = rel(pg[k].reshape(ref.shape), ref)
         print(name, dtype, " ".join(f"{k.replace('.weight','')}={v:.1e}" for k, v in errs.items()))
+for name in sorted(cases.MIXER_BF16_CASES):
+    D, P, N, B, g, _ = cases.MIXER_BF16_CASES[name]
+    z, params, grads = load_case(gd, name)
+    u, dout = cases.mixer_bf16_inputs(name, torch.float32)
+    for dtype in (torch.float32, torch.bfloat16):
+        out, du, pg = run_cuda(params, u, dout, g, g, P, N, dtype)
+        errs = {"out": rel(out, z["out"]), "du": rel(du, z["du"])}
+        for k, ref in grads.items():
+            errs[k] = rel(pg[k].reshape(ref.shape), ref)
+        print(name, dtype, " ".join(f"{k.replace('.weight','')}={v:.1e}" for k, v in errs.items()))

@@ -13,6 +13,11 @@ from oracle import adnssd_oracle as AO
 pytestmark = pytest.mark.gpu
 
 TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+# The fp64-verified goldens MIXER_CASES perturb EVERY parameter by N(0, 0.3^2) (in_proj 15x its init scale) so that no
+# term of the check-mode comparison vanishes.  In that regime bf16 storage of the in_proj / conv outputs alone moves du by
+# up to 2.1e-2 (CPU emulation with everything else in fp64, DESIGN.md "bf16 error budget"), so the bf16 bound there is a
+# sanity bound; the 2e-2 contract is asserted on the model-scale goldens MIXER_BF16_CASES.
+BF16_STRESS_TOL = 1e-1
 
 
 def rel(a, b):
@@ -46,8 +51,25 @@ def test_mixer_matches_reference_golden(golden_dir, name, dtype):
     u, dout = cases.mixer_inputs(name, torch.float32)
     out, du, pg = run_cuda(params, u, dout, g, g, P, N, dtype)
     s = cases.SUBSAMPLE_STRIDE if g >= 64 else 1
-    tol = TOL[dtype]
+    tol = TOL[dtype] if dtype == torch.float32 else BF16_STRESS_TOL
     errs = {"out": rel(out[:, ::s], z["out"]), "du": rel(du[:, ::s], z["du"])}
+    assert set(pg) == set(grads)
+    for k, ref in grads.items():
+        errs[k] = rel(pg[k].reshape(ref.shape), ref)
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, f"{name} {dtype}: {bad} (all: {errs})"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("name", sorted(cases.MIXER_BF16_CASES))
+def test_mixer_matches_reference_golden_model_scale(golden_dir, name, dtype):
+    """The contract of BASELINE.json: <= 2e-2 in bf16, <= 1e-4 in fp32 check mode, per output / gradient tensor."""
+    D, P, N, B, g, _ = cases.MIXER_BF16_CASES[name]
+    z, params, grads = load_case(golden_dir, name)
+    u, dout = cases.mixer_bf16_inputs(name, torch.float32)
+    out, du, pg = run_cuda(params, u, dout, g, g, P, N, dtype)
+    tol = TOL[dtype]
+    errs = {"out": rel(out, z["out"]), "du": rel(du, z["du"])}
     assert set(pg) == set(grads)
     for k, ref in grads.items():
         errs[k] = rel(pg[k].reshape(ref.shape), ref)
@@ -68,7 +90,7 @@ def test_mixer_matches_oracle_ragged_shapes(cfg, dtype):
     ref_out = AO.mixer_forward(p64, u.double(), H, W, P, N)
     ref_du, ref_g = AO.mixer_backward(p64, u.double(), H, W, P, N, dout.double())
     out, du, pg = run_cuda(params, u, dout, H, W, P, N, dtype)
-    tol = TOL[dtype]
+    tol = TOL[dtype] if dtype == torch.float32 else BF16_STRESS_TOL   # perturb=0.3 stress regime, see above
     errs = {"out": rel(out, ref_out), "du": rel(du, ref_du)}
     for k, ref in ref_g.items():
         errs[k] = rel(pg[k].reshape(ref.shape), ref)

@@ -43,6 +43,19 @@ def test_mixer_oracle_matches_reference_fp64(golden_dir, name):
         assert rel(og[k].reshape(ref.shape), ref) < 1e-11, k
 
 
+@pytest.mark.parametrize("name", sorted(cases.MIXER_BF16_CASES))
+def test_mixer_oracle_matches_reference_model_scale(golden_dir, name):
+    D, P, N, B, g, _ = cases.MIXER_BF16_CASES[name]
+    z, params, grads = load(golden_dir, name)          # stored as float32
+    p = {k: v.double() for k, v in params.items()}
+    u, dout = cases.mixer_bf16_inputs(name, torch.float32)
+    out = AO.mixer_forward(p, u.double(), g, g, P, N)
+    du, og = AO.mixer_backward(p, u.double(), g, g, P, N, dout.double())
+    assert rel(out, z["out"]) < 1e-6 and rel(du, z["du"]) < 1e-6
+    for k, ref in grads.items():
+        assert rel(og[k].reshape(ref.shape), ref) < 1e-6, k
+
+
 def test_mixer_oracle_explicit_backward_equals_autograd():
     D, P, N, g = 16, 4, 8, 5
     p = AO.init_params(D, P, N, seed=3, perturb=0.3, dtype=torch.float64)
