@@ -15,7 +15,7 @@ struct ConvWeightPtrs {
   const float *c13x1, *c31x1, *c13x2, *c31x2, *c13bc1, *c31bc1, *c13bc2, *c31bc2, *c2d, *c2dz;
 };
 
-__global__ void k_assemble_conv(ConvWeightPtrs w, float* __restrict__ Kc, int Di, int CC) {
+static __global__ void k_assemble_conv(ConvWeightPtrs w, float* __restrict__ Kc, int Di, int CC) {
   int cc = blockIdx.x * blockDim.x + threadIdx.x;
   if (cc >= CC) return;
   float k[9];
@@ -530,7 +530,7 @@ struct GradAcc {
   float *dWin, *dWout, *dgamma, *dbeta, *dD, *dAlog, *ddtb, *dalpha1, *dK;
 };
 
-__global__ void k_finalize(GradAcc a, AdnWeights w, AdnWeightGrads g, int D, int Di, int GN, int nh, int dip) {
+static __global__ void k_finalize(GradAcc a, AdnWeights w, AdnWeightGrads g, int D, int Di, int GN, int nh, int dip) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const float a1 = *w.alpha1;
@@ -617,31 +617,31 @@ struct SavedBufs {
 // Workspace (never saved) intermediates are fp32 in both modes: bf16 rounding is confined to the I/O and saved tensors.
 typedef float TWs;
 
-template <typename T>
+template <typename T, typename TW = TWs>
 struct FwdWs {
   float* Kc;
-  TWs *bufA, *bufB;  // (T, Di) each: wx then y-gemm ; yn
+  TW *bufA, *bufB;  // (T, Di) each: wx then y-gemm ; yn
   SavedBufs<T> tmp;  // used when the caller passes saved == NULL (inference)
   size_t bytes;
   FwdWs(const MixerDims& d, void* p) : tmp(d, nullptr) {
     Carver c(p);
     Kc = c.take<float>((size_t)d.CC * 9);
-    bufA = c.take<TWs>((size_t)d.T * d.Di);
-    bufB = c.take<TWs>((size_t)d.T * d.Di);
+    bufA = c.take<TW>((size_t)d.T * d.Di);
+    bufB = c.take<TW>((size_t)d.T * d.Di);
     size_t here = c.off;
     tmp = SavedBufs<T>(d, p ? (char*)p + here : nullptr);
     bytes = here + tmp.bytes;
   }
 };
 
-template <typename T>
+template <typename T, typename TW = TWs>
 struct BwdWs {
   float* Kc;
   float* zero_begin;
   GradAcc acc;
   float* dS;
   size_t zero_bytes;
-  TWs *g, *ybuf, *ynbuf, *dact, *draw;
+  TW *g, *ybuf, *ynbuf, *dact, *draw;
   size_t bytes;
   BwdWs(const MixerDims& d, void* p) {
     Carver c(p);
@@ -659,11 +659,11 @@ struct BwdWs {
     acc.dK = c.take<float>((size_t)d.CC * 9);
     dS = c.take<float>((size_t)d.B * d.GN * d.Di);
     zero_bytes = c.off - z0;
-    g = c.take<TWs>((size_t)d.T * 2 * d.Di);
-    ybuf = c.take<TWs>((size_t)d.T * d.Di);
-    ynbuf = c.take<TWs>((size_t)d.T * d.Di);
-    dact = c.take<TWs>((size_t)d.T * d.CC);
-    draw = c.take<TWs>((size_t)d.T * d.ldr);
+    g = c.take<TW>((size_t)d.T * 2 * d.Di);
+    ybuf = c.take<TW>((size_t)d.T * d.Di);
+    ynbuf = c.take<TW>((size_t)d.T * d.Di);
+    dact = c.take<TW>((size_t)d.T * d.CC);
+    draw = c.take<TW>((size_t)d.T * d.ldr);
     bytes = c.off;
   }
 };

@@ -1,10 +1,18 @@
-// sm_100a tensor-core (tcgen05 / TMEM) path of the ADN-SSD mixer, bf16 I/O.
+// sm_100a tensor-core (tcgen05 / TMEM) path of the ADN-SSD mixer, bf16 I/O, for the shapes ADNM-UNet's
+// full-resolution refiner uses (d_model 32, headdim 4, d_state 16) and neighbours.  Same stage split and the same
+// saved-tensor layout as the generic path (adnssd_generic.cuh); each stage is replaced by a fused kernel:
+//   k_prep          fp32 master weights -> bf16 hi/lo operand images, conv kernel assembly
+//   k_inproj        raw = u . W_in^T           tcgen05 (bf16 hi + lo weights, fp32 accumulate in TMEM)
+//   k_conv_fwd8     depthwise 3x3 + SiLU       128-bit loads, register window, coalesced channels-last
+//   k_conv_bwd4     conv backward + dK         same mapping, block-level reduction of the kernel gradient
 #include "adnssd_sm100.cuh"
 
+#include "adnssd_generic.cuh"
 #include "sm100_utils.cuh"
 
 namespace adn {
 using namespace sm100;
+typedef bf16 TWf;   // workspace intermediates of the fast path are bf16 (tensor-core operands)
 
 // ------------------------------------------------------------------------------------------------
 // UMMA self-test: one CTA, one 128 x N x K problem, operands staged in the T8 layout.
@@ -25,7 +33,6 @@ k_umma_selftest(int mode, int N, int K, const bf16* __restrict__ A, const bf16* 
     for (int i = tid; i < 128 * K; i += 128) { int r = i / K, c = i % K; sA[t8_off(r, c, 128)] = A[i]; }
     for (int i = tid; i < N * K; i += 128) { int r = i / K, c = i % K; sB[t8_off(r, c, N)] = Bm[i]; }
   } else {
-    // tiles are [K tokens][channels]: rows = tokens
     for (int i = tid; i < K * 128; i += 128) { int t = i / 128, c = i % 128; sA[t8_off(t, c, K)] = A[i]; }
     for (int i = tid; i < K * N; i += 128) { int t = i / N, c = i % N; sB[t8_off(t, c, K)] = Bm[i]; }
   }
@@ -63,12 +70,1323 @@ k_umma_selftest(int mode, int N, int K, const bf16* __restrict__ A, const bf16* 
   if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
-bool sm100_supported(const MixerDims&) { return false; }
-void sm100_workspace_bytes(const MixerDims&, size_t* f, size_t* b) { *f = 0; *b = 0; }
-int sm100_forward(const MixerDims&, const AdnWeights&, const bf16*, bf16*, void*, void*, cudaStream_t) {
-  set_error("sm100 path not built"); return ADN_ERR_ARCH; }
-int sm100_backward(const MixerDims&, const AdnWeights&, const bf16*, const void*, const bf16*, bf16*,
-                   const AdnWeightGrads&, void*, cudaStream_t) { set_error("sm100 path not built"); return ADN_ERR_ARCH; }
+// ------------------------------------------------------------------------------------------------
+// cp.async helpers (16-byte, L2-only caching; src_bytes = 0 zero-fills)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Load a [128 tokens][CH*8 channels] bf16 tile (row pitch ld elements, first channel c0) into T8 shared memory.
+// Lane mapping: 8 consecutive tokens x consecutive 16-byte chunks per warp instruction: conflict-free shared-memory
+// writes, 8 x (CH*16)-byte contiguous global segments.  Rows >= rows_valid are zero-filled.
+__device__ __forceinline__ void load_tile_t8(bf16* sdst, const bf16* __restrict__ gsrc, long long ld, int CH,
+                                             int rows_valid, int tid, int nthreads) {
+  for (int i = tid; i < 128 * CH; i += nthreads) {
+    int tok8 = i & 7, rest = i >> 3;
+    int chunk = rest % CH, tok = (rest / CH) * 8 + tok8;
+    bool ok = tok < rows_valid;
+    const bf16* src = gsrc + (long long)(ok ? tok : 0) * ld + chunk * 8;
+    cp_async16(sdst + (chunk * 128 + tok) * 8, src, ok ? 16 : 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_prep: bf16 hi/lo images of in_proj.weight ([dip][D] row-major, hi + lo = fp32 value to ~2^-17)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_prep_split(const float* __restrict__ w, bf16* __restrict__ hi, bf16* __restrict__ lo, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = w[i];
+  bf16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_inproj: raw[T][ldr] = u[T][D] . W_in^T   (models/ADNssd.py:309).  Persistent CTAs, 128 tokens per tile.
+// A = u tile (K-major, cp.async double buffered), B = W_in rows [n0, n0+nn) as hi and lo bf16 images (K-major):
+// D(tmem) = A.B_hi^T + A.B_lo^T with fp32 accumulation, so raw carries no weight-rounding error.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128)
+k_inproj(const bf16* __restrict__ u, const bf16* __restrict__ Whi, const bf16* __restrict__ Wlo, bf16* __restrict__ raw,
+         int ldr, int dip, long long T, int num_tiles, int* __restrict__ status) {
+  constexpr int CH = D / 8;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  bf16* sWhi = reinterpret_cast<bf16*>(smem);   // [CH][256][8]
+  bf16* sWlo = sWhi + 256 * D;
+  bf16* sA0 = sWlo + 256 * D;                   // 2 x [CH][128][8]
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  uint32_t parity = 0;
+  for (int n0 = 0; n0 < dip; n0 += 256) {
+    const int nn = min(256, dip - n0);
+    __syncthreads();
+    for (int i = tid; i < nn * CH; i += 128) {
+      int j = i / CH, dc = i % CH;
+      const uint4 h = *reinterpret_cast<const uint4*>(Whi + (long long)(n0 + j) * D + dc * 8);
+      const uint4 l = *reinterpret_cast<const uint4*>(Wlo + (long long)(n0 + j) * D + dc * 8);
+      *reinterpret_cast<uint4*>(sWhi + (dc * nn + j) * 8) = h;
+      *reinterpret_cast<uint4*>(sWlo + (dc * nn + j) * 8) = l;
+    }
+    int tile = blockIdx.x, stage = 0;
+    if (tile < num_tiles) {
+      long long t0 = (long long)tile * 128;
+      load_tile_t8(sA0, u + t0 * D, D, CH, (int)min((long long)128, T - t0), tid, 128);
+    }
+    cp_async_commit();
+    for (; tile < num_tiles; tile += gridDim.x, stage ^= 1) {
+      const int nxt = tile + gridDim.x;
+      if (nxt < num_tiles) {
+        long long t1 = (long long)nxt * 128;
+        load_tile_t8(sA0 + (stage ^ 1) * 128 * D, u + t1 * D, D, CH, (int)min((long long)128, T - t1), tid, 128);
+      }
+      cp_async_commit();
+      cp_async_wait<1>();
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA0 + stage * 128 * D), bh = smem_u32(sWhi), bl = smem_u32(sWlo);
+        const uint32_t idesc = make_idesc_rt(128, nn, false, false);
+#pragma unroll
+        for (int k = 0; k < D; k += 16) umma(tbase, desc_kmajor(a0, 128, 0, k), desc_kmajor(bh, nn, 0, k), idesc, k > 0);
+#pragma unroll
+        for (int k = 0; k < D; k += 16) umma(tbase, desc_kmajor(a0, 128, 0, k), desc_kmajor(bl, nn, 0, k), idesc, true);
+        umma_commit(&bar);
+      }
+      const bool ok = mbar_wait(&bar, parity);
+      parity ^= 1;
+      tc_fence_after();
+      if (!ok) { if (tid == 0) atomicExch(status, 1); break; }
+      const long long row = (long long)tile * 128 + tid;
+      bf16* dst = raw + row * ldr + n0;
+      for (int c = 0; c < nn; c += 32) {
+        float v0[16], v1[16];
+        tmem_ld16(tmem_addr(tbase, warp * 32, c), v0);
+        if (c + 16 < nn) tmem_ld16(tmem_addr(tbase, warp * 32, c + 16), v1);
+        tmem_wait_ld();
+        if (row < T) {
+          float a[8], b[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { a[j] = v0[j]; b[j] = v0[8 + j]; }
+          *reinterpret_cast<uint4*>(dst + c) = pack8(a);
+          *reinterpret_cast<uint4*>(dst + c + 8) = pack8(b);
+          if (c + 16 < nn) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] = v1[j]; b[j] = v1[8 + j]; }
+            *reinterpret_cast<uint4*>(dst + c + 16) = pack8(a);
+            *reinterpret_cast<uint4*>(dst + c + 24) = pack8(b);
+          }
+        }
+      }
+      tc_fence_before();   // TMEM reads of this tile are ordered before the next tile's MMA (after the next __syncthreads)
+    }
+    cp_async_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 3x3 + SiLU, channels-last bf16, 8 channels (one 16-byte vector) per thread, ROWS8 output rows per
+// thread with a 3x3 register window.  Flat thread index over (column, channel-vector) with the channel-vector
+// fastest: a warp reads / writes 512 contiguous bytes.   grid (ceil(W*CG/128), ceil(H/ROWS8), B)
+// ------------------------------------------------------------------------------------------------
+constexpr int ROWS8 = 16;
+
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_grad_fast(float x) {
+  float s = __fdividef(1.f, 1.f + __expf(-x));
+  return s * (1.f + x * (1.f - s));
+}
+
+__device__ __forceinline__ uint4 ldg16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+__global__ void __launch_bounds__(128)
+k_conv_fwd8(const bf16* __restrict__ raw, int ldr, const float* __restrict__ Kc, bf16* __restrict__ pre,
+            bf16* __restrict__ act, int H, int W, int CC) {
+  const int CG = CC >> 3;
+  const int idx = blockIdx.x * 128 + threadIdx.x;
+  if (idx >= W * CG) return;
+  const int x = idx / CG, cg = idx % CG, c0 = cg * 8;
+  const int b = blockIdx.z, y0 = blockIdx.y * ROWS8, y1 = min(H, y0 + ROWS8);
+  float k[9][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) k[t][i] = __ldg(Kc + (c0 + i) * 9 + t);
+  const bf16* src = raw + (long long)b * H * W * ldr + c0;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  const bool xl = x > 0, xr = x + 1 < W;
+  uint4 win[3][3];
+  auto load_row = [&](int y, uint4 (&r)[3]) {
+    if (y >= 0 && y < H) {
+      const bf16* p = src + ((long long)y * W + x) * ldr;
+      r[0] = xl ? ldg16(p - ldr) : zero;
+      r[1] = ldg16(p);
+      r[2] = xr ? ldg16(p + ldr) : zero;
+    } else {
+      r[0] = r[1] = r[2] = zero;
+    }
+  };
+  load_row(y0 - 1, win[0]);
+  load_row(y0, win[1]);
+  for (int y = y0; y < y1; ++y) {
+    load_row(y + 1, win[2]);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        float v[8];
+        unpack8(win[r][s], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fmaf(k[r * 3 + s][i], v[i], a[i]);
+      }
+    const long long off = (((long long)b * H + y) * W + x) * CC + c0;
+    if (pre) *reinterpret_cast<uint4*>(pre + off) = pack8(a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = silu_fast(a[i]);
+    *reinterpret_cast<uint4*>(act + off) = pack8(a);
+#pragma unroll
+    for (int s = 0; s < 3; ++s) { win[0][s] = win[1][s]; win[1][s] = win[2][s]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv backward, 4 channels per thread: draw[:, :CC] = convT(dact * silu'(pre)); dK += raw (x) dpre.
+// Flat mapping like the forward; block = 192 threads; block-level smem reduction of dK, then global atomics.
+//   grid (ceil(W*CG4/192), ceil(H/ROWS8), ceil(B/BPB)); each block loops over BPB samples to amortise the reduction
+// ------------------------------------------------------------------------------------------------
+template <typename TW>
+__global__ void __launch_bounds__(192)
+k_conv_bwd4(const TW* __restrict__ dact, const bf16* __restrict__ pre, const bf16* __restrict__ raw, int ldr,
+            const float* __restrict__ Kc, TW* __restrict__ draw, float* __restrict__ dK, int B, int H, int W, int CC,
+            int bpb) {
+  extern __shared__ float red[];   // [CC*9] block-local dK
+  const int CG = CC >> 2;
+  for (int i = threadIdx.x; i < CC * 9; i += 192) red[i] = 0.f;
+  __syncthreads();
+  const int idx = blockIdx.x * 192 + threadIdx.x;
+  const bool active = idx < W * CG;
+  const int x = active ? idx / CG : 0, cg = active ? idx % CG : 0, c0 = cg * 4;
+  const int y0 = blockIdx.y * ROWS8, y1 = min(H, y0 + ROWS8);
+  float dk[9][4] = {};
+  if (active) {
+    float k[9][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) k[t][i] = __ldg(Kc + (c0 + i) * 9 + t);
+    const bool xl = x > 0, xr = x + 1 < W;
+    for (int b = blockIdx.z * bpb; b < min(B, (blockIdx.z + 1) * bpb); ++b) {
+      const long long boff = (long long)b * H * W;
+      const TW* g = dact + boff * CC + c0;
+      const bf16* p = pre + boff * CC + c0;
+      float win[3][3][4];
+      auto load_row = [&](int y, float (&r)[3][4]) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const bool ok = y >= 0 && y < H && (s == 1 || (s == 0 ? xl : xr));
+          if (ok) {
+            float gv[4], pv[4];
+            const long long off = ((long long)y * W + x + s - 1) * CC;
+            ld4(g + off, gv);
+            ld4(p + off, pv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[s][i] = gv[i] * silu_grad_fast(pv[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[s][i] = 0.f;
+          }
+        }
+      };
+      load_row(y0 - 1, win[0]);
+      load_row(y0, win[1]);
+      for (int y = y0; y < y1; ++y) {
+        load_row(y + 1, win[2]);
+        const long long tok = boff + (long long)y * W + x;
+        float rc[4], o[4] = {0.f, 0.f, 0.f, 0.f};
+        ld4(raw + tok * ldr + c0, rc);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float d = win[2 - a][2 - bb][i];
+              o[i] = fmaf(k[a * 3 + bb][i], d, o[i]);
+              dk[a * 3 + bb][i] = fmaf(rc[i], d, dk[a * 3 + bb][i]);
+            }
+        st4(draw + tok * ldr + c0, o);
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { win[0][s][i] = win[1][s][i]; win[1][s][i] = win[2][s][i]; }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(&red[(c0 + i) * 9 + t], dk[t][i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CC * 9; i += 192)
+    if (red[i] != 0.f) atomicAdd(dK + i, red[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_state: S'[b][j][c] += [j%2==c%2] * sum_l Bc[l,j] * w[l,hd(c)] * xc[l,c]      (models/ADNssd.py:267-280, both parities)
+// One CTA = a slice of the tiles of one sample.  Per 128-token tile: x, B and the dt columns arrive by cp.async in
+// the T8 layout; each thread (= token) turns its dt values into w = softplus(dt+bias)*exp(A_log) and scales its x row
+// in place; then  D(tmem)[c][j] += sum_tok wx[tok][c] * Bc[tok][j]  is ONE tcgen05 reduction over the tokens
+// (A = wx and B = Bc both MN-major, M padded to 128 channels with zero chunks), accumulated in TMEM across tiles.
+// headdim 4: the 8 channels of chunk cg belong to heads 2cg (even channels) and 2cg+1 (odd channels).
+// ------------------------------------------------------------------------------------------------
+template <int DI, int GN>
+__global__ void __launch_bounds__(128)
+k_state(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int CC, const float* __restrict__ dt_bias,
+        const float* __restrict__ A_log, float* __restrict__ S, int L, int tiles_per_batch, int ctas_per_batch,
+        int* __restrict__ status) {
+  constexpr int XC = DI / 8, BC = GN / 8, DC = DI / 32, NH = DI / 4;
+  constexpr int STAGE = (16 + BC + DC) * 128 * 8;   // bf16 elements per stage
+  constexpr uint32_t TCOLS = GN <= 32 ? 32 : (GN <= 64 ? 64 : 128);
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ float s_bias[NH], s_eA[NH];
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_slot;
+  bf16* sbase = reinterpret_cast<bf16*>(smem);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.x / ctas_per_batch, part = blockIdx.x % ctas_per_batch;
+  for (int i = tid; i < NH; i += 128) { s_bias[i] = dt_bias[i]; s_eA[i] = __expf(A_log[i]); }
+  // zero the padding chunks [XC, 16) of the wx operand in both stages
+  for (int st = 0; st < 2; ++st)
+    for (int i = tid; i < (16 - XC) * 128; i += 128)
+      *reinterpret_cast<uint4*>(sbase + st * STAGE + (XC * 128 + i) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  const uint32_t idesc = make_idesc_rt(128, GN, true, true);
+  int it = 0;
+  bool ok = true;
+  for (int i = part; i < tiles_per_batch; i += ctas_per_batch, ++it) {
+    const int stage = it & 1;
+    bf16* sX = sbase + stage * STAGE;
+    bf16* sB = sX + 16 * 128 * 8;
+    bf16* sDt = sB + BC * 128 * 8;
+    if (it >= 2) ok = ok && mbar_wait(&bar[stage], ((it >> 1) - 1) & 1);   // the MMAs that read this stage are done
+    const int rows = min(128, L - i * 128);
+    const long long tok0 = (long long)b * L + (long long)i * 128;
+    load_tile_t8(sX, act + tok0 * CC + DI, CC, XC, rows, tid, 128);
+    load_tile_t8(sB, act + tok0 * CC + 2 * DI, CC, BC, rows, tid, 128);
+    load_tile_t8(sDt, raw + tok0 * ldr + CC, ldr, DC, rows, tid, 128);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    float w[NH];
+#pragma unroll
+    for (int dc = 0; dc < DC; ++dc) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(sDt + (dc * 128 + tid) * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[dc * 8 + j] = softplusf_(v[j] + s_bias[dc * 8 + j]) * s_eA[dc * 8 + j];
+    }
+#pragma unroll
+    for (int cg = 0; cg < XC; ++cg) {
+      uint4* slot = reinterpret_cast<uint4*>(sX + (cg * 128 + tid) * 8);
+      float v[8];
+      unpack8(*slot, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= w[2 * cg + (j & 1)];
+      *slot = pack8(v);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(sX), b0 = smem_u32(sB);
+#pragma unroll
+      for (int k = 0; k < 128; k += 16)
+        umma(tbase, desc_mnmajor(a0, 128, 0, k), desc_mnmajor(b0, 128, 0, k), idesc, it > 0 || k > 0);
+      umma_commit(&bar[stage]);
+    }
+  }
+  if (it > 0) {
+    const int last = (it - 1) & 1;
+    ok = ok && mbar_wait(&bar[last], ((it - 1) >> 1) & 1);
+    tc_fence_after();
+    if (ok) {
+      for (int c0 = 0; c0 < GN; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_addr(tbase, warp * 32, c0), v);
+        tmem_wait_ld();
+        if (tid < DI) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if ((((c0 + j) ^ tid) & 1) == 0) atomicAdd(S + ((long long)b * GN + c0 + j) * DI + tid, v[j]);
+        }
+      }
+    } else if (tid == 0) {
+      atomicExch(status, 2);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, TCOLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_readout: per 128-token tile  y = Cc.S' + D*xc  ->  LayerNorm  ->  out = alpha1 * [LN(y) | zc] . W_out^T
+// (models/ADNssd.py:281-283, :456-461).  Two tcgen05 GEMMs per tile; between them each thread owns one token row
+// (TMEM lane = token), so the LayerNorm statistics are thread-local.  S' is used as bf16 hi + lo (fp32-accurate).
+// ------------------------------------------------------------------------------------------------
+template <int DI, int GN>
+__global__ void __launch_bounds__(128)
+k_readout(const bf16* __restrict__ act, int CC, const float* __restrict__ S, const float* __restrict__ Dp,
+          const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ alpha1p,
+          const bf16* __restrict__ Wout, bf16* __restrict__ out, int L, int tiles_per_batch, int num_tiles,
+          int* __restrict__ status) {
+  constexpr int D = DI / 2, XC = DI / 8, CCH = GN / 8, CATC = 2 * DI / 8;
+  constexpr uint32_t TCOLS = (DI + D) <= 128 ? 128 : 256;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ float sG[DI], sBt[DI], sDh[DI];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  bf16* sC = reinterpret_cast<bf16*>(smem);   // [CCH][128][8]
+  bf16* sCat = sC + CCH * 128 * 8;            // [CATC][128][8]: chunks [0,XC) = LN(y), [XC,2XC) = zc
+  bf16* sX = sCat + CATC * 128 * 8;           // [XC][128][8]
+  bf16* sShi = sX + XC * 128 * 8;             // [CCH][DI][8]   S'^T as a K-major B operand: row = c, K = j
+  bf16* sSlo = sShi + CCH * DI * 8;
+  bf16* sW = sSlo + CCH * DI * 8;             // [CATC][D][8]   W_out: row = d, K = j'
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < DI; i += 128) { sG[i] = gamma[i]; sBt[i] = beta[i]; sDh[i] = Dp[head_of_channel(i, 4)]; }
+  for (int i = tid; i < D * CATC; i += 128) {
+    int d = i / CATC, jc = i % CATC;
+    *reinterpret_cast<uint4*>(sW + (jc * D + d) * 8) = *reinterpret_cast<const uint4*>(Wout + (long long)d * 2 * DI + jc * 8);
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  const float a1 = *alpha1p;
+  uint32_t ph = 0;
+  int cur_b = -1;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_batch, i = tile % tiles_per_batch;
+    const int rows = min(128, L - i * 128);
+    const long long tok0 = (long long)b * L + (long long)i * 128;
+    if (b != cur_b) {
+      for (int idx = tid; idx < CCH * DI; idx += 128) {
+        int jc = idx / DI, c = idx % DI;
+        float v[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v[q] = S[((long long)b * GN + jc * 8 + q) * DI + c];
+          lo[q] = v[q] - __bfloat162float(__float2bfloat16_rn(v[q]));
+        }
+        *reinterpret_cast<uint4*>(sShi + (jc * DI + c) * 8) = pack8(v);
+        *reinterpret_cast<uint4*>(sSlo + (jc * DI + c) * 8) = pack8(lo);
+      }
+      cur_b = b;
+    }
+    load_tile_t8(sC, act + tok0 * CC + 2 * DI + GN, CC, CCH, rows, tid, 128);
+    load_tile_t8(sCat + XC * 128 * 8, act + tok0 * CC, CC, XC, rows, tid, 128);
+    load_tile_t8(sX, act + tok0 * CC + DI, CC, XC, rows, tid, 128);
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(sC), bh = smem_u32(sShi), bl = smem_u32(sSlo);
+      const uint32_t idesc = make_idesc_rt(128, DI, false, false);
+#pragma unroll
+      for (int k = 0; k < GN; k += 16) umma(tbase, desc_kmajor(a0, 128, 0, k), desc_kmajor(bh, DI, 0, k), idesc, k > 0);
+#pragma unroll
+      for (int k = 0; k < GN; k += 16) umma(tbase, desc_kmajor(a0, 128, 0, k), desc_kmajor(bl, DI, 0, k), idesc, true);
+      umma_commit(&bar);
+    }
+    bool ok = mbar_wait(&bar, ph);
+    ph ^= 1;
+    tc_fence_after();
+    if (!ok) { if (tid == 0) atomicExch(status, 3); break; }
+    float y[DI];
+#pragma unroll
+    for (int cb = 0; cb < DI; cb += 16) {
+      float v[16], x0[8], x1[8];
+      tmem_ld16(tmem_addr(tbase, warp * 32, cb), v);
+      unpack8(*reinterpret_cast<const uint4*>(sX + ((cb / 8) * 128 + tid) * 8), x0);
+      unpack8(*reinterpret_cast<const uint4*>(sX + ((cb / 8 + 1) * 128 + tid) * 8), x1);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        y[cb + j] = v[j] + sDh[cb + j] * x0[j];
+        y[cb + 8 + j] = v[8 + j] + sDh[cb + 8 + j] * x1[j];
+      }
+    }
+    float mu = 0.f;
+#pragma unroll
+    for (int c = 0; c < DI; ++c) mu += y[c];
+    mu *= (1.f / DI);
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < DI; ++c) { float dlt = y[c] - mu; var = fmaf(dlt, dlt, var); }
+    const float rstd = rsqrtf(var * (1.f / DI) + 1e-5f);
+#pragma unroll
+    for (int cg = 0; cg < XC; ++cg) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (y[cg * 8 + j] - mu) * rstd * sG[cg * 8 + j] + sBt[cg * 8 + j];
+      *reinterpret_cast<uint4*>(sCat + (cg * 128 + tid) * 8) = pack8(v);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(sCat), b0 = smem_u32(sW);
+      const uint32_t idesc = make_idesc_rt(128, D, false, false);
+#pragma unroll
+      for (int k = 0; k < 2 * DI; k += 16) umma(tbase + DI, desc_kmajor(a0, 128, 0, k), desc_kmajor(b0, D, 0, k), idesc, k > 0);
+      umma_commit(&bar);
+    }
+    ok = mbar_wait(&bar, ph);
+    ph ^= 1;
+    tc_fence_after();
+    if (!ok) { if (tid == 0) atomicExch(status, 4); break; }
+#pragma unroll
+    for (int cb = 0; cb < D; cb += 16) {
+      float v[16];
+      tmem_ld16(tmem_addr(tbase, warp * 32, DI + cb), v);
+      tmem_wait_ld();
+      if (tid < rows) {
+        float a[8], bq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a[j] = a1 * v[j]; bq[j] = a1 * v[8 + j]; }
+        bf16* dst = out + (tok0 + tid) * D + cb;
+        *reinterpret_cast<uint4*>(dst) = pack8(a);
+        *reinterpret_cast<uint4*>(dst + 8) = pack8(bq);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, TCOLS);
+}
+
+// Build the bf16 hi / lo images of a per-sample fp32 matrix M[b][j][c] (GN x DI, the state S' or its gradient)
+// as K-major B operands in both orientations:
+//   "a": rows = c (DI), K = j (GN): element (c, j) at ((j/8)*DI + c)*8 + j%8     (used by  X[tok][c] = sum_j A[tok][j] M[j][c])
+//   "b": rows = j (GN), K = c (DI): element (j, c) at ((c/8)*GN + j)*8 + c%8     (used by  X[tok][j] = sum_c A[tok][c] M[j][c])
+template <int DI, int GN>
+__device__ __forceinline__ void stage_state_a(const float* __restrict__ M, bf16* hi, bf16* lo, int tid) {
+  for (int idx = tid; idx < (GN / 8) * DI; idx += 128) {
+    int jc = idx / DI, c = idx % DI;
+    float v[8], l[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      v[q] = M[(jc * 8 + q) * DI + c];
+      l[q] = v[q] - __bfloat162float(__float2bfloat16_rn(v[q]));
+    }
+    *reinterpret_cast<uint4*>(hi + (jc * DI + c) * 8) = pack8(v);
+    *reinterpret_cast<uint4*>(lo + (jc * DI + c) * 8) = pack8(l);
+  }
+}
+template <int DI, int GN>
+__device__ __forceinline__ void stage_state_b(const float* __restrict__ M, bf16* hi, bf16* lo, int tid) {
+  for (int idx = tid; idx < (DI / 8) * GN; idx += 128) {
+    int cc = idx % (DI / 8), j = idx / (DI / 8);
+    float v[8], l[8];
+    const float4 p0 = *reinterpret_cast<const float4*>(M + j * DI + cc * 8);
+    const float4 p1 = *reinterpret_cast<const float4*>(M + j * DI + cc * 8 + 4);
+    v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) l[q] = v[q] - __bfloat162float(__float2bfloat16_rn(v[q]));
+    *reinterpret_cast<uint4*>(hi + (cc * GN + j) * 8) = pack8(v);
+    *reinterpret_cast<uint4*>(lo + (cc * GN + j) * 8) = pack8(l);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_bwd1 (phase B1 of oracle/adnssd_oracle.py::mixer_backward), per 128-token tile:
+//   g   = dout . W_out                      tcgen05, N = 2*DI           (d out / d [LN(y) | zc], without alpha1)
+//   Y   = Cc . S'                           tcgen05 (recompute), then y = Y + D*x, LayerNorm statistics per thread
+//   dy  = LN backward of alpha1*g_y,  dzc = alpha1*g_z                  -> dact[:, x] and dact[:, z]
+//   dCc = dy . S'^T                         tcgen05                     -> dact[:, C]
+//   Rt[j][d] += sum_tok [yhat | zc][tok][j] * dout[tok][d]   tcgen05 reduction over tokens (-> dW_out, dgamma, dbeta, dalpha1)
+//   dS'[c][j] += sum_tok dy[tok][c] * Cc[tok][j]             tcgen05 reduction over tokens (flushed per sample)
+// ------------------------------------------------------------------------------------------------
+template <int DI, int GN>
+__global__ void __launch_bounds__(128)
+k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, const float* __restrict__ S,
+       const float* __restrict__ Dp, const float* __restrict__ gamma, const float* __restrict__ alpha1p,
+       const bf16* __restrict__ Wout, bf16* __restrict__ dact, float* __restrict__ Rt, float* __restrict__ sdout,
+       float* __restrict__ dS, int L, int tiles_per_batch, int num_tiles, int tiles_per_cta, int* __restrict__ status) {
+  constexpr int D = DI / 2, XC = DI / 8, CCH = GN / 8, DC = D / 8;
+  constexpr int COL_Y = 2 * DI, COL_RT = COL_Y + DI, COL_DS = COL_RT + D;
+  constexpr uint32_t TCOLS = (COL_DS + GN) <= 256 ? 256 : 512;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ float sG[DI], sDh[DI];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  bf16* sDout = reinterpret_cast<bf16*>(smem);      // [DC][128][8]
+  bf16* sC = sDout + DC * 128 * 8;                  // [CCH][128][8]
+  bf16* sCat = sC + CCH * 128 * 8;                  // [16][128][8]   [yhat | zc]
+  bf16* sXY = sCat + 16 * 128 * 8;                  // [16][128][8]   x, then dy in place; chunks >= XC stay zero
+  bf16* sWT = sXY + 16 * 128 * 8;                   // [DC][2DI][8]   W_out^T: row j', K = d
+  bf16* sSa_hi = sWT + DC * 2 * DI * 8;             // [CCH][DI][8]
+  bf16* sSa_lo = sSa_hi + CCH * DI * 8;
+  bf16* sSb_hi = sSa_lo + CCH * DI * 8;             // [XC][GN][8]
+  bf16* sSb_lo = sSb_hi + XC * GN * 8;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < DI; i += 128) { sG[i] = gamma[i]; sDh[i] = Dp[head_of_channel(i, 4)]; }
+  for (int i = tid; i < (16 - XC) * 128; i += 128)
+    *reinterpret_cast<uint4*>(sXY + (XC * 128 + i) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < DC * 2 * DI; i += 128) {
+    int dc = i / (2 * DI), j = i % (2 * DI);
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __bfloat162float(Wout[(long long)(dc * 8 + q) * 2 * DI + j]);
+    *reinterpret_cast<uint4*>(sWT + (dc * 2 * DI + j) * 8) = pack8(v);
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  const float a1 = *alpha1p;
+  uint32_t ph = 0;
+  int cur_b = -1;
+  bool rt_fresh = true, ds_fresh = true, ok = true;
+  float sd[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) sd[i] = 0.f;
+  const int tile_begin = blockIdx.x * tiles_per_cta, tile_end = min(num_tiles, tile_begin + tiles_per_cta);
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int b = tile / tiles_per_batch, i = tile % tiles_per_batch;
+    const int rows = min(128, L - i * 128);
+    const long long tok0 = (long long)b * L + (long long)i * 128;
+    if (b != cur_b) {
+      stage_state_a<DI, GN>(S + (long long)b * GN * DI, sSa_hi, sSa_lo, tid);
+      stage_state_b<DI, GN>(S + (long long)b * GN * DI, sSb_hi, sSb_lo, tid);
+      cur_b = b;
+    }
+    load_tile_t8(sDout, dout + tok0 * D, D, DC, rows, tid, 128);
+    load_tile_t8(sC, act + tok0 * CC + 2 * DI + GN, CC, CCH, rows, tid, 128);
+    load_tile_t8(sCat + XC * 128 * 8, act + tok0 * CC, CC, XC, rows, tid, 128);
+    load_tile_t8(sXY, act + tok0 * CC + DI, CC, XC, rows, tid, 128);
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t aD = smem_u32(sDout), bW = smem_u32(sWT), aC = smem_u32(sC), bh = smem_u32(sSa_hi), bl = smem_u32(sSa_lo);
+      const uint32_t id_g = make_idesc_rt(128, 2 * DI, false, false), id_y = make_idesc_rt(128, DI, false, false);
+#pragma unroll
+      for (int k = 0; k < D; k += 16) umma(tbase, desc_kmajor(aD, 128, 0, k), desc_kmajor(bW, 2 * DI, 0, k), id_g, k > 0);
+#pragma unroll
+      for (int k = 0; k < GN; k += 16) umma(tbase + COL_Y, desc_kmajor(aC, 128, 0, k), desc_kmajor(bh, DI, 0, k), id_y, k > 0);
+#pragma unroll
+      for (int k = 0; k < GN; k += 16) umma(tbase + COL_Y, desc_kmajor(aC, 128, 0, k), desc_kmajor(bl, DI, 0, k), id_y, true);
+      umma_commit(&bar);
+    }
+    ok = mbar_wait(&bar, ph);
+    ph ^= 1;
+    tc_fence_after();
+    if (!ok) { if (tid == 0) atomicExch(status, 5); break; }
+    // ---- y, LayerNorm statistics, yhat
+    float y[DI];
+#pragma unroll
+    for (int cb = 0; cb < DI; cb += 16) {
+      float v[16], x0[8], x1[8];
+      tmem_ld16(tmem_addr(tbase, warp * 32, COL_Y + cb), v);
+      unpack8(*reinterpret_cast<const uint4*>(sXY + ((cb / 8) * 128 + tid) * 8), x0);
+      unpack8(*reinterpret_cast<const uint4*>(sXY + ((cb / 8 + 1) * 128 + tid) * 8), x1);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        y[cb + j] = v[j] + sDh[cb + j] * x0[j];
+        y[cb + 8 + j] = v[8 + j] + sDh[cb + 8 + j] * x1[j];
+      }
+    }
+    float mu = 0.f;
+#pragma unroll
+    for (int c = 0; c < DI; ++c) mu += y[c];
+    mu *= (1.f / DI);
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < DI; ++c) { y[c] -= mu; var = fmaf(y[c], y[c], var); }
+    const float rstd = rsqrtf(var * (1.f / DI) + 1e-5f);
+#pragma unroll
+    for (int cg = 0; cg < XC; ++cg) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { y[cg * 8 + j] *= rstd; v[j] = y[cg * 8 + j]; }
+      *reinterpret_cast<uint4*>(sCat + (cg * 128 + tid) * 8) = pack8(v);
+    }
+    // ---- LN backward: dyh = alpha1 * g_y * gamma ; dy = rstd * (dyh - mean(dyh) - yhat * mean(dyh*yhat))
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int cb = 0; cb < DI; cb += 16) {
+      float v[16];
+      tmem_ld16(tmem_addr(tbase, warp * 32, cb), v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float dyh = a1 * v[j] * sG[cb + j];
+        m1 += dyh;
+        m2 = fmaf(dyh, y[cb + j], m2);
+      }
+    }
+    m1 *= (1.f / DI);
+    m2 *= (1.f / DI);
+    bf16* drow = dact + (tok0 + tid) * CC;
+#pragma unroll
+    for (int cb = 0; cb < DI; cb += 16) {
+      float v[16], o0[8], o1[8];
+      tmem_ld16(tmem_addr(tbase, warp * 32, cb), v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o0[j] = rstd * (a1 * v[j] * sG[cb + j] - m1 - y[cb + j] * m2);
+        o1[j] = rstd * (a1 * v[8 + j] * sG[cb + 8 + j] - m1 - y[cb + 8 + j] * m2);
+      }
+      const uint4 p0 = pack8(o0), p1 = pack8(o1);
+      *reinterpret_cast<uint4*>(sXY + ((cb / 8) * 128 + tid) * 8) = p0;
+      *reinterpret_cast<uint4*>(sXY + ((cb / 8 + 1) * 128 + tid) * 8) = p1;
+      if (tid < rows) {
+        *reinterpret_cast<uint4*>(drow + DI + cb) = p0;
+        *reinterpret_cast<uint4*>(drow + DI + cb + 8) = p1;
+      }
+    }
+#pragma unroll
+    for (int cb = 0; cb < DI; cb += 16) {
+      float v[16], o0[8], o1[8];
+      tmem_ld16(tmem_addr(tbase, warp * 32, DI + cb), v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o0[j] = a1 * v[j]; o1[j] = a1 * v[8 + j]; }
+      if (tid < rows) {
+        *reinterpret_cast<uint4*>(drow + cb) = pack8(o0);
+        *reinterpret_cast<uint4*>(drow + cb + 8) = pack8(o1);
+      }
+    }
+#pragma unroll
+    for (int dc = 0; dc < DC; ++dc) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(sDout + (dc * 128 + tid) * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sd[dc * 8 + j] += v[j];
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t aXY = smem_u32(sXY), bh = smem_u32(sSb_hi), bl = smem_u32(sSb_lo), aCat = smem_u32(sCat),
+                     bD = smem_u32(sDout), bC = smem_u32(sC);
+      const uint32_t id_c = make_idesc_rt(128, GN, false, false), id_r = make_idesc_rt(128, D, true, true),
+                     id_s = make_idesc_rt(128, GN, true, true);
+#pragma unroll
+      for (int k = 0; k < DI; k += 16) umma(tbase, desc_kmajor(aXY, 128, 0, k), desc_kmajor(bh, GN, 0, k), id_c, k > 0);
+#pragma unroll
+      for (int k = 0; k < DI; k += 16) umma(tbase, desc_kmajor(aXY, 128, 0, k), desc_kmajor(bl, GN, 0, k), id_c, true);
+#pragma unroll
+      for (int k = 0; k < 128; k += 16)
+        umma(tbase + COL_RT, desc_mnmajor(aCat, 128, 0, k), desc_mnmajor(bD, 128, 0, k), id_r, !rt_fresh || k > 0);
+#pragma unroll
+      for (int k = 0; k < 128; k += 16)
+        umma(tbase + COL_DS, desc_mnmajor(aXY, 128, 0, k), desc_mnmajor(bC, 128, 0, k), id_s, !ds_fresh || k > 0);
+      umma_commit(&bar);
+    }
+    rt_fresh = false;
+    ds_fresh = false;
+    ok = mbar_wait(&bar, ph);
+    ph ^= 1;
+    tc_fence_after();
+    if (!ok) { if (tid == 0) atomicExch(status, 6); break; }
+#pragma unroll
+    for (int cb = 0; cb < GN; cb += 16) {
+      float v[16], o0[8], o1[8];
+      tmem_ld16(tmem_addr(tbase, warp * 32, cb), v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o0[j] = v[j]; o1[j] = v[8 + j]; }
+      if (tid < rows) {
+        *reinterpret_cast<uint4*>(drow + 2 * DI + GN + cb) = pack8(o0);
+        *reinterpret_cast<uint4*>(drow + 2 * DI + GN + cb + 8) = pack8(o1);
+      }
+    }
+    const bool last_of_batch = (tile + 1 == tile_end) || ((tile + 1) / tiles_per_batch != b);
+    if (last_of_batch) {
+      for (int cb = 0; cb < GN; cb += 16) {
+        float v[16];
+        tmem_ld16(tmem_addr(tbase, warp * 32, COL_DS + cb), v);
+        tmem_wait_ld();
+        if (tid < DI) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if ((((cb + j) ^ tid) & 1) == 0) atomicAdd(dS + ((long long)b * GN + cb + j) * DI + tid, v[j]);
+        }
+      }
+      ds_fresh = true;
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (ok && !rt_fresh) {
+    for (int cb = 0; cb < D; cb += 16) {
+      float v[16];
+      tmem_ld16(tmem_addr(tbase, warp * 32, COL_RT + cb), v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) atomicAdd(Rt + tid * D + cb + j, v[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      float v = warp_sum(sd[i]);
+      if ((tid & 31) == 0) atomicAdd(sdout + i, v);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, TCOLS);
+}
+
+// Rt / sdout -> the accumulators the shared finalize kernel expects (raw dW_out, dgamma, dbeta, dalpha1).
+//   dW_out_raw[d][c] = gamma[c]*Rt[c][d] + beta[c]*sd[d]  (c < DI),  Rt[c][d]  (c >= DI)
+//   dgamma[c] = a1 * sum_d W[d][c] Rt[c][d] ;  dbeta[c] = a1 * sum_d W[d][c] sd[d] ;  dalpha1 = sum W .* dW_out_raw
+__global__ void k_bwd1_post(const float* __restrict__ Rt, const float* __restrict__ sdout, const float* __restrict__ Wout,
+                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                            const float* __restrict__ alpha1p, float* __restrict__ dWout, float* __restrict__ dgamma,
+                            float* __restrict__ dbeta, float* __restrict__ dalpha1, int D, int DI) {
+  __shared__ float red[32];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const float a1 = *alpha1p;
+  float da = 0.f;
+  if (c < 2 * DI) {
+    float dg = 0.f, db = 0.f;
+    for (int d = 0; d < D; ++d) {
+      const float r = Rt[c * D + d], wv = Wout[d * 2 * DI + c];
+      float raw;
+      if (c < DI) {
+        raw = gamma[c] * r + beta[c] * sdout[d];
+        dg = fmaf(wv, r, dg);
+        db = fmaf(wv, sdout[d], db);
+      } else {
+        raw = r;
+      }
+      dWout[d * 2 * DI + c] = raw;
+      da = fmaf(wv, raw, da);
+    }
+    if (c < DI) { dgamma[c] = a1 * dg; dbeta[c] = a1 * db; }
+  }
+  da = warp_sum(da);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = da;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    atomicAdd(dalpha1, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_bwd2 (phase B2), per 128-token tile, after dS' is complete:
+//   G   = Bc . dS'                          tcgen05
+//   dxc = D*dy + w*G (in place over dy), wx = w*x, dw[h] = sum_{c in h} x*G, ddt = dw*exp(A_log)*sigmoid(dt+bias)
+//   dBc = wx . dS'^T                        tcgen05
+//   per-head parameter gradients dD, dA_log, ddt_bias accumulate per thread and are reduced once per CTA.
+// ------------------------------------------------------------------------------------------------
+template <int DI, int GN>
+__global__ void __launch_bounds__(128)
+k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int CC, const float* __restrict__ dS,
+       const float* __restrict__ dt_bias, const float* __restrict__ A_log, const float* __restrict__ Dp,
+       bf16* __restrict__ dact, bf16* __restrict__ draw, float* __restrict__ dD, float* __restrict__ dAlog,
+       float* __restrict__ ddtb, int L, int tiles_per_batch, int num_tiles, int tiles_per_cta, int* __restrict__ status) {
+  constexpr int XC = DI / 8, BC = GN / 8, DC = DI / 32, NH = DI / 4;
+  constexpr uint32_t TCOLS = (DI + GN) <= 128 ? 128 : 256;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ float s_bias[NH], s_eA[NH], s_D[NH];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  bf16* sB = reinterpret_cast<bf16*>(smem);      // [BC][128][8]
+  bf16* sX = sB + BC * 128 * 8;                  // [XC][128][8]  x, then w*x in place
+  bf16* sDy = sX + XC * 128 * 8;                 // [XC][128][8]
+  bf16* sDt = sDy + XC * 128 * 8;                // [DC][128][8]
+  bf16* sTa_hi = sDt + DC * 128 * 8;             // [BC][DI][8]
+  bf16* sTa_lo = sTa_hi + BC * DI * 8;
+  bf16* sTb_hi = sTa_lo + BC * DI * 8;           // [XC][GN][8]
+  bf16* sTb_lo = sTb_hi + XC * GN * 8;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < NH; i += 128) { s_bias[i] = dt_bias[i]; s_eA[i] = __expf(A_log[i]); s_D[i] = Dp[i]; }
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  uint32_t ph = 0;
+  int cur_b = -1;
+  bool ok = true;
+  float aD[NH], aA[NH], aB[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) { aD[h] = 0.f; aA[h] = 0.f; aB[h] = 0.f; }
+  const int tile_begin = blockIdx.x * tiles_per_cta, tile_end = min(num_tiles, tile_begin + tiles_per_cta);
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int b = tile / tiles_per_batch, i = tile % tiles_per_batch;
+    const int rows = min(128, L - i * 128);
+    const long long tok0 = (long long)b * L + (long long)i * 128;
+    if (b != cur_b) {
+      stage_state_a<DI, GN>(dS + (long long)b * GN * DI, sTa_hi, sTa_lo, tid);
+      stage_state_b<DI, GN>(dS + (long long)b * GN * DI, sTb_hi, sTb_lo, tid);
+      cur_b = b;
+    }
+    load_tile_t8(sB, act + tok0 * CC + 2 * DI, CC, BC, rows, tid, 128);
+    load_tile_t8(sX, act + tok0 * CC + DI, CC, XC, rows, tid, 128);
+    load_tile_t8(sDy, dact + tok0 * CC + DI, CC, XC, rows, tid, 128);
+    load_tile_t8(sDt, raw + tok0 * ldr + CC, ldr, DC, rows, tid, 128);
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t aB_ = smem_u32(sB), bh = smem_u32(sTa_hi), bl = smem_u32(sTa_lo);
+      const uint32_t idesc = make_idesc_rt(128, DI, false, false);
+#pragma unroll
+      for (int k = 0; k < GN; k += 16) umma(tbase, desc_kmajor(aB_, 128, 0, k), desc_kmajor(bh, DI, 0, k), idesc, k > 0);
+#pragma unroll
+      for (int k = 0; k < GN; k += 16) umma(tbase, desc_kmajor(aB_, 128, 0, k), desc_kmajor(bl, DI, 0, k), idesc, true);
+      umma_commit(&bar);
+    }
+    // decay weights while the MMA runs
+    float w[NH], sg[NH];
+#pragma unroll
+    for (int dc = 0; dc < DC; ++dc) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(sDt + (dc * 128 + tid) * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = v[j] + s_bias[dc * 8 + j];
+        w[dc * 8 + j] = softplusf_(a) * s_eA[dc * 8 + j];
+        sg[dc * 8 + j] = a > 20.f ? 1.f : __fdividef(1.f, 1.f + __expf(-a));
+      }
+    }
+    ok = mbar_wait(&bar, ph);
+    ph ^= 1;
+    tc_fence_after();
+    if (!ok) { if (tid == 0) atomicExch(status, 7); break; }
+    float dw[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) dw[h] = 0.f;
+    bf16* drow = dact + (tok0 + tid) * CC;
+    const bool valid = tid < rows;
+#pragma unroll
+    for (int cb = 0; cb < DI; cb += 16) {
+      float G[16];
+      tmem_ld16(tmem_addr(tbase, warp * 32, cb), G);
+      tmem_wait_ld();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int cg = cb / 8 + half;
+        float x[8], dy[8], o[8], wx[8];
+        unpack8(*reinterpret_cast<const uint4*>(sX + (cg * 128 + tid) * 8), x);
+        unpack8(*reinterpret_cast<const uint4*>(sDy + (cg * 128 + tid) * 8), dy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int h = 2 * cg + (j & 1);
+          const float g = G[half * 8 + j];
+          o[j] = s_D[h] * dy[j] + w[h] * g;
+          wx[j] = w[h] * x[j];
+          dw[h] = fmaf(x[j], g, dw[h]);
+          if (valid) aD[h] = fmaf(dy[j], x[j], aD[h]);
+        }
+        *reinterpret_cast<uint4*>(sX + (cg * 128 + tid) * 8) = pack8(wx);
+        if (valid) *reinterpret_cast<uint4*>(drow + DI + cg * 8) = pack8(o);
+      }
+    }
+    {
+      bf16* trow = draw + (tok0 + tid) * ldr + CC;
+#pragma unroll
+      for (int dc = 0; dc < DC; ++dc) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int h = dc * 8 + j;
+          o[j] = dw[h] * s_eA[h] * sg[h];
+          if (valid) { aA[h] = fmaf(dw[h], w[h], aA[h]); aB[h] += o[j]; }
+        }
+        if (valid) *reinterpret_cast<uint4*>(trow + dc * 8) = pack8(o);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t aX = smem_u32(sX), bh = smem_u32(sTb_hi), bl = smem_u32(sTb_lo);
+      const uint32_t idesc = make_idesc_rt(128, GN, false, false);
+#pragma unroll
+      for (int k = 0; k < DI; k += 16) umma(tbase + DI, desc_kmajor(aX, 128, 0, k), desc_kmajor(bh, GN, 0, k), idesc, k > 0);
+#pragma unroll
+      for (int k = 0; k < DI; k += 16) umma(tbase + DI, desc_kmajor(aX, 128, 0, k), desc_kmajor(bl, GN, 0, k), idesc, true);
+      umma_commit(&bar);
+    }
+    ok = mbar_wait(&bar, ph);
+    ph ^= 1;
+    tc_fence_after();
+    if (!ok) { if (tid == 0) atomicExch(status, 8); break; }
+#pragma unroll
+    for (int cb = 0; cb < GN; cb += 16) {
+      float v[16], o0[8], o1[8];
+      tmem_ld16(tmem_addr(tbase, warp * 32, DI + cb), v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o0[j] = v[j]; o1[j] = v[8 + j]; }
+      if (valid) {
+        *reinterpret_cast<uint4*>(drow + 2 * DI + cb) = pack8(o0);
+        *reinterpret_cast<uint4*>(drow + 2 * DI + cb + 8) = pack8(o1);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    const float vD = warp_sum(aD[h]), vA = warp_sum(aA[h]), vB = warp_sum(aB[h]);
+    if ((tid & 31) == 0) { atomicAdd(dD + h, vD); atomicAdd(dAlog + h, vA); atomicAdd(ddtb + h, vB); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, TCOLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_bwd4 (in_proj backward), per 128-token tile:
+//   du = draw . W_in                        tcgen05 (hi + lo weights), K = dip
+//   dW_in[j][d] += sum_tok draw[tok][j] * u[tok][d]      tcgen05 reduction over tokens, M blocks of 128 rows j
+// ------------------------------------------------------------------------------------------------
+template <int D, int MB>
+__global__ void __launch_bounds__(128)
+k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__ u, const bf16* __restrict__ Whi,
+       const bf16* __restrict__ Wlo, bf16* __restrict__ du, float* __restrict__ dWin, long long T, int num_tiles,
+       int tiles_per_cta, int* __restrict__ status) {
+  constexpr int DC = D / 8;
+  constexpr uint32_t TCOLS = (D + MB * D) <= 128 ? 128 : 256;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int JC = dip / 8;                          // real 8-channel chunks of draw
+  bf16* sDraw = reinterpret_cast<bf16*>(smem);     // [16*MB][128][8], chunks >= JC stay zero
+  bf16* sU = sDraw + 16 * MB * 128 * 8;            // [DC][128][8]
+  bf16* sWhi = sU + DC * 128 * 8;                  // [JC][D][8]   W_in^T: row d, K = j
+  bf16* sWlo = sWhi + 16 * MB * D * 8;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (16 * MB - JC) * 128; i += 128)
+    *reinterpret_cast<uint4*>(sDraw + (JC * 128 + i) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < JC * D; i += 128) {
+    int jc = i / D, d = i % D;
+    float h[8], l[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      h[q] = __bfloat162float(Whi[(long long)(jc * 8 + q) * D + d]);
+      l[q] = __bfloat162float(Wlo[(long long)(jc * 8 + q) * D + d]);
+    }
+    *reinterpret_cast<uint4*>(sWhi + (jc * D + d) * 8) = pack8(h);
+    *reinterpret_cast<uint4*>(sWlo + (jc * D + d) * 8) = pack8(l);
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  uint32_t ph = 0;
+  bool fresh = true, ok = true;
+  const int tile_begin = blockIdx.x * tiles_per_cta, tile_end = min(num_tiles, tile_begin + tiles_per_cta);
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const long long tok0 = (long long)tile * 128;
+    const int rows = (int)min((long long)128, T - tok0);
+    load_tile_t8(sDraw, draw + tok0 * ldr, ldr, JC, rows, tid, 128);
+    load_tile_t8(sU, u + tok0 * D, D, DC, rows, tid, 128);
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t aR = smem_u32(sDraw), bh = smem_u32(sWhi), bl = smem_u32(sWlo), bU = smem_u32(sU);
+      const uint32_t id_u = make_idesc_rt(128, D, false, false), id_w = make_idesc_rt(128, D, true, true);
+      for (int k = 0; k < dip; k += 16) umma(tbase, desc_kmajor(aR, 128, 0, k), desc_kmajor(bh, D, 0, k), id_u, k > 0);
+      for (int k = 0; k < dip; k += 16) umma(tbase, desc_kmajor(aR, 128, 0, k), desc_kmajor(bl, D, 0, k), id_u, true);
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+        for (int k = 0; k < 128; k += 16)
+          umma(tbase + D + mb * D, desc_mnmajor(aR, 128, mb * 128, k), desc_mnmajor(bU, 128, 0, k), id_w, !fresh || k > 0);
+      umma_commit(&bar);
+    }
+    fresh = false;
+    ok = mbar_wait(&bar, ph);
+    ph ^= 1;
+    tc_fence_after();
+    if (!ok) { if (tid == 0) atomicExch(status, 9); break; }
+#pragma unroll
+    for (int cb = 0; cb < D; cb += 16) {
+      float v[16], o0[8], o1[8];
+      tmem_ld16(tmem_addr(tbase, warp * 32, cb), v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o0[j] = v[j]; o1[j] = v[8 + j]; }
+      if (tid < rows) {
+        bf16* dst = du + (tok0 + tid) * D + cb;
+        *reinterpret_cast<uint4*>(dst) = pack8(o0);
+        *reinterpret_cast<uint4*>(dst + 8) = pack8(o1);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (ok && !fresh) {
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) {
+      const int j = mb * 128 + tid;
+#pragma unroll
+      for (int cb = 0; cb < D; cb += 16) {
+        float v[16];
+        tmem_ld16(tmem_addr(tbase, warp * 32, D + mb * D + cb), v);
+        tmem_wait_ld();
+        if (j < dip) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) atomicAdd(dWin + (long long)j * D + cb + q, v[q]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, TCOLS);
+}
+
+__global__ void k_to_bf16(const float* __restrict__ w, bf16* __restrict__ o, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = __float2bfloat16_rn(w[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct FastWs {           // placed after the generic workspace of the same pass
+  bf16 *Whi, *Wlo, *Wout;
+  float *Rt, *sdout;     // k_bwd1 accumulators: Rt[2Di][D], sdout[D] (contiguous, zeroed together)
+  int* status;
+  size_t bytes;
+  FastWs(const MixerDims& d, void* p) {
+    Carver c(p);
+    Whi = c.take<bf16>((size_t)d.dip * d.D);
+    Wlo = c.take<bf16>((size_t)d.dip * d.D);
+    Wout = c.take<bf16>((size_t)d.D * 2 * d.Di);
+    Rt = c.take<float>((size_t)2 * d.Di * d.D + d.D);
+    sdout = Rt ? Rt + (size_t)2 * d.Di * d.D : nullptr;
+    status = c.take<int>(64);
+    bytes = c.off;
+  }
+};
+
+bool sm100_supported(const MixerDims& d) {
+  // instantiated tile shapes: d_model 32 (d_inner 64), headdim 4, ngroups*d_state in {32, 128}
+  return d.D == 32 && d.Di == 64 && d.P == 4 && (d.GN == 32 || d.GN == 128) && d.dip % 16 == 0 && d.ldr == d.dip;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  ADN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return ADN_OK;
+}
+
+template <int DI, int GN>
+static int launch_state(const MixerDims& d, const bf16* act, const bf16* raw, const AdnWeights& w, float* S, int* status,
+                        cudaStream_t st) {
+  constexpr size_t smem = 2 * (size_t)(16 + GN / 8 + DI / 32) * 128 * 8 * sizeof(bf16);
+  int rc = set_smem(k_state<DI, GN>, smem);
+  if (rc) return rc;
+  const int tpb = cdiv(d.L, 128);
+  const int cpb = max(1, min(tpb, cdiv(148 * 2, d.B)));
+  { ADN_KERNEL("k_state", st); k_state<DI, GN><<<d.B * cpb, 128, smem, st>>>(act, raw, d.ldr, d.CC, w.dt_bias, w.A_log, S, d.L, tpb, cpb, status); }
+  return ADN_OK;
+}
+
+template <int DI, int GN>
+static int launch_readout(const MixerDims& d, const bf16* act, const float* S, const AdnWeights& w, const bf16* Wout,
+                          bf16* out, int* status, cudaStream_t st) {
+  constexpr size_t smem = ((size_t)(GN / 8 + 2 * DI / 8 + DI / 8) * 128 * 8 + 2 * (GN / 8) * DI * 8 + (2 * DI / 8) * (DI / 2) * 8) * sizeof(bf16);
+  int rc = set_smem(k_readout<DI, GN>, smem);
+  if (rc) return rc;
+  const int tpb = cdiv(d.L, 128), nt = tpb * d.B;
+  const int per_sm = smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3);
+  { ADN_KERNEL("k_readout", st); k_readout<DI, GN><<<min(nt, 148 * per_sm), 128, smem, st>>>(act, d.CC, S, w.D, w.norm_w, w.norm_b, w.alpha1, Wout, out, d.L, tpb, nt, status); }
+  return ADN_OK;
+}
+
+void sm100_workspace_bytes(const MixerDims& d, size_t* f, size_t* b) {
+  size_t extra = FastWs(d, nullptr).bytes;
+  *f = FwdWs<bf16, TWf>(d, nullptr).bytes + extra;
+  *b = BwdWs<bf16, TWf>(d, nullptr).bytes + extra;
+}
+
+template <int D>
+static int launch_inproj(const MixerDims& d, const bf16* u, const FastWs& F, bf16* raw, cudaStream_t st) {
+  const int num_tiles = cdiv(d.T, 128);
+  const size_t smem = (size_t)(2 * 256 * D + 2 * 128 * D) * sizeof(bf16);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADN_CHECK_CUDA(cudaFuncSetAttribute(k_inproj<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int grid = min(num_tiles, 148 * 2);
+  { ADN_KERNEL("k_inproj", st); k_inproj<D><<<grid, 128, smem, st>>>(u, F.Whi, F.Wlo, raw, d.ldr, d.dip, d.T, num_tiles, F.status); }
+  return ADN_OK;
+}
+
+static inline void split_tiles(int num_tiles, int per_sm, int* grid, int* per_cta) {
+  const int target = max(1, min(num_tiles, 148 * per_sm));
+  *per_cta = cdiv(num_tiles, target);
+  *grid = cdiv(num_tiles, *per_cta);
+}
+
+template <int DI, int GN>
+static int launch_bwd1(const MixerDims& d, const bf16* dout, const bf16* act, const float* S, const AdnWeights& w,
+                       const FastWs& F, bf16* dact, float* dS, cudaStream_t st) {
+  constexpr int D = DI / 2;
+  constexpr size_t smem = ((size_t)(D / 8 + GN / 8 + 32) * 128 * 8 + (D / 8) * 2 * DI * 8 + 2 * (GN / 8) * DI * 8 + 2 * (DI / 8) * GN * 8) * sizeof(bf16);
+  int rc = set_smem(k_bwd1<DI, GN>, smem);
+  if (rc) return rc;
+  const int tpb = cdiv(d.L, 128), nt = tpb * d.B;
+  int grid, per;
+  split_tiles(nt, smem > 110 * 1024 ? 1 : 2, &grid, &per);
+  { ADN_KERNEL("k_bwd1", st); k_bwd1<DI, GN><<<grid, 128, smem, st>>>(dout, act, d.CC, S, w.D, w.norm_w, w.alpha1, F.Wout, dact, F.Rt, F.sdout, dS, d.L, tpb, nt, per, F.status); }
+  return ADN_OK;
+}
+
+template <int DI, int GN>
+static int launch_bwd2(const MixerDims& d, const bf16* act, const bf16* raw, const float* dS, const AdnWeights& w,
+                       const FastWs& F, bf16* dact, bf16* draw, const GradAcc& acc, cudaStream_t st) {
+  constexpr size_t smem = ((size_t)(GN / 8 + 2 * (DI / 8) + DI / 32) * 128 * 8 + 2 * (GN / 8) * DI * 8 + 2 * (DI / 8) * GN * 8) * sizeof(bf16);
+  int rc = set_smem(k_bwd2<DI, GN>, smem);
+  if (rc) return rc;
+  const int tpb = cdiv(d.L, 128), nt = tpb * d.B;
+  int grid, per;
+  split_tiles(nt, smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3), &grid, &per);
+  { ADN_KERNEL("k_bwd2", st); k_bwd2<DI, GN><<<grid, 128, smem, st>>>(act, raw, d.ldr, d.CC, dS, w.dt_bias, w.A_log, w.D, dact, draw, acc.dD, acc.dAlog, acc.ddtb, d.L, tpb, nt, per, F.status); }
+  return ADN_OK;
+}
+
+template <int D, int MB>
+static int launch_bwd4(const MixerDims& d, const bf16* draw, const bf16* u, const FastWs& F, bf16* du, float* dWin,
+                       cudaStream_t st) {
+  constexpr size_t smem = ((size_t)(16 * MB + D / 8) * 128 * 8 + 2 * 16 * MB * D * 8) * sizeof(bf16);
+  int rc = set_smem(k_bwd4<D, MB>, smem);
+  if (rc) return rc;
+  const int nt = cdiv(d.T, 128);
+  int grid, per;
+  split_tiles(nt, smem > 110 * 1024 ? 1 : 2, &grid, &per);
+  { ADN_KERNEL("k_bwd4", st); k_bwd4<D, MB><<<grid, 128, smem, st>>>(draw, d.ldr, d.dip, u, F.Whi, F.Wlo, du, dWin, d.T, nt, per, F.status); }
+  return ADN_OK;
+}
+
+int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* out, void* saved, void* ws,
+                  cudaStream_t st) {
+  typedef bf16 T;
+  FwdWs<T, TWf> W(d, ws);
+  FastWs F(d, (char*)ws + W.bytes);
+  SavedBufs<T> S = saved ? SavedBufs<T>(d, saved) : W.tmp;
+  const bool training = saved != nullptr;
+  const long long Tt = d.T;
+  { ADN_KERNEL("k_assemble_conv", st); k_assemble_conv<<<cdiv(d.CC, 128), 128, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC); }
+  ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
+  { ADN_KERNEL("k_prep_split", st); k_prep_split<<<cdiv((long long)d.dip * d.D, 256), 256, 0, st>>>(w.in_proj_w, F.Whi, F.Wlo, (long long)d.dip * d.D); }
+  // (1) in_proj on tcgen05
+  int rc = d.D == 16 ? launch_inproj<16>(d, u, F, S.raw, st) : d.D == 32 ? launch_inproj<32>(d, u, F, S.raw, st)
+                                                                         : launch_inproj<64>(d, u, F, S.raw, st);
+  if (rc) return rc;
+  // (2) depthwise 3x3 + SiLU
+  {
+    dim3 grid(cdiv((long long)d.W * (d.CC / 8), 128), cdiv(d.H, ROWS8), d.B);
+    { ADN_KERNEL("k_conv_fwd8", st); k_conv_fwd8<<<grid, 128, 0, st>>>(S.raw, d.ldr, W.Kc, training ? S.pre : nullptr, S.act, d.H, d.W, d.CC); }
+  }
+  (void)Tt;
+  // (4a) state on tcgen05 (reduction over tokens), (4b)+(5) readout + LayerNorm + out_proj on tcgen05
+  ADN_CHECK_CUDA(cudaMemsetAsync(S.S, 0, (size_t)d.B * d.GN * d.Di * sizeof(float), st));
+  { ADN_KERNEL("k_to_bf16", st); k_to_bf16<<<cdiv((long long)d.D * 2 * d.Di, 256), 256, 0, st>>>(w.out_proj_w, F.Wout, (long long)d.D * 2 * d.Di); }
+  rc = d.GN == 32 ? launch_state<64, 32>(d, S.act, S.raw, w, S.S, F.status, st) : launch_state<64, 128>(d, S.act, S.raw, w, S.S, F.status, st);
+  if (rc) return rc;
+  rc = d.GN == 32 ? launch_readout<64, 32>(d, S.act, S.S, w, F.Wout, out, F.status, st)
+                  : launch_readout<64, 128>(d, S.act, S.S, w, F.Wout, out, F.status, st);
+  if (rc) return rc;
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
+int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const void* saved, const bf16* dout,
+                   bf16* du, const AdnWeightGrads& g, void* ws, cudaStream_t st) {
+  typedef bf16 T;
+  BwdWs<T, TWf> W(d, ws);
+  FastWs F(d, (char*)ws + W.bytes);
+  SavedBufs<T> S(d, const_cast<void*>(saved));
+  ADN_CHECK_CUDA(cudaMemsetAsync(W.zero_begin, 0, W.zero_bytes, st));
+  ADN_CHECK_CUDA(cudaMemsetAsync(F.Rt, 0, ((size_t)2 * d.Di * d.D + d.D) * sizeof(float), st));
+  ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
+  { ADN_KERNEL("k_assemble_conv", st); k_assemble_conv<<<cdiv(d.CC, 128), 128, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC); }
+  { ADN_KERNEL("k_prep_split", st); k_prep_split<<<cdiv((long long)d.dip * d.D, 256), 256, 0, st>>>(w.in_proj_w, F.Whi, F.Wlo, (long long)d.dip * d.D); }
+  { ADN_KERNEL("k_to_bf16", st); k_to_bf16<<<cdiv((long long)d.D * 2 * d.Di, 256), 256, 0, st>>>(w.out_proj_w, F.Wout, (long long)d.D * 2 * d.Di); }
+  // ---- phase B1: dout -> dy, dzc, dCc ; reductions Rt, dS'
+  int rc = d.GN == 32 ? launch_bwd1<64, 32>(d, dout, S.act, S.S, w, F, W.dact, W.dS, st)
+                      : launch_bwd1<64, 128>(d, dout, S.act, S.S, w, F, W.dact, W.dS, st);
+  if (rc) return rc;
+  { ADN_KERNEL("k_bwd1_post", st); k_bwd1_post<<<cdiv(2 * d.Di, 128), 128, 0, st>>>(F.Rt, F.sdout, w.out_proj_w, w.norm_w, w.norm_b, w.alpha1, W.acc.dWout, W.acc.dgamma, W.acc.dbeta, W.acc.dalpha1, d.D, d.Di); }
+  // ---- phase B2: dS' -> dxc, dBc, ddt
+  rc = d.GN == 32 ? launch_bwd2<64, 32>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st)
+                  : launch_bwd2<64, 128>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st);
+  if (rc) return rc;
+  // ---- conv backward
+  {
+    const int bpb = 4;
+    dim3 grid(cdiv((long long)d.W * (d.CC / 4), 192), cdiv(d.H, ROWS8), cdiv(d.B, bpb));
+    { ADN_KERNEL("k_conv_bwd4", st); k_conv_bwd4<TWf><<<grid, 192, d.CC * 9 * sizeof(float), st>>>(W.dact, S.pre, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.B, d.H, d.W, d.CC, bpb); }
+  }
+  // ---- in_proj backward
+  rc = d.dip <= 128 ? launch_bwd4<32, 1>(d, W.draw, u, F, du, W.acc.dWin, st)
+       : d.dip <= 256 ? launch_bwd4<32, 2>(d, W.draw, u, F, du, W.acc.dWin, st)
+                      : launch_bwd4<32, 4>(d, W.draw, u, F, du, W.acc.dWin, st);
+  if (rc) return rc;
+  { ADN_KERNEL("k_finalize", st); k_finalize<<<148, 256, 0, st>>>(W.acc, w, g, d.D, d.Di, d.GN, d.nh, d.dip); }
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
 }  // namespace adn
 
 extern "C" int adn_selftest_umma(int mode, int N, int K, const void* A, const void* B, float* C, int* status, void* stream) {
