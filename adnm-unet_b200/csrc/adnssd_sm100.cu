@@ -215,6 +215,20 @@ __device__ __forceinline__ float silu_grad_fast(float x) {
 
 __device__ __forceinline__ uint4 ldg16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
+// bf16x8 (one 16-byte vector) -> four float2
+__device__ __forceinline__ void unpack8_f2(const uint4& u, float2 (&v)[4]) {
+  v[0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+  v[1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+  v[2] = make_float2(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u));
+  v[3] = make_float2(__uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
+}
+__device__ __forceinline__ uint4 pack8_f2(const float2 (&v)[4]) {
+  return make_uint4(pack_bf16(v[0].x, v[0].y), pack_bf16(v[1].x, v[1].y), pack_bf16(v[2].x, v[2].y), pack_bf16(v[3].x, v[3].y));
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+// The 3x3 window lives in registers as fp32 pairs (unpacked once per load); rows rotate through three slots by
+// unrolling the row loop by 3, and the 9 taps x 8 channels are 36 packed FFMA2 (fma.rn.f32x2) per output row.
 __global__ void __launch_bounds__(128)
 k_conv_fwd8(const bf16* __restrict__ raw, int ldr, const float* __restrict__ Kc, bf16* __restrict__ pre,
             bf16* __restrict__ act, int H, int W, int CC) {
@@ -223,47 +237,153 @@ k_conv_fwd8(const bf16* __restrict__ raw, int ldr, const float* __restrict__ Kc,
   if (idx >= W * CG) return;
   const int x = idx / CG, cg = idx % CG, c0 = cg * 8;
   const int b = blockIdx.z, y0 = blockIdx.y * ROWS8, y1 = min(H, y0 + ROWS8);
-  float k[9][8];
+  float2 k2[9][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int t = 0; t < 9; ++t) k[t][i] = __ldg(Kc + (c0 + i) * 9 + t);
+    for (int p = 0; p < 4; ++p) k2[t][p] = make_float2(__ldg(Kc + (c0 + 2 * p) * 9 + t), __ldg(Kc + (c0 + 2 * p + 1) * 9 + t));
   const bf16* src = raw + (long long)b * H * W * ldr + c0;
-  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
   const bool xl = x > 0, xr = x + 1 < W;
-  uint4 win[3][3];
-  auto load_row = [&](int y, uint4 (&r)[3]) {
+  float2 win[3][3][4];
+  auto load_row = [&](int y, float2 (&r)[3][4]) {
     if (y >= 0 && y < H) {
       const bf16* p = src + ((long long)y * W + x) * ldr;
-      r[0] = xl ? ldg16(p - ldr) : zero;
-      r[1] = ldg16(p);
-      r[2] = xr ? ldg16(p + ldr) : zero;
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      unpack8_f2(xl ? ldg16(p - ldr) : zero, r[0]);
+      unpack8_f2(ldg16(p), r[1]);
+      unpack8_f2(xr ? ldg16(p + ldr) : zero, r[2]);
     } else {
-      r[0] = r[1] = r[2] = zero;
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[s][q] = make_float2(0.f, 0.f);
     }
   };
   load_row(y0 - 1, win[0]);
   load_row(y0, win[1]);
-  for (int y = y0; y < y1; ++y) {
-    load_row(y + 1, win[2]);
-    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int yb = y0; yb < y1; yb += 3) {
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int ph = 0; ph < 3; ++ph) {
+      const int y = yb + ph;
+      if (y < y1) {
+        load_row(y + 1, win[(ph + 2) % 3]);
+        float2 a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q] = __ffma2_rn(k2[r * 3 + s][q], win[(ph + r) % 3][s][q], a[q]);
+        const long long off = (((long long)b * H + y) * W + x) * CC + c0;
+        if (pre) *reinterpret_cast<uint4*>(pre + off) = pack8_f2(a);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { a[q].x *= sigmoid_fast(a[q].x); a[q].y *= sigmoid_fast(a[q].y); }
+        *reinterpret_cast<uint4*>(act + off) = pack8_f2(a);
+      }
+    }
+  }
+}
+
+// dact <- dact * silu'(pre), in place, 8 elements per thread
+__global__ void __launch_bounds__(256)
+k_dpre(bf16* __restrict__ dact, const bf16* __restrict__ pre, long long n8) {
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n8) return;
+  float g[8], p[8];
+  unpack8(*reinterpret_cast<const uint4*>(dact + i * 8), g);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(pre + i * 8)), p);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float sgm = sigmoid_fast(p[j]);
+    g[j] *= sgm * (1.f + p[j] * (1.f - sgm));
+  }
+  *reinterpret_cast<uint4*>(dact + i * 8) = pack8(g);
+}
+
+// conv backward on dpre (= dact * silu'(pre), already applied): draw[:, :CC] = convT(dpre), dK += raw (x) dpre.
+// 4 channels per thread (two float2 lanes), full image column per thread (no halo recomputation), one sample per
+// blockIdx.y.  Block = 192 consecutive (column, channel-quad) pairs = 4 whole tokens when CC/4 == 48.
+__global__ void __launch_bounds__(192)
+k_conv_bwd_dpre(const bf16* __restrict__ dpre, const bf16* __restrict__ raw, int ldr, const float* __restrict__ Kc,
+                bf16* __restrict__ draw, float* __restrict__ dK, int H, int W, int CC, int rows_per_block) {
+  extern __shared__ float red[];   // [CC*9]
+  const int CG = CC >> 2;
+  for (int i = threadIdx.x; i < CC * 9; i += 192) red[i] = 0.f;
+  __syncthreads();
+  const int idx = blockIdx.x * 192 + threadIdx.x;
+  const bool active = idx < W * CG;
+  const int x = active ? idx / CG : 0, cg = active ? idx % CG : 0, c0 = cg * 4;
+  const int b = blockIdx.y;
+  const int y0 = blockIdx.z * rows_per_block, y1 = min(H, y0 + rows_per_block);
+  if (active) {
+    float2 k2[9][2], dk[9][2];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        k2[t][p] = make_float2(__ldg(Kc + (c0 + 2 * p) * 9 + t), __ldg(Kc + (c0 + 2 * p + 1) * 9 + t));
+        dk[t][p] = make_float2(0.f, 0.f);
+      }
+    const long long boff = (long long)b * H * W;
+    const bf16* g = dpre + boff * CC + c0;
+    const bool xl = x > 0, xr = x + 1 < W;
+    float2 win[3][3][2];
+    auto ld = [&](const bf16* p, float2 (&v)[2]) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+      v[0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+      v[1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+    };
+    auto load_row = [&](int y, float2 (&r)[3][2]) {
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
-        float v[8];
-        unpack8(win[r][s], v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = fmaf(k[r * 3 + s][i], v[i], a[i]);
+        const bool okp = y >= 0 && y < H && (s == 1 || (s == 0 ? xl : xr));
+        if (okp) ld(g + ((long long)y * W + x + s - 1) * CC, r[s]);
+        else { r[s][0] = make_float2(0.f, 0.f); r[s][1] = make_float2(0.f, 0.f); }
       }
-    const long long off = (((long long)b * H + y) * W + x) * CC + c0;
-    if (pre) *reinterpret_cast<uint4*>(pre + off) = pack8(a);
+    };
+    load_row(y0 - 1, win[0]);
+    load_row(y0, win[1]);
+    for (int yb = y0; yb < y1; yb += 3) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = silu_fast(a[i]);
-    *reinterpret_cast<uint4*>(act + off) = pack8(a);
+      for (int ph = 0; ph < 3; ++ph) {
+        const int y = yb + ph;
+        if (y < y1) {
+          load_row(y + 1, win[(ph + 2) % 3]);
+          const long long tok = boff + (long long)y * W + x;
+          float2 rc[2], o[2];
+          ld(raw + tok * ldr + c0, rc);
+          o[0] = make_float2(0.f, 0.f); o[1] = make_float2(0.f, 0.f);
+          // draw[y,x] = sum_ab K[a][b] * dpre[y-a+1][x-b+1] ; dK[a][b] += raw[y,x] * dpre[y-a+1][x-b+1]
 #pragma unroll
-    for (int s = 0; s < 3; ++s) { win[0][s] = win[1][s]; win[1][s] = win[2][s]; }
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+              for (int p = 0; p < 2; ++p) {
+                const float2 dv = win[(ph + 2 - a) % 3][2 - bb][p];
+                o[p] = __ffma2_rn(k2[a * 3 + bb][p], dv, o[p]);
+                dk[a * 3 + bb][p] = __ffma2_rn(rc[p], dv, dk[a * 3 + bb][p]);
+              }
+          uint2 ov;
+          ov.x = pack_bf16(o[0].x, o[0].y);
+          ov.y = pack_bf16(o[1].x, o[1].y);
+          *reinterpret_cast<uint2*>(draw + tok * ldr + c0) = ov;
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        atomicAdd(&red[(c0 + 2 * p) * 9 + t], dk[t][p].x);
+        atomicAdd(&red[(c0 + 2 * p + 1) * 9 + t], dk[t][p].y);
+      }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CC * 9; i += 192)
+    if (red[i] != 0.f) atomicAdd(dK + i, red[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1197,6 +1317,200 @@ __global__ void k_to_bf16(const float* __restrict__ w, bf16* __restrict__ o, lon
 }
 
 // ------------------------------------------------------------------------------------------------
+// Shared-memory halo-tiled depthwise 3x3 (channels-last bf16).  One CTA = one sample, one 32-channel slab, one
+// CT_Y x CT_X spatial tile.  The (CT_Y+2) x (CT_X+2) x 32-channel halo tile is fetched with 16-byte cp.async
+// (all requests in flight at once: the memory-level parallelism the register-window kernels lacked), zero-filled
+// outside the image.  Thread = (column, 8-channel chunk); it walks down its column with an fp32 register window fed
+// by conflict-free LDS.128 and does the 9 taps x 8 channels as 36 FFMA2.
+// ------------------------------------------------------------------------------------------------
+constexpr int CT_X = 32, CT_Y = 16, CT_XH = CT_X + 2, CT_YH = CT_Y + 2;
+
+__device__ __forceinline__ void conv_tile_load(uint4* sdst, const bf16* __restrict__ g, long long ld, int H, int W, int y0,
+                                               int x0, int halo, int tid) {
+  // tile rows y0-halo .. y0+CT_Y-1+halo, cols x0-halo .. ; 4 chunks of 8 channels per token
+  const int TH = CT_Y + 2 * halo, TW = CT_X + 2 * halo;
+  for (int i = tid; i < TH * TW * 4; i += 128) {
+    const int ch = i & 3, c = (i >> 2) % TW, r = (i >> 2) / TW;
+    const int y = y0 - halo + r, x = x0 - halo + c;
+    const bool ok = y >= 0 && y < H && x >= 0 && x < W;
+    const bf16* src = g + ((long long)(ok ? y : 0) * W + (ok ? x : 0)) * ld + ch * 8;
+    cp_async16(sdst + i, src, ok ? 16 : 0);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_conv_fwd_tile(const bf16* __restrict__ raw, int ldr, const float* __restrict__ Kc, bf16* __restrict__ pre,
+                bf16* __restrict__ act, int H, int W, int CC, int slabs) {
+  __shared__ uint4 tile[CT_YH * CT_XH * 4];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z / slabs, slab = blockIdx.z % slabs;
+  const int x0 = blockIdx.x * CT_X, y0 = blockIdx.y * CT_Y, c0 = slab * 32;
+  conv_tile_load(tile, raw + (long long)b * H * W * ldr + c0, ldr, H, W, y0, x0, 1, tid);
+  cp_async_commit();
+  const int xl = tid >> 2, ch = tid & 3, cc = c0 + ch * 8;
+  float2 k2[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) k2[t][p] = make_float2(__ldg(Kc + (cc + 2 * p) * 9 + t), __ldg(Kc + (cc + 2 * p + 1) * 9 + t));
+  cp_async_wait<0>();
+  __syncthreads();
+  const int x = x0 + xl;
+  if (x >= W) return;
+  float2 win[3][3][4];
+  auto load_row = [&](int r, float2 (&w3)[3][4]) {
+#pragma unroll
+    for (int s = 0; s < 3; ++s) unpack8_f2(tile[(r * CT_XH + xl + s) * 4 + ch], w3[s]);
+  };
+  load_row(0, win[0]);
+  load_row(1, win[1]);
+  const int ny = min(CT_Y, H - y0);
+  for (int rb = 0; rb < ny; rb += 3) {
+#pragma unroll
+    for (int ph = 0; ph < 3; ++ph) {
+      const int r = rb + ph;
+      if (r < ny) {
+        load_row(r + 2, win[(ph + 2) % 3]);
+        float2 a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+          for (int sx = 0; sx < 3; ++sx)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q] = __ffma2_rn(k2[rr * 3 + sx][q], win[(ph + rr) % 3][sx][q], a[q]);
+        const long long off = (((long long)b * H + y0 + r) * W + x) * CC + cc;
+        if (pre) *reinterpret_cast<uint4*>(pre + off) = pack8_f2(a);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { a[q].x *= sigmoid_fast(a[q].x); a[q].y *= sigmoid_fast(a[q].y); }
+        *reinterpret_cast<uint4*>(act + off) = pack8_f2(a);
+      }
+    }
+  }
+}
+
+// conv backward, tiled: dpre = dact * silu'(pre) is formed ONCE per element in shared memory (halo tile), then
+//   pass 1: draw[y,x] = sum_ab K[a][b] dpre[y-a+1][x-b+1]        (36 FFMA2 per row)
+//   pass 2: dK[a][b] += raw[y,x] * dpre[y-a+1][x-b+1]            (36 FFMA2 per row, per-thread fp32 accumulators)
+// and the per-thread dK are reduced through shared memory before one global atomic per (channel, tap) per CTA.
+__global__ void __launch_bounds__(128)
+k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, const bf16* __restrict__ raw, int ldr,
+                const float* __restrict__ Kc, bf16* __restrict__ draw, float* __restrict__ dK, int H, int W, int CC,
+                int slabs) {
+  extern __shared__ __align__(16) uint8_t csm[];
+  uint4* tD = reinterpret_cast<uint4*>(csm);          // dact -> dpre, halo tile
+  uint4* tP = tD + CT_YH * CT_XH * 4;                 // pre, halo tile
+  uint4* tR = tP + CT_YH * CT_XH * 4;                 // raw, centre tile (CT_Y x CT_X)
+  float* red = reinterpret_cast<float*>(tR + CT_Y * CT_X * 4);   // [32 channels][9]
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z / slabs, slab = blockIdx.z % slabs;
+  const int x0 = blockIdx.x * CT_X, y0 = blockIdx.y * CT_Y, c0 = slab * 32;
+  const long long boff = (long long)b * H * W;
+  conv_tile_load(tD, dact + boff * CC + c0, CC, H, W, y0, x0, 1, tid);
+  conv_tile_load(tP, pre + boff * CC + c0, CC, H, W, y0, x0, 1, tid);
+  conv_tile_load(tR, raw + boff * ldr + c0, ldr, H, W, y0, x0, 0, tid);
+  cp_async_commit();
+  for (int i = tid; i < 32 * 9; i += 128) red[i] = 0.f;
+  const int xl = tid >> 2, ch = tid & 3, cc = c0 + ch * 8;
+  cp_async_wait<0>();
+  __syncthreads();
+  for (int i = tid; i < CT_YH * CT_XH * 4; i += 128) {
+    float g[8], p[8];
+    unpack8(tD[i], g);
+    unpack8(tP[i], p);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sgm = sigmoid_fast(p[j]);
+      g[j] *= sgm * (1.f + p[j] * (1.f - sgm));
+    }
+    tD[i] = pack8(g);
+  }
+  __syncthreads();
+  const int x = x0 + xl;
+  const int ny = min(CT_Y, H - y0);
+  const bool xin = x < W;   // columns beyond the image compute on zero-filled tile data and never store
+  float2 dk[9][4];
+  {
+    float2 win[3][3][4];
+    auto load_row = [&](int r, float2 (&w3)[3][4]) {
+#pragma unroll
+      for (int s = 0; s < 3; ++s) unpack8_f2(tD[(r * CT_XH + xl + s) * 4 + ch], w3[s]);
+    };
+    {  // pass 1: transposed convolution
+      float2 k2[9][4];
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) k2[t][p] = make_float2(__ldg(Kc + (cc + 2 * p) * 9 + t), __ldg(Kc + (cc + 2 * p + 1) * 9 + t));
+      load_row(0, win[0]);
+      load_row(1, win[1]);
+      for (int rb = 0; rb < ny; rb += 3) {
+#pragma unroll
+        for (int ph = 0; ph < 3; ++ph) {
+          const int r = rb + ph;
+          if (r < ny) {
+            load_row(r + 2, win[(ph + 2) % 3]);
+            float2 o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+              for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) o[q] = __ffma2_rn(k2[a * 3 + bb][q], win[(ph + 2 - a) % 3][2 - bb][q], o[q]);
+            if (xin) *reinterpret_cast<uint4*>(draw + (boff + (long long)(y0 + r) * W + x) * ldr + cc) = pack8_f2(o);
+          }
+        }
+      }
+    }
+    {  // pass 2: kernel gradient
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dk[t][q] = make_float2(0.f, 0.f);
+      load_row(0, win[0]);
+      load_row(1, win[1]);
+      for (int rb = 0; rb < ny; rb += 3) {
+#pragma unroll
+        for (int ph = 0; ph < 3; ++ph) {
+          const int r = rb + ph;
+          if (r < ny) {
+            load_row(r + 2, win[(ph + 2) % 3]);
+            float2 rc[4];
+            unpack8_f2(tR[(r * CT_X + xl) * 4 + ch], rc);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+              for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dk[a * 3 + bb][q] = __ffma2_rn(rc[q], win[(ph + 2 - a) % 3][2 - bb][q], dk[a * 3 + bb][q]);
+          }
+        }
+      }
+    }
+  }
+  // reduce over the 32 columns of the tile (all lanes participate: columns beyond the image hold zeros):
+  // lanes of a warp = 8 columns x 4 chunks -> xor-shuffle over the column bits, then shared-memory atomics
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float vx = dk[t][q].x, vy = dk[t][q].y;
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) { vx += __shfl_xor_sync(0xffffffffu, vx, o); vy += __shfl_xor_sync(0xffffffffu, vy, o); }
+      if ((tid & 31) < 4) {
+        atomicAdd(&red[(ch * 8 + 2 * q) * 9 + t], vx);
+        atomicAdd(&red[(ch * 8 + 2 * q + 1) * 9 + t], vy);
+      }
+    }
+  __syncthreads();
+  for (int i = tid; i < 32 * 9; i += 128)
+    if (red[i] != 0.f) atomicAdd(dK + c0 * 9 + i, red[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct FastWs {           // placed after the generic workspace of the same pass
@@ -1218,7 +1532,7 @@ struct FastWs {           // placed after the generic workspace of the same pass
 
 bool sm100_supported(const MixerDims& d) {
   // instantiated tile shapes: d_model 32 (d_inner 64), headdim 4, ngroups*d_state in {32, 128}
-  return d.D == 32 && d.Di == 64 && d.P == 4 && (d.GN == 32 || d.GN == 128) && d.dip % 16 == 0 && d.ldr == d.dip;
+  return d.D == 32 && d.Di == 64 && d.P == 4 && (d.GN == 32 || d.GN == 128) && d.dip % 16 == 0 && d.ldr == d.dip && d.CC % 32 == 0;
 }
 
 template <typename K>
@@ -1334,8 +1648,9 @@ int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* 
   if (rc) return rc;
   // (2) depthwise 3x3 + SiLU
   {
-    dim3 grid(cdiv((long long)d.W * (d.CC / 8), 128), cdiv(d.H, ROWS8), d.B);
-    { ADN_KERNEL("k_conv_fwd8", st); k_conv_fwd8<<<grid, 128, 0, st>>>(S.raw, d.ldr, W.Kc, training ? S.pre : nullptr, S.act, d.H, d.W, d.CC); }
+    const int slabs = d.CC / 32;
+    dim3 grid(cdiv(d.W, CT_X), cdiv(d.H, CT_Y), d.B * slabs);
+    { ADN_KERNEL("k_conv_fwd_tile", st); k_conv_fwd_tile<<<grid, 128, 0, st>>>(S.raw, d.ldr, W.Kc, training ? S.pre : nullptr, S.act, d.H, d.W, d.CC, slabs); }
   }
   (void)Tt;
   // (4a) state on tcgen05 (reduction over tokens), (4b)+(5) readout + LayerNorm + out_proj on tcgen05
@@ -1371,11 +1686,14 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   rc = d.GN == 32 ? launch_bwd2<64, 32>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st)
                   : launch_bwd2<64, 128>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st);
   if (rc) return rc;
-  // ---- conv backward
+  // ---- conv backward (dpre formed in shared memory; transposed conv + kernel gradient)
   {
-    const int bpb = 4;
-    dim3 grid(cdiv((long long)d.W * (d.CC / 4), 192), cdiv(d.H, ROWS8), cdiv(d.B, bpb));
-    { ADN_KERNEL("k_conv_bwd4", st); k_conv_bwd4<TWf><<<grid, 192, d.CC * 9 * sizeof(float), st>>>(W.dact, S.pre, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.B, d.H, d.W, d.CC, bpb); }
+    const int slabs = d.CC / 32;
+    const size_t smem = (size_t)(2 * CT_YH * CT_XH * 4 + CT_Y * CT_X * 4) * 16 + 32 * 9 * sizeof(float);
+    rc = set_smem(k_conv_bwd_tile, smem);
+    if (rc) return rc;
+    dim3 grid(cdiv(d.W, CT_X), cdiv(d.H, CT_Y), d.B * slabs);
+    { ADN_KERNEL("k_conv_bwd_tile", st); k_conv_bwd_tile<<<grid, 128, smem, st>>>(W.dact, S.pre, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.H, d.W, d.CC, slabs); }
   }
   // ---- in_proj backward
   rc = d.dip <= 128 ? launch_bwd4<32, 1>(d, W.draw, u, F, du, W.acc.dWin, st)
