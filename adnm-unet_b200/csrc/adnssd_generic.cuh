@@ -15,9 +15,7 @@ struct ConvWeightPtrs {
   const float *c13x1, *c31x1, *c13x2, *c31x2, *c13bc1, *c31bc1, *c13bc2, *c31bc2, *c2d, *c2dz;
 };
 
-static __global__ void k_assemble_conv(ConvWeightPtrs w, float* __restrict__ Kc, int Di, int CC) {
-  int cc = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cc >= CC) return;
+__device__ __forceinline__ void assemble_conv_channel(const ConvWeightPtrs& w, float* __restrict__ Kc, int Di, int cc) {
   float k[9];
   if (cc < Di) {
 #pragma unroll
@@ -46,6 +44,11 @@ static __global__ void k_assemble_conv(ConvWeightPtrs w, float* __restrict__ Kc,
   }
 #pragma unroll
   for (int t = 0; t < 9; ++t) Kc[cc * 9 + t] = k[t];
+}
+
+static __global__ void k_assemble_conv(ConvWeightPtrs w, float* __restrict__ Kc, int Di, int CC) {
+  int cc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cc < CC) assemble_conv_channel(w, Kc, Di, cc);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -95,18 +95,6 @@ __device__ __forceinline__ void load_tile_t8(bf16* sdst, const bf16* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_prep: bf16 hi/lo images of in_proj.weight ([dip][D] row-major, hi + lo = fp32 value to ~2^-17)
-// ------------------------------------------------------------------------------------------------
-__global__ void k_prep_split(const float* __restrict__ w, bf16* __restrict__ hi, bf16* __restrict__ lo, long long n) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float v = w[i];
-  bf16 h = __float2bfloat16_rn(v);
-  hi[i] = h;
-  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
-}
-
-// ------------------------------------------------------------------------------------------------
 // k_inproj: raw[T][ldr] = u[T][D] . W_in^T   (models/ADNssd.py:309).  Persistent CTAs, 128 tokens per tile.
 // A = u tile (K-major, cp.async double buffered), B = W_in rows [n0, n0+nn) as hi and lo bf16 images (K-major):
 // D(tmem) = A.B_hi^T + A.B_lo^T with fp32 accumulation, so raw carries no weight-rounding error.
@@ -200,20 +188,6 @@ k_inproj(const bf16* __restrict__ u, const bf16* __restrict__ Whi, const bf16* _
   if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
-// ------------------------------------------------------------------------------------------------
-// depthwise 3x3 + SiLU, channels-last bf16, 8 channels (one 16-byte vector) per thread, ROWS8 output rows per
-// thread with a 3x3 register window.  Flat thread index over (column, channel-vector) with the channel-vector
-// fastest: a warp reads / writes 512 contiguous bytes.   grid (ceil(W*CG/128), ceil(H/ROWS8), B)
-// ------------------------------------------------------------------------------------------------
-constexpr int ROWS8 = 16;
-
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
-__device__ __forceinline__ float silu_grad_fast(float x) {
-  float s = __fdividef(1.f, 1.f + __expf(-x));
-  return s * (1.f + x * (1.f - s));
-}
-
-__device__ __forceinline__ uint4 ldg16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 // bf16x8 (one 16-byte vector) -> four float2
 __device__ __forceinline__ void unpack8_f2(const uint4& u, float2 (&v)[4]) {
@@ -226,247 +200,6 @@ __device__ __forceinline__ uint4 pack8_f2(const float2 (&v)[4]) {
   return make_uint4(pack_bf16(v[0].x, v[0].y), pack_bf16(v[1].x, v[1].y), pack_bf16(v[2].x, v[2].y), pack_bf16(v[3].x, v[3].y));
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-
-// The 3x3 window lives in registers as fp32 pairs (unpacked once per load); rows rotate through three slots by
-// unrolling the row loop by 3, and the 9 taps x 8 channels are 36 packed FFMA2 (fma.rn.f32x2) per output row.
-__global__ void __launch_bounds__(128)
-k_conv_fwd8(const bf16* __restrict__ raw, int ldr, const float* __restrict__ Kc, bf16* __restrict__ pre,
-            bf16* __restrict__ act, int H, int W, int CC) {
-  const int CG = CC >> 3;
-  const int idx = blockIdx.x * 128 + threadIdx.x;
-  if (idx >= W * CG) return;
-  const int x = idx / CG, cg = idx % CG, c0 = cg * 8;
-  const int b = blockIdx.z, y0 = blockIdx.y * ROWS8, y1 = min(H, y0 + ROWS8);
-  float2 k2[9][4];
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int p = 0; p < 4; ++p) k2[t][p] = make_float2(__ldg(Kc + (c0 + 2 * p) * 9 + t), __ldg(Kc + (c0 + 2 * p + 1) * 9 + t));
-  const bf16* src = raw + (long long)b * H * W * ldr + c0;
-  const bool xl = x > 0, xr = x + 1 < W;
-  float2 win[3][3][4];
-  auto load_row = [&](int y, float2 (&r)[3][4]) {
-    if (y >= 0 && y < H) {
-      const bf16* p = src + ((long long)y * W + x) * ldr;
-      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-      unpack8_f2(xl ? ldg16(p - ldr) : zero, r[0]);
-      unpack8_f2(ldg16(p), r[1]);
-      unpack8_f2(xr ? ldg16(p + ldr) : zero, r[2]);
-    } else {
-#pragma unroll
-      for (int s = 0; s < 3; ++s)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) r[s][q] = make_float2(0.f, 0.f);
-    }
-  };
-  load_row(y0 - 1, win[0]);
-  load_row(y0, win[1]);
-  for (int yb = y0; yb < y1; yb += 3) {
-#pragma unroll
-    for (int ph = 0; ph < 3; ++ph) {
-      const int y = yb + ph;
-      if (y < y1) {
-        load_row(y + 1, win[(ph + 2) % 3]);
-        float2 a[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) a[q] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int s = 0; s < 3; ++s)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) a[q] = __ffma2_rn(k2[r * 3 + s][q], win[(ph + r) % 3][s][q], a[q]);
-        const long long off = (((long long)b * H + y) * W + x) * CC + c0;
-        if (pre) *reinterpret_cast<uint4*>(pre + off) = pack8_f2(a);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { a[q].x *= sigmoid_fast(a[q].x); a[q].y *= sigmoid_fast(a[q].y); }
-        *reinterpret_cast<uint4*>(act + off) = pack8_f2(a);
-      }
-    }
-  }
-}
-
-// dact <- dact * silu'(pre), in place, 8 elements per thread
-__global__ void __launch_bounds__(256)
-k_dpre(bf16* __restrict__ dact, const bf16* __restrict__ pre, long long n8) {
-  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n8) return;
-  float g[8], p[8];
-  unpack8(*reinterpret_cast<const uint4*>(dact + i * 8), g);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(pre + i * 8)), p);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float sgm = sigmoid_fast(p[j]);
-    g[j] *= sgm * (1.f + p[j] * (1.f - sgm));
-  }
-  *reinterpret_cast<uint4*>(dact + i * 8) = pack8(g);
-}
-
-// conv backward on dpre (= dact * silu'(pre), already applied): draw[:, :CC] = convT(dpre), dK += raw (x) dpre.
-// 4 channels per thread (two float2 lanes), full image column per thread (no halo recomputation), one sample per
-// blockIdx.y.  Block = 192 consecutive (column, channel-quad) pairs = 4 whole tokens when CC/4 == 48.
-__global__ void __launch_bounds__(192)
-k_conv_bwd_dpre(const bf16* __restrict__ dpre, const bf16* __restrict__ raw, int ldr, const float* __restrict__ Kc,
-                bf16* __restrict__ draw, float* __restrict__ dK, int H, int W, int CC, int rows_per_block) {
-  extern __shared__ float red[];   // [CC*9]
-  const int CG = CC >> 2;
-  for (int i = threadIdx.x; i < CC * 9; i += 192) red[i] = 0.f;
-  __syncthreads();
-  const int idx = blockIdx.x * 192 + threadIdx.x;
-  const bool active = idx < W * CG;
-  const int x = active ? idx / CG : 0, cg = active ? idx % CG : 0, c0 = cg * 4;
-  const int b = blockIdx.y;
-  const int y0 = blockIdx.z * rows_per_block, y1 = min(H, y0 + rows_per_block);
-  if (active) {
-    float2 k2[9][2], dk[9][2];
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        k2[t][p] = make_float2(__ldg(Kc + (c0 + 2 * p) * 9 + t), __ldg(Kc + (c0 + 2 * p + 1) * 9 + t));
-        dk[t][p] = make_float2(0.f, 0.f);
-      }
-    const long long boff = (long long)b * H * W;
-    const bf16* g = dpre + boff * CC + c0;
-    const bool xl = x > 0, xr = x + 1 < W;
-    float2 win[3][3][2];
-    auto ld = [&](const bf16* p, float2 (&v)[2]) {
-      const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
-      v[0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
-      v[1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
-    };
-    auto load_row = [&](int y, float2 (&r)[3][2]) {
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const bool okp = y >= 0 && y < H && (s == 1 || (s == 0 ? xl : xr));
-        if (okp) ld(g + ((long long)y * W + x + s - 1) * CC, r[s]);
-        else { r[s][0] = make_float2(0.f, 0.f); r[s][1] = make_float2(0.f, 0.f); }
-      }
-    };
-    load_row(y0 - 1, win[0]);
-    load_row(y0, win[1]);
-    for (int yb = y0; yb < y1; yb += 3) {
-#pragma unroll
-      for (int ph = 0; ph < 3; ++ph) {
-        const int y = yb + ph;
-        if (y < y1) {
-          load_row(y + 1, win[(ph + 2) % 3]);
-          const long long tok = boff + (long long)y * W + x;
-          float2 rc[2], o[2];
-          ld(raw + tok * ldr + c0, rc);
-          o[0] = make_float2(0.f, 0.f); o[1] = make_float2(0.f, 0.f);
-          // draw[y,x] = sum_ab K[a][b] * dpre[y-a+1][x-b+1] ; dK[a][b] += raw[y,x] * dpre[y-a+1][x-b+1]
-#pragma unroll
-          for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int bb = 0; bb < 3; ++bb)
-#pragma unroll
-              for (int p = 0; p < 2; ++p) {
-                const float2 dv = win[(ph + 2 - a) % 3][2 - bb][p];
-                o[p] = __ffma2_rn(k2[a * 3 + bb][p], dv, o[p]);
-                dk[a * 3 + bb][p] = __ffma2_rn(rc[p], dv, dk[a * 3 + bb][p]);
-              }
-          uint2 ov;
-          ov.x = pack_bf16(o[0].x, o[0].y);
-          ov.y = pack_bf16(o[1].x, o[1].y);
-          *reinterpret_cast<uint2*>(draw + tok * ldr + c0) = ov;
-        }
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        atomicAdd(&red[(c0 + 2 * p) * 9 + t], dk[t][p].x);
-        atomicAdd(&red[(c0 + 2 * p + 1) * 9 + t], dk[t][p].y);
-      }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < CC * 9; i += 192)
-    if (red[i] != 0.f) atomicAdd(dK + i, red[i]);
-}
-
-// ------------------------------------------------------------------------------------------------
-// conv backward, 4 channels per thread: draw[:, :CC] = convT(dact * silu'(pre)); dK += raw (x) dpre.
-// Flat mapping like the forward; block = 192 threads; block-level smem reduction of dK, then global atomics.
-//   grid (ceil(W*CG4/192), ceil(H/ROWS8), ceil(B/BPB)); each block loops over BPB samples to amortise the reduction
-// ------------------------------------------------------------------------------------------------
-template <typename TW>
-__global__ void __launch_bounds__(192)
-k_conv_bwd4(const TW* __restrict__ dact, const bf16* __restrict__ pre, const bf16* __restrict__ raw, int ldr,
-            const float* __restrict__ Kc, TW* __restrict__ draw, float* __restrict__ dK, int B, int H, int W, int CC,
-            int bpb) {
-  extern __shared__ float red[];   // [CC*9] block-local dK
-  const int CG = CC >> 2;
-  for (int i = threadIdx.x; i < CC * 9; i += 192) red[i] = 0.f;
-  __syncthreads();
-  const int idx = blockIdx.x * 192 + threadIdx.x;
-  const bool active = idx < W * CG;
-  const int x = active ? idx / CG : 0, cg = active ? idx % CG : 0, c0 = cg * 4;
-  const int y0 = blockIdx.y * ROWS8, y1 = min(H, y0 + ROWS8);
-  float dk[9][4] = {};
-  if (active) {
-    float k[9][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int t = 0; t < 9; ++t) k[t][i] = __ldg(Kc + (c0 + i) * 9 + t);
-    const bool xl = x > 0, xr = x + 1 < W;
-    for (int b = blockIdx.z * bpb; b < min(B, (blockIdx.z + 1) * bpb); ++b) {
-      const long long boff = (long long)b * H * W;
-      const TW* g = dact + boff * CC + c0;
-      const bf16* p = pre + boff * CC + c0;
-      float win[3][3][4];
-      auto load_row = [&](int y, float (&r)[3][4]) {
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const bool ok = y >= 0 && y < H && (s == 1 || (s == 0 ? xl : xr));
-          if (ok) {
-            float gv[4], pv[4];
-            const long long off = ((long long)y * W + x + s - 1) * CC;
-            ld4(g + off, gv);
-            ld4(p + off, pv);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) r[s][i] = gv[i] * silu_grad_fast(pv[i]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) r[s][i] = 0.f;
-          }
-        }
-      };
-      load_row(y0 - 1, win[0]);
-      load_row(y0, win[1]);
-      for (int y = y0; y < y1; ++y) {
-        load_row(y + 1, win[2]);
-        const long long tok = boff + (long long)y * W + x;
-        float rc[4], o[4] = {0.f, 0.f, 0.f, 0.f};
-        ld4(raw + tok * ldr + c0, rc);
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-          for (int bb = 0; bb < 3; ++bb)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float d = win[2 - a][2 - bb][i];
-              o[i] = fmaf(k[a * 3 + bb][i], d, o[i]);
-              dk[a * 3 + bb][i] = fmaf(rc[i], d, dk[a * 3 + bb][i]);
-            }
-        st4(draw + tok * ldr + c0, o);
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { win[0][s][i] = win[1][s][i]; win[1][s][i] = win[2][s][i]; }
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(&red[(c0 + i) * 9 + t], dk[t][i]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < CC * 9; i += 192)
-    if (red[i] != 0.f) atomicAdd(dK + i, red[i]);
-}
 
 // ------------------------------------------------------------------------------------------------
 // k_state: S'[b][j][c] += [j%2==c%2] * sum_l Bc[l,j] * w[l,hd(c)] * xc[l,c]      (models/ADNssd.py:267-280, both parities)
@@ -998,38 +731,26 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
 // Rt / sdout -> the accumulators the shared finalize kernel expects (raw dW_out, dgamma, dbeta, dalpha1).
 //   dW_out_raw[d][c] = gamma[c]*Rt[c][d] + beta[c]*sd[d]  (c < DI),  Rt[c][d]  (c >= DI)
 //   dgamma[c] = a1 * sum_d W[d][c] Rt[c][d] ;  dbeta[c] = a1 * sum_d W[d][c] sd[d] ;  dalpha1 = sum W .* dW_out_raw
-__global__ void k_bwd1_post(const float* __restrict__ Rt, const float* __restrict__ sdout, const float* __restrict__ Wout,
-                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                            const float* __restrict__ alpha1p, float* __restrict__ dWout, float* __restrict__ dgamma,
-                            float* __restrict__ dbeta, float* __restrict__ dalpha1, int D, int DI) {
-  __shared__ float red[32];
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32)
+k_bwd1_post(const float* __restrict__ Rt, const float* __restrict__ sdout, const float* __restrict__ Wout,
+            const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ alpha1p,
+            float* __restrict__ dWout, float* __restrict__ dgamma, float* __restrict__ dbeta,
+            float* __restrict__ dalpha1, int D, int DI) {
+  const int c = blockIdx.x;          // one warp per column c of [LN(y) | zc]; lanes stride over d
   const float a1 = *alpha1p;
-  float da = 0.f;
-  if (c < 2 * DI) {
-    float dg = 0.f, db = 0.f;
-    for (int d = 0; d < D; ++d) {
-      const float r = Rt[c * D + d], wv = Wout[d * 2 * DI + c];
-      float raw;
-      if (c < DI) {
-        raw = gamma[c] * r + beta[c] * sdout[d];
-        dg = fmaf(wv, r, dg);
-        db = fmaf(wv, sdout[d], db);
-      } else {
-        raw = r;
-      }
-      dWout[d * 2 * DI + c] = raw;
-      da = fmaf(wv, raw, da);
-    }
-    if (c < DI) { dgamma[c] = a1 * dg; dbeta[c] = a1 * db; }
+  float dg = 0.f, db = 0.f, da = 0.f;
+  for (int d = threadIdx.x; d < D; d += 32) {
+    const float r = Rt[c * D + d], wv = Wout[d * 2 * DI + c], sd = sdout[d];
+    const float raw = c < DI ? gamma[c] * r + beta[c] * sd : r;
+    dWout[d * 2 * DI + c] = raw;
+    da = fmaf(wv, raw, da);
+    dg = fmaf(wv, r, dg);
+    db = fmaf(wv, sd, db);
   }
-  da = warp_sum(da);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = da;
-  __syncthreads();
+  dg = warp_sum(dg); db = warp_sum(db); da = warp_sum(da);
   if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-    atomicAdd(dalpha1, t);
+    if (c < DI) { dgamma[c] = a1 * dg; dbeta[c] = a1 * db; }
+    atomicAdd(dalpha1, da);
   }
 }
 
@@ -1311,9 +1032,19 @@ k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__
   if (warp == 0) tmem_dealloc(tbase, TCOLS);
 }
 
-__global__ void k_to_bf16(const float* __restrict__ w, bf16* __restrict__ o, long long n) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) o[i] = __float2bfloat16_rn(w[i]);
+// One launch for all per-call weight preparation: conv kernel assembly, in_proj hi/lo split, out_proj -> bf16.
+__global__ void k_prep(ConvWeightPtrs cw, float* __restrict__ Kc, int Di, int CC, const float* __restrict__ win,
+                       bf16* __restrict__ whi, bf16* __restrict__ wlo, int n_in, const float* __restrict__ wout,
+                       bf16* __restrict__ wout_bf, int n_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < CC) assemble_conv_channel(cw, Kc, Di, i);
+  if (i < n_in) {
+    const float v = win[i];
+    const bf16 h = __float2bfloat16_rn(v);
+    whi[i] = h;
+    wlo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+  if (i < n_out) wout_bf[i] = __float2bfloat16_rn(wout[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1639,9 +1370,11 @@ int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* 
   SavedBufs<T> S = saved ? SavedBufs<T>(d, saved) : W.tmp;
   const bool training = saved != nullptr;
   const long long Tt = d.T;
-  { ADN_KERNEL("k_assemble_conv", st); k_assemble_conv<<<cdiv(d.CC, 128), 128, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC); }
   ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
-  { ADN_KERNEL("k_prep_split", st); k_prep_split<<<cdiv((long long)d.dip * d.D, 256), 256, 0, st>>>(w.in_proj_w, F.Whi, F.Wlo, (long long)d.dip * d.D); }
+  {
+    const int n_in = d.dip * d.D, n_out = d.D * 2 * d.Di, n = max(max(n_in, n_out), d.CC);
+    { ADN_KERNEL("k_prep", st); k_prep<<<cdiv(n, 256), 256, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC, w.in_proj_w, F.Whi, F.Wlo, n_in, w.out_proj_w, F.Wout, n_out); }
+  }
   // (1) in_proj on tcgen05
   int rc = d.D == 16 ? launch_inproj<16>(d, u, F, S.raw, st) : d.D == 32 ? launch_inproj<32>(d, u, F, S.raw, st)
                                                                          : launch_inproj<64>(d, u, F, S.raw, st);
@@ -1655,7 +1388,6 @@ int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* 
   (void)Tt;
   // (4a) state on tcgen05 (reduction over tokens), (4b)+(5) readout + LayerNorm + out_proj on tcgen05
   ADN_CHECK_CUDA(cudaMemsetAsync(S.S, 0, (size_t)d.B * d.GN * d.Di * sizeof(float), st));
-  { ADN_KERNEL("k_to_bf16", st); k_to_bf16<<<cdiv((long long)d.D * 2 * d.Di, 256), 256, 0, st>>>(w.out_proj_w, F.Wout, (long long)d.D * 2 * d.Di); }
   rc = d.GN == 32 ? launch_state<64, 32>(d, S.act, S.raw, w, S.S, F.status, st) : launch_state<64, 128>(d, S.act, S.raw, w, S.S, F.status, st);
   if (rc) return rc;
   rc = d.GN == 32 ? launch_readout<64, 32>(d, S.act, S.S, w, F.Wout, out, F.status, st)
@@ -1674,14 +1406,15 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   ADN_CHECK_CUDA(cudaMemsetAsync(W.zero_begin, 0, W.zero_bytes, st));
   ADN_CHECK_CUDA(cudaMemsetAsync(F.Rt, 0, ((size_t)2 * d.Di * d.D + d.D) * sizeof(float), st));
   ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
-  { ADN_KERNEL("k_assemble_conv", st); k_assemble_conv<<<cdiv(d.CC, 128), 128, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC); }
-  { ADN_KERNEL("k_prep_split", st); k_prep_split<<<cdiv((long long)d.dip * d.D, 256), 256, 0, st>>>(w.in_proj_w, F.Whi, F.Wlo, (long long)d.dip * d.D); }
-  { ADN_KERNEL("k_to_bf16", st); k_to_bf16<<<cdiv((long long)d.D * 2 * d.Di, 256), 256, 0, st>>>(w.out_proj_w, F.Wout, (long long)d.D * 2 * d.Di); }
+  {
+    const int n_in = d.dip * d.D, n_out = d.D * 2 * d.Di, n = max(max(n_in, n_out), d.CC);
+    { ADN_KERNEL("k_prep", st); k_prep<<<cdiv(n, 256), 256, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC, w.in_proj_w, F.Whi, F.Wlo, n_in, w.out_proj_w, F.Wout, n_out); }
+  }
   // ---- phase B1: dout -> dy, dzc, dCc ; reductions Rt, dS'
   int rc = d.GN == 32 ? launch_bwd1<64, 32>(d, dout, S.act, S.S, w, F, W.dact, W.dS, st)
                       : launch_bwd1<64, 128>(d, dout, S.act, S.S, w, F, W.dact, W.dS, st);
   if (rc) return rc;
-  { ADN_KERNEL("k_bwd1_post", st); k_bwd1_post<<<cdiv(2 * d.Di, 128), 128, 0, st>>>(F.Rt, F.sdout, w.out_proj_w, w.norm_w, w.norm_b, w.alpha1, W.acc.dWout, W.acc.dgamma, W.acc.dbeta, W.acc.dalpha1, d.D, d.Di); }
+  { ADN_KERNEL("k_bwd1_post", st); k_bwd1_post<<<2 * d.Di, 32, 0, st>>>(F.Rt, F.sdout, w.out_proj_w, w.norm_w, w.norm_b, w.alpha1, W.acc.dWout, W.acc.dgamma, W.acc.dbeta, W.acc.dalpha1, d.D, d.Di); }
   // ---- phase B2: dS' -> dxc, dBc, ddt
   rc = d.GN == 32 ? launch_bwd2<64, 32>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st)
                   : launch_bwd2<64, 128>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st);
