@@ -54,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -162,15 +162,12 @@ def run_ours(args):
     host_g = [torch.randn(B, L, D, generator=g).bfloat16().pin_memory() for _ in range(N_INPUT_SETS)]
     dev_u = [t.to(dev) for t in host_u]
     dev_g = [t.to(dev) for t in host_g]
-    host_out = torch.empty(B, L, D, dtype=torch.bfloat16).pin_memory()
-    host_du = torch.empty(B, L, D, dtype=torch.bfloat16).pin_memory()
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+    from adnm_unet_b200.dp import GradAllReducer
+    reducer = GradAllReducer(params) if world > 1 else None
 
     def allreduce_grads():
-        if world > 1:
-            torch.cat([p.grad.reshape(-1) for p in params], out=flat)
-            dist.all_reduce(flat)
-            flat.mul_(1.0 / world)
+        if reducer is not None:
+            reducer()       # NCCL all-reduce(sum) / world of the flat parameter-gradient bucket
 
     def step_resident(i):
         u = dev_u[i % N_INPUT_SETS].requires_grad_(True)
@@ -182,28 +179,63 @@ def run_ours(args):
         allreduce_grads()
         return out, u.grad
 
+    # ---- end-to-end: host buffers in, host buffers out, every step.  Copies run on their own streams so that the H2D of
+    # step i+1 and the D2H of step i-1 overlap the kernels of step i (double-buffered device staging slots).
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    NSLOT = 2
+    slot_u = [torch.empty(B, L, D, dtype=torch.bfloat16, device=dev) for _ in range(NSLOT)]
+    slot_g = [torch.empty(B, L, D, dtype=torch.bfloat16, device=dev) for _ in range(NSLOT)]
+    host_outs = [torch.empty(B, L, D, dtype=torch.bfloat16).pin_memory() for _ in range(NSLOT)]
+    host_dus = [torch.empty(B, L, D, dtype=torch.bfloat16).pin_memory() for _ in range(NSLOT)]
+    ev_in = [torch.cuda.Event() for _ in range(NSLOT)]
+    ev_done = [torch.cuda.Event() for _ in range(NSLOT)]
+    ev_out = [torch.cuda.Event() for _ in range(NSLOT)]
+    keep = [None] * NSLOT
+
     def step_e2e(i):
-        u = host_u[i % N_INPUT_SETS].to(dev, non_blocking=True).requires_grad_(True)
-        go = host_g[i % N_INPUT_SETS].to(dev, non_blocking=True)
+        k = i % NSLOT
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_done[k])            # the kernels that last read this staging slot have finished
+            slot_u[k].copy_(host_u[i % N_INPUT_SETS], non_blocking=True)
+            slot_g[k].copy_(host_g[i % N_INPUT_SETS], non_blocking=True)
+            ev_in[k].record(s_in)
+        cur.wait_event(ev_in[k])
+        cur.wait_event(ev_out[k])                  # the previous D2H out of this slot's result tensors has finished
+        u = slot_u[k].detach().requires_grad_(True)
         for p in params:
             p.grad = None
         out = mixer(u, GRID, GRID)
-        out.backward(go)
+        out.backward(slot_g[k])
         allreduce_grads()
-        host_out.copy_(out.detach(), non_blocking=True)
-        host_du.copy_(u.grad, non_blocking=True)
+        ev_done[k].record(cur)
+        keep[k] = (out.detach(), u.grad)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_done[k])
+            host_outs[k].copy_(keep[k][0], non_blocking=True)
+            host_dus[k].copy_(keep[k][1], non_blocking=True)
+            keep[k][0].record_stream(s_out)
+            keep[k][1].record_stream(s_out)
+            ev_out[k].record(s_out)
+
+    def drain_e2e():
+        cur = torch.cuda.current_stream()
+        for k in range(NSLOT):
+            cur.wait_event(ev_out[k])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, drain=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(i)
+        if drain:
+            drain()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -221,7 +253,7 @@ def run_ours(args):
     ms = timed(step_resident, args.steps)
     launches = _lib.launch_count() - n0
     clocks = sampler.stop() if sampler else None
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, args.steps, drain_e2e)
 
     # per-kernel device times (CUDA events recorded by the library on the launching stream), a few extra steps
     barrier()
@@ -246,7 +278,7 @@ def run_ours(args):
         # dominant kernel: achieved = bytes it must move per launch / its mean launch time
         top_bytes = KERNEL_ALG_BYTES.get(top, lambda D, T: None)(D, tokens)
         roof = {"bound": "hbm", "kernel": top, "achieved": (top_bytes / (top_ms * 1e-3) / 1e9) if top_bytes else None,
-                "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": load_traffic(top),
                 "kernel_ms_per_launch": top_ms, "kernel_share_of_step": per[top][0] / tot,
                 "step_achieved": alg_bytes_step / (step_ms * 1e-3) / 1e9, "step_algorithmic_bytes": alg_bytes_step}
         roof["frac"] = (roof["achieved"] / hbm_peak) if roof["achieved"] else None
@@ -281,18 +313,45 @@ def _dims(D):
     return Di, GN, nh, CC, CC + nh
 
 
-KERNEL_ALG_BYTES = {
-    "k_conv_fwd": lambda D, T: T * 2 * (3 * _dims(D)[3]),                      # read raw[:, :CC], write pre + act
-    "k_conv_bwd": lambda D, T: T * 2 * (4 * _dims(D)[3]),                      # read dact, pre, raw ; write draw
-    "k_gemm": lambda D, T: None,
-}
+# bytes each kernel must move once per token (bf16 = 2 bytes)
+def _alg(D):
+    Di, GN, nh, CC, dip = _dims(D)
+    return {
+        "k_inproj": 2 * (D + dip),
+        "k_conv_fwd_tile": 2 * 3 * CC,
+        "k_state": 2 * (Di + GN + nh),
+        "k_readout": 2 * (2 * Di + GN) + 2 * D,
+        "k_bwd1": 2 * D + 4 * (2 * Di + GN),
+        "k_bwd2": 2 * (2 * Di + GN + nh) + 2 * (Di + GN + nh),
+        "k_conv_bwd_tile": 2 * 4 * CC,
+        "k_bwd4": 2 * (dip + 2 * D),
+    }
+
+
+class _AlgBytes(dict):
+    def get(self, name, default=None):
+        return (lambda D, T: _alg(D)[name] * T) if name in _alg(32) else default
+
+
+KERNEL_ALG_BYTES = _AlgBytes()
+
+
+def load_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full summary."""
+    p = os.path.join(ROOT, "profiles", "r01_mixer_kernels.json")
+    if not os.path.isfile(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    e = d.get("kernels", {}).get(kernel)
+    return (e["dram_read_bytes"] + e["dram_write_bytes"]) if e else None
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--d-model", type=int, default=32)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
