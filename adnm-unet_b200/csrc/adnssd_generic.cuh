@@ -531,6 +531,10 @@ k_bwd_heads(const T* __restrict__ raw, long long ldr, const T* __restrict__ act,
 // ------------------------------------------------------------------------------------------------
 struct GradAcc {
   float *dWin, *dWout, *dgamma, *dbeta, *dD, *dAlog, *ddtb, *dalpha1, *dK;
+  // optional per-CTA partial sums of dW_in (the tcgen05 path writes one slab per CTA instead of contended atomics);
+  // finalize adds dWin_parts slabs of dip*D floats starting at dWin_part to dWin
+  const float* dWin_part;
+  int dWin_parts;
 };
 
 static __global__ void k_finalize(GradAcc a, AdnWeights w, AdnWeightGrads g, int D, int Di, int GN, int nh, int dip) {
@@ -538,7 +542,11 @@ static __global__ void k_finalize(GradAcc a, AdnWeights w, AdnWeightGrads g, int
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const float a1 = *w.alpha1;
   if (g.in_proj_w)
-    for (long long i = i0; i < (long long)dip * D; i += stride) g.in_proj_w[i] = a.dWin[i];
+    for (long long i = i0; i < (long long)dip * D; i += stride) {
+      float v = a.dWin[i];
+      for (int p = 0; p < a.dWin_parts; ++p) v += a.dWin_part[(long long)p * dip * D + i];
+      g.in_proj_w[i] = v;
+    }
   if (g.out_proj_w)
     for (long long i = i0; i < (long long)D * 2 * Di; i += stride) g.out_proj_w[i] = a1 * a.dWout[i];
   for (long long i = i0; i < Di; i += stride) {
@@ -652,6 +660,8 @@ struct BwdWs {
     size_t z0 = c.off;
     zero_begin = p ? (float*)((char*)p + z0) : nullptr;
     acc.dWin = c.take<float>((size_t)d.dip * d.D);
+    acc.dWin_part = nullptr;
+    acc.dWin_parts = 0;
     acc.dWout = c.take<float>((size_t)d.D * 2 * d.Di);
     acc.dgamma = c.take<float>(d.Di);
     acc.dbeta = c.take<float>(d.Di);

@@ -158,25 +158,37 @@ k_inproj(const bf16* __restrict__ u, const bf16* __restrict__ Whi, const bf16* _
       parity ^= 1;
       tc_fence_after();
       if (!ok) { if (tid == 0) atomicExch(status, 1); break; }
-      const long long row = (long long)tile * 128 + tid;
-      bf16* dst = raw + row * ldr + n0;
+      // epilogue: TMEM -> registers -> bf16 -> padded row-major staging tile (conflict-free 16-byte row writes),
+      // then a cooperative copy-out in which consecutive threads write consecutive 16-byte chunks of a row
+      uint8_t* stg = reinterpret_cast<uint8_t*>(sA0 + 2 * 128 * D);
+      const int pitch = nn * 2 + 16;
       for (int c = 0; c < nn; c += 32) {
         float v0[16], v1[16];
         tmem_ld16(tmem_addr(tbase, warp * 32, c), v0);
         if (c + 16 < nn) tmem_ld16(tmem_addr(tbase, warp * 32, c + 16), v1);
         tmem_wait_ld();
-        if (row < T) {
-          float a[8], b[8];
+        float a[8], b[8];
+        uint8_t* srow = stg + tid * pitch + c * 2;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { a[j] = v0[j]; b[j] = v0[8 + j]; }
-          *reinterpret_cast<uint4*>(dst + c) = pack8(a);
-          *reinterpret_cast<uint4*>(dst + c + 8) = pack8(b);
-          if (c + 16 < nn) {
+        for (int j = 0; j < 8; ++j) { a[j] = v0[j]; b[j] = v0[8 + j]; }
+        *reinterpret_cast<uint4*>(srow) = pack8(a);
+        *reinterpret_cast<uint4*>(srow + 16) = pack8(b);
+        if (c + 16 < nn) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { a[j] = v1[j]; b[j] = v1[8 + j]; }
-            *reinterpret_cast<uint4*>(dst + c + 16) = pack8(a);
-            *reinterpret_cast<uint4*>(dst + c + 24) = pack8(b);
-          }
+          for (int j = 0; j < 8; ++j) { a[j] = v1[j]; b[j] = v1[8 + j]; }
+          *reinterpret_cast<uint4*>(srow + 32) = pack8(a);
+          *reinterpret_cast<uint4*>(srow + 48) = pack8(b);
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+      {
+        const int nch = nn >> 3;
+        const long long row0 = (long long)tile * 128;
+        const int rows = (int)min((long long)128, T - row0);
+        for (int i = tid; i < rows * nch; i += 128) {
+          const int r = i / nch, ch = i % nch;
+          *reinterpret_cast<uint4*>(raw + (row0 + r) * ldr + n0 + ch * 8) = *reinterpret_cast<const uint4*>(stg + r * pitch + ch * 16);
         }
       }
       tc_fence_before();   // TMEM reads of this tile are ordered before the next tile's MMA (after the next __syncthreads)
@@ -238,19 +250,30 @@ k_state(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int
   const uint32_t idesc = make_idesc_rt(128, GN, true, true);
   int it = 0;
   bool ok = true;
-  for (int i = part; i < tiles_per_batch; i += ctas_per_batch, ++it) {
-    const int stage = it & 1;
+  auto issue_loads = [&](int i, int stage) {
     bf16* sX = sbase + stage * STAGE;
     bf16* sB = sX + 16 * 128 * 8;
     bf16* sDt = sB + BC * 128 * 8;
-    if (it >= 2) ok = ok && mbar_wait(&bar[stage], ((it >> 1) - 1) & 1);   // the MMAs that read this stage are done
     const int rows = min(128, L - i * 128);
     const long long tok0 = (long long)b * L + (long long)i * 128;
     load_tile_t8(sX, act + tok0 * CC + DI, CC, XC, rows, tid, 128);
     load_tile_t8(sB, act + tok0 * CC + 2 * DI, CC, BC, rows, tid, 128);
     load_tile_t8(sDt, raw + tok0 * ldr + CC, ldr, DC, rows, tid, 128);
+  };
+  if (part < tiles_per_batch) issue_loads(part, 0);
+  cp_async_commit();
+  for (int i = part; i < tiles_per_batch; i += ctas_per_batch, ++it) {
+    const int stage = it & 1;
+    bf16* sX = sbase + stage * STAGE;
+    bf16* sB = sX + 16 * 128 * 8;
+    bf16* sDt = sB + BC * 128 * 8;
+    // prefetch the next tile into the other stage once the MMAs that read it (iteration it-1) are done
+    if (i + ctas_per_batch < tiles_per_batch) {
+      if (it >= 1) ok = ok && mbar_wait(&bar[stage ^ 1], ((it - 1) >> 1) & 1);
+      issue_loads(i + ctas_per_batch, stage ^ 1);
+    }
     cp_async_commit();
-    cp_async_wait<0>();
+    cp_async_wait<1>();
     __syncthreads();
     float w[NH];
 #pragma unroll
@@ -932,32 +955,26 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
 // ------------------------------------------------------------------------------------------------
 template <int D, int MB>
 __global__ void __launch_bounds__(128)
-k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__ u, const bf16* __restrict__ Whi,
-       const bf16* __restrict__ Wlo, bf16* __restrict__ du, float* __restrict__ dWin, long long T, int num_tiles,
+k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__ u, const bf16* __restrict__ WThi,
+       const bf16* __restrict__ WTlo, bf16* __restrict__ du, float* __restrict__ dWin_part, long long T, int num_tiles,
        int tiles_per_cta, int* __restrict__ status) {
   constexpr int DC = D / 8;
+  constexpr int STAGE = (16 * MB + DC) * 128 * 8;   // bf16 elements per stage: draw tile (padded to 16*MB chunks) + u tile
   constexpr uint32_t TCOLS = (D + MB * D) <= 128 ? 128 : 256;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int JC = dip / 8;                          // real 8-channel chunks of draw
-  bf16* sDraw = reinterpret_cast<bf16*>(smem);     // [16*MB][128][8], chunks >= JC stay zero
-  bf16* sU = sDraw + 16 * MB * 128 * 8;            // [DC][128][8]
-  bf16* sWhi = sU + DC * 128 * 8;                  // [JC][D][8]   W_in^T: row d, K = j
+  bf16* sStage = reinterpret_cast<bf16*>(smem);    // 2 x { [16*MB][128][8] draw (chunks >= JC stay zero), [DC][128][8] u }
+  bf16* sWhi = sStage + 2 * STAGE;                 // [16*MB][D][8]   W_in^T: row d, K = j
   bf16* sWlo = sWhi + 16 * MB * D * 8;
   const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < (16 * MB - JC) * 128; i += 128)
-    *reinterpret_cast<uint4*>(sDraw + (JC * 128 + i) * 8) = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = tid; i < JC * D; i += 128) {
-    int jc = i / D, d = i % D;
-    float h[8], l[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      h[q] = __bfloat162float(Whi[(long long)(jc * 8 + q) * D + d]);
-      l[q] = __bfloat162float(Wlo[(long long)(jc * 8 + q) * D + d]);
-    }
-    *reinterpret_cast<uint4*>(sWhi + (jc * D + d) * 8) = pack8(h);
-    *reinterpret_cast<uint4*>(sWlo + (jc * D + d) * 8) = pack8(l);
+  for (int st = 0; st < 2; ++st)
+    for (int i = tid; i < (16 * MB - JC) * 128; i += 128)
+      *reinterpret_cast<uint4*>(sStage + st * STAGE + (JC * 128 + i) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 16 * MB * D; i += 128) {   // the W_in^T images were laid out by k_prep: straight 16-byte copies
+    *reinterpret_cast<uint4*>(sWhi + i * 8) = __ldg(reinterpret_cast<const uint4*>(WThi + i * 8));
+    *reinterpret_cast<uint4*>(sWlo + i * 8) = __ldg(reinterpret_cast<const uint4*>(WTlo + i * 8));
   }
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
@@ -968,15 +985,28 @@ k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__
   uint32_t ph = 0;
   bool fresh = true, ok = true;
   const int tile_begin = blockIdx.x * tiles_per_cta, tile_end = min(num_tiles, tile_begin + tiles_per_cta);
-  for (int tile = tile_begin; tile < tile_end; ++tile) {
+  auto issue_loads = [&](int tile, int stage) {
     const long long tok0 = (long long)tile * 128;
     const int rows = (int)min((long long)128, T - tok0);
+    bf16* sDraw = sStage + stage * STAGE;
     load_tile_t8(sDraw, draw + tok0 * ldr, ldr, JC, rows, tid, 128);
-    load_tile_t8(sU, u + tok0 * D, D, DC, rows, tid, 128);
+    load_tile_t8(sDraw + 16 * MB * 128 * 8, u + tok0 * D, D, DC, rows, tid, 128);
+  };
+  if (tile_begin < tile_end) issue_loads(tile_begin, 0);
+  cp_async_commit();
+  for (int tile = tile_begin, it = 0; tile < tile_end; ++tile, ++it) {
+    const int stage = it & 1;
+    // prefetch the next tile into the other stage: its previous reader (the MMAs of tile-1) completed before the
+    // epilogue of the previous iteration, and every thread passed that iteration's trailing __syncthreads
+    if (tile + 1 < tile_end) issue_loads(tile + 1, stage ^ 1);
     cp_async_commit();
-    cp_async_wait<0>();
+    cp_async_wait<1>();
     fence_async_smem();
     __syncthreads();
+    const long long tok0 = (long long)tile * 128;
+    const int rows = (int)min((long long)128, T - tok0);
+    bf16* sDraw = sStage + stage * STAGE;
+    bf16* sU = sDraw + 16 * MB * 128 * 8;
     if (tid == 0) {
       tc_fence_after();
       const uint32_t aR = smem_u32(sDraw), bh = smem_u32(sWhi), bl = smem_u32(sWlo), bU = smem_u32(sU);
@@ -1011,18 +1041,27 @@ k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__
     tc_fence_before();
     __syncthreads();
   }
-  if (ok && !fresh) {
+  cp_async_wait<0>();
+  {
+    // one private slab of dip*D partial sums per CTA (summed by k_finalize): no atomics, deterministic
+    float* slab = dWin_part + (long long)blockIdx.x * dip * D;
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb) {
       const int j = mb * 128 + tid;
 #pragma unroll
       for (int cb = 0; cb < D; cb += 16) {
         float v[16];
-        tmem_ld16(tmem_addr(tbase, warp * 32, D + mb * D + cb), v);
-        tmem_wait_ld();
+        if (ok && !fresh) {
+          tmem_ld16(tmem_addr(tbase, warp * 32, D + mb * D + cb), v);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = 0.f;
+        }
         if (j < dip) {
 #pragma unroll
-          for (int q = 0; q < 16; ++q) atomicAdd(dWin + (long long)j * D + cb + q, v[q]);
+          for (int q = 0; q < 16; q += 4)
+            *reinterpret_cast<float4*>(slab + (long long)j * D + cb + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
         }
       }
     }
@@ -1032,11 +1071,37 @@ k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__
   if (warp == 0) tmem_dealloc(tbase, TCOLS);
 }
 
+// acc[i] += sum_p part[p][i]   (per-CTA partial slabs of dW_in); block = 32 elements x 8 part-lanes
+__global__ void __launch_bounds__(256)
+k_reduce_parts(const float* __restrict__ part, float* __restrict__ acc, int n, int parts) {
+  __shared__ float red[8][33];
+  const int e = blockIdx.x * 32 + (threadIdx.x & 31), pl = threadIdx.x >> 5;
+  float v = 0.f;
+  if (e < n)
+    for (int p = pl; p < parts; p += 8) v += part[(long long)p * n + e];
+  red[pl][threadIdx.x & 31] = v;
+  __syncthreads();
+  if (pl == 0 && e < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
+    acc[e] += t;
+  }
+}
+
 // One launch for all per-call weight preparation: conv kernel assembly, in_proj hi/lo split, out_proj -> bf16.
 __global__ void k_prep(ConvWeightPtrs cw, float* __restrict__ Kc, int Di, int CC, const float* __restrict__ win,
                        bf16* __restrict__ whi, bf16* __restrict__ wlo, int n_in, const float* __restrict__ wout,
-                       bf16* __restrict__ wout_bf, int n_out) {
+                       bf16* __restrict__ wout_bf, int n_out, bf16* __restrict__ wt_hi, bf16* __restrict__ wt_lo, int n_wt,
+                       int D, int dip) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wt_hi != nullptr && i < n_wt) {   // element ((jc*D + d)*8 + q) of the W_in^T image = W_in[jc*8+q][d]
+    const int q = i & 7, d = (i >> 3) % D, j = ((i >> 3) / D) * 8 + q;
+    const float v = j < dip ? win[j * D + d] : 0.f;
+    const bf16 h = __float2bfloat16_rn(v);
+    wt_hi[i] = h;
+    wt_lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
   if (i < CC) assemble_conv_channel(cw, Kc, Di, i);
   if (i < n_in) {
     const float v = win[i];
@@ -1121,123 +1186,126 @@ k_conv_fwd_tile(const bf16* __restrict__ raw, int ldr, const float* __restrict__
   }
 }
 
-// conv backward, tiled: dpre = dact * silu'(pre) is formed ONCE per element in shared memory (halo tile), then
-//   pass 1: draw[y,x] = sum_ab K[a][b] dpre[y-a+1][x-b+1]        (36 FFMA2 per row)
-//   pass 2: dK[a][b] += raw[y,x] * dpre[y-a+1][x-b+1]            (36 FFMA2 per row, per-thread fp32 accumulators)
-// and the per-thread dK are reduced through shared memory before one global atomic per (channel, tap) per CTA.
-__global__ void __launch_bounds__(128)
+// conv backward, tiled.  dpre = dact * SiLU'(pre) is formed ONCE per element in the shared-memory halo tile (pre is
+// streamed straight from global by the thread that fetched the matching dact chunk), then ONE pass per output row does
+//   draw[y,x]  = sum_ab K[a][b] dpre[y-a+1][x-b+1]      and      dK[a][b] += raw[y,x] * dpre[y-a+1][x-b+1]
+// sharing the unpacked register window.  256 threads: thread = (column, 4-channel half chunk) so that window (18) +
+// taps (18) + kernel-gradient accumulators (18 float2) fit in registers.  dK is reduced by shuffles + shared-memory
+// atomics, then one global atomic per (channel, tap) per CTA.
+__device__ __forceinline__ void unpack4_f2(const uint2& u, float2 (&v)[2]) {
+  v[0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+  v[1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+
+__global__ void __launch_bounds__(256)
 k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, const bf16* __restrict__ raw, int ldr,
                 const float* __restrict__ Kc, bf16* __restrict__ draw, float* __restrict__ dK, int H, int W, int CC,
                 int slabs) {
-  extern __shared__ __align__(16) uint8_t csm[];
-  uint4* tD = reinterpret_cast<uint4*>(csm);          // dact -> dpre, halo tile
-  uint4* tP = tD + CT_YH * CT_XH * 4;                 // pre, halo tile
-  uint4* tR = tP + CT_YH * CT_XH * 4;                 // raw, centre tile (CT_Y x CT_X)
-  float* red = reinterpret_cast<float*>(tR + CT_Y * CT_X * 4);   // [32 channels][9]
+  __shared__ uint4 tD[CT_YH * CT_XH * 4];   // dact -> dpre, halo tile
+  __shared__ float red[32 * 9];
   const int tid = threadIdx.x;
   const int b = blockIdx.z / slabs, slab = blockIdx.z % slabs;
   const int x0 = blockIdx.x * CT_X, y0 = blockIdx.y * CT_Y, c0 = slab * 32;
   const long long boff = (long long)b * H * W;
-  conv_tile_load(tD, dact + boff * CC + c0, CC, H, W, y0, x0, 1, tid);
-  conv_tile_load(tP, pre + boff * CC + c0, CC, H, W, y0, x0, 1, tid);
-  conv_tile_load(tR, raw + boff * ldr + c0, ldr, H, W, y0, x0, 0, tid);
-  cp_async_commit();
-  for (int i = tid; i < 32 * 9; i += 128) red[i] = 0.f;
-  const int xl = tid >> 2, ch = tid & 3, cc = c0 + ch * 8;
-  cp_async_wait<0>();
-  __syncthreads();
-  for (int i = tid; i < CT_YH * CT_XH * 4; i += 128) {
-    float g[8], p[8];
-    unpack8(tD[i], g);
-    unpack8(tP[i], p);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float sgm = sigmoid_fast(p[j]);
-      g[j] *= sgm * (1.f + p[j] * (1.f - sgm));
+  {
+    const bf16* g = dact + boff * CC + c0;
+    for (int i = tid; i < CT_YH * CT_XH * 4; i += 256) {
+      const int chn = i & 3, c = (i >> 2) % CT_XH, r = (i >> 2) / CT_XH;
+      const int y = y0 - 1 + r, x = x0 - 1 + c;
+      const bool ok = y >= 0 && y < H && x >= 0 && x < W;
+      cp_async16(tD + i, g + ((long long)(ok ? y : 0) * W + (ok ? x : 0)) * CC + chn * 8, ok ? 16 : 0);
     }
-    tD[i] = pack8(g);
+  }
+  cp_async_commit();
+  for (int i = tid; i < 32 * 9; i += 256) red[i] = 0.f;
+  const int xl = tid >> 3, hc = tid & 7, cc = c0 + hc * 4;   // hc: 4-channel half chunk inside the 32-channel slab
+  float2 k2[9][2];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int p = 0; p < 2; ++p) k2[t][p] = make_float2(__ldg(Kc + (cc + 2 * p) * 9 + t), __ldg(Kc + (cc + 2 * p + 1) * 9 + t));
+  // each thread multiplies exactly the chunks it fetched itself: only its own cp.async group has to be complete
+  cp_async_wait<0>();
+  {
+    const bf16* ps = pre + boff * CC + c0;
+    for (int i = tid; i < CT_YH * CT_XH * 4; i += 256) {
+      const int chn = i & 3, c = (i >> 2) % CT_XH, r = (i >> 2) / CT_XH;
+      const int y = y0 - 1 + r, x = x0 - 1 + c;
+      if (y >= 0 && y < H && x >= 0 && x < W) {
+        float g[8], p[8];
+        unpack8(tD[i], g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(ps + ((long long)y * W + x) * CC + chn * 8)), p);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float sgm = sigmoid_fast(p[j]);
+          g[j] *= sgm * (1.f + p[j] * (1.f - sgm));
+        }
+        tD[i] = pack8(g);
+      }
+    }
   }
   __syncthreads();
   const int x = x0 + xl;
   const int ny = min(CT_Y, H - y0);
   const bool xin = x < W;   // columns beyond the image compute on zero-filled tile data and never store
-  float2 dk[9][4];
-  {
-    float2 win[3][3][4];
-    auto load_row = [&](int r, float2 (&w3)[3][4]) {
+  const uint2* tD2 = reinterpret_cast<const uint2*>(tD);
+  float2 dk[9][2], win[3][3][2];
 #pragma unroll
-      for (int s = 0; s < 3; ++s) unpack8_f2(tD[(r * CT_XH + xl + s) * 4 + ch], w3[s]);
-    };
-    {  // pass 1: transposed convolution
-      float2 k2[9][4];
+  for (int t = 0; t < 9; ++t) { dk[t][0] = make_float2(0.f, 0.f); dk[t][1] = make_float2(0.f, 0.f); }
+  auto load_row = [&](int r, float2 (&w3)[3][2]) {
 #pragma unroll
-      for (int t = 0; t < 9; ++t)
+    for (int s = 0; s < 3; ++s) unpack4_f2(tD2[(r * CT_XH + xl + s) * 8 + hc], w3[s]);
+  };
+  load_row(0, win[0]);
+  load_row(1, win[1]);
+  const bf16* rsrc = raw + (boff + (long long)y0 * W + (xin ? x : 0)) * ldr + cc;
+  const uint2 zero2 = make_uint2(0u, 0u);
+  uint2 rnext = (xin && ny > 0) ? __ldg(reinterpret_cast<const uint2*>(rsrc)) : zero2;
+  for (int rb = 0; rb < ny; rb += 3) {
 #pragma unroll
-        for (int p = 0; p < 4; ++p) k2[t][p] = make_float2(__ldg(Kc + (cc + 2 * p) * 9 + t), __ldg(Kc + (cc + 2 * p + 1) * 9 + t));
-      load_row(0, win[0]);
-      load_row(1, win[1]);
-      for (int rb = 0; rb < ny; rb += 3) {
+    for (int ph = 0; ph < 3; ++ph) {
+      const int r = rb + ph;
+      if (r < ny) {
+        load_row(r + 2, win[(ph + 2) % 3]);
+        float2 rc[2], o[2];
+        unpack4_f2(rnext, rc);
+        rnext = (xin && r + 1 < ny) ? __ldg(reinterpret_cast<const uint2*>(rsrc + (long long)(r + 1) * W * ldr)) : zero2;
+        o[0] = make_float2(0.f, 0.f);
+        o[1] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int ph = 0; ph < 3; ++ph) {
-          const int r = rb + ph;
-          if (r < ny) {
-            load_row(r + 2, win[(ph + 2) % 3]);
-            float2 o[4];
+        for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) o[q] = make_float2(0.f, 0.f);
+          for (int bb = 0; bb < 3; ++bb)
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-              for (int bb = 0; bb < 3; ++bb)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) o[q] = __ffma2_rn(k2[a * 3 + bb][q], win[(ph + 2 - a) % 3][2 - bb][q], o[q]);
-            if (xin) *reinterpret_cast<uint4*>(draw + (boff + (long long)(y0 + r) * W + x) * ldr + cc) = pack8_f2(o);
-          }
-        }
-      }
-    }
-    {  // pass 2: kernel gradient
-#pragma unroll
-      for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dk[t][q] = make_float2(0.f, 0.f);
-      load_row(0, win[0]);
-      load_row(1, win[1]);
-      for (int rb = 0; rb < ny; rb += 3) {
-#pragma unroll
-        for (int ph = 0; ph < 3; ++ph) {
-          const int r = rb + ph;
-          if (r < ny) {
-            load_row(r + 2, win[(ph + 2) % 3]);
-            float2 rc[4];
-            unpack8_f2(tR[(r * CT_X + xl) * 4 + ch], rc);
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-              for (int bb = 0; bb < 3; ++bb)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) dk[a * 3 + bb][q] = __ffma2_rn(rc[q], win[(ph + 2 - a) % 3][2 - bb][q], dk[a * 3 + bb][q]);
-          }
+            for (int q = 0; q < 2; ++q) {
+              const float2 dv = win[(ph + 2 - a) % 3][2 - bb][q];
+              o[q] = __ffma2_rn(k2[a * 3 + bb][q], dv, o[q]);
+              dk[a * 3 + bb][q] = __ffma2_rn(rc[q], dv, dk[a * 3 + bb][q]);
+            }
+        if (xin) {
+          uint2 ov;
+          ov.x = pack_bf16(o[0].x, o[0].y);
+          ov.y = pack_bf16(o[1].x, o[1].y);
+          *reinterpret_cast<uint2*>(draw + (boff + (long long)(y0 + r) * W + x) * ldr + cc) = ov;
         }
       }
     }
   }
-  // reduce over the 32 columns of the tile (all lanes participate: columns beyond the image hold zeros):
-  // lanes of a warp = 8 columns x 4 chunks -> xor-shuffle over the column bits, then shared-memory atomics
+  // reduce over the columns: lanes of a warp = 4 columns x 8 half chunks -> xor-shuffle over the two column bits
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
       float vx = dk[t][q].x, vy = dk[t][q].y;
 #pragma unroll
-      for (int o = 4; o < 32; o <<= 1) { vx += __shfl_xor_sync(0xffffffffu, vx, o); vy += __shfl_xor_sync(0xffffffffu, vy, o); }
-      if ((tid & 31) < 4) {
-        atomicAdd(&red[(ch * 8 + 2 * q) * 9 + t], vx);
-        atomicAdd(&red[(ch * 8 + 2 * q + 1) * 9 + t], vy);
+      for (int o = 8; o < 32; o <<= 1) { vx += __shfl_xor_sync(0xffffffffu, vx, o); vy += __shfl_xor_sync(0xffffffffu, vy, o); }
+      if ((tid & 31) < 8) {
+        atomicAdd(&red[(hc * 4 + 2 * q) * 9 + t], vx);
+        atomicAdd(&red[(hc * 4 + 2 * q + 1) * 9 + t], vy);
       }
     }
   __syncthreads();
-  for (int i = tid; i < 32 * 9; i += 128)
+  for (int i = tid; i < 32 * 9; i += 256)
     if (red[i] != 0.f) atomicAdd(dK + c0 * 9 + i, red[i]);
 }
 
@@ -1246,6 +1314,9 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
 // ------------------------------------------------------------------------------------------------
 struct FastWs {           // placed after the generic workspace of the same pass
   bf16 *Whi, *Wlo, *Wout;
+  bf16 *WT_hi, *WT_lo;   // W_in^T as a K-major B operand image: [ceil(dip/128)*16 chunks][D][8], zero padded
+  float* dWin_part;      // [148][dip*D] per-CTA partial sums of dW_in (k_bwd4)
+  int wt_chunks;
   float *Rt, *sdout;     // k_bwd1 accumulators: Rt[2Di][D], sdout[D] (contiguous, zeroed together)
   int* status;
   size_t bytes;
@@ -1254,6 +1325,10 @@ struct FastWs {           // placed after the generic workspace of the same pass
     Whi = c.take<bf16>((size_t)d.dip * d.D);
     Wlo = c.take<bf16>((size_t)d.dip * d.D);
     Wout = c.take<bf16>((size_t)d.D * 2 * d.Di);
+    wt_chunks = 16 * cdiv(d.dip, 128);
+    WT_hi = c.take<bf16>((size_t)wt_chunks * d.D * 8);
+    WT_lo = c.take<bf16>((size_t)wt_chunks * d.D * 8);
+    dWin_part = c.take<float>((size_t)148 * d.dip * d.D);
     Rt = c.take<float>((size_t)2 * d.Di * d.D + d.D);
     sdout = Rt ? Rt + (size_t)2 * d.Di * d.D : nullptr;
     status = c.take<int>(64);
@@ -1305,12 +1380,8 @@ void sm100_workspace_bytes(const MixerDims& d, size_t* f, size_t* b) {
 template <int D>
 static int launch_inproj(const MixerDims& d, const bf16* u, const FastWs& F, bf16* raw, cudaStream_t st) {
   const int num_tiles = cdiv(d.T, 128);
-  const size_t smem = (size_t)(2 * 256 * D + 2 * 128 * D) * sizeof(bf16);
-  static bool attr_set = false;
-  if (!attr_set) {
-    ADN_CHECK_CUDA(cudaFuncSetAttribute(k_inproj<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  const size_t smem = (size_t)(2 * 256 * D + 2 * 128 * D) * sizeof(bf16) + 128 * (size_t)(min(256, d.dip) * 2 + 16);
+  ADN_CHECK_CUDA(cudaFuncSetAttribute(k_inproj<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(num_tiles, 148 * 2);
   { ADN_KERNEL("k_inproj", st); k_inproj<D><<<grid, 128, smem, st>>>(u, F.Whi, F.Wlo, raw, d.ldr, d.dip, d.T, num_tiles, F.status); }
   return ADN_OK;
@@ -1350,15 +1421,17 @@ static int launch_bwd2(const MixerDims& d, const bf16* act, const bf16* raw, con
 }
 
 template <int D, int MB>
-static int launch_bwd4(const MixerDims& d, const bf16* draw, const bf16* u, const FastWs& F, bf16* du, float* dWin,
+static int launch_bwd4(const MixerDims& d, const bf16* draw, const bf16* u, const FastWs& F, bf16* du, GradAcc* acc,
                        cudaStream_t st) {
-  constexpr size_t smem = ((size_t)(16 * MB + D / 8) * 128 * 8 + 2 * 16 * MB * D * 8) * sizeof(bf16);
+  constexpr size_t smem = (2 * (size_t)(16 * MB + D / 8) * 128 * 8 + 2 * 16 * MB * D * 8) * sizeof(bf16);
+  static_assert(smem <= 227 * 1024, "k_bwd4 stages do not fit shared memory");
   int rc = set_smem(k_bwd4<D, MB>, smem);
   if (rc) return rc;
   const int nt = cdiv(d.T, 128);
   int grid, per;
-  split_tiles(nt, smem > 110 * 1024 ? 1 : 2, &grid, &per);
-  { ADN_KERNEL("k_bwd4", st); k_bwd4<D, MB><<<grid, 128, smem, st>>>(draw, d.ldr, d.dip, u, F.Whi, F.Wlo, du, dWin, d.T, nt, per, F.status); }
+  split_tiles(nt, 1, &grid, &per);      // one CTA per SM (<= 148 partial slabs)
+  { ADN_KERNEL("k_bwd4", st); k_bwd4<D, MB><<<grid, 128, smem, st>>>(draw, d.ldr, d.dip, u, F.WT_hi, F.WT_lo, du, F.dWin_part, d.T, nt, per, F.status); }
+  { ADN_KERNEL("k_reduce_parts", st); k_reduce_parts<<<cdiv(d.dip * d.D, 32), 256, 0, st>>>(F.dWin_part, acc->dWin, d.dip * d.D, grid); }
   return ADN_OK;
 }
 
@@ -1373,7 +1446,7 @@ int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* 
   ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
   {
     const int n_in = d.dip * d.D, n_out = d.D * 2 * d.Di, n = max(max(n_in, n_out), d.CC);
-    { ADN_KERNEL("k_prep", st); k_prep<<<cdiv(n, 256), 256, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC, w.in_proj_w, F.Whi, F.Wlo, n_in, w.out_proj_w, F.Wout, n_out); }
+    { ADN_KERNEL("k_prep", st); k_prep<<<cdiv(n, 256), 256, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC, w.in_proj_w, F.Whi, F.Wlo, n_in, w.out_proj_w, F.Wout, n_out, nullptr, nullptr, 0, d.D, d.dip); }
   }
   // (1) in_proj on tcgen05
   int rc = d.D == 16 ? launch_inproj<16>(d, u, F, S.raw, st) : d.D == 32 ? launch_inproj<32>(d, u, F, S.raw, st)
@@ -1407,8 +1480,9 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   ADN_CHECK_CUDA(cudaMemsetAsync(F.Rt, 0, ((size_t)2 * d.Di * d.D + d.D) * sizeof(float), st));
   ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
   {
-    const int n_in = d.dip * d.D, n_out = d.D * 2 * d.Di, n = max(max(n_in, n_out), d.CC);
-    { ADN_KERNEL("k_prep", st); k_prep<<<cdiv(n, 256), 256, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC, w.in_proj_w, F.Whi, F.Wlo, n_in, w.out_proj_w, F.Wout, n_out); }
+    const int n_in = d.dip * d.D, n_out = d.D * 2 * d.Di, n_wt = F.wt_chunks * d.D * 8;
+    const int n = max(max(max(n_in, n_out), d.CC), n_wt);
+    { ADN_KERNEL("k_prep", st); k_prep<<<cdiv(n, 256), 256, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC, w.in_proj_w, F.Whi, F.Wlo, n_in, w.out_proj_w, F.Wout, n_out, F.WT_hi, F.WT_lo, n_wt, d.D, d.dip); }
   }
   // ---- phase B1: dout -> dy, dzc, dCc ; reductions Rt, dS'
   int rc = d.GN == 32 ? launch_bwd1<64, 32>(d, dout, S.act, S.S, w, F, W.dact, W.dS, st)
@@ -1422,17 +1496,18 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   // ---- conv backward (dpre formed in shared memory; transposed conv + kernel gradient)
   {
     const int slabs = d.CC / 32;
-    const size_t smem = (size_t)(2 * CT_YH * CT_XH * 4 + CT_Y * CT_X * 4) * 16 + 32 * 9 * sizeof(float);
-    rc = set_smem(k_conv_bwd_tile, smem);
-    if (rc) return rc;
     dim3 grid(cdiv(d.W, CT_X), cdiv(d.H, CT_Y), d.B * slabs);
-    { ADN_KERNEL("k_conv_bwd_tile", st); k_conv_bwd_tile<<<grid, 128, smem, st>>>(W.dact, S.pre, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.H, d.W, d.CC, slabs); }
+    { ADN_KERNEL("k_conv_bwd_tile", st); k_conv_bwd_tile<<<grid, 256, 0, st>>>(W.dact, S.pre, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.H, d.W, d.CC, slabs); }
   }
   // ---- in_proj backward
-  rc = d.dip <= 128 ? launch_bwd4<32, 1>(d, W.draw, u, F, du, W.acc.dWin, st)
-       : d.dip <= 256 ? launch_bwd4<32, 2>(d, W.draw, u, F, du, W.acc.dWin, st)
-                      : launch_bwd4<32, 4>(d, W.draw, u, F, du, W.acc.dWin, st);
-  if (rc) return rc;
+  if (d.dip <= 256) {
+    rc = d.dip <= 128 ? launch_bwd4<32, 1>(d, W.draw, u, F, du, &W.acc, st)
+                      : launch_bwd4<32, 2>(d, W.draw, u, F, du, &W.acc, st);
+    if (rc) return rc;
+  } else {  // wide in_proj (d_state 64): generic GEMMs for this stage
+    launch_gemm<TWf, T, false>(st, W.draw, d.ldr, 0, w.in_proj_w, d.D, 0, du, d.D, 0, (int)d.T, d.D, d.dip, 1, nullptr, 0);
+    launch_reduce_gemm<TWf, T>(st, W.draw, d.ldr, u, d.D, W.acc.dWin, d.D, 0, d.dip, d.D, (int)d.T, 1, 0);
+  }
   { ADN_KERNEL("k_finalize", st); k_finalize<<<148, 256, 0, st>>>(W.acc, w, g, d.D, d.Di, d.GN, d.nh, d.dip); }
   ADN_CHECK_LAUNCH();
   return ADN_OK;

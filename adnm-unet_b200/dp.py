@@ -38,29 +38,24 @@ class GradAllReducer:
 
     @torch.no_grad()
     def __call__(self):
+        """One gather kernel (torch.cat into the flat bucket), one all-reduce, one scale; afterwards every p.grad is a
+        VIEW into the flat bucket (no scatter copies) - valid until the next call."""
         if self.present is None:
             self._presence()
-        off = 0
-        for p, n, pres in zip(self.params, self.sizes, self.present):
-            if pres:
-                if p.grad is None:
-                    self.flat[off:off + n].zero_()
-                else:
-                    self.flat[off:off + n].copy_(p.grad.reshape(-1))
-                off += n
-        used = self.flat[:off]
+        live = [(p, n) for p, n, pres in zip(self.params, self.sizes, self.present) if pres]
+        total = sum(n for _, n in live)
+        used = self.flat[:total]
+        pieces = [(p.grad.reshape(-1).to(self.flat.dtype) if p.grad is not None
+                   else torch.zeros(n, dtype=self.flat.dtype, device=self.flat.device)) for p, n in live]
+        if pieces:
+            torch.cat(pieces, out=used)
         if self.world > 1:
             dist.all_reduce(used, group=self.group)
             used.mul_(1.0 / self.world)
         off = 0
-        for p, n, pres in zip(self.params, self.sizes, self.present):
-            if pres:
-                g = used[off:off + n].view_as(p)
-                if p.grad is None:
-                    p.grad = g.clone()
-                else:
-                    p.grad.copy_(g)
-                off += n
+        for p, n in live:
+            p.grad = used[off:off + n].view_as(p)
+            off += n
         return used
 
     def grad_norm(self):

@@ -147,6 +147,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its banner there)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     assert lib.adn_device_supported() == 1
