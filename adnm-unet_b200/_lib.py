@@ -61,6 +61,8 @@ EXPORTS = {
     "adn_prof_enable": (C.c_int, [C.c_int]),
     "adn_prof_count": (C.c_int, []),
     "adn_prof_get": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
+    "adn_phase_enable": (C.c_int, [C.c_int]),
+    "adn_phase_read": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "adn_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -19,12 +19,12 @@ def _stale():
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, phase_timing=False):
     if not force and not _stale():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + (["-DADN_PHASE_TIMING"] if phase_timing else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
@@ -34,4 +34,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv or "--phase-timing" in sys.argv, verbose="-v" in sys.argv,
+                phase_timing="--phase-timing" in sys.argv))

@@ -14,6 +14,27 @@ namespace adn {
 using namespace sm100;
 typedef bf16 TWf;   // workspace intermediates of the fast path are bf16 (tensor-core operands)
 
+// ---- optional in-kernel phase timers (diagnostics, adn_phase_*): thread 0 of every CTA adds the SM-clock cycles spent
+// between consecutive PHASE marks into g_phase[kernel][phase]; disabled (one predicated branch per mark) by default.
+__device__ unsigned long long g_phase[8][8];
+__device__ int g_phase_on = 0;
+#ifdef ADN_PHASE_TIMING     // build with -DADN_PHASE_TIMING (python -m adnm_unet_b200.build --phase-timing); costs registers
+struct PhaseTimer {
+  long long t;
+  int kid;
+  bool on;
+  __device__ __forceinline__ PhaseTimer(int k) : t(0), kid(k), on(g_phase_on != 0 && threadIdx.x == 0) { if (on) t = clock64(); }
+  __device__ __forceinline__ void mark(int ph) {
+    if (on) { long long n = clock64(); atomicAdd(&g_phase[kid][ph], (unsigned long long)(n - t)); t = n; }
+  }
+};
+#else
+struct PhaseTimer {
+  __device__ __forceinline__ PhaseTimer(int) {}
+  __device__ __forceinline__ void mark(int) {}
+};
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // UMMA self-test: one CTA, one 128 x N x K problem, operands staged in the T8 layout.
 //   mode 0: A[128][K], B[N][K] row-major (both K-major):   C = A . B^T
@@ -85,12 +106,21 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // writes, 8 x (CH*16)-byte contiguous global segments.  Rows >= rows_valid are zero-filled.
 __device__ __forceinline__ void load_tile_t8(bf16* sdst, const bf16* __restrict__ gsrc, long long ld, int CH,
                                              int rows_valid, int tid, int nthreads) {
-  for (int i = tid; i < 128 * CH; i += nthreads) {
-    int tok8 = i & 7, rest = i >> 3;
-    int chunk = rest % CH, tok = (rest / CH) * 8 + tok8;
-    bool ok = tok < rows_valid;
-    const bf16* src = gsrc + (long long)(ok ? tok : 0) * ld + chunk * 8;
-    cp_async16(sdst + (chunk * 128 + tok) * 8, src, ok ? 16 : 0);
+  // lane = (token-in-block tok8, chunk-in-group cq): one warp instruction moves 8 tokens x 4 consecutive chunks.
+  // Warps stride over the 16 token blocks, an inner loop strides over the chunk groups: adds only, no div / mod.
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+  const int tok8 = lane & 7, cq = lane >> 3;
+  for (int tb = warp; tb < 16; tb += nwarps) {
+    const int tok = tb * 8 + tok8;
+    const bool ok = tok < rows_valid;
+    const bf16* src = gsrc + (long long)(ok ? tok : 0) * ld + cq * 8;
+    bf16* dst = sdst + (cq * 128 + tok) * 8;
+    const int nb = ok ? 16 : 0;
+    for (int c = cq; c < CH; c += 4) {
+      cp_async16(dst, src, nb);
+      src += 32;
+      dst += 4 * 128 * 8;
+    }
   }
 }
 
@@ -551,6 +581,7 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
+  PhaseTimer pt(0);
   const float a1 = *alpha1p;
   uint32_t ph = 0;
   int cur_b = -1;
@@ -573,9 +604,11 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
     load_tile_t8(sCat + XC * 128 * 8, act + tok0 * CC, CC, XC, rows, tid, 128);
     load_tile_t8(sXY, act + tok0 * CC + DI, CC, XC, rows, tid, 128);
     cp_async_commit();
+    pt.mark(0);
     cp_async_wait<0>();
     fence_async_smem();
     __syncthreads();
+    pt.mark(1);
     if (tid == 0) {
       tc_fence_after();
       const uint32_t aD = smem_u32(sDout), bW = smem_u32(sWT), aC = smem_u32(sC), bh = smem_u32(sSa_hi), bl = smem_u32(sSa_lo);
@@ -591,6 +624,7 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
     ok = mbar_wait(&bar, ph);
     ph ^= 1;
     tc_fence_after();
+    pt.mark(2);
     if (!ok) { if (tid == 0) atomicExch(status, 5); break; }
     // ---- y, LayerNorm statistics, yhat
     float y[DI];
@@ -622,6 +656,7 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
       for (int j = 0; j < 8; ++j) { y[cg * 8 + j] *= rstd; v[j] = y[cg * 8 + j]; }
       *reinterpret_cast<uint4*>(sCat + (cg * 128 + tid) * 8) = pack8(v);
     }
+    pt.mark(3);
     // ---- LN backward: dyh = alpha1 * g_y * gamma ; dy = rstd * (dyh - mean(dyh) - yhat * mean(dyh*yhat))
     float m1 = 0.f, m2 = 0.f;
 #pragma unroll
@@ -676,6 +711,7 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
 #pragma unroll
       for (int j = 0; j < 8; ++j) sd[dc * 8 + j] += v[j];
     }
+    pt.mark(4);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -702,6 +738,7 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
     ok = mbar_wait(&bar, ph);
     ph ^= 1;
     tc_fence_after();
+    pt.mark(5);
     if (!ok) { if (tid == 0) atomicExch(status, 6); break; }
 #pragma unroll
     for (int cb = 0; cb < GN; cb += 16) {
@@ -731,6 +768,7 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
     }
     tc_fence_before();
     __syncthreads();
+    pt.mark(6);
   }
   if (ok && !rt_fresh) {
     for (int cb = 0; cb < D; cb += 16) {
@@ -812,6 +850,7 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
+  PhaseTimer pt(1);
   uint32_t ph = 0;
   int cur_b = -1;
   bool ok = true;
@@ -833,9 +872,11 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
     load_tile_t8(sDy, dact + tok0 * CC + DI, CC, XC, rows, tid, 128);
     load_tile_t8(sDt, raw + tok0 * ldr + CC, ldr, DC, rows, tid, 128);
     cp_async_commit();
+    pt.mark(0);
     cp_async_wait<0>();
     fence_async_smem();
     __syncthreads();
+    pt.mark(1);
     if (tid == 0) {
       tc_fence_after();
       const uint32_t aB_ = smem_u32(sB), bh = smem_u32(sTa_hi), bl = smem_u32(sTa_lo);
@@ -859,9 +900,11 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
         sg[dc * 8 + j] = a > 20.f ? 1.f : __fdividef(1.f, 1.f + __expf(-a));
       }
     }
+    pt.mark(2);
     ok = mbar_wait(&bar, ph);
     ph ^= 1;
     tc_fence_after();
+    pt.mark(3);
     if (!ok) { if (tid == 0) atomicExch(status, 7); break; }
     float dw[NH];
 #pragma unroll
@@ -906,6 +949,7 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
         if (valid) *reinterpret_cast<uint4*>(trow + dc * 8) = pack8(o);
       }
     }
+    pt.mark(4);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -922,6 +966,7 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
     ok = mbar_wait(&bar, ph);
     ph ^= 1;
     tc_fence_after();
+    pt.mark(5);
     if (!ok) { if (tid == 0) atomicExch(status, 8); break; }
 #pragma unroll
     for (int cb = 0; cb < GN; cb += 16) {
@@ -937,6 +982,7 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
     }
     tc_fence_before();
     __syncthreads();
+    pt.mark(6);
   }
 #pragma unroll
   for (int h = 0; h < NH; ++h) {
@@ -982,6 +1028,7 @@ k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
+  PhaseTimer pt(2);
   uint32_t ph = 0;
   bool fresh = true, ok = true;
   const int tile_begin = blockIdx.x * tiles_per_cta, tile_end = min(num_tiles, tile_begin + tiles_per_cta);
@@ -1000,9 +1047,11 @@ k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__
     // epilogue of the previous iteration, and every thread passed that iteration's trailing __syncthreads
     if (tile + 1 < tile_end) issue_loads(tile + 1, stage ^ 1);
     cp_async_commit();
+    pt.mark(0);
     cp_async_wait<1>();
     fence_async_smem();
     __syncthreads();
+    pt.mark(1);
     const long long tok0 = (long long)tile * 128;
     const int rows = (int)min((long long)128, T - tok0);
     bf16* sDraw = sStage + stage * STAGE;
@@ -1011,19 +1060,33 @@ k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__
       tc_fence_after();
       const uint32_t aR = smem_u32(sDraw), bh = smem_u32(sWhi), bl = smem_u32(sWlo), bU = smem_u32(sU);
       const uint32_t id_u = make_idesc_rt(128, D, false, false), id_w = make_idesc_rt(128, D, true, true);
-      for (int k = 0; k < dip; k += 16) umma(tbase, desc_kmajor(aR, 128, 0, k), desc_kmajor(bh, D, 0, k), id_u, k > 0);
-      for (int k = 0; k < dip; k += 16) umma(tbase, desc_kmajor(aR, 128, 0, k), desc_kmajor(bl, D, 0, k), id_u, true);
+      // descriptors advance by a constant per K step: 2 chunks of the K-major tiles, 16 token rows of the MN-major ones
+      uint64_t dA = desc_kmajor(aR, 128, 0, 0), dBh = desc_kmajor(bh, D, 0, 0), dBl = desc_kmajor(bl, D, 0, 0);
+      for (int k = 0; k < dip; k += 16) {
+        umma(tbase, dA, dBh, id_u, k > 0);
+        umma(tbase, dA, dBl, id_u, true);
+        dA = desc_advance(dA, 2 * 128 * 16);
+        dBh = desc_advance(dBh, 2 * D * 16);
+        dBl = desc_advance(dBl, 2 * D * 16);
+      }
 #pragma unroll
-      for (int mb = 0; mb < MB; ++mb)
+      for (int mb = 0; mb < MB; ++mb) {
+        uint64_t dAm = desc_mnmajor(aR, 128, mb * 128, 0), dU = desc_mnmajor(bU, 128, 0, 0);
 #pragma unroll
-        for (int k = 0; k < 128; k += 16)
-          umma(tbase + D + mb * D, desc_mnmajor(aR, 128, mb * 128, k), desc_mnmajor(bU, 128, 0, k), id_w, !fresh || k > 0);
+        for (int k = 0; k < 128; k += 16) {
+          umma(tbase + D + mb * D, dAm, dU, id_w, !fresh || k > 0);
+          dAm = desc_advance(dAm, 16 * 16);
+          dU = desc_advance(dU, 16 * 16);
+        }
+      }
       umma_commit(&bar);
     }
     fresh = false;
+    pt.mark(2);
     ok = mbar_wait(&bar, ph);
     ph ^= 1;
     tc_fence_after();
+    pt.mark(3);
     if (!ok) { if (tid == 0) atomicExch(status, 9); break; }
 #pragma unroll
     for (int cb = 0; cb < D; cb += 16) {
@@ -1040,8 +1103,10 @@ k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__
     }
     tc_fence_before();
     __syncthreads();
+    pt.mark(4);
   }
   cp_async_wait<0>();
+  pt.mark(5);
   {
     // one private slab of dip*D partial sums per CTA (summed by k_finalize): no atomics, deterministic
     float* slab = dWin_part + (long long)blockIdx.x * dip * D;
@@ -1204,6 +1269,7 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
   __shared__ uint4 tD[CT_YH * CT_XH * 4];   // dact -> dpre, halo tile
   __shared__ float red[32 * 9];
   const int tid = threadIdx.x;
+  PhaseTimer pt(3);
   const int b = blockIdx.z / slabs, slab = blockIdx.z % slabs;
   const int x0 = blockIdx.x * CT_X, y0 = blockIdx.y * CT_Y, c0 = slab * 32;
   const long long boff = (long long)b * H * W;
@@ -1225,7 +1291,9 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
 #pragma unroll
     for (int p = 0; p < 2; ++p) k2[t][p] = make_float2(__ldg(Kc + (cc + 2 * p) * 9 + t), __ldg(Kc + (cc + 2 * p + 1) * 9 + t));
   // each thread multiplies exactly the chunks it fetched itself: only its own cp.async group has to be complete
+  pt.mark(0);
   cp_async_wait<0>();
+  pt.mark(1);
   {
     const bf16* ps = pre + boff * CC + c0;
     for (int i = tid; i < CT_YH * CT_XH * 4; i += 256) {
@@ -1244,7 +1312,9 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
       }
     }
   }
+  pt.mark(2);
   __syncthreads();
+  pt.mark(3);
   const int x = x0 + xl;
   const int ny = min(CT_Y, H - y0);
   const bool xin = x < W;   // columns beyond the image compute on zero-filled tile data and never store
@@ -1291,6 +1361,7 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
       }
     }
   }
+  pt.mark(4);
   // reduce over the columns: lanes of a warp = 4 columns x 8 half chunks -> xor-shuffle over the two column bits
 #pragma unroll
   for (int t = 0; t < 9; ++t)
@@ -1307,6 +1378,7 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
   __syncthreads();
   for (int i = tid; i < 32 * 9; i += 256)
     if (red[i] != 0.f) atomicAdd(dK + c0 * 9 + i, red[i]);
+  pt.mark(5);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1514,6 +1586,21 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
 }
 
 }  // namespace adn
+
+extern "C" int adn_phase_enable(int on) {
+  using namespace adn;
+  unsigned long long zero[64] = {0};
+  ADN_CHECK_CUDA(cudaMemcpyToSymbol(g_phase, zero, sizeof(zero)));
+  ADN_CHECK_CUDA(cudaMemcpyToSymbol(g_phase_on, &on, sizeof(int)));
+  return ADN_OK;
+}
+extern "C" int adn_phase_read(unsigned long long* out64) {
+  using namespace adn;
+  ADN_REQUIRE(out64 != nullptr, ADN_ERR_NULL, "adn_phase_read: NULL");
+  ADN_CHECK_CUDA(cudaDeviceSynchronize());
+  ADN_CHECK_CUDA(cudaMemcpyFromSymbol(out64, g_phase, 64 * sizeof(unsigned long long)));
+  return ADN_OK;
+}
 
 extern "C" int adn_selftest_umma(int mode, int N, int K, const void* A, const void* B, float* C, int* status, void* stream) {
   using namespace adn;

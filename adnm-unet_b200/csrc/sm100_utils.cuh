@@ -39,6 +39,10 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_saddr, int R, int
   return make_desc(tile_saddr + (uint32_t)(((c0 >> 3) * R + t0) * 16), 128, (uint32_t)R * 16);
 }
 
+// Advance a descriptor's start address by `bytes` (the 14-bit start-address field is in 16-byte units): consecutive
+// K steps of one operand differ by a constant, so the issuing thread adds instead of rebuilding the descriptor.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
 // ---- instruction descriptor, kind::f16, bf16 x bf16 -> fp32
 template <int M, int N, bool A_MN, bool B_MN>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {

@@ -162,6 +162,11 @@ unsigned long long adn_launch_count(void);
 int adn_prof_enable(int on);
 int adn_prof_count(void);
 int adn_prof_get(int i, const char** name, float* ms);
+/* In-kernel phase timers of the tcgen05 / conv kernels (SM-clock cycles of thread 0 of every CTA, summed):
+ * adn_phase_enable(1) zeroes and arms them, adn_phase_read copies the 8 x 8 table [kernel][phase] to HOST memory
+ * (synchronises the device).  Kernel ids: 0 k_bwd1, 1 k_bwd2, 2 k_bwd4, 3 k_conv_bwd_tile. */
+int adn_phase_enable(int on);
+int adn_phase_read(unsigned long long* out64);
 /* Hardware self-test of the tcgen05 building blocks (one 128 x N x K bf16 GEMM through shared-memory descriptors
  * and TMEM).  mode 0: A[128][K], B[N][K] (K-major operands); mode 1: A[K][128], B[K][N] (MN-major operands).
  * C is float[128][N]; *status (device int) is set to 1 if the MMA completion barrier timed out. */

@@ -1,0 +1,24 @@
+"""Diagnostic: in-kernel phase timers (adn_phase_*) for one fwd+bwd of the benchmark mixer shape."""
+import ctypes as C, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import adnm_unet_b200 as A
+from adnm_unet_b200 import _lib
+lib = _lib.load()
+torch.manual_seed(0)
+m = A.Mamba2(d_model=32, headdim=4, d_state=16).cuda()
+u = torch.randn(16, 128 * 128, 32, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+go = torch.randn_like(u)
+for _ in range(2):
+    m(u, 128, 128).backward(go)
+torch.cuda.synchronize()
+lib.adn_phase_enable(1)
+m(u, 128, 128).backward(go)
+buf = (C.c_ulonglong * 64)()
+lib.adn_phase_read(buf)
+lib.adn_phase_enable(0)
+names = {0: "k_bwd1", 1: "k_bwd2", 2: "k_bwd4", 3: "k_conv_bwd_tile"}
+for k, n in names.items():
+    row = [buf[k * 8 + i] for i in range(8)]
+    tot = sum(row) or 1
+    print(n, "total Mcycles(thread0 sum)", round(tot / 1e6, 2), [f"{100 * v / tot:.0f}%" for v in row])
