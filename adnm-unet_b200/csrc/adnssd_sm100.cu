@@ -124,6 +124,12 @@ __device__ __forceinline__ void load_tile_t8(bf16* sdst, const bf16* __restrict_
   }
 }
 
+// thread-0 helper: one bulk copy of `nchunks` consecutive 8-channel chunks of token tile `tile` of a TL tensor
+__device__ __forceinline__ void tl_bulk(bf16* sdst, const bf16* __restrict__ g, long long tile, int NCH, int chunk0,
+                                        int nchunks, uint64_t* bar) {
+  bulk_g2s(sdst, g + ((tile * NCH + chunk0) * 128) * 8, (uint32_t)nchunks * 128 * 16, bar);
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_inproj: raw[T][ldr] = u[T][D] . W_in^T   (models/ADNssd.py:309).  Persistent CTAs, 128 tokens per tile.
 // A = u tile (K-major, cp.async double buffered), B = W_in rows [n0, n0+nn) as hi and lo bf16 images (K-major):
@@ -188,37 +194,27 @@ k_inproj(const bf16* __restrict__ u, const bf16* __restrict__ Whi, const bf16* _
       parity ^= 1;
       tc_fence_after();
       if (!ok) { if (tid == 0) atomicExch(status, 1); break; }
-      // epilogue: TMEM -> registers -> bf16 -> padded row-major staging tile (conflict-free 16-byte row writes),
-      // then a cooperative copy-out in which consecutive threads write consecutive 16-byte chunks of a row
-      uint8_t* stg = reinterpret_cast<uint8_t*>(sA0 + 2 * 128 * D);
-      const int pitch = nn * 2 + 16;
-      for (int c = 0; c < nn; c += 32) {
-        float v0[16], v1[16];
-        tmem_ld16(tmem_addr(tbase, warp * 32, c), v0);
-        if (c + 16 < nn) tmem_ld16(tmem_addr(tbase, warp * 32, c + 16), v1);
-        tmem_wait_ld();
-        float a[8], b[8];
-        uint8_t* srow = stg + tid * pitch + c * 2;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { a[j] = v0[j]; b[j] = v0[8 + j]; }
-        *reinterpret_cast<uint4*>(srow) = pack8(a);
-        *reinterpret_cast<uint4*>(srow + 16) = pack8(b);
-        if (c + 16 < nn) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { a[j] = v1[j]; b[j] = v1[8 + j]; }
-          *reinterpret_cast<uint4*>(srow + 32) = pack8(a);
-          *reinterpret_cast<uint4*>(srow + 48) = pack8(b);
-        }
-      }
-      tc_fence_before();
-      __syncthreads();
+      // epilogue: raw is stored in the tiled layout, so thread t (token row t) writes 16 bytes at row t of each
+      // 8-channel chunk: consecutive threads -> consecutive 16-byte slots, fully coalesced straight from registers
       {
-        const int nch = nn >> 3;
-        const long long row0 = (long long)tile * 128;
-        const int rows = (int)min((long long)128, T - row0);
-        for (int i = tid; i < rows * nch; i += 128) {
-          const int r = i / nch, ch = i % nch;
-          *reinterpret_cast<uint4*>(raw + (row0 + r) * ldr + n0 + ch * 8) = *reinterpret_cast<const uint4*>(stg + r * pitch + ch * 16);
+        const int NR = ldr >> 3;
+        bf16* dst = raw + (((long long)tile * NR + (n0 >> 3)) * 128 + tid) * 8;
+        for (int c = 0; c < nn; c += 32) {
+          float v0[16], v1[16];
+          tmem_ld16(tmem_addr(tbase, warp * 32, c), v0);
+          if (c + 16 < nn) tmem_ld16(tmem_addr(tbase, warp * 32, c + 16), v1);
+          tmem_wait_ld();
+          float a[8], b[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { a[j] = v0[j]; b[j] = v0[8 + j]; }
+          *reinterpret_cast<uint4*>(dst + (long long)(c >> 3) * 1024) = pack8(a);
+          *reinterpret_cast<uint4*>(dst + (long long)((c >> 3) + 1) * 1024) = pack8(b);
+          if (c + 16 < nn) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] = v1[j]; b[j] = v1[8 + j]; }
+            *reinterpret_cast<uint4*>(dst + (long long)((c >> 3) + 2) * 1024) = pack8(a);
+            *reinterpret_cast<uint4*>(dst + (long long)((c >> 3) + 3) * 1024) = pack8(b);
+          }
         }
       }
       tc_fence_before();   // TMEM reads of this tile are ordered before the next tile's MMA (after the next __syncthreads)
@@ -261,18 +257,23 @@ k_state(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int
   constexpr uint32_t TCOLS = GN <= 32 ? 32 : (GN <= 64 ? 64 : 128);
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_bias[NH], s_eA[NH];
-  __shared__ uint64_t bar[2];
+  __shared__ uint64_t bar[2], ld_bar[2];
   __shared__ uint32_t tmem_slot;
   bf16* sbase = reinterpret_cast<bf16*>(smem);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.x / ctas_per_batch, part = blockIdx.x % ctas_per_batch;
+  const int NA = CC >> 3, NR = ldr >> 3;
   for (int i = tid; i < NH; i += 128) { s_bias[i] = dt_bias[i]; s_eA[i] = __expf(A_log[i]); }
   // zero the padding chunks [XC, 16) of the wx operand in both stages
   for (int st = 0; st < 2; ++st)
     for (int i = tid; i < (16 - XC) * 128; i += 128)
       *reinterpret_cast<uint4*>(sbase + st * STAGE + (XC * 128 + i) * 8) = make_uint4(0u, 0u, 0u, 0u);
-  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+  if (tid == 0) {
+    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&ld_bar[0], 1); mbar_init(&ld_bar[1], 1);
+    fence_mbar_init();
+  }
   if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
+  fence_async_smem();     // the zero padding written above must be visible to the tensor-core (async) proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -280,18 +281,20 @@ k_state(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int
   const uint32_t idesc = make_idesc_rt(128, GN, true, true);
   int it = 0;
   bool ok = true;
+  // act / raw are stored tiled (TL): x, B and the dt columns of a 128-token tile are three contiguous blocks
   auto issue_loads = [&](int i, int stage) {
-    bf16* sX = sbase + stage * STAGE;
-    bf16* sB = sX + 16 * 128 * 8;
-    bf16* sDt = sB + BC * 128 * 8;
-    const int rows = min(128, L - i * 128);
-    const long long tok0 = (long long)b * L + (long long)i * 128;
-    load_tile_t8(sX, act + tok0 * CC + DI, CC, XC, rows, tid, 128);
-    load_tile_t8(sB, act + tok0 * CC + 2 * DI, CC, BC, rows, tid, 128);
-    load_tile_t8(sDt, raw + tok0 * ldr + CC, ldr, DC, rows, tid, 128);
+    if (tid == 0) {
+      bf16* sX = sbase + stage * STAGE;
+      bf16* sB = sX + 16 * 128 * 8;
+      bf16* sDt = sB + BC * 128 * 8;
+      const long long tile = ((long long)b * L >> 7) + i;
+      mbar_expect_tx(&ld_bar[stage], (uint32_t)(XC + BC + DC) * 128 * 16);
+      tl_bulk(sX, act, tile, NA, XC, XC, &ld_bar[stage]);
+      tl_bulk(sB, act, tile, NA, 2 * XC, BC, &ld_bar[stage]);
+      tl_bulk(sDt, raw, tile, NR, NA, DC, &ld_bar[stage]);
+    }
   };
   if (part < tiles_per_batch) issue_loads(part, 0);
-  cp_async_commit();
   for (int i = part; i < tiles_per_batch; i += ctas_per_batch, ++it) {
     const int stage = it & 1;
     bf16* sX = sbase + stage * STAGE;
@@ -302,9 +305,7 @@ k_state(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int
       if (it >= 1) ok = ok && mbar_wait(&bar[stage ^ 1], ((it - 1) >> 1) & 1);
       issue_loads(i + ctas_per_batch, stage ^ 1);
     }
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
+    ok = ok && mbar_wait(&ld_bar[stage], (it >> 1) & 1);
     float w[NH];
 #pragma unroll
     for (int dc = 0; dc < DC; ++dc) {
@@ -372,7 +373,7 @@ k_readout(const bf16* __restrict__ act, int CC, const float* __restrict__ S, con
   constexpr uint32_t TCOLS = (DI + D) <= 128 ? 128 : 256;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float sG[DI], sBt[DI], sDh[DI];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, ld_bar;
   __shared__ uint32_t tmem_slot;
   bf16* sC = reinterpret_cast<bf16*>(smem);   // [CCH][128][8]
   bf16* sCat = sC + CCH * 128 * 8;            // [CATC][128][8]: chunks [0,XC) = LN(y), [XC,2XC) = zc
@@ -386,7 +387,9 @@ k_readout(const bf16* __restrict__ act, int CC, const float* __restrict__ S, con
     int d = i / CATC, jc = i % CATC;
     *reinterpret_cast<uint4*>(sW + (jc * D + d) * 8) = *reinterpret_cast<const uint4*>(Wout + (long long)d * 2 * DI + jc * 8);
   }
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&ld_bar, 1); fence_mbar_init(); }
+  const int NA = CC >> 3;
+  uint32_t lph = 0;
   if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
@@ -413,11 +416,13 @@ k_readout(const bf16* __restrict__ act, int CC, const float* __restrict__ S, con
       }
       cur_b = b;
     }
-    load_tile_t8(sC, act + tok0 * CC + 2 * DI + GN, CC, CCH, rows, tid, 128);
-    load_tile_t8(sCat + XC * 128 * 8, act + tok0 * CC, CC, XC, rows, tid, 128);
-    load_tile_t8(sX, act + tok0 * CC + DI, CC, XC, rows, tid, 128);
-    cp_async_commit();
-    cp_async_wait<0>();
+    if (tid == 0) {   // act is TL: [z | x] (chunks 0..2XC) land in sCat[XC..2XC) + sX, which are adjacent; C separately
+      mbar_expect_tx(&ld_bar, (uint32_t)(2 * XC + CCH) * 128 * 16);
+      tl_bulk(sCat + XC * 128 * 8, act, tile, NA, 0, 2 * XC, &ld_bar);
+      tl_bulk(sC, act, tile, NA, 2 * XC + CCH, CCH, &ld_bar);
+    }
+    bool ok = mbar_wait(&ld_bar, lph);
+    lph ^= 1;
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -430,7 +435,7 @@ k_readout(const bf16* __restrict__ act, int CC, const float* __restrict__ S, con
       for (int k = 0; k < GN; k += 16) umma(tbase, desc_kmajor(a0, 128, 0, k), desc_kmajor(bl, DI, 0, k), idesc, true);
       umma_commit(&bar);
     }
-    bool ok = mbar_wait(&bar, ph);
+    ok = mbar_wait(&bar, ph) && ok;
     ph ^= 1;
     tc_fence_after();
     if (!ok) { if (tid == 0) atomicExch(status, 3); break; }
@@ -553,7 +558,7 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
   constexpr uint32_t TCOLS = (COL_DS + GN) <= 256 ? 256 : 512;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float sG[DI], sDh[DI];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, ld_bar;
   __shared__ uint32_t tmem_slot;
   bf16* sDout = reinterpret_cast<bf16*>(smem);      // [DC][128][8]
   bf16* sC = sDout + DC * 128 * 8;                  // [CCH][128][8]
@@ -575,7 +580,9 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
     for (int q = 0; q < 8; ++q) v[q] = __bfloat162float(Wout[(long long)(dc * 8 + q) * 2 * DI + j]);
     *reinterpret_cast<uint4*>(sWT + (dc * 2 * DI + j) * 8) = pack8(v);
   }
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&ld_bar, 1); fence_mbar_init(); }
+  const int NA = CC >> 3;
+  uint32_t lph = 0;
   if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
@@ -599,13 +606,17 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
       stage_state_b<DI, GN>(S + (long long)b * GN * DI, sSb_hi, sSb_lo, tid);
       cur_b = b;
     }
-    load_tile_t8(sDout, dout + tok0 * D, D, DC, rows, tid, 128);
-    load_tile_t8(sC, act + tok0 * CC + 2 * DI + GN, CC, CCH, rows, tid, 128);
-    load_tile_t8(sCat + XC * 128 * 8, act + tok0 * CC, CC, XC, rows, tid, 128);
-    load_tile_t8(sXY, act + tok0 * CC + DI, CC, XC, rows, tid, 128);
+    if (tid == 0) {   // act is TL: [z | x] -> sCat[XC..16) + sXY[0..XC) (adjacent in shared memory), C -> sC
+      mbar_expect_tx(&ld_bar, (uint32_t)(2 * XC + CCH) * 128 * 16);
+      tl_bulk(sCat + XC * 128 * 8, act, tile, NA, 0, 2 * XC, &ld_bar);
+      tl_bulk(sC, act, tile, NA, 2 * XC + CCH, CCH, &ld_bar);
+    }
+    load_tile_t8(sDout, dout + tok0 * D, D, DC, rows, tid, 128);   // dout is an external row-major tensor
     cp_async_commit();
     pt.mark(0);
     cp_async_wait<0>();
+    ok = mbar_wait(&ld_bar, lph) && ok;
+    lph ^= 1;
     fence_async_smem();
     __syncthreads();
     pt.mark(1);
@@ -621,7 +632,7 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
       for (int k = 0; k < GN; k += 16) umma(tbase + COL_Y, desc_kmajor(aC, 128, 0, k), desc_kmajor(bl, DI, 0, k), id_y, true);
       umma_commit(&bar);
     }
-    ok = mbar_wait(&bar, ph);
+    ok = mbar_wait(&bar, ph) && ok;
     ph ^= 1;
     tc_fence_after();
     pt.mark(2);
@@ -673,7 +684,7 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
     }
     m1 *= (1.f / DI);
     m2 *= (1.f / DI);
-    bf16* drow = dact + (tok0 + tid) * CC;
+    bf16* drow = dact + (((long long)tile * NA) * 128 + tid) * 8;   // dact is TL: chunk k of this row at drow + k*1024
 #pragma unroll
     for (int cb = 0; cb < DI; cb += 16) {
       float v[16], o0[8], o1[8];
@@ -688,8 +699,8 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
       *reinterpret_cast<uint4*>(sXY + ((cb / 8) * 128 + tid) * 8) = p0;
       *reinterpret_cast<uint4*>(sXY + ((cb / 8 + 1) * 128 + tid) * 8) = p1;
       if (tid < rows) {
-        *reinterpret_cast<uint4*>(drow + DI + cb) = p0;
-        *reinterpret_cast<uint4*>(drow + DI + cb + 8) = p1;
+        *reinterpret_cast<uint4*>(drow + (long long)(XC + cb / 8) * 1024) = p0;
+        *reinterpret_cast<uint4*>(drow + (long long)(XC + cb / 8 + 1) * 1024) = p1;
       }
     }
 #pragma unroll
@@ -700,8 +711,8 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
 #pragma unroll
       for (int j = 0; j < 8; ++j) { o0[j] = a1 * v[j]; o1[j] = a1 * v[8 + j]; }
       if (tid < rows) {
-        *reinterpret_cast<uint4*>(drow + cb) = pack8(o0);
-        *reinterpret_cast<uint4*>(drow + cb + 8) = pack8(o1);
+        *reinterpret_cast<uint4*>(drow + (long long)(cb / 8) * 1024) = pack8(o0);
+        *reinterpret_cast<uint4*>(drow + (long long)(cb / 8 + 1) * 1024) = pack8(o1);
       }
     }
 #pragma unroll
@@ -748,8 +759,8 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
 #pragma unroll
       for (int j = 0; j < 8; ++j) { o0[j] = v[j]; o1[j] = v[8 + j]; }
       if (tid < rows) {
-        *reinterpret_cast<uint4*>(drow + 2 * DI + GN + cb) = pack8(o0);
-        *reinterpret_cast<uint4*>(drow + 2 * DI + GN + cb + 8) = pack8(o1);
+        *reinterpret_cast<uint4*>(drow + (long long)(2 * XC + CCH + cb / 8) * 1024) = pack8(o0);
+        *reinterpret_cast<uint4*>(drow + (long long)(2 * XC + CCH + cb / 8 + 1) * 1024) = pack8(o1);
       }
     }
     const bool last_of_batch = (tile + 1 == tile_end) || ((tile + 1) / tiles_per_batch != b);
@@ -832,11 +843,11 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
   constexpr uint32_t TCOLS = (DI + GN) <= 128 ? 128 : 256;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_bias[NH], s_eA[NH], s_D[NH];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, ld_bar;
   __shared__ uint32_t tmem_slot;
-  bf16* sB = reinterpret_cast<bf16*>(smem);      // [BC][128][8]
-  bf16* sX = sB + BC * 128 * 8;                  // [XC][128][8]  x, then w*x in place
-  bf16* sDy = sX + XC * 128 * 8;                 // [XC][128][8]
+  bf16* sX = reinterpret_cast<bf16*>(smem);      // [XC][128][8]  x, then w*x in place
+  bf16* sB = sX + XC * 128 * 8;                  // [BC][128][8]  (x and B are adjacent chunks of act: one bulk copy)
+  bf16* sDy = sB + BC * 128 * 8;                 // [XC][128][8]
   bf16* sDt = sDy + XC * 128 * 8;                // [DC][128][8]
   bf16* sTa_hi = sDt + DC * 128 * 8;             // [BC][DI][8]
   bf16* sTa_lo = sTa_hi + BC * DI * 8;
@@ -844,7 +855,9 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
   bf16* sTb_lo = sTb_hi + XC * GN * 8;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < NH; i += 128) { s_bias[i] = dt_bias[i]; s_eA[i] = __expf(A_log[i]); s_D[i] = Dp[i]; }
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&ld_bar, 1); fence_mbar_init(); }
+  const int NA = CC >> 3, NR = ldr >> 3;
+  uint32_t lph = 0;
   if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
@@ -867,13 +880,15 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
       stage_state_b<DI, GN>(dS + (long long)b * GN * DI, sTb_hi, sTb_lo, tid);
       cur_b = b;
     }
-    load_tile_t8(sB, act + tok0 * CC + 2 * DI, CC, BC, rows, tid, 128);
-    load_tile_t8(sX, act + tok0 * CC + DI, CC, XC, rows, tid, 128);
-    load_tile_t8(sDy, dact + tok0 * CC + DI, CC, XC, rows, tid, 128);
-    load_tile_t8(sDt, raw + tok0 * ldr + CC, ldr, DC, rows, tid, 128);
-    cp_async_commit();
+    if (tid == 0) {   // TL tensors: [x | B] of act, dy of dact, dt columns of raw
+      mbar_expect_tx(&ld_bar, (uint32_t)(2 * XC + BC + DC) * 128 * 16);
+      tl_bulk(sX, act, tile, NA, XC, XC + BC, &ld_bar);
+      tl_bulk(sDy, dact, tile, NA, XC, XC, &ld_bar);
+      tl_bulk(sDt, raw, tile, NR, NA, DC, &ld_bar);
+    }
     pt.mark(0);
-    cp_async_wait<0>();
+    ok = mbar_wait(&ld_bar, lph) && ok;
+    lph ^= 1;
     fence_async_smem();
     __syncthreads();
     pt.mark(1);
@@ -901,7 +916,7 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
       }
     }
     pt.mark(2);
-    ok = mbar_wait(&bar, ph);
+    ok = mbar_wait(&bar, ph) && ok;
     ph ^= 1;
     tc_fence_after();
     pt.mark(3);
@@ -909,7 +924,7 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
     float dw[NH];
 #pragma unroll
     for (int h = 0; h < NH; ++h) dw[h] = 0.f;
-    bf16* drow = dact + (tok0 + tid) * CC;
+    bf16* drow = dact + (((long long)tile * NA) * 128 + tid) * 8;   // TL: chunk k of this row at drow + k*1024
     const bool valid = tid < rows;
 #pragma unroll
     for (int cb = 0; cb < DI; cb += 16) {
@@ -932,11 +947,11 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
           if (valid) aD[h] = fmaf(dy[j], x[j], aD[h]);
         }
         *reinterpret_cast<uint4*>(sX + (cg * 128 + tid) * 8) = pack8(wx);
-        if (valid) *reinterpret_cast<uint4*>(drow + DI + cg * 8) = pack8(o);
+        if (valid) *reinterpret_cast<uint4*>(drow + (long long)(XC + cg) * 1024) = pack8(o);
       }
     }
     {
-      bf16* trow = draw + (tok0 + tid) * ldr + CC;
+      bf16* trow = draw + tl_off(tok0 + tid, CC, ldr >> 3);   // draw is in the tiled layout: chunk stride 128*8
 #pragma unroll
       for (int dc = 0; dc < DC; ++dc) {
         float o[8];
@@ -946,7 +961,7 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
           o[j] = dw[h] * s_eA[h] * sg[h];
           if (valid) { aA[h] = fmaf(dw[h], w[h], aA[h]); aB[h] += o[j]; }
         }
-        if (valid) *reinterpret_cast<uint4*>(trow + dc * 8) = pack8(o);
+        if (valid) *reinterpret_cast<uint4*>(trow + (long long)dc * 128 * 8) = pack8(o);
       }
     }
     pt.mark(4);
@@ -976,8 +991,8 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
 #pragma unroll
       for (int j = 0; j < 8; ++j) { o0[j] = v[j]; o1[j] = v[8 + j]; }
       if (valid) {
-        *reinterpret_cast<uint4*>(drow + 2 * DI + cb) = pack8(o0);
-        *reinterpret_cast<uint4*>(drow + 2 * DI + cb + 8) = pack8(o1);
+        *reinterpret_cast<uint4*>(drow + (long long)(2 * XC + cb / 8) * 1024) = pack8(o0);
+        *reinterpret_cast<uint4*>(drow + (long long)(2 * XC + cb / 8 + 1) * 1024) = pack8(o1);
       }
     }
     tc_fence_before();
@@ -999,7 +1014,7 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
 //   du = draw . W_in                        tcgen05 (hi + lo weights), K = dip
 //   dW_in[j][d] += sum_tok draw[tok][j] * u[tok][d]      tcgen05 reduction over tokens, M blocks of 128 rows j
 // ------------------------------------------------------------------------------------------------
-template <int D, int MB>
+template <int D, int MB, int NS>
 __global__ void __launch_bounds__(128)
 k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__ u, const bf16* __restrict__ WThi,
        const bf16* __restrict__ WTlo, bf16* __restrict__ du, float* __restrict__ dWin_part, long long T, int num_tiles,
@@ -1009,20 +1024,21 @@ k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__
   constexpr uint32_t TCOLS = (D + MB * D) <= 128 ? 128 : 256;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t ld_bar[2];
   __shared__ uint32_t tmem_slot;
   const int JC = dip / 8;                          // real 8-channel chunks of draw
-  bf16* sStage = reinterpret_cast<bf16*>(smem);    // 2 x { [16*MB][128][8] draw (chunks >= JC stay zero), [DC][128][8] u }
-  bf16* sWhi = sStage + 2 * STAGE;                 // [16*MB][D][8]   W_in^T: row d, K = j
+  bf16* sStage = reinterpret_cast<bf16*>(smem);    // NS x { [16*MB][128][8] draw (chunks >= JC stay zero), [DC][128][8] u }
+  bf16* sWhi = sStage + NS * STAGE;                // [16*MB][D][8]   W_in^T: row d, K = j
   bf16* sWlo = sWhi + 16 * MB * D * 8;
   const int tid = threadIdx.x, warp = tid >> 5;
-  for (int st = 0; st < 2; ++st)
+  for (int st = 0; st < NS; ++st)
     for (int i = tid; i < (16 * MB - JC) * 128; i += 128)
       *reinterpret_cast<uint4*>(sStage + st * STAGE + (JC * 128 + i) * 8) = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < 16 * MB * D; i += 128) {   // the W_in^T images were laid out by k_prep: straight 16-byte copies
     *reinterpret_cast<uint4*>(sWhi + i * 8) = __ldg(reinterpret_cast<const uint4*>(WThi + i * 8));
     *reinterpret_cast<uint4*>(sWlo + i * 8) = __ldg(reinterpret_cast<const uint4*>(WTlo + i * 8));
   }
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&ld_bar[0], 1); mbar_init(&ld_bar[1], 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
@@ -1036,19 +1052,30 @@ k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__
     const long long tok0 = (long long)tile * 128;
     const int rows = (int)min((long long)128, T - tok0);
     bf16* sDraw = sStage + stage * STAGE;
-    load_tile_t8(sDraw, draw + tok0 * ldr, ldr, JC, rows, tid, 128);
+    // draw is stored tiled (TL): the whole 128-token x dip tile is one contiguous block -> one bulk copy
+    if (tid == 0) {
+      mbar_expect_tx(&ld_bar[stage], (uint32_t)JC * 128 * 16);
+      bulk_g2s(sDraw, draw + (long long)tile * JC * 128 * 8, (uint32_t)JC * 128 * 16, &ld_bar[stage]);
+    }
     load_tile_t8(sDraw + 16 * MB * 128 * 8, u + tok0 * D, D, DC, rows, tid, 128);
   };
-  if (tile_begin < tile_end) issue_loads(tile_begin, 0);
-  cp_async_commit();
+  if (NS == 2) {
+    if (tile_begin < tile_end) issue_loads(tile_begin, 0);
+    cp_async_commit();
+  }
   for (int tile = tile_begin, it = 0; tile < tile_end; ++tile, ++it) {
-    const int stage = it & 1;
-    // prefetch the next tile into the other stage: its previous reader (the MMAs of tile-1) completed before the
-    // epilogue of the previous iteration, and every thread passed that iteration's trailing __syncthreads
-    if (tile + 1 < tile_end) issue_loads(tile + 1, stage ^ 1);
+    const int stage = NS == 2 ? (it & 1) : 0;
+    // NS == 2: prefetch the next tile into the other stage: its previous reader (the MMAs of tile-1) completed before
+    // the epilogue of the previous iteration, and every thread passed that iteration's trailing __syncthreads
+    if (NS == 2) {
+      if (tile + 1 < tile_end) issue_loads(tile + 1, stage ^ 1);
+    } else {
+      issue_loads(tile, 0);
+    }
     cp_async_commit();
     pt.mark(0);
-    cp_async_wait<1>();
+    if (NS == 2) cp_async_wait<1>(); else cp_async_wait<0>();
+    ok = ok && mbar_wait(&ld_bar[stage], NS == 2 ? ((it >> 1) & 1) : (it & 1));
     fence_async_smem();
     __syncthreads();
     pt.mark(1);
@@ -1186,15 +1213,16 @@ __global__ void k_prep(ConvWeightPtrs cw, float* __restrict__ Kc, int Di, int CC
 // ------------------------------------------------------------------------------------------------
 constexpr int CT_X = 32, CT_Y = 16, CT_XH = CT_X + 2, CT_YH = CT_Y + 2;
 
-__device__ __forceinline__ void conv_tile_load(uint4* sdst, const bf16* __restrict__ g, long long ld, int H, int W, int y0,
-                                               int x0, int halo, int tid) {
+// g: TL tensor with NCH chunks; tok_base = first token of the sample; c0 = first channel of the 32-channel slab
+__device__ __forceinline__ void conv_tile_load(uint4* sdst, const bf16* __restrict__ g, int NCH, int tok_base, int c0,
+                                               int H, int W, int y0, int x0, int halo, int tid, int nthreads) {
   // tile rows y0-halo .. y0+CT_Y-1+halo, cols x0-halo .. ; 4 chunks of 8 channels per token
   const int TH = CT_Y + 2 * halo, TW = CT_X + 2 * halo;
-  for (int i = tid; i < TH * TW * 4; i += 128) {
+  for (int i = tid; i < TH * TW * 4; i += nthreads) {
     const int ch = i & 3, c = (i >> 2) % TW, r = (i >> 2) / TW;
     const int y = y0 - halo + r, x = x0 - halo + c;
     const bool ok = y >= 0 && y < H && x >= 0 && x < W;
-    const bf16* src = g + ((long long)(ok ? y : 0) * W + (ok ? x : 0)) * ld + ch * 8;
+    const bf16* src = g + tl_off32(tok_base + (ok ? y * W + x : 0), c0 + ch * 8, NCH);
     cp_async16(sdst + i, src, ok ? 16 : 0);
   }
 }
@@ -1206,7 +1234,7 @@ k_conv_fwd_tile(const bf16* __restrict__ raw, int ldr, const float* __restrict__
   const int tid = threadIdx.x;
   const int b = blockIdx.z / slabs, slab = blockIdx.z % slabs;
   const int x0 = blockIdx.x * CT_X, y0 = blockIdx.y * CT_Y, c0 = slab * 32;
-  conv_tile_load(tile, raw + (long long)b * H * W * ldr + c0, ldr, H, W, y0, x0, 1, tid);
+  conv_tile_load(tile, raw, ldr >> 3, b * H * W, c0, H, W, y0, x0, 1, tid, 128);
   cp_async_commit();
   const int xl = tid >> 2, ch = tid & 3, cc = c0 + ch * 8;
   float2 k2[9][4];
@@ -1241,7 +1269,7 @@ k_conv_fwd_tile(const bf16* __restrict__ raw, int ldr, const float* __restrict__
           for (int sx = 0; sx < 3; ++sx)
 #pragma unroll
             for (int q = 0; q < 4; ++q) a[q] = __ffma2_rn(k2[rr * 3 + sx][q], win[(ph + rr) % 3][sx][q], a[q]);
-        const long long off = (((long long)b * H + y0 + r) * W + x) * CC + cc;
+        const long long off = tl_off32((b * H + y0 + r) * W + x, cc, CC >> 3);
         if (pre) *reinterpret_cast<uint4*>(pre + off) = pack8_f2(a);
 #pragma unroll
         for (int q = 0; q < 4; ++q) { a[q].x *= sigmoid_fast(a[q].x); a[q].y *= sigmoid_fast(a[q].y); }
@@ -1262,7 +1290,7 @@ __device__ __forceinline__ void unpack4_f2(const uint2& u, float2 (&v)[2]) {
   v[1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, const bf16* __restrict__ raw, int ldr,
                 const float* __restrict__ Kc, bf16* __restrict__ draw, float* __restrict__ dK, int H, int W, int CC,
                 int slabs) {
@@ -1272,16 +1300,8 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
   PhaseTimer pt(3);
   const int b = blockIdx.z / slabs, slab = blockIdx.z % slabs;
   const int x0 = blockIdx.x * CT_X, y0 = blockIdx.y * CT_Y, c0 = slab * 32;
-  const long long boff = (long long)b * H * W;
-  {
-    const bf16* g = dact + boff * CC + c0;
-    for (int i = tid; i < CT_YH * CT_XH * 4; i += 256) {
-      const int chn = i & 3, c = (i >> 2) % CT_XH, r = (i >> 2) / CT_XH;
-      const int y = y0 - 1 + r, x = x0 - 1 + c;
-      const bool ok = y >= 0 && y < H && x >= 0 && x < W;
-      cp_async16(tD + i, g + ((long long)(ok ? y : 0) * W + (ok ? x : 0)) * CC + chn * 8, ok ? 16 : 0);
-    }
-  }
+  const int boff = b * H * W;
+  conv_tile_load(tD, dact, CC >> 3, boff, c0, H, W, y0, x0, 1, tid, 256);
   cp_async_commit();
   for (int i = tid; i < 32 * 9; i += 256) red[i] = 0.f;
   const int xl = tid >> 3, hc = tid & 7, cc = c0 + hc * 4;   // hc: 4-channel half chunk inside the 32-channel slab
@@ -1295,14 +1315,13 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
   cp_async_wait<0>();
   pt.mark(1);
   {
-    const bf16* ps = pre + boff * CC + c0;
     for (int i = tid; i < CT_YH * CT_XH * 4; i += 256) {
       const int chn = i & 3, c = (i >> 2) % CT_XH, r = (i >> 2) / CT_XH;
       const int y = y0 - 1 + r, x = x0 - 1 + c;
       if (y >= 0 && y < H && x >= 0 && x < W) {
         float g[8], p[8];
         unpack8(tD[i], g);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(ps + ((long long)y * W + x) * CC + chn * 8)), p);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(pre + tl_off32(boff + y * W + x, c0 + chn * 8, CC >> 3))), p);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float sgm = sigmoid_fast(p[j]);
@@ -1328,9 +1347,10 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
   };
   load_row(0, win[0]);
   load_row(1, win[1]);
-  const bf16* rsrc = raw + (boff + (long long)y0 * W + (xin ? x : 0)) * ldr + cc;
+  const int NR = ldr >> 3;
+  const int rtok = boff + y0 * W + (xin ? x : 0);   // raw is TL: rows of one column are W tokens apart
   const uint2 zero2 = make_uint2(0u, 0u);
-  uint2 rnext = (xin && ny > 0) ? __ldg(reinterpret_cast<const uint2*>(rsrc)) : zero2;
+  uint2 rnext = (xin && ny > 0) ? __ldg(reinterpret_cast<const uint2*>(raw + tl_off32(rtok, cc, NR))) : zero2;
   for (int rb = 0; rb < ny; rb += 3) {
 #pragma unroll
     for (int ph = 0; ph < 3; ++ph) {
@@ -1339,7 +1359,7 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
         load_row(r + 2, win[(ph + 2) % 3]);
         float2 rc[2], o[2];
         unpack4_f2(rnext, rc);
-        rnext = (xin && r + 1 < ny) ? __ldg(reinterpret_cast<const uint2*>(rsrc + (long long)(r + 1) * W * ldr)) : zero2;
+        rnext = (xin && r + 1 < ny) ? __ldg(reinterpret_cast<const uint2*>(raw + tl_off32(rtok + (r + 1) * W, cc, NR))) : zero2;
         o[0] = make_float2(0.f, 0.f);
         o[1] = make_float2(0.f, 0.f);
 #pragma unroll
@@ -1356,7 +1376,7 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
           uint2 ov;
           ov.x = pack_bf16(o[0].x, o[0].y);
           ov.y = pack_bf16(o[1].x, o[1].y);
-          *reinterpret_cast<uint2*>(draw + (boff + (long long)(y0 + r) * W + x) * ldr + cc) = ov;
+          *reinterpret_cast<uint2*>(draw + tl_off32(boff + (y0 + r) * W + x, cc, NR)) = ov;
         }
       }
     }
@@ -1410,7 +1430,7 @@ struct FastWs {           // placed after the generic workspace of the same pass
 
 bool sm100_supported(const MixerDims& d) {
   // instantiated tile shapes: d_model 32 (d_inner 64), headdim 4, ngroups*d_state in {32, 128}
-  return d.D == 32 && d.Di == 64 && d.P == 4 && (d.GN == 32 || d.GN == 128) && d.dip % 16 == 0 && d.ldr == d.dip && d.CC % 32 == 0;
+  return d.D == 32 && d.Di == 64 && d.P == 4 && (d.GN == 32 || d.GN == 128) && d.dip % 16 == 0 && d.dip <= 512 && d.ldr == d.dip && d.CC % 32 == 0 && d.L % 128 == 0;
 }
 
 template <typename K>
@@ -1452,7 +1472,7 @@ void sm100_workspace_bytes(const MixerDims& d, size_t* f, size_t* b) {
 template <int D>
 static int launch_inproj(const MixerDims& d, const bf16* u, const FastWs& F, bf16* raw, cudaStream_t st) {
   const int num_tiles = cdiv(d.T, 128);
-  const size_t smem = (size_t)(2 * 256 * D + 2 * 128 * D) * sizeof(bf16) + 128 * (size_t)(min(256, d.dip) * 2 + 16);
+  const size_t smem = (size_t)(2 * 256 * D + 2 * 128 * D) * sizeof(bf16);
   ADN_CHECK_CUDA(cudaFuncSetAttribute(k_inproj<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(num_tiles, 148 * 2);
   { ADN_KERNEL("k_inproj", st); k_inproj<D><<<grid, 128, smem, st>>>(u, F.Whi, F.Wlo, raw, d.ldr, d.dip, d.T, num_tiles, F.status); }
@@ -1492,17 +1512,17 @@ static int launch_bwd2(const MixerDims& d, const bf16* act, const bf16* raw, con
   return ADN_OK;
 }
 
-template <int D, int MB>
+template <int D, int MB, int NS>
 static int launch_bwd4(const MixerDims& d, const bf16* draw, const bf16* u, const FastWs& F, bf16* du, GradAcc* acc,
                        cudaStream_t st) {
-  constexpr size_t smem = (2 * (size_t)(16 * MB + D / 8) * 128 * 8 + 2 * 16 * MB * D * 8) * sizeof(bf16);
+  constexpr size_t smem = (NS * (size_t)(16 * MB + D / 8) * 128 * 8 + 2 * 16 * MB * D * 8) * sizeof(bf16);
   static_assert(smem <= 227 * 1024, "k_bwd4 stages do not fit shared memory");
-  int rc = set_smem(k_bwd4<D, MB>, smem);
+  int rc = set_smem(k_bwd4<D, MB, NS>, smem);
   if (rc) return rc;
   const int nt = cdiv(d.T, 128);
   int grid, per;
   split_tiles(nt, 1, &grid, &per);      // one CTA per SM (<= 148 partial slabs)
-  { ADN_KERNEL("k_bwd4", st); k_bwd4<D, MB><<<grid, 128, smem, st>>>(draw, d.ldr, d.dip, u, F.WT_hi, F.WT_lo, du, F.dWin_part, d.T, nt, per, F.status); }
+  { ADN_KERNEL("k_bwd4", st); k_bwd4<D, MB, NS><<<grid, 128, smem, st>>>(draw, d.ldr, d.dip, u, F.WT_hi, F.WT_lo, du, F.dWin_part, d.T, nt, per, F.status); }
   { ADN_KERNEL("k_reduce_parts", st); k_reduce_parts<<<cdiv(d.dip * d.D, 32), 256, 0, st>>>(F.dWin_part, acc->dWin, d.dip * d.D, grid); }
   return ADN_OK;
 }
@@ -1572,14 +1592,10 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
     { ADN_KERNEL("k_conv_bwd_tile", st); k_conv_bwd_tile<<<grid, 256, 0, st>>>(W.dact, S.pre, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.H, d.W, d.CC, slabs); }
   }
   // ---- in_proj backward
-  if (d.dip <= 256) {
-    rc = d.dip <= 128 ? launch_bwd4<32, 1>(d, W.draw, u, F, du, &W.acc, st)
-                      : launch_bwd4<32, 2>(d, W.draw, u, F, du, &W.acc, st);
-    if (rc) return rc;
-  } else {  // wide in_proj (d_state 64): generic GEMMs for this stage
-    launch_gemm<TWf, T, false>(st, W.draw, d.ldr, 0, w.in_proj_w, d.D, 0, du, d.D, 0, (int)d.T, d.D, d.dip, 1, nullptr, 0);
-    launch_reduce_gemm<TWf, T>(st, W.draw, d.ldr, u, d.D, W.acc.dWin, d.D, 0, d.dip, d.D, (int)d.T, 1, 0);
-  }
+  rc = d.dip <= 128 ? launch_bwd4<32, 1, 2>(d, W.draw, u, F, du, &W.acc, st)
+       : d.dip <= 256 ? launch_bwd4<32, 2, 2>(d, W.draw, u, F, du, &W.acc, st)
+                      : launch_bwd4<32, 4, 1>(d, W.draw, u, F, du, &W.acc, st);   // wide in_proj: one stage fits
+  if (rc) return rc;
   { ADN_KERNEL("k_finalize", st); k_finalize<<<148, 256, 0, st>>>(W.acc, w, g, d.D, d.Di, d.GN, d.nh, d.dip); }
   ADN_CHECK_LAUNCH();
   return ADN_OK;

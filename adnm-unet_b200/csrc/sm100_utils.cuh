@@ -99,6 +99,28 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   return false;
 }
 
+// ---- bulk asynchronous copy global -> shared (one instruction moves `bytes`, a multiple of 16; completion is signalled
+// on an mbarrier as a byte count).  Issued by ONE thread after mbar_expect_tx() for the same barrier.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- tiled global layout "TL" of the internal activation tensors: tokens in tiles of 128, inside a tile the T8 layout
+// [chunk][128 rows][8]: element (tok, c) of a tensor with NCH = channels/8 chunks.  A tile's chunk range is contiguous,
+// so it moves global -> shared with ONE bulk copy, and "thread t owns token row t" kernels store fully coalesced.
+__host__ __device__ __forceinline__ long long tl_off(long long tok, int c, int NCH) {
+  return (((tok >> 7) * NCH + (c >> 3)) * 128 + (tok & 127)) * 8 + (c & 7);
+}
+// 32-bit token index variant for hot loops (tokens < 2^31 is validated at the ABI): one 64-bit multiply-add
+__device__ __forceinline__ long long tl_off32(int tok, int c, int NCH) {
+  return (long long)((tok >> 7) * NCH + (c >> 3)) * 1024 + (((tok & 127) << 3) + (c & 7));
+}
+
 // ---- fences
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
