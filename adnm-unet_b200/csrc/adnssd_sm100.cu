@@ -1212,12 +1212,14 @@ __global__ void k_prep(ConvWeightPtrs cw, float* __restrict__ Kc, int Di, int CC
 // by conflict-free LDS.128 and does the 9 taps x 8 channels as 36 FFMA2.
 // ------------------------------------------------------------------------------------------------
 constexpr int CT_X = 32, CT_Y = 16, CT_XH = CT_X + 2, CT_YH = CT_Y + 2;
+constexpr int CB_Y = 32;   // tile height of the conv backward (fewer dK reductions, less halo)
 
 // g: TL tensor with NCH chunks; tok_base = first token of the sample; c0 = first channel of the 32-channel slab
+template <int TY>
 __device__ __forceinline__ void conv_tile_load(uint4* sdst, const bf16* __restrict__ g, int NCH, int tok_base, int c0,
                                                int H, int W, int y0, int x0, int halo, int tid, int nthreads) {
-  // tile rows y0-halo .. y0+CT_Y-1+halo, cols x0-halo .. ; 4 chunks of 8 channels per token
-  const int TH = CT_Y + 2 * halo, TW = CT_X + 2 * halo;
+  // tile rows y0-halo .. y0+TY-1+halo, cols x0-halo .. ; 4 chunks of 8 channels per token
+  const int TH = TY + 2 * halo, TW = CT_X + 2 * halo;
   for (int i = tid; i < TH * TW * 4; i += nthreads) {
     const int ch = i & 3, c = (i >> 2) % TW, r = (i >> 2) / TW;
     const int y = y0 - halo + r, x = x0 - halo + c;
@@ -1234,7 +1236,7 @@ k_conv_fwd_tile(const bf16* __restrict__ raw, int ldr, const float* __restrict__
   const int tid = threadIdx.x;
   const int b = blockIdx.z / slabs, slab = blockIdx.z % slabs;
   const int x0 = blockIdx.x * CT_X, y0 = blockIdx.y * CT_Y, c0 = slab * 32;
-  conv_tile_load(tile, raw, ldr >> 3, b * H * W, c0, H, W, y0, x0, 1, tid, 128);
+  conv_tile_load<CT_Y>(tile, raw, ldr >> 3, b * H * W, c0, H, W, y0, x0, 1, tid, 128);
   cp_async_commit();
   const int xl = tid >> 2, ch = tid & 3, cc = c0 + ch * 8;
   float2 k2[9][4];
@@ -1270,9 +1272,17 @@ k_conv_fwd_tile(const bf16* __restrict__ raw, int ldr, const float* __restrict__
 #pragma unroll
             for (int q = 0; q < 4; ++q) a[q] = __ffma2_rn(k2[rr * 3 + sx][q], win[(ph + rr) % 3][sx][q], a[q]);
         const long long off = tl_off32((b * H + y0 + r) * W + x, cc, CC >> 3);
-        if (pre) *reinterpret_cast<uint4*>(pre + off) = pack8_f2(a);
+        // On this path the "pre" slot of the saved tensors holds SiLU'(pre) = s + SiLU(pre)*(1 - s), s = sigmoid(pre):
+        // the backward only ever needs that factor, which removes every exp / divide from the conv backward.
+        float2 gq[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { a[q].x *= sigmoid_fast(a[q].x); a[q].y *= sigmoid_fast(a[q].y); }
+        for (int q = 0; q < 4; ++q) {
+          const float2 sg = make_float2(sigmoid_fast(a[q].x), sigmoid_fast(a[q].y));
+          a[q] = __ffma2_rn(a[q], sg, make_float2(0.f, 0.f));
+          const float2 om = __ffma2_rn(sg, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+          gq[q] = __ffma2_rn(a[q], om, sg);
+        }
+        if (pre) *reinterpret_cast<uint4*>(pre + off) = pack8_f2(gq);
         *reinterpret_cast<uint4*>(act + off) = pack8_f2(a);
       }
     }
@@ -1291,17 +1301,18 @@ __device__ __forceinline__ void unpack4_f2(const uint2& u, float2 (&v)[2]) {
 }
 
 __global__ void __launch_bounds__(256, 2)
-k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, const bf16* __restrict__ raw, int ldr,
+k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ sgrad, const bf16* __restrict__ raw, int ldr,
                 const float* __restrict__ Kc, bf16* __restrict__ draw, float* __restrict__ dK, int H, int W, int CC,
                 int slabs) {
-  __shared__ uint4 tD[CT_YH * CT_XH * 4];   // dact -> dpre, halo tile
+  extern __shared__ __align__(16) uint8_t csm[];
+  uint4* tD = reinterpret_cast<uint4*>(csm);   // dact -> dpre, (CB_Y+2) x (CT_X+2) halo tile
   __shared__ float red[32 * 9];
   const int tid = threadIdx.x;
   PhaseTimer pt(3);
   const int b = blockIdx.z / slabs, slab = blockIdx.z % slabs;
-  const int x0 = blockIdx.x * CT_X, y0 = blockIdx.y * CT_Y, c0 = slab * 32;
+  const int x0 = blockIdx.x * CT_X, y0 = blockIdx.y * CB_Y, c0 = slab * 32;
   const int boff = b * H * W;
-  conv_tile_load(tD, dact, CC >> 3, boff, c0, H, W, y0, x0, 1, tid, 256);
+  conv_tile_load<CB_Y>(tD, dact, CC >> 3, boff, c0, H, W, y0, x0, 1, tid, 256);
   cp_async_commit();
   for (int i = tid; i < 32 * 9; i += 256) red[i] = 0.f;
   const int xl = tid >> 3, hc = tid & 7, cc = c0 + hc * 4;   // hc: 4-channel half chunk inside the 32-channel slab
@@ -1315,19 +1326,30 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
   cp_async_wait<0>();
   pt.mark(1);
   {
-    for (int i = tid; i < CT_YH * CT_XH * 4; i += 256) {
-      const int chn = i & 3, c = (i >> 2) % CT_XH, r = (i >> 2) / CT_XH;
-      const int y = y0 - 1 + r, x = x0 - 1 + c;
-      if (y >= 0 && y < H && x >= 0 && x < W) {
-        float g[8], p[8];
-        unpack8(tD[i], g);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(pre + tl_off32(boff + y * W + x, c0 + chn * 8, CC >> 3))), p);
+    // sgrad is streamed from global in batches of PB independent loads per thread (latency overlap), then multiplied in
+    constexpr int PB = 6, NEL = (CB_Y + 2) * CT_XH * 4;
+    for (int base = tid; base < NEL; base += 256 * PB) {
+      uint4 sv[PB];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float sgm = sigmoid_fast(p[j]);
-          g[j] *= sgm * (1.f + p[j] * (1.f - sgm));
+      for (int u = 0; u < PB; ++u) {
+        const int i = base + u * 256;
+        const int chn = i & 3, c = (i >> 2) % CT_XH, r = (i >> 2) / CT_XH;
+        const int y = y0 - 1 + r, x = x0 - 1 + c;
+        const bool okp = i < NEL && y >= 0 && y < H && x >= 0 && x < W;
+        sv[u] = okp ? __ldg(reinterpret_cast<const uint4*>(sgrad + tl_off32(boff + y * W + x, c0 + chn * 8, CC >> 3)))
+                    : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < PB; ++u) {
+        const int i = base + u * 256;
+        if (i < NEL) {
+          float2 g[4], sg[4];
+          unpack8_f2(tD[i], g);
+          unpack8_f2(sv[u], sg);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) g[q] = __ffma2_rn(g[q], sg[q], make_float2(0.f, 0.f));
+          tD[i] = pack8_f2(g);       // out-of-image elements: zero-filled tile x zero = zero
         }
-        tD[i] = pack8(g);
       }
     }
   }
@@ -1335,7 +1357,7 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
   __syncthreads();
   pt.mark(3);
   const int x = x0 + xl;
-  const int ny = min(CT_Y, H - y0);
+  const int ny = min(CB_Y, H - y0);
   const bool xin = x < W;   // columns beyond the image compute on zero-filled tile data and never store
   const uint2* tD2 = reinterpret_cast<const uint2*>(tD);
   float2 dk[9][2], win[3][3][2];
@@ -1350,7 +1372,11 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
   const int NR = ldr >> 3;
   const int rtok = boff + y0 * W + (xin ? x : 0);   // raw is TL: rows of one column are W tokens apart
   const uint2 zero2 = make_uint2(0u, 0u);
-  uint2 rnext = (xin && ny > 0) ? __ldg(reinterpret_cast<const uint2*>(raw + tl_off32(rtok, cc, NR))) : zero2;
+  // the centre raw value of row r is fetched three rows ahead (ring of 3 registers matching the 3-way unroll)
+  uint2 rn[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+    rn[q] = (xin && q < ny) ? __ldg(reinterpret_cast<const uint2*>(raw + tl_off32(rtok + q * W, cc, NR))) : zero2;
   for (int rb = 0; rb < ny; rb += 3) {
 #pragma unroll
     for (int ph = 0; ph < 3; ++ph) {
@@ -1358,8 +1384,8 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ pre, con
       if (r < ny) {
         load_row(r + 2, win[(ph + 2) % 3]);
         float2 rc[2], o[2];
-        unpack4_f2(rnext, rc);
-        rnext = (xin && r + 1 < ny) ? __ldg(reinterpret_cast<const uint2*>(raw + tl_off32(rtok + (r + 1) * W, cc, NR))) : zero2;
+        unpack4_f2(rn[ph], rc);
+        rn[ph] = (xin && r + 3 < ny) ? __ldg(reinterpret_cast<const uint2*>(raw + tl_off32(rtok + (r + 3) * W, cc, NR))) : zero2;
         o[0] = make_float2(0.f, 0.f);
         o[1] = make_float2(0.f, 0.f);
 #pragma unroll
@@ -1588,8 +1614,11 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   // ---- conv backward (dpre formed in shared memory; transposed conv + kernel gradient)
   {
     const int slabs = d.CC / 32;
-    dim3 grid(cdiv(d.W, CT_X), cdiv(d.H, CT_Y), d.B * slabs);
-    { ADN_KERNEL("k_conv_bwd_tile", st); k_conv_bwd_tile<<<grid, 256, 0, st>>>(W.dact, S.pre, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.H, d.W, d.CC, slabs); }
+    const size_t smem = (size_t)(CB_Y + 2) * CT_XH * 4 * 16;
+    rc = set_smem(k_conv_bwd_tile, smem);
+    if (rc) return rc;
+    dim3 grid(cdiv(d.W, CT_X), cdiv(d.H, CB_Y), d.B * slabs);
+    { ADN_KERNEL("k_conv_bwd_tile", st); k_conv_bwd_tile<<<grid, 256, smem, st>>>(W.dact, S.pre, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.H, d.W, d.CC, slabs); }
   }
   // ---- in_proj backward
   rc = d.dip <= 128 ? launch_bwd4<32, 1, 2>(d, W.draw, u, F, du, &W.acc, st)
