@@ -238,6 +238,8 @@ __device__ __forceinline__ uint4 pack8_f2(const float2 (&v)[4]) {
   return make_uint4(pack_bf16(v[0].x, v[0].y), pack_bf16(v[1].x, v[1].y), pack_bf16(v[2].x, v[2].y), pack_bf16(v[3].x, v[3].y));
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// softplus with hardware exp2 / log2 (bf16 path only; the fp32 check mode keeps log1pf): abs error ~1e-7
+__device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : __logf(1.f + __expf(x)); }
 
 // ------------------------------------------------------------------------------------------------
 // k_state: S'[b][j][c] += [j%2==c%2] * sum_l Bc[l,j] * w[l,hd(c)] * xc[l,c]      (models/ADNssd.py:267-280, both parities)
@@ -312,7 +314,7 @@ k_state(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int
       float v[8];
       unpack8(*reinterpret_cast<const uint4*>(sDt + (dc * 128 + tid) * 8), v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) w[dc * 8 + j] = softplusf_(v[j] + s_bias[dc * 8 + j]) * s_eA[dc * 8 + j];
+      for (int j = 0; j < 8; ++j) w[dc * 8 + j] = softplus_fast(v[j] + s_bias[dc * 8 + j]) * s_eA[dc * 8 + j];
     }
 #pragma unroll
     for (int cg = 0; cg < XC; ++cg) {
@@ -843,21 +845,21 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
   constexpr uint32_t TCOLS = (DI + GN) <= 128 ? 128 : 256;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_bias[NH], s_eA[NH], s_D[NH];
-  __shared__ uint64_t bar, ld_bar;
+  __shared__ uint64_t bar, ld_bar[2];
   __shared__ uint32_t tmem_slot;
-  bf16* sX = reinterpret_cast<bf16*>(smem);      // [XC][128][8]  x, then w*x in place
-  bf16* sB = sX + XC * 128 * 8;                  // [BC][128][8]  (x and B are adjacent chunks of act: one bulk copy)
-  bf16* sDy = sB + BC * 128 * 8;                 // [XC][128][8]
-  bf16* sDt = sDy + XC * 128 * 8;                // [DC][128][8]
-  bf16* sTa_hi = sDt + DC * 128 * 8;             // [BC][DI][8]
+  // two input stages (the next tile is fetched while this one is computed), each:
+  //   sX [XC][128][8] x, then w*x in place | sB [BC][128][8] (x and B are adjacent chunks of act: one bulk copy)
+  //   sDy [XC][128][8] | sDt [DC][128][8]
+  constexpr int STAGE = (2 * XC + BC + DC) * 128 * 8;
+  bf16* sStage = reinterpret_cast<bf16*>(smem);
+  bf16* sTa_hi = sStage + 2 * STAGE;             // [BC][DI][8]
   bf16* sTa_lo = sTa_hi + BC * DI * 8;
   bf16* sTb_hi = sTa_lo + BC * DI * 8;           // [XC][GN][8]
   bf16* sTb_lo = sTb_hi + XC * GN * 8;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < NH; i += 128) { s_bias[i] = dt_bias[i]; s_eA[i] = __expf(A_log[i]); s_D[i] = Dp[i]; }
-  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&ld_bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&ld_bar[0], 1); mbar_init(&ld_bar[1], 1); fence_mbar_init(); }
   const int NA = CC >> 3, NR = ldr >> 3;
-  uint32_t lph = 0;
   if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
@@ -871,7 +873,24 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
 #pragma unroll
   for (int h = 0; h < NH; ++h) { aD[h] = 0.f; aA[h] = 0.f; aB[h] = 0.f; }
   const int tile_begin = blockIdx.x * tiles_per_cta, tile_end = min(num_tiles, tile_begin + tiles_per_cta);
-  for (int tile = tile_begin; tile < tile_end; ++tile) {
+  auto issue_loads = [&](int tile, int stage) {   // thread 0 only; TL tensors: [x | B] of act, dy of dact, dt columns of raw
+    bf16* sX = sStage + stage * STAGE;
+    bf16* sDy = sX + (XC + BC) * 128 * 8;
+    bf16* sDt = sDy + XC * 128 * 8;
+    mbar_expect_tx(&ld_bar[stage], (uint32_t)(2 * XC + BC + DC) * 128 * 16);
+    tl_bulk(sX, act, tile, NA, XC, XC + BC, &ld_bar[stage]);
+    tl_bulk(sDy, dact, tile, NA, XC, XC, &ld_bar[stage]);
+    tl_bulk(sDt, raw, tile, NR, NA, DC, &ld_bar[stage]);
+  };
+  if (tid == 0 && tile_begin < tile_end) issue_loads(tile_begin, 0);
+  for (int tile = tile_begin, it = 0; tile < tile_end; ++tile, ++it) {
+    const int stage = it & 1;
+    bf16* sX = sStage + stage * STAGE;
+    bf16* sB = sX + XC * 128 * 8;
+    bf16* sDy = sB + BC * 128 * 8;
+    bf16* sDt = sDy + XC * 128 * 8;
+    // prefetch: the other stage was last read by iteration it-1, whose MMAs completed and whose trailing barrier passed
+    if (tid == 0 && tile + 1 < tile_end) issue_loads(tile + 1, stage ^ 1);
     const int b = tile / tiles_per_batch, i = tile % tiles_per_batch;
     const int rows = min(128, L - i * 128);
     const long long tok0 = (long long)b * L + (long long)i * 128;
@@ -880,15 +899,8 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
       stage_state_b<DI, GN>(dS + (long long)b * GN * DI, sTb_hi, sTb_lo, tid);
       cur_b = b;
     }
-    if (tid == 0) {   // TL tensors: [x | B] of act, dy of dact, dt columns of raw
-      mbar_expect_tx(&ld_bar, (uint32_t)(2 * XC + BC + DC) * 128 * 16);
-      tl_bulk(sX, act, tile, NA, XC, XC + BC, &ld_bar);
-      tl_bulk(sDy, dact, tile, NA, XC, XC, &ld_bar);
-      tl_bulk(sDt, raw, tile, NR, NA, DC, &ld_bar);
-    }
     pt.mark(0);
-    ok = mbar_wait(&ld_bar, lph) && ok;
-    lph ^= 1;
+    ok = mbar_wait(&ld_bar[stage], (it >> 1) & 1) && ok;
     fence_async_smem();
     __syncthreads();
     pt.mark(1);
@@ -911,7 +923,7 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float a = v[j] + s_bias[dc * 8 + j];
-        w[dc * 8 + j] = softplusf_(a) * s_eA[dc * 8 + j];
+        w[dc * 8 + j] = softplus_fast(a) * s_eA[dc * 8 + j];
         sg[dc * 8 + j] = a > 20.f ? 1.f : __fdividef(1.f, 1.f + __expf(-a));
       }
     }
@@ -1528,7 +1540,8 @@ static int launch_bwd1(const MixerDims& d, const bf16* dout, const bf16* act, co
 template <int DI, int GN>
 static int launch_bwd2(const MixerDims& d, const bf16* act, const bf16* raw, const float* dS, const AdnWeights& w,
                        const FastWs& F, bf16* dact, bf16* draw, const GradAcc& acc, cudaStream_t st) {
-  constexpr size_t smem = ((size_t)(GN / 8 + 2 * (DI / 8) + DI / 32) * 128 * 8 + 2 * (GN / 8) * DI * 8 + 2 * (DI / 8) * GN * 8) * sizeof(bf16);
+  constexpr size_t smem = (2 * (size_t)(GN / 8 + 2 * (DI / 8) + DI / 32) * 128 * 8 + 2 * (GN / 8) * DI * 8 + 2 * (DI / 8) * GN * 8) * sizeof(bf16);
+  static_assert(smem <= 227 * 1024, "k_bwd2 stages do not fit shared memory");
   int rc = set_smem(k_bwd2<DI, GN>, smem);
   if (rc) return rc;
   const int tpb = cdiv(d.L, 128), nt = tpb * d.B;
