@@ -17,6 +17,30 @@ constexpr int WT_MAXK = 7;
 
 struct LevelGeom { int h, w, h2, w2; };  // this level's input plane and its sub-band plane (h2 = ceil(h/2))
 
+// the 2x2 quad (a b; c d) whose top-left pixel is (y0, x0) of a plane with row pitch w (zero beyond the plane);
+// when w is even the two pixels of a row are fetched with one 2-element vector load (x0 is always even)
+__device__ __forceinline__ void ld2(const float* p, float& a, float& b) { const float2 t = *reinterpret_cast<const float2*>(p); a = t.x; b = t.y; }
+__device__ __forceinline__ void ld2(const bf16* p, float& a, float& b) {
+  const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(p);
+  const float2 f = __bfloat1622float2(t);
+  a = f.x; b = f.y;
+}
+template <typename TI>
+__device__ __forceinline__ void load_quad(const TI* __restrict__ src, int h, int w, int y0, int x0, bool weven, float& a, float& b,
+                                          float& c, float& d) {
+  const bool yb = y0 + 1 < h;
+  if (weven) {
+    ld2(src + (long long)y0 * w + x0, a, b);
+    if (yb) ld2(src + (long long)(y0 + 1) * w + x0, c, d); else { c = 0.f; d = 0.f; }
+  } else {
+    const bool xb = x0 + 1 < w;
+    a = ldf(src + (long long)y0 * w + x0);
+    b = xb ? ldf(src + (long long)y0 * w + x0 + 1) : 0.f;
+    c = yb ? ldf(src + (long long)(y0 + 1) * w + x0) : 0.f;
+    d = (xb && yb) ? ldf(src + (long long)(y0 + 1) * w + x0 + 1) : 0.f;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LL band only: out[p][y][x] = 0.5 * (a + b + c + d) of the (zero-padded) 2x2 quad.   thread = one output
 // ---------------------------------------------------------------------------------------------
@@ -36,6 +60,23 @@ __global__ void k_haar_ll(const TI* __restrict__ in, float* __restrict__ out, lo
   float c = yb ? ldf(src + (long long)(y0 + 1) * w + x0) : 0.f;
   float d = (xb && yb) ? ldf(src + (long long)(y0 + 1) * w + x0 + 1) : 0.f;
   out[idx] = 0.5f * (a + b + c + d);
+}
+
+// Same, for even h and w % 4 == 0: one thread = two adjacent outputs from two aligned 4-element row segments
+template <typename TI>
+__global__ void k_haar_ll_vec(const TI* __restrict__ in, float* __restrict__ out, long long planes, int h, int w) {
+  const int w2 = w >> 1, h2 = h >> 1, wq = w >> 2;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = planes * h2 * wq;
+  if (idx >= total) return;
+  const int xq = (int)(idx % wq), y = (int)((idx / wq) % h2);
+  const long long p = idx / ((long long)wq * h2);
+  const TI* r0 = in + (p * h + 2 * y) * w + 4 * xq;
+  float t[4], u[4];
+  ld4(r0, t);
+  ld4(r0 + w, u);
+  float2 o = make_float2(0.5f * (t[0] + t[1] + u[0] + u[1]), 0.5f * (t[2] + t[3] + u[2] + u[3]));
+  *reinterpret_cast<float2*>(out + (p * h2 + y) * w2 + 2 * xq) = o;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -65,6 +106,7 @@ k_wt_level(const TI* __restrict__ in, const float* __restrict__ coarse, TO* __re
   const int sy0 = ty * WT_TH, sx0 = tx * WT_TW;
   const TI* src = in + plane * (long long)g.h * g.w;
   const int tid = threadIdx.x;
+  const bool weven = (g.w & 1) == 0 && ((plane * (long long)g.h * g.w) & 1) == 0;
   for (int i = tid; i < 4 * K * K; i += 128) {
     int band = i / (K * K), t = i % (K * K);
     Wk[band][FLIP ? K * K - 1 - t : t] = Wl[((long long)c * 4 + band) * K * K + t];
@@ -75,14 +117,7 @@ k_wt_level(const TI* __restrict__ in, const float* __restrict__ coarse, TO* __re
     int sy = i / SW, sx = i % SW;
     int gy = sy0 - R + sy, gx = sx0 - R + sx;
     float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
-    if (gy >= 0 && gy < g.h2 && gx >= 0 && gx < g.w2) {
-      int y0 = 2 * gy, x0 = 2 * gx;
-      bool yb = y0 + 1 < g.h, xb = x0 + 1 < g.w;
-      a = ldf(src + (long long)y0 * g.w + x0);
-      if (xb) b = ldf(src + (long long)y0 * g.w + x0 + 1);
-      if (yb) cc = ldf(src + (long long)(y0 + 1) * g.w + x0);
-      if (xb && yb) d = ldf(src + (long long)(y0 + 1) * g.w + x0 + 1);
-    }
+    if (gy >= 0 && gy < g.h2 && gx >= 0 && gx < g.w2) load_quad(src, g.h, g.w, 2 * gy, 2 * gx, weven, a, b, cc, d);
     S[0][sy][sx] = 0.5f * (a + b + cc + d);
     S[1][sy][sx] = 0.5f * (a + b - cc - d);
     S[2][sy][sx] = 0.5f * (a - b + cc - d);
@@ -190,6 +225,7 @@ __global__ void k_wt_wgrad(const TX* __restrict__ xin, const TG* __restrict__ gi
   const TX* xs = xin + plane * (long long)g.h * g.w;
   const TG* gs = gin + plane * (long long)g.h * g.w;
   const int tid = threadIdx.x, nt = blockDim.x;
+  const bool weven = (g.w & 1) == 0 && ((plane * (long long)g.h * g.w) & 1) == 0;
   for (int i = tid; i < NB * K * K; i += nt) red[i] = 0.f;
   if (tid == 0) redsum = 0.f;
   for (int i = tid; i < SH * SW; i += nt) {
@@ -198,14 +234,7 @@ __global__ void k_wt_wgrad(const TX* __restrict__ xin, const TG* __restrict__ gi
     bool in = gy >= 0 && gy < dh && gx >= 0 && gx < dw;
     if (NB == 4) {
       float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
-      if (in) {
-        int y0 = 2 * gy, x0 = 2 * gx;
-        bool yb = y0 + 1 < g.h, xb = x0 + 1 < g.w;
-        a = ldf(xs + (long long)y0 * g.w + x0);
-        if (xb) b = ldf(xs + (long long)y0 * g.w + x0 + 1);
-        if (yb) cc = ldf(xs + (long long)(y0 + 1) * g.w + x0);
-        if (xb && yb) d = ldf(xs + (long long)(y0 + 1) * g.w + x0 + 1);
-      }
+      if (in) load_quad(xs, g.h, g.w, 2 * gy, 2 * gx, weven, a, b, cc, d);
       S[0][sy][sx] = 0.5f * (a + b + cc + d);
       S[NB > 1 ? 1 : 0][sy][sx] = 0.5f * (a + b - cc - d);
       S[NB > 2 ? 2 : 0][sy][sx] = 0.5f * (a - b + cc - d);
@@ -221,14 +250,7 @@ __global__ void k_wt_wgrad(const TX* __restrict__ xin, const TG* __restrict__ gi
     bool in = gy < dh && gx < dw;
     if (NB == 4) {
       float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
-      if (in) {
-        int y0 = 2 * gy, x0 = 2 * gx;
-        bool yb = y0 + 1 < g.h, xb = x0 + 1 < g.w;
-        a = ldf(gs + (long long)y0 * g.w + x0);
-        if (xb) b = ldf(gs + (long long)y0 * g.w + x0 + 1);
-        if (yb) cc = ldf(gs + (long long)(y0 + 1) * g.w + x0);
-        if (xb && yb) d = ldf(gs + (long long)(y0 + 1) * g.w + x0 + 1);
-      }
+      if (in) load_quad(gs, g.h, g.w, 2 * gy, 2 * gx, weven, a, b, cc, d);
       Dt[0][sy][sx] = 0.5f * (a + b + cc + d);
       Dt[NB > 1 ? 1 : 0][sy][sx] = 0.5f * (a + b - cc - d);
       Dt[NB > 2 ? 2 : 0][sy][sx] = 0.5f * (a - b + cc - d);
@@ -240,7 +262,7 @@ __global__ void k_wt_wgrad(const TX* __restrict__ xin, const TG* __restrict__ gi
     }
   }
   __syncthreads();
-  // roles: tid -> (rows group rg in [0,8), band, a)
+  // roles: tid -> (rows group rg in [0,8), band, tap row a): slides a K-wide window along x for its tap row
   const int role = tid;
   if (role < NB * K * 8) {
     const int rg = role % 8, a = (role / 8) % K, band = role / (8 * K);
@@ -280,28 +302,35 @@ struct WtFinalize {
   const float *Rb, *sumg;
 };
 
-__global__ void k_wt_finalize(WtFinalize a, WtWeights w, WtWeightGrads g, int C, int K2, int levels) {
-  const int i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-  for (int l = 0; l < levels; ++l) {
-    for (int ch = i0; ch < 4 * C; ch += stride) {
-      const float sc = w.wavelet_scale_w[l][ch];
-      float ds = 0.f;
-      for (int t = 0; t < K2; ++t) {
-        float r = a.Rl[l][ch * K2 + t];
-        if (g.wavelet_conv_w[l]) g.wavelet_conv_w[l][ch * K2 + t] = sc * r;
-        ds += w.wavelet_conv_w[l][ch * K2 + t] * r;
-      }
-      if (g.wavelet_scale_w[l]) g.wavelet_scale_w[l][ch] = ds;
-    }
-  }
-  for (int c = i0; c < C; c += stride) {
-    const float bs = w.base_scale_w[c], sg = a.sumg[c];
+__global__ void __launch_bounds__(32)
+k_wt_finalize(WtFinalize a, WtWeights w, WtWeightGrads g, int C, int K2, int levels) {
+  // blockIdx.x < levels*4C: one warp per (level, sub-band channel); then C warps for the base conv channels
+  const int lane = threadIdx.x;
+  int id = blockIdx.x;
+  if (id < levels * 4 * C) {
+    const int l = id / (4 * C), ch = id % (4 * C);
+    const float sc = w.wavelet_scale_w[l][ch];
     float ds = 0.f;
-    for (int t = 0; t < K2; ++t) {
-      float r = a.Rb[c * K2 + t];
-      if (g.base_conv_w) g.base_conv_w[c * K2 + t] = bs * r;
-      ds += w.base_conv_w[c * K2 + t] * r;
+    for (int t = lane; t < K2; t += 32) {
+      const float r = a.Rl[l][ch * K2 + t];
+      if (g.wavelet_conv_w[l]) g.wavelet_conv_w[l][ch * K2 + t] = sc * r;
+      ds = fmaf(w.wavelet_conv_w[l][ch * K2 + t], r, ds);
     }
+    ds = warp_sum(ds);
+    if (lane == 0 && g.wavelet_scale_w[l]) g.wavelet_scale_w[l][ch] = ds;
+    return;
+  }
+  const int c = id - levels * 4 * C;
+  if (c >= C) return;
+  const float bs = w.base_scale_w[c], sg = a.sumg[c];
+  float ds = 0.f;
+  for (int t = lane; t < K2; t += 32) {
+    const float r = a.Rb[c * K2 + t];
+    if (g.base_conv_w) g.base_conv_w[c * K2 + t] = bs * r;
+    ds = fmaf(w.base_conv_w[c * K2 + t], r, ds);
+  }
+  ds = warp_sum(ds);
+  if (lane == 0) {
     if (w.base_conv_b) {
       ds += w.base_conv_b[c] * sg;
       if (g.base_conv_b) g.base_conv_b[c] = bs * sg;
@@ -416,11 +445,16 @@ static int run_pass(const WtShape& s, const WtPlan& p, const WtWeights& w, const
   for (int i = 1; i < p.L; ++i) {
     float* o = pyr + p.pyr_off[i];
     long long total = p.planes * p.g[i].h * p.g[i].w;
-    if (i == 1)
-      { ADN_KERNEL("k_haar_ll", st); k_haar_ll<T><<<cdiv(total, 256), 256, 0, st>>>(src, o, p.planes, p.g[0].h, p.g[0].w, p.g[0].h2, p.g[0].w2); }
-    else
-      { ADN_KERNEL("k_haar_ll", st); k_haar_ll<float><<<cdiv(total, 256), 256, 0, st>>>(pyr + p.pyr_off[i - 1], o, p.planes, p.g[i - 1].h, p.g[i - 1].w,
-                                                        p.g[i - 1].h2, p.g[i - 1].w2); }
+    const LevelGeom& gi = p.g[i - 1];
+    const bool vec = (gi.h % 2 == 0) && (gi.w % 4 == 0);
+    if (i == 1) {
+      if (vec) { ADN_KERNEL("k_haar_ll", st); k_haar_ll_vec<T><<<cdiv(total / 2, 256), 256, 0, st>>>(src, o, p.planes, gi.h, gi.w); }
+      else { ADN_KERNEL("k_haar_ll", st); k_haar_ll<T><<<cdiv(total, 256), 256, 0, st>>>(src, o, p.planes, gi.h, gi.w, gi.h2, gi.w2); }
+    } else {
+      const float* pin = pyr + p.pyr_off[i - 1];
+      if (vec) { ADN_KERNEL("k_haar_ll", st); k_haar_ll_vec<float><<<cdiv(total / 2, 256), 256, 0, st>>>(pin, o, p.planes, gi.h, gi.w); }
+      else { ADN_KERNEL("k_haar_ll", st); k_haar_ll<float><<<cdiv(total, 256), 256, 0, st>>>(pin, o, p.planes, gi.h, gi.w, gi.h2, gi.w2); }
+    }
   }
   for (int i = p.L - 1; i >= 0; --i) {
     const float* coarse = (i == p.L - 1) ? nullptr : chain + p.pyr_off[i + 1];
@@ -480,7 +514,7 @@ static int wt_backward(const WtShape& s, const WtWeights& w0, const T* x, const 
   WtFinalize f;
   for (int l = 0; l < ADN_WT_MAX_LEVELS; ++l) f.Rl[l] = l < s.levels ? acc.Rl[l] : nullptr;
   f.Rb = acc.Rb; f.sumg = acc.sumg;
-  { ADN_KERNEL("k_wt_finalize", st); k_wt_finalize<<<cdiv(4 * s.C, 128), 128, 0, st>>>(f, w, g, s.C, s.k * s.k, s.levels); }
+  { ADN_KERNEL("k_wt_finalize", st); k_wt_finalize<<<s.levels * 4 * s.C + s.C, 32, 0, st>>>(f, w, g, s.C, s.k * s.k, s.levels); }
   ADN_CHECK_LAUNCH();
   return ADN_OK;
 }
