@@ -117,6 +117,7 @@ int adnssd_workspace_bytes(const AdnShape* s, size_t* saved_bytes, size_t* fwd_w
     sm100_workspace_bytes(d, &fw2, &bw2);
     fw = fw > fw2 ? fw : fw2;
     bw = bw > bw2 ? bw : bw2;
+    sv += sm100_saved_extra_bytes(d);
   }
   if (saved_bytes) *saved_bytes = sv;
   if (fwd_ws) *fwd_ws = fw;

@@ -537,10 +537,12 @@ struct GradAcc {
   int dWin_parts;
 };
 
-static __global__ void k_finalize(GradAcc a, AdnWeights w, AdnWeightGrads g, int D, int Di, int GN, int nh, int dip) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// `proj` = also emit in_proj / out_proj / norm / alpha1 gradients from the accumulators (the tcgen05 path produces those
+// in its own fused finalize and passes proj = false)
+__device__ __forceinline__ void finalize_body(const GradAcc& a, const AdnWeights& w, const AdnWeightGrads& g, int D, int Di,
+                                              int GN, int nh, int dip, long long i0, long long stride, bool proj) {
   const float a1 = *w.alpha1;
+  if (proj) {
   if (g.in_proj_w)
     for (long long i = i0; i < (long long)dip * D; i += stride) {
       float v = a.dWin[i];
@@ -553,12 +555,13 @@ static __global__ void k_finalize(GradAcc a, AdnWeights w, AdnWeightGrads g, int
     if (g.norm_w) g.norm_w[i] = a.dgamma[i];
     if (g.norm_b) g.norm_b[i] = a.dbeta[i];
   }
+  if (i0 == 0 && g.alpha1) g.alpha1[0] = a.dalpha1[0];
+  }
   for (long long i = i0; i < nh; i += stride) {
     if (g.D) g.D[i] = a.dD[i];
     if (g.A_log) g.A_log[i] = a.dAlog[i];
     if (g.dt_bias) g.dt_bias[i] = a.ddtb[i];
   }
-  if (i0 == 0 && g.alpha1) g.alpha1[0] = a.dalpha1[0];
   if (g.conv2d_z_w)
     for (long long i = i0; i < (long long)Di * 9; i += stride) g.conv2d_z_w[i] = a.dK[i];
   const int Wd = Di + 2 * GN;
@@ -592,6 +595,11 @@ static __global__ void k_finalize(GradAcc a, AdnWeights w, AdnWeightGrads g, int
     if (g31) g31[tap] = dk[tap * 3 + 0] * w13[0] + dk[tap * 3 + 1] * w13[1] + dk[tap * 3 + 2] * w13[2];
     if (g13) g13[tap] = dk[0 * 3 + tap] * w31[0] + dk[1 * 3 + tap] * w31[1] + dk[2 * 3 + tap] * w31[2];
   }
+}
+
+static __global__ void k_finalize(GradAcc a, AdnWeights w, AdnWeightGrads g, int D, int Di, int GN, int nh, int dip) {
+  finalize_body(a, w, g, D, Di, GN, nh, dip, (long long)blockIdx.x * blockDim.x + threadIdx.x,
+                (long long)gridDim.x * blockDim.x, true);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -802,31 +802,6 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
   if (warp == 0) tmem_dealloc(tbase, TCOLS);
 }
 
-// Rt / sdout -> the accumulators the shared finalize kernel expects (raw dW_out, dgamma, dbeta, dalpha1).
-//   dW_out_raw[d][c] = gamma[c]*Rt[c][d] + beta[c]*sd[d]  (c < DI),  Rt[c][d]  (c >= DI)
-//   dgamma[c] = a1 * sum_d W[d][c] Rt[c][d] ;  dbeta[c] = a1 * sum_d W[d][c] sd[d] ;  dalpha1 = sum W .* dW_out_raw
-__global__ void __launch_bounds__(32)
-k_bwd1_post(const float* __restrict__ Rt, const float* __restrict__ sdout, const float* __restrict__ Wout,
-            const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ alpha1p,
-            float* __restrict__ dWout, float* __restrict__ dgamma, float* __restrict__ dbeta,
-            float* __restrict__ dalpha1, int D, int DI) {
-  const int c = blockIdx.x;          // one warp per column c of [LN(y) | zc]; lanes stride over d
-  const float a1 = *alpha1p;
-  float dg = 0.f, db = 0.f, da = 0.f;
-  for (int d = threadIdx.x; d < D; d += 32) {
-    const float r = Rt[c * D + d], wv = Wout[d * 2 * DI + c], sd = sdout[d];
-    const float raw = c < DI ? gamma[c] * r + beta[c] * sd : r;
-    dWout[d * 2 * DI + c] = raw;
-    da = fmaf(wv, raw, da);
-    dg = fmaf(wv, r, dg);
-    db = fmaf(wv, sd, db);
-  }
-  dg = warp_sum(dg); db = warp_sum(db); da = warp_sum(da);
-  if (threadIdx.x == 0) {
-    if (c < DI) { dgamma[c] = a1 * dg; dbeta[c] = a1 * db; }
-    atomicAdd(dalpha1, da);
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // k_bwd2 (phase B2), per 128-token tile, after dS' is complete:
@@ -1175,22 +1150,58 @@ k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__
   if (warp == 0) tmem_dealloc(tbase, TCOLS);
 }
 
-// acc[i] += sum_p part[p][i]   (per-CTA partial slabs of dW_in); block = 32 elements x 8 part-lanes
+
+// One launch for every parameter gradient of the tcgen05 path:
+//   blocks [0, nb_in)            dW_in = sum of the per-CTA slabs written by k_bwd4            (32 elements x 8 slab lanes)
+//   blocks [nb_in, nb_in + 2Di)  dW_out, dgamma, dbeta, dalpha1 partial from Rt / sum(dout)    (one warp per column)
+//   remaining blocks             dD, dA_log, ddt_bias and the ten conv weight gradients from dK (shared finalize_body)
 __global__ void __launch_bounds__(256)
-k_reduce_parts(const float* __restrict__ part, float* __restrict__ acc, int n, int parts) {
+k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, const float* __restrict__ Rt, const float* __restrict__ sdout,
+                int D, int Di, int GN, int nh, int dip, int nb_in, int nb_rest) {
   __shared__ float red[8][33];
-  const int e = blockIdx.x * 32 + (threadIdx.x & 31), pl = threadIdx.x >> 5;
-  float v = 0.f;
-  if (e < n)
-    for (int p = pl; p < parts; p += 8) v += part[(long long)p * n + e];
-  red[pl][threadIdx.x & 31] = v;
-  __syncthreads();
-  if (pl == 0 && e < n) {
-    float t = 0.f;
+  const int tid = threadIdx.x;
+  int blk = blockIdx.x;
+  if (blk < nb_in) {
+    const int n = dip * D, e = blk * 32 + (tid & 31), pl = tid >> 5;
+    float v = 0.f;
+    if (e < n)
+      for (int p = pl; p < a.dWin_parts; p += 8) v += a.dWin_part[(long long)p * n + e];
+    red[pl][tid & 31] = v;
+    __syncthreads();
+    if (pl == 0 && e < n && g.in_proj_w) {
+      float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
-    acc[e] += t;
+      for (int k = 0; k < 8; ++k) t += red[k][tid & 31];
+      g.in_proj_w[e] = t;
+    }
+    return;
   }
+  blk -= nb_in;
+  if (blk < 2 * Di) {
+    if (tid >= 32) return;
+    const int c = blk;
+    const float a1 = *w.alpha1;
+    float dg = 0.f, db = 0.f, da = 0.f;
+    for (int d = tid; d < D; d += 32) {
+      const float r = Rt[c * D + d], wv = w.out_proj_w[d * 2 * Di + c], sd = sdout[d];
+      const float rawv = c < Di ? w.norm_w[c] * r + w.norm_b[c] * sd : r;
+      if (g.out_proj_w) g.out_proj_w[d * 2 * Di + c] = a1 * rawv;
+      da = fmaf(wv, rawv, da);
+      dg = fmaf(wv, r, dg);
+      db = fmaf(wv, sd, db);
+    }
+    dg = warp_sum(dg); db = warp_sum(db); da = warp_sum(da);
+    if (tid == 0) {
+      if (c < Di) {
+        if (g.norm_w) g.norm_w[c] = a1 * dg;
+        if (g.norm_b) g.norm_b[c] = a1 * db;
+      }
+      if (g.alpha1) atomicAdd(g.alpha1, da);     // g.alpha1 is zeroed by the host before this launch
+    }
+    return;
+  }
+  blk -= 2 * Di;
+  finalize_body(a, w, g, D, Di, GN, nh, dip, (long long)blk * 256 + tid, (long long)nb_rest * 256, false);
 }
 
 // One launch for all per-call weight preparation: conv kernel assembly, in_proj hi/lo split, out_proj -> bf16.
@@ -1442,22 +1453,34 @@ k_conv_bwd_tile(const bf16* __restrict__ dact, const bf16* __restrict__ sgrad, c
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct FastWs {           // placed after the generic workspace of the same pass
+// Per-call weight preparation (k_prep).  During training it lives at the end of the `saved` buffer, so the backward pass
+// reuses what the forward prepared (the weights cannot change in between); for inference it lives in the workspace.
+struct PrepBufs {
+  float* Kc;             // [CC][9] assembled conv kernels
   bf16 *Whi, *Wlo, *Wout;
   bf16 *WT_hi, *WT_lo;   // W_in^T as a K-major B operand image: [ceil(dip/128)*16 chunks][D][8], zero padded
-  float* dWin_part;      // [148][dip*D] per-CTA partial sums of dW_in (k_bwd4)
   int wt_chunks;
-  float *Rt, *sdout;     // k_bwd1 accumulators: Rt[2Di][D], sdout[D] (contiguous, zeroed together)
-  int* status;
   size_t bytes;
-  FastWs(const MixerDims& d, void* p) {
+  PrepBufs(const MixerDims& d, void* p) {
     Carver c(p);
+    Kc = c.take<float>((size_t)d.CC * 9);
     Whi = c.take<bf16>((size_t)d.dip * d.D);
     Wlo = c.take<bf16>((size_t)d.dip * d.D);
     Wout = c.take<bf16>((size_t)d.D * 2 * d.Di);
     wt_chunks = 16 * cdiv(d.dip, 128);
     WT_hi = c.take<bf16>((size_t)wt_chunks * d.D * 8);
     WT_lo = c.take<bf16>((size_t)wt_chunks * d.D * 8);
+    bytes = c.off;
+  }
+};
+
+struct FastWs {           // placed after the generic workspace of the same pass
+  float* dWin_part;      // [148][dip*D] per-CTA partial sums of dW_in (k_bwd4)
+  float *Rt, *sdout;     // k_bwd1 accumulators: Rt[2Di][D], sdout[D] (contiguous, zeroed together)
+  int* status;
+  size_t bytes;
+  FastWs(const MixerDims& d, void* p) {
+    Carver c(p);
     dWin_part = c.take<float>((size_t)148 * d.dip * d.D);
     Rt = c.take<float>((size_t)2 * d.Di * d.D + d.D);
     sdout = Rt ? Rt + (size_t)2 * d.Di * d.D : nullptr;
@@ -1501,19 +1524,21 @@ static int launch_readout(const MixerDims& d, const bf16* act, const float* S, c
   return ADN_OK;
 }
 
+size_t sm100_saved_extra_bytes(const MixerDims& d) { return sm100_supported(d) ? PrepBufs(d, nullptr).bytes : 0; }
+
 void sm100_workspace_bytes(const MixerDims& d, size_t* f, size_t* b) {
-  size_t extra = FastWs(d, nullptr).bytes;
+  size_t extra = FastWs(d, nullptr).bytes + PrepBufs(d, nullptr).bytes;
   *f = FwdWs<bf16, TWf>(d, nullptr).bytes + extra;
   *b = BwdWs<bf16, TWf>(d, nullptr).bytes + extra;
 }
 
 template <int D>
-static int launch_inproj(const MixerDims& d, const bf16* u, const FastWs& F, bf16* raw, cudaStream_t st) {
+static int launch_inproj(const MixerDims& d, const bf16* u, const PrepBufs& P, const FastWs& F, bf16* raw, cudaStream_t st) {
   const int num_tiles = cdiv(d.T, 128);
   const size_t smem = (size_t)(2 * 256 * D + 2 * 128 * D) * sizeof(bf16);
   ADN_CHECK_CUDA(cudaFuncSetAttribute(k_inproj<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(num_tiles, 148 * 2);
-  { ADN_KERNEL("k_inproj", st); k_inproj<D><<<grid, 128, smem, st>>>(u, F.Whi, F.Wlo, raw, d.ldr, d.dip, d.T, num_tiles, F.status); }
+  { ADN_KERNEL("k_inproj", st); k_inproj<D><<<grid, 128, smem, st>>>(u, P.Whi, P.Wlo, raw, d.ldr, d.dip, d.T, num_tiles, F.status); }
   return ADN_OK;
 }
 
@@ -1525,7 +1550,7 @@ static inline void split_tiles(int num_tiles, int per_sm, int* grid, int* per_ct
 
 template <int DI, int GN>
 static int launch_bwd1(const MixerDims& d, const bf16* dout, const bf16* act, const float* S, const AdnWeights& w,
-                       const FastWs& F, bf16* dact, float* dS, cudaStream_t st) {
+                       const PrepBufs& P, const FastWs& F, bf16* dact, float* dS, cudaStream_t st) {
   constexpr int D = DI / 2;
   constexpr size_t smem = ((size_t)(D / 8 + GN / 8 + 32) * 128 * 8 + (D / 8) * 2 * DI * 8 + 2 * (GN / 8) * DI * 8 + 2 * (DI / 8) * GN * 8) * sizeof(bf16);
   int rc = set_smem(k_bwd1<DI, GN>, smem);
@@ -1533,7 +1558,7 @@ static int launch_bwd1(const MixerDims& d, const bf16* dout, const bf16* act, co
   const int tpb = cdiv(d.L, 128), nt = tpb * d.B;
   int grid, per;
   split_tiles(nt, smem > 110 * 1024 ? 1 : 2, &grid, &per);
-  { ADN_KERNEL("k_bwd1", st); k_bwd1<DI, GN><<<grid, 128, smem, st>>>(dout, act, d.CC, S, w.D, w.norm_w, w.alpha1, F.Wout, dact, F.Rt, F.sdout, dS, d.L, tpb, nt, per, F.status); }
+  { ADN_KERNEL("k_bwd1", st); k_bwd1<DI, GN><<<grid, 128, smem, st>>>(dout, act, d.CC, S, w.D, w.norm_w, w.alpha1, P.Wout, dact, F.Rt, F.sdout, dS, d.L, tpb, nt, per, F.status); }
   return ADN_OK;
 }
 
@@ -1552,7 +1577,7 @@ static int launch_bwd2(const MixerDims& d, const bf16* act, const bf16* raw, con
 }
 
 template <int D, int MB, int NS>
-static int launch_bwd4(const MixerDims& d, const bf16* draw, const bf16* u, const FastWs& F, bf16* du, GradAcc* acc,
+static int launch_bwd4(const MixerDims& d, const bf16* draw, const bf16* u, const PrepBufs& P, const FastWs& F, bf16* du, GradAcc* acc,
                        cudaStream_t st) {
   constexpr size_t smem = (NS * (size_t)(16 * MB + D / 8) * 128 * 8 + 2 * 16 * MB * D * 8) * sizeof(bf16);
   static_assert(smem <= 227 * 1024, "k_bwd4 stages do not fit shared memory");
@@ -1561,8 +1586,9 @@ static int launch_bwd4(const MixerDims& d, const bf16* draw, const bf16* u, cons
   const int nt = cdiv(d.T, 128);
   int grid, per;
   split_tiles(nt, 1, &grid, &per);      // one CTA per SM (<= 148 partial slabs)
-  { ADN_KERNEL("k_bwd4", st); k_bwd4<D, MB, NS><<<grid, 128, smem, st>>>(draw, d.ldr, d.dip, u, F.WT_hi, F.WT_lo, du, F.dWin_part, d.T, nt, per, F.status); }
-  { ADN_KERNEL("k_reduce_parts", st); k_reduce_parts<<<cdiv(d.dip * d.D, 32), 256, 0, st>>>(F.dWin_part, acc->dWin, d.dip * d.D, grid); }
+  { ADN_KERNEL("k_bwd4", st); k_bwd4<D, MB, NS><<<grid, 128, smem, st>>>(draw, d.ldr, d.dip, u, P.WT_hi, P.WT_lo, du, F.dWin_part, d.T, nt, per, F.status); }
+  acc->dWin_part = F.dWin_part;
+  acc->dWin_parts = grid;
   return ADN_OK;
 }
 
@@ -1573,29 +1599,31 @@ int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* 
   FastWs F(d, (char*)ws + W.bytes);
   SavedBufs<T> S = saved ? SavedBufs<T>(d, saved) : W.tmp;
   const bool training = saved != nullptr;
+  PrepBufs P(d, training ? (char*)saved + S.bytes : (char*)ws + W.bytes + F.bytes);
   const long long Tt = d.T;
   ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
   {
-    const int n_in = d.dip * d.D, n_out = d.D * 2 * d.Di, n = max(max(n_in, n_out), d.CC);
-    { ADN_KERNEL("k_prep", st); k_prep<<<cdiv(n, 256), 256, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC, w.in_proj_w, F.Whi, F.Wlo, n_in, w.out_proj_w, F.Wout, n_out, nullptr, nullptr, 0, d.D, d.dip); }
+    const int n_in = d.dip * d.D, n_out = d.D * 2 * d.Di, n_wt = P.wt_chunks * d.D * 8;
+    const int n = max(max(max(n_in, n_out), d.CC), n_wt);
+    { ADN_KERNEL("k_prep", st); k_prep<<<cdiv(n, 256), 256, 0, st>>>(conv_ptrs(w), P.Kc, d.Di, d.CC, w.in_proj_w, P.Whi, P.Wlo, n_in, w.out_proj_w, P.Wout, n_out, P.WT_hi, P.WT_lo, n_wt, d.D, d.dip); }
   }
   // (1) in_proj on tcgen05
-  int rc = d.D == 16 ? launch_inproj<16>(d, u, F, S.raw, st) : d.D == 32 ? launch_inproj<32>(d, u, F, S.raw, st)
-                                                                         : launch_inproj<64>(d, u, F, S.raw, st);
+  int rc = d.D == 16 ? launch_inproj<16>(d, u, P, F, S.raw, st) : d.D == 32 ? launch_inproj<32>(d, u, P, F, S.raw, st)
+                                                                         : launch_inproj<64>(d, u, P, F, S.raw, st);
   if (rc) return rc;
   // (2) depthwise 3x3 + SiLU
   {
     const int slabs = d.CC / 32;
     dim3 grid(cdiv(d.W, CT_X), cdiv(d.H, CT_Y), d.B * slabs);
-    { ADN_KERNEL("k_conv_fwd_tile", st); k_conv_fwd_tile<<<grid, 128, 0, st>>>(S.raw, d.ldr, W.Kc, training ? S.pre : nullptr, S.act, d.H, d.W, d.CC, slabs); }
+    { ADN_KERNEL("k_conv_fwd_tile", st); k_conv_fwd_tile<<<grid, 128, 0, st>>>(S.raw, d.ldr, P.Kc, training ? S.pre : nullptr, S.act, d.H, d.W, d.CC, slabs); }
   }
   (void)Tt;
   // (4a) state on tcgen05 (reduction over tokens), (4b)+(5) readout + LayerNorm + out_proj on tcgen05
   ADN_CHECK_CUDA(cudaMemsetAsync(S.S, 0, (size_t)d.B * d.GN * d.Di * sizeof(float), st));
   rc = d.GN == 32 ? launch_state<64, 32>(d, S.act, S.raw, w, S.S, F.status, st) : launch_state<64, 128>(d, S.act, S.raw, w, S.S, F.status, st);
   if (rc) return rc;
-  rc = d.GN == 32 ? launch_readout<64, 32>(d, S.act, S.S, w, F.Wout, out, F.status, st)
-                  : launch_readout<64, 128>(d, S.act, S.S, w, F.Wout, out, F.status, st);
+  rc = d.GN == 32 ? launch_readout<64, 32>(d, S.act, S.S, w, P.Wout, out, F.status, st)
+                  : launch_readout<64, 128>(d, S.act, S.S, w, P.Wout, out, F.status, st);
   if (rc) return rc;
   ADN_CHECK_LAUNCH();
   return ADN_OK;
@@ -1607,19 +1635,14 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   BwdWs<T, TWf> W(d, ws);
   FastWs F(d, (char*)ws + W.bytes);
   SavedBufs<T> S(d, const_cast<void*>(saved));
+  PrepBufs P(d, (char*)const_cast<void*>(saved) + S.bytes);   // prepared by the forward pass of this step
   ADN_CHECK_CUDA(cudaMemsetAsync(W.zero_begin, 0, W.zero_bytes, st));
   ADN_CHECK_CUDA(cudaMemsetAsync(F.Rt, 0, ((size_t)2 * d.Di * d.D + d.D) * sizeof(float), st));
   ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
-  {
-    const int n_in = d.dip * d.D, n_out = d.D * 2 * d.Di, n_wt = F.wt_chunks * d.D * 8;
-    const int n = max(max(max(n_in, n_out), d.CC), n_wt);
-    { ADN_KERNEL("k_prep", st); k_prep<<<cdiv(n, 256), 256, 0, st>>>(conv_ptrs(w), W.Kc, d.Di, d.CC, w.in_proj_w, F.Whi, F.Wlo, n_in, w.out_proj_w, F.Wout, n_out, F.WT_hi, F.WT_lo, n_wt, d.D, d.dip); }
-  }
   // ---- phase B1: dout -> dy, dzc, dCc ; reductions Rt, dS'
-  int rc = d.GN == 32 ? launch_bwd1<64, 32>(d, dout, S.act, S.S, w, F, W.dact, W.dS, st)
-                      : launch_bwd1<64, 128>(d, dout, S.act, S.S, w, F, W.dact, W.dS, st);
+  int rc = d.GN == 32 ? launch_bwd1<64, 32>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st)
+                      : launch_bwd1<64, 128>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st);
   if (rc) return rc;
-  { ADN_KERNEL("k_bwd1_post", st); k_bwd1_post<<<2 * d.Di, 32, 0, st>>>(F.Rt, F.sdout, w.out_proj_w, w.norm_w, w.norm_b, w.alpha1, W.acc.dWout, W.acc.dgamma, W.acc.dbeta, W.acc.dalpha1, d.D, d.Di); }
   // ---- phase B2: dS' -> dxc, dBc, ddt
   rc = d.GN == 32 ? launch_bwd2<64, 32>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st)
                   : launch_bwd2<64, 128>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st);
@@ -1631,14 +1654,18 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
     rc = set_smem(k_conv_bwd_tile, smem);
     if (rc) return rc;
     dim3 grid(cdiv(d.W, CT_X), cdiv(d.H, CB_Y), d.B * slabs);
-    { ADN_KERNEL("k_conv_bwd_tile", st); k_conv_bwd_tile<<<grid, 256, smem, st>>>(W.dact, S.pre, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.H, d.W, d.CC, slabs); }
+    { ADN_KERNEL("k_conv_bwd_tile", st); k_conv_bwd_tile<<<grid, 256, smem, st>>>(W.dact, S.pre, S.raw, d.ldr, P.Kc, W.draw, W.acc.dK, d.H, d.W, d.CC, slabs); }
   }
   // ---- in_proj backward
-  rc = d.dip <= 128 ? launch_bwd4<32, 1, 2>(d, W.draw, u, F, du, &W.acc, st)
-       : d.dip <= 256 ? launch_bwd4<32, 2, 2>(d, W.draw, u, F, du, &W.acc, st)
-                      : launch_bwd4<32, 4, 1>(d, W.draw, u, F, du, &W.acc, st);   // wide in_proj: one stage fits
+  rc = d.dip <= 128 ? launch_bwd4<32, 1, 2>(d, W.draw, u, P, F, du, &W.acc, st)
+       : d.dip <= 256 ? launch_bwd4<32, 2, 2>(d, W.draw, u, P, F, du, &W.acc, st)
+                      : launch_bwd4<32, 4, 1>(d, W.draw, u, P, F, du, &W.acc, st);   // wide in_proj: one stage fits
   if (rc) return rc;
-  { ADN_KERNEL("k_finalize", st); k_finalize<<<148, 256, 0, st>>>(W.acc, w, g, d.D, d.Di, d.GN, d.nh, d.dip); }
+  {
+    if (g.alpha1) ADN_CHECK_CUDA(cudaMemsetAsync(g.alpha1, 0, sizeof(float), st));
+    const int nb_in = cdiv(d.dip * d.D, 32), nb_rest = 8;
+    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<nb_in + 2 * d.Di + nb_rest, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest); }
+  }
   ADN_CHECK_LAUNCH();
   return ADN_OK;
 }
