@@ -142,3 +142,41 @@ def test_errors_are_loud():
         A.adnssd_mixer(torch.zeros(1, 16, 32, device="cuda"), 4, 4, pc, headdim=4, d_state=16, ngroups=4)
     with pytest.raises(RuntimeError, match="dtype"):
         A.adnssd_mixer(torch.zeros(1, 16, 32, device="cuda", dtype=torch.float16), 4, 4, pc, headdim=4, d_state=16)
+
+
+def _rand_params(D, P, N, dev):
+    return {k: v.to(dev).requires_grad_(k not in AO.UNUSED_PARAMS) for k, v in AO.init_params(D, P, N, seed=21, perturb=0.05).items()}
+
+
+@pytest.mark.parametrize("B,g", [(16, 128), (2, 256)], ids=["bench_shape_B16_128x128", "refiner_256x256"])
+def test_full_size_fast_path_agrees_with_check_mode(B, g):
+    """BASELINE full sizes (configs[1] and the 256x256 refiner grid): the bf16 tcgen05 path against the fp32 check-mode
+    path of the same library on the same inputs (the oracle itself would take minutes at this size), plus batch
+    independence (a size-independent property of the path: every op is per-sample)."""
+    import adnm_unet_b200 as A
+    dev = torch.device("cuda:0")
+    D, P, N = 32, 4, 16
+    gen = torch.Generator().manual_seed(5)
+    u = torch.randn(B, g * g, D, generator=gen)
+    dout = torch.randn(B, g * g, D, generator=gen)
+    res = {}
+    for dtype in (torch.float32, torch.bfloat16):
+        p = _rand_params(D, P, N, dev)
+        ud = u.to(dev, dtype).requires_grad_(True)
+        out = A.adnssd_mixer(ud, g, g, p, headdim=P, d_state=N)
+        out.backward(dout.to(dev, dtype))
+        torch.cuda.synchronize()
+        res[dtype] = (out.detach().float().cpu(), ud.grad.float().cpu(), {k: v.grad.float().cpu() for k, v in p.items() if v.grad is not None})
+        del out, ud, p
+        torch.cuda.empty_cache()
+    ref, fast = res[torch.float32], res[torch.bfloat16]
+    errs = {"out": rel(fast[0], ref[0]), "du": rel(fast[1], ref[1])}
+    for k in ref[2]:
+        errs[k] = rel(fast[2][k], ref[2][k])
+    bad = {k: v for k, v in errs.items() if not v < 2e-2}
+    assert not bad, f"{bad} (all: {errs})"
+    # batch independence: sample 1 alone gives the same rows as inside the batch
+    p = _rand_params(D, P, N, dev)
+    with torch.no_grad():
+        alone = A.adnssd_mixer(u[1:2].to(dev, torch.bfloat16), g, g, p, headdim=P, d_state=N).float().cpu()
+    assert rel(alone[0], fast[0][1]) < 5e-3
