@@ -91,6 +91,63 @@ k_umma_selftest(int mode, int N, int K, const bf16* __restrict__ A, const bf16* 
   if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
+// Shifted / padded operand self-test (tests/test_umma_gpu.py::test_umma_shift): the fused conv kernels address a
+// zero-padded row buffer [chunk][pitch][8] through descriptors whose start address is moved by whole rows (16 bytes) and
+// whose chunk stride is pitch*16 rather than a multiple of 128 bytes.
+//   mode 0: A[pitch][K], B[pitch][K] row-major, K-major operands:  C = A[shiftA : shiftA+128] . B[shiftB : shiftB+N]^T
+//   mode 1: A[pitch][128], B[pitch][N] row-major, MN-major operands: C[m][n] = sum_{k<K} A[shiftA+k][m] * B[shiftB+k][n]
+__global__ void __launch_bounds__(128)
+k_umma_shift_selftest(int mode, int N, int K, int pitch, int shiftA, int shiftB, const bf16* __restrict__ A,
+                      const bf16* __restrict__ Bm, float* __restrict__ C, int* __restrict__ status) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int colsA = mode == 0 ? K : 128, colsB = mode == 0 ? K : N;
+  bf16* sA = reinterpret_cast<bf16*>(smem);
+  bf16* sB = sA + pitch * colsA;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < pitch * colsA; i += 128) { int r = i / colsA, c = i % colsA; sA[t8_off(r, c, pitch)] = A[i]; }
+  for (int i = tid; i < pitch * colsB; i += 128) { int r = i / colsB, c = i % colsB; sB[t8_off(r, c, pitch)] = Bm[i]; }
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_rt(128, N, mode == 1, mode == 1);
+    const uint32_t a0 = smem_u32(sA) + shiftA * 16, b0 = smem_u32(sB) + shiftB * 16;
+    for (int k = 0; k < K; k += 16) {
+      uint64_t da, db;
+      if (mode == 0) {
+        da = make_desc(a0 + (k >> 3) * pitch * 16, pitch * 16, 128);
+        db = make_desc(b0 + (k >> 3) * pitch * 16, pitch * 16, 128);
+      } else {
+        da = make_desc(a0 + k * 16, 128, pitch * 16);
+        db = make_desc(b0 + k * 16, 128, pitch * 16);
+      }
+      umma(tbase, da, db, idesc, k > 0);
+    }
+    umma_commit(&bar);
+  }
+  bool ok = mbar_wait(&bar, 0);
+  tc_fence_after();
+  if (!ok) { if (tid == 0) *status = 1; }
+  else {
+    for (int c = 0; c < N; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_addr(tbase, warp * 32, c), v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) C[(long long)tid * N + c + j] = v[j];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 256);
+}
+
 // ------------------------------------------------------------------------------------------------
 // cp.async helpers (16-byte, L2-only caching; src_bytes = 0 zero-fills)
 // ------------------------------------------------------------------------------------------------
@@ -1697,6 +1754,26 @@ extern "C" int adn_selftest_umma(int mode, int N, int K, const void* A, const vo
   cudaStream_t st = (cudaStream_t)stream;
   ADN_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
   { ADN_KERNEL("k_umma_selftest", st); k_umma_selftest<<<1, 128, smem, st>>>(mode, N, K, (const bf16*)A, (const bf16*)B, C, status); }
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
+extern "C" int adn_selftest_umma_shift(int mode, int N, int K, int pitch, int shiftA, int shiftB, const void* A, const void* B,
+                                       float* C, int* status, void* stream) {
+  using namespace adn;
+  ADN_REQUIRE(A && B && C && status, ADN_ERR_NULL, "adn_selftest_umma_shift: NULL argument");
+  ADN_REQUIRE((mode == 0 || mode == 1) && N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256 &&
+                  shiftA >= 0 && shiftB >= 0 && pitch <= 512,
+              ADN_ERR_SHAPE, "adn_selftest_umma_shift: bad shape");
+  ADN_REQUIRE(mode == 0 ? (shiftA + 128 <= pitch && shiftB + N <= pitch) : (shiftA + K <= pitch && shiftB + K <= pitch),
+              ADN_ERR_SHAPE, "adn_selftest_umma_shift: shift + extent exceeds pitch");
+  const int colsA = mode == 0 ? K : 128, colsB = mode == 0 ? K : N;
+  size_t smem = (size_t)pitch * (colsA + colsB) * sizeof(bf16);
+  ADN_REQUIRE(smem <= 200 * 1024, ADN_ERR_SHAPE, "adn_selftest_umma_shift: tile too large");
+  ADN_CHECK_CUDA(cudaFuncSetAttribute(k_umma_shift_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaStream_t st = (cudaStream_t)stream;
+  ADN_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+  { ADN_KERNEL("k_umma_shift_selftest", st); k_umma_shift_selftest<<<1, 128, smem, st>>>(mode, N, K, pitch, shiftA, shiftB, (const bf16*)A, (const bf16*)B, C, status); }
   ADN_CHECK_LAUNCH();
   return ADN_OK;
 }

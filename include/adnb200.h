@@ -171,6 +171,12 @@ int adn_phase_read(unsigned long long* out64);
  * and TMEM).  mode 0: A[128][K], B[N][K] (K-major operands); mode 1: A[K][128], B[K][N] (MN-major operands).
  * C is float[128][N]; *status (device int) is set to 1 if the MMA completion barrier timed out. */
 int adn_selftest_umma(int mode, int N, int K, const void* A, const void* B, float* C, int* status, void* stream);
+/* Same, with the operands staged in a row-padded buffer ([chunk][pitch rows][8]) and addressed through descriptors whose
+ * start address is shifted by whole rows (the addressing the fused conv-as-GEMM kernels rely on).
+ * mode 0: A[pitch][K], B[pitch][K]:  C = A[shiftA:shiftA+128] . B[shiftB:shiftB+N]^T
+ * mode 1: A[pitch][128], B[pitch][N]: C[m][n] = sum_{k<K} A[shiftA+k][m] * B[shiftB+k][n] */
+int adn_selftest_umma_shift(int mode, int N, int K, int pitch, int shiftA, int shiftB, const void* A, const void* B,
+                            float* C, int* status, void* stream);
 
 #ifdef __cplusplus
 }
