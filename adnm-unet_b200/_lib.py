@@ -65,6 +65,7 @@ EXPORTS = {
     "adn_phase_read": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "adn_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "adn_selftest_umma_shift": (C.c_int, [C.c_int] * 6 + [C.c_void_p] * 5),
+    "adn_bench_umma": (C.c_int, [C.c_int] * 6 + [C.c_void_p] * 2),
 }
 
 

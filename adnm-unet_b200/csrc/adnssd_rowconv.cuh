@@ -1,0 +1,667 @@
+// Conv-as-GEMM kernels of the sm_100a ADN-SSD path ("row" kernels; token grids with W == 128, d_model 32, d_state 16).
+//
+// The depthwise 3x3 convolution that follows in_proj (models/ADNssd.py:329-372,388-390) is linear in u:
+//     pre[p][c] = sum_t K[c][t] * raw[p + d_t][c] = sum_t  u[p + d_t][:] . Wt[t][c][:],    Wt[t][c][d] = K[c][t] * W_in[c][d]
+// so in_proj + conv is ONE K = 9*32 GEMM per 128-token image row whose A operand is the u row shifted by the tap offset
+// d_t = (a-1, b-1), t = 3a+b.  The shift costs nothing on tcgen05: the rows of a T8 operand are 16 bytes apart, so a row
+// shift is a change of the descriptor start address (tests/test_umma_gpu.py::test_umma_shift).  Image rows live in
+// zero-padded "row slots"  [chunk][130 positions][8]  (position 1 + x holds token x; positions 0 and 129 are the zero
+// padding of the conv), and a vertical tap selects the slot of the neighbouring image row.  The same identity gives
+// the whole backward of in_proj + conv from dpre = dact * SiLU'(pre) with no CUDA-core convolution at all:
+//     du[q]      = sum_t dpre[q - d_t][:] . Wt[t]                                       (k_bconv_du)
+//     M_t[c][d]  = sum_p dpre[p][c] * u[p + d_t][d]                                     (k_bconv_wg, accumulated in TMEM)
+//     dK[c][t]   = sum_d W_in[c][d] * M_t[c][d],      dW_in[c][d] = sum_t K[c][t] * M_t[c][d]
+// raw (the in_proj output) is never materialised; only its dt columns are stored (the decay weights need them).
+//
+// All three kernels are warp-specialised: a producer warp (cp.async / cp.async.bulk into a ring, mbarrier completion),
+// one MMA-issuing thread, and epilogue warps that own TMEM lane quarters (thread = token row).
+#pragma once
+
+namespace rowconv {
+using namespace adn;
+using namespace adn::sm100;
+
+constexpr int RP = 130;                  // positions per chunk of a padded row slot
+constexpr int D = 32, DI = 64, GN = 32, CC = 192, NA = 24, DIP = 208, NH = 16;
+constexpr int CHB = RP * 16;             // bytes of one padded chunk (2080)
+constexpr int USLOT_B = 4 * CHB;         // padded u row slot: 32 channels (8320 bytes)
+constexpr int NUS = 4;                   // u ring slots
+constexpr int WTF_TAP_B = 4 * DIP * 16;  // forward B operand of one tap: [4 chunks][208][8] bf16 (13312 bytes)
+constexpr int WTF_B = 9 * WTF_TAP_B;
+constexpr int WTB_TG_B = 2048;           // backward B operand of one (tap, 32-channel group): [4 chunks][32][8] bf16
+constexpr int WTB_B = 9 * 6 * WTB_TG_B + 1024;   // + W_dt^T image [2 chunks][32][8]
+
+// true in exactly one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// tcgen05.mma with a compile-time accumulate flag (the issue loops of the row kernels are fully unrolled: one thread
+// issues every MMA of the CTA, so every instruction in its loop counts)
+template <bool ACC>
+__device__ __forceinline__ void umma_c(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC ? 1 : 0)
+      : "memory");
+}
+// descriptor + byte offset (the start-address field counts 16-byte units and never carries out of its 14 bits here)
+__device__ __forceinline__ uint64_t dadd(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
+// One tap of the assembled per-channel 3x3 kernel (same rules as assemble_conv_channel).
+__device__ __forceinline__ float conv_tap(const ConvWeightPtrs& w, int Di, int cc, int t) {
+  if (cc < Di) return w.c2dz[cc * 9 + t];
+  const int c = cc - Di;
+  if ((c & 1) == 0) return w.c2d[(c >> 1) * 9 + t];
+  const int i = c >> 2, nx = Di >> 2;
+  const bool first = (c & 3) == 1;
+  const float *w31, *w13;
+  if (i < nx) {
+    w31 = (first ? w.c31x1 : w.c31x2) + i * 3;
+    w13 = (first ? w.c13x1 : w.c13x2) + i * 3;
+  } else {
+    w31 = (first ? w.c31bc1 : w.c31bc2) + (i - nx) * 3;
+    w13 = (first ? w.c13bc1 : w.c13bc2) + (i - nx) * 3;
+  }
+  return w31[t / 3] * w13[t % 3];
+}
+
+// Weight images of the conv-as-GEMM kernels (one thread per element, called from k_prep):
+//   WtF[t] : K-major B operand [N = 208][K = 32] of the forward GEMM; rows >= 192 (dt) are W_in for the centre tap, else 0
+//   WtB[t][g] : K-major B operand [N = 32 (d)][K = 32 channels of group g] of the du GEMM, then W_dt^T [N = 32][K = 16]
+__device__ __forceinline__ void prep_rowconv(const ConvWeightPtrs& cw, const float* __restrict__ win, bf16* __restrict__ wtf,
+                                             bf16* __restrict__ wtb, int i) {
+  if (i < 9 * DIP * D) {
+    const int t = i / (DIP * D), rem = i % (DIP * D);
+    const int dchunk = rem / (DIP * 8), n = (rem >> 3) % DIP, d = dchunk * 8 + (rem & 7);
+    float v;
+    if (n < CC) v = conv_tap(cw, DI, n, t) * win[n * D + d];
+    else v = t == 4 ? win[n * D + d] : 0.f;
+    wtf[i] = __float2bfloat16_rn(v);
+  }
+  if (i < 9 * 6 * 1024) {
+    const int tg = i >> 10, rem = i & 1023, t = tg / 6, g = tg % 6;
+    const int c = g * 32 + (rem >> 8) * 8 + (rem & 7), d = (rem >> 3) & 31;
+    wtb[i] = __float2bfloat16_rn(conv_tap(cw, DI, c, t) * win[c * D + d]);
+  } else if (i < 9 * 6 * 1024 + 512) {
+    const int e = i - 9 * 6 * 1024, j = (e >> 8) * 8 + (e & 7), d = (e >> 3) & 31;
+    wtb[i] = __float2bfloat16_rn(win[(CC + j) * D + d]);
+  }
+}
+
+// One warp: copy one row-major u row (128 tokens x 32 channels, 8 KB contiguous) into positions 1..128 of a padded slot.
+__device__ __forceinline__ void urow_load(uint8_t* slot, const bf16* __restrict__ urow, int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int piece = i * 32 + lane, tok = piece >> 2, ch = piece & 3;
+    cp_async16(slot + ch * CHB + (1 + tok) * 16, urow + piece * 8, 16);
+  }
+}
+
+// Producer warp of the u ring: rows [gfirst, glast] -> slot (g - gfirst) % NUS; full[] has count 32, empty[] count 1.
+__device__ __forceinline__ void urow_producer(uint8_t* sU, const bf16* __restrict__ u, int gfirst, int glast, uint64_t* full,
+                                              uint64_t* empty, int lane) {
+  const int n = glast - gfirst + 1;
+  for (int i = 0; i <= n; ++i) {
+    if (i < n) {
+      if (i >= NUS) mbar_wait(&empty[i % NUS], ((i / NUS) - 1) & 1);
+      urow_load(sU + (i % NUS) * USLOT_B, u + (long long)(gfirst + i) * 128 * D, lane);
+    }
+    cp_async_commit();
+    if (i >= 1) {
+      cp_async_wait<1>();
+      fence_async_smem();
+      mbar_arrive(&full[(i - 1) % NUS]);
+    }
+  }
+}
+
+// SiLU and SiLU' of 32 accumulator columns of this thread's token row (two TMEM loads in flight, packed fp32x2 math);
+// stores four chunks of act (and of sgrad) in the TL layout.  MODE 0: nothing else; 1: also copy the bf16 act chunks to
+// shared memory (Bc operand of the state MMA); 2: write w * act (decay-weighted x; w8 = the eight head weights of these
+// four chunks) to shared memory.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+template <int MODE>
+__device__ __forceinline__ void silu32(uint32_t taddr, bf16* a_dst, bf16* g_dst, uint8_t* s_dst, const float* w8) {
+  float v[2][16];
+  tmem_ld16(taddr, v[0]);
+  tmem_ld16(taddr + 16, v[1]);
+  tmem_wait_ld();
+#pragma unroll
+  for (int hh = 0; hh < 4; ++hh) {
+    float2 a[4], gq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = make_float2(v[hh >> 1][(hh & 1) * 8 + 2 * j], v[hh >> 1][(hh & 1) * 8 + 2 * j + 1]);
+      const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+      const float2 d = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.f, 1.f));
+      const float2 sg = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+      a[j] = __fmul2_rn(x, sg);
+      const float2 om = __ffma2_rn(sg, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+      gq[j] = __ffma2_rn(a[j], om, sg);
+    }
+    const uint4 pa = pack8_f2(a);
+    *reinterpret_cast<uint4*>(a_dst + hh * 1024) = pa;
+    if (g_dst) *reinterpret_cast<uint4*>(g_dst + hh * 1024) = pack8_f2(gq);
+    if (MODE == 1) *reinterpret_cast<uint4*>(s_dst + hh * 2048) = pa;
+    if (MODE == 2) {
+      float2 r[4];
+      unpack8_f2(pa, r);
+      const float2 w2 = make_float2(w8[hh * 2], w8[hh * 2 + 1]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = __fmul2_rn(r[j], w2);
+      *reinterpret_cast<uint4*>(s_dst + hh * 2048) = pack8_f2(r);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fconv: forward in_proj + depthwise 3x3 + SiLU (+ SiLU') + decay weights + state accumulation, one image row
+// (128 tokens) per step.  Stages (1)-(4a) of the mixer (models/ADNssd.py:309-390, :267-280).
+//   warps 0-7  epilogue (lane quarter q = warp & 3, column half = warp >> 2)
+//   warp  8    u-row producer (cp.async into the padded ring)
+//   warp  9    lane 0 issues every tcgen05.mma
+// TMEM: two 208-column accumulators [z | x | B | C | dt] + 32 columns of the per-sample state S'[c][j].
+// ------------------------------------------------------------------------------------------------
+constexpr int FC_ST_B = 12 * 2048;   // state operands of one row: wx chunks 0..7, Bc chunks 8..11
+constexpr int FC_SMEM = 2 * FC_ST_B + NUS * USLOT_B + WTF_B;
+constexpr int FC_COL_S = 2 * DIP;
+
+__global__ void __launch_bounds__(320, 1)
+k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* __restrict__ dt_bias,
+        const float* __restrict__ A_log, bf16* __restrict__ act, bf16* __restrict__ sgrad, bf16* __restrict__ dtraw,
+        float* __restrict__ S, int H, int rows_total, int rows_per_cta, int* __restrict__ status) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full[NUS], empty[NUS], acc_full[2], acc_empty[2], st_full[2], st_empty[2], s_done, s_free;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[NH], s_eA[NH];
+  uint8_t* sSt = smem;
+  uint8_t* sU = smem + 2 * FC_ST_B;
+  uint8_t* sW = sU + NUS * USLOT_B;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R0 = blockIdx.x * rows_per_cta, R1 = min(rows_total, R0 + rows_per_cta);
+  for (int i = tid; i < (2 * FC_ST_B + NUS * USLOT_B) / 16; i += 320) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < WTF_B / 16; i += 320) reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(WtF) + i);
+  if (tid < NH) { s_bias[tid] = dt_bias[tid]; s_eA[tid] = __expf(A_log[tid]); }
+  if (tid == 0) {
+    for (int i = 0; i < NUS; ++i) { mbar_init(&full[i], 32); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); mbar_init(&st_full[i], 8); mbar_init(&st_empty[i], 1); }
+    mbar_init(&s_done, 1);
+    mbar_init(&s_free, 8);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(&tmem_slot, 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  const int gfirst = max(R0 - 1, 0), glast = min(R1, rows_total - 1);
+  bool ok = true;
+  if (R0 < R1) {
+    if (warp == 8) {
+      urow_producer(sU, u, gfirst, glast, full, empty, lane);
+    } else if (warp == 9) {
+      if (elect_one()) {   // one elected lane of the converged warp: tcgen05.mma is emitted without a lane-serialising loop
+        const uint32_t idesc = make_idesc_rt(128, DIP, false, false), idesc_s = make_idesc_rt(128, GN, true, true);
+        const uint32_t ubase = smem_u32(sU), wbase = smem_u32(sW), stbase = smem_u32(sSt);
+        const uint64_t dU0 = make_desc(ubase, CHB, 128), dW0 = make_desc(wbase, DIP * 16, 128);
+        int next_wait = gfirst, fl = 0;
+        for (int R = R0; R <= R1; ++R) {
+          if (R < R1) {
+            const int it = R - R0, acc = it & 1, y = R % H;
+            const int need = min(R + 1, glast);
+            while (next_wait <= need) {
+              const int i = next_wait - gfirst;
+              ok = mbar_wait(&full[i % NUS], (i / NUS) & 1) && ok;
+              ++next_wait;
+            }
+            if (it >= 2) ok = mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1) && ok;
+            tc_fence_after();
+            const uint32_t tacc = tbase + acc * DIP;
+            if (y > 0 && y < H - 1) {      // interior row: all nine taps, fully unrolled, descriptors = base + constant
+              uint64_t dA[3];
+#pragma unroll
+              for (int a = 0; a < 3; ++a) dA[a] = dadd(dU0, (uint32_t)(((R + a - 1) - gfirst) % NUS) * USLOT_B);
+#pragma unroll
+              for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+#pragma unroll
+                  for (int ks = 0; ks < 2; ++ks) {
+                    const uint64_t da = dadd(dA[a], b * 16 + ks * 2 * CHB);
+                    const uint64_t db = dadd(dW0, (a * 3 + b) * WTF_TAP_B + ks * 2 * DIP * 16);
+                    if (a == 0 && b == 0 && ks == 0) umma_c<false>(tacc, da, db, idesc);
+                    else umma_c<true>(tacc, da, db, idesc);
+                  }
+            } else {
+              bool first = true;
+              for (int a = 0; a < 3; ++a) {
+                if (y + a - 1 < 0 || y + a - 1 >= H) continue;
+                const uint32_t ab = ubase + (uint32_t)(((R + a - 1) - gfirst) % NUS) * USLOT_B;
+                for (int b = 0; b < 3; ++b) {
+#pragma unroll
+                  for (int ks = 0; ks < 2; ++ks) {
+                    const uint64_t da = make_desc(ab + b * 16 + ks * 2 * CHB, CHB, 128);
+                    const uint64_t db = make_desc(wbase + (a * 3 + b) * WTF_TAP_B + ks * 2 * DIP * 16, DIP * 16, 128);
+                    umma(tacc, da, db, idesc, !first);
+                    first = false;
+                  }
+                }
+              }
+            }
+            umma_commit(&acc_full[acc]);
+            if (R - 1 >= gfirst) umma_commit(&empty[((R - 1) - gfirst) % NUS]);
+          }
+          if (R > R0) {   // state accumulation of the previous row (its epilogue produced w*x and Bc)
+            const int Rp = R - 1, it = Rp - R0, sb = it & 1, yp = Rp % H;
+            ok = mbar_wait(&st_full[sb], (it >> 1) & 1) && ok;
+            tc_fence_after();
+            const bool first_of_sample = (Rp == R0) || (yp == 0);
+            if (first_of_sample && fl > 0) { ok = mbar_wait(&s_free, (fl - 1) & 1) && ok; tc_fence_after(); }
+            const uint32_t a0 = stbase + sb * FC_ST_B, b0 = a0 + 8 * 2048;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma(tbase + FC_COL_S, make_desc(a0 + k * 256, 128, 2048), make_desc(b0 + k * 256, 128, 2048), idesc_s,
+                   !(first_of_sample && k == 0));
+            umma_commit(&st_empty[sb]);
+            if ((Rp == R1 - 1) || (yp == H - 1)) { umma_commit(&s_done); ++fl; }
+          }
+        }
+        if (!ok) atomicExch(status, 20);
+      }
+    } else {
+      const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+      int fl = 0;
+      for (int R = R0; R < R1; ++R) {
+        const int it = R - R0, acc = it & 1, y = R % H, b = R / H;
+        ok = mbar_wait(&acc_full[acc], (it >> 1) & 1) && ok;
+        if (it >= 2) ok = mbar_wait(&st_empty[acc], ((it >> 1) - 1) & 1) && ok;
+        tc_fence_after();
+        const uint32_t ta = tbase + ((uint32_t)(q * 32) << 16) + acc * DIP;
+        bf16* arow = act + ((long long)R * NA * 128 + row) * 8;
+        bf16* grow = sgrad ? sgrad + ((long long)R * NA * 128 + row) * 8 : nullptr;
+        uint8_t* st = sSt + acc * FC_ST_B + row * 16;
+        if (half == 0) {
+#pragma unroll 1
+          for (int cb = 0; cb < DI; cb += 32)
+            silu32<0>(ta + cb, arow + (cb >> 3) * 1024, grow ? grow + (cb >> 3) * 1024 : nullptr, nullptr, nullptr);
+          silu32<1>(ta + 2 * DI, arow + ((2 * DI) >> 3) * 1024, grow ? grow + ((2 * DI) >> 3) * 1024 : nullptr, st + 8 * 2048, nullptr);
+        } else {
+          float w[NH];
+          {
+            float v[16];
+            tmem_ld16(ta + CC, v);
+            tmem_wait_ld();
+            float lo[8], hi[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+            const uint4 p0 = pack8(lo), p1 = pack8(hi);
+            bf16* drow = dtraw + ((long long)R * 2 * 128 + row) * 8;
+            *reinterpret_cast<uint4*>(drow) = p0;
+            *reinterpret_cast<uint4*>(drow + 1024) = p1;
+            unpack8(p0, lo);     // the decay weights are formed from the stored (bf16) dt so that backward sees the same w
+            unpack8(p1, hi);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              w[j] = softplus_fast(lo[j] + s_bias[j]) * s_eA[j];
+              w[8 + j] = softplus_fast(hi[j] + s_bias[8 + j]) * s_eA[8 + j];
+            }
+          }
+          silu32<2>(ta + DI, arow + (DI >> 3) * 1024, grow ? grow + (DI >> 3) * 1024 : nullptr, st, &w[0]);
+          silu32<2>(ta + DI + 32, arow + ((DI + 32) >> 3) * 1024, grow ? grow + ((DI + 32) >> 3) * 1024 : nullptr, st + 4 * 2048, &w[8]);
+          silu32<0>(ta + 2 * DI + GN, arow + ((2 * DI + GN) >> 3) * 1024, grow ? grow + ((2 * DI + GN) >> 3) * 1024 : nullptr,
+                    nullptr, nullptr);
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&acc_empty[acc]); mbar_arrive(&st_full[acc]); }
+        if ((R == R1 - 1) || (y == H - 1)) {   // flush the state of sample b accumulated by this CTA
+          ok = mbar_wait(&s_done, fl & 1) && ok;
+          ++fl;
+          tc_fence_after();
+          if (q < 2 && ok) {
+            float v[16];
+            tmem_ld16(tbase + ((uint32_t)(q * 32) << 16) + FC_COL_S + half * 16, v);
+            tmem_wait_ld();
+            const int c = q * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int jj = half * 16 + j;
+              if (((jj ^ c) & 1) == 0) atomicAdd(S + ((long long)b * GN + jj) * DI + c, v[j]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free);
+        }
+      }
+      if (!ok && lane == 0) atomicExch(status, 21);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tbase, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_bconv_du: du[q] = sum_t dpre[q - d_t] . Wt[t] + ddt[q] . W_dt     (backward-data of in_proj o conv, one image row per
+// accumulator).  Work unit = (row, 32-channel group): the three dpre rows y-1, y, y+1 of the group are bulk-copied into a
+// padded stage (12 copies of 2 KB), then 9 taps x 2 K-steps of 128x32x16 MMAs accumulate into the row's 32 TMEM columns.
+//   warps 0-3 epilogue (du row-major store), warp 4 lane 0 bulk-copy producer, warp 5 lane 0 MMA issue.
+// ------------------------------------------------------------------------------------------------
+constexpr int DU_NST = 3;
+constexpr int DU_STG_B = 3 * USLOT_B + 4096;      // 3 padded row slots of one group + the ddt tile [2 chunks][128][8]
+constexpr int DU_SMEM = DU_NST * DU_STG_B + WTB_B;
+
+__global__ void __launch_bounds__(192, 1)
+k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf16* __restrict__ WtB, bf16* __restrict__ du,
+           int H, int rows_total, int rows_per_cta, int* __restrict__ status) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full[DU_NST], empty[DU_NST], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  uint8_t* sStg = smem;
+  uint8_t* sW = smem + DU_NST * DU_STG_B;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R0 = blockIdx.x * rows_per_cta, R1 = min(rows_total, R0 + rows_per_cta);
+  for (int i = tid; i < DU_NST * DU_STG_B / 16; i += 192) reinterpret_cast<uint4*>(sStg)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < WTB_B / 16; i += 192) reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(WtB) + i);
+  if (tid == 0) {
+    for (int i = 0; i < DU_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(&tmem_slot, 64);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  bool ok = true;
+  if (warp == 4) {
+    if (elect_one()) {
+      int un = 0;
+      for (int R = R0; R < R1; ++R) {
+        const int y = R % H;
+        for (int g = 0; g < 6; ++g, ++un) {
+          const int stg = un % DU_NST;
+          if (un >= DU_NST) ok = mbar_wait(&empty[stg], ((un / DU_NST) - 1) & 1) && ok;
+          uint8_t* sb = sStg + stg * DU_STG_B;
+          const int nrows = 1 + (y > 0 ? 1 : 0) + (y < H - 1 ? 1 : 0);
+          mbar_expect_tx(&full[stg], (uint32_t)nrows * 4 * 2048 + (g == 0 ? 4096u : 0u));
+          for (int e = -1; e <= 1; ++e) {
+            if (y + e < 0 || y + e >= H) continue;
+            const bf16* src = dpre + ((long long)(R + e) * NA + g * 4) * 1024;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) bulk_g2s(sb + (e + 1) * USLOT_B + ch * CHB + 16, src + ch * 1024, 2048, &full[stg]);
+          }
+          if (g == 0) bulk_g2s(sb + 3 * USLOT_B, ddt + (long long)R * 2 * 1024, 4096, &full[stg]);
+        }
+      }
+      if (!ok) atomicExch(status, 22);
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_rt(128, D, false, false);
+      const uint32_t sbase = smem_u32(sStg), wbase = smem_u32(sW);
+      const uint64_t dS0 = make_desc(sbase, CHB, 128), dW0 = make_desc(wbase, 512, 128);
+      int un = 0;
+      for (int R = R0; R < R1; ++R) {
+        const int it = R - R0, acc = it & 1, y = R % H;
+        bool first = true;
+        for (int g = 0; g < 6; ++g, ++un) {
+          const int stg = un % DU_NST;
+          ok = mbar_wait(&full[stg], (un / DU_NST) & 1) && ok;
+          if (g == 0 && it >= 2) ok = mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1) && ok;
+          tc_fence_after();
+          const uint32_t sb = sbase + stg * DU_STG_B;
+          if (y > 0 && y < H - 1) {        // interior row: fully unrolled, descriptors = base + constant
+            const uint64_t dA = dadd(dS0, stg * DU_STG_B), dB = dadd(dW0, g * WTB_TG_B);
+            const uint32_t tacc = tbase + acc * D;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+              for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint64_t da = dadd(dA, (2 - a) * USLOT_B + (2 - b) * 16 + ks * 2 * CHB);
+                  const uint64_t db = dadd(dB, (a * 3 + b) * 6 * WTB_TG_B + ks * 2 * 512);
+                  if (a == 0 && b == 0 && ks == 0) umma(tacc, da, db, idesc, g != 0);
+                  else umma_c<true>(tacc, da, db, idesc);
+                }
+            first = false;
+          } else {
+            for (int a = 0; a < 3; ++a) {
+              const int e = 1 - a;          // source image row y + e
+              if (y + e < 0 || y + e >= H) continue;
+              for (int b = 0; b < 3; ++b) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint64_t da = make_desc(sb + (e + 1) * USLOT_B + (2 - b) * 16 + ks * 2 * CHB, CHB, 128);
+                  const uint64_t db = make_desc(wbase + ((a * 3 + b) * 6 + g) * WTB_TG_B + ks * 2 * 512, 512, 128);
+                  umma(tbase + acc * D, da, db, idesc, !first);
+                  first = false;
+                }
+              }
+            }
+          }
+          if (g == 0)
+            umma(tbase + acc * D, make_desc(sb + 3 * USLOT_B, 2048, 128), make_desc(wbase + 9 * 6 * WTB_TG_B, 512, 128), idesc, true);
+          umma_commit(&empty[stg]);
+        }
+        umma_commit(&acc_full[acc]);
+      }
+      if (!ok) atomicExch(status, 23);
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    for (int R = R0; R < R1; ++R) {
+      const int it = R - R0, acc = it & 1;
+      ok = mbar_wait(&acc_full[acc], (it >> 1) & 1) && ok;
+      tc_fence_after();
+      float v0[16], v1[16];
+      tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + acc * D, v0);
+      tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + acc * D + 16, v1);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (ok) {
+        float o[8];
+        bf16* dst = du + ((long long)R * 128 + row) * D;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = v0[j];
+        *reinterpret_cast<uint4*>(dst) = pack8(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = v0[8 + j];
+        *reinterpret_cast<uint4*>(dst + 8) = pack8(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = v1[j];
+        *reinterpret_cast<uint4*>(dst + 16) = pack8(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = v1[8 + j];
+        *reinterpret_cast<uint4*>(dst + 24) = pack8(o);
+      }
+    }
+    if (!ok && lane == 0) atomicExch(status, 24);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tbase, 64);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_bconv_wg: M_t[c][d] = sum_p dpre[p][c] * u[p + d_t][d] for the 128-channel block mb of this CTA, nine 32-column TMEM
+// accumulators kept for the CTA's whole row range; the epilogue contracts them into dK and dW_in (fp32 atomics, one per
+// output element per CTA).   mb 0: channels 0..127 (z, x).   mb 1: channels 128..191 (B, C) + the 16 dt rows (their
+// centre tap is dW_in[192 + j]) + 48 idle rows.
+//   warps 0-3 epilogue (warp 0 lane 0 is also the dpre-tile producer), warp 4 u-row producer, warp 5 lane 0 MMA issue.
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_NST = 3;
+constexpr int WG_STG_B = 16 * 2048;
+constexpr int WG_SMEM = WG_NST * WG_STG_B + NUS * USLOT_B;
+
+__global__ void __launch_bounds__(192, 1)
+k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf16* __restrict__ u,
+           const float* __restrict__ Win, const float* __restrict__ Kc, float* __restrict__ dK, float* __restrict__ dWin,
+           int H, int rows_total, int rows_per_cta, int ctas_per_block, int* __restrict__ status) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full[NUS], empty[NUS], a_full[WG_NST], a_empty[WG_NST], done;
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t s_tapmask;
+  uint8_t* sA = smem;
+  uint8_t* sU = smem + WG_NST * WG_STG_B;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mb = blockIdx.x / ctas_per_block, part = blockIdx.x % ctas_per_block;
+  const int R0 = part * rows_per_cta, R1 = min(rows_total, R0 + rows_per_cta);
+  for (int i = tid; i < WG_SMEM / 16; i += 192) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    for (int i = 0; i < NUS; ++i) { mbar_init(&full[i], 32); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < WG_NST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    mbar_init(&done, 1);
+    s_tapmask = 0;
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(&tmem_slot, 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  const int gfirst = max(R0 - 1, 0), glast = min(R1, rows_total - 1);
+  bool ok = true;
+  if (R0 < R1) {
+    if (warp == 4) {
+      urow_producer(sU, u, gfirst, glast, full, empty, lane);
+    } else if (warp == 5) {
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc_rt(128, D, true, true);
+        const uint32_t abase = smem_u32(sA), ubase = smem_u32(sU);
+        const uint64_t dA0 = make_desc(abase, 128, 2048), dU0 = make_desc(ubase, 128, CHB);
+        int next_wait = gfirst;
+        uint32_t mask = 0;
+        for (int R = R0; R < R1; ++R) {
+          const int it = R - R0, stg = it % WG_NST, y = R % H;
+          const int need = min(R + 1, glast);
+          while (next_wait <= need) {
+            const int i = next_wait - gfirst;
+            ok = mbar_wait(&full[i % NUS], (i / NUS) & 1) && ok;
+            ++next_wait;
+          }
+          ok = mbar_wait(&a_full[stg], (it / WG_NST) & 1) && ok;
+          tc_fence_after();
+          const uint32_t ab = abase + stg * WG_STG_B;
+          if (mask == 0x1FFu && y > 0 && y < H - 1) {   // steady state: every tap accumulates, fully unrolled
+            const uint64_t dA = dadd(dA0, stg * WG_STG_B);
+            uint64_t dB[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) dB[a] = dadd(dU0, (uint32_t)(((R + a - 1) - gfirst) % NUS) * USLOT_B);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+              for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  umma_c<true>(tbase + (a * 3 + b) * D, dadd(dA, k * 256), dadd(dB[a], b * 16 + k * 256), idesc);
+          } else
+          for (int a = 0; a < 3; ++a) {
+            if (y + a - 1 < 0 || y + a - 1 >= H) continue;
+            const uint32_t ub = ubase + (uint32_t)(((R + a - 1) - gfirst) % NUS) * USLOT_B;
+            for (int b = 0; b < 3; ++b) {
+              const int t = a * 3 + b;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                umma(tbase + t * D, make_desc(ab + k * 256, 128, 2048), make_desc(ub + b * 16 + k * 256, 128, CHB), idesc,
+                     ((mask >> t) & 1) != 0 || k > 0);
+              mask |= 1u << t;
+            }
+          }
+          umma_commit(&a_empty[stg]);
+          if (R - 1 >= gfirst) umma_commit(&empty[((R - 1) - gfirst) % NUS]);
+        }
+        s_tapmask = mask;
+        umma_commit(&done);
+        if (!ok) atomicExch(status, 25);
+      }
+    } else {
+      if (warp == 0 && elect_one()) {   // dpre tile producer
+        for (int R = R0; R < R1; ++R) {
+          const int it = R - R0, stg = it % WG_NST;
+          if (it >= WG_NST) ok = mbar_wait(&a_empty[stg], ((it / WG_NST) - 1) & 1) && ok;
+          uint8_t* sb = sA + stg * WG_STG_B;
+          if (mb == 0) {
+            mbar_expect_tx(&a_full[stg], 16 * 2048);
+            bulk_g2s(sb, dpre + (long long)R * NA * 1024, 16 * 2048, &a_full[stg]);
+          } else {
+            mbar_expect_tx(&a_full[stg], 8 * 2048 + 4096);
+            bulk_g2s(sb, dpre + ((long long)R * NA + 16) * 1024, 8 * 2048, &a_full[stg]);
+            bulk_g2s(sb + 8 * 2048, ddt + (long long)R * 2 * 1024, 4096, &a_full[stg]);
+          }
+        }
+      }
+      __syncwarp();
+      ok = mbar_wait(&done, 0) && ok;
+      tc_fence_after();
+      const uint32_t mask = *reinterpret_cast<volatile uint32_t*>(&s_tapmask);
+      const int m = warp * 32 + lane;
+      const int c = mb * 128 + m;      // conv channel (mb 1: m < 64), or dt row 192 + (m - 64)
+      if (ok && (mb == 0 || m < 64)) {
+        float wrow[D], dw[D];
+#pragma unroll
+        for (int d = 0; d < D; d += 4) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(Win + c * D + d));
+          wrow[d] = t4.x; wrow[d + 1] = t4.y; wrow[d + 2] = t4.z; wrow[d + 3] = t4.w;
+          dw[d] = dw[d + 1] = dw[d + 2] = dw[d + 3] = 0.f;
+        }
+#pragma unroll 1
+        for (int t = 0; t < 9; ++t) {
+          if (!((mask >> t) & 1)) continue;     // warp-uniform
+          float v0[16], v1[16];
+          tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + t * D, v0);
+          tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + t * D + 16, v1);
+          tmem_wait_ld();
+          const float kt = __ldg(Kc + c * 9 + t);
+          float dk = 0.f;
+#pragma unroll
+          for (int d = 0; d < 16; ++d) {
+            dk = fmaf(wrow[d], v0[d], dk);
+            dk = fmaf(wrow[16 + d], v1[d], dk);
+            dw[d] = fmaf(kt, v0[d], dw[d]);
+            dw[16 + d] = fmaf(kt, v1[d], dw[16 + d]);
+          }
+          atomicAdd(dK + c * 9 + t, dk);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) atomicAdd(dWin + c * D + d, dw[d]);
+      } else if (ok && mb == 1 && warp == 2 && ((mask >> 4) & 1)) {   // warp-uniform branch: tcgen05.ld is .sync.aligned
+        float v0[16], v1[16];
+        tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + 4 * D, v0);
+        tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + 4 * D + 16, v1);
+        tmem_wait_ld();
+        if (lane < NH) {
+          float* dst = dWin + (CC + lane) * D;
+#pragma unroll
+          for (int d = 0; d < 16; ++d) { atomicAdd(dst + d, v0[d]); atomicAdd(dst + 16 + d, v1[d]); }
+        }
+      }
+      if (!ok && lane == 0) atomicExch(status, 26);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tbase, 512);
+}
+
+}  // namespace rowconv

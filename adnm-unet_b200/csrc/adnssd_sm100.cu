@@ -7,6 +7,8 @@
 //   k_conv_bwd4     conv backward + dK         same mapping, block-level reduction of the kernel gradient
 #include "adnssd_sm100.cuh"
 
+#include <stdlib.h>
+
 #include "adnssd_generic.cuh"
 #include "sm100_utils.cuh"
 
@@ -142,6 +144,38 @@ k_umma_shift_selftest(int mode, int N, int K, int pitch, int shiftA, int shiftB,
 #pragma unroll
       for (int j = 0; j < 16; ++j) C[(long long)tid * N + c + j] = v[j];
     }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 256);
+}
+
+// tcgen05.mma issue-rate probe (diagnostics): thread 0 issues `iters` back-to-back 128 x N x 16 MMAs on operands staged with
+// row pitch `pitch` and start shift `shift` rows; cycles[0] = SM clocks from first issue to completion.
+__global__ void __launch_bounds__(128)
+k_umma_bench(int mode, int N, int pitch, int shift, int iters, long long* __restrict__ cycles) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 48 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_rt(128, N, mode == 1, mode == 1);
+    const uint32_t a0 = smem_u32(smem) + shift * 16, b0 = smem_u32(smem) + 24 * 1024 + shift * 16;
+    const uint64_t da = mode == 0 ? make_desc(a0, pitch * 16, 128) : make_desc(a0, 128, pitch * 16);
+    const uint64_t db = mode == 0 ? make_desc(b0, pitch * 16, 128) : make_desc(b0, 128, pitch * 16);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) umma(tbase, da, db, idesc, true);
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    cycles[blockIdx.x] = clock64() - t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -297,6 +331,11 @@ __device__ __forceinline__ uint4 pack8_f2(const float2 (&v)[4]) {
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 // softplus with hardware exp2 / log2 (bf16 path only; the fp32 check mode keeps log1pf): abs error ~1e-7
 __device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : __logf(1.f + __expf(x)); }
+
+}  // namespace adn
+#include "adnssd_rowconv.cuh"
+namespace adn {
+using namespace sm100;
 
 // ------------------------------------------------------------------------------------------------
 // k_state: S'[b][j][c] += [j%2==c%2] * sum_l Bc[l,j] * w[l,hd(c)] * xc[l,c]      (models/ADNssd.py:267-280, both parities)
@@ -611,7 +650,9 @@ __global__ void __launch_bounds__(128)
 k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, const float* __restrict__ S,
        const float* __restrict__ Dp, const float* __restrict__ gamma, const float* __restrict__ alpha1p,
        const bf16* __restrict__ Wout, bf16* __restrict__ dact, float* __restrict__ Rt, float* __restrict__ sdout,
-       float* __restrict__ dS, int L, int tiles_per_batch, int num_tiles, int tiles_per_cta, int* __restrict__ status) {
+       float* __restrict__ dS, int L, int tiles_per_batch, int num_tiles, int tiles_per_cta, int* __restrict__ status,
+       const bf16* __restrict__ sgrad) {
+  // sgrad != nullptr (row-kernel path): the z and C column blocks are written as dpre = dact * SiLU'(pre)
   constexpr int D = DI / 2, XC = DI / 8, CCH = GN / 8, DC = D / 8;
   constexpr int COL_Y = 2 * DI, COL_RT = COL_Y + DI, COL_DS = COL_RT + D;
   constexpr uint32_t TCOLS = (COL_DS + GN) <= 256 ? 256 : 512;
@@ -770,6 +811,14 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
 #pragma unroll
       for (int j = 0; j < 8; ++j) { o0[j] = a1 * v[j]; o1[j] = a1 * v[8 + j]; }
       if (tid < rows) {
+        if (sgrad) {
+          const bf16* srow = sgrad + (((long long)tile * NA) * 128 + tid) * 8;
+          float s0[8], s1[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(srow + (long long)(cb / 8) * 1024)), s0);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(srow + (long long)(cb / 8 + 1) * 1024)), s1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { o0[j] *= s0[j]; o1[j] *= s1[j]; }
+        }
         *reinterpret_cast<uint4*>(drow + (long long)(cb / 8) * 1024) = pack8(o0);
         *reinterpret_cast<uint4*>(drow + (long long)(cb / 8 + 1) * 1024) = pack8(o1);
       }
@@ -818,6 +867,14 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
 #pragma unroll
       for (int j = 0; j < 8; ++j) { o0[j] = v[j]; o1[j] = v[8 + j]; }
       if (tid < rows) {
+        if (sgrad) {
+          const bf16* srow = sgrad + (((long long)tile * NA) * 128 + tid) * 8;
+          float s0[8], s1[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(srow + (long long)(2 * XC + CCH + cb / 8) * 1024)), s0);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(srow + (long long)(2 * XC + CCH + cb / 8 + 1) * 1024)), s1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { o0[j] *= s0[j]; o1[j] *= s1[j]; }
+        }
         *reinterpret_cast<uint4*>(drow + (long long)(2 * XC + CCH + cb / 8) * 1024) = pack8(o0);
         *reinterpret_cast<uint4*>(drow + (long long)(2 * XC + CCH + cb / 8 + 1) * 1024) = pack8(o1);
       }
@@ -872,7 +929,10 @@ __global__ void __launch_bounds__(128)
 k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int CC, const float* __restrict__ dS,
        const float* __restrict__ dt_bias, const float* __restrict__ A_log, const float* __restrict__ Dp,
        bf16* __restrict__ dact, bf16* __restrict__ draw, float* __restrict__ dD, float* __restrict__ dAlog,
-       float* __restrict__ ddtb, int L, int tiles_per_batch, int num_tiles, int tiles_per_cta, int* __restrict__ status) {
+       float* __restrict__ ddtb, int L, int tiles_per_batch, int num_tiles, int tiles_per_cta, int* __restrict__ status,
+       const bf16* __restrict__ sgrad, int dt_nch, int dt_c0) {
+  // dt columns: chunks [dt_c0, dt_c0 + DC) of `raw` and of `draw`, both TL tensors with dt_nch chunks per tile.
+  // sgrad != nullptr (row-kernel path): the x and B column blocks are written as dpre = dact * SiLU'(pre)
   constexpr int XC = DI / 8, BC = GN / 8, DC = DI / 32, NH = DI / 4;
   constexpr uint32_t TCOLS = (DI + GN) <= 128 ? 128 : 256;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -891,7 +951,7 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < NH; i += 128) { s_bias[i] = dt_bias[i]; s_eA[i] = __expf(A_log[i]); s_D[i] = Dp[i]; }
   if (tid == 0) { mbar_init(&bar, 1); mbar_init(&ld_bar[0], 1); mbar_init(&ld_bar[1], 1); fence_mbar_init(); }
-  const int NA = CC >> 3, NR = ldr >> 3;
+  const int NA = CC >> 3;
   if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
@@ -912,7 +972,7 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
     mbar_expect_tx(&ld_bar[stage], (uint32_t)(2 * XC + BC + DC) * 128 * 16);
     tl_bulk(sX, act, tile, NA, XC, XC + BC, &ld_bar[stage]);
     tl_bulk(sDy, dact, tile, NA, XC, XC, &ld_bar[stage]);
-    tl_bulk(sDt, raw, tile, NR, NA, DC, &ld_bar[stage]);
+    tl_bulk(sDt, raw, tile, dt_nch, dt_c0, DC, &ld_bar[stage]);
   };
   if (tid == 0 && tile_begin < tile_end) issue_loads(tile_begin, 0);
   for (int tile = tile_begin, it = 0; tile < tile_end; ++tile, ++it) {
@@ -991,11 +1051,19 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
           if (valid) aD[h] = fmaf(dy[j], x[j], aD[h]);
         }
         *reinterpret_cast<uint4*>(sX + (cg * 128 + tid) * 8) = pack8(wx);
-        if (valid) *reinterpret_cast<uint4*>(drow + (long long)(XC + cg) * 1024) = pack8(o);
+        if (valid) {
+          if (sgrad) {
+            float sv[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(sgrad + (((long long)tile * NA + XC + cg) * 128 + tid) * 8)), sv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] *= sv[j];
+          }
+          *reinterpret_cast<uint4*>(drow + (long long)(XC + cg) * 1024) = pack8(o);
+        }
       }
     }
     {
-      bf16* trow = draw + tl_off(tok0 + tid, CC, ldr >> 3);   // draw is in the tiled layout: chunk stride 128*8
+      bf16* trow = draw + tl_off(tok0 + tid, dt_c0 * 8, dt_nch);   // draw is in the tiled layout: chunk stride 128*8
 #pragma unroll
       for (int dc = 0; dc < DC; ++dc) {
         float o[8];
@@ -1035,6 +1103,14 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
 #pragma unroll
       for (int j = 0; j < 8; ++j) { o0[j] = v[j]; o1[j] = v[8 + j]; }
       if (valid) {
+        if (sgrad) {
+          const bf16* srow = sgrad + (((long long)tile * NA) * 128 + tid) * 8;
+          float s0[8], s1[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(srow + (long long)(2 * XC + cb / 8) * 1024)), s0);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(srow + (long long)(2 * XC + cb / 8 + 1) * 1024)), s1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { o0[j] *= s0[j]; o1[j] *= s1[j]; }
+        }
         *reinterpret_cast<uint4*>(drow + (long long)(2 * XC + cb / 8) * 1024) = pack8(o0);
         *reinterpret_cast<uint4*>(drow + (long long)(2 * XC + cb / 8 + 1) * 1024) = pack8(o1);
       }
@@ -1220,7 +1296,7 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, const float* __restri
   int blk = blockIdx.x;
   if (blk < nb_in) {
     const int n = dip * D, e = blk * 32 + (tid & 31), pl = tid >> 5;
-    float v = 0.f;
+    float v = (e < n && pl == 0 && a.dWin_parts == 0) ? a.dWin[e] : 0.f;   // row-kernel path: atomically accumulated
     if (e < n)
       for (int p = pl; p < a.dWin_parts; p += 8) v += a.dWin_part[(long long)p * n + e];
     red[pl][tid & 31] = v;
@@ -1265,8 +1341,9 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, const float* __restri
 __global__ void k_prep(ConvWeightPtrs cw, float* __restrict__ Kc, int Di, int CC, const float* __restrict__ win,
                        bf16* __restrict__ whi, bf16* __restrict__ wlo, int n_in, const float* __restrict__ wout,
                        bf16* __restrict__ wout_bf, int n_out, bf16* __restrict__ wt_hi, bf16* __restrict__ wt_lo, int n_wt,
-                       int D, int dip) {
+                       int D, int dip, bf16* __restrict__ wtf, bf16* __restrict__ wtb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wtf != nullptr) rowconv::prep_rowconv(cw, win, wtf, wtb, i);   // conv-as-GEMM weight images (row kernels)
   if (wt_hi != nullptr && i < n_wt) {   // element ((jc*D + d)*8 + q) of the W_in^T image = W_in[jc*8+q][d]
     const int q = i & 7, d = (i >> 3) % D, j = ((i >> 3) / D) * 8 + q;
     const float v = j < dip ? win[j * D + d] : 0.f;
@@ -1516,6 +1593,7 @@ struct PrepBufs {
   float* Kc;             // [CC][9] assembled conv kernels
   bf16 *Whi, *Wlo, *Wout;
   bf16 *WT_hi, *WT_lo;   // W_in^T as a K-major B operand image: [ceil(dip/128)*16 chunks][D][8], zero padded
+  bf16 *WtF, *WtB;       // conv-as-GEMM weight images of the row kernels (adnssd_rowconv.cuh)
   int wt_chunks;
   size_t bytes;
   PrepBufs(const MixerDims& d, void* p) {
@@ -1527,6 +1605,8 @@ struct PrepBufs {
     wt_chunks = 16 * cdiv(d.dip, 128);
     WT_hi = c.take<bf16>((size_t)wt_chunks * d.D * 8);
     WT_lo = c.take<bf16>((size_t)wt_chunks * d.D * 8);
+    WtF = c.take<bf16>((size_t)rowconv::WTF_B / 2);
+    WtB = c.take<bf16>((size_t)rowconv::WTB_B / 2);
     bytes = c.off;
   }
 };
@@ -1545,6 +1625,13 @@ struct FastWs {           // placed after the generic workspace of the same pass
     bytes = c.off;
   }
 };
+
+// shapes served by the conv-as-GEMM row kernels: the full-resolution refiner mixers at 128-token-wide grids
+static bool rowconv_supported(const MixerDims& d) {
+  const char* e = getenv("ADN_ROWCONV");      // diagnostics: ADN_ROWCONV=0 keeps these shapes on the tile kernels
+  if (e && e[0] == '0') return false;
+  return d.D == 32 && d.Di == 64 && d.P == 4 && d.GN == 32 && d.W == 128 && d.dip == 208 && d.ldr == 208;
+}
 
 bool sm100_supported(const MixerDims& d) {
   // instantiated tile shapes: d_model 32 (d_inner 64), headdim 4, ngroups*d_state in {32, 128}
@@ -1607,7 +1694,7 @@ static inline void split_tiles(int num_tiles, int per_sm, int* grid, int* per_ct
 
 template <int DI, int GN>
 static int launch_bwd1(const MixerDims& d, const bf16* dout, const bf16* act, const float* S, const AdnWeights& w,
-                       const PrepBufs& P, const FastWs& F, bf16* dact, float* dS, cudaStream_t st) {
+                       const PrepBufs& P, const FastWs& F, bf16* dact, float* dS, cudaStream_t st, const bf16* sgrad) {
   constexpr int D = DI / 2;
   constexpr size_t smem = ((size_t)(D / 8 + GN / 8 + 32) * 128 * 8 + (D / 8) * 2 * DI * 8 + 2 * (GN / 8) * DI * 8 + 2 * (DI / 8) * GN * 8) * sizeof(bf16);
   int rc = set_smem(k_bwd1<DI, GN>, smem);
@@ -1615,13 +1702,14 @@ static int launch_bwd1(const MixerDims& d, const bf16* dout, const bf16* act, co
   const int tpb = cdiv(d.L, 128), nt = tpb * d.B;
   int grid, per;
   split_tiles(nt, smem > 110 * 1024 ? 1 : 2, &grid, &per);
-  { ADN_KERNEL("k_bwd1", st); k_bwd1<DI, GN><<<grid, 128, smem, st>>>(dout, act, d.CC, S, w.D, w.norm_w, w.alpha1, P.Wout, dact, F.Rt, F.sdout, dS, d.L, tpb, nt, per, F.status); }
+  { ADN_KERNEL("k_bwd1", st); k_bwd1<DI, GN><<<grid, 128, smem, st>>>(dout, act, d.CC, S, w.D, w.norm_w, w.alpha1, P.Wout, dact, F.Rt, F.sdout, dS, d.L, tpb, nt, per, F.status, sgrad); }
   return ADN_OK;
 }
 
 template <int DI, int GN>
 static int launch_bwd2(const MixerDims& d, const bf16* act, const bf16* raw, const float* dS, const AdnWeights& w,
-                       const FastWs& F, bf16* dact, bf16* draw, const GradAcc& acc, cudaStream_t st) {
+                       const FastWs& F, bf16* dact, bf16* draw, const GradAcc& acc, cudaStream_t st, const bf16* sgrad,
+                       int dt_nch, int dt_c0) {
   constexpr size_t smem = (2 * (size_t)(GN / 8 + 2 * (DI / 8) + DI / 32) * 128 * 8 + 2 * (GN / 8) * DI * 8 + 2 * (DI / 8) * GN * 8) * sizeof(bf16);
   static_assert(smem <= 227 * 1024, "k_bwd2 stages do not fit shared memory");
   int rc = set_smem(k_bwd2<DI, GN>, smem);
@@ -1629,7 +1717,7 @@ static int launch_bwd2(const MixerDims& d, const bf16* act, const bf16* raw, con
   const int tpb = cdiv(d.L, 128), nt = tpb * d.B;
   int grid, per;
   split_tiles(nt, smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3), &grid, &per);
-  { ADN_KERNEL("k_bwd2", st); k_bwd2<DI, GN><<<grid, 128, smem, st>>>(act, raw, d.ldr, d.CC, dS, w.dt_bias, w.A_log, w.D, dact, draw, acc.dD, acc.dAlog, acc.ddtb, d.L, tpb, nt, per, F.status); }
+  { ADN_KERNEL("k_bwd2", st); k_bwd2<DI, GN><<<grid, 128, smem, st>>>(act, raw, d.ldr, d.CC, dS, w.dt_bias, w.A_log, w.D, dact, draw, acc.dD, acc.dAlog, acc.ddtb, d.L, tpb, nt, per, F.status, sgrad, dt_nch, dt_c0); }
   return ADN_OK;
 }
 
@@ -1661,8 +1749,22 @@ int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* 
   ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
   {
     const int n_in = d.dip * d.D, n_out = d.D * 2 * d.Di, n_wt = P.wt_chunks * d.D * 8;
-    const int n = max(max(max(n_in, n_out), d.CC), n_wt);
-    { ADN_KERNEL("k_prep", st); k_prep<<<cdiv(n, 256), 256, 0, st>>>(conv_ptrs(w), P.Kc, d.Di, d.CC, w.in_proj_w, P.Whi, P.Wlo, n_in, w.out_proj_w, P.Wout, n_out, P.WT_hi, P.WT_lo, n_wt, d.D, d.dip); }
+    const bool rows = rowconv_supported(d);
+    const int n = max(max(max(max(n_in, n_out), d.CC), n_wt), rows ? 9 * rowconv::DIP * rowconv::D : 0);
+    { ADN_KERNEL("k_prep", st); k_prep<<<cdiv(n, 256), 256, 0, st>>>(conv_ptrs(w), P.Kc, d.Di, d.CC, w.in_proj_w, P.Whi, P.Wlo, n_in, w.out_proj_w, P.Wout, n_out, P.WT_hi, P.WT_lo, n_wt, d.D, d.dip, rows ? P.WtF : nullptr, P.WtB); }
+  }
+  if (rowconv_supported(d)) {
+    // (1)-(4a) fused: in_proj + conv + SiLU + decay weights + state, one image row per step (adnssd_rowconv.cuh).
+    // The `raw` slot of the saved tensors only holds the dt columns, as a TL tensor with 2 chunks per tile.
+    ADN_CHECK_CUDA(cudaMemsetAsync(S.S, 0, (size_t)d.B * d.GN * d.Di * sizeof(float), st));
+    int rc = set_smem(rowconv::k_fconv, rowconv::FC_SMEM);
+    if (rc) return rc;
+    const int rows_total = d.B * d.H, per = cdiv(rows_total, 148), grid = cdiv(rows_total, per);
+    { ADN_KERNEL("k_fconv", st); rowconv::k_fconv<<<grid, 320, rowconv::FC_SMEM, st>>>(u, P.WtF, w.dt_bias, w.A_log, S.act, training ? S.pre : nullptr, S.raw, S.S, d.H, rows_total, per, F.status); }
+    rc = launch_readout<64, 32>(d, S.act, S.S, w, P.Wout, out, F.status, st);
+    if (rc) return rc;
+    ADN_CHECK_LAUNCH();
+    return ADN_OK;
   }
   // (1) in_proj on tcgen05
   int rc = d.D == 16 ? launch_inproj<16>(d, u, P, F, S.raw, st) : d.D == 32 ? launch_inproj<32>(d, u, P, F, S.raw, st)
@@ -1697,12 +1799,39 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   ADN_CHECK_CUDA(cudaMemsetAsync(F.Rt, 0, ((size_t)2 * d.Di * d.D + d.D) * sizeof(float), st));
   ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
   // ---- phase B1: dout -> dy, dzc, dCc ; reductions Rt, dS'
-  int rc = d.GN == 32 ? launch_bwd1<64, 32>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st)
-                      : launch_bwd1<64, 128>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st);
+  if (rowconv_supported(d)) {
+    // B1 / B2 write dpre = dact * SiLU'(pre) directly; ddt goes to a compact TL tensor (2 chunks per tile) in W.draw
+    int rc = launch_bwd1<64, 32>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st, S.pre);
+    if (rc) return rc;
+    rc = launch_bwd2<64, 32>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st, S.pre, 2, 0);
+    if (rc) return rc;
+    const int rows_total = d.B * d.H;
+    {
+      rc = set_smem(rowconv::k_bconv_du, rowconv::DU_SMEM);
+      if (rc) return rc;
+      const int per = cdiv(rows_total, 148), grid = cdiv(rows_total, per);
+      { ADN_KERNEL("k_bconv_du", st); rowconv::k_bconv_du<<<grid, 192, rowconv::DU_SMEM, st>>>(W.dact, W.draw, P.WtB, du, d.H, rows_total, per, F.status); }
+    }
+    {
+      rc = set_smem(rowconv::k_bconv_wg, rowconv::WG_SMEM);
+      if (rc) return rc;
+      const int cpb = max(1, min(74, rows_total)), per = cdiv(rows_total, cpb), parts = cdiv(rows_total, per);
+      { ADN_KERNEL("k_bconv_wg", st); rowconv::k_bconv_wg<<<2 * parts, 192, rowconv::WG_SMEM, st>>>(W.dact, W.draw, u, w.in_proj_w, P.Kc, W.acc.dK, W.acc.dWin, d.H, rows_total, per, parts, F.status); }
+    }
+    W.acc.dWin_part = nullptr;
+    W.acc.dWin_parts = 0;
+    if (g.alpha1) ADN_CHECK_CUDA(cudaMemsetAsync(g.alpha1, 0, sizeof(float), st));
+    const int nb_in = cdiv(d.dip * d.D, 32), nb_rest = 8;
+    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<nb_in + 2 * d.Di + nb_rest, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest); }
+    ADN_CHECK_LAUNCH();
+    return ADN_OK;
+  }
+  int rc = d.GN == 32 ? launch_bwd1<64, 32>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st, nullptr)
+                      : launch_bwd1<64, 128>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st, nullptr);
   if (rc) return rc;
   // ---- phase B2: dS' -> dxc, dBc, ddt
-  rc = d.GN == 32 ? launch_bwd2<64, 32>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st)
-                  : launch_bwd2<64, 128>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st);
+  rc = d.GN == 32 ? launch_bwd2<64, 32>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st, nullptr, d.ldr >> 3, d.CC >> 3)
+                  : launch_bwd2<64, 128>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st, nullptr, d.ldr >> 3, d.CC >> 3);
   if (rc) return rc;
   // ---- conv backward (dpre formed in shared memory; transposed conv + kernel gradient)
   {
@@ -1774,6 +1903,18 @@ extern "C" int adn_selftest_umma_shift(int mode, int N, int K, int pitch, int sh
   cudaStream_t st = (cudaStream_t)stream;
   ADN_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
   { ADN_KERNEL("k_umma_shift_selftest", st); k_umma_shift_selftest<<<1, 128, smem, st>>>(mode, N, K, pitch, shiftA, shiftB, (const bf16*)A, (const bf16*)B, C, status); }
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
+extern "C" int adn_bench_umma(int mode, int N, int pitch, int shift, int iters, int ctas, long long* cycles, void* stream) {
+  using namespace adn;
+  ADN_REQUIRE(cycles && (mode == 0 || mode == 1) && N % 16 == 0 && N >= 16 && N <= 256 && pitch >= 128 && pitch <= 160 && shift >= 0 &&
+                  shift <= 8 && ctas >= 1, ADN_ERR_SHAPE, "adn_bench_umma: bad arguments");
+  const size_t smem = 64 * 1024;
+  ADN_CHECK_CUDA(cudaFuncSetAttribute(k_umma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaStream_t st = (cudaStream_t)stream;
+  { ADN_KERNEL("k_umma_bench", st); k_umma_bench<<<ctas, 128, smem, st>>>(mode, N, pitch, shift, iters, cycles); }
   ADN_CHECK_LAUNCH();
   return ADN_OK;
 }

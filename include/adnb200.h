@@ -178,6 +178,10 @@ int adn_selftest_umma(int mode, int N, int K, const void* A, const void* B, floa
 int adn_selftest_umma_shift(int mode, int N, int K, int pitch, int shiftA, int shiftB, const void* A, const void* B,
                             float* C, int* status, void* stream);
 
+/* tcgen05.mma issue-rate probe: `ctas` CTAs each issue `iters` 128 x N x 16 bf16 MMAs (mode 0 K-major, 1 MN-major operands,
+ * row pitch `pitch`, start shifted by `shift` rows); cycles[cta] (DEVICE int64) = SM clocks from first issue to completion. */
+int adn_bench_umma(int mode, int N, int pitch, int shift, int iters, int ctas, long long* cycles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,30 @@ def test_mixer_matches_oracle_ragged_shapes(cfg, dtype):
     assert not bad, f"{cfg} {dtype}: {bad}"
 
 
+@pytest.mark.parametrize("cfg", [(3, 5, 128), (2, 1, 128), (1, 2, 128), (5, 37, 128)], ids=lambda c: "B%d_%dx%d" % c)
+def test_row_kernels_match_oracle(cfg):
+    """128-token-wide grids take the conv-as-GEMM row kernels (adnssd_rowconv.cuh): several samples per CTA range,
+    H = 1 (no vertical taps), H = 2, and a CTA range that ends mid-sample; model-scale weights, bf16 contract 2e-2."""
+    B, H, W = cfg
+    D, P, N = 32, 4, 16
+    params = AO.init_params(D, P, N, seed=9, perturb=0.05, dtype=torch.float32)
+    u = cases.rng_normal(21, (B, H * W, D), torch.float32)
+    dout = cases.rng_normal(22, (B, H * W, D), torch.float32)
+    p64 = {k: v.double() for k, v in params.items()}
+    ref_out = AO.mixer_forward(p64, u.double(), H, W, P, N)
+    ref_du, ref_g = AO.mixer_backward(p64, u.double(), H, W, P, N, dout.double())
+    out, du, pg = run_cuda(params, u, dout, H, W, P, N, torch.bfloat16)
+    errs = {"out": rel(out, ref_out), "du": rel(du, ref_du)}
+    for k, ref in ref_g.items():
+        errs[k] = rel(pg[k].reshape(ref.shape), ref)
+    # alpha1 is a scalar: d alpha1 = <dout, out> / alpha1 is a sum over every token with heavy cancellation, so its error is
+    # measured against the sum of the magnitudes of its terms rather than against the (cancelled) result
+    terms = (dout.double() * ref_out).abs().sum() / p64["alpha1"].abs()
+    errs["alpha1"] = ((pg["alpha1"].double().cpu() - ref_g["alpha1"]).abs() / terms).item()
+    bad = {k: v for k, v in errs.items() if not v < 2e-2}
+    assert not bad, f"{cfg}: {bad} (all: {errs})"
+
+
 def test_module_is_a_drop_in(golden_dir):
     """Strict state_dict load of reference-shaped weights, forward(u, H, W), grads land on the same 18 parameters."""
     import adnm_unet_b200 as A
