@@ -113,8 +113,28 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """Raw cudaStream_t of torch's current stream on `device` (default: the current device)."""
+    idx = torch.cuda.current_device() if device is None or device.index is None else device.index
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(idx))
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def on_device(device):
+    """Context that makes `device` current for the library call; free when it already is."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(device)
 
 
 def scratch(nbytes, device):

@@ -732,6 +732,15 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
       for (int k = 0; k < GN; k += 16) umma(tbase + COL_Y, desc_kmajor(aC, 128, 0, k), desc_kmajor(bl, DI, 0, k), id_y, true);
       umma_commit(&bar);
     }
+    // SiLU' of this row's z and C columns, fetched into registers while the MMAs run (tiles are full: L % 128 == 0)
+    uint4 sgz[XC], sgc[CCH];
+    if (sgrad) {
+      const bf16* srow = sgrad + (((long long)tile * NA) * 128 + tid) * 8;
+#pragma unroll
+      for (int q = 0; q < XC; ++q) sgz[q] = __ldg(reinterpret_cast<const uint4*>(srow + (long long)q * 1024));
+#pragma unroll
+      for (int q = 0; q < CCH; ++q) sgc[q] = __ldg(reinterpret_cast<const uint4*>(srow + (long long)(2 * XC + CCH + q) * 1024));
+    }
     ok = mbar_wait(&bar, ph) && ok;
     ph ^= 1;
     tc_fence_after();
@@ -812,10 +821,9 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
       for (int j = 0; j < 8; ++j) { o0[j] = a1 * v[j]; o1[j] = a1 * v[8 + j]; }
       if (tid < rows) {
         if (sgrad) {
-          const bf16* srow = sgrad + (((long long)tile * NA) * 128 + tid) * 8;
           float s0[8], s1[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(srow + (long long)(cb / 8) * 1024)), s0);
-          unpack8(__ldg(reinterpret_cast<const uint4*>(srow + (long long)(cb / 8 + 1) * 1024)), s1);
+          unpack8(sgz[cb / 8], s0);
+          unpack8(sgz[cb / 8 + 1], s1);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { o0[j] *= s0[j]; o1[j] *= s1[j]; }
         }
@@ -868,10 +876,9 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
       for (int j = 0; j < 8; ++j) { o0[j] = v[j]; o1[j] = v[8 + j]; }
       if (tid < rows) {
         if (sgrad) {
-          const bf16* srow = sgrad + (((long long)tile * NA) * 128 + tid) * 8;
           float s0[8], s1[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(srow + (long long)(2 * XC + CCH + cb / 8) * 1024)), s0);
-          unpack8(__ldg(reinterpret_cast<const uint4*>(srow + (long long)(2 * XC + CCH + cb / 8 + 1) * 1024)), s1);
+          unpack8(sgc[cb / 8], s0);
+          unpack8(sgc[cb / 8 + 1], s1);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { o0[j] *= s0[j]; o1[j] *= s1[j]; }
         }
@@ -1006,6 +1013,15 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
       for (int k = 0; k < GN; k += 16) umma(tbase, desc_kmajor(aB_, 128, 0, k), desc_kmajor(bl, DI, 0, k), idesc, true);
       umma_commit(&bar);
     }
+    // SiLU' of this row's x and B columns, fetched into registers while the MMA runs (tiles are full: L % 128 == 0)
+    uint4 sgx[XC], sgb[BC];
+    if (sgrad) {
+      const bf16* srow = sgrad + (((long long)tile * NA) * 128 + tid) * 8;
+#pragma unroll
+      for (int q = 0; q < XC; ++q) sgx[q] = __ldg(reinterpret_cast<const uint4*>(srow + (long long)(XC + q) * 1024));
+#pragma unroll
+      for (int q = 0; q < BC; ++q) sgb[q] = __ldg(reinterpret_cast<const uint4*>(srow + (long long)(2 * XC + q) * 1024));
+    }
     // decay weights while the MMA runs
     float w[NH], sg[NH];
 #pragma unroll
@@ -1054,7 +1070,7 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
         if (valid) {
           if (sgrad) {
             float sv[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(sgrad + (((long long)tile * NA + XC + cg) * 128 + tid) * 8)), sv);
+            unpack8(sgx[cg], sv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] *= sv[j];
           }
@@ -1104,10 +1120,9 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
       for (int j = 0; j < 8; ++j) { o0[j] = v[j]; o1[j] = v[8 + j]; }
       if (valid) {
         if (sgrad) {
-          const bf16* srow = sgrad + (((long long)tile * NA) * 128 + tid) * 8;
           float s0[8], s1[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(srow + (long long)(2 * XC + cb / 8) * 1024)), s0);
-          unpack8(__ldg(reinterpret_cast<const uint4*>(srow + (long long)(2 * XC + cb / 8 + 1) * 1024)), s1);
+          unpack8(sgb[cb / 8], s0);
+          unpack8(sgb[cb / 8 + 1], s1);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { o0[j] *= s0[j]; o1[j] *= s1[j]; }
         }

@@ -27,11 +27,21 @@ UNUSED_KEYS = ("scale", "shift", "alpha2")          # declared, never read by th
 USED_KEYS = tuple(k for k in PARAM_KEYS if k not in UNUSED_KEYS)
 
 
-def _shape_struct(u, H, W, headdim, d_state, d_inner, ngroups):
+_SHAPE_CACHE = {}   # (B, H, W, D, Di, P, G, N, dtype) -> (AdnShape, saved bytes, fwd workspace bytes, bwd workspace bytes)
+
+
+def _shape_info(u, H, W, headdim, d_state, d_inner, ngroups):
     B, L, D = u.shape
     if L != H * W:
         raise RuntimeError(f"adnssd: L={L} != H*W={H * W}")
-    return _lib.AdnShape(B=B, H=H, W=W, D=D, Di=d_inner, P=headdim, G=ngroups, N=d_state, dtype=_lib.dtype_code(u), flags=0)
+    key = (B, H, W, D, d_inner, headdim, ngroups, d_state, u.dtype)
+    hit = _SHAPE_CACHE.get(key)
+    if hit is None:
+        shape = _lib.AdnShape(B=B, H=H, W=W, D=D, Di=d_inner, P=headdim, G=ngroups, N=d_state, dtype=_lib.dtype_code(u), flags=0)
+        sv, fw, bw = (_lib.C.c_size_t() for _ in range(3))
+        _lib.check(_lib.load().adnssd_workspace_bytes(shape, sv, fw, bw), "adnssd_workspace_bytes")
+        hit = _SHAPE_CACHE[key] = (shape, sv.value, fw.value, bw.value)
+    return hit
 
 
 def _weights_struct(cls, tensors):
@@ -45,7 +55,12 @@ def _weights_struct(cls, tensors):
 def _prep_param(p, device):
     if p.device != device:
         raise RuntimeError(f"adnssd: parameter on {p.device}, activations on {device}")
+    if p.dtype == torch.float32 and p.is_contiguous():
+        return p                      # only its data_ptr() is used
     return p.detach().float().contiguous()
+
+
+_GRAD_NUMEL = {}   # tuple of parameter shapes -> (sizes, total): the 18 gradients live in ONE flat fp32 buffer
 
 
 class _AdnSsdFunction(torch.autograd.Function):
@@ -56,40 +71,42 @@ class _AdnSsdFunction(torch.autograd.Function):
         _lib.require_cuda(u, "u")
         lib = _lib.load()
         u = u.contiguous()
-        shape = _shape_struct(u, H, W, headdim, d_state, d_inner, ngroups)
+        shape, sv, fw, bw = _shape_info(u, H, W, headdim, d_state, d_inner, ngroups)
         tensors = {k: _prep_param(p, u.device) for k, p in zip(USED_KEYS, params)}
         wts = _weights_struct(_lib.AdnWeights, tensors)
-        sv, fw, bw = (_lib.C.c_size_t() for _ in range(3))
-        _lib.check(lib.adnssd_workspace_bytes(shape, sv, fw, bw), "adnssd_workspace_bytes")
         need_grad = any(ctx.needs_input_grad)
-        saved = _lib.scratch(sv.value, u.device) if need_grad else None
-        ws = _lib.scratch(fw.value, u.device)
+        saved = _lib.scratch(sv, u.device) if need_grad else None
+        ws = _lib.scratch(fw, u.device)
         out = torch.empty_like(u)
-        with torch.cuda.device(u.device):
+        with _lib.on_device(u.device):
             _lib.check(lib.adnssd_forward(shape, wts, _lib.ptr(u), _lib.ptr(out), _lib.ptr(saved), _lib.ptr(ws),
-                                          _lib.stream_ptr()), "adnssd_forward")
+                                          _lib.stream_ptr(u.device)), "adnssd_forward")
         if need_grad:
             ctx.save_for_backward(u, saved, *params)
-            ctx.cfg = (H, W, headdim, d_state, d_inner, ngroups, bw.value)
+            # the prepared fp32 tensors are kept alive next to their pointer struct (no-ops for fp32 contiguous parameters)
+            ctx.cfg = (shape, bw, wts, tensors)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         lib = _lib.load()
         u, saved, *params = ctx.saved_tensors
-        H, W, headdim, d_state, d_inner, ngroups, bw = ctx.cfg
+        shape, bw, wts, tensors = ctx.cfg
         dout = dout.to(u.dtype).contiguous()
-        shape = _shape_struct(u, H, W, headdim, d_state, d_inner, ngroups)
-        tensors = {k: _prep_param(p, u.device) for k, p in zip(USED_KEYS, params)}
-        wts = _weights_struct(_lib.AdnWeights, tensors)
-        grads = {k: torch.empty_like(t) for k, t in tensors.items()}
+        skey = tuple(t.shape for t in tensors.values())
+        meta = _GRAD_NUMEL.get(skey)
+        if meta is None:
+            sizes = [t.numel() for t in tensors.values()]
+            meta = _GRAD_NUMEL[skey] = (sizes, sum(sizes))
+        flat = torch.empty(meta[1], dtype=torch.float32, device=u.device)
+        grads = dict(zip(USED_KEYS, flat.split(meta[0])))
         gst = _weights_struct(_lib.AdnWeightGrads, grads)
         du = torch.empty_like(u)
         ws = _lib.scratch(bw, u.device)
-        with torch.cuda.device(u.device):
+        with _lib.on_device(u.device):
             _lib.check(lib.adnssd_backward(shape, wts, _lib.ptr(u), _lib.ptr(saved), _lib.ptr(dout), _lib.ptr(du), gst,
-                                           _lib.ptr(ws), _lib.stream_ptr()), "adnssd_backward")
-        pg = tuple(grads[k].to(p.dtype).reshape(p.shape) if need else None
+                                           _lib.ptr(ws), _lib.stream_ptr(u.device)), "adnssd_backward")
+        pg = tuple((grads[k].view(p.shape) if p.dtype == torch.float32 else grads[k].to(p.dtype).view(p.shape)) if need else None
                    for k, p, need in zip(USED_KEYS, params, ctx.needs_input_grad[7:]))
         return (du if ctx.needs_input_grad[0] else None, None, None, None, None, None, None) + pg
 

@@ -171,7 +171,7 @@ def run_ours(args):
         if reducer is not None:
             reducer()       # NCCL all-reduce(sum) / world of the flat parameter-gradient bucket
 
-    def step_resident(i):
+    def step_eager(i):
         u = dev_u[i % N_INPUT_SETS].requires_grad_(True)
         u.grad = None
         for p in params:
@@ -180,6 +180,49 @@ def run_ours(args):
         out.backward(dev_g[i % N_INPUT_SETS])
         allreduce_grads()
         return out, u.grad
+
+    # ---- CUDA graphs: one captured fwd+bwd of the public module per static (u, dout) pair, replayed in the timed loops
+    # (the C ABI enqueues on the caller's stream without host synchronisation, so the whole step is capturable; the host
+    # then issues one cudaGraphLaunch per step instead of ~15 launches through Python / autograd).
+    pool = torch.cuda.graph_pool_handle() if args.graph else None
+
+    def capture(u_static, g_static):
+        u_static.requires_grad_(True)
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):                       # warm-up outside capture (PyTorch CUDA-graph recipe)
+            for _ in range(2):
+                u_static.grad = None
+                for p in params:
+                    p.grad = None
+                mixer(u_static, GRID, GRID).backward(g_static)
+        torch.cuda.current_stream().wait_stream(s)
+        u_static.grad = None
+        for p in params:
+            p.grad = None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, pool=pool):
+            out = mixer(u_static, GRID, GRID)
+            out.backward(g_static)
+        # the 18 parameter gradients are views of ONE flat fp32 buffer (adnm_unet_b200/mixer.py): all-reduce it in one call
+        flat = torch.empty(0, dtype=torch.float32, device=dev).set_(params[0].grad.untyped_storage())
+        assert flat.numel() == sum(p.numel() for p in params), "flat gradient buffer layout changed"
+        return graph, out.detach(), u_static.grad, flat
+
+    n0 = _lib.launch_count()
+    step_eager(0)
+    launches_per_step = _lib.launch_count() - n0
+    graphs = [capture(dev_u[k], dev_g[k]) for k in range(N_INPUT_SETS)] if args.graph else None
+
+    def step_resident(i):
+        if graphs is None:
+            return step_eager(i)
+        graph, out, du, flat = graphs[i % N_INPUT_SETS]
+        graph.replay()
+        if world > 1:
+            dist.all_reduce(flat)
+            flat.div_(world)
+        return out, du
 
     # ---- end-to-end: host buffers in, host buffers out, every step.  Copies run on their own streams so that the H2D of
     # step i+1 and the D2H of step i-1 overlap the kernels of step i (double-buffered device staging slots).
@@ -194,30 +237,43 @@ def run_ours(args):
     ev_out = [torch.cuda.Event() for _ in range(NSLOT)]
     keep = [None] * NSLOT
 
+    slot_graphs = [capture(slot_u[k], slot_g[k]) for k in range(NSLOT)] if args.graph else None
+
     def step_e2e(i):
         k = i % NSLOT
         cur = torch.cuda.current_stream()
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_done[k])            # the kernels that last read this staging slot have finished
-            slot_u[k].copy_(host_u[i % N_INPUT_SETS], non_blocking=True)
-            slot_g[k].copy_(host_g[i % N_INPUT_SETS], non_blocking=True)
+            with torch.no_grad():
+                slot_u[k].copy_(host_u[i % N_INPUT_SETS], non_blocking=True)
+                slot_g[k].copy_(host_g[i % N_INPUT_SETS], non_blocking=True)
             ev_in[k].record(s_in)
         cur.wait_event(ev_in[k])
         cur.wait_event(ev_out[k])                  # the previous D2H out of this slot's result tensors has finished
-        u = slot_u[k].detach().requires_grad_(True)
-        for p in params:
-            p.grad = None
-        out = mixer(u, GRID, GRID)
-        out.backward(slot_g[k])
-        allreduce_grads()
+        if slot_graphs is None:
+            u = slot_u[k].detach().requires_grad_(True)
+            for p in params:
+                p.grad = None
+            out = mixer(u, GRID, GRID)
+            out.backward(slot_g[k])
+            allreduce_grads()
+            res = (out.detach(), u.grad)
+        else:
+            graph, out, du, flat = slot_graphs[k]
+            graph.replay()
+            if world > 1:
+                dist.all_reduce(flat)
+                flat.div_(world)
+            res = (out, du)
         ev_done[k].record(cur)
-        keep[k] = (out.detach(), u.grad)
+        keep[k] = res
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_done[k])
             host_outs[k].copy_(keep[k][0], non_blocking=True)
             host_dus[k].copy_(keep[k][1], non_blocking=True)
-            keep[k][0].record_stream(s_out)
-            keep[k][1].record_stream(s_out)
+            if slot_graphs is None:
+                keep[k][0].record_stream(s_out)
+                keep[k][1].record_stream(s_out)
             ev_out[k].record(s_out)
 
     def drain_e2e():
@@ -251,9 +307,8 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    n0 = _lib.launch_count()
     ms = timed(step_resident, args.steps)
-    launches = _lib.launch_count() - n0
+    launches = launches_per_step * args.steps      # kernels of this library per step (counted on an eager step) x steps
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(step_e2e, args.steps, drain_e2e)
 
@@ -261,7 +316,7 @@ def run_ours(args):
     barrier()
     with _lib.profile() as prof:
         for i in range(min(args.steps, 5)):
-            step_resident(i)
+            step_eager(i)
     per = {}
     for name, t in prof.records:
         a = per.setdefault(name, [0.0, 0])
@@ -292,7 +347,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"ADN-SSD mixer fwd+bwd (BASELINE configs[1]): D={D}, headdim={HEADDIM}, d_state={D_STATE}, "
                                    f"B={B}/GPU, {GRID}x{GRID} tokens", "global_batch": B * world, "tokens_per_step": tokens * world,
-                       "parallelism": f"dp{world}", "l2": f"{N_INPUT_SETS} rotating input sets (> L2) + ~1 GB of intermediates rewritten per step"},
+                       "parallelism": f"dp{world}", "launch": "cuda_graph_replay" if args.graph else "eager", "l2": f"{N_INPUT_SETS} rotating input sets (> L2) + ~1 GB of intermediates rewritten per step"},
             "e2e": {"value": world * tokens * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": 2 * tokens * D * 2, "d2h_bytes_per_step": 2 * tokens * D * 2,
                     "ms_per_step": ms_e2e / args.steps},
@@ -357,6 +412,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--d-model", type=int, default=32)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="issue every step through Python / autograd instead of replaying a captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
