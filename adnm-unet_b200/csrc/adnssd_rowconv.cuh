@@ -25,7 +25,8 @@ constexpr int RP = 130;                  // positions per chunk of a padded row 
 constexpr int D = 32, DI = 64, GN = 32, CC = 192, NA = 24, DIP = 208, NH = 16;
 constexpr int CHB = RP * 16;             // bytes of one padded chunk (2080)
 constexpr int USLOT_B = 4 * CHB;         // padded u row slot: 32 channels (8320 bytes)
-constexpr int NUS = 4;                   // u ring slots
+constexpr int NUS = 6;                   // u ring slots of k_fconv (one copy per row)
+constexpr int NUW = 5;                   // u ring slots of k_bconv_wg (three shifted copies per row)
 constexpr int WTF_TAP_B = 4 * DIP * 16;  // forward B operand of one tap: [4 chunks][208][8] bf16 (13312 bytes)
 constexpr int WTF_B = 9 * WTF_TAP_B;
 constexpr int WTB_TG_B = 2048;           // backward B operand of one (tap, 32-channel group): [4 chunks][32][8] bf16
@@ -99,30 +100,77 @@ __device__ __forceinline__ void prep_rowconv(const ConvWeightPtrs& cw, const flo
 }
 
 // One warp: copy one row-major u row (128 tokens x 32 channels, 8 KB contiguous) into positions 1..128 of a padded slot.
+// NCOPY = 3 writes the row three times, the copies UCOPY_B = 4*CHB - 16 bytes apart: chunk (b, dc) of the 12-chunk operand
+// that starts at the slot base with chunk stride CHB is then chunk dc of the row shifted by b positions, i.e. the three
+// horizontal taps become ONE operand with N (or K) = 96.  Consecutive copies overlap in one 16-byte padding position
+// (the last pad of copy b and the first pad of copy b+1), which is zero in both.
+constexpr int UCOPY_B = 4 * CHB - 16;
+constexpr int USLOT3_B = 2 * UCOPY_B + 4 * CHB;    // 24928 bytes
+
+template <int NCOPY>
 __device__ __forceinline__ void urow_load(uint8_t* slot, const bf16* __restrict__ urow, int lane) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int piece = i * 32 + lane, tok = piece >> 2, ch = piece & 3;
-    cp_async16(slot + ch * CHB + (1 + tok) * 16, urow + piece * 8, 16);
+#pragma unroll
+    for (int c = 0; c < NCOPY; ++c) cp_async16(slot + c * UCOPY_B + ch * CHB + (1 + tok) * 16, urow + piece * 8, 16);
   }
 }
 
-// Producer warp of the u ring: rows [gfirst, glast] -> slot (g - gfirst) % NUS; full[] has count 32, empty[] count 1.
+// Producer warp of the u ring: rows [gfirst, glast] -> slot (g - gfirst) % NSLOT; full[] has count 32, empty[] count 1.
+// Up to LAG + 1 row loads are in flight (cp.async groups); a row is published once its group has landed.
+// u_tl != nullptr: rows [tl_first, tl_last] are also written back to global memory in the TL layout ([row][4 chunks][128][8]),
+// from which the backward kernels fetch them with bulk copies.
+template <int NCOPY, int NSLOT>
 __device__ __forceinline__ void urow_producer(uint8_t* sU, const bf16* __restrict__ u, int gfirst, int glast, uint64_t* full,
-                                              uint64_t* empty, int lane) {
+                                              uint64_t* empty, int lane, bf16* __restrict__ u_tl = nullptr, int tl_first = 0,
+                                              int tl_last = -1) {
+  constexpr int SLOT = NCOPY == 1 ? USLOT_B : USLOT3_B;
+  constexpr int LAG = 2;
   const int n = glast - gfirst + 1;
-  for (int i = 0; i <= n; ++i) {
+  for (int i = 0; i < n + LAG; ++i) {
     if (i < n) {
-      if (i >= NUS) mbar_wait(&empty[i % NUS], ((i / NUS) - 1) & 1);
-      urow_load(sU + (i % NUS) * USLOT_B, u + (long long)(gfirst + i) * 128 * D, lane);
+      if (i >= NSLOT) mbar_wait(&empty[i % NSLOT], ((i / NSLOT) - 1) & 1);
+      urow_load<NCOPY>(sU + (i % NSLOT) * SLOT, u + (long long)(gfirst + i) * 128 * D, lane);
     }
     cp_async_commit();
-    if (i >= 1) {
-      cp_async_wait<1>();
+    if (i >= LAG) {
+      cp_async_wait<LAG>();
       fence_async_smem();
-      mbar_arrive(&full[(i - 1) % NUS]);
+      mbar_arrive(&full[(i - LAG) % NSLOT]);
+      const int g = gfirst + i - LAG;
+      if (u_tl != nullptr && g >= tl_first && g <= tl_last) {
+        __syncwarp();     // the row was fetched by all 32 lanes
+        const uint8_t* slot = sU + ((i - LAG) % NSLOT) * SLOT;
+        uint4* dst = reinterpret_cast<uint4*>(u_tl + (long long)g * 128 * D);
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+          const int piece = k * 32 + lane;
+          dst[piece] = *reinterpret_cast<const uint4*>(slot + (piece >> 7) * CHB + (1 + (piece & 127)) * 16);
+        }
+      }
     }
   }
+}
+
+// Elected-thread producer of a three-copy u ring from the TL copy of u (12 bulk copies of 2 KB per row).
+template <int NSLOT>
+__device__ __forceinline__ bool urow3_bulk_producer(uint8_t* sU, const bf16* __restrict__ u_tl, int gfirst, int glast,
+                                                    uint64_t* full, uint64_t* empty) {
+  bool ok = true;
+  const int n = glast - gfirst + 1;
+  for (int i = 0; i < n; ++i) {
+    const int sl = i % NSLOT;
+    if (i >= NSLOT) ok = mbar_wait(&empty[sl], ((i / NSLOT) - 1) & 1) && ok;
+    mbar_expect_tx(&full[sl], 3 * 4 * 2048);
+    const bf16* src = u_tl + (long long)(gfirst + i) * 128 * D;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int dc = 0; dc < 4; ++dc)
+        bulk_g2s(sU + sl * USLOT3_B + c * UCOPY_B + dc * CHB + 16, src + dc * 1024, 2048, &full[sl]);
+  }
+  return ok;
 }
 
 // SiLU and SiLU' of 32 accumulator columns of this thread's token row (two TMEM loads in flight, packed fp32x2 math);
@@ -144,6 +192,8 @@ __device__ __forceinline__ void silu32(uint32_t taddr, bf16* a_dst, bf16* g_dst,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 x = make_float2(v[hh >> 1][(hh & 1) * 8 + 2 * j], v[hh >> 1][(hh & 1) * 8 + 2 * j + 1]);
+      // sigmoid = 1 / (1 + 2^(-x log2 e)): two MUFU ops per element.  (A MUFU-free Newton reciprocal was measured slower:
+      // the epilogue is bound by instruction issue / latency of 3 warps per scheduler, not by the MUFU pipe.)
       const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
       const float2 d = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.f, 1.f));
       const float2 sg = make_float2(rcp_approx(d.x), rcp_approx(d.y));
@@ -169,21 +219,22 @@ __device__ __forceinline__ void silu32(uint32_t taddr, bf16* a_dst, bf16* g_dst,
 // ------------------------------------------------------------------------------------------------
 // k_fconv: forward in_proj + depthwise 3x3 + SiLU (+ SiLU') + decay weights + state accumulation, one image row
 // (128 tokens) per step.  Stages (1)-(4a) of the mixer (models/ADNssd.py:309-390, :267-280).
-//   warps 0-7  epilogue (lane quarter q = warp & 3, column half = warp >> 2)
-//   warp  8    u-row producer (cp.async into the padded ring)
-//   warp  9    lane 0 issues every tcgen05.mma
+//   warps 0-11 epilogue (lane quarter q = warp & 3, column group = warp >> 2: z | dt + x | B + C)
+//   warp  12   u-row producer (cp.async into the padded ring)
+//   warp  13   one elected lane issues every tcgen05.mma (and the bulk copies of the weight image)
 // TMEM: two 208-column accumulators [z | x | B | C | dt] + 32 columns of the per-sample state S'[c][j].
 // ------------------------------------------------------------------------------------------------
 constexpr int FC_ST_B = 12 * 2048;   // state operands of one row: wx chunks 0..7, Bc chunks 8..11
 constexpr int FC_SMEM = 2 * FC_ST_B + NUS * USLOT_B + WTF_B;
 constexpr int FC_COL_S = 2 * DIP;
+constexpr int FC_EPI_WARPS = 12, FC_THREADS = (FC_EPI_WARPS + 2) * 32;   // 3 column groups x 4 lane quarters + producer + MMA
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(FC_THREADS, 1)
 k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* __restrict__ dt_bias,
         const float* __restrict__ A_log, bf16* __restrict__ act, bf16* __restrict__ sgrad, bf16* __restrict__ dtraw,
-        float* __restrict__ S, int H, int rows_total, int rows_per_cta, int* __restrict__ status) {
+        float* __restrict__ S, int H, int rows_total, int rows_per_cta, int* __restrict__ status, bf16* __restrict__ u_tl) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full[NUS], empty[NUS], acc_full[2], acc_empty[2], st_full[2], st_empty[2], s_done, s_free;
+  __shared__ uint64_t full[NUS], empty[NUS], acc_full[2], acc_empty[2], st_full[2], st_empty[2], s_done, s_free, w_full;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_bias[NH], s_eA[NH];
   uint8_t* sSt = smem;
@@ -191,17 +242,17 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
   uint8_t* sW = sU + NUS * USLOT_B;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R0 = blockIdx.x * rows_per_cta, R1 = min(rows_total, R0 + rows_per_cta);
-  for (int i = tid; i < (2 * FC_ST_B + NUS * USLOT_B) / 16; i += 320) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = tid; i < WTF_B / 16; i += 320) reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(WtF) + i);
+  for (int i = tid; i < (2 * FC_ST_B + NUS * USLOT_B) / 16; i += FC_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid < NH) { s_bias[tid] = dt_bias[tid]; s_eA[tid] = __expf(A_log[tid]); }
   if (tid == 0) {
     for (int i = 0; i < NUS; ++i) { mbar_init(&full[i], 32); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); mbar_init(&st_full[i], 8); mbar_init(&st_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], FC_EPI_WARPS); mbar_init(&st_full[i], FC_EPI_WARPS); mbar_init(&st_empty[i], 1); }
     mbar_init(&s_done, 1);
-    mbar_init(&s_free, 8);
+    mbar_init(&s_free, FC_EPI_WARPS);
+    mbar_init(&w_full, 1);
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc(&tmem_slot, 512);
+  if (warp == FC_EPI_WARPS + 1) tmem_alloc(&tmem_slot, 512);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -210,15 +261,21 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
   const int gfirst = max(R0 - 1, 0), glast = min(R1, rows_total - 1);
   bool ok = true;
   if (R0 < R1) {
-    if (warp == 8) {
-      urow_producer(sU, u, gfirst, glast, full, empty, lane);
-    } else if (warp == 9) {
+    if (warp == FC_EPI_WARPS) {
+      urow_producer<1, NUS>(sU, u, gfirst, glast, full, empty, lane, u_tl, R0, R1 - 1);
+    } else if (warp == FC_EPI_WARPS + 1) {
       if (elect_one()) {   // one elected lane of the converged warp: tcgen05.mma is emitted without a lane-serialising loop
+        // the weight image arrives by nine bulk copies while the first u rows are in flight
+        mbar_expect_tx(&w_full, WTF_B);
+        for (int t = 0; t < 9; ++t) bulk_g2s(sW + t * WTF_TAP_B, reinterpret_cast<const uint8_t*>(WtF) + t * WTF_TAP_B, WTF_TAP_B, &w_full);
         const uint32_t idesc = make_idesc_rt(128, DIP, false, false), idesc_s = make_idesc_rt(128, GN, true, true);
         const uint32_t ubase = smem_u32(sU), wbase = smem_u32(sW), stbase = smem_u32(sSt);
         const uint64_t dU0 = make_desc(ubase, CHB, 128), dW0 = make_desc(wbase, DIP * 16, 128);
         int next_wait = gfirst, fl = 0;
+        PhaseTimer pt(4, true);
+        ok = mbar_wait(&w_full, 0) && ok;
         for (int R = R0; R <= R1; ++R) {
+          pt.mark(7);
           if (R < R1) {
             const int it = R - R0, acc = it & 1, y = R % H;
             const int need = min(R + 1, glast);
@@ -227,8 +284,10 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
               ok = mbar_wait(&full[i % NUS], (i / NUS) & 1) && ok;
               ++next_wait;
             }
+            pt.mark(0);
             if (it >= 2) ok = mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1) && ok;
             tc_fence_after();
+            pt.mark(1);
             const uint32_t tacc = tbase + acc * DIP;
             if (y > 0 && y < H - 1) {      // interior row: all nine taps, fully unrolled, descriptors = base + constant
               uint64_t dA[3];
@@ -263,11 +322,13 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
             }
             umma_commit(&acc_full[acc]);
             if (R - 1 >= gfirst) umma_commit(&empty[((R - 1) - gfirst) % NUS]);
+            pt.mark(2);
           }
           if (R > R0) {   // state accumulation of the previous row (its epilogue produced w*x and Bc)
             const int Rp = R - 1, it = Rp - R0, sb = it & 1, yp = Rp % H;
             ok = mbar_wait(&st_full[sb], (it >> 1) & 1) && ok;
             tc_fence_after();
+            pt.mark(3);
             const bool first_of_sample = (Rp == R0) || (yp == 0);
             if (first_of_sample && fl > 0) { ok = mbar_wait(&s_free, (fl - 1) & 1) && ok; tc_fence_after(); }
             const uint32_t a0 = stbase + sb * FC_ST_B, b0 = a0 + 8 * 2048;
@@ -277,27 +338,35 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
                    !(first_of_sample && k == 0));
             umma_commit(&st_empty[sb]);
             if ((Rp == R1 - 1) || (yp == H - 1)) { umma_commit(&s_done); ++fl; }
+            pt.mark(4);
           }
         }
         if (!ok) atomicExch(status, 20);
       }
     } else {
-      const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+      const int q = warp & 3, grp = warp >> 2, row = q * 32 + lane;   // column group: 0 = z, 1 = dt + x, 2 = B + C
       int fl = 0;
+      PhaseTimer pt(7, tid == 0 || tid == 128 || tid == 256);
       for (int R = R0; R < R1; ++R) {
         const int it = R - R0, acc = it & 1, y = R % H, b = R / H;
+        pt.mark(7);
         ok = mbar_wait(&acc_full[acc], (it >> 1) & 1) && ok;
+        pt.mark(0);
         if (it >= 2) ok = mbar_wait(&st_empty[acc], ((it >> 1) - 1) & 1) && ok;
         tc_fence_after();
+        pt.mark(1);
         const uint32_t ta = tbase + ((uint32_t)(q * 32) << 16) + acc * DIP;
         bf16* arow = act + ((long long)R * NA * 128 + row) * 8;
         bf16* grow = sgrad ? sgrad + ((long long)R * NA * 128 + row) * 8 : nullptr;
         uint8_t* st = sSt + acc * FC_ST_B + row * 16;
-        if (half == 0) {
+        if (grp == 0) {
 #pragma unroll 1
           for (int cb = 0; cb < DI; cb += 32)
             silu32<0>(ta + cb, arow + (cb >> 3) * 1024, grow ? grow + (cb >> 3) * 1024 : nullptr, nullptr, nullptr);
+        } else if (grp == 2) {
           silu32<1>(ta + 2 * DI, arow + ((2 * DI) >> 3) * 1024, grow ? grow + ((2 * DI) >> 3) * 1024 : nullptr, st + 8 * 2048, nullptr);
+          silu32<0>(ta + 2 * DI + GN, arow + ((2 * DI + GN) >> 3) * 1024, grow ? grow + ((2 * DI + GN) >> 3) * 1024 : nullptr,
+                    nullptr, nullptr);
         } else {
           float w[NH];
           {
@@ -321,18 +390,19 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
           }
           silu32<2>(ta + DI, arow + (DI >> 3) * 1024, grow ? grow + (DI >> 3) * 1024 : nullptr, st, &w[0]);
           silu32<2>(ta + DI + 32, arow + ((DI + 32) >> 3) * 1024, grow ? grow + ((DI + 32) >> 3) * 1024 : nullptr, st + 4 * 2048, &w[8]);
-          silu32<0>(ta + 2 * DI + GN, arow + ((2 * DI + GN) >> 3) * 1024, grow ? grow + ((2 * DI + GN) >> 3) * 1024 : nullptr,
-                    nullptr, nullptr);
         }
+        pt.mark(2 + (grp == 1));
         tc_fence_before();
         fence_async_smem();
         __syncwarp();
         if (lane == 0) { mbar_arrive(&acc_empty[acc]); mbar_arrive(&st_full[acc]); }
+        pt.mark(4);
         if ((R == R1 - 1) || (y == H - 1)) {   // flush the state of sample b accumulated by this CTA
           ok = mbar_wait(&s_done, fl & 1) && ok;
           ++fl;
           tc_fence_after();
-          if (q < 2 && ok) {
+          if (q < 2 && grp < 2 && ok) {
+            const int half = grp;
             float v[16];
             tmem_ld16(tbase + ((uint32_t)(q * 32) << 16) + FC_COL_S + half * 16, v);
             tmem_wait_ld();
@@ -353,7 +423,7 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tbase, 512);
+  if (warp == FC_EPI_WARPS + 1) tmem_dealloc(tbase, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -417,15 +487,19 @@ k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
       const uint32_t idesc = make_idesc_rt(128, D, false, false);
       const uint32_t sbase = smem_u32(sStg), wbase = smem_u32(sW);
       const uint64_t dS0 = make_desc(sbase, CHB, 128), dW0 = make_desc(wbase, 512, 128);
+      PhaseTimer pt(5, true);
       int un = 0;
       for (int R = R0; R < R1; ++R) {
         const int it = R - R0, acc = it & 1, y = R % H;
         bool first = true;
         for (int g = 0; g < 6; ++g, ++un) {
           const int stg = un % DU_NST;
+          pt.mark(7);
           ok = mbar_wait(&full[stg], (un / DU_NST) & 1) && ok;
+          pt.mark(0);
           if (g == 0 && it >= 2) ok = mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1) && ok;
           tc_fence_after();
+          pt.mark(1);
           const uint32_t sb = sbase + stg * DU_STG_B;
           if (y > 0 && y < H - 1) {        // interior row: fully unrolled, descriptors = base + constant
             const uint64_t dA = dadd(dS0, stg * DU_STG_B), dB = dadd(dW0, g * WTB_TG_B);
@@ -460,6 +534,7 @@ k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
           if (g == 0)
             umma(tbase + acc * D, make_desc(sb + 3 * USLOT_B, 2048, 128), make_desc(wbase + 9 * 6 * WTB_TG_B, 512, 128), idesc, true);
           umma_commit(&empty[stg]);
+          pt.mark(2);
         }
         umma_commit(&acc_full[acc]);
       }
@@ -511,14 +586,14 @@ k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
 // ------------------------------------------------------------------------------------------------
 constexpr int WG_NST = 3;
 constexpr int WG_STG_B = 16 * 2048;
-constexpr int WG_SMEM = WG_NST * WG_STG_B + NUS * USLOT_B;
+constexpr int WG_SMEM = WG_NST * WG_STG_B + NUW * USLOT3_B;
 
 __global__ void __launch_bounds__(192, 1)
-k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf16* __restrict__ u,
+k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf16* __restrict__ u /* TL copy of u */,
            const float* __restrict__ Win, const float* __restrict__ Kc, float* __restrict__ dK, float* __restrict__ dWin,
            int H, int rows_total, int rows_per_cta, int ctas_per_block, int* __restrict__ status) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full[NUS], empty[NUS], a_full[WG_NST], a_empty[WG_NST], done;
+  __shared__ uint64_t full[NUW], empty[NUW], a_full[WG_NST], a_empty[WG_NST], done;
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t s_tapmask;
   uint8_t* sA = smem;
@@ -526,11 +601,12 @@ k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mb = blockIdx.x / ctas_per_block, part = blockIdx.x % ctas_per_block;
   const int R0 = part * rows_per_cta, R1 = min(rows_total, R0 + rows_per_cta);
+  PhaseTimer ptc(6, tid == 64);
   for (int i = tid; i < WG_SMEM / 16; i += 192) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
-    for (int i = 0; i < NUS; ++i) { mbar_init(&full[i], 32); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NUW; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < WG_NST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    mbar_init(&done, 1);
+    mbar_init(&done, 2);   // MMA completion (tcgen05.commit) + the issuing thread's release of s_tapmask
     s_tapmask = 0;
     fence_mbar_init();
   }
@@ -540,59 +616,65 @@ k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
+  ptc.mark(5);
   const int gfirst = max(R0 - 1, 0), glast = min(R1, rows_total - 1);
   bool ok = true;
   if (R0 < R1) {
     if (warp == 4) {
-      urow_producer(sU, u, gfirst, glast, full, empty, lane);
+      if (elect_one()) {
+        if (!urow3_bulk_producer<NUW>(sU, u, gfirst, glast, full, empty)) atomicExch(status, 27);
+      }
     } else if (warp == 5) {
       if (elect_one()) {
-        const uint32_t idesc = make_idesc_rt(128, D, true, true);
+        const uint32_t idesc = make_idesc_rt(128, 3 * D, true, true);
         const uint32_t abase = smem_u32(sA), ubase = smem_u32(sU);
         const uint64_t dA0 = make_desc(abase, 128, 2048), dU0 = make_desc(ubase, 128, CHB);
         int next_wait = gfirst;
         uint32_t mask = 0;
+        PhaseTimer pt(6, true);
         for (int R = R0; R < R1; ++R) {
           const int it = R - R0, stg = it % WG_NST, y = R % H;
           const int need = min(R + 1, glast);
+          pt.mark(7);
           while (next_wait <= need) {
             const int i = next_wait - gfirst;
-            ok = mbar_wait(&full[i % NUS], (i / NUS) & 1) && ok;
+            ok = mbar_wait(&full[i % NUW], (i / NUW) & 1) && ok;
             ++next_wait;
           }
+          pt.mark(0);
           ok = mbar_wait(&a_full[stg], (it / WG_NST) & 1) && ok;
           tc_fence_after();
+          pt.mark(1);
           const uint32_t ab = abase + stg * WG_STG_B;
+          // the three horizontal taps of image row y + a - 1 are one B operand with N = 96 (three shifted copies of the u row)
           if (mask == 0x1FFu && y > 0 && y < H - 1) {   // steady state: every tap accumulates, fully unrolled
             const uint64_t dA = dadd(dA0, stg * WG_STG_B);
             uint64_t dB[3];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) dB[a] = dadd(dU0, (uint32_t)(((R + a - 1) - gfirst) % NUS) * USLOT_B);
+            for (int a = 0; a < 3; ++a) dB[a] = dadd(dU0, (uint32_t)(((R + a - 1) - gfirst) % NUW) * USLOT3_B);
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
-              for (int b = 0; b < 3; ++b)
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                  umma_c<true>(tbase + (a * 3 + b) * D, dadd(dA, k * 256), dadd(dB[a], b * 16 + k * 256), idesc);
-          } else
-          for (int a = 0; a < 3; ++a) {
-            if (y + a - 1 < 0 || y + a - 1 >= H) continue;
-            const uint32_t ub = ubase + (uint32_t)(((R + a - 1) - gfirst) % NUS) * USLOT_B;
-            for (int b = 0; b < 3; ++b) {
-              const int t = a * 3 + b;
+              for (int k = 0; k < 8; ++k)
+                umma_c<true>(tbase + a * 3 * D, dadd(dA, k * 256), dadd(dB[a], k * 256), idesc);
+          } else {
+            for (int a = 0; a < 3; ++a) {
+              if (y + a - 1 < 0 || y + a - 1 >= H) continue;
+              const uint32_t ub = ubase + (uint32_t)(((R + a - 1) - gfirst) % NUW) * USLOT3_B;
+              const bool init = ((mask >> (3 * a)) & 1) != 0;
 #pragma unroll
               for (int k = 0; k < 8; ++k)
-                umma(tbase + t * D, make_desc(ab + k * 256, 128, 2048), make_desc(ub + b * 16 + k * 256, 128, CHB), idesc,
-                     ((mask >> t) & 1) != 0 || k > 0);
-              mask |= 1u << t;
+                umma(tbase + a * 3 * D, make_desc(ab + k * 256, 128, 2048), make_desc(ub + k * 256, 128, CHB), idesc, init || k > 0);
+              mask |= 7u << (3 * a);
             }
           }
           umma_commit(&a_empty[stg]);
-          if (R - 1 >= gfirst) umma_commit(&empty[((R - 1) - gfirst) % NUS]);
+          if (R - 1 >= gfirst) umma_commit(&empty[((R - 1) - gfirst) % NUW]);
+          pt.mark(2);
         }
         s_tapmask = mask;
         umma_commit(&done);
+        mbar_arrive(&done);
         if (!ok) atomicExch(status, 25);
       }
     } else {
@@ -612,8 +694,10 @@ k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
         }
       }
       __syncwarp();
+      PhaseTimer pt(6, tid == 32);
       ok = mbar_wait(&done, 0) && ok;
       tc_fence_after();
+      pt.mark(3);
       const uint32_t mask = *reinterpret_cast<volatile uint32_t*>(&s_tapmask);
       const int m = warp * 32 + lane;
       const int c = mb * 128 + m;      // conv channel (mb 1: m < 64), or dt row 192 + (m - 64)
@@ -656,11 +740,13 @@ k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
           for (int d = 0; d < 16; ++d) { atomicAdd(dst + d, v0[d]); atomicAdd(dst + 16 + d, v1[d]); }
         }
       }
+      pt.mark(4);
       if (!ok && lane == 0) atomicExch(status, 26);
     }
   }
   tc_fence_before();
   __syncthreads();
+  ptc.mark(6);
   if (warp == 5) tmem_dealloc(tbase, 512);
 }
 

@@ -26,6 +26,7 @@ struct PhaseTimer {
   int kid;
   bool on;
   __device__ __forceinline__ PhaseTimer(int k) : t(0), kid(k), on(g_phase_on != 0 && threadIdx.x == 0) { if (on) t = clock64(); }
+  __device__ __forceinline__ PhaseTimer(int k, bool mine) : t(0), kid(k), on(g_phase_on != 0 && mine) { if (on) t = clock64(); }
   __device__ __forceinline__ void mark(int ph) {
     if (on) { long long n = clock64(); atomicAdd(&g_phase[kid][ph], (unsigned long long)(n - t)); t = n; }
   }
@@ -33,6 +34,7 @@ struct PhaseTimer {
 #else
 struct PhaseTimer {
   __device__ __forceinline__ PhaseTimer(int) {}
+  __device__ __forceinline__ PhaseTimer(int, bool) {}
   __device__ __forceinline__ void mark(int) {}
 };
 #endif
@@ -1770,12 +1772,14 @@ int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* 
   }
   if (rowconv_supported(d)) {
     // (1)-(4a) fused: in_proj + conv + SiLU + decay weights + state, one image row per step (adnssd_rowconv.cuh).
-    // The `raw` slot of the saved tensors only holds the dt columns, as a TL tensor with 2 chunks per tile.
+    // The `raw` slot of the saved tensors only holds the dt columns, as a TL tensor with 2 chunks per tile, and the `wdec`
+    // slot (T x nh floats = T x D bf16 for headdim 4) holds a TL copy of u for the bulk copies of the backward pass.
+    static_assert(sizeof(float) * rowconv::NH == sizeof(bf16) * rowconv::D, "u_tl does not fit the wdec slot");
     ADN_CHECK_CUDA(cudaMemsetAsync(S.S, 0, (size_t)d.B * d.GN * d.Di * sizeof(float), st));
     int rc = set_smem(rowconv::k_fconv, rowconv::FC_SMEM);
     if (rc) return rc;
     const int rows_total = d.B * d.H, per = cdiv(rows_total, 148), grid = cdiv(rows_total, per);
-    { ADN_KERNEL("k_fconv", st); rowconv::k_fconv<<<grid, 320, rowconv::FC_SMEM, st>>>(u, P.WtF, w.dt_bias, w.A_log, S.act, training ? S.pre : nullptr, S.raw, S.S, d.H, rows_total, per, F.status); }
+    { ADN_KERNEL("k_fconv", st); rowconv::k_fconv<<<grid, rowconv::FC_THREADS, rowconv::FC_SMEM, st>>>(u, P.WtF, w.dt_bias, w.A_log, S.act, training ? S.pre : nullptr, S.raw, S.S, d.H, rows_total, per, F.status, training ? reinterpret_cast<bf16*>(S.wdec) : nullptr); }
     rc = launch_readout<64, 32>(d, S.act, S.S, w, P.Wout, out, F.status, st);
     if (rc) return rc;
     ADN_CHECK_LAUNCH();
@@ -1831,7 +1835,7 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
       rc = set_smem(rowconv::k_bconv_wg, rowconv::WG_SMEM);
       if (rc) return rc;
       const int cpb = max(1, min(74, rows_total)), per = cdiv(rows_total, cpb), parts = cdiv(rows_total, per);
-      { ADN_KERNEL("k_bconv_wg", st); rowconv::k_bconv_wg<<<2 * parts, 192, rowconv::WG_SMEM, st>>>(W.dact, W.draw, u, w.in_proj_w, P.Kc, W.acc.dK, W.acc.dWin, d.H, rows_total, per, parts, F.status); }
+      { ADN_KERNEL("k_bconv_wg", st); rowconv::k_bconv_wg<<<2 * parts, 192, rowconv::WG_SMEM, st>>>(W.dact, W.draw, reinterpret_cast<const bf16*>(S.wdec), w.in_proj_w, P.Kc, W.acc.dK, W.acc.dWin, d.H, rows_total, per, parts, F.status); }
     }
     W.acc.dWin_part = nullptr;
     W.acc.dWin_parts = 0;

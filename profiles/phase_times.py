@@ -17,8 +17,12 @@ m(u, 128, 128).backward(go)
 buf = (C.c_ulonglong * 64)()
 lib.adn_phase_read(buf)
 lib.adn_phase_enable(0)
-names = {0: "k_bwd1", 1: "k_bwd2", 2: "k_bwd4", 3: "k_conv_bwd_tile"}
+names = {0: "k_bwd1", 1: "k_bwd2", 2: "k_bwd4", 3: "k_conv_bwd_tile",
+         4: "k_fconv MMA thread [wait u | wait acc_empty | issue conv | wait st_full | issue state | . | . | loop]",
+         5: "k_bconv_du MMA thread [wait stage | wait acc_empty | issue | . | . | . | . | loop]",
+         6: "k_bconv_wg MMA thread [wait u | wait A | issue | (epi) wait done | (epi) contract+atomics | CTA prologue | CTA body | loop]",
+         7: "k_fconv epilogue t0+t128 [wait acc_full | wait st_empty | compute half0 | compute half1 | release | . | . | loop]"}
 for k, n in names.items():
     row = [buf[k * 8 + i] for i in range(8)]
     tot = sum(row) or 1
-    print(n, "total Mcycles(thread0 sum)", round(tot / 1e6, 2), [f"{100 * v / tot:.0f}%" for v in row])
+    print(n, "total Mcycles(thread0 sum)", round(tot / 1e6, 2), [f"{100 * v / tot:.0f}%" for v in row], "kcycles/CTA(148):", [round(v / 148e3, 1) for v in row])
