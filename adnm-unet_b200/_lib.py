@@ -63,6 +63,7 @@ EXPORTS = {
     "adn_prof_get": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
     "adn_phase_enable": (C.c_int, [C.c_int]),
     "adn_phase_read": (C.c_int, [C.POINTER(C.c_ulonglong)]),
+    "adn_cta_times_read": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "adn_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "adn_selftest_umma_shift": (C.c_int, [C.c_int] * 6 + [C.c_void_p] * 5),
     "adn_bench_umma": (C.c_int, [C.c_int] * 6 + [C.c_void_p] * 2),

@@ -78,7 +78,7 @@ __device__ __forceinline__ float conv_tap(const ConvWeightPtrs& w, int Di, int c
 
 // Weight images of the conv-as-GEMM kernels (one thread per element, called from k_prep):
 //   WtF[t] : K-major B operand [N = 208][K = 32] of the forward GEMM; rows >= 192 (dt) are W_in for the centre tap, else 0
-//   WtB[t][g] : K-major B operand [N = 32 (d)][K = 32 channels of group g] of the du GEMM, then W_dt^T [N = 32][K = 16]
+//   WtB[a][g] : K-major B operand [N = 96 (b, d)][K = 32 channels of group g] of the du GEMM (k_bconv_du), then W_dt^T [N = 32][K = 16]
 __device__ __forceinline__ void prep_rowconv(const ConvWeightPtrs& cw, const float* __restrict__ win, bf16* __restrict__ wtf,
                                              bf16* __restrict__ wtb, int i) {
   if (i < 9 * DIP * D) {
@@ -89,10 +89,10 @@ __device__ __forceinline__ void prep_rowconv(const ConvWeightPtrs& cw, const flo
     else v = t == 4 ? win[n * D + d] : 0.f;
     wtf[i] = __float2bfloat16_rn(v);
   }
-  if (i < 9 * 6 * 1024) {
-    const int tg = i >> 10, rem = i & 1023, t = tg / 6, g = tg % 6;
-    const int c = g * 32 + (rem >> 8) * 8 + (rem & 7), d = (rem >> 3) & 31;
-    wtb[i] = __float2bfloat16_rn(conv_tap(cw, DI, c, t) * win[c * D + d]);
+  if (i < 18 * 3072) {        // (a, g) image: [4 chunks of channels][96 rows n = b*32 + d][8]
+    const int ag = i / 3072, rem = i % 3072, a = ag / 6, g = ag % 6;
+    const int n = (rem >> 3) % 96, b = n >> 5, d = n & 31, c = g * 32 + (rem / 768) * 8 + (rem & 7);
+    wtb[i] = __float2bfloat16_rn(conv_tap(cw, DI, c, a * 3 + b) * win[c * D + d]);
   } else if (i < 9 * 6 * 1024 + 512) {
     const int e = i - 9 * 6 * 1024, j = (e >> 8) * 8 + (e & 7), d = (e >> 3) & 31;
     wtb[i] = __float2bfloat16_rn(win[(CC + j) * D + d]);
@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1)
 k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* __restrict__ dt_bias,
         const float* __restrict__ A_log, bf16* __restrict__ act, bf16* __restrict__ sgrad, bf16* __restrict__ dtraw,
         float* __restrict__ S, int H, int rows_total, int rows_per_cta, int* __restrict__ status, bf16* __restrict__ u_tl) {
+  ADN_CTA_STAMP(0, 0);
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[NUS], empty[NUS], acc_full[2], acc_empty[2], st_full[2], st_empty[2], s_done, s_free, w_full;
   __shared__ uint32_t tmem_slot;
@@ -258,6 +259,7 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
+  ADN_CTA_STAMP(0, 2);
   const int gfirst = max(R0 - 1, 0), glast = min(R1, rows_total - 1);
   bool ok = true;
   if (R0 < R1) {
@@ -341,6 +343,7 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
             pt.mark(4);
           }
         }
+        ADN_CTA_STAMP_ANY(0, 3);
         if (!ok) atomicExch(status, 20);
       }
     } else {
@@ -423,158 +426,197 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
   }
   tc_fence_before();
   __syncthreads();
+  ADN_CTA_STAMP(0, 1);
   if (warp == FC_EPI_WARPS + 1) tmem_dealloc(tbase, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_bconv_du: du[q] = sum_t dpre[q - d_t] . Wt[t] + ddt[q] . W_dt     (backward-data of in_proj o conv, one image row per
-// accumulator).  Work unit = (row, 32-channel group): the three dpre rows y-1, y, y+1 of the group are bulk-copied into a
-// padded stage (12 copies of 2 KB), then 9 taps x 2 K-steps of 128x32x16 MMAs accumulate into the row's 32 TMEM columns.
-//   warps 0-3 epilogue (du row-major store), warp 4 lane 0 bulk-copy producer, warp 5 lane 0 MMA issue.
+// k_bconv_du: du[q] = sum_t dpre[q - d_t] . Wt[t] + ddt[q] . W_dt     (backward-data of in_proj o conv).
+// The horizontal shift is moved to the OUTPUT side so that every MMA has N = 96 and unshifted, unpadded operands:
+//     Z_b[y][x'][d] = sum_a sum_c dpre[y - (a-1)][x'][c] * Wt[a,b][c][d]        (N = 96 = (b, d), K = 3 rows x 192 channels)
+//     du[y][x]      = Z_0[y][x+1] + Z_1[y][x] + Z_2[y][x-1]                     (zero outside the row)
+// (a 128x32x16 MMA costs the same ~46 cycles of shared-memory operand traffic as a 128x96x16 one, profiles/umma_issue_rate.py).
+// The CTA streams the dpre rows of its range ONCE, in (row, 32-channel group) units of one 8 KB bulk copy; input row r feeds
+// the accumulators of output rows r-1, r, r+1, which live in a ring of four 96-column TMEM slots.  The epilogue adds the
+// three shifted pieces with warp shuffles (+ a 256-byte exchange between neighbouring warps) and stores du row-major.
+//   warps 0-3 epilogue, warp 4: elected bulk-copy producer, warp 5: elected MMA issuer.
 // ------------------------------------------------------------------------------------------------
-constexpr int DU_NST = 3;
-constexpr int DU_STG_B = 3 * USLOT_B + 4096;      // 3 padded row slots of one group + the ddt tile [2 chunks][128][8]
-constexpr int DU_SMEM = DU_NST * DU_STG_B + WTB_B;
+constexpr int DU_NST = 8;
+constexpr int DU_STG_B = 8192 + 4096;             // one (row, group) tile [4 chunks][128][8] + the row's ddt tile (group 0 only)
+constexpr int WTZ_AG_B = 4 * 96 * 16;             // B operand of one (vertical tap a, group g): [4 chunks][96 (b,d)][8] bf16
+constexpr int DU_SMEM = DU_NST * DU_STG_B + WTB_B + (2 * 4 + 1) * 64 * 4;   // + exchange rows [parity][warp][64] and one zero row
+static_assert(18 * WTZ_AG_B + 1024 == WTB_B, "weight image size");
 
 __global__ void __launch_bounds__(192, 1)
-k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf16* __restrict__ WtB, bf16* __restrict__ du,
-           int H, int rows_total, int rows_per_cta, int* __restrict__ status) {
+k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf16* __restrict__ WtZ, bf16* __restrict__ du,
+           int H, int rows_total, int rows_per_cta, int* __restrict__ status, int dbg) {
+  // dbg (diagnostics, ADN_DU_DBG): 1 = no loads, 2 = no MMAs, 4 = no du stores; results are then meaningless
+  ADN_CTA_STAMP(1, 0);
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full[DU_NST], empty[DU_NST], acc_full[2], acc_empty[2];
+  __shared__ uint64_t full[DU_NST], empty[DU_NST], slot_full[4], slot_empty[4];
   __shared__ uint32_t tmem_slot;
   uint8_t* sStg = smem;
   uint8_t* sW = smem + DU_NST * DU_STG_B;
+  float* sX = reinterpret_cast<float*>(sW + WTB_B);      // [parity][warp][0: lane 0's Z_0, 1: lane 31's Z_2][32 d]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R0 = blockIdx.x * rows_per_cta, R1 = min(rows_total, R0 + rows_per_cta);
-  for (int i = tid; i < DU_NST * DU_STG_B / 16; i += 192) reinterpret_cast<uint4*>(sStg)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = tid; i < WTB_B / 16; i += 192) reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(WtB) + i);
+  for (int i = tid; i < WTB_B / 16; i += 192) reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(WtZ) + i);
+  if (tid < 64) sX[8 * 64 + tid] = 0.f;
   if (tid == 0) {
     for (int i = 0; i < DU_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 4); }
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(&tmem_slot, 64);
+  if (warp == 5) tmem_alloc(&tmem_slot, 512);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
+  ADN_CTA_STAMP(1, 2);
   bool ok = true;
-  if (warp == 4) {
-    if (elect_one()) {
-      int un = 0;
-      for (int R = R0; R < R1; ++R) {
-        const int y = R % H;
-        for (int g = 0; g < 6; ++g, ++un) {
-          const int stg = un % DU_NST;
-          if (un >= DU_NST) ok = mbar_wait(&empty[stg], ((un / DU_NST) - 1) & 1) && ok;
-          uint8_t* sb = sStg + stg * DU_STG_B;
-          const int nrows = 1 + (y > 0 ? 1 : 0) + (y < H - 1 ? 1 : 0);
-          mbar_expect_tx(&full[stg], (uint32_t)nrows * 4 * 2048 + (g == 0 ? 4096u : 0u));
-          for (int e = -1; e <= 1; ++e) {
-            if (y + e < 0 || y + e >= H) continue;
-            const bf16* src = dpre + ((long long)(R + e) * NA + g * 4) * 1024;
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) bulk_g2s(sb + (e + 1) * USLOT_B + ch * CHB + 16, src + ch * 1024, 2048, &full[stg]);
+  if (R0 < R1) {
+    // input rows: the range plus one halo row on each side when that row belongs to the same sample
+    const int rin0 = (R0 % H) > 0 ? R0 - 1 : R0, rin1 = ((R1 - 1) % H) < H - 1 ? R1 : R1 - 1;
+    if (warp == 4) {
+      if (elect_one()) {
+        int un = 0;
+        PhaseTimer pp(2, true);
+        for (int r = rin0; r <= rin1; ++r) {
+          for (int g = 0; g < 6; ++g, ++un) {
+            const int stg = un % DU_NST;
+            pp.mark(1);
+            if (un >= DU_NST) ok = mbar_wait(&empty[stg], ((un / DU_NST) - 1) & 1) && ok;
+            pp.mark(0);
+            uint8_t* sb = sStg + stg * DU_STG_B;
+            const bool dt = g == 0 && r >= R0 && r < R1;
+            if (dbg & 1) { mbar_arrive(&full[stg]); continue; }
+            mbar_expect_tx(&full[stg], 8192u + (dt ? 4096u : 0u));
+            bulk_g2s(sb, dpre + ((long long)r * NA + g * 4) * 1024, 8192, &full[stg]);
+            if (dt) bulk_g2s(sb + 8192, ddt + (long long)r * 2 * 1024, 4096, &full[stg]);
           }
-          if (g == 0) bulk_g2s(sb + 3 * USLOT_B, ddt + (long long)R * 2 * 1024, 4096, &full[stg]);
         }
+        if (!ok) atomicExch(status, 22);
       }
-      if (!ok) atomicExch(status, 22);
-    }
-  } else if (warp == 5) {
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_rt(128, D, false, false);
-      const uint32_t sbase = smem_u32(sStg), wbase = smem_u32(sW);
-      const uint64_t dS0 = make_desc(sbase, CHB, 128), dW0 = make_desc(wbase, 512, 128);
-      PhaseTimer pt(5, true);
-      int un = 0;
-      for (int R = R0; R < R1; ++R) {
-        const int it = R - R0, acc = it & 1, y = R % H;
-        bool first = true;
-        for (int g = 0; g < 6; ++g, ++un) {
-          const int stg = un % DU_NST;
-          pt.mark(7);
-          ok = mbar_wait(&full[stg], (un / DU_NST) & 1) && ok;
-          pt.mark(0);
-          if (g == 0 && it >= 2) ok = mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1) && ok;
-          tc_fence_after();
-          pt.mark(1);
-          const uint32_t sb = sbase + stg * DU_STG_B;
-          if (y > 0 && y < H - 1) {        // interior row: fully unrolled, descriptors = base + constant
-            const uint64_t dA = dadd(dS0, stg * DU_STG_B), dB = dadd(dW0, g * WTB_TG_B);
-            const uint32_t tacc = tbase + acc * D;
+    } else if (warp == 5) {
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc_rt(128, 3 * D, false, false), idesc_dt = make_idesc_rt(128, D, false, false);
+        const uint32_t sbase = smem_u32(sStg), wbase = smem_u32(sW);
+        const uint64_t dS0 = make_desc(sbase, 2048, 128), dW0 = make_desc(wbase, 96 * 16, 128);
+        const uint64_t dWdt = make_desc(wbase + 18 * WTZ_AG_B, 512, 128);
+        PhaseTimer pt(5, true);
+        int un = 0;
+        for (int r = rin0; r <= rin1; ++r) {
+          const int y = r % H;
+          for (int g = 0; g < 6; ++g, ++un) {
+            const int stg = un % DU_NST;
+            pt.mark(7);
+            ok = mbar_wait(&full[stg], (un / DU_NST) & 1) && ok;
+            pt.mark(0);
+            const uint64_t dA = dadd(dS0, stg * DU_STG_B);
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-              for (int b = 0; b < 3; ++b)
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  const uint64_t da = dadd(dA, (2 - a) * USLOT_B + (2 - b) * 16 + ks * 2 * CHB);
-                  const uint64_t db = dadd(dB, (a * 3 + b) * 6 * WTB_TG_B + ks * 2 * 512);
-                  if (a == 0 && b == 0 && ks == 0) umma(tacc, da, db, idesc, g != 0);
-                  else umma_c<true>(tacc, da, db, idesc);
-                }
-            first = false;
-          } else {
             for (int a = 0; a < 3; ++a) {
-              const int e = 1 - a;          // source image row y + e
-              if (y + e < 0 || y + e >= H) continue;
-              for (int b = 0; b < 3; ++b) {
+              const int rout = r + a - 1, yout = y + a - 1;
+              if (yout < 0 || yout >= H || rout < R0 || rout >= R1) continue;
+              const int k = rout - R0;
+              const uint32_t tacc = tbase + (k & 3) * 96;
+              // the first contribution to an output row comes from the input row above it (a == 2), or from the row itself at
+              // the top edge of the image
+              const bool init = g == 0 && r == (yout > 0 ? rout - 1 : rout);
+              if (init && k >= 4) { ok = mbar_wait(&slot_empty[k & 3], ((k >> 2) - 1) & 1) && ok; }
+              tc_fence_after();
+              const uint64_t dB = dadd(dW0, (a * 6 + g) * WTZ_AG_B);
+              if (dbg & 2) continue;
+              umma(tacc, dA, dB, idesc, !init);
+              umma_c<true>(tacc, dadd(dA, 2 * 2048), dadd(dB, 2 * 96 * 16), idesc);
+            }
+            if (g == 0 && r >= R0 && r < R1 && !(dbg & 2))      // ddt . W_dt lands in the unshifted piece Z_1 of the row's own accumulator
+              umma_c<true>(tbase + ((r - R0) & 3) * 96 + D, dadd(dA, 8192), dWdt, idesc_dt);
+            umma_commit(&empty[stg]);
+            pt.mark(2);
+          }
+          if (y > 0 && r - 1 >= R0) umma_commit(&slot_full[(r - 1 - R0) & 3]);
+          if (y == H - 1 && r < R1) umma_commit(&slot_full[(r - R0) & 3]);
+        }
+        ADN_CTA_STAMP_ANY(1, 3);
+        if (!ok) atomicExch(status, 23);
+      }
+    } else {
+      const int x = warp * 32 + lane;
+      PhaseTimer pe(3, tid == 0);
+      for (int r = R0; r < R1; ++r) {
+        const int k = r - R0, par = k & 1;
+        pe.mark(7);
+        ok = mbar_wait(&slot_full[k & 3], (k >> 2) & 1) && ok;
+        tc_fence_after();
+        pe.mark(0);
+        const uint32_t ta = tbase + ((uint32_t)(warp * 32) << 16) + (k & 3) * 96;
+        float z[6][16];
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  const uint64_t da = make_desc(sb + (e + 1) * USLOT_B + (2 - b) * 16 + ks * 2 * CHB, CHB, 128);
-                  const uint64_t db = make_desc(wbase + ((a * 3 + b) * 6 + g) * WTB_TG_B + ks * 2 * 512, 512, 128);
-                  umma(tbase + acc * D, da, db, idesc, !first);
-                  first = false;
-                }
-              }
+        for (int i = 0; i < 6; ++i) tmem_ld16(ta + i * 16, z[i]);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slot_empty[k & 3]);
+        // neighbour exchange across warp boundaries, branch-free: lane 0 publishes its Z_0 row, lane 31 its Z_2 row (vector
+        // stores); after the barrier EVERY lane loads the two candidate rows (broadcast reads) and keeps them only where the
+        // shuffle has no source lane.  Warp 3 / warp 0 read the permanently-zero row instead (image border).
+        float* xw = sX + (par * 4 + warp) * 64;
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            *reinterpret_cast<float4*>(xw + j) = make_float4(z[0][j], z[0][j + 1], z[0][j + 2], z[0][j + 3]);
+            *reinterpret_cast<float4*>(xw + 16 + j) = make_float4(z[1][j], z[1][j + 1], z[1][j + 2], z[1][j + 3]);
+          }
+        }
+        if (lane == 31) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            *reinterpret_cast<float4*>(xw + 32 + j) = make_float4(z[4][j], z[4][j + 1], z[4][j + 2], z[4][j + 3]);
+            *reinterpret_cast<float4*>(xw + 48 + j) = make_float4(z[5][j], z[5][j + 1], z[5][j + 2], z[5][j + 3]);
+          }
+        }
+        pe.mark(1);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        pe.mark(2);
+        const float* xn = warp < 3 ? sX + (par * 4 + warp + 1) * 64 : sX + 8 * 64;        // next warp's lane 0: Z_0[x + 1]
+        const float* xp = warp > 0 ? sX + (par * 4 + warp - 1) * 64 + 32 : sX + 8 * 64;   // previous warp's lane 31: Z_2[x - 1]
+        const bool hi = lane == 31, lo = lane == 0;
+        float o[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j4 = 0; j4 < 16; j4 += 4) {
+            const float4 e0 = *reinterpret_cast<const float4*>(xn + h * 16 + j4);
+            const float4 e2 = *reinterpret_cast<const float4*>(xp + h * 16 + j4);
+            const float e0v[4] = {e0.x, e0.y, e0.z, e0.w}, e2v[4] = {e2.x, e2.y, e2.z, e2.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int j = j4 + q;
+              const float s0 = __shfl_down_sync(0xffffffffu, z[h][j], 1);
+              const float s2 = __shfl_up_sync(0xffffffffu, z[4 + h][j], 1);
+              o[h * 16 + j] = z[2 + h][j] + (hi ? e0v[q] : s0) + (lo ? e2v[q] : s2);
             }
           }
-          if (g == 0)
-            umma(tbase + acc * D, make_desc(sb + 3 * USLOT_B, 2048, 128), make_desc(wbase + 9 * 6 * WTB_TG_B, 512, 128), idesc, true);
-          umma_commit(&empty[stg]);
-          pt.mark(2);
+        if (ok && !(dbg & 4)) {
+          bf16* dst = du + ((long long)r * 128 + x) * D;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v8[j] = o[q * 8 + j];
+            *reinterpret_cast<uint4*>(dst + q * 8) = pack8(v8);
+          }
         }
-        umma_commit(&acc_full[acc]);
+        pe.mark(3);
       }
-      if (!ok) atomicExch(status, 23);
+      if (!ok && lane == 0) atomicExch(status, 24);
     }
-  } else {
-    const int row = warp * 32 + lane;
-    for (int R = R0; R < R1; ++R) {
-      const int it = R - R0, acc = it & 1;
-      ok = mbar_wait(&acc_full[acc], (it >> 1) & 1) && ok;
-      tc_fence_after();
-      float v0[16], v1[16];
-      tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + acc * D, v0);
-      tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + acc * D + 16, v1);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (ok) {
-        float o[8];
-        bf16* dst = du + ((long long)R * 128 + row) * D;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = v0[j];
-        *reinterpret_cast<uint4*>(dst) = pack8(o);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = v0[8 + j];
-        *reinterpret_cast<uint4*>(dst + 8) = pack8(o);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = v1[j];
-        *reinterpret_cast<uint4*>(dst + 16) = pack8(o);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = v1[8 + j];
-        *reinterpret_cast<uint4*>(dst + 24) = pack8(o);
-      }
-    }
-    if (!ok && lane == 0) atomicExch(status, 24);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tbase, 64);
+  ADN_CTA_STAMP(1, 1);
+  if (warp == 5) tmem_dealloc(tbase, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -592,6 +634,7 @@ __global__ void __launch_bounds__(192, 1)
 k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf16* __restrict__ u /* TL copy of u */,
            const float* __restrict__ Win, const float* __restrict__ Kc, float* __restrict__ dK, float* __restrict__ dWin,
            int H, int rows_total, int rows_per_cta, int ctas_per_block, int* __restrict__ status) {
+  ADN_CTA_STAMP(2, 0);
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[NUW], empty[NUW], a_full[WG_NST], a_empty[WG_NST], done;
   __shared__ uint32_t tmem_slot;
@@ -616,6 +659,7 @@ k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
+  ADN_CTA_STAMP(2, 2);
   ptc.mark(5);
   const int gfirst = max(R0 - 1, 0), glast = min(R1, rows_total - 1);
   bool ok = true;
@@ -675,6 +719,7 @@ k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
         s_tapmask = mask;
         umma_commit(&done);
         mbar_arrive(&done);
+        ADN_CTA_STAMP_ANY(2, 3);
         if (!ok) atomicExch(status, 25);
       }
     } else {
@@ -747,6 +792,7 @@ k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
   tc_fence_before();
   __syncthreads();
   ptc.mark(6);
+  ADN_CTA_STAMP(2, 1);
   if (warp == 5) tmem_dealloc(tbase, 512);
 }
 

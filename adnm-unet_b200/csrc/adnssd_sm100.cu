@@ -20,6 +20,16 @@ typedef bf16 TWf;   // workspace intermediates of the fast path are bf16 (tensor
 // between consecutive PHASE marks into g_phase[kernel][phase]; disabled (one predicated branch per mark) by default.
 __device__ unsigned long long g_phase[8][8];
 __device__ int g_phase_on = 0;
+// per-CTA start / end times (globaltimer, ns) of the row kernels: [kernel 0 k_fconv, 1 k_bconv_du, 2 k_bconv_wg][CTA][2]
+__device__ unsigned long long g_cta_t[3][160][4];
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#ifdef ADN_PHASE_TIMING
+#define ADN_CTA_STAMP(kid, which) do { if (g_phase_on != 0 && threadIdx.x == 0 && blockIdx.x < 160) g_cta_t[kid][blockIdx.x][which] = gtime_ns(); } while (0)
+#define ADN_CTA_STAMP_ANY(kid, which) do { if (g_phase_on != 0 && blockIdx.x < 160) g_cta_t[kid][blockIdx.x][which] = gtime_ns(); } while (0)
+#else
+#define ADN_CTA_STAMP(kid, which) do { } while (0)
+#define ADN_CTA_STAMP_ANY(kid, which) do { } while (0)
+#endif
 #ifdef ADN_PHASE_TIMING     // build with -DADN_PHASE_TIMING (python -m adnm_unet_b200.build --phase-timing); costs registers
 struct PhaseTimer {
   long long t;
@@ -1644,6 +1654,13 @@ struct FastWs {           // placed after the generic workspace of the same pass
 };
 
 // shapes served by the conv-as-GEMM row kernels: the full-resolution refiner mixers at 128-token-wide grids
+// rows per CTA of the row kernels: one CTA per SM by default; ADN_ROWS_PER_CTA overrides (diagnostics)
+static int rows_per_cta(int rows_total, int ctas) {
+  const char* e = getenv("ADN_ROWS_PER_CTA");
+  if (e && atoi(e) > 0) return atoi(e);
+  return cdiv(rows_total, ctas);
+}
+
 static bool rowconv_supported(const MixerDims& d) {
   const char* e = getenv("ADN_ROWCONV");      // diagnostics: ADN_ROWCONV=0 keeps these shapes on the tile kernels
   if (e && e[0] == '0') return false;
@@ -1778,7 +1795,7 @@ int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* 
     ADN_CHECK_CUDA(cudaMemsetAsync(S.S, 0, (size_t)d.B * d.GN * d.Di * sizeof(float), st));
     int rc = set_smem(rowconv::k_fconv, rowconv::FC_SMEM);
     if (rc) return rc;
-    const int rows_total = d.B * d.H, per = cdiv(rows_total, 148), grid = cdiv(rows_total, per);
+    const int rows_total = d.B * d.H, per = rows_per_cta(rows_total, 148), grid = cdiv(rows_total, per);
     { ADN_KERNEL("k_fconv", st); rowconv::k_fconv<<<grid, rowconv::FC_THREADS, rowconv::FC_SMEM, st>>>(u, P.WtF, w.dt_bias, w.A_log, S.act, training ? S.pre : nullptr, S.raw, S.S, d.H, rows_total, per, F.status, training ? reinterpret_cast<bf16*>(S.wdec) : nullptr); }
     rc = launch_readout<64, 32>(d, S.act, S.S, w, P.Wout, out, F.status, st);
     if (rc) return rc;
@@ -1828,8 +1845,8 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
     {
       rc = set_smem(rowconv::k_bconv_du, rowconv::DU_SMEM);
       if (rc) return rc;
-      const int per = cdiv(rows_total, 148), grid = cdiv(rows_total, per);
-      { ADN_KERNEL("k_bconv_du", st); rowconv::k_bconv_du<<<grid, 192, rowconv::DU_SMEM, st>>>(W.dact, W.draw, P.WtB, du, d.H, rows_total, per, F.status); }
+      const int per = rows_per_cta(rows_total, 148), grid = cdiv(rows_total, per);
+      { ADN_KERNEL("k_bconv_du", st); rowconv::k_bconv_du<<<grid, 192, rowconv::DU_SMEM, st>>>(W.dact, W.draw, P.WtB, du, d.H, rows_total, per, F.status, getenv("ADN_DU_DBG") ? atoi(getenv("ADN_DU_DBG")) : 0); }
     }
     {
       rc = set_smem(rowconv::k_bconv_wg, rowconv::WG_SMEM);
@@ -1882,6 +1899,13 @@ extern "C" int adn_phase_enable(int on) {
   unsigned long long zero[64] = {0};
   ADN_CHECK_CUDA(cudaMemcpyToSymbol(g_phase, zero, sizeof(zero)));
   ADN_CHECK_CUDA(cudaMemcpyToSymbol(g_phase_on, &on, sizeof(int)));
+  return ADN_OK;
+}
+extern "C" int adn_cta_times_read(unsigned long long* out960) {
+  using namespace adn;
+  ADN_REQUIRE(out960 != nullptr, ADN_ERR_NULL, "adn_cta_times_read: NULL");
+  ADN_CHECK_CUDA(cudaDeviceSynchronize());
+  ADN_CHECK_CUDA(cudaMemcpyFromSymbol(out960, g_cta_t, 3 * 160 * 4 * sizeof(unsigned long long)));
   return ADN_OK;
 }
 extern "C" int adn_phase_read(unsigned long long* out64) {

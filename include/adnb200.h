@@ -167,6 +167,9 @@ int adn_prof_get(int i, const char** name, float* ms);
  * (synchronises the device).  Kernel ids: 0 k_bwd1, 1 k_bwd2, 2 k_bwd4, 3 k_conv_bwd_tile. */
 int adn_phase_enable(int on);
 int adn_phase_read(unsigned long long* out64);
+/* Per-CTA start / end times (GPU globaltimer, ns) of the row kernels of the last armed step, HOST buffer of 3 x 160 x 4
+ * values [kernel: 0 k_fconv, 1 k_bconv_du, 2 k_bconv_wg][CTA][start, end, after prologue, MMA loop end]; only filled by -DADN_PHASE_TIMING builds. */
+int adn_cta_times_read(unsigned long long* out1920);
 /* Hardware self-test of the tcgen05 building blocks (one 128 x N x K bf16 GEMM through shared-memory descriptors
  * and TMEM).  mode 0: A[128][K], B[N][K] (K-major operands); mode 1: A[K][128], B[K][N] (MN-major operands).
  * C is float[128][N]; *status (device int) is set to 1 if the MMA completion barrier timed out. */
