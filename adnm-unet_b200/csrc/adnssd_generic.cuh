@@ -535,7 +535,18 @@ struct GradAcc {
   // finalize adds dWin_parts slabs of dip*D floats starting at dWin_part to dWin
   const float* dWin_part;
   int dWin_parts;
+  // optional per-CTA partial sums of dK (k_bconv_wg): dK_parts slabs of CC*9 floats; dK itself is then unused
+  const float* dK_part;
+  int dK_parts, dK_stride;
+  int* sync_counter;   // zeroed with the accumulators; grid-level hand-off inside k_finalize_fast
 };
+
+__device__ __forceinline__ float dk_at(const GradAcc& a, int idx) {
+  if (a.dK_parts == 0) return a.dK[idx];
+  float v = 0.f;
+  for (int p = 0; p < a.dK_parts; ++p) v += a.dK_part[(long long)p * a.dK_stride + idx];
+  return v;
+}
 
 // `proj` = also emit in_proj / out_proj / norm / alpha1 gradients from the accumulators (the tcgen05 path produces those
 // in its own fused finalize and passes proj = false)
@@ -563,17 +574,19 @@ __device__ __forceinline__ void finalize_body(const GradAcc& a, const AdnWeights
     if (g.dt_bias) g.dt_bias[i] = a.ddtb[i];
   }
   if (g.conv2d_z_w)
-    for (long long i = i0; i < (long long)Di * 9; i += stride) g.conv2d_z_w[i] = a.dK[i];
+    for (long long i = i0; i < (long long)Di * 9; i += stride) g.conv2d_z_w[i] = dk_at(a, (int)i);
   const int Wd = Di + 2 * GN;
   if (g.conv2d_w)
     for (long long i = i0; i < (long long)(Wd / 2) * 9; i += stride)
-      g.conv2d_w[i] = a.dK[(Di + 2 * (i / 9)) * 9 + (i % 9)];
+      g.conv2d_w[i] = dk_at(a, (int)((Di + 2 * (i / 9)) * 9 + (i % 9)));
   // pairs: index space (tag in {0,1}) x (Wd/4 groups) x 3 taps
   const int ng = Wd / 4, nx = Di / 4;
   for (long long i = i0; i < 2LL * ng * 3; i += stride) {
     int tap = (int)(i % 3), gi = (int)((i / 3) % ng), tag = (int)(i / (3 * ng));
     int ch = Di + 4 * gi + (tag == 0 ? 1 : 3);
-    const float* dk = a.dK + ch * 9;
+    float dk[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) dk[q] = dk_at(a, ch * 9 + q);
     const float *w31, *w13;
     float *g31, *g13;
     if (gi < nx) {
@@ -670,6 +683,9 @@ struct BwdWs {
     acc.dWin = c.take<float>((size_t)d.dip * d.D);
     acc.dWin_part = nullptr;
     acc.dWin_parts = 0;
+    acc.dK_part = nullptr;
+    acc.dK_parts = 0;
+    acc.dK_stride = 0;
     acc.dWout = c.take<float>((size_t)d.D * 2 * d.Di);
     acc.dgamma = c.take<float>(d.Di);
     acc.dbeta = c.take<float>(d.Di);
@@ -678,6 +694,7 @@ struct BwdWs {
     acc.ddtb = c.take<float>(d.nh);
     acc.dalpha1 = c.take<float>(1);
     acc.dK = c.take<float>((size_t)d.CC * 9);
+    acc.sync_counter = c.take<int>(64);
     dS = c.take<float>((size_t)d.B * d.GN * d.Di);
     zero_bytes = c.off - z0;
     g = c.take<TW>((size_t)d.T * 2 * d.Di);

@@ -621,8 +621,8 @@ k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
 
 // ------------------------------------------------------------------------------------------------
 // k_bconv_wg: M_t[c][d] = sum_p dpre[p][c] * u[p + d_t][d] for the 128-channel block mb of this CTA, nine 32-column TMEM
-// accumulators kept for the CTA's whole row range; the epilogue contracts them into dK and dW_in (fp32 atomics, one per
-// output element per CTA).   mb 0: channels 0..127 (z, x).   mb 1: channels 128..191 (B, C) + the 16 dt rows (their
+// accumulators kept for the CTA's whole row range; the epilogue contracts them into per-CTA slabs of dK and dW_in partial
+// sums (added up by k_finalize_fast).   mb 0: channels 0..127 (z, x).   mb 1: channels 128..191 (B, C) + the 16 dt rows (their
 // centre tap is dW_in[192 + j]) + 48 idle rows.
 //   warps 0-3 epilogue (warp 0 lane 0 is also the dpre-tile producer), warp 4 u-row producer, warp 5 lane 0 MMA issue.
 // ------------------------------------------------------------------------------------------------
@@ -746,7 +746,11 @@ k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
       const uint32_t mask = *reinterpret_cast<volatile uint32_t*>(&s_tapmask);
       const int m = warp * 32 + lane;
       const int c = mb * 128 + m;      // conv channel (mb 1: m < 64), or dt row 192 + (m - 64)
-      if (ok && (mb == 0 || m < 64)) {
+      // every CTA writes its own slab of partial sums (no atomics: 74 CTAs per address would serialise in L2);
+      // k_finalize_fast adds the slabs.  Taps this CTA never accumulated (image-border rows only) count as zero.
+      float* dKs = dK + (long long)part * (CC * 9);
+      float* dWs = dWin + (long long)part * (DIP * D);
+      if (mb == 0 || warp < 2) {      // warp-uniform: tcgen05.ld is .sync.aligned
         float wrow[D], dw[D];
 #pragma unroll
         for (int d = 0; d < D; d += 4) {
@@ -756,33 +760,43 @@ k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
         }
 #pragma unroll 1
         for (int t = 0; t < 9; ++t) {
-          if (!((mask >> t) & 1)) continue;     // warp-uniform
-          float v0[16], v1[16];
-          tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + t * D, v0);
-          tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + t * D + 16, v1);
-          tmem_wait_ld();
-          const float kt = __ldg(Kc + c * 9 + t);
           float dk = 0.f;
+          if (ok && ((mask >> t) & 1)) {     // warp-uniform
+            float v0[16], v1[16];
+            tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + t * D, v0);
+            tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + t * D + 16, v1);
+            tmem_wait_ld();
+            const float kt = __ldg(Kc + c * 9 + t);
+            float dk1 = 0.f;
 #pragma unroll
-          for (int d = 0; d < 16; ++d) {
-            dk = fmaf(wrow[d], v0[d], dk);
-            dk = fmaf(wrow[16 + d], v1[d], dk);
-            dw[d] = fmaf(kt, v0[d], dw[d]);
-            dw[16 + d] = fmaf(kt, v1[d], dw[16 + d]);
+            for (int d = 0; d < 16; ++d) {
+              dk = fmaf(wrow[d], v0[d], dk);
+              dk1 = fmaf(wrow[16 + d], v1[d], dk1);
+              dw[d] = fmaf(kt, v0[d], dw[d]);
+              dw[16 + d] = fmaf(kt, v1[d], dw[16 + d]);
+            }
+            dk += dk1;
           }
-          atomicAdd(dK + c * 9 + t, dk);
+          dKs[c * 9 + t] = dk;
         }
 #pragma unroll
-        for (int d = 0; d < D; ++d) atomicAdd(dWin + c * D + d, dw[d]);
-      } else if (ok && mb == 1 && warp == 2 && ((mask >> 4) & 1)) {   // warp-uniform branch: tcgen05.ld is .sync.aligned
+        for (int d = 0; d < D; d += 4) *reinterpret_cast<float4*>(dWs + c * D + d) = make_float4(dw[d], dw[d + 1], dw[d + 2], dw[d + 3]);
+      } else if (warp == 2) {        // mb 1, rows 64..79: the dt rows of W_in (centre tap)
         float v0[16], v1[16];
-        tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + 4 * D, v0);
-        tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + 4 * D + 16, v1);
-        tmem_wait_ld();
-        if (lane < NH) {
-          float* dst = dWin + (CC + lane) * D;
 #pragma unroll
-          for (int d = 0; d < 16; ++d) { atomicAdd(dst + d, v0[d]); atomicAdd(dst + 16 + d, v1[d]); }
+        for (int d = 0; d < 16; ++d) { v0[d] = 0.f; v1[d] = 0.f; }
+        if (ok && ((mask >> 4) & 1)) {
+          tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + 4 * D, v0);
+          tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + 4 * D + 16, v1);
+          tmem_wait_ld();
+        }
+        if (lane < NH) {
+          float* dst = dWs + (CC + lane) * D;
+#pragma unroll
+          for (int d = 0; d < 16; d += 4) {
+            *reinterpret_cast<float4*>(dst + d) = make_float4(v0[d], v0[d + 1], v0[d + 2], v0[d + 3]);
+            *reinterpret_cast<float4*>(dst + 16 + d) = make_float4(v1[d], v1[d + 1], v1[d + 2], v1[d + 3]);
+          }
         }
       }
       pt.mark(4);

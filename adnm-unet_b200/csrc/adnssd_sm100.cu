@@ -530,6 +530,11 @@ k_readout(const bf16* __restrict__ act, int CC, const float* __restrict__ S, con
       mbar_expect_tx(&ld_bar, (uint32_t)(2 * XC + CCH) * 128 * 16);
       tl_bulk(sCat + XC * 128 * 8, act, tile, NA, 0, 2 * XC, &ld_bar);
       tl_bulk(sC, act, tile, NA, 2 * XC + CCH, CCH, &ld_bar);
+      if (tile + (int)gridDim.x < num_tiles) {   // pull the next tile's inputs into L2 while this one is processed
+        const long long nt = tile + gridDim.x;
+        bulk_prefetch_l2(act + (nt * NA) * 1024, (uint32_t)(2 * XC) * 2048);
+        bulk_prefetch_l2(act + (nt * NA + 2 * XC + CCH) * 1024, (uint32_t)CCH * 2048);
+      }
     }
     bool ok = mbar_wait(&ld_bar, lph);
     lph ^= 1;
@@ -722,6 +727,16 @@ k_bwd1(const bf16* __restrict__ dout, const bf16* __restrict__ act, int CC, cons
       mbar_expect_tx(&ld_bar, (uint32_t)(2 * XC + CCH) * 128 * 16);
       tl_bulk(sCat + XC * 128 * 8, act, tile, NA, 0, 2 * XC, &ld_bar);
       tl_bulk(sC, act, tile, NA, 2 * XC + CCH, CCH, &ld_bar);
+      if (tile + 1 < tile_end) {   // pull the next tile's inputs into L2 while this one is processed
+        const long long nt = tile + 1;
+        bulk_prefetch_l2(act + (nt * NA) * 1024, (uint32_t)(2 * XC) * 2048);
+        bulk_prefetch_l2(act + (nt * NA + 2 * XC + CCH) * 1024, (uint32_t)CCH * 2048);
+        bulk_prefetch_l2(dout + nt * 128 * D, 128 * D * 2);
+        if (sgrad) {
+          bulk_prefetch_l2(sgrad + (nt * NA) * 1024, (uint32_t)XC * 2048);
+          bulk_prefetch_l2(sgrad + (nt * NA + 2 * XC + CCH) * 1024, (uint32_t)CCH * 2048);
+        }
+      }
     }
     load_tile_t8(sDout, dout + tok0 * D, D, DC, rows, tid, 128);   // dout is an external row-major tensor
     cp_async_commit();
@@ -1001,7 +1016,10 @@ k_bwd2(const bf16* __restrict__ act, const bf16* __restrict__ raw, int ldr, int 
     bf16* sDy = sB + BC * 128 * 8;
     bf16* sDt = sDy + XC * 128 * 8;
     // prefetch: the other stage was last read by iteration it-1, whose MMAs completed and whose trailing barrier passed
-    if (tid == 0 && tile + 1 < tile_end) issue_loads(tile + 1, stage ^ 1);
+    if (tid == 0 && tile + 1 < tile_end) {
+      issue_loads(tile + 1, stage ^ 1);
+      if (sgrad) bulk_prefetch_l2(sgrad + ((long long)(tile + 1) * NA + XC) * 1024, (uint32_t)(XC + BC) * 2048);
+    }
     const int b = tile / tiles_per_batch, i = tile % tiles_per_batch;
     const int rows = min(128, L - i * 128);
     const long long tok0 = (long long)b * L + (long long)i * 128;
@@ -1361,6 +1379,32 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, const float* __restri
     return;
   }
   blk -= 2 * Di;
+  if (a.dK_parts > 0) {
+    // k_bconv_wg left one slab of dK partial sums per CTA: the nb_rest blocks of this range add them up (independent loads,
+    // one output element per thread), hand over through a counter (all blocks of this small grid are co-resident), and
+    // then run the chain rule on the reduced dK
+    for (int e = blk * 256 + tid; e < a.dK_stride; e += nb_rest * 256) {
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+      int p = 0;
+      for (; p + 4 <= a.dK_parts; p += 4) {
+        v0 += a.dK_part[(long long)p * a.dK_stride + e];
+        v1 += a.dK_part[(long long)(p + 1) * a.dK_stride + e];
+        v2 += a.dK_part[(long long)(p + 2) * a.dK_stride + e];
+        v3 += a.dK_part[(long long)(p + 3) * a.dK_stride + e];
+      }
+      for (; p < a.dK_parts; ++p) v0 += a.dK_part[(long long)p * a.dK_stride + e];
+      a.dK[e] = (v0 + v1) + (v2 + v3);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      atomicAdd(a.sync_counter, 1);
+      while (atomicAdd(a.sync_counter, 0) < nb_rest) { }
+      __threadfence();
+    }
+    __syncthreads();
+    a.dK_parts = 0;
+  }
   finalize_body(a, w, g, D, Di, GN, nh, dip, (long long)blk * 256 + tid, (long long)nb_rest * 256, false);
 }
 
@@ -1639,13 +1683,15 @@ struct PrepBufs {
 };
 
 struct FastWs {           // placed after the generic workspace of the same pass
-  float* dWin_part;      // [148][dip*D] per-CTA partial sums of dW_in (k_bwd4)
+  float* dWin_part;      // [148][dip*D] per-CTA partial sums of dW_in (k_bwd4 / k_bconv_wg)
+  float* dK_part;        // [148][CC*9] per-CTA partial sums of dK (k_bconv_wg)
   float *Rt, *sdout;     // k_bwd1 accumulators: Rt[2Di][D], sdout[D] (contiguous, zeroed together)
   int* status;
   size_t bytes;
   FastWs(const MixerDims& d, void* p) {
     Carver c(p);
     dWin_part = c.take<float>((size_t)148 * d.dip * d.D);
+    dK_part = c.take<float>((size_t)148 * d.CC * 9);
     Rt = c.take<float>((size_t)2 * d.Di * d.D + d.D);
     sdout = Rt ? Rt + (size_t)2 * d.Di * d.D : nullptr;
     status = c.take<int>(64);
@@ -1852,10 +1898,13 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
       rc = set_smem(rowconv::k_bconv_wg, rowconv::WG_SMEM);
       if (rc) return rc;
       const int cpb = max(1, min(74, rows_total)), per = cdiv(rows_total, cpb), parts = cdiv(rows_total, per);
-      { ADN_KERNEL("k_bconv_wg", st); rowconv::k_bconv_wg<<<2 * parts, 192, rowconv::WG_SMEM, st>>>(W.dact, W.draw, reinterpret_cast<const bf16*>(S.wdec), w.in_proj_w, P.Kc, W.acc.dK, W.acc.dWin, d.H, rows_total, per, parts, F.status); }
+      { ADN_KERNEL("k_bconv_wg", st); rowconv::k_bconv_wg<<<2 * parts, 192, rowconv::WG_SMEM, st>>>(W.dact, W.draw, reinterpret_cast<const bf16*>(S.wdec), w.in_proj_w, P.Kc, F.dK_part, F.dWin_part, d.H, rows_total, per, parts, F.status); }
+      W.acc.dWin_part = F.dWin_part;
+      W.acc.dWin_parts = parts;
+      W.acc.dK_part = F.dK_part;
+      W.acc.dK_parts = parts;
+      W.acc.dK_stride = d.CC * 9;
     }
-    W.acc.dWin_part = nullptr;
-    W.acc.dWin_parts = 0;
     if (g.alpha1) ADN_CHECK_CUDA(cudaMemsetAsync(g.alpha1, 0, sizeof(float), st));
     const int nb_in = cdiv(d.dip * d.D, 32), nb_rest = 8;
     { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<nb_in + 2 * d.Di + nb_rest, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest); }

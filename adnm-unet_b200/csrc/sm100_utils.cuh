@@ -110,6 +110,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                : "memory");
 }
 
+// L2 prefetch of a contiguous global range (multiple of 16 bytes); fire-and-forget, issued by ONE thread
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
 // ---- tiled global layout "TL" of the internal activation tensors: tokens in tiles of 128, inside a tile the T8 layout
 // [chunk][128 rows][8]: element (tok, c) of a tensor with NCH = channels/8 chunks.  A tile's chunk range is contiguous,
 // so it moves global -> shared with ONE bulk copy, and "thread t owns token row t" kernels store fully coalesced.
