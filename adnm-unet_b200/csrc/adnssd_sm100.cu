@@ -346,6 +346,7 @@ __device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : 
 
 }  // namespace adn
 #include "adnssd_rowconv.cuh"
+#include "adnssd_bwdws.cuh"
 namespace adn {
 using namespace sm100;
 
@@ -1883,10 +1884,22 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   // ---- phase B1: dout -> dy, dzc, dCc ; reductions Rt, dS'
   if (rowconv_supported(d)) {
     // B1 / B2 write dpre = dact * SiLU'(pre) directly; ddt goes to a compact TL tensor (2 chunks per tile) in W.draw
-    int rc = launch_bwd1<64, 32>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st, S.pre);
-    if (rc) return rc;
-    rc = launch_bwd2<64, 32>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st, S.pre, 2, 0);
-    if (rc) return rc;
+    int rc;
+    const char* ews = getenv("ADN_BWD_WS");      // diagnostics: ADN_BWD_WS=0 keeps the monolithic tile kernels
+    if (ews && ews[0] == '0') {
+      rc = launch_bwd1<64, 32>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st, S.pre);
+      if (rc) return rc;
+      rc = launch_bwd2<64, 32>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st, S.pre, 2, 0);
+      if (rc) return rc;
+    } else {
+      const int tpb = d.L / 128, nt = tpb * d.B, per = cdiv(nt, 148), grid = cdiv(nt, per);
+      rc = set_smem(bwdws::k_bwd1_ws, bwdws::B1_SMEM);
+      if (rc) return rc;
+      { ADN_KERNEL("k_bwd1_ws", st); bwdws::k_bwd1_ws<<<grid, 320, bwdws::B1_SMEM, st>>>(dout, S.act, S.pre, S.S, w.D, w.norm_w, w.alpha1, P.Wout, W.dact, F.Rt, F.sdout, W.dS, tpb, nt, per, F.status); }
+      rc = set_smem(bwdws::k_bwd2_ws, bwdws::B2_SMEM);
+      if (rc) return rc;
+      { ADN_KERNEL("k_bwd2_ws", st); bwdws::k_bwd2_ws<<<grid, 320, bwdws::B2_SMEM, st>>>(S.act, S.pre, S.raw, W.dS, w.dt_bias, w.A_log, w.D, W.dact, W.draw, W.acc.dD, W.acc.dAlog, W.acc.ddtb, tpb, nt, per, F.status); }
+    }
     const int rows_total = d.B * d.H;
     {
       rc = set_smem(rowconv::k_bconv_du, rowconv::DU_SMEM);
