@@ -212,17 +212,19 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
 #pragma unroll
       for (int i = 0; i < 16; ++i) sd[i] = 0.f;
       int fl = 0;
+      PhaseTimer pt(0, tid == 0);
+      uint4 sgc_prev[2], sgc_cur[2];     // SiLU' of the C columns: fetched one tile ahead of their use in epi2
       auto epi2 = [&](int t) {
         const int it = t - T0, s = it & 1, b = t / tiles_per_batch, i_in_b = t % tiles_per_batch;
         ok = mbar_wait(&mma2_done[s], (it >> 1) & 1) && ok;
         tc_fence_after();
+        pt.mark(5);
         const uint32_t ta = tbase + ((uint32_t)(q * 32) << 16) + s * B1_TSTG;
         float v[16];
         tmem_ld16(ta + B1_COL_DC + h * 16, v);
-        const bf16* srow = sgrad + (((long long)t * NA + 2 * XC + CCH + 2 * h) * 128 + row) * 8;
         float s0[8], s1[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(srow)), s0);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(srow + 1024)), s1);
+        unpack8(sgc_prev[0], s0);
+        unpack8(sgc_prev[1], s1);
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
@@ -265,10 +267,15 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
           const bf16* srow = sgrad + (((long long)t * NA + 4 * h) * 128 + row) * 8;
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) sgz[c4] = __ldg(reinterpret_cast<const uint4*>(srow + c4 * 1024));
+          const bf16* crow = sgrad + (((long long)t * NA + 2 * XC + CCH + 2 * h) * 128 + row) * 8;
+          sgc_cur[0] = __ldg(reinterpret_cast<const uint4*>(crow));
+          sgc_cur[1] = __ldg(reinterpret_cast<const uint4*>(crow + 1024));
         }
+        pt.mark(6);
         ok = mbar_wait(&full[s], (it >> 1) & 1) && ok;      // x and dout of this stage are read from shared memory below
         ok = mbar_wait(&mma1_done[s], (it >> 1) & 1) && ok;
         tc_fence_after();
+        pt.mark(0);
         const uint32_t ta = tbase + ((uint32_t)(q * 32) << 16) + s * B1_TSTG;
         // ---- y, partial LayerNorm sums over this half's 32 channels
         float y[32];
@@ -289,7 +296,9 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
 #pragma unroll
         for (int c = 0; c < 32; ++c) { p1 += y[c]; p2 = fmaf(y[c], y[c], p2); }
         sXch[(0 * 2 + h) * 128 + row] = make_float2(p1, p2);
+        pt.mark(1);
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        pt.mark(2);
         {
           const float2 o = sXch[(0 * 2 + (h ^ 1)) * 128 + row];
           p1 += o.x;
@@ -320,7 +329,9 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
           }
         }
         sXch[(1 * 2 + h) * 128 + row] = make_float2(m1, m2);
+        pt.mark(3);
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        pt.mark(2);
         {
           const float2 o = sXch[(1 * 2 + (h ^ 1)) * 128 + row];
           m1 = (m1 + o.x) * (1.f / DI);
@@ -361,21 +372,32 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&epi1_done[s]);
+        pt.mark(4);
         if (t > T0) epi2(t - 1);
+        sgc_prev[0] = sgc_cur[0];
+        sgc_prev[1] = sgc_cur[1];
       }
       epi2(T1 - 1);
-      // ---- flush Rt (TMEM lanes = rows j' of [yhat | zc], 32 columns d) and sum(dout)
-      if (ok) {
+      pt.mark(6);
+      // ---- flush Rt (TMEM lanes = rows j' of [yhat | zc], 32 columns d) and sum(dout) into this CTA's slab (no atomics:
+      // one address would receive an update from every CTA); k_finalize_fast adds the slabs
+      {
+        float* slab = Rt + (long long)blockIdx.x * (2 * DI * D + D);
         float v[16];
         tmem_ld16(tbase + ((uint32_t)(q * 32) << 16) + B1_COL_RT + h * 16, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(Rt + row * D + h * 16 + j, v[j]);
-      }
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(slab + row * D + h * 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        // sum(dout): reduce the four lane quarters of this column half through shared memory (the exchange buffer is free now)
+        float* red = reinterpret_cast<float*>(sXch);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float v = warp_sum(sd[i]);
-        if (lane == 0) atomicAdd(sdout + h * 16 + i, v);
+        for (int i = 0; i < 16; ++i) {
+          const float w = warp_sum(sd[i]);
+          if (lane == 0) red[(h * 4 + q) * 16 + i] = w;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (q == 0 && lane < 16)
+          slab[2 * DI * D + h * 16 + lane] = red[(h * 4 + 0) * 16 + lane] + red[(h * 4 + 1) * 16 + lane] + red[(h * 4 + 2) * 16 + lane] + red[(h * 4 + 3) * 16 + lane];
       }
       if (!ok && lane == 0) atomicExch(status, 31);
     }
@@ -401,12 +423,13 @@ constexpr int B2_TSTG = 96, B2_COL_DB = 64;
 __global__ void __launch_bounds__(320, 1)
 k_bwd2_ws(const bf16* __restrict__ act, const bf16* __restrict__ sgrad, const bf16* __restrict__ dtraw, const float* __restrict__ dS,
           const float* __restrict__ dt_bias, const float* __restrict__ A_log, const float* __restrict__ Dp,
-          bf16* __restrict__ dact, bf16* __restrict__ ddt, float* __restrict__ dD, float* __restrict__ dAlog,
-          float* __restrict__ ddtb, int tiles_per_batch, int num_tiles, int tiles_per_cta, int* __restrict__ status) {
+          bf16* __restrict__ dact, bf16* __restrict__ ddt, float* __restrict__ head_part /* [CTA][dD | dA_log | ddt_bias] */,
+          int tiles_per_batch, int num_tiles, int tiles_per_cta, int* __restrict__ status) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[2], mma1_done[2], epi1_done[2], mma2_done[2], acc_free[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_bias[NH], s_eA[NH], s_D[NH];
+  __shared__ float s_red[8][24];
   uint8_t* sStg = smem;
   uint8_t* sImg = smem + 2 * B2_STG_B;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -490,16 +513,16 @@ k_bwd2_ws(const bf16* __restrict__ act, const bf16* __restrict__ sgrad, const bf
       float aD[8], aA[8], aB[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) { aD[i] = 0.f; aA[i] = 0.f; aB[i] = 0.f; }
+      uint4 sgb_prev[2], sgb_cur[2];     // SiLU' of the B columns: fetched one tile ahead of their use in epi2
       auto epi2 = [&](int t) {
         const int it = t - T0, s = it & 1;
         ok = mbar_wait(&mma2_done[s], (it >> 1) & 1) && ok;
         tc_fence_after();
         float v[16];
         tmem_ld16(tbase + ((uint32_t)(q * 32) << 16) + s * B2_TSTG + B2_COL_DB + h * 16, v);
-        const bf16* srow = sgrad + (((long long)t * NA + 2 * XC + 2 * h) * 128 + row) * 8;
         float s0[8], s1[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(srow)), s0);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(srow + 1024)), s1);
+        unpack8(sgb_prev[0], s0);
+        unpack8(sgb_prev[1], s1);
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
@@ -522,6 +545,9 @@ k_bwd2_ws(const bf16* __restrict__ act, const bf16* __restrict__ sgrad, const bf
           const bf16* srow = sgrad + (((long long)t * NA + XC + 4 * h) * 128 + row) * 8;
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) sgx[c4] = __ldg(reinterpret_cast<const uint4*>(srow + c4 * 1024));
+          const bf16* brow = sgrad + (((long long)t * NA + 2 * XC + 2 * h) * 128 + row) * 8;
+          sgb_cur[0] = __ldg(reinterpret_cast<const uint4*>(brow));
+          sgb_cur[1] = __ldg(reinterpret_cast<const uint4*>(brow + 1024));
         }
         ok = mbar_wait(&full[s], (it >> 1) & 1) && ok;     // the dt columns are read before MMA1 completes
         float w[8], sg[8];
@@ -582,12 +608,21 @@ k_bwd2_ws(const bf16* __restrict__ act, const bf16* __restrict__ sgrad, const bf
         __syncwarp();
         if (lane == 0) mbar_arrive(&epi1_done[s]);
         if (t > T0) epi2(t - 1);
+        sgb_prev[0] = sgb_cur[0];
+        sgb_prev[1] = sgb_cur[1];
       }
       epi2(T1 - 1);
+      // per-head parameter gradients: warp sums -> shared memory -> one slab of 3*NH floats per CTA (no atomics: every CTA
+      // would hit the same 48 addresses); k_finalize_fast adds the slabs
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float vD = warp_sum(aD[j]), vA = warp_sum(aA[j]), vB = warp_sum(aB[j]);
-        if (lane == 0) { atomicAdd(dD + 8 * h + j, vD); atomicAdd(dAlog + 8 * h + j, vA); atomicAdd(ddtb + 8 * h + j, vB); }
+        if (lane == 0) { s_red[warp][j] = vD; s_red[warp][8 + j] = vA; s_red[warp][16 + j] = vB; }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (q == 0 && lane < 24) {
+        const float v = s_red[4 * h + 0][lane] + s_red[4 * h + 1][lane] + s_red[4 * h + 2][lane] + s_red[4 * h + 3][lane];
+        head_part[(long long)blockIdx.x * 3 * NH + (lane >> 3) * NH + 8 * h + (lane & 7)] = v;
       }
       if (!ok && lane == 0) atomicExch(status, 33);
     }

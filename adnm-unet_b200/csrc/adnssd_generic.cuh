@@ -539,6 +539,9 @@ struct GradAcc {
   const float* dK_part;
   int dK_parts, dK_stride;
   int* sync_counter;   // zeroed with the accumulators; grid-level hand-off inside k_finalize_fast
+  // optional per-CTA partial sums of [dD | dA_log | ddt_bias] (k_bwd2_ws): head_parts slabs of 3*nh floats
+  const float* head_part;
+  int head_parts;
 };
 
 __device__ __forceinline__ float dk_at(const GradAcc& a, int idx) {
@@ -569,9 +572,15 @@ __device__ __forceinline__ void finalize_body(const GradAcc& a, const AdnWeights
   if (i0 == 0 && g.alpha1) g.alpha1[0] = a.dalpha1[0];
   }
   for (long long i = i0; i < nh; i += stride) {
-    if (g.D) g.D[i] = a.dD[i];
-    if (g.A_log) g.A_log[i] = a.dAlog[i];
-    if (g.dt_bias) g.dt_bias[i] = a.ddtb[i];
+    float vD = a.dD[i], vA = a.dAlog[i], vB = a.ddtb[i];
+    for (int p = 0; p < a.head_parts; ++p) {
+      vD += a.head_part[(long long)p * 3 * nh + i];
+      vA += a.head_part[(long long)p * 3 * nh + nh + i];
+      vB += a.head_part[(long long)p * 3 * nh + 2 * nh + i];
+    }
+    if (g.D) g.D[i] = vD;
+    if (g.A_log) g.A_log[i] = vA;
+    if (g.dt_bias) g.dt_bias[i] = vB;
   }
   if (g.conv2d_z_w)
     for (long long i = i0; i < (long long)Di * 9; i += stride) g.conv2d_z_w[i] = dk_at(a, (int)i);
@@ -686,6 +695,8 @@ struct BwdWs {
     acc.dK_part = nullptr;
     acc.dK_parts = 0;
     acc.dK_stride = 0;
+    acc.head_part = nullptr;
+    acc.head_parts = 0;
     acc.dWout = c.take<float>((size_t)d.D * 2 * d.Di);
     acc.dgamma = c.take<float>(d.Di);
     acc.dbeta = c.take<float>(d.Di);

@@ -1335,14 +1335,65 @@ k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__
 //   blocks [nb_in, nb_in + 2Di)  dW_out, dgamma, dbeta, dalpha1 partial from Rt / sum(dout)    (one warp per column)
 //   remaining blocks             dD, dA_log, ddt_bias and the ten conv weight gradients from dK (shared finalize_body)
 __global__ void __launch_bounds__(256)
-k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, const float* __restrict__ Rt, const float* __restrict__ sdout,
-                int D, int Di, int GN, int nh, int dip, int nb_in, int nb_rest) {
+k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ Rt, float* __restrict__ sdout,
+                int D, int Di, int GN, int nh, int dip, int nb_in, int nb_rest, int rt_parts) {
   __shared__ float red[8][33];
   const int tid = threadIdx.x;
+  // ---- phase 1 (row-kernel / warp-specialised path): the backward kernels left one slab of partial sums per CTA instead
+  // of contended atomics.  Every block adds up 32-element chunks (8 slab lanes x 32 elements, coalesced), then the grid
+  // meets at a counter (this small grid is always co-resident) and phase 2 reads the reduced arrays.
+  //   set 0: dW_in   set 1: dK   set 2: [Rt | sum(dout)] (reduced in place into slab 0)   set 3: [dD | dA_log | ddt_bias]
+  if (a.dWin_parts > 0 || a.dK_parts > 0 || rt_parts > 0 || a.head_parts > 0) {
+    const int n0 = a.dWin_parts > 0 ? dip * D : 0, n1 = a.dK_parts > 0 ? a.dK_stride : 0;
+    const int rs = 2 * Di * D + D, n2 = rt_parts > 0 ? rs : 0, n3 = a.head_parts > 0 ? 3 * nh : 0;
+    const int c0 = (n0 + 31) / 32, c1 = (n1 + 31) / 32, c2 = (n2 + 31) / 32, c3 = (n3 + 31) / 32;
+    const int el = tid & 31, pl = tid >> 5;
+    for (int chunk = blockIdx.x; chunk < c0 + c1 + c2 + c3; chunk += gridDim.x) {
+      const float* src;
+      int parts, stride, n, e;
+      int set;
+      if (chunk < c0) { set = 0; src = a.dWin_part; parts = a.dWin_parts; stride = n0; n = n0; e = chunk * 32 + el; }
+      else if (chunk < c0 + c1) { set = 1; src = a.dK_part; parts = a.dK_parts; stride = n1; n = n1; e = (chunk - c0) * 32 + el; }
+      else if (chunk < c0 + c1 + c2) { set = 2; src = Rt; parts = rt_parts; stride = rs; n = n2; e = (chunk - c0 - c1) * 32 + el; }
+      else { set = 3; src = a.head_part; parts = a.head_parts; stride = n3; n = n3; e = (chunk - c0 - c1 - c2) * 32 + el; }
+      float v = 0.f;
+      if (e < n)
+        for (int p = pl; p < parts; p += 8) v += src[(long long)p * stride + e];
+      __syncthreads();
+      red[pl][el] = v;
+      __syncthreads();
+      if (pl == 0 && e < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][el];
+        if (set == 0) a.dWin[e] = t;
+        else if (set == 1) a.dK[e] = t;
+        else if (set == 2) Rt[e] = t;
+        else if (e < nh) a.dD[e] = t;
+        else if (e < 2 * nh) a.dAlog[e - nh] = t;
+        else a.ddtb[e - 2 * nh] = t;
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      atomicAdd(a.sync_counter, 1);
+      while (atomicAdd(a.sync_counter, 0) < (int)gridDim.x) { }
+      __threadfence();
+    }
+    __syncthreads();
+    a.dWin_parts = 0;
+    a.dK_parts = 0;
+    a.head_parts = 0;
+  }
+  // ---- phase 2
+  //   blocks [0, nb_in)            dW_in from the accumulator / the per-CTA slabs of k_bwd4        (32 elements x 8 slab lanes)
+  //   blocks [nb_in, nb_in + 2Di)  dW_out, dgamma, dbeta, dalpha1 partial from Rt / sum(dout)    (one warp per column)
+  //   remaining blocks             dD, dA_log, ddt_bias and the ten conv weight gradients from dK (shared finalize_body)
   int blk = blockIdx.x;
   if (blk < nb_in) {
     const int n = dip * D, e = blk * 32 + (tid & 31), pl = tid >> 5;
-    float v = (e < n && pl == 0 && a.dWin_parts == 0) ? a.dWin[e] : 0.f;   // row-kernel path: atomically accumulated
+    float v = (e < n && pl == 0 && a.dWin_parts == 0) ? a.dWin[e] : 0.f;
     if (e < n)
       for (int p = pl; p < a.dWin_parts; p += 8) v += a.dWin_part[(long long)p * n + e];
     red[pl][tid & 31] = v;
@@ -1380,32 +1431,6 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, const float* __restri
     return;
   }
   blk -= 2 * Di;
-  if (a.dK_parts > 0) {
-    // k_bconv_wg left one slab of dK partial sums per CTA: the nb_rest blocks of this range add them up (independent loads,
-    // one output element per thread), hand over through a counter (all blocks of this small grid are co-resident), and
-    // then run the chain rule on the reduced dK
-    for (int e = blk * 256 + tid; e < a.dK_stride; e += nb_rest * 256) {
-      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-      int p = 0;
-      for (; p + 4 <= a.dK_parts; p += 4) {
-        v0 += a.dK_part[(long long)p * a.dK_stride + e];
-        v1 += a.dK_part[(long long)(p + 1) * a.dK_stride + e];
-        v2 += a.dK_part[(long long)(p + 2) * a.dK_stride + e];
-        v3 += a.dK_part[(long long)(p + 3) * a.dK_stride + e];
-      }
-      for (; p < a.dK_parts; ++p) v0 += a.dK_part[(long long)p * a.dK_stride + e];
-      a.dK[e] = (v0 + v1) + (v2 + v3);
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      atomicAdd(a.sync_counter, 1);
-      while (atomicAdd(a.sync_counter, 0) < nb_rest) { }
-      __threadfence();
-    }
-    __syncthreads();
-    a.dK_parts = 0;
-  }
   finalize_body(a, w, g, D, Di, GN, nh, dip, (long long)blk * 256 + tid, (long long)nb_rest * 256, false);
 }
 
@@ -1686,15 +1711,17 @@ struct PrepBufs {
 struct FastWs {           // placed after the generic workspace of the same pass
   float* dWin_part;      // [148][dip*D] per-CTA partial sums of dW_in (k_bwd4 / k_bconv_wg)
   float* dK_part;        // [148][CC*9] per-CTA partial sums of dK (k_bconv_wg)
-  float *Rt, *sdout;     // k_bwd1 accumulators: Rt[2Di][D], sdout[D] (contiguous, zeroed together)
+  float *Rt, *sdout;     // k_bwd1 accumulators: Rt[2Di][D], sdout[D] (contiguous, zeroed together); slabs on the ws path
+  float* head_part;      // [148][3*nh] per-CTA partial sums of dD, dA_log, ddt_bias (k_bwd2_ws)
   int* status;
   size_t bytes;
   FastWs(const MixerDims& d, void* p) {
     Carver c(p);
     dWin_part = c.take<float>((size_t)148 * d.dip * d.D);
     dK_part = c.take<float>((size_t)148 * d.CC * 9);
-    Rt = c.take<float>((size_t)2 * d.Di * d.D + d.D);
+    Rt = c.take<float>((size_t)148 * (2 * d.Di * d.D + d.D));      // one slab per CTA on the warp-specialised path
     sdout = Rt ? Rt + (size_t)2 * d.Di * d.D : nullptr;
+    head_part = c.take<float>((size_t)148 * 3 * d.nh);
     status = c.take<int>(64);
     bytes = c.off;
   }
@@ -1884,7 +1911,7 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   // ---- phase B1: dout -> dy, dzc, dCc ; reductions Rt, dS'
   if (rowconv_supported(d)) {
     // B1 / B2 write dpre = dact * SiLU'(pre) directly; ddt goes to a compact TL tensor (2 chunks per tile) in W.draw
-    int rc;
+    int rc, rt_parts = 0;
     const char* ews = getenv("ADN_BWD_WS");      // diagnostics: ADN_BWD_WS=0 keeps the monolithic tile kernels
     if (ews && ews[0] == '0') {
       rc = launch_bwd1<64, 32>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st, S.pre);
@@ -1898,7 +1925,10 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
       { ADN_KERNEL("k_bwd1_ws", st); bwdws::k_bwd1_ws<<<grid, 320, bwdws::B1_SMEM, st>>>(dout, S.act, S.pre, S.S, w.D, w.norm_w, w.alpha1, P.Wout, W.dact, F.Rt, F.sdout, W.dS, tpb, nt, per, F.status); }
       rc = set_smem(bwdws::k_bwd2_ws, bwdws::B2_SMEM);
       if (rc) return rc;
-      { ADN_KERNEL("k_bwd2_ws", st); bwdws::k_bwd2_ws<<<grid, 320, bwdws::B2_SMEM, st>>>(S.act, S.pre, S.raw, W.dS, w.dt_bias, w.A_log, w.D, W.dact, W.draw, W.acc.dD, W.acc.dAlog, W.acc.ddtb, tpb, nt, per, F.status); }
+      { ADN_KERNEL("k_bwd2_ws", st); bwdws::k_bwd2_ws<<<grid, 320, bwdws::B2_SMEM, st>>>(S.act, S.pre, S.raw, W.dS, w.dt_bias, w.A_log, w.D, W.dact, W.draw, F.head_part, tpb, nt, per, F.status); }
+      rt_parts = grid;
+      W.acc.head_part = F.head_part;
+      W.acc.head_parts = grid;
     }
     const int rows_total = d.B * d.H;
     {
@@ -1920,7 +1950,7 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
     }
     if (g.alpha1) ADN_CHECK_CUDA(cudaMemsetAsync(g.alpha1, 0, sizeof(float), st));
     const int nb_in = cdiv(d.dip * d.D, 32), nb_rest = 8;
-    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<nb_in + 2 * d.Di + nb_rest, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest); }
+    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<nb_in + 2 * d.Di + nb_rest, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest, rt_parts); }
     ADN_CHECK_LAUNCH();
     return ADN_OK;
   }
@@ -1948,7 +1978,7 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   {
     if (g.alpha1) ADN_CHECK_CUDA(cudaMemsetAsync(g.alpha1, 0, sizeof(float), st));
     const int nb_in = cdiv(d.dip * d.D, 32), nb_rest = 8;
-    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<nb_in + 2 * d.Di + nb_rest, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest); }
+    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<nb_in + 2 * d.Di + nb_rest, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest, 0); }
   }
   ADN_CHECK_LAUNCH();
   return ADN_OK;

@@ -17,7 +17,7 @@ m(u, 128, 128).backward(go)
 buf = (C.c_ulonglong * 64)()
 lib.adn_phase_read(buf)
 lib.adn_phase_enable(0)
-names = {0: "k_bwd1", 1: "k_bwd2", 2: "k_bconv_du producer [wait empty | issue]", 3: "k_bconv_du epilogue t0 [wait slot_full | tmem ld + release | exchange + bar | shuffle + store | . | . | . | loop]",
+names = {0: "k_bwd1_ws epilogue t0 [wait mma1 | y + stats | bar.sync x2 | yhat + g_y sums | dy, dz stores + sd | wait mma2 | epi2 + loop | .]", 1: "k_bwd2", 2: "k_bconv_du producer [wait empty | issue]", 3: "k_bconv_du epilogue t0 [wait slot_full | tmem ld + release | exchange + bar | shuffle + store | . | . | . | loop]",
          4: "k_fconv MMA thread [wait u | wait acc_empty | issue conv | wait st_full | issue state | . | . | loop]",
          5: "k_bconv_du MMA thread [wait stage | wait acc_empty | issue | . | . | . | . | loop]",
          6: "k_bconv_wg MMA thread [wait u | wait A | issue | (epi) wait done | (epi) contract+atomics | CTA prologue | CTA body | loop]",
