@@ -1871,8 +1871,19 @@ int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* 
     if (rc) return rc;
     const int rows_total = d.B * d.H, per = rows_per_cta(rows_total, 148), grid = cdiv(rows_total, per);
     { ADN_KERNEL("k_fconv", st); rowconv::k_fconv<<<grid, rowconv::FC_THREADS, rowconv::FC_SMEM, st>>>(u, P.WtF, w.dt_bias, w.A_log, S.act, training ? S.pre : nullptr, S.raw, S.S, d.H, rows_total, per, F.status, training ? reinterpret_cast<bf16*>(S.wdec) : nullptr); }
-    rc = launch_readout<64, 32>(d, S.act, S.S, w, P.Wout, out, F.status, st);
-    if (rc) return rc;
+    // The warp-specialised readout (one CTA per SM, two tiles in flight) measured SLOWER than the monolithic tile kernel
+    // at three CTAs per SM (41.7 vs 33.2 us at the benchmark shape): this stage is light enough that plain occupancy
+    // hides its latencies better.  It stays selectable for experiments (ADN_READOUT_WS=1).
+    const char* ews = getenv("ADN_READOUT_WS");
+    if (!(ews && ews[0] == '1')) {
+      rc = launch_readout<64, 32>(d, S.act, S.S, w, P.Wout, out, F.status, st);
+      if (rc) return rc;
+    } else {
+      const int tpb = d.L / 128, nt = tpb * d.B, per = cdiv(nt, 148), grid = cdiv(nt, per);
+      rc = set_smem(bwdws::k_readout_ws, bwdws::RO_SMEM);
+      if (rc) return rc;
+      { ADN_KERNEL("k_readout_ws", st); bwdws::k_readout_ws<<<grid, 320, bwdws::RO_SMEM, st>>>(S.act, S.S, w.D, w.norm_w, w.norm_b, w.alpha1, P.Wout, out, tpb, nt, per, F.status); }
+    }
     ADN_CHECK_LAUNCH();
     return ADN_OK;
   }

@@ -374,6 +374,7 @@ def _dims(D):
 def _alg(D):
     Di, GN, nh, CC, dip = _dims(D)
     return {
+        # tile kernels (token grids that are not 128 wide)
         "k_inproj": 2 * (D + dip),
         "k_conv_fwd_tile": 2 * 3 * CC,
         "k_state": 2 * (Di + GN + nh),
@@ -382,6 +383,12 @@ def _alg(D):
         "k_bwd2": 2 * (2 * Di + GN + nh) + 2 * (Di + GN + nh),
         "k_conv_bwd_tile": 2 * 4 * CC,
         "k_bwd4": 2 * (dip + 2 * D),
+        # row kernels + warp-specialised backward (128-wide grids: the benchmark shape)
+        "k_fconv": 2 * D + 2 * (2 * CC + nh) + 2 * D,                       # read u; write act, SiLU', dt, TL copy of u
+        "k_bwd1_ws": 2 * D + 2 * (2 * Di + GN) + 2 * (Di + GN) + 2 * (2 * Di + GN),   # dout, act z|x|C, SiLU' z|C; dpre z, dy, dpre C
+        "k_bwd2_ws": 2 * (Di + GN) + 2 * Di + 2 * nh + 2 * (Di + GN) + 2 * (Di + GN + nh),   # act x|B, dy, dt, SiLU' x|B; dpre x|B, ddt
+        "k_bconv_du": 2 * (CC + nh) + 2 * D,                                # dpre, ddt; du
+        "k_bconv_wg": 2 * (CC + nh) + 2 * D,                                # dpre, ddt, TL copy of u
     }
 
 

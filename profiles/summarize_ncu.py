@@ -37,7 +37,7 @@ def main(rep, out):
     kernels = {}
     for r in rows[2:]:
         name = re.sub(r"^void ", "", r[idx["Kernel Name"]])
-        short = re.match(r"(?:adn::)?(\w+)", name).group(1)
+        short = re.match(r"(?:\w+::)*(\w+)", name).group(1)
         e = {"signature": name[:120]}
         for m, key in METRICS.items():
             if m in idx and r[idx[m]] not in ("", "n/a"):
