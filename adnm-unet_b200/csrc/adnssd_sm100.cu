@@ -1933,7 +1933,7 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
       const int tpb = d.L / 128, nt = tpb * d.B, per = cdiv(nt, 148), grid = cdiv(nt, per);
       rc = set_smem(bwdws::k_bwd1_ws, bwdws::B1_SMEM);
       if (rc) return rc;
-      { ADN_KERNEL("k_bwd1_ws", st); bwdws::k_bwd1_ws<<<grid, 320, bwdws::B1_SMEM, st>>>(dout, S.act, S.pre, S.S, w.D, w.norm_w, w.alpha1, P.Wout, W.dact, F.Rt, F.sdout, W.dS, tpb, nt, per, F.status); }
+      { ADN_KERNEL("k_bwd1_ws", st); bwdws::k_bwd1_ws<<<grid, bwdws::WS_THREADS, bwdws::B1_SMEM, st>>>(dout, S.act, S.pre, S.S, w.D, w.norm_w, w.alpha1, P.Wout, W.dact, F.Rt, F.sdout, W.dS, tpb, nt, per, F.status); }
       rc = set_smem(bwdws::k_bwd2_ws, bwdws::B2_SMEM);
       if (rc) return rc;
       { ADN_KERNEL("k_bwd2_ws", st); bwdws::k_bwd2_ws<<<grid, 320, bwdws::B2_SMEM, st>>>(S.act, S.pre, S.raw, W.dS, w.dt_bias, w.A_log, w.D, W.dact, W.draw, F.head_part, tpb, nt, per, F.status); }
