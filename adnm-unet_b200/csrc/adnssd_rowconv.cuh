@@ -216,18 +216,81 @@ __device__ __forceinline__ void silu32(uint32_t taddr, bf16* a_dst, bf16* g_dst,
   }
 }
 
+// One epilogue column group of k_fconv: 48 accumulator columns [48 G, 48 G + 48) = chunks [6 G, 6 G + 6) of [z | x | B | C]
+// (three TMEM loads in flight, packed fp32x2 math).  Per chunk: SiLU -> act, SiLU' -> sgrad (TL layout); x chunks also write
+// w * act (decay-weighted x, heads 2(c-8), 2(c-8)+1) and B chunks a copy of act to the state operands in shared memory.
+//   G 0: z0 z1 z2 | G 1: z3 x0 x1 (heads 0..7) | G 2: x2 x3 B0 (heads 8..15) | G 3: B1 C0 C1 (+ stores the dt columns)
+template <int G>
+__device__ __forceinline__ void fconv_epi_group(uint32_t ta, bf16* arow, bf16* grow, uint8_t* st, bf16* dtrow,
+                                                const float* s_bias, const float* s_eA) {
+  float v[3][16];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tmem_ld16(ta + 48 * G + 16 * i, v[i]);
+  float w[8];
+  if constexpr (G == 1 || G == 2) {
+    float d8[8];
+    tmem_ld8(ta + CC + (G == 1 ? 0 : 8), d8);
+    tmem_wait_ld();
+    const uint4 p = pack8(d8);      // the decay weights are formed from the stored (bf16) dt so that backward sees the same w
+    unpack8(p, d8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = softplus_fast(d8[j] + s_bias[(G == 1 ? 0 : 8) + j]) * s_eA[(G == 1 ? 0 : 8) + j];
+  } else if constexpr (G == 3) {
+    float d16[16];
+    tmem_ld16(ta + CC, d16);
+    tmem_wait_ld();
+    float lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { lo[j] = d16[j]; hi[j] = d16[8 + j]; }
+    *reinterpret_cast<uint4*>(dtrow) = pack8(lo);
+    *reinterpret_cast<uint4*>(dtrow + 1024) = pack8(hi);
+  } else {
+    tmem_wait_ld();
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    constexpr int c0 = 6 * G;
+    const int c = c0 + i;                      // compile-time after unrolling
+    float2 a[4], gq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = make_float2(v[i >> 1][(i & 1) * 8 + 2 * j], v[i >> 1][(i & 1) * 8 + 2 * j + 1]);
+      const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+      const float2 d = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.f, 1.f));
+      const float2 sg = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+      a[j] = __fmul2_rn(x, sg);
+      const float2 om = __ffma2_rn(sg, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+      gq[j] = __ffma2_rn(a[j], om, sg);
+    }
+    const uint4 pa = pack8_f2(a);
+    *reinterpret_cast<uint4*>(arow + c * 1024) = pa;
+    if (grow) *reinterpret_cast<uint4*>(grow + c * 1024) = pack8_f2(gq);
+    if (c >= 8 && c < 16) {                    // x chunk: decay-weighted copy for the state MMA (A operand chunk c - 8)
+      float2 r[4];
+      unpack8_f2(pa, r);
+      const int hl = (2 * (c - 8)) & 7;        // local index of the chunk's first head in w[8]
+      const float2 w2 = make_float2(w[hl], w[hl + 1]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = __fmul2_rn(r[j], w2);
+      *reinterpret_cast<uint4*>(st + (c - 8) * 2048) = pack8_f2(r);
+    } else if (c >= 16 && c < 20) {            // B chunk: B operand chunk 8 + (c - 16)
+      *reinterpret_cast<uint4*>(st + (8 + c - 16) * 2048) = pa;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_fconv: forward in_proj + depthwise 3x3 + SiLU (+ SiLU') + decay weights + state accumulation, one image row
 // (128 tokens) per step.  Stages (1)-(4a) of the mixer (models/ADNssd.py:309-390, :267-280).
-//   warps 0-11 epilogue (lane quarter q = warp & 3, column group = warp >> 2: z | dt + x | B + C)
-//   warp  12   u-row producer (cp.async into the padded ring)
-//   warp  13   one elected lane issues every tcgen05.mma (and the bulk copies of the weight image)
+//   warps 0-15 epilogue (lane quarter q = warp & 3, column group = warp >> 2: 48 of the 192 conv columns each)
+//   warp  16   u-row producer (cp.async into the padded ring)
+//   warp  17   one elected lane issues every tcgen05.mma (and the bulk copies of the weight image)
 // TMEM: two 208-column accumulators [z | x | B | C | dt] + 32 columns of the per-sample state S'[c][j].
 // ------------------------------------------------------------------------------------------------
 constexpr int FC_ST_B = 12 * 2048;   // state operands of one row: wx chunks 0..7, Bc chunks 8..11
 constexpr int FC_SMEM = 2 * FC_ST_B + NUS * USLOT_B + WTF_B;
 constexpr int FC_COL_S = 2 * DIP;
-constexpr int FC_EPI_WARPS = 12, FC_THREADS = (FC_EPI_WARPS + 2) * 32;   // 3 column groups x 4 lane quarters + producer + MMA
+constexpr int FC_EPI_WARPS = 16, FC_THREADS = (FC_EPI_WARPS + 2) * 32;   // 4 column groups x 4 lane quarters + producer + MMA
 
 __global__ void __launch_bounds__(FC_THREADS, 1)
 k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* __restrict__ dt_bias,
@@ -347,7 +410,7 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
         if (!ok) atomicExch(status, 20);
       }
     } else {
-      const int q = warp & 3, grp = warp >> 2, row = q * 32 + lane;   // column group: 0 = z, 1 = dt + x, 2 = B + C
+      const int q = warp & 3, grp = warp >> 2, row = q * 32 + lane;   // column group: 48 columns each (fconv_epi_group)
       int fl = 0;
       PhaseTimer pt(7, tid == 0 || tid == 128 || tid == 256);
       for (int R = R0; R < R1; ++R) {
@@ -362,38 +425,11 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
         bf16* arow = act + ((long long)R * NA * 128 + row) * 8;
         bf16* grow = sgrad ? sgrad + ((long long)R * NA * 128 + row) * 8 : nullptr;
         uint8_t* st = sSt + acc * FC_ST_B + row * 16;
-        if (grp == 0) {
-#pragma unroll 1
-          for (int cb = 0; cb < DI; cb += 32)
-            silu32<0>(ta + cb, arow + (cb >> 3) * 1024, grow ? grow + (cb >> 3) * 1024 : nullptr, nullptr, nullptr);
-        } else if (grp == 2) {
-          silu32<1>(ta + 2 * DI, arow + ((2 * DI) >> 3) * 1024, grow ? grow + ((2 * DI) >> 3) * 1024 : nullptr, st + 8 * 2048, nullptr);
-          silu32<0>(ta + 2 * DI + GN, arow + ((2 * DI + GN) >> 3) * 1024, grow ? grow + ((2 * DI + GN) >> 3) * 1024 : nullptr,
-                    nullptr, nullptr);
-        } else {
-          float w[NH];
-          {
-            float v[16];
-            tmem_ld16(ta + CC, v);
-            tmem_wait_ld();
-            float lo[8], hi[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-            const uint4 p0 = pack8(lo), p1 = pack8(hi);
-            bf16* drow = dtraw + ((long long)R * 2 * 128 + row) * 8;
-            *reinterpret_cast<uint4*>(drow) = p0;
-            *reinterpret_cast<uint4*>(drow + 1024) = p1;
-            unpack8(p0, lo);     // the decay weights are formed from the stored (bf16) dt so that backward sees the same w
-            unpack8(p1, hi);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              w[j] = softplus_fast(lo[j] + s_bias[j]) * s_eA[j];
-              w[8 + j] = softplus_fast(hi[j] + s_bias[8 + j]) * s_eA[8 + j];
-            }
-          }
-          silu32<2>(ta + DI, arow + (DI >> 3) * 1024, grow ? grow + (DI >> 3) * 1024 : nullptr, st, &w[0]);
-          silu32<2>(ta + DI + 32, arow + ((DI + 32) >> 3) * 1024, grow ? grow + ((DI + 32) >> 3) * 1024 : nullptr, st + 4 * 2048, &w[8]);
-        }
+        bf16* dtrow = dtraw + ((long long)R * 2 * 128 + row) * 8;
+        if (grp == 0) fconv_epi_group<0>(ta, arow, grow, st, dtrow, s_bias, s_eA);
+        else if (grp == 1) fconv_epi_group<1>(ta, arow, grow, st, dtrow, s_bias, s_eA);
+        else if (grp == 2) fconv_epi_group<2>(ta, arow, grow, st, dtrow, s_bias, s_eA);
+        else fconv_epi_group<3>(ta, arow, grow, st, dtrow, s_bias, s_eA);
         pt.mark(2 + (grp == 1));
         tc_fence_before();
         fence_async_smem();

@@ -1431,6 +1431,7 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ R
     return;
   }
   blk -= 2 * Di;
+  if (blk >= nb_rest) return;      // extra blocks only take part in phase 1
   finalize_body(a, w, g, D, Di, GN, nh, dip, (long long)blk * 256 + tid, (long long)nb_rest * 256, false);
 }
 
@@ -1961,7 +1962,10 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
     }
     if (g.alpha1) ADN_CHECK_CUDA(cudaMemsetAsync(g.alpha1, 0, sizeof(float), st));
     const int nb_in = cdiv(d.dip * d.D, 32), nb_rest = 8;
-    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<nb_in + 2 * d.Di + nb_rest, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest, rt_parts); }
+    // every block of this grid (344 x 256 threads at the benchmark shape, < 3 blocks per SM) is co-resident, which the
+    // counter hand-off between the two phases relies on; a 148 x 6 grid for phase 1 measured no faster
+    const int fgrid = nb_in + 2 * d.Di + nb_rest;
+    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<fgrid, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest, rt_parts); }
     ADN_CHECK_LAUNCH();
     return ADN_OK;
   }

@@ -129,8 +129,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ADN-SSD mixer fwd+bwd, D={args.d_model}, headdim={HEADDIM}, d_state={D_STATE}, "
-                               f"{GRID}x{GRID} tokens (CPU sample B={batch}; GPU arm B={B_PER_GPU}/GPU)"},
+        "config": {"workload": f"ADN-SSD mixer fwd+bwd (BASELINE configs[1]): D={args.d_model}, headdim={HEADDIM}, d_state={D_STATE}, "
+                               f"B={B_PER_GPU}/GPU, {GRID}x{GRID} tokens",
+                   "note": f"CPU arm: each step is a bounded sample of that workload, B={batch} of the {B_PER_GPU} samples"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
