@@ -209,3 +209,76 @@ def test_full_size_fast_path_agrees_with_check_mode(B, g):
     with torch.no_grad():
         alone = A.adnssd_mixer(u[1:2].to(dev, torch.bfloat16), g, g, p, headdim=P, d_state=N).float().cpu()
     assert rel(alone[0], fast[0][1]) < 5e-3
+
+
+def test_row_kernels_agree_with_tile_kernels():
+    """The two sm_100a kernel families (conv-as-GEMM row kernels + warp-specialised backward vs. the halo-tile kernels)
+    on the same 128-wide grid: independent implementations of the same math, selected with ADN_ROWCONV (diagnostic switch
+    read by the library at every call)."""
+    B, H, W, D, P, N = 3, 9, 128, 32, 4, 16
+    params = AO.init_params(D, P, N, seed=31, perturb=0.05, dtype=torch.float32)
+    u = cases.rng_normal(41, (B, H * W, D), torch.float32)
+    dout = cases.rng_normal(42, (B, H * W, D), torch.float32)
+    res = {}
+    for flag in ("1", "0"):
+        os.environ["ADN_ROWCONV"] = flag
+        try:
+            res[flag] = run_cuda(params, u, dout, H, W, P, N, torch.bfloat16)
+        finally:
+            os.environ.pop("ADN_ROWCONV", None)
+    out1, du1, g1 = res["1"]
+    out0, du0, g0 = res["0"]
+    errs = {"out": rel(out1, out0.float().cpu()), "du": rel(du1, du0.float().cpu())}
+    for k in g0:
+        if k != "alpha1":      # scalar with heavy cancellation, covered by test_row_kernels_match_oracle
+            errs[k] = rel(g1[k], g0[k].float().cpu())
+    bad = {k: v for k, v in errs.items() if not v < 2e-2}
+    assert not bad, f"{bad} (all: {errs})"
+
+
+def test_module_step_is_cuda_graph_capturable():
+    """bench.py replays a captured fwd+bwd of the public module: a replay on new contents of the static input must
+    reproduce the eager result (the C ABI enqueues on the caller's stream, allocates nothing and never synchronises)."""
+    import adnm_unet_b200 as A
+    torch.manual_seed(3)
+    dev = torch.device("cuda:0")
+    m = A.Mamba2(d_model=32, headdim=4, d_state=16).to(dev)
+    params = [p for n, p in m.named_parameters() if n not in ("scale", "shift", "alpha2")]
+    H, W = 4, 128
+    u = torch.randn(2, H * W, 32, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    go = torch.randn_like(u)
+
+    def clear():
+        u.grad = None
+        for p in params:
+            p.grad = None
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):                     # warm-up outside capture
+        for _ in range(2):
+            clear()
+            m(u, H, W).backward(go)
+    torch.cuda.current_stream().wait_stream(s)
+    clear()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = m(u, H, W)
+        out.backward(go)
+    new_u = torch.randn(2, H * W, 32, generator=torch.Generator().manual_seed(99)).to(dev, torch.bfloat16)
+    with torch.no_grad():
+        u.copy_(new_u)
+    graph.replay()
+    torch.cuda.synchronize()
+    g_out, g_du, g_par = out.detach().clone(), u.grad.detach().clone(), [p.grad.detach().clone() for p in params]
+    # eager reference on the same input
+    ue = new_u.clone().requires_grad_(True)
+    for p in params:
+        p.grad = None
+    oe = m(ue, H, W)
+    oe.backward(go)
+    torch.cuda.synchronize()
+    assert rel(g_out, oe.detach().float().cpu()) < 1e-3          # fp32 atomics in the state reduction: not bit-exact
+    assert rel(g_du, ue.grad.float().cpu()) < 1e-3
+    for gp, p in zip(g_par, params):
+        assert rel(gp, p.grad.float().cpu()) < 5e-3
