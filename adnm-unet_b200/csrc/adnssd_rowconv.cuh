@@ -489,16 +489,16 @@ k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
   // dbg (diagnostics, ADN_DU_DBG): 1 = no loads, 2 = no MMAs, 4 = no du stores; results are then meaningless
   ADN_CTA_STAMP(1, 0);
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full[DU_NST], empty[DU_NST], slot_full[4], slot_empty[4];
+  __shared__ uint64_t full[DU_NST], empty[DU_NST], slot_full[4], slot_empty[4], w_full;
   __shared__ uint32_t tmem_slot;
   uint8_t* sStg = smem;
   uint8_t* sW = smem + DU_NST * DU_STG_B;
   float* sX = reinterpret_cast<float*>(sW + WTB_B);      // [parity][warp][0: lane 0's Z_0, 1: lane 31's Z_2][32 d]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R0 = blockIdx.x * rows_per_cta, R1 = min(rows_total, R0 + rows_per_cta);
-  for (int i = tid; i < WTB_B / 16; i += 192) reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(WtZ) + i);
   if (tid < 64) sX[8 * 64 + tid] = 0.f;
   if (tid == 0) {
+    mbar_init(&w_full, 1);
     for (int i = 0; i < DU_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 4); }
     fence_mbar_init();
@@ -541,6 +541,11 @@ k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
         const uint64_t dS0 = make_desc(sbase, 2048, 128), dW0 = make_desc(wbase, 96 * 16, 128);
         const uint64_t dWdt = make_desc(wbase + 18 * WTZ_AG_B, 512, 128);
         PhaseTimer pt(5, true);
+        // the weight image arrives by bulk copies while the first dpre tiles are in flight
+        mbar_expect_tx(&w_full, WTB_B);
+        for (int i = 0; i < 18; ++i) bulk_g2s(sW + i * WTZ_AG_B, reinterpret_cast<const uint8_t*>(WtZ) + i * WTZ_AG_B, WTZ_AG_B, &w_full);
+        bulk_g2s(sW + 18 * WTZ_AG_B, reinterpret_cast<const uint8_t*>(WtZ) + 18 * WTZ_AG_B, 1024, &w_full);
+        ok = mbar_wait(&w_full, 0) && ok;
         int un = 0;
         for (int r = rin0; r <= rin1; ++r) {
           const int y = r % H;

@@ -1357,8 +1357,18 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ R
       else if (chunk < c0 + c1 + c2) { set = 2; src = Rt; parts = rt_parts; stride = rs; n = n2; e = (chunk - c0 - c1) * 32 + el; }
       else { set = 3; src = a.head_part; parts = a.head_parts; stride = n3; n = n3; e = (chunk - c0 - c1 - c2) * 32 + el; }
       float v = 0.f;
-      if (e < n)
-        for (int p = pl; p < parts; p += 8) v += src[(long long)p * stride + e];
+      if (e < n) {      // up to ~19 slabs per thread: independent loads, four partial sums
+        float v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        int p = pl;
+        for (; p + 24 < parts; p += 32) {
+          v += src[(long long)p * stride + e];
+          v1 += src[(long long)(p + 8) * stride + e];
+          v2 += src[(long long)(p + 16) * stride + e];
+          v3 += src[(long long)(p + 24) * stride + e];
+        }
+        for (; p < parts; p += 8) v += src[(long long)p * stride + e];
+        v = (v + v1) + (v2 + v3);
+      }
       __syncthreads();
       red[pl][el] = v;
       __syncthreads();

@@ -278,7 +278,8 @@ def test_module_step_is_cuda_graph_capturable():
     oe = m(ue, H, W)
     oe.backward(go)
     torch.cuda.synchronize()
-    assert rel(g_out, oe.detach().float().cpu()) < 1e-3          # fp32 atomics in the state reduction: not bit-exact
-    assert rel(g_du, ue.grad.float().cpu()) < 1e-3
+    # fp32 atomics in the state reduction make two runs differ by an ulp of the bf16 outputs (2^-8 of the value)
+    assert rel(g_out, oe.detach().float().cpu()) < 4e-3
+    assert rel(g_du, ue.grad.float().cpu()) < 4e-3
     for gp, p in zip(g_par, params):
-        assert rel(gp, p.grad.float().cpu()) < 5e-3
+        assert rel(gp, p.grad.float().cpu()) < 1e-2
