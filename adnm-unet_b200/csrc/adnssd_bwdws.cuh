@@ -76,7 +76,7 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
           const bf16* __restrict__ Wout, bf16* __restrict__ dact, float* __restrict__ Rt, float* __restrict__ sdout,
           float* __restrict__ dS, int tiles_per_batch, int num_tiles, int tiles_per_cta, int* __restrict__ status) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full[2], mma1_done[2], epi1_done[2], mma2_done[2], acc_free[2], s_done, s_free;
+  __shared__ uint64_t full[2], mma1_done[2], epi1_done[2], mma2_done[2], acc_free[2], gy_free[2], s_done, s_free;
   __shared__ uint32_t tmem_slot;
   __shared__ float sG[DI], sDh[DI];
   uint8_t* sStg = smem;
@@ -103,7 +103,8 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
       mbar_init(&mma1_done[i], 1);
       mbar_init(&epi1_done[i], WS_EPI_WARPS);
       mbar_init(&mma2_done[i], 1);
-      mbar_init(&acc_free[i], WS_EPI_WARPS);
+      mbar_init(&acc_free[i], WS_EPI_WARPS);      // dCc columns consumed (second epilogue)
+      mbar_init(&gy_free[i], WS_EPI_WARPS);       // g / Y columns consumed (first epilogue): MMA1 of tile t+2 does not wait for EPI2
     }
     mbar_init(&s_done, 1);
     mbar_init(&s_free, WS_EPI_WARPS);
@@ -133,6 +134,14 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
           // act TL: z (chunks 0..7) -> sCat[8..16), x (8..15) -> sXY[0..8): adjacent in the stage; C (20..23) -> sC
           bulk_g2s(sb + (DC + CCH + XC) * 2048, act + ((long long)t * NA) * 1024, 2 * XC * 2048, &full[s]);
           bulk_g2s(sb + DC * 2048, act + ((long long)t * NA + 2 * XC + CCH) * 1024, CCH * 2048, &full[s]);
+          if (t + 1 < T1) {     // only two shared-memory stages: the next tile's loads cannot start before this stage's
+            const long long nt = t + 1;   // reader is done, so pull its operands into L2 now (their latency is then ~1/3)
+            bulk_prefetch_l2(act + (nt * NA) * 1024, 2 * XC * 2048);
+            bulk_prefetch_l2(act + (nt * NA + 2 * XC + CCH) * 1024, CCH * 2048);
+            bulk_prefetch_l2(dout + nt * 128 * D, 128 * D * 2);
+            bulk_prefetch_l2(sgrad + (nt * NA) * 1024, XC * 2048);
+            bulk_prefetch_l2(sgrad + (nt * NA + 2 * XC + CCH) * 1024, CCH * 2048);
+          }
         }
         // dout tile (row-major external tensor) -> T8: 512 16-byte pieces, 16 per lane
         {
@@ -160,6 +169,7 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
         auto mma2 = [&](int t) {
           const int it = t - T0, s = it & 1, b = t / tiles_per_batch, i_in_b = t % tiles_per_batch;
           ok = mbar_wait(&epi1_done[s], (it >> 1) & 1) && ok;
+          if (it >= 2) ok = mbar_wait(&acc_free[s], ((it >> 1) - 1) & 1) && ok;     // dCc of tile t-2 has been read
           tc_fence_after();
           const uint32_t sb = sbase + s * B1_STG_B, tb = tbase + s * B1_TSTG;
           const uint32_t aDout = sb, aC = sb + DC * 2048, aCat = sb + (DC + CCH) * 2048, aXY = sb + (DC + CCH + 16) * 2048;
@@ -187,7 +197,7 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
         for (int t = T0; t < T1; ++t) {
           const int it = t - T0, s = it & 1, b = t / tiles_per_batch;
           ok = mbar_wait(&full[s], (it >> 1) & 1) && ok;
-          if (it >= 2) ok = mbar_wait(&acc_free[s], ((it >> 1) - 1) & 1) && ok;
+          if (it >= 2) ok = mbar_wait(&gy_free[s], ((it >> 1) - 1) & 1) && ok;
           tc_fence_after();
           const uint32_t sb = sbase + s * B1_STG_B, tb = tbase + s * B1_TSTG;
           const uint32_t img = ibase + (b & 1) * SIMG_B;
@@ -367,7 +377,7 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
         tc_fence_before();
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&epi1_done[s]);
+        if (lane == 0) { mbar_arrive(&epi1_done[s]); mbar_arrive(&gy_free[s]); }
         pt.mark(4);
         if (t > T0) epi2(t - 1);
         sgc_prev = sgc_cur;
@@ -422,7 +432,7 @@ k_bwd2_ws(const bf16* __restrict__ act, const bf16* __restrict__ sgrad, const bf
           bf16* __restrict__ dact, bf16* __restrict__ ddt, float* __restrict__ head_part /* [CTA][dD | dA_log | ddt_bias] */,
           int tiles_per_batch, int num_tiles, int tiles_per_cta, int* __restrict__ status) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full[2], mma1_done[2], epi1_done[2], mma2_done[2], acc_free[2];
+  __shared__ uint64_t full[2], mma1_done[2], epi1_done[2], mma2_done[2], acc_free[2], g_free[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_bias[NH], s_eA[NH], s_D[NH];
   __shared__ float s_red[8][24];
@@ -437,7 +447,8 @@ k_bwd2_ws(const bf16* __restrict__ act, const bf16* __restrict__ sgrad, const bf
       mbar_init(&mma1_done[i], 1);
       mbar_init(&epi1_done[i], 8);
       mbar_init(&mma2_done[i], 1);
-      mbar_init(&acc_free[i], 8);
+      mbar_init(&acc_free[i], 8);        // dBc columns consumed (second epilogue)
+      mbar_init(&g_free[i], 8);          // G columns consumed (first epilogue): MMA1 of tile t+2 does not wait for EPI2
     }
     fence_mbar_init();
   }
@@ -464,6 +475,13 @@ k_bwd2_ws(const bf16* __restrict__ act, const bf16* __restrict__ sgrad, const bf
           bulk_g2s(sb, act + ((long long)t * NA + XC) * 1024, (XC + CCH) * 2048, &full[s]);                 // x | B
           bulk_g2s(sb + (XC + CCH) * 2048, dact + ((long long)t * NA + XC) * 1024, XC * 2048, &full[s]);   // dy (written by B1)
           bulk_g2s(sb + (XC + CCH + XC) * 2048, dtraw + (long long)t * 2 * 1024, 2 * 2048, &full[s]);      // dt columns
+          if (t + 1 < T1) {     // L2 prefetch of the next tile (see k_bwd1_ws)
+            const long long nt = t + 1;
+            bulk_prefetch_l2(act + (nt * NA + XC) * 1024, (XC + CCH) * 2048);
+            bulk_prefetch_l2(dact + (nt * NA + XC) * 1024, XC * 2048);
+            bulk_prefetch_l2(dtraw + nt * 2 * 1024, 2 * 2048);
+            bulk_prefetch_l2(sgrad + (nt * NA + XC) * 1024, (XC + CCH) * 2048);
+          }
         }
         fence_async_smem();
         mbar_arrive(&full[s]);
@@ -475,6 +493,7 @@ k_bwd2_ws(const bf16* __restrict__ act, const bf16* __restrict__ sgrad, const bf
         auto mma2 = [&](int t) {
           const int it = t - T0, s = it & 1, b = t / tiles_per_batch;
           ok = mbar_wait(&epi1_done[s], (it >> 1) & 1) && ok;
+          if (it >= 2) ok = mbar_wait(&acc_free[s], ((it >> 1) - 1) & 1) && ok;     // dBc of tile t-2 has been read
           tc_fence_after();
           const uint32_t tb = tbase + s * B2_TSTG, img = ibase + (b & 1) * SIMG_B;
           const uint64_t dX = make_desc(sbase + s * B2_STG_B, 2048, 128), dBh = make_desc(img + 8192, 512, 128), dBl = make_desc(img + 12288, 512, 128);
@@ -490,7 +509,7 @@ k_bwd2_ws(const bf16* __restrict__ act, const bf16* __restrict__ sgrad, const bf
         for (int t = T0; t < T1; ++t) {
           const int it = t - T0, s = it & 1, b = t / tiles_per_batch;
           ok = mbar_wait(&full[s], (it >> 1) & 1) && ok;
-          if (it >= 2) ok = mbar_wait(&acc_free[s], ((it >> 1) - 1) & 1) && ok;
+          if (it >= 2) ok = mbar_wait(&g_free[s], ((it >> 1) - 1) & 1) && ok;
           tc_fence_after();
           const uint32_t tb = tbase + s * B2_TSTG, img = ibase + (b & 1) * SIMG_B;
           const uint64_t dB = make_desc(sbase + s * B2_STG_B + XC * 2048, 2048, 128), dAh = make_desc(img, DI * 16, 128), dAl = make_desc(img + 4096, DI * 16, 128);
@@ -602,7 +621,7 @@ k_bwd2_ws(const bf16* __restrict__ act, const bf16* __restrict__ sgrad, const bf
         tc_fence_before();
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&epi1_done[s]);
+        if (lane == 0) { mbar_arrive(&epi1_done[s]); mbar_arrive(&g_free[s]); }
         if (t > T0) epi2(t - 1);
         sgb_prev[0] = sgb_cur[0];
         sgb_prev[1] = sgb_cur[1];
