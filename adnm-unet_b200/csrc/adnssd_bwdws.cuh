@@ -283,23 +283,33 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
         tc_fence_after();
         pt.mark(0);
         const uint32_t ta = tbase + ((uint32_t)(q * 32) << 16) + s * B1_TSTG;
-        // ---- y, partial LayerNorm sums over this quarter's 16 channels
-        float y[16];
+        // ---- all three accumulator slices of this thread (Y, g_y, g_z: 48 columns) are requested up front so that the
+        // TMEM latency is exposed once per tile instead of three times
+        float y[16], gy[16], gz[16];
         float p1 = 0.f, p2 = 0.f;
         {
-          float v[16], x0[8], x1[8];
-          tmem_ld16(ta + B1_COL_Y + cq * 16, v);
+          float x0[8], x1[8];
+          tmem_ld16(ta + B1_COL_Y + cq * 16, y);
+          tmem_ld16(ta + cq * 16, gy);
+          tmem_ld16(ta + DI + cq * 16, gz);
           unpack8(*reinterpret_cast<const uint4*>(sXYRow + (2 * cq) * 2048), x0);
           unpack8(*reinterpret_cast<const uint4*>(sXYRow + (2 * cq + 1) * 2048), x1);
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            y[j] = fmaf(sDh[cq * 16 + j], x0[j], v[j]);
-            y[8 + j] = fmaf(sDh[cq * 16 + 8 + j], x1[j], v[8 + j]);
+            y[j] = fmaf(sDh[cq * 16 + j], x0[j], y[j]);
+            y[8 + j] = fmaf(sDh[cq * 16 + 8 + j], x1[j], y[8 + j]);
           }
         }
+        {   // two interleaved partial sums per statistic (shorter dependency chains)
+          float q1 = 0.f, q2 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) { p1 += y[c]; p2 = fmaf(y[c], y[c], p2); }
+          for (int c = 0; c < 16; c += 2) {
+            p1 += y[c]; p2 = fmaf(y[c], y[c], p2);
+            q1 += y[c + 1]; q2 = fmaf(y[c + 1], y[c + 1], q2);
+          }
+          p1 += q1; p2 += q2;
+        }
         sXch[(0 * 4 + cq) * 128 + row] = make_float2(p1, p2);
         pt.mark(1);
         asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -320,18 +330,17 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
           *reinterpret_cast<uint4*>(sCatRow + (2 * cq + cg) * 2048) = pack8(v);
         }
         // ---- LN backward: dyh = alpha1 * g_y * gamma ; dy = rstd * (dyh - mean(dyh) - yhat * mean(dyh*yhat))
-        float gy[16];
         float m1 = 0.f, m2 = 0.f;
         {
-          float v[16];
-          tmem_ld16(ta + cq * 16, v);
-          tmem_wait_ld();
+          float n1 = 0.f, n2 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            gy[j] = a1 * v[j] * sG[cq * 16 + j];
-            m1 += gy[j];
-            m2 = fmaf(gy[j], y[j], m2);
+          for (int j = 0; j < 16; j += 2) {
+            gy[j] = a1 * gy[j] * sG[cq * 16 + j];
+            gy[j + 1] = a1 * gy[j + 1] * sG[cq * 16 + j + 1];
+            m1 += gy[j]; m2 = fmaf(gy[j], y[j], m2);
+            n1 += gy[j + 1]; n2 = fmaf(gy[j + 1], y[j + 1], n2);
           }
+          m1 += n1; m2 += n2;
         }
         sXch[(1 * 4 + cq) * 128 + row] = make_float2(m1, m2);
         pt.mark(3);
@@ -357,13 +366,11 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
         }
         // ---- dpre_z = alpha1 * g_z * SiLU'(pre_z)
         {
-          float v[16], s0[8], s1[8], o0[8], o1[8];
-          tmem_ld16(ta + DI + cq * 16, v);
+          float s0[8], s1[8], o0[8], o1[8];
           unpack8(sgz[0], s0);
           unpack8(sgz[1], s1);
-          tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { o0[j] = a1 * v[j] * s0[j]; o1[j] = a1 * v[8 + j] * s1[j]; }
+          for (int j = 0; j < 8; ++j) { o0[j] = a1 * gz[j] * s0[j]; o1[j] = a1 * gz[8 + j] * s1[j]; }
           *reinterpret_cast<uint4*>(drow + (long long)(2 * cq) * 1024) = pack8(o0);
           *reinterpret_cast<uint4*>(drow + (long long)(2 * cq + 1) * 1024) = pack8(o1);
         }

@@ -619,6 +619,9 @@ k_readout(const bf16* __restrict__ act, int CC, const float* __restrict__ S, con
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tbase, TCOLS);
+  // Fail loudly without a host synchronisation: a kernel of this forward pass that timed out on a barrier (async-pipe
+  // fault) left a non-zero status word; the last kernel of the pass then poisons the output with NaNs.
+  if (blockIdx.x == 0 && tid < 8 && *reinterpret_cast<volatile int*>(status) != 0) out[tid] = __float2bfloat16_rn(__int_as_float(0x7fc00000));
 }
 
 // Build the bf16 hi / lo images of a per-sample fp32 matrix M[b][j][c] (GN x DI, the state S' or its gradient)
@@ -1336,9 +1339,15 @@ k_bwd4(const bf16* __restrict__ draw, int ldr, int dip, const bf16* __restrict__
 //   remaining blocks             dD, dA_log, ddt_bias and the ten conv weight gradients from dK (shared finalize_body)
 __global__ void __launch_bounds__(256)
 k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ Rt, float* __restrict__ sdout,
-                int D, int Di, int GN, int nh, int dip, int nb_in, int nb_rest, int rt_parts) {
+                int D, int Di, int GN, int nh, int dip, int nb_in, int nb_rest, int rt_parts, const int* __restrict__ status,
+                bf16* __restrict__ du) {
   __shared__ float red[8][33];
   const int tid = threadIdx.x;
+  // Fail loudly without a host synchronisation: if a kernel of this backward pass flagged a pipeline fault (barrier
+  // time-out), the gradients that leave this last kernel are poisoned with NaNs (and so is du[0..7]).
+  const bool bad = *status != 0;
+  const float poison = bad ? __int_as_float(0x7fc00000) : 0.f;
+  if (bad && blockIdx.x == 0 && tid < 8) du[tid] = __float2bfloat16_rn(poison);
   // ---- phase 1 (row-kernel / warp-specialised path): the backward kernels left one slab of partial sums per CTA instead
   // of contended atomics.  Every block adds up 32-element chunks (8 slab lanes x 32 elements, coalesced), then the grid
   // meets at a counter (this small grid is always co-resident) and phase 2 reads the reduced arrays.
@@ -1412,7 +1421,7 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ R
       float t = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) t += red[k][tid & 31];
-      g.in_proj_w[e] = t;
+      g.in_proj_w[e] = t + poison;
     }
     return;
   }
@@ -1425,7 +1434,7 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ R
     for (int d = tid; d < D; d += 32) {
       const float r = Rt[c * D + d], wv = w.out_proj_w[d * 2 * Di + c], sd = sdout[d];
       const float rawv = c < Di ? w.norm_w[c] * r + w.norm_b[c] * sd : r;
-      if (g.out_proj_w) g.out_proj_w[d * 2 * Di + c] = a1 * rawv;
+      if (g.out_proj_w) g.out_proj_w[d * 2 * Di + c] = a1 * rawv + poison;
       da = fmaf(wv, rawv, da);
       dg = fmaf(wv, r, dg);
       db = fmaf(wv, sd, db);
@@ -1433,10 +1442,10 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ R
     dg = warp_sum(dg); db = warp_sum(db); da = warp_sum(da);
     if (tid == 0) {
       if (c < Di) {
-        if (g.norm_w) g.norm_w[c] = a1 * dg;
-        if (g.norm_b) g.norm_b[c] = a1 * db;
+        if (g.norm_w) g.norm_w[c] = a1 * dg + poison;
+        if (g.norm_b) g.norm_b[c] = a1 * db + poison;
       }
-      if (g.alpha1) atomicAdd(g.alpha1, da);     // g.alpha1 is zeroed by the host before this launch
+      if (g.alpha1) atomicAdd(g.alpha1, da + poison);     // g.alpha1 is zeroed by the host before this launch
     }
     return;
   }
@@ -1975,7 +1984,7 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
     // every block of this grid (344 x 256 threads at the benchmark shape, < 3 blocks per SM) is co-resident, which the
     // counter hand-off between the two phases relies on; a 148 x 6 grid for phase 1 measured no faster
     const int fgrid = nb_in + 2 * d.Di + nb_rest;
-    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<fgrid, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest, rt_parts); }
+    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<fgrid, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest, rt_parts, F.status, du); }
     ADN_CHECK_LAUNCH();
     return ADN_OK;
   }
@@ -2003,7 +2012,7 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   {
     if (g.alpha1) ADN_CHECK_CUDA(cudaMemsetAsync(g.alpha1, 0, sizeof(float), st));
     const int nb_in = cdiv(d.dip * d.D, 32), nb_rest = 8;
-    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<nb_in + 2 * d.Di + nb_rest, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest, 0); }
+    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<nb_in + 2 * d.Di + nb_rest, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest, 0, F.status, du); }
   }
   ADN_CHECK_LAUNCH();
   return ADN_OK;
