@@ -74,9 +74,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf16* __restrict__ sgrad, const float* __restrict__ S,
           const float* __restrict__ Dp, const float* __restrict__ gamma, const float* __restrict__ alpha1p,
           const bf16* __restrict__ Wout, bf16* __restrict__ dact, float* __restrict__ Rt, float* __restrict__ sdout,
-          float* __restrict__ dS, int tiles_per_batch, int num_tiles, int tiles_per_cta, int* __restrict__ status) {
+          float* __restrict__ dS, int tiles_per_batch, int num_tiles, int tiles_per_cta, int* __restrict__ status,
+          float* __restrict__ dalpha1) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[2], mma1_done[2], epi1_done[2], mma2_done[2], acc_free[2], gy_free[2], s_done, s_free;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && dalpha1 != nullptr) *dalpha1 = 0.f;   // k_finalize_fast accumulates into it
   __shared__ uint32_t tmem_slot;
   __shared__ float sG[DI], sDh[DI];
   uint8_t* sStg = smem;

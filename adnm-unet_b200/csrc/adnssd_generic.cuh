@@ -681,6 +681,7 @@ struct BwdWs {
   float* zero_begin;
   GradAcc acc;
   float* dS;
+  int* status;
   size_t zero_bytes;
   TW *g, *ybuf, *ynbuf, *dact, *draw;
   size_t bytes;
@@ -706,6 +707,7 @@ struct BwdWs {
     acc.dalpha1 = c.take<float>(1);
     acc.dK = c.take<float>((size_t)d.CC * 9);
     acc.sync_counter = c.take<int>(64);
+    status = c.take<int>(64);      // pipeline-fault word of the backward pass, zeroed with the accumulators
     dS = c.take<float>((size_t)d.B * d.GN * d.Di);
     zero_bytes = c.off - z0;
     g = c.take<TW>((size_t)d.T * 2 * d.Di);

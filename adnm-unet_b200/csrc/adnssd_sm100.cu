@@ -1458,8 +1458,14 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ R
 __global__ void k_prep(ConvWeightPtrs cw, float* __restrict__ Kc, int Di, int CC, const float* __restrict__ win,
                        bf16* __restrict__ whi, bf16* __restrict__ wlo, int n_in, const float* __restrict__ wout,
                        bf16* __restrict__ wout_bf, int n_out, bf16* __restrict__ wt_hi, bf16* __restrict__ wt_lo, int n_wt,
-                       int D, int dip, bf16* __restrict__ wtf, bf16* __restrict__ wtb) {
+                       int D, int dip, bf16* __restrict__ wtf, bf16* __restrict__ wtb, float* __restrict__ zero_f,
+                       int n_zero_f, int* __restrict__ zero_status) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // row-kernel path: this first kernel of the forward pass also clears the state accumulator and the fault word
+  // (two memset nodes less per step)
+  if (zero_f != nullptr)
+    for (int j = i; j < n_zero_f; j += gridDim.x * blockDim.x) zero_f[j] = 0.f;
+  if (zero_status != nullptr && i < 64) zero_status[i] = 0;
   if (wtf != nullptr) rowconv::prep_rowconv(cw, win, wtf, wtb, i);   // conv-as-GEMM weight images (row kernels)
   if (wt_hi != nullptr && i < n_wt) {   // element ((jc*D + d)*8 + q) of the W_in^T image = W_in[jc*8+q][d]
     const int q = i & 7, d = (i >> 3) % D, j = ((i >> 3) / D) * 8 + q;
@@ -1874,19 +1880,18 @@ int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* 
   const bool training = saved != nullptr;
   PrepBufs P(d, training ? (char*)saved + S.bytes : (char*)ws + W.bytes + F.bytes);
   const long long Tt = d.T;
-  ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
   {
     const int n_in = d.dip * d.D, n_out = d.D * 2 * d.Di, n_wt = P.wt_chunks * d.D * 8;
     const bool rows = rowconv_supported(d);
+    if (!rows) ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
     const int n = max(max(max(max(n_in, n_out), d.CC), n_wt), rows ? 9 * rowconv::DIP * rowconv::D : 0);
-    { ADN_KERNEL("k_prep", st); k_prep<<<cdiv(n, 256), 256, 0, st>>>(conv_ptrs(w), P.Kc, d.Di, d.CC, w.in_proj_w, P.Whi, P.Wlo, n_in, w.out_proj_w, P.Wout, n_out, P.WT_hi, P.WT_lo, n_wt, d.D, d.dip, rows ? P.WtF : nullptr, P.WtB); }
+    { ADN_KERNEL("k_prep", st); k_prep<<<cdiv(n, 256), 256, 0, st>>>(conv_ptrs(w), P.Kc, d.Di, d.CC, w.in_proj_w, P.Whi, P.Wlo, n_in, w.out_proj_w, P.Wout, n_out, P.WT_hi, P.WT_lo, n_wt, d.D, d.dip, rows ? P.WtF : nullptr, P.WtB, rows ? S.S : nullptr, d.B * d.GN * d.Di, rows ? F.status : nullptr); }
   }
   if (rowconv_supported(d)) {
     // (1)-(4a) fused: in_proj + conv + SiLU + decay weights + state, one image row per step (adnssd_rowconv.cuh).
     // The `raw` slot of the saved tensors only holds the dt columns, as a TL tensor with 2 chunks per tile, and the `wdec`
     // slot (T x nh floats = T x D bf16 for headdim 4) holds a TL copy of u for the bulk copies of the backward pass.
     static_assert(sizeof(float) * rowconv::NH == sizeof(bf16) * rowconv::D, "u_tl does not fit the wdec slot");
-    ADN_CHECK_CUDA(cudaMemsetAsync(S.S, 0, (size_t)d.B * d.GN * d.Di * sizeof(float), st));
     int rc = set_smem(rowconv::k_fconv, rowconv::FC_SMEM);
     if (rc) return rc;
     const int rows_total = d.B * d.H, per = rows_per_cta(rows_total, 148), grid = cdiv(rows_total, per);
@@ -1936,15 +1941,21 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   FastWs F(d, (char*)ws + W.bytes);
   SavedBufs<T> S(d, const_cast<void*>(saved));
   PrepBufs P(d, (char*)const_cast<void*>(saved) + S.bytes);   // prepared by the forward pass of this step
-  ADN_CHECK_CUDA(cudaMemsetAsync(W.zero_begin, 0, W.zero_bytes, st));
-  ADN_CHECK_CUDA(cudaMemsetAsync(F.Rt, 0, ((size_t)2 * d.Di * d.D + d.D) * sizeof(float), st));
-  ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
+  ADN_CHECK_CUDA(cudaMemsetAsync(W.zero_begin, 0, W.zero_bytes, st));     // accumulators, dS', hand-off counter, W.status
   // ---- phase B1: dout -> dy, dzc, dCc ; reductions Rt, dS'
   if (rowconv_supported(d)) {
     // B1 / B2 write dpre = dact * SiLU'(pre) directly; ddt goes to a compact TL tensor (2 chunks per tile) in W.draw
     int rc, rt_parts = 0;
     const char* ews = getenv("ADN_BWD_WS");      // diagnostics: ADN_BWD_WS=0 keeps the monolithic tile kernels
-    if (ews && ews[0] == '0') {
+    const bool ws_path = !(ews && ews[0] == '0');
+    // warp-specialised path: ONE memset per backward pass (the fault word lives in the zeroed region, Rt / sum(dout) are
+    // slabs that are fully overwritten, and k_bwd1_ws clears the alpha1 gradient that k_finalize_fast accumulates into)
+    int* status = ws_path ? W.status : F.status;
+    if (!ws_path) {
+      ADN_CHECK_CUDA(cudaMemsetAsync(F.Rt, 0, ((size_t)2 * d.Di * d.D + d.D) * sizeof(float), st));
+      ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
+    }
+    if (!ws_path) {
       rc = launch_bwd1<64, 32>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st, S.pre);
       if (rc) return rc;
       rc = launch_bwd2<64, 32>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st, S.pre, 2, 0);
@@ -1953,10 +1964,10 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
       const int tpb = d.L / 128, nt = tpb * d.B, per = cdiv(nt, 148), grid = cdiv(nt, per);
       rc = set_smem(bwdws::k_bwd1_ws, bwdws::B1_SMEM);
       if (rc) return rc;
-      { ADN_KERNEL("k_bwd1_ws", st); bwdws::k_bwd1_ws<<<grid, bwdws::WS_THREADS, bwdws::B1_SMEM, st>>>(dout, S.act, S.pre, S.S, w.D, w.norm_w, w.alpha1, P.Wout, W.dact, F.Rt, F.sdout, W.dS, tpb, nt, per, F.status); }
+      { ADN_KERNEL("k_bwd1_ws", st); bwdws::k_bwd1_ws<<<grid, bwdws::WS_THREADS, bwdws::B1_SMEM, st>>>(dout, S.act, S.pre, S.S, w.D, w.norm_w, w.alpha1, P.Wout, W.dact, F.Rt, F.sdout, W.dS, tpb, nt, per, status, g.alpha1); }
       rc = set_smem(bwdws::k_bwd2_ws, bwdws::B2_SMEM);
       if (rc) return rc;
-      { ADN_KERNEL("k_bwd2_ws", st); bwdws::k_bwd2_ws<<<grid, 320, bwdws::B2_SMEM, st>>>(S.act, S.pre, S.raw, W.dS, w.dt_bias, w.A_log, w.D, W.dact, W.draw, F.head_part, tpb, nt, per, F.status); }
+      { ADN_KERNEL("k_bwd2_ws", st); bwdws::k_bwd2_ws<<<grid, 320, bwdws::B2_SMEM, st>>>(S.act, S.pre, S.raw, W.dS, w.dt_bias, w.A_log, w.D, W.dact, W.draw, F.head_part, tpb, nt, per, status); }
       rt_parts = grid;
       W.acc.head_part = F.head_part;
       W.acc.head_parts = grid;
@@ -1966,28 +1977,30 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
       rc = set_smem(rowconv::k_bconv_du, rowconv::DU_SMEM);
       if (rc) return rc;
       const int per = rows_per_cta(rows_total, 148), grid = cdiv(rows_total, per);
-      { ADN_KERNEL("k_bconv_du", st); rowconv::k_bconv_du<<<grid, 192, rowconv::DU_SMEM, st>>>(W.dact, W.draw, P.WtB, du, d.H, rows_total, per, F.status, getenv("ADN_DU_DBG") ? atoi(getenv("ADN_DU_DBG")) : 0); }
+      { ADN_KERNEL("k_bconv_du", st); rowconv::k_bconv_du<<<grid, 192, rowconv::DU_SMEM, st>>>(W.dact, W.draw, P.WtB, du, d.H, rows_total, per, status, getenv("ADN_DU_DBG") ? atoi(getenv("ADN_DU_DBG")) : 0); }
     }
     {
       rc = set_smem(rowconv::k_bconv_wg, rowconv::WG_SMEM);
       if (rc) return rc;
       const int cpb = max(1, min(74, rows_total)), per = cdiv(rows_total, cpb), parts = cdiv(rows_total, per);
-      { ADN_KERNEL("k_bconv_wg", st); rowconv::k_bconv_wg<<<2 * parts, 192, rowconv::WG_SMEM, st>>>(W.dact, W.draw, reinterpret_cast<const bf16*>(S.wdec), w.in_proj_w, P.Kc, F.dK_part, F.dWin_part, d.H, rows_total, per, parts, F.status); }
+      { ADN_KERNEL("k_bconv_wg", st); rowconv::k_bconv_wg<<<2 * parts, 192, rowconv::WG_SMEM, st>>>(W.dact, W.draw, reinterpret_cast<const bf16*>(S.wdec), w.in_proj_w, P.Kc, F.dK_part, F.dWin_part, d.H, rows_total, per, parts, status); }
       W.acc.dWin_part = F.dWin_part;
       W.acc.dWin_parts = parts;
       W.acc.dK_part = F.dK_part;
       W.acc.dK_parts = parts;
       W.acc.dK_stride = d.CC * 9;
     }
-    if (g.alpha1) ADN_CHECK_CUDA(cudaMemsetAsync(g.alpha1, 0, sizeof(float), st));
+    if (g.alpha1 && !ws_path) ADN_CHECK_CUDA(cudaMemsetAsync(g.alpha1, 0, sizeof(float), st));
     const int nb_in = cdiv(d.dip * d.D, 32), nb_rest = 8;
     // every block of this grid (344 x 256 threads at the benchmark shape, < 3 blocks per SM) is co-resident, which the
     // counter hand-off between the two phases relies on; a 148 x 6 grid for phase 1 measured no faster
     const int fgrid = nb_in + 2 * d.Di + nb_rest;
-    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<fgrid, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest, rt_parts, F.status, du); }
+    { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<fgrid, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest, rt_parts, status, du); }
     ADN_CHECK_LAUNCH();
     return ADN_OK;
   }
+  ADN_CHECK_CUDA(cudaMemsetAsync(F.Rt, 0, ((size_t)2 * d.Di * d.D + d.D) * sizeof(float), st));
+  ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
   int rc = d.GN == 32 ? launch_bwd1<64, 32>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st, nullptr)
                       : launch_bwd1<64, 128>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st, nullptr);
   if (rc) return rc;
