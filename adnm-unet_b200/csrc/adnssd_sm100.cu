@@ -1768,8 +1768,8 @@ static bool rowconv_supported(const MixerDims& d) {
 }
 
 bool sm100_supported(const MixerDims& d) {
-  // instantiated tile shapes: d_model 32 (d_inner 64), headdim 4, ngroups*d_state in {32, 128}
-  return d.D == 32 && d.Di == 64 && d.P == 4 && (d.GN == 32 || d.GN == 128) && d.dip % 16 == 0 && d.dip <= 512 && d.ldr == d.dip && d.CC % 32 == 0 && d.L % 128 == 0;
+  // instantiated tile shapes: d_model 32 (d_inner 64), headdim 4, ngroups*d_state in {32, 64, 128} (d_state 16, 32, 64)
+  return d.D == 32 && d.Di == 64 && d.P == 4 && (d.GN == 32 || d.GN == 64 || d.GN == 128) && d.dip % 16 == 0 && d.dip <= 512 && d.ldr == d.dip && d.CC % 32 == 0 && d.L % 128 == 0;
 }
 
 template <typename K>
@@ -1925,10 +1925,13 @@ int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* 
   (void)Tt;
   // (4a) state on tcgen05 (reduction over tokens), (4b)+(5) readout + LayerNorm + out_proj on tcgen05
   ADN_CHECK_CUDA(cudaMemsetAsync(S.S, 0, (size_t)d.B * d.GN * d.Di * sizeof(float), st));
-  rc = d.GN == 32 ? launch_state<64, 32>(d, S.act, S.raw, w, S.S, F.status, st) : launch_state<64, 128>(d, S.act, S.raw, w, S.S, F.status, st);
+  rc = d.GN == 32 ? launch_state<64, 32>(d, S.act, S.raw, w, S.S, F.status, st)
+       : d.GN == 64 ? launch_state<64, 64>(d, S.act, S.raw, w, S.S, F.status, st)
+                    : launch_state<64, 128>(d, S.act, S.raw, w, S.S, F.status, st);
   if (rc) return rc;
   rc = d.GN == 32 ? launch_readout<64, 32>(d, S.act, S.S, w, P.Wout, out, F.status, st)
-                  : launch_readout<64, 128>(d, S.act, S.S, w, P.Wout, out, F.status, st);
+       : d.GN == 64 ? launch_readout<64, 64>(d, S.act, S.S, w, P.Wout, out, F.status, st)
+                    : launch_readout<64, 128>(d, S.act, S.S, w, P.Wout, out, F.status, st);
   if (rc) return rc;
   ADN_CHECK_LAUNCH();
   return ADN_OK;
@@ -2002,11 +2005,13 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   ADN_CHECK_CUDA(cudaMemsetAsync(F.Rt, 0, ((size_t)2 * d.Di * d.D + d.D) * sizeof(float), st));
   ADN_CHECK_CUDA(cudaMemsetAsync(F.status, 0, 256, st));
   int rc = d.GN == 32 ? launch_bwd1<64, 32>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st, nullptr)
-                      : launch_bwd1<64, 128>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st, nullptr);
+           : d.GN == 64 ? launch_bwd1<64, 64>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st, nullptr)
+                        : launch_bwd1<64, 128>(d, dout, S.act, S.S, w, P, F, W.dact, W.dS, st, nullptr);
   if (rc) return rc;
   // ---- phase B2: dS' -> dxc, dBc, ddt
   rc = d.GN == 32 ? launch_bwd2<64, 32>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st, nullptr, d.ldr >> 3, d.CC >> 3)
-                  : launch_bwd2<64, 128>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st, nullptr, d.ldr >> 3, d.CC >> 3);
+       : d.GN == 64 ? launch_bwd2<64, 64>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st, nullptr, d.ldr >> 3, d.CC >> 3)
+                    : launch_bwd2<64, 128>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st, nullptr, d.ldr >> 3, d.CC >> 3);
   if (rc) return rc;
   // ---- conv backward (dpre formed in shared memory; transposed conv + kernel gradient)
   {

@@ -78,7 +78,8 @@ def test_mixer_matches_reference_golden_model_scale(golden_dir, name, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
-@pytest.mark.parametrize("cfg", [(16, 4, 8, 3, 5, 9), (32, 4, 16, 1, 33, 17), (48, 8, 16, 2, 7, 7), (256, 4, 16, 2, 4, 4)],
+@pytest.mark.parametrize("cfg", [(16, 4, 8, 3, 5, 9), (32, 4, 16, 1, 33, 17), (48, 8, 16, 2, 7, 7), (256, 4, 16, 2, 4, 4),
+                                 (32, 4, 32, 2, 16, 16), (32, 4, 64, 2, 8, 32)],   # d_state 32 / 64: tcgen05 tile kernels
                          ids=lambda c: "D%d_P%d_N%d_B%d_%dx%d" % c)
 def test_mixer_matches_oracle_ragged_shapes(cfg, dtype):
     """Non-square and odd token grids, tiny and large d_model: compared with the CPU oracle in fp64."""
