@@ -99,39 +99,53 @@ __device__ __forceinline__ void prep_rowconv(const ConvWeightPtrs& cw, const flo
   }
 }
 
-// One warp: copy one row-major u row (128 tokens x 32 channels, 8 KB contiguous) into positions 1..128 of a padded slot.
-// NCOPY = 3 writes the row three times, the copies UCOPY_B = 4*CHB - 16 bytes apart: chunk (b, dc) of the 12-chunk operand
-// that starts at the slot base with chunk stride CHB is then chunk dc of the row shifted by b positions, i.e. the three
-// horizontal taps become ONE operand with N (or K) = 96.  Consecutive copies overlap in one 16-byte padding position
-// (the last pad of copy b and the first pad of copy b+1), which is zero in both.
-constexpr int UCOPY_B = 4 * CHB - 16;
-constexpr int USLOT3_B = 2 * UCOPY_B + 4 * CHB;    // 24928 bytes
+// Token grids wider than 128 (W = 128 * TPR) are processed as B * TPR independent "strip images" of H rows x 128 tokens:
+// row index R of the kernels -> strip image R / H (= b * TPR + xt), image row y = R % H -> global 128-token tile
+// (b * H + y) * TPR + xt of the TL tensors.  Vertical neighbours are consecutive rows of a strip; the horizontal
+// neighbours across a strip edge come from the adjacent tile of the same image row (pad positions of the row slots).
+struct Strip {
+  int H, TPR;
+  __device__ __forceinline__ int tile(int R) const {
+    const int img = R / H, y = R - img * H, b = img / TPR, xt = img - b * TPR;
+    return (b * H + y) * TPR + xt;
+  }
+  __device__ __forceinline__ int xt(int R) const { return (R / H) % TPR; }
+  __device__ __forceinline__ int sample(int R) const { return (R / H) / TPR; }
+};
 
-template <int NCOPY>
-__device__ __forceinline__ void urow_load(uint8_t* slot, const bf16* __restrict__ urow, int lane) {
+// One warp: copy one row-major u tile (128 tokens x 32 channels, 8 KB contiguous) into positions 1..128 of a padded slot and
+// its two horizontal neighbour tokens (or zeros at the image border) into the pad positions 0 and 129.
+__device__ __forceinline__ void urow_load(uint8_t* slot, const bf16* __restrict__ u, int tile, bool has_left, bool has_right,
+                                          int lane) {
+  const bf16* urow = u + (long long)tile * 128 * D;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int piece = i * 32 + lane, tok = piece >> 2, ch = piece & 3;
-#pragma unroll
-    for (int c = 0; c < NCOPY; ++c) cp_async16(slot + c * UCOPY_B + ch * CHB + (1 + tok) * 16, urow + piece * 8, 16);
+    cp_async16(slot + ch * CHB + (1 + tok) * 16, urow + piece * 8, 16);
+  }
+  if (lane < 8) {
+    const int side = lane >> 2, ch = lane & 3;
+    const bool valid = side ? has_right : has_left;
+    const bf16* src = valid ? (side ? urow + 128 * D + ch * 8 : urow - D + ch * 8) : urow;
+    cp_async16(slot + ch * CHB + (side ? 129 : 0) * 16, src, valid ? 16 : 0);      // src_bytes 0 zero-fills
   }
 }
 
 // Producer warp of the u ring: rows [gfirst, glast] -> slot (g - gfirst) % NSLOT; full[] has count 32, empty[] count 1.
 // Up to LAG + 1 row loads are in flight (cp.async groups); a row is published once its group has landed.
-// u_tl != nullptr: rows [tl_first, tl_last] are also written back to global memory in the TL layout ([row][4 chunks][128][8]),
+// u_tl != nullptr: rows [tl_first, tl_last] are also written back to global memory in the TL layout ([tile][4 chunks][128][8]),
 // from which the backward kernels fetch them with bulk copies.
-template <int NCOPY, int NSLOT>
-__device__ __forceinline__ void urow_producer(uint8_t* sU, const bf16* __restrict__ u, int gfirst, int glast, uint64_t* full,
-                                              uint64_t* empty, int lane, bf16* __restrict__ u_tl = nullptr, int tl_first = 0,
-                                              int tl_last = -1) {
-  constexpr int SLOT = NCOPY == 1 ? USLOT_B : USLOT3_B;
+template <int NSLOT>
+__device__ __forceinline__ void urow_producer(uint8_t* sU, const bf16* __restrict__ u, Strip sm, int gfirst, int glast,
+                                              uint64_t* full, uint64_t* empty, int lane, bf16* __restrict__ u_tl = nullptr,
+                                              int tl_first = 0, int tl_last = -1) {
   constexpr int LAG = 2;
   const int n = glast - gfirst + 1;
   for (int i = 0; i < n + LAG; ++i) {
     if (i < n) {
       if (i >= NSLOT) mbar_wait(&empty[i % NSLOT], ((i / NSLOT) - 1) & 1);
-      urow_load<NCOPY>(sU + (i % NSLOT) * SLOT, u + (long long)(gfirst + i) * 128 * D, lane);
+      const int g = gfirst + i, xt = sm.xt(g);
+      urow_load(sU + (i % NSLOT) * USLOT_B, u, sm.tile(g), xt > 0, xt < sm.TPR - 1, lane);
     }
     cp_async_commit();
     if (i >= LAG) {
@@ -141,8 +155,8 @@ __device__ __forceinline__ void urow_producer(uint8_t* sU, const bf16* __restric
       const int g = gfirst + i - LAG;
       if (u_tl != nullptr && g >= tl_first && g <= tl_last) {
         __syncwarp();     // the row was fetched by all 32 lanes
-        const uint8_t* slot = sU + ((i - LAG) % NSLOT) * SLOT;
-        uint4* dst = reinterpret_cast<uint4*>(u_tl + (long long)g * 128 * D);
+        const uint8_t* slot = sU + ((i - LAG) % NSLOT) * USLOT_B;
+        uint4* dst = reinterpret_cast<uint4*>(u_tl + (long long)sm.tile(g) * 128 * D);
 #pragma unroll 4
         for (int k = 0; k < 16; ++k) {
           const int piece = k * 32 + lane;
@@ -153,22 +167,34 @@ __device__ __forceinline__ void urow_producer(uint8_t* sU, const bf16* __restric
   }
 }
 
-// Elected-thread producer of a three-copy u ring from the TL copy of u (12 bulk copies of 2 KB per row).
+// Three-copy u slot of k_bconv_wg: 12 unpadded chunks [copy b][chunk dc][128 rows][8]; copy b holds tokens b-1 .. b+126 of
+// the tile, so that chunk (b, dc) of ONE 12-chunk operand (chunk stride 2048) is chunk dc shifted by b-1 tokens: the three
+// horizontal taps are one operand with N = 96.  Row 0 of copy 0 / row 127 of copy 2 are the neighbour tokens of the
+// adjacent tiles of the same image row, or zeros at the image border (16-byte bulk copies from `zeros16`).
+constexpr int USLOT3_B = 12 * 2048;
+
+// Elected-thread producer of the three-copy u ring from the TL copy of u (20 bulk copies per tile).
 template <int NSLOT>
-__device__ __forceinline__ bool urow3_bulk_producer(uint8_t* sU, const bf16* __restrict__ u_tl, int gfirst, int glast,
-                                                    uint64_t* full, uint64_t* empty) {
+__device__ __forceinline__ bool urow3_bulk_producer(uint8_t* sU, const bf16* __restrict__ u_tl, const void* zeros16, Strip sm,
+                                                    int gfirst, int glast, uint64_t* full, uint64_t* empty) {
   bool ok = true;
   const int n = glast - gfirst + 1;
   for (int i = 0; i < n; ++i) {
     const int sl = i % NSLOT;
     if (i >= NSLOT) ok = mbar_wait(&empty[sl], ((i / NSLOT) - 1) & 1) && ok;
     mbar_expect_tx(&full[sl], 3 * 4 * 2048);
-    const bf16* src = u_tl + (long long)(gfirst + i) * 128 * D;
+    const int g = gfirst + i, xt = sm.xt(g);
+    const bf16* src = u_tl + (long long)sm.tile(g) * 128 * D;
+    uint8_t* slot = sU + sl * USLOT3_B;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int dc = 0; dc < 4; ++dc)
-        bulk_g2s(sU + sl * USLOT3_B + c * UCOPY_B + dc * CHB + 16, src + dc * 1024, 2048, &full[sl]);
+    for (int dc = 0; dc < 4; ++dc) {
+      const bf16* ch = src + dc * 1024;
+      bulk_g2s(slot + (0 * 4 + dc) * 2048 + 16, ch, 2032, &full[sl]);                                   // tokens 0..126 -> rows 1..127
+      bulk_g2s(slot + (0 * 4 + dc) * 2048, xt > 0 ? (const void*)(ch - 128 * D + 127 * 8) : zeros16, 16, &full[sl]);
+      bulk_g2s(slot + (1 * 4 + dc) * 2048, ch, 2048, &full[sl]);                                        // tokens 0..127
+      bulk_g2s(slot + (2 * 4 + dc) * 2048, ch + 8, 2032, &full[sl]);                                    // tokens 1..127 -> rows 0..126
+      bulk_g2s(slot + (2 * 4 + dc) * 2048 + 2032, xt < sm.TPR - 1 ? (const void*)(ch + 128 * D) : zeros16, 16, &full[sl]);
+    }
   }
   return ok;
 }
@@ -295,7 +321,8 @@ constexpr int FC_EPI_WARPS = 16, FC_THREADS = (FC_EPI_WARPS + 2) * 32;   // 4 co
 __global__ void __launch_bounds__(FC_THREADS, 1)
 k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* __restrict__ dt_bias,
         const float* __restrict__ A_log, bf16* __restrict__ act, bf16* __restrict__ sgrad, bf16* __restrict__ dtraw,
-        float* __restrict__ S, int H, int rows_total, int rows_per_cta, int* __restrict__ status, bf16* __restrict__ u_tl) {
+        float* __restrict__ S, int H, int rows_total, int rows_per_cta, int* __restrict__ status, bf16* __restrict__ u_tl,
+        int TPR) {
   ADN_CTA_STAMP(0, 0);
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[NUS], empty[NUS], acc_full[2], acc_empty[2], st_full[2], st_empty[2], s_done, s_free, w_full;
@@ -327,7 +354,7 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
   bool ok = true;
   if (R0 < R1) {
     if (warp == FC_EPI_WARPS) {
-      urow_producer<1, NUS>(sU, u, gfirst, glast, full, empty, lane, u_tl, R0, R1 - 1);
+      urow_producer<NUS>(sU, u, Strip{H, TPR}, gfirst, glast, full, empty, lane, u_tl, R0, R1 - 1);
     } else if (warp == FC_EPI_WARPS + 1) {
       if (elect_one()) {   // one elected lane of the converged warp: tcgen05.mma is emitted without a lane-serialising loop
         // the weight image arrives by nine bulk copies while the first u rows are in flight
@@ -414,7 +441,9 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
       int fl = 0;
       PhaseTimer pt(7, tid == 0 || tid == 128 || tid == 256);
       for (int R = R0; R < R1; ++R) {
-        const int it = R - R0, acc = it & 1, y = R % H, b = R / H;
+        const Strip sm{H, TPR};
+        const int it = R - R0, acc = it & 1, y = R % H, b = sm.sample(R);
+        const long long tile = sm.tile(R);
         pt.mark(7);
         ok = mbar_wait(&acc_full[acc], (it >> 1) & 1) && ok;
         pt.mark(0);
@@ -422,10 +451,10 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
         tc_fence_after();
         pt.mark(1);
         const uint32_t ta = tbase + ((uint32_t)(q * 32) << 16) + acc * DIP;
-        bf16* arow = act + ((long long)R * NA * 128 + row) * 8;
-        bf16* grow = sgrad ? sgrad + ((long long)R * NA * 128 + row) * 8 : nullptr;
+        bf16* arow = act + (tile * NA * 128 + row) * 8;
+        bf16* grow = sgrad ? sgrad + (tile * NA * 128 + row) * 8 : nullptr;
         uint8_t* st = sSt + acc * FC_ST_B + row * 16;
-        bf16* dtrow = dtraw + ((long long)R * 2 * 128 + row) * 8;
+        bf16* dtrow = dtraw + (tile * 2 * 128 + row) * 8;
         if (grp == 0) fconv_epi_group<0>(ta, arow, grow, st, dtrow, s_bias, s_eA);
         else if (grp == 1) fconv_epi_group<1>(ta, arow, grow, st, dtrow, s_bias, s_eA);
         else if (grp == 2) fconv_epi_group<2>(ta, arow, grow, st, dtrow, s_bias, s_eA);
@@ -485,7 +514,8 @@ static_assert(18 * WTZ_AG_B + 1024 == WTB_B, "weight image size");
 
 __global__ void __launch_bounds__(192, 1)
 k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf16* __restrict__ WtZ, bf16* __restrict__ du,
-           int H, int rows_total, int rows_per_cta, int* __restrict__ status, int dbg) {
+           int H, int rows_total, int rows_per_cta, int* __restrict__ status, int dbg, int TPR) {
+  // TPR > 1 (strip images, see Strip): the pieces Z_0[x+1] / Z_2[x-1] that cross a strip edge are added by k_bconv_du_edge
   // dbg (diagnostics, ADN_DU_DBG): 1 = no loads, 2 = no MMAs, 4 = no du stores; results are then meaningless
   ADN_CTA_STAMP(1, 0);
   extern __shared__ __align__(128) uint8_t smem[];
@@ -528,8 +558,9 @@ k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
             const bool dt = g == 0 && r >= R0 && r < R1;
             if (dbg & 1) { mbar_arrive(&full[stg]); continue; }
             mbar_expect_tx(&full[stg], 8192u + (dt ? 4096u : 0u));
-            bulk_g2s(sb, dpre + ((long long)r * NA + g * 4) * 1024, 8192, &full[stg]);
-            if (dt) bulk_g2s(sb + 8192, ddt + (long long)r * 2 * 1024, 4096, &full[stg]);
+            const long long tile = Strip{H, TPR}.tile(r);
+            bulk_g2s(sb, dpre + (tile * NA + g * 4) * 1024, 8192, &full[stg]);
+            if (dt) bulk_g2s(sb + 8192, ddt + tile * 2 * 1024, 4096, &full[stg]);
           }
         }
         if (!ok) atomicExch(status, 22);
@@ -640,7 +671,7 @@ k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
             }
           }
         if (ok && !(dbg & 4)) {
-          bf16* dst = du + ((long long)r * 128 + x) * D;
+          bf16* dst = du + ((long long)Strip{H, TPR}.tile(r) * 128 + x) * D;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float v8[8];
@@ -661,6 +692,38 @@ k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_bconv_du_edge (W > 128 only): k_bconv_du treats every 128-token strip as its own image, so the two tokens on either
+// side of an interior strip edge miss the conv taps that reach across it:
+//   du[y][127 of strip e]   += sum_a dpre[y-(a-1)][0 of strip e+1][:]   . Wt[a, b=0]
+//   du[y][0   of strip e+1] += sum_a dpre[y-(a-1)][127 of strip e][:]   . Wt[a, b=2]
+// One warp per token (lane = output column d), fp32 weights K[c][t] * W_in[c][d]; runs after k_bconv_du on the same stream.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_bconv_du_edge(const bf16* __restrict__ dpre, const float* __restrict__ Kc, const float* __restrict__ Win, bf16* __restrict__ du,
+                int H, int TPR, int n_edges /* B * H * (TPR - 1) */) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= 2 * n_edges) return;
+  const int side = wid & 1, e = wid >> 1;                  // side 0: last token of the left strip, 1: first token of the right strip
+  const int xe = e % (TPR - 1), by = e / (TPR - 1), y = by % H, b = by / H;
+  const int tile_l = (b * H + y) * TPR + xe, tile_r = tile_l + 1;
+  const int tile_dst = side ? tile_r : tile_l, x_dst = side ? 0 : 127;
+  const int x_src = side ? 127 : 0, bt = side ? 2 : 0;     // source token inside the neighbouring tile, horizontal tap index
+  float acc = 0.f;
+  for (int a = 0; a < 3; ++a) {
+    const int ys = y - (a - 1);
+    if (ys < 0 || ys >= H) continue;
+    const long long tile_src = (long long)(b * H + ys) * TPR + xe + (side ? 0 : 1);
+    const bf16* row = dpre + tile_src * NA * 1024 + x_src * 8;
+    for (int c = 0; c < CC; ++c) {
+      const float v = __bfloat162float(row[(c >> 3) * 1024 + (c & 7)]);
+      acc = fmaf(v * __ldg(Kc + c * 9 + 3 * a + bt), __ldg(Win + c * D + lane), acc);
+    }
+  }
+  bf16* dst = du + ((long long)tile_dst * 128 + x_dst) * D + lane;
+  *dst = __float2bfloat16_rn(__bfloat162float(*dst) + acc);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_bconv_wg: M_t[c][d] = sum_p dpre[p][c] * u[p + d_t][d] for the 128-channel block mb of this CTA, nine 32-column TMEM
 // accumulators kept for the CTA's whole row range; the epilogue contracts them into per-CTA slabs of dK and dW_in partial
 // sums (added up by k_finalize_fast).   mb 0: channels 0..127 (z, x).   mb 1: channels 128..191 (B, C) + the 16 dt rows (their
@@ -670,11 +733,13 @@ k_bconv_du(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
 constexpr int WG_NST = 3;
 constexpr int WG_STG_B = 16 * 2048;
 constexpr int WG_SMEM = WG_NST * WG_STG_B + NUW * USLOT3_B;
+static_assert(WG_SMEM <= 227 * 1024, "k_bconv_wg shared memory");
 
 __global__ void __launch_bounds__(192, 1)
 k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf16* __restrict__ u /* TL copy of u */,
            const float* __restrict__ Win, const float* __restrict__ Kc, float* __restrict__ dK, float* __restrict__ dWin,
-           int H, int rows_total, int rows_per_cta, int ctas_per_block, int* __restrict__ status) {
+           int H, int rows_total, int rows_per_cta, int ctas_per_block, int* __restrict__ status, int TPR,
+           const void* __restrict__ zeros16) {
   ADN_CTA_STAMP(2, 0);
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[NUW], empty[NUW], a_full[WG_NST], a_empty[WG_NST], done;
@@ -707,13 +772,13 @@ k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
   if (R0 < R1) {
     if (warp == 4) {
       if (elect_one()) {
-        if (!urow3_bulk_producer<NUW>(sU, u, gfirst, glast, full, empty)) atomicExch(status, 27);
+        if (!urow3_bulk_producer<NUW>(sU, u, zeros16, Strip{H, TPR}, gfirst, glast, full, empty)) atomicExch(status, 27);
       }
     } else if (warp == 5) {
       if (elect_one()) {
         const uint32_t idesc = make_idesc_rt(128, 3 * D, true, true);
         const uint32_t abase = smem_u32(sA), ubase = smem_u32(sU);
-        const uint64_t dA0 = make_desc(abase, 128, 2048), dU0 = make_desc(ubase, 128, CHB);
+        const uint64_t dA0 = make_desc(abase, 128, 2048), dU0 = make_desc(ubase, 128, 2048);
         int next_wait = gfirst;
         uint32_t mask = 0;
         PhaseTimer pt(6, true);
@@ -749,7 +814,7 @@ k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
               const bool init = ((mask >> (3 * a)) & 1) != 0;
 #pragma unroll
               for (int k = 0; k < 8; ++k)
-                umma(tbase + a * 3 * D, make_desc(ab + k * 256, 128, 2048), make_desc(ub + k * 256, 128, CHB), idesc, init || k > 0);
+                umma(tbase + a * 3 * D, make_desc(ab + k * 256, 128, 2048), make_desc(ub + k * 256, 128, 2048), idesc, init || k > 0);
               mask |= 7u << (3 * a);
             }
           }
@@ -769,13 +834,14 @@ k_bconv_wg(const bf16* __restrict__ dpre, const bf16* __restrict__ ddt, const bf
           const int it = R - R0, stg = it % WG_NST;
           if (it >= WG_NST) ok = mbar_wait(&a_empty[stg], ((it / WG_NST) - 1) & 1) && ok;
           uint8_t* sb = sA + stg * WG_STG_B;
+          const long long tile = Strip{H, TPR}.tile(R);
           if (mb == 0) {
             mbar_expect_tx(&a_full[stg], 16 * 2048);
-            bulk_g2s(sb, dpre + (long long)R * NA * 1024, 16 * 2048, &a_full[stg]);
+            bulk_g2s(sb, dpre + tile * NA * 1024, 16 * 2048, &a_full[stg]);
           } else {
             mbar_expect_tx(&a_full[stg], 8 * 2048 + 4096);
-            bulk_g2s(sb, dpre + ((long long)R * NA + 16) * 1024, 8 * 2048, &a_full[stg]);
-            bulk_g2s(sb + 8 * 2048, ddt + (long long)R * 2 * 1024, 4096, &a_full[stg]);
+            bulk_g2s(sb, dpre + (tile * NA + 16) * 1024, 8 * 2048, &a_full[stg]);
+            bulk_g2s(sb + 8 * 2048, ddt + tile * 2 * 1024, 4096, &a_full[stg]);
           }
         }
       }

@@ -1764,7 +1764,10 @@ static int rows_per_cta(int rows_total, int ctas) {
 static bool rowconv_supported(const MixerDims& d) {
   const char* e = getenv("ADN_ROWCONV");      // diagnostics: ADN_ROWCONV=0 keeps these shapes on the tile kernels
   if (e && e[0] == '0') return false;
-  return d.D == 32 && d.Di == 64 && d.P == 4 && d.GN == 32 && d.W == 128 && d.dip == 208 && d.ldr == 208;
+  const char* ew = getenv("ADN_ROW_WIDE");     // diagnostics: ADN_ROW_WIDE=0 restricts the row kernels to W == 128
+  const bool wide = !(ew && ew[0] == '0');
+  return d.D == 32 && d.Di == 64 && d.P == 4 && d.GN == 32 && d.dip == 208 && d.ldr == 208 &&
+         (d.W == 128 || (wide && d.W % 128 == 0 && d.W <= 1024));
 }
 
 bool sm100_supported(const MixerDims& d) {
@@ -1894,8 +1897,8 @@ int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* 
     static_assert(sizeof(float) * rowconv::NH == sizeof(bf16) * rowconv::D, "u_tl does not fit the wdec slot");
     int rc = set_smem(rowconv::k_fconv, rowconv::FC_SMEM);
     if (rc) return rc;
-    const int rows_total = d.B * d.H, per = rows_per_cta(rows_total, 148), grid = cdiv(rows_total, per);
-    { ADN_KERNEL("k_fconv", st); rowconv::k_fconv<<<grid, rowconv::FC_THREADS, rowconv::FC_SMEM, st>>>(u, P.WtF, w.dt_bias, w.A_log, S.act, training ? S.pre : nullptr, S.raw, S.S, d.H, rows_total, per, F.status, training ? reinterpret_cast<bf16*>(S.wdec) : nullptr); }
+    const int rows_total = d.B * d.H * (d.W / 128), per = rows_per_cta(rows_total, 148), grid = cdiv(rows_total, per);   // strip rows
+    { ADN_KERNEL("k_fconv", st); rowconv::k_fconv<<<grid, rowconv::FC_THREADS, rowconv::FC_SMEM, st>>>(u, P.WtF, w.dt_bias, w.A_log, S.act, training ? S.pre : nullptr, S.raw, S.S, d.H, rows_total, per, F.status, training ? reinterpret_cast<bf16*>(S.wdec) : nullptr, d.W / 128); }
     // The warp-specialised readout (one CTA per SM, two tiles in flight) measured SLOWER than the monolithic tile kernel
     // at three CTAs per SM (41.7 vs 33.2 us at the benchmark shape): this stage is light enough that plain occupancy
     // hides its latencies better.  It stays selectable for experiments (ADN_READOUT_WS=1).
@@ -1975,18 +1978,22 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
       W.acc.head_part = F.head_part;
       W.acc.head_parts = grid;
     }
-    const int rows_total = d.B * d.H;
+    const int TPR = d.W / 128, rows_total = d.B * d.H * TPR;      // rows of the 128-wide strip images
     {
       rc = set_smem(rowconv::k_bconv_du, rowconv::DU_SMEM);
       if (rc) return rc;
       const int per = rows_per_cta(rows_total, 148), grid = cdiv(rows_total, per);
-      { ADN_KERNEL("k_bconv_du", st); rowconv::k_bconv_du<<<grid, 192, rowconv::DU_SMEM, st>>>(W.dact, W.draw, P.WtB, du, d.H, rows_total, per, status, getenv("ADN_DU_DBG") ? atoi(getenv("ADN_DU_DBG")) : 0); }
+      { ADN_KERNEL("k_bconv_du", st); rowconv::k_bconv_du<<<grid, 192, rowconv::DU_SMEM, st>>>(W.dact, W.draw, P.WtB, du, d.H, rows_total, per, status, getenv("ADN_DU_DBG") ? atoi(getenv("ADN_DU_DBG")) : 0, TPR); }
+      if (TPR > 1) {
+        const int n_edges = d.B * d.H * (TPR - 1);
+        { ADN_KERNEL("k_bconv_du_edge", st); rowconv::k_bconv_du_edge<<<cdiv(2LL * n_edges * 32, 256), 256, 0, st>>>(W.dact, P.Kc, w.in_proj_w, du, d.H, TPR, n_edges); }
+      }
     }
     {
       rc = set_smem(rowconv::k_bconv_wg, rowconv::WG_SMEM);
       if (rc) return rc;
       const int cpb = max(1, min(74, rows_total)), per = cdiv(rows_total, cpb), parts = cdiv(rows_total, per);
-      { ADN_KERNEL("k_bconv_wg", st); rowconv::k_bconv_wg<<<2 * parts, 192, rowconv::WG_SMEM, st>>>(W.dact, W.draw, reinterpret_cast<const bf16*>(S.wdec), w.in_proj_w, P.Kc, F.dK_part, F.dWin_part, d.H, rows_total, per, parts, status); }
+      { ADN_KERNEL("k_bconv_wg", st); rowconv::k_bconv_wg<<<2 * parts, 192, rowconv::WG_SMEM, st>>>(W.dact, W.draw, reinterpret_cast<const bf16*>(S.wdec), w.in_proj_w, P.Kc, F.dK_part, F.dWin_part, d.H, rows_total, per, parts, status, TPR, W.acc.sync_counter + 16); }
       W.acc.dWin_part = F.dWin_part;
       W.acc.dWin_parts = parts;
       W.acc.dK_part = F.dK_part;

@@ -99,10 +99,12 @@ def test_mixer_matches_oracle_ragged_shapes(cfg, dtype):
     assert not bad, f"{cfg} {dtype}: {bad}"
 
 
-@pytest.mark.parametrize("cfg", [(3, 5, 128), (2, 1, 128), (1, 2, 128), (5, 37, 128)], ids=lambda c: "B%d_%dx%d" % c)
+@pytest.mark.parametrize("cfg", [(3, 5, 128), (2, 1, 128), (1, 2, 128), (5, 37, 128), (1, 3, 256), (2, 5, 256), (1, 2, 384)],
+                         ids=lambda c: "B%d_%dx%d" % c)
 def test_row_kernels_match_oracle(cfg):
-    """128-token-wide grids take the conv-as-GEMM row kernels (adnssd_rowconv.cuh): several samples per CTA range,
-    H = 1 (no vertical taps), H = 2, and a CTA range that ends mid-sample; model-scale weights, bf16 contract 2e-2."""
+    """Grids whose width is a multiple of 128 take the conv-as-GEMM row kernels (adnssd_rowconv.cuh): several samples per
+    CTA range, H = 1 (no vertical taps), H = 2, a CTA range that ends mid-sample, and 256 / 384-wide grids (processed as
+    128-wide strip images with neighbour tokens across the strip edges); model-scale weights, bf16 contract 2e-2."""
     B, H, W = cfg
     D, P, N = 32, 4, 16
     params = AO.init_params(D, P, N, seed=9, perturb=0.05, dtype=torch.float32)
