@@ -228,8 +228,11 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
       PhaseTimer pt(0, tid == 0);
       uint4 sgc_prev, sgc_cur;     // SiLU' of this thread's C columns: fetched one tile ahead of their use in epi2
       sgc_prev = make_uint4(0u, 0u, 0u, 0u);
+      // (sample, tile-in-sample) of the tile handled by epi2, tracked without per-tile integer divisions
+      int e2_b = T0 / tiles_per_batch, e2_i = T0 - e2_b * tiles_per_batch;
       auto epi2 = [&](int t) {
-        const int it = t - T0, s = it & 1, b = t / tiles_per_batch, i_in_b = t % tiles_per_batch;
+        const int it = t - T0, s = it & 1, b = e2_b, i_in_b = e2_i;
+        if (++e2_i == tiles_per_batch) { e2_i = 0; ++e2_b; }
         ok = mbar_wait(&mma2_done[s], (it >> 1) & 1) && ok;
         tc_fence_after();
         pt.mark(5);

@@ -112,6 +112,27 @@ struct Strip {
   __device__ __forceinline__ int xt(int R) const { return (R / H) % TPR; }
   __device__ __forceinline__ int sample(int R) const { return (R / H) / TPR; }
 };
+// (sample, image row, tile) of consecutive strip rows without per-row integer divisions (the epilogue warps are bound by
+// instruction issue: four runtime divisions per row and thread cost k_fconv 11 %)
+struct StripIter {
+  int H, TPR, b, xt, y, tile;
+  __device__ __forceinline__ StripIter(Strip sm, int R) : H(sm.H), TPR(sm.TPR) {
+    const int img = R / H;
+    y = R - img * H;
+    b = img / TPR;
+    xt = img - b * TPR;
+    tile = (b * H + y) * TPR + xt;
+  }
+  __device__ __forceinline__ void next() {
+    ++y;
+    tile += TPR;
+    if (y == H) {
+      y = 0;
+      if (++xt == TPR) { xt = 0; ++b; }
+      tile = b * H * TPR + xt;
+    }
+  }
+};
 
 // One warp: copy one row-major u tile (128 tokens x 32 channels, 8 KB contiguous) into positions 1..128 of a padded slot and
 // its two horizontal neighbour tokens (or zeros at the image border) into the pad positions 0 and 129.
@@ -205,6 +226,7 @@ __device__ __forceinline__ bool urow3_bulk_producer(uint8_t* sU, const bf16* __r
 // four chunks) to shared memory.
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 template <int MODE>
 __device__ __forceinline__ void silu32(uint32_t taddr, bf16* a_dst, bf16* g_dst, uint8_t* s_dst, const float* w8) {
@@ -281,11 +303,14 @@ __device__ __forceinline__ void fconv_epi_group(uint32_t ta, bf16* arow, bf16* g
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 x = make_float2(v[i >> 1][(i & 1) * 8 + 2 * j], v[i >> 1][(i & 1) * 8 + 2 * j + 1]);
-      const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
-      const float2 d = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.f, 1.f));
-      const float2 sg = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+      // sigmoid(x) = 0.5 + 0.5 tanh(x / 2): ONE MUFU op per element.  The four epilogue warps of a scheduler share a 4-lane
+      // MUFU pipe (8 cycles per warp instruction), which bounds this loop; tanh.approx (relative error 2^-11, i.e. <= 2.5e-4
+      // absolute on the sigmoid) is well inside the rounding of the bf16 tensors these values are stored in.
+      const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+      const float2 th = make_float2(tanh_approx(hx.x), tanh_approx(hx.y));
+      const float2 sg = __ffma2_rn(th, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
       a[j] = __fmul2_rn(x, sg);
-      const float2 om = __ffma2_rn(sg, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+      const float2 om = __ffma2_rn(th, make_float2(-0.5f, -0.5f), make_float2(0.5f, 0.5f));
       gq[j] = __ffma2_rn(a[j], om, sg);
     }
     const uint4 pa = pack8_f2(a);
@@ -440,10 +465,10 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
       const int q = warp & 3, grp = warp >> 2, row = q * 32 + lane;   // column group: 48 columns each (fconv_epi_group)
       int fl = 0;
       PhaseTimer pt(7, tid == 0 || tid == 128 || tid == 256);
-      for (int R = R0; R < R1; ++R) {
-        const Strip sm{H, TPR};
-        const int it = R - R0, acc = it & 1, y = R % H, b = sm.sample(R);
-        const long long tile = sm.tile(R);
+      StripIter si(Strip{H, TPR}, R0);
+      for (int R = R0; R < R1; ++R, si.next()) {
+        const int it = R - R0, acc = it & 1, y = si.y, b = si.b;
+        const long long tile = si.tile;
         pt.mark(7);
         ok = mbar_wait(&acc_full[acc], (it >> 1) & 1) && ok;
         pt.mark(0);
@@ -461,7 +486,7 @@ k_fconv(const bf16* __restrict__ u, const bf16* __restrict__ WtF, const float* _
         else fconv_epi_group<3>(ta, arow, grow, st, dtrow, s_bias, s_eA);
         pt.mark(2 + (grp == 1));
         tc_fence_before();
-        fence_async_smem();
+        if (grp != 0) fence_async_smem();      // group 0 (z columns only) wrote no operand of the state MMA
         __syncwarp();
         if (lane == 0) { mbar_arrive(&acc_empty[acc]); mbar_arrive(&st_full[acc]); }
         pt.mark(4);

@@ -188,13 +188,21 @@ k_wt_level(const TI* __restrict__ in, const float* __restrict__ coarse, TO* __re
     }
   }
   TO* dst = out + plane * (long long)g.h * g.w;
+  const int x0 = 2 * (sx0 + px);                      // multiple of 8
+  const bool vec = (g.w & 7) == 0 && x0 + 8 <= g.w;   // the strip's 8 outputs of a row: two 4-element vector stores
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
     int y = 2 * gy + rr;
     if (y >= g.h) continue;
+    if (vec) {
+      float lo[4] = {o[rr][0], o[rr][1], o[rr][2], o[rr][3]}, hi[4] = {o[rr][4], o[rr][5], o[rr][6], o[rr][7]};
+      st4(dst + (long long)y * g.w + x0, lo);
+      st4(dst + (long long)y * g.w + x0 + 4, hi);
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      int x = 2 * (sx0 + px) + j;
+      int x = x0 + j;
       if (x < g.w) stf(dst + (long long)y * g.w + x, o[rr][j]);
     }
   }
