@@ -545,7 +545,7 @@ struct GradAcc {
 };
 
 __device__ __forceinline__ float dk_at(const GradAcc& a, int idx) {
-  if (a.dK_parts == 0) return a.dK[idx];
+  if (a.dK_parts == 0) return __ldcg(a.dK + idx);     // may have been reduced by other SMs earlier in the same kernel
   float v = 0.f;
   for (int p = 0; p < a.dK_parts; ++p) v += a.dK_part[(long long)p * a.dK_stride + idx];
   return v;
@@ -572,7 +572,7 @@ __device__ __forceinline__ void finalize_body(const GradAcc& a, const AdnWeights
   if (i0 == 0 && g.alpha1) g.alpha1[0] = a.dalpha1[0];
   }
   for (long long i = i0; i < nh; i += stride) {
-    float vD = a.dD[i], vA = a.dAlog[i], vB = a.ddtb[i];
+    float vD = __ldcg(a.dD + i), vA = __ldcg(a.dAlog + i), vB = __ldcg(a.ddtb + i);
     for (int p = 0; p < a.head_parts; ++p) {
       vD += a.head_part[(long long)p * 3 * nh + i];
       vA += a.head_part[(long long)p * 3 * nh + nh + i];

@@ -1366,17 +1366,15 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ R
       else if (chunk < c0 + c1 + c2) { set = 2; src = Rt; parts = rt_parts; stride = rs; n = n2; e = (chunk - c0 - c1) * 32 + el; }
       else { set = 3; src = a.head_part; parts = a.head_parts; stride = n3; n = n3; e = (chunk - c0 - c1 - c2) * 32 + el; }
       float v = 0.f;
-      if (e < n) {      // up to ~19 slabs per thread: independent loads, four partial sums
-        float v1 = 0.f, v2 = 0.f, v3 = 0.f;
-        int p = pl;
-        for (; p + 24 < parts; p += 32) {
-          v += src[(long long)p * stride + e];
-          v1 += src[(long long)(p + 8) * stride + e];
-          v2 += src[(long long)(p + 16) * stride + e];
-          v3 += src[(long long)(p + 24) * stride + e];
+      if (e < n) {      // up to 19 slabs per thread (<= 148 CTAs / 8 lanes): every load is issued before the first add
+        float t[20];
+#pragma unroll
+        for (int k = 0; k < 20; ++k) {
+          const int p = pl + 8 * k;
+          t[k] = p < parts ? __ldcg(src + (long long)p * stride + e) : 0.f;   // L2 only: nothing of the slabs may linger in L1
         }
-        for (; p < parts; p += 8) v += src[(long long)p * stride + e];
-        v = (v + v1) + (v2 + v3);
+#pragma unroll
+        for (int k = 0; k < 20; k += 4) v += (t[k] + t[k + 1]) + (t[k + 2] + t[k + 3]);
       }
       __syncthreads();
       red[pl][el] = v;
@@ -1412,7 +1410,8 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ R
   int blk = blockIdx.x;
   if (blk < nb_in) {
     const int n = dip * D, e = blk * 32 + (tid & 31), pl = tid >> 5;
-    float v = (e < n && pl == 0 && a.dWin_parts == 0) ? a.dWin[e] : 0.f;
+    // phase 2 reads what OTHER SMs wrote in phase 1: __ldcg (L2) loads, never the non-coherent L1
+    float v = (e < n && pl == 0 && a.dWin_parts == 0) ? __ldcg(a.dWin + e) : 0.f;
     if (e < n)
       for (int p = pl; p < a.dWin_parts; p += 8) v += a.dWin_part[(long long)p * n + e];
     red[pl][tid & 31] = v;
@@ -1432,7 +1431,7 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ R
     const float a1 = *w.alpha1;
     float dg = 0.f, db = 0.f, da = 0.f;
     for (int d = tid; d < D; d += 32) {
-      const float r = Rt[c * D + d], wv = w.out_proj_w[d * 2 * Di + c], sd = sdout[d];
+      const float r = __ldcg(Rt + c * D + d), wv = w.out_proj_w[d * 2 * Di + c], sd = __ldcg(sdout + d);
       const float rawv = c < Di ? w.norm_w[c] * r + w.norm_b[c] * sd : r;
       if (g.out_proj_w) g.out_proj_w[d * 2 * Di + c] = a1 * rawv + poison;
       da = fmaf(wv, rawv, da);

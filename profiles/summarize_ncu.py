@@ -1,6 +1,6 @@
 """ncu report -> small JSON summary committed under profiles/ (run where `ncu` is on PATH; no GPU needed).
 
-    python profiles/summarize_ncu.py gpurun_out/prof_r1b.ncu-rep profiles/r01_mixer_kernels.json
+    python profiles/summarize_ncu.py gpurun_out/prof_r1b.ncu-rep profiles/r01_mixer_kernels.json ["command label"]
 """
 import csv
 import io
@@ -29,7 +29,7 @@ UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ns": 1e-3,
               "usecond": 1.0, "nsecond": 1e-3}
 
 
-def main(rep, out):
+def main(rep, out, command="python profiles/run_mixer_once.py (D=32, B=16, 128x128 tokens, bf16), second step"):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -44,7 +44,7 @@ def main(rep, out):
                 v = float(r[idx[m]].replace(",", ""))
                 e[key] = v * UNIT_SCALE.get(units[idx[m]], 1.0)
         kernels[short] = e
-    json.dump({"source": rep, "command": "python profiles/run_mixer_once.py (D=32, B=16, 128x128 tokens, bf16), second step",
+    json.dump({"source": rep, "command": command,
                "ncu": "--set full --clock-control none --import-source on", "kernels": kernels}, open(out, "w"), indent=1)
     for k, e in kernels.items():
         print(f"{k:20s} {e.get('time_us', 0):8.1f} us  dram {(e.get('dram_read_bytes', 0) + e.get('dram_write_bytes', 0)) / 1e6:7.1f} MB"
@@ -52,4 +52,4 @@ def main(rep, out):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(*sys.argv[1:4])
