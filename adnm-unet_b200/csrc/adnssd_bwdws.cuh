@@ -65,7 +65,7 @@ __device__ __forceinline__ void stage_state_warp(const float* __restrict__ M, ui
 // ------------------------------------------------------------------------------------------------
 constexpr int B1_STG_B = (DC + CCH + 16 + 16) * 2048;      // dout | C | [yhat | zc] | [x -> dy | zero padding]
 constexpr int B1_WT_B = DC * 2 * DI * 16;                  // W_out^T image: [4 chunks of d][128 rows j'][8]
-constexpr int B1_XCH_B = 2 * 4 * 128 * 8;                  // two exchange buffers [column quarter][row] of float2
+constexpr int B1_XCH_B = 2 * 4 * 128 * 16;                 // two exchange buffers [column quarter][row] of float4
 constexpr int WS_EPI_WARPS = 16, WS_THREADS = (WS_EPI_WARPS + 2) * 32;   // 4 column quarters x 4 lane quarters + producer + MMA
 constexpr int B1_SMEM = 2 * B1_STG_B + B1_WT_B + 2 * SIMG_B + B1_XCH_B;
 constexpr int B1_TSTG = 224, B1_COL_Y = 128, B1_COL_DC = 192, B1_COL_RT = 448, B1_COL_DS = 480;
@@ -306,27 +306,35 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
             y[8 + j] = fmaf(sDh[cq * 16 + 8 + j], x1[j], y[8 + j]);
           }
         }
-        {   // two interleaved partial sums per statistic (shorter dependency chains)
-          float q1 = 0.f, q2 = 0.f;
+        // ---- ONE exchange per tile: the LayerNorm statistics (sum y, sum y^2) and the two sums of its backward
+        // (sum gy, sum gy*y with gy = alpha1 * g_y * gamma) all come straight from the accumulators, and
+        // mean(gy * yhat) = rstd * (mean(gy * y) - mu * mean(gy)).  Exchange buffers alternate per tile (one barrier per tile).
+        float p3 = 0.f, p4 = 0.f;
+        {
+          float q1 = 0.f, q2 = 0.f, q3 = 0.f, q4 = 0.f;
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
-            p1 += y[c]; p2 = fmaf(y[c], y[c], p2);
-            q1 += y[c + 1]; q2 = fmaf(y[c + 1], y[c + 1], q2);
+            gy[c] = a1 * gy[c] * sG[cq * 16 + c];
+            gy[c + 1] = a1 * gy[c + 1] * sG[cq * 16 + c + 1];
+            p1 += y[c]; p2 = fmaf(y[c], y[c], p2); p3 += gy[c]; p4 = fmaf(gy[c], y[c], p4);
+            q1 += y[c + 1]; q2 = fmaf(y[c + 1], y[c + 1], q2); q3 += gy[c + 1]; q4 = fmaf(gy[c + 1], y[c + 1], q4);
           }
-          p1 += q1; p2 += q2;
+          p1 += q1; p2 += q2; p3 += q3; p4 += q4;
         }
-        sXch[(0 * 4 + cq) * 128 + row] = make_float2(p1, p2);
+        float4* xch = reinterpret_cast<float4*>(sXch) + (it & 1) * 4 * 128;
+        xch[cq * 128 + row] = make_float4(p1, p2, p3, p4);
         pt.mark(1);
         asm volatile("bar.sync 1, 512;" ::: "memory");
         pt.mark(2);
 #pragma unroll
         for (int o = 1; o < 4; ++o) {
-          const float2 v = sXch[(0 * 4 + ((cq + o) & 3)) * 128 + row];
-          p1 += v.x;
-          p2 += v.y;
+          const float4 v = xch[((cq + o) & 3) * 128 + row];
+          p1 += v.x; p2 += v.y; p3 += v.z; p4 += v.w;
         }
         const float mu = p1 * (1.f / DI);
         const float rstd = rsqrtf(fmaxf(p2 * (1.f / DI) - mu * mu, 0.f) + 1e-5f);
+        const float m1 = p3 * (1.f / DI);
+        const float m2 = rstd * (p4 * (1.f / DI) - mu * m1);
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
           float v[8];
@@ -334,31 +342,7 @@ k_bwd1_ws(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf1
           for (int j = 0; j < 8; ++j) { y[cg * 8 + j] = (y[cg * 8 + j] - mu) * rstd; v[j] = y[cg * 8 + j]; }
           *reinterpret_cast<uint4*>(sCatRow + (2 * cq + cg) * 2048) = pack8(v);
         }
-        // ---- LN backward: dyh = alpha1 * g_y * gamma ; dy = rstd * (dyh - mean(dyh) - yhat * mean(dyh*yhat))
-        float m1 = 0.f, m2 = 0.f;
-        {
-          float n1 = 0.f, n2 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            gy[j] = a1 * gy[j] * sG[cq * 16 + j];
-            gy[j + 1] = a1 * gy[j + 1] * sG[cq * 16 + j + 1];
-            m1 += gy[j]; m2 = fmaf(gy[j], y[j], m2);
-            n1 += gy[j + 1]; n2 = fmaf(gy[j + 1], y[j + 1], n2);
-          }
-          m1 += n1; m2 += n2;
-        }
-        sXch[(1 * 4 + cq) * 128 + row] = make_float2(m1, m2);
         pt.mark(3);
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        pt.mark(2);
-#pragma unroll
-        for (int o = 1; o < 4; ++o) {
-          const float2 v = sXch[(1 * 4 + ((cq + o) & 3)) * 128 + row];
-          m1 += v.x;
-          m2 += v.y;
-        }
-        m1 *= (1.f / DI);
-        m2 *= (1.f / DI);
         bf16* drow = dact + (((long long)t * NA) * 128 + row) * 8;
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
