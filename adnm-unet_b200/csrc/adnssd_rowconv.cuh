@@ -1,4 +1,5 @@
-// Conv-as-GEMM kernels of the sm_100a ADN-SSD path ("row" kernels; token grids with W == 128, d_model 32, d_state 16).
+// Conv-as-GEMM kernels of the sm_100a ADN-SSD path ("row" kernels; token grids with W % 128 == 0, d_model 32, d_state 16;
+// grids wider than 128 are processed as 128-wide strip images, see struct Strip).
 //
 // The depthwise 3x3 convolution that follows in_proj (models/ADNssd.py:329-372,388-390) is linear in u:
 //     pre[p][c] = sum_t K[c][t] * raw[p + d_t][c] = sum_t  u[p + d_t][:] . Wt[t][c][:],    Wt[t][c][d] = K[c][t] * W_in[c][d]
@@ -14,7 +15,10 @@
 // raw (the in_proj output) is never materialised; only its dt columns are stored (the decay weights need them).
 //
 // All three kernels are warp-specialised: a producer warp (cp.async / cp.async.bulk into a ring, mbarrier completion),
-// one MMA-issuing thread, and epilogue warps that own TMEM lane quarters (thread = token row).
+// one MMA-issuing thread (an elected lane of a converged warp), and epilogue warps that own TMEM lane quarters
+// (thread = token row).  k_bconv_du moves the horizontal shift to the output side and k_bconv_wg merges the three
+// horizontal taps into one N = 96 operand (see the kernel headers): a 128xNx16 MMA with both operands in shared memory costs
+// max(N/2, (4096 + 32 N)/128) cycles, i.e. ~46 cycles for any N <= 64, so few wide MMAs beat many narrow ones.
 #pragma once
 
 namespace rowconv {
