@@ -8,5 +8,7 @@ from adnm_unet_b200.wtconv import WTConv2d, wtconv2d  # noqa: F401
 from adnm_unet_b200.metrics import threshold_counts, csi_hss  # noqa: F401
 from adnm_unet_b200.inject import install_into_reference  # noqa: F401
 from adnm_unet_b200.dp import GradAllReducer, shard_range  # noqa: F401
+from adnm_unet_b200.graphed import graphed_mixer  # noqa: F401
 
-__all__ = ["Mamba2", "adnssd_mixer", "WTConv2d", "wtconv2d", "threshold_counts", "csi_hss", "install_into_reference"]
+__all__ = ["Mamba2", "adnssd_mixer", "WTConv2d", "wtconv2d", "threshold_counts", "csi_hss", "install_into_reference",
+           "graphed_mixer"]

@@ -23,3 +23,16 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(N): step()
 pr.disable(); torch.cuda.synchronize()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
+
+# the same loop through adnm_unet_b200.graphed_mixer (forward and backward replayed as CUDA graphs inside autograd)
+f = A.graphed_mixer(m, u.detach(), 128, 128)
+def gstep():
+    u.grad = None
+    for p in params: p.grad = None
+    f(u).backward(go)
+for _ in range(10): gstep()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(N): gstep()
+t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print(f"graphed_mixer B={B}: host issue time {1e6*(t1-t0)/N:.0f} us/step, wall incl. GPU drain {1e6*(t2-t0)/N:.0f} us/step")

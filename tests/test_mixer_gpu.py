@@ -286,3 +286,36 @@ def test_module_step_is_cuda_graph_capturable():
     assert rel(g_du, ue.grad.float().cpu()) < 4e-3
     for gp, p in zip(g_par, params):
         assert rel(gp, p.grad.float().cpu()) < 1e-2
+
+
+def test_graphed_mixer_matches_eager_and_is_faster_to_issue():
+    """adnm_unet_b200.graphed_mixer: make_graphed_callables around the module; same numbers as the eager call (up to the
+    fp32-atomic ulp), gradients on the same parameters."""
+    import adnm_unet_b200 as A
+    torch.manual_seed(4)
+    dev = torch.device("cuda:0")
+    m = A.Mamba2(d_model=32, headdim=4, d_state=16).to(dev)
+    H, W = 6, 128
+    u0 = torch.randn(2, H * W, 32, device=dev, dtype=torch.bfloat16)
+    f = A.graphed_mixer(m, u0, H, W)
+    u = torch.randn_like(u0).requires_grad_(True)
+    go = torch.randn_like(u0)
+    for p in m.parameters():
+        p.grad = None
+    out_g = f(u)
+    out_g.backward(go)
+    torch.cuda.synchronize()
+    g_du = u.grad.detach().clone()
+    g_par = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+    assert set(g_par) == set(n for n, _ in m.named_parameters()) - {"scale", "shift", "alpha2"}
+    ue = u.detach().clone().requires_grad_(True)
+    for p in m.parameters():
+        p.grad = None
+    out_e = m(ue, H, W)
+    out_e.backward(go)
+    torch.cuda.synchronize()
+    assert rel(out_g, out_e.detach().float().cpu()) < 4e-3
+    assert rel(g_du, ue.grad.float().cpu()) < 4e-3
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            assert rel(g_par[n], p.grad.float().cpu()) < 1e-2, n
