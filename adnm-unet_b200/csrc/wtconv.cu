@@ -270,30 +270,43 @@ __global__ void k_wt_wgrad(const TX* __restrict__ xin, const TG* __restrict__ gi
     }
   }
   __syncthreads();
-  // roles: tid -> (rows group rg in [0,8), band, tap row a): slides a K-wide window along x for its tap row
+  // roles: tid -> (row group rg, tap row a, band, x segment): slides a K-wide window along x for its tap row.  The window
+  // walk is fully unrolled (the shift is register renaming: 2 LDS + K FMA per position).  NB == 4: 8 groups of 2 rows over
+  // the whole tile width; NB == 1 (base conv): 16 single rows x 2 half-width segments, so that all 160 threads work.
+  constexpr int XSEG = NB == 4 ? 1 : 2, XW = WT_TW / XSEG, RPT = NB == 4 ? 2 : 1, NRG = WT_TH / RPT;
   const int role = tid;
-  if (role < NB * K * 8) {
-    const int rg = role % 8, a = (role / 8) % K, band = role / (8 * K);
+  if (role < NB * K * NRG * XSEG) {
+    const int rg = role % NRG, a = (role / NRG) % K, band = (role / (NRG * K)) % NB, x0 = (role / (NRG * K * NB)) * XW;
     float acc[K];
 #pragma unroll
     for (int bb = 0; bb < K; ++bb) acc[bb] = 0.f;
 #pragma unroll
-    for (int yy = 0; yy < WT_TH / 8; ++yy) {
-      const int y = rg * (WT_TH / 8) + yy;
+    for (int yy = 0; yy < RPT; ++yy) {
+      const int y = rg * RPT + yy;
+      const float* srow = &S[band][y + a][x0];
+      const float* drow = &Dt[band][y][x0];
       float win[K];
 #pragma unroll
-      for (int bb = 0; bb < K - 1; ++bb) win[bb + 1] = S[band][y + a][bb];
-      for (int x = 0; x < WT_TW; ++x) {
+      for (int bb = 0; bb < K - 1; ++bb) win[bb + 1] = srow[bb];
+#pragma unroll
+      for (int x = 0; x < XW; ++x) {
 #pragma unroll
         for (int bb = 0; bb < K - 1; ++bb) win[bb] = win[bb + 1];
-        win[K - 1] = S[band][y + a][x + K - 1];
-        const float dv = Dt[band][y][x];
+        win[K - 1] = srow[x + K - 1];
+        const float dv = drow[x];
 #pragma unroll
         for (int bb = 0; bb < K; ++bb) acc[bb] = fmaf(dv, win[bb], acc[bb]);
       }
     }
+    // the NRG row groups of one (x segment, band, tap row) are consecutive lanes: add them up with shuffles (whole warps are
+    // inside this branch) so that one lane per tap issues the shared-memory atomic (a CAS loop for fp32: it must not contend)
 #pragma unroll
-    for (int bb = 0; bb < K; ++bb) atomicAdd(&red[(band * K + a) * K + bb], acc[bb]);
+    for (int bb = 0; bb < K; ++bb) {
+      float v = acc[bb];
+#pragma unroll
+      for (int m = 1; m < NRG; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      if (rg == 0) atomicAdd(&red[(band * K + a) * K + bb], v);
+    }
   }
   if (NB == 1) {
     lsum = warp_sum(lsum);
@@ -429,7 +442,7 @@ static void launch_wgrad(cudaStream_t st, int k, const TX* xin, const TG* gin, f
   int dh = NB == 4 ? g.h2 : g.h, dw = NB == 4 ? g.w2 : g.w;
   int tx = cdiv(dw, WT_TW), ty = cdiv(dh, WT_TH);
   long long blocks = planes * tx * ty;
-  int threads = ((NB * k * 8 + 31) / 32) * 32;
+  int threads = (((NB == 4 ? 4 * k * 8 : k * 32) + 31) / 32) * 32;   // one thread per role of k_wt_wgrad
   if (threads < 64) threads = 64;
 #define ADN_WT_LAUNCH(KK) \
   {                                                                                                             \
