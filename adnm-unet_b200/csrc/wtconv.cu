@@ -217,9 +217,11 @@ k_wt_level(const TI* __restrict__ in, const float* __restrict__ coarse, TO* __re
 template <typename TX, typename TG, int K, int NB>
 __global__ void k_wt_wgrad(const TX* __restrict__ xin, const TG* __restrict__ gin, float* __restrict__ Rout,
                            float* __restrict__ sumg, int C, LevelGeom g, int tiles_x, int tiles_y) {
-  constexpr int R = K / 2, SH = WT_TH + 2 * R, SW = WT_TW + 2 * R, SWP = SW + 1;
+  // tile of the correlation domain: 16 x 32 sub-band positions (NB == 4) or 32 x 64 pixels (base conv: less halo, 4x fewer CTAs)
+  constexpr int TH = NB == 4 ? WT_TH : 2 * WT_TH, TW = NB == 4 ? WT_TW : 2 * WT_TW;
+  constexpr int R = K / 2, SH = TH + 2 * R, SW = TW + 2 * R, SWP = SW + 1;
   __shared__ float S[NB][SH][SWP];
-  __shared__ float Dt[NB][WT_TH][WT_TW + 1];
+  __shared__ float Dt[NB][TH][TW + 1];
   __shared__ float red[NB * K * K];
   __shared__ float redsum;
   int bid = blockIdx.x;
@@ -227,7 +229,7 @@ __global__ void k_wt_wgrad(const TX* __restrict__ xin, const TG* __restrict__ gi
   const int ty = bid % tiles_y;
   const long long plane = bid / tiles_y;
   const int c = (int)(plane % C);
-  const int sy0 = ty * WT_TH, sx0 = tx * WT_TW;
+  const int sy0 = ty * TH, sx0 = tx * TW;
   // extent of the tiled domain: sub-band plane (NB==4) or the pixel plane itself (NB==1)
   const int dh = NB == 4 ? g.h2 : g.h, dw = NB == 4 ? g.w2 : g.w;
   const TX* xs = xin + plane * (long long)g.h * g.w;
@@ -252,8 +254,8 @@ __global__ void k_wt_wgrad(const TX* __restrict__ xin, const TG* __restrict__ gi
     }
   }
   float lsum = 0.f;
-  for (int i = tid; i < WT_TH * WT_TW; i += nt) {
-    int sy = i / WT_TW, sx = i % WT_TW;
+  for (int i = tid; i < TH * TW; i += nt) {
+    int sy = i / TW, sx = i % TW;
     int gy = sy0 + sy, gx = sx0 + sx;
     bool in = gy < dh && gx < dw;
     if (NB == 4) {
@@ -272,8 +274,8 @@ __global__ void k_wt_wgrad(const TX* __restrict__ xin, const TG* __restrict__ gi
   __syncthreads();
   // roles: tid -> (row group rg, tap row a, band, x segment): slides a K-wide window along x for its tap row.  The window
   // walk is fully unrolled (the shift is register renaming: 2 LDS + K FMA per position).  NB == 4: 8 groups of 2 rows over
-  // the whole tile width; NB == 1 (base conv): 16 single rows x 2 half-width segments, so that all 160 threads work.
-  constexpr int XSEG = NB == 4 ? 1 : 2, XW = WT_TW / XSEG, RPT = NB == 4 ? 2 : 1, NRG = WT_TH / RPT;
+  // the whole tile width; NB == 1 (base conv): 32 single rows, so that all K * 32 threads work.
+  constexpr int XSEG = 1, XW = TW / XSEG, RPT = NB == 4 ? 2 : 1, NRG = TH / RPT;
   const int role = tid;
   if (role < NB * K * NRG * XSEG) {
     const int rg = role % NRG, a = (role / NRG) % K, band = (role / (NRG * K)) % NB, x0 = (role / (NRG * K * NB)) * XW;
@@ -440,7 +442,7 @@ template <typename TX, typename TG, int NB>
 static void launch_wgrad(cudaStream_t st, int k, const TX* xin, const TG* gin, float* Rout, float* sumg, int C,
                          const LevelGeom& g, long long planes) {
   int dh = NB == 4 ? g.h2 : g.h, dw = NB == 4 ? g.w2 : g.w;
-  int tx = cdiv(dw, WT_TW), ty = cdiv(dh, WT_TH);
+  int tx = cdiv(dw, NB == 4 ? WT_TW : 2 * WT_TW), ty = cdiv(dh, NB == 4 ? WT_TH : 2 * WT_TH);   // tile of k_wt_wgrad<.., NB>
   long long blocks = planes * tx * ty;
   int threads = (((NB == 4 ? 4 * k * 8 : k * 32) + 31) / 32) * 32;   // one thread per role of k_wt_wgrad
   if (threads < 64) threads = 64;
