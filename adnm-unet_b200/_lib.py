@@ -54,6 +54,10 @@ EXPORTS = {
                                   C.c_void_p, C.POINTER(WtWeightGrads), C.c_void_p, C.c_void_p]),
     "adn_threshold_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.c_int32, C.c_float,
                                        C.c_void_p, C.c_void_p]),
+    "adn_sumsq_workspace_floats": (C.c_int, []),
+    "adn_sumsq_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adn_adamw_flat": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 5 +
+                       [C.c_int32, C.c_float, C.c_float, C.c_void_p]),
     "adn_last_error": (C.c_char_p, []),
     "adn_abi_version": (C.c_int, []),
     "adn_device_supported": (C.c_int, []),

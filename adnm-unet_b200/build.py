@@ -6,7 +6,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libadnb200.so")
-SOURCES = ["adnssd_api.cu", "adnssd_sm100.cu", "wtconv.cu", "metrics.cu"]
+SOURCES = ["adnssd_api.cu", "adnssd_sm100.cu", "wtconv.cu", "metrics.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -44,6 +44,21 @@ struct ProfScope {
 #define ADN_CAT(a, b) ADN_CAT2(a, b)
 #define ADN_KERNEL(name, st) adn::ProfScope ADN_CAT(_adn_prof_, __LINE__)(name, st)
 
+// Number of SMs of the current device, queried once per process (148 on a B200; the fallback when no device is visible,
+// e.g. the size queries of the CPU-only ABI tests).  Grid sizes and per-CTA slab buffers are derived from it.
+int sm_count();
+// Diagnostic switches (ADN_* environment variables), read ONCE at first use: forward and backward always agree on the
+// kernel family and the saved layout, and no getenv() sits on the launch path.
+struct EnvCfg {
+  int rows_per_cta;   // ADN_ROWS_PER_CTA (0 = one CTA per SM)
+  bool rowconv;       // ADN_ROWCONV=0    keeps the 128-wide shapes on the halo-tile kernels
+  bool row_wide;      // ADN_ROW_WIDE=0   restricts the row kernels to W == 128
+  bool bwd_ws;        // ADN_BWD_WS=0     monolithic tile kernels for B1 / B2
+  int du_dbg;         // ADN_DU_DBG       knock-out mask of k_bconv_du
+  bool wide;          // ADN_WIDE=0       keeps d_model >= 64 on the CUDA-core generic path
+};
+const EnvCfg& env();
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

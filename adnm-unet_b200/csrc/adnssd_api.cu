@@ -1,6 +1,7 @@
 // C-ABI entry points of the ADN-SSD mixer (include/adnb200.h).  Validates the shape, carves the caller's
 // buffers and enqueues the kernels on the caller's stream.  No allocation, no host sync, no CPU fallback.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "adn_common.cuh"
@@ -16,6 +17,33 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+int sm_count() {
+  static int n = -1;
+  if (n < 0) {
+    int dev = 0, v = 0;
+    n = (cudaGetDevice(&dev) == cudaSuccess &&
+         cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;
+    cudaGetLastError();
+  }
+  return n;
+}
+
+const EnvCfg& env() {
+  static const EnvCfg cfg = [] {
+    auto flag = [](const char* name, bool dflt) { const char* e = getenv(name); return e ? e[0] != '0' : dflt; };
+    auto num = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; };
+    EnvCfg c;
+    c.rows_per_cta = num("ADN_ROWS_PER_CTA");
+    c.rowconv = flag("ADN_ROWCONV", true);
+    c.row_wide = flag("ADN_ROW_WIDE", true);
+    c.bwd_ws = flag("ADN_BWD_WS", true);
+    c.du_dbg = num("ADN_DU_DBG");
+    c.wide = flag("ADN_WIDE", true);
+    return c;
+  }();
+  return cfg;
 }
 
 // ---- diagnostics: launch counter + optional per-launch CUDA-event timing
@@ -51,6 +79,10 @@ static int validate(const AdnShape* s) {
               s->G);
   ADN_REQUIRE(s->Di > 0 && s->Di % 4 == 0, ADN_ERR_SHAPE, "d_inner must be a positive multiple of 4 (got %d)", s->Di);
   ADN_REQUIRE(s->P > 0 && s->Di % s->P == 0, ADN_ERR_SHAPE, "d_inner %% headdim != 0 (%d, %d)", s->Di, s->P);
+  // the even/odd channel split gives each parity Di/2 channels grouped into heads of P (models/ADNssd.py:371-386: the
+  // reference's rearrange 'b l (h p)' raises otherwise); an odd head count would index dt_bias / A_log / D out of bounds
+  ADN_REQUIRE((s->Di / 2) % s->P == 0 && (s->Di / s->P) % 2 == 0, ADN_ERR_SHAPE,
+              "(d_inner / 2) %% headdim != 0: the parity split needs an even number of heads (d_inner %d, headdim %d)", s->Di, s->P);
   ADN_REQUIRE(s->N > 0 && (s->G * s->N) % 4 == 0, ADN_ERR_SHAPE, "ngroups*d_state must be a multiple of 4 (got %d)",
               s->G * s->N);
   ADN_REQUIRE(s->dtype == ADN_F32 || s->dtype == ADN_BF16, ADN_ERR_DTYPE, "unsupported dtype %d", s->dtype);

@@ -643,182 +643,4 @@ k_bwd2_ws(const bf16* __restrict__ act, const bf16* __restrict__ sgrad, const bf
   if (warp == 9) tmem_dealloc(tbase, 256);
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_readout_ws (forward stages 4b + 5), per 128-token tile:
-//   MMA1: Y = Cc . S' (hi + lo)
-//   EPI1: y = Y + D*x;  LayerNorm (the two column halves exchange their partial sums);  LN(y) -> sCat
-//   MMA2: out = [LN(y) | zc] . W_out^T          (N = 32, K = 128)
-//   EPI2: out * alpha1 -> global (row-major external tensor)
-// ------------------------------------------------------------------------------------------------
-constexpr int RO_STG_B = (CCH + 16 + XC) * 2048;          // C | [LN(y) | zc] | x
-constexpr int RO_W_B = 16 * D * 16;                       // W_out image: [16 chunks of j'][32 rows d][8]
-constexpr int RO_SMEM = 2 * RO_STG_B + RO_W_B + 2 * SIMG_B + 2 * 2 * 128 * 8;   // + two exchange buffers [half][row] of float2
-constexpr int RO_TSTG = 96, RO_COL_OUT = 64;
-
-__global__ void __launch_bounds__(320, 1)
-k_readout_ws(const bf16* __restrict__ act, const float* __restrict__ S, const float* __restrict__ Dp,
-             const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ alpha1p,
-             const bf16* __restrict__ Wout, bf16* __restrict__ out, int tiles_per_batch, int num_tiles, int tiles_per_cta,
-             int* __restrict__ status) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full[2], mma1_done[2], epi1_done[2], mma2_done[2], acc_free[2];
-  __shared__ uint32_t tmem_slot;
-  __shared__ float sG[DI], sBt[DI], sDh[DI];
-  uint8_t* sStg = smem;
-  uint8_t* sW = smem + 2 * RO_STG_B;
-  uint8_t* sImg = sW + RO_W_B;
-  float2* sXch = reinterpret_cast<float2*>(sImg + 2 * SIMG_B);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int T0 = blockIdx.x * tiles_per_cta, T1 = min(num_tiles, T0 + tiles_per_cta);
-  for (int i = tid; i < DI; i += 320) { sG[i] = gamma[i]; sBt[i] = beta[i]; sDh[i] = Dp[head_of_channel(i, 4)]; }
-  for (int i = tid; i < 16 * D; i += 320) {
-    const int jc = i / D, d = i % D;
-    *reinterpret_cast<uint4*>(sW + (jc * D + d) * 16) = __ldg(reinterpret_cast<const uint4*>(Wout + (long long)d * 2 * DI + jc * 8));
-  }
-  if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&full[i], 33);
-      mbar_init(&mma1_done[i], 1);
-      mbar_init(&epi1_done[i], 8);
-      mbar_init(&mma2_done[i], 1);
-      mbar_init(&acc_free[i], 8);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 9) tmem_alloc(&tmem_slot, 256);
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tbase = tmem_slot;
-  bool ok = true;
-  if (T0 < T1) {
-    if (warp == 8) {
-      int cur_b = -1;
-      for (int t = T0; t < T1; ++t) {
-        const int it = t - T0, s = it & 1, b = t / tiles_per_batch;
-        uint8_t* sb = sStg + s * RO_STG_B;
-        if (it >= 2) ok = mbar_wait(&mma2_done[s], ((it >> 1) - 1) & 1) && ok;
-        if (b != cur_b) {
-          stage_state_warp(S + (long long)b * GN * DI, sImg + (b & 1) * SIMG_B, lane);
-          cur_b = b;
-        }
-        if (lane == 0) {
-          mbar_expect_tx(&full[s], (uint32_t)(2 * XC + CCH) * 2048);
-          bulk_g2s(sb + (CCH + XC) * 2048, act + ((long long)t * NA) * 1024, 2 * XC * 2048, &full[s]);          // z -> sCat[8..16), x -> sX
-          bulk_g2s(sb, act + ((long long)t * NA + 2 * XC + CCH) * 1024, CCH * 2048, &full[s]);                  // C
-        }
-        fence_async_smem();
-        mbar_arrive(&full[s]);
-      }
-    } else if (warp == 9) {
-      if (elect_one()) {
-        const uint32_t sbase = smem_u32(sStg), wbase = smem_u32(sW), ibase = smem_u32(sImg);
-        const uint32_t id_y = make_idesc_rt(128, DI, false, false), id_o = make_idesc_rt(128, D, false, false);
-        auto mma2 = [&](int t) {
-          const int it = t - T0, s = it & 1;
-          ok = mbar_wait(&epi1_done[s], (it >> 1) & 1) && ok;
-          tc_fence_after();
-          const uint64_t dA = make_desc(sbase + s * RO_STG_B + CCH * 2048, 2048, 128), dB = make_desc(wbase, D * 16, 128);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (k == 0) umma_c<false>(tbase + s * RO_TSTG + RO_COL_OUT, dA, dB, id_o);
-            else umma_c<true>(tbase + s * RO_TSTG + RO_COL_OUT, dadd(dA, k * 2 * 2048), dadd(dB, k * 2 * D * 16), id_o);
-          }
-          umma_commit(&mma2_done[s]);
-        };
-        for (int t = T0; t < T1; ++t) {
-          const int it = t - T0, s = it & 1, b = t / tiles_per_batch;
-          ok = mbar_wait(&full[s], (it >> 1) & 1) && ok;
-          if (it >= 2) ok = mbar_wait(&acc_free[s], ((it >> 1) - 1) & 1) && ok;
-          tc_fence_after();
-          const uint32_t tb = tbase + s * RO_TSTG, img = ibase + (b & 1) * SIMG_B;
-          const uint64_t dC = make_desc(sbase + s * RO_STG_B, 2048, 128), dAh = make_desc(img, DI * 16, 128), dAl = make_desc(img + 4096, DI * 16, 128);
-          umma_c<false>(tb, dC, dAh, id_y);
-          umma_c<true>(tb, dadd(dC, 2 * 2048), dadd(dAh, 2 * DI * 16), id_y);
-          umma_c<true>(tb, dC, dAl, id_y);
-          umma_c<true>(tb, dadd(dC, 2 * 2048), dadd(dAl, 2 * DI * 16), id_y);
-          umma_commit(&mma1_done[s]);
-          if (t > T0) mma2(t - 1);
-        }
-        mma2(T1 - 1);
-        if (!ok) atomicExch(status, 34);
-      }
-    } else {
-      const int q = warp & 3, h = warp >> 2, row = q * 32 + lane;
-      const float a1 = *alpha1p;
-      auto epi2 = [&](int t) {
-        const int it = t - T0, s = it & 1;
-        ok = mbar_wait(&mma2_done[s], (it >> 1) & 1) && ok;
-        tc_fence_after();
-        float v[16];
-        tmem_ld16(tbase + ((uint32_t)(q * 32) << 16) + s * RO_TSTG + RO_COL_OUT + h * 16, v);
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_free[s]);
-        float o0[8], o1[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { o0[j] = a1 * v[j]; o1[j] = a1 * v[8 + j]; }
-        bf16* dst = out + ((long long)t * 128 + row) * D + h * 16;
-        *reinterpret_cast<uint4*>(dst) = pack8(o0);
-        *reinterpret_cast<uint4*>(dst + 8) = pack8(o1);
-      };
-      for (int t = T0; t < T1; ++t) {
-        const int it = t - T0, s = it & 1;
-        uint8_t* sb = sStg + s * RO_STG_B;
-        uint8_t* sCatRow = sb + CCH * 2048 + row * 16;
-        const uint8_t* sXRow = sb + (CCH + 16) * 2048 + row * 16;
-        ok = mbar_wait(&full[s], (it >> 1) & 1) && ok;
-        ok = mbar_wait(&mma1_done[s], (it >> 1) & 1) && ok;
-        tc_fence_after();
-        const uint32_t ta = tbase + ((uint32_t)(q * 32) << 16) + s * RO_TSTG;
-        float y[32];
-        float p1 = 0.f, p2 = 0.f;
-#pragma unroll
-        for (int cb = 0; cb < 32; cb += 16) {
-          float v[16], x0[8], x1[8];
-          tmem_ld16(ta + h * 32 + cb, v);
-          unpack8(*reinterpret_cast<const uint4*>(sXRow + (4 * h + cb / 8) * 2048), x0);
-          unpack8(*reinterpret_cast<const uint4*>(sXRow + (4 * h + cb / 8 + 1) * 2048), x1);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            y[cb + j] = fmaf(sDh[h * 32 + cb + j], x0[j], v[j]);
-            y[cb + 8 + j] = fmaf(sDh[h * 32 + cb + 8 + j], x1[j], v[8 + j]);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) { p1 += y[c]; p2 = fmaf(y[c], y[c], p2); }
-        sXch[((it & 1) * 2 + h) * 128 + row] = make_float2(p1, p2);      // buffers alternate per tile: one barrier per tile
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        {
-          const float2 o = sXch[((it & 1) * 2 + (h ^ 1)) * 128 + row];
-          p1 += o.x;
-          p2 += o.y;
-        }
-        const float mu = p1 * (1.f / DI);
-        const float rstd = rsqrtf(fmaxf(p2 * (1.f / DI) - mu * mu, 0.f) + 1e-5f);
-#pragma unroll
-        for (int cg = 0; cg < 4; ++cg) {
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = (y[cg * 8 + j] - mu) * rstd * sG[h * 32 + cg * 8 + j] + sBt[h * 32 + cg * 8 + j];
-          *reinterpret_cast<uint4*>(sCatRow + (4 * h + cg) * 2048) = pack8(v);
-        }
-        tc_fence_before();
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&epi1_done[s]);
-        if (t > T0) epi2(t - 1);
-      }
-      epi2(T1 - 1);
-      if (!ok && lane == 0) atomicExch(status, 35);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) tmem_dealloc(tbase, 256);
-}
-
 }  // namespace bwdws

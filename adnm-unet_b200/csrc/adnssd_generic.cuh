@@ -200,7 +200,7 @@ static inline void launch_reduce_gemm(cudaStream_t st, const TX* X, long long ld
                                       int parity_mask) {
   // enough splits to fill the machine (148 SMs x ~4 CTAs) without shredding the reduction
   int tiles = cdiv(N1, 64) * cdiv(N2, 64) * B;
-  int splits = max(1, min(cdiv(L, 64), cdiv(148 * 4, tiles)));
+  int splits = max(1, min(cdiv(L, 64), cdiv(sm_count() * 4, tiles)));
   int chunk = cdiv(cdiv(L, splits), 16) * 16;
   splits = cdiv(L, chunk);
   dim3 grid(cdiv(N2, 64), cdiv(N1, 64), B * splits);
@@ -811,7 +811,7 @@ int generic_backward(const MixerDims& d, const AdnWeights& w, const T* u, const 
   // ---- in_proj backward
   launch_gemm<TWs, T, false>(st, W.draw, d.ldr, 0, w.in_proj_w, d.D, 0, du, d.D, 0, (int)Tt, d.D, d.dip, 1, nullptr, 0);
   launch_reduce_gemm<TWs, T>(st, W.draw, d.ldr, u, d.D, W.acc.dWin, d.D, 0, d.dip, d.D, (int)Tt, 1, 0);
-  { ADN_KERNEL("k_finalize", st); k_finalize<<<148, 256, 0, st>>>(W.acc, w, g, d.D, d.Di, d.GN, d.nh, d.dip); }
+  { ADN_KERNEL("k_finalize", st); k_finalize<<<sm_count(), 256, 0, st>>>(W.acc, w, g, d.D, d.Di, d.GN, d.nh, d.dip); }
   ADN_CHECK_LAUNCH();
   return ADN_OK;
 }

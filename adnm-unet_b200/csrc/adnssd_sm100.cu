@@ -1346,8 +1346,8 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ R
   // Fail loudly without a host synchronisation: if a kernel of this backward pass flagged a pipeline fault (barrier
   // time-out), the gradients that leave this last kernel are poisoned with NaNs (and so is du[0..7]).
   const bool bad = *status != 0;
-  const float poison = bad ? __int_as_float(0x7fc00000) : 0.f;
-  if (bad && blockIdx.x == 0 && tid < 8) du[tid] = __float2bfloat16_rn(poison);
+  float poison_late = bad ? __int_as_float(0x7fc00000) : 0.f;
+  if (bad && blockIdx.x == 0 && tid < 8) du[tid] = __float2bfloat16_rn(poison_late);
   // ---- phase 1 (row-kernel / warp-specialised path): the backward kernels left one slab of partial sums per CTA instead
   // of contended atomics.  Every block adds up 32-element chunks (8 slab lanes x 32 elements, coalesced), then the grid
   // meets at a counter (this small grid is always co-resident) and phase 2 reads the reduced arrays.
@@ -1393,16 +1393,29 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ R
     }
     __threadfence();
     __syncthreads();
+    // Grid hand-off through a counter.  The launch is an ordinary one, so co-residency of the grid is checked on the host
+    // (launch_finalize_fast: occupancy x SMs >= grid) and the wait is BOUNDED anyway: if a block cannot be scheduled next
+    // to its peers (MPS / MIG / a co-running kernel holding the SMs) the spin times out after ~2 s and every gradient this
+    // block writes is poisoned with NaNs - loud downstream, never a hung GPU.
+    __shared__ int s_timeout;
     if (tid == 0) {
       atomicAdd(a.sync_counter, 1);
-      while (atomicAdd(a.sync_counter, 0) < (int)gridDim.x) { }
+      int ok = 0;
+      for (unsigned spin = 0; spin < (1u << 22); ++spin) {
+        if (atomicAdd(a.sync_counter, 0) >= (int)gridDim.x) { ok = 1; break; }
+        __nanosleep(spin < 64 ? 20 : 500);
+      }
+      s_timeout = !ok;
       __threadfence();
     }
     __syncthreads();
+    if (s_timeout) poison_late = __int_as_float(0x7fc00000);
     a.dWin_parts = 0;
     a.dK_parts = 0;
     a.head_parts = 0;
+    if (s_timeout && tid < 8) du[tid] = __float2bfloat16_rn(poison_late);
   }
+  const float poison = poison_late;
   // ---- phase 2
   //   blocks [0, nb_in)            dW_in from the accumulator / the per-CTA slabs of k_bwd4        (32 elements x 8 slab lanes)
   //   blocks [nb_in, nb_in + 2Di)  dW_out, dgamma, dbeta, dalpha1 partial from Rt / sum(dout)    (one warp per column)
@@ -1451,6 +1464,16 @@ k_finalize_fast(GradAcc a, AdnWeights w, AdnWeightGrads g, float* __restrict__ R
   blk -= 2 * Di;
   if (blk >= nb_rest) return;      // extra blocks only take part in phase 1
   finalize_body(a, w, g, D, Di, GN, nh, dip, (long long)blk * 256 + tid, (long long)nb_rest * 256, false);
+}
+
+// k_finalize_fast hands off between its two phases through a counter: the whole grid must be co-resident.  Verified on the
+// host (occupancy query cached per process); the in-kernel wait is bounded as well.
+static int check_finalize_grid(int fgrid) {
+  static int occ = -1;
+  if (occ < 0) ADN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_finalize_fast, 256, 0));
+  ADN_REQUIRE(fgrid <= occ * sm_count(), ADN_ERR_SHAPE, "k_finalize_fast: grid %d exceeds the co-resident capacity %d x %d",
+              fgrid, occ, sm_count());
+  return ADN_OK;
 }
 
 // One launch for all per-call weight preparation: conv kernel assembly, in_proj hi/lo split, out_proj -> bf16.
@@ -1742,11 +1765,11 @@ struct FastWs {           // placed after the generic workspace of the same pass
   size_t bytes;
   FastWs(const MixerDims& d, void* p) {
     Carver c(p);
-    dWin_part = c.take<float>((size_t)148 * d.dip * d.D);
-    dK_part = c.take<float>((size_t)148 * d.CC * 9);
-    Rt = c.take<float>((size_t)148 * (2 * d.Di * d.D + d.D));      // one slab per CTA on the warp-specialised path
+    dWin_part = c.take<float>((size_t)sm_count() * d.dip * d.D);
+    dK_part = c.take<float>((size_t)sm_count() * d.CC * 9);
+    Rt = c.take<float>((size_t)sm_count() * (2 * d.Di * d.D + d.D));      // one slab per CTA on the warp-specialised path
     sdout = Rt ? Rt + (size_t)2 * d.Di * d.D : nullptr;
-    head_part = c.take<float>((size_t)148 * 3 * d.nh);
+    head_part = c.take<float>((size_t)sm_count() * 3 * d.nh);
     status = c.take<int>(64);
     bytes = c.off;
   }
@@ -1755,16 +1778,14 @@ struct FastWs {           // placed after the generic workspace of the same pass
 // shapes served by the conv-as-GEMM row kernels: the full-resolution refiner mixers at 128-token-wide grids
 // rows per CTA of the row kernels: one CTA per SM by default; ADN_ROWS_PER_CTA overrides (diagnostics)
 static int rows_per_cta(int rows_total, int ctas) {
-  const char* e = getenv("ADN_ROWS_PER_CTA");
-  if (e && atoi(e) > 0) return atoi(e);
+  // the override may only coarsen the split: the per-CTA slab buffers are sized for `ctas` CTAs
+  if (env().rows_per_cta > 0 && cdiv(rows_total, env().rows_per_cta) <= ctas) return env().rows_per_cta;
   return cdiv(rows_total, ctas);
 }
 
 static bool rowconv_supported(const MixerDims& d) {
-  const char* e = getenv("ADN_ROWCONV");      // diagnostics: ADN_ROWCONV=0 keeps these shapes on the tile kernels
-  if (e && e[0] == '0') return false;
-  const char* ew = getenv("ADN_ROW_WIDE");     // diagnostics: ADN_ROW_WIDE=0 restricts the row kernels to W == 128
-  const bool wide = !(ew && ew[0] == '0');
+  if (!env().rowconv) return false;             // diagnostics: ADN_ROWCONV=0 keeps these shapes on the tile kernels
+  const bool wide = env().row_wide;             // diagnostics: ADN_ROW_WIDE=0 restricts the row kernels to W == 128
   return d.D == 32 && d.Di == 64 && d.P == 4 && d.GN == 32 && d.dip == 208 && d.ldr == 208 &&
          (d.W == 128 || (wide && d.W % 128 == 0 && d.W <= 1024));
 }
@@ -1787,7 +1808,7 @@ static int launch_state(const MixerDims& d, const bf16* act, const bf16* raw, co
   int rc = set_smem(k_state<DI, GN>, smem);
   if (rc) return rc;
   const int tpb = cdiv(d.L, 128);
-  const int cpb = max(1, min(tpb, cdiv(148 * 2, d.B)));
+  const int cpb = max(1, min(tpb, cdiv(sm_count() * 2, d.B)));
   { ADN_KERNEL("k_state", st); k_state<DI, GN><<<d.B * cpb, 128, smem, st>>>(act, raw, d.ldr, d.CC, w.dt_bias, w.A_log, S, d.L, tpb, cpb, status); }
   return ADN_OK;
 }
@@ -1800,7 +1821,7 @@ static int launch_readout(const MixerDims& d, const bf16* act, const float* S, c
   if (rc) return rc;
   const int tpb = cdiv(d.L, 128), nt = tpb * d.B;
   const int per_sm = smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3);
-  { ADN_KERNEL("k_readout", st); k_readout<DI, GN><<<min(nt, 148 * per_sm), 128, smem, st>>>(act, d.CC, S, w.D, w.norm_w, w.norm_b, w.alpha1, Wout, out, d.L, tpb, nt, status); }
+  { ADN_KERNEL("k_readout", st); k_readout<DI, GN><<<min(nt, sm_count() * per_sm), 128, smem, st>>>(act, d.CC, S, w.D, w.norm_w, w.norm_b, w.alpha1, Wout, out, d.L, tpb, nt, status); }
   return ADN_OK;
 }
 
@@ -1817,13 +1838,13 @@ static int launch_inproj(const MixerDims& d, const bf16* u, const PrepBufs& P, c
   const int num_tiles = cdiv(d.T, 128);
   const size_t smem = (size_t)(2 * 256 * D + 2 * 128 * D) * sizeof(bf16);
   ADN_CHECK_CUDA(cudaFuncSetAttribute(k_inproj<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = min(num_tiles, 148 * 2);
+  const int grid = min(num_tiles, sm_count() * 2);
   { ADN_KERNEL("k_inproj", st); k_inproj<D><<<grid, 128, smem, st>>>(u, P.Whi, P.Wlo, raw, d.ldr, d.dip, d.T, num_tiles, F.status); }
   return ADN_OK;
 }
 
 static inline void split_tiles(int num_tiles, int per_sm, int* grid, int* per_cta) {
-  const int target = max(1, min(num_tiles, 148 * per_sm));
+  const int target = max(1, min(num_tiles, sm_count() * per_sm));
   *per_cta = cdiv(num_tiles, target);
   *grid = cdiv(num_tiles, *per_cta);
 }
@@ -1896,21 +1917,12 @@ int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* 
     static_assert(sizeof(float) * rowconv::NH == sizeof(bf16) * rowconv::D, "u_tl does not fit the wdec slot");
     int rc = set_smem(rowconv::k_fconv, rowconv::FC_SMEM);
     if (rc) return rc;
-    const int rows_total = d.B * d.H * (d.W / 128), per = rows_per_cta(rows_total, 148), grid = cdiv(rows_total, per);   // strip rows
+    const int rows_total = d.B * d.H * (d.W / 128), per = rows_per_cta(rows_total, sm_count()), grid = cdiv(rows_total, per);   // strip rows
     { ADN_KERNEL("k_fconv", st); rowconv::k_fconv<<<grid, rowconv::FC_THREADS, rowconv::FC_SMEM, st>>>(u, P.WtF, w.dt_bias, w.A_log, S.act, training ? S.pre : nullptr, S.raw, S.S, d.H, rows_total, per, F.status, training ? reinterpret_cast<bf16*>(S.wdec) : nullptr, d.W / 128); }
-    // The warp-specialised readout (one CTA per SM, two tiles in flight) measured SLOWER than the monolithic tile kernel
-    // at three CTAs per SM (41.7 vs 33.2 us at the benchmark shape): this stage is light enough that plain occupancy
-    // hides its latencies better.  It stays selectable for experiments (ADN_READOUT_WS=1).
-    const char* ews = getenv("ADN_READOUT_WS");
-    if (!(ews && ews[0] == '1')) {
-      rc = launch_readout<64, 32>(d, S.act, S.S, w, P.Wout, out, F.status, st);
-      if (rc) return rc;
-    } else {
-      const int tpb = d.L / 128, nt = tpb * d.B, per = cdiv(nt, 148), grid = cdiv(nt, per);
-      rc = set_smem(bwdws::k_readout_ws, bwdws::RO_SMEM);
-      if (rc) return rc;
-      { ADN_KERNEL("k_readout_ws", st); bwdws::k_readout_ws<<<grid, 320, bwdws::RO_SMEM, st>>>(S.act, S.S, w.D, w.norm_w, w.norm_b, w.alpha1, P.Wout, out, tpb, nt, per, F.status); }
-    }
+    // (A warp-specialised readout, one CTA per SM with two tiles in flight, measured SLOWER than this monolithic tile
+    // kernel at three CTAs per SM - 41.7 vs 33.2 us at the benchmark shape - and was removed in round 2.)
+    rc = launch_readout<64, 32>(d, S.act, S.S, w, P.Wout, out, F.status, st);
+    if (rc) return rc;
     ADN_CHECK_LAUNCH();
     return ADN_OK;
   }
@@ -1951,8 +1963,7 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   if (rowconv_supported(d)) {
     // B1 / B2 write dpre = dact * SiLU'(pre) directly; ddt goes to a compact TL tensor (2 chunks per tile) in W.draw
     int rc, rt_parts = 0;
-    const char* ews = getenv("ADN_BWD_WS");      // diagnostics: ADN_BWD_WS=0 keeps the monolithic tile kernels
-    const bool ws_path = !(ews && ews[0] == '0');
+    const bool ws_path = env().bwd_ws;            // diagnostics: ADN_BWD_WS=0 keeps the monolithic tile kernels
     // warp-specialised path: ONE memset per backward pass (the fault word lives in the zeroed region, Rt / sum(dout) are
     // slabs that are fully overwritten, and k_bwd1_ws clears the alpha1 gradient that k_finalize_fast accumulates into)
     int* status = ws_path ? W.status : F.status;
@@ -1966,7 +1977,7 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
       rc = launch_bwd2<64, 32>(d, S.act, S.raw, W.dS, w, F, W.dact, W.draw, W.acc, st, S.pre, 2, 0);
       if (rc) return rc;
     } else {
-      const int tpb = d.L / 128, nt = tpb * d.B, per = cdiv(nt, 148), grid = cdiv(nt, per);
+      const int tpb = d.L / 128, nt = tpb * d.B, per = cdiv(nt, sm_count()), grid = cdiv(nt, per);
       rc = set_smem(bwdws::k_bwd1_ws, bwdws::B1_SMEM);
       if (rc) return rc;
       { ADN_KERNEL("k_bwd1_ws", st); bwdws::k_bwd1_ws<<<grid, bwdws::WS_THREADS, bwdws::B1_SMEM, st>>>(dout, S.act, S.pre, S.S, w.D, w.norm_w, w.alpha1, P.Wout, W.dact, F.Rt, F.sdout, W.dS, tpb, nt, per, status, g.alpha1); }
@@ -1981,8 +1992,8 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
     {
       rc = set_smem(rowconv::k_bconv_du, rowconv::DU_SMEM);
       if (rc) return rc;
-      const int per = rows_per_cta(rows_total, 148), grid = cdiv(rows_total, per);
-      { ADN_KERNEL("k_bconv_du", st); rowconv::k_bconv_du<<<grid, 192, rowconv::DU_SMEM, st>>>(W.dact, W.draw, P.WtB, du, d.H, rows_total, per, status, getenv("ADN_DU_DBG") ? atoi(getenv("ADN_DU_DBG")) : 0, TPR); }
+      const int per = rows_per_cta(rows_total, sm_count()), grid = cdiv(rows_total, per);
+      { ADN_KERNEL("k_bconv_du", st); rowconv::k_bconv_du<<<grid, 192, rowconv::DU_SMEM, st>>>(W.dact, W.draw, P.WtB, du, d.H, rows_total, per, status, env().du_dbg, TPR); }
       if (TPR > 1) {
         const int n_edges = d.B * d.H * (TPR - 1);
         { ADN_KERNEL("k_bconv_du_edge", st); rowconv::k_bconv_du_edge<<<cdiv(2LL * n_edges * 32, 256), 256, 0, st>>>(W.dact, P.Kc, w.in_proj_w, du, d.H, TPR, n_edges); }
@@ -1991,7 +2002,7 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
     {
       rc = set_smem(rowconv::k_bconv_wg, rowconv::WG_SMEM);
       if (rc) return rc;
-      const int cpb = max(1, min(74, rows_total)), per = cdiv(rows_total, cpb), parts = cdiv(rows_total, per);
+      const int cpb = max(1, min(sm_count() / 2, rows_total)), per = cdiv(rows_total, cpb), parts = cdiv(rows_total, per);
       { ADN_KERNEL("k_bconv_wg", st); rowconv::k_bconv_wg<<<2 * parts, 192, rowconv::WG_SMEM, st>>>(W.dact, W.draw, reinterpret_cast<const bf16*>(S.wdec), w.in_proj_w, P.Kc, F.dK_part, F.dWin_part, d.H, rows_total, per, parts, status, TPR, W.acc.sync_counter + 16); }
       W.acc.dWin_part = F.dWin_part;
       W.acc.dWin_parts = parts;
@@ -2004,6 +2015,8 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
     // every block of this grid (344 x 256 threads at the benchmark shape, < 3 blocks per SM) is co-resident, which the
     // counter hand-off between the two phases relies on; a 148 x 6 grid for phase 1 measured no faster
     const int fgrid = nb_in + 2 * d.Di + nb_rest;
+    rc = check_finalize_grid(fgrid);
+    if (rc) return rc;
     { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<fgrid, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest, rt_parts, status, du); }
     ADN_CHECK_LAUNCH();
     return ADN_OK;
@@ -2036,6 +2049,8 @@ int sm100_backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const
   {
     if (g.alpha1) ADN_CHECK_CUDA(cudaMemsetAsync(g.alpha1, 0, sizeof(float), st));
     const int nb_in = cdiv(d.dip * d.D, 32), nb_rest = 8;
+    rc = check_finalize_grid(nb_in + 2 * d.Di + nb_rest);
+    if (rc) return rc;
     { ADN_KERNEL("k_finalize_fast", st); k_finalize_fast<<<nb_in + 2 * d.Di + nb_rest, 256, 0, st>>>(W.acc, w, g, F.Rt, F.sdout, d.D, d.Di, d.GN, d.nh, d.dip, nb_in, nb_rest, 0, F.status, du); }
   }
   ADN_CHECK_LAUNCH();

@@ -96,7 +96,7 @@ extern "C" int adn_threshold_counts(const float* obs, const float* sim, int64_t 
   if (n == 0) return ADN_OK;
   // each thread may count at most 2^32 events: 148*8 blocks x 256 threads x 4 => fine up to 2^50 elements
   long long blocks = (n / 4 + 255) / 256;
-  int grid = (int)(blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks));
+  int grid = (int)(blocks < 1 ? 1 : (blocks > sm_count() * 8 ? sm_count() * 8 : blocks));
   { ADN_KERNEL("k_threshold_counts", st); k_threshold_counts<<<grid, 256, 0, st>>>(obs, sim, n, thr, value_scale, (unsigned long long*)table); }
   ADN_CHECK_LAUNCH();
   return ADN_OK;

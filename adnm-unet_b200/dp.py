@@ -27,7 +27,12 @@ class GradAllReducer:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.sizes = [p.numel() for p in self.params]
         dev = self.params[0].device if self.params else torch.device("cpu")
-        self.flat = torch.zeros(sum(self.sizes), dtype=self.params[0].dtype if self.params else torch.float32, device=dev)
+        # one bucket dtype: the widest parameter dtype (fp32 masters in every use of this class); narrower parameters
+        # get a converted copy back as their .grad
+        dt = torch.float32
+        if self.params and all(p.dtype == self.params[0].dtype for p in self.params):
+            dt = self.params[0].dtype
+        self.flat = torch.zeros(sum(self.sizes), dtype=dt, device=dev)
         self.present = None
 
     def _presence(self):
@@ -38,23 +43,29 @@ class GradAllReducer:
 
     @torch.no_grad()
     def __call__(self):
-        """One gather kernel (torch.cat into the flat bucket), one all-reduce, one scale; afterwards every p.grad is a
-        VIEW into the flat bucket (no scatter copies) - valid until the next call."""
+        """Gather into the flat bucket (slice-wise copies; a gradient that already IS its slice - kept by the caller across
+        steps, e.g. optimizer.zero_grad(set_to_none=False) or gradient accumulation - is left in place instead of being
+        copied onto itself), one all-reduce, one scale; afterwards every p.grad is a VIEW into the flat bucket."""
         if self.present is None:
             self._presence()
         live = [(p, n) for p, n, pres in zip(self.params, self.sizes, self.present) if pres]
         total = sum(n for _, n in live)
         used = self.flat[:total]
-        pieces = [(p.grad.reshape(-1).to(self.flat.dtype) if p.grad is not None
-                   else torch.zeros(n, dtype=self.flat.dtype, device=self.flat.device)) for p, n in live]
-        if pieces:
-            torch.cat(pieces, out=used)
+        off = 0
+        for p, n in live:
+            dst = used[off:off + n]
+            if p.grad is None:
+                dst.zero_()
+            elif p.grad.data_ptr() != dst.data_ptr() or p.grad.dtype != dst.dtype:
+                dst.copy_(p.grad.reshape(-1))
+            off += n
         if self.world > 1:
             dist.all_reduce(used, group=self.group)
             used.mul_(1.0 / self.world)
         off = 0
         for p, n in live:
-            p.grad = used[off:off + n].view_as(p)
+            v = used[off:off + n].view_as(p)
+            p.grad = v if p.dtype == used.dtype else v.to(p.dtype)
             off += n
         return used
 

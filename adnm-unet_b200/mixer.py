@@ -60,22 +60,26 @@ def _prep_param(p, device):
     return p.detach().float().contiguous()
 
 
+STATS = {"forward_training": 0, "forward_inference": 0}   # which kernel variant ran (saved != NULL / saved == NULL)
 _GRAD_NUMEL = {}   # tuple of parameter shapes -> (sizes, total): the 18 gradients live in ONE flat fp32 buffer
 
 
 class _AdnSsdFunction(torch.autograd.Function):
-    """u, then the 18 used parameters in USED_KEYS order."""
+    """u, then the 18 used parameters in USED_KEYS order.  `grad_mode` is torch.is_grad_enabled() sampled at the call
+    site: inside forward() grad mode is always off and ctx.needs_input_grad ignores torch.no_grad(), so without it an
+    eval-mode forward would allocate `saved` and run the training variant of the kernels."""
 
     @staticmethod
-    def forward(ctx, u, H, W, headdim, d_state, d_inner, ngroups, *params):
+    def forward(ctx, u, H, W, headdim, d_state, d_inner, ngroups, grad_mode, *params):
         _lib.require_cuda(u, "u")
         lib = _lib.load()
         u = u.contiguous()
         shape, sv, fw, bw = _shape_info(u, H, W, headdim, d_state, d_inner, ngroups)
         tensors = {k: _prep_param(p, u.device) for k, p in zip(USED_KEYS, params)}
         wts = _weights_struct(_lib.AdnWeights, tensors)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = bool(grad_mode) and any(ctx.needs_input_grad)
         saved = _lib.scratch(sv, u.device) if need_grad else None
+        STATS["forward_training" if need_grad else "forward_inference"] += 1
         ws = _lib.scratch(fw, u.device)
         out = torch.empty_like(u)
         with _lib.on_device(u.device):
@@ -107,15 +111,15 @@ class _AdnSsdFunction(torch.autograd.Function):
             _lib.check(lib.adnssd_backward(shape, wts, _lib.ptr(u), _lib.ptr(saved), _lib.ptr(dout), _lib.ptr(du), gst,
                                            _lib.ptr(ws), _lib.stream_ptr(u.device)), "adnssd_backward")
         pg = tuple((grads[k].view(p.shape) if p.dtype == torch.float32 else grads[k].to(p.dtype).view(p.shape)) if need else None
-                   for k, p, need in zip(USED_KEYS, params, ctx.needs_input_grad[7:]))
-        return (du if ctx.needs_input_grad[0] else None, None, None, None, None, None, None) + pg
+                   for k, p, need in zip(USED_KEYS, params, ctx.needs_input_grad[8:]))
+        return (du if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, None) + pg
 
 
 def adnssd_mixer(u, H, W, params, headdim, d_state, ngroups=2, expand=2):
     """Functional form: `params` maps the reference's state_dict keys (PARAM_KEYS) to tensors."""
     d_inner = int(expand * u.shape[-1])
     return _AdnSsdFunction.apply(u, int(H), int(W), int(headdim), int(d_state), d_inner, int(ngroups),
-                                 *[params[k] for k in USED_KEYS])
+                                 torch.is_grad_enabled(), *[params[k] for k in USED_KEYS])
 
 
 class Mamba2(nn.Module):
@@ -141,6 +145,9 @@ class Mamba2(nn.Module):
             ngroups = self.d_inner // headdim
         self.ngroups = ngroups
         assert self.d_inner % headdim == 0
+        if (self.d_inner // 2) % headdim != 0:
+            # the reference's parity split `rearrange(x, 'b l (h p) -> ...')` on d_inner/2 channels raises in this case
+            raise ValueError(f"(d_inner/2) % headdim != 0 (d_inner={self.d_inner}, headdim={headdim})")
         self.nheads = self.d_inner // headdim
         self.dt_limit, self.learnable_init_states = dt_limit, learnable_init_states
         self.chunk_size, self.use_mem_eff_path, self.layer_idx = chunk_size, use_mem_eff_path, layer_idx
@@ -188,7 +195,7 @@ class Mamba2(nn.Module):
     def forward(self, u, H, W, seq_idx=None):
         if seq_idx is not None:
             raise NotImplementedError("seq_idx is always None in ADNM-UNet")
-        if torch.is_autocast_enabled():
-            u = u.to(torch.get_autocast_gpu_dtype())
+        if torch.is_autocast_enabled("cuda"):
+            u = u.to(torch.get_autocast_dtype("cuda"))
         return _AdnSsdFunction.apply(u, int(H), int(W), self.headdim, self.d_state, self.d_inner, self.ngroups,
-                                     *[self._param(k) for k in USED_KEYS])
+                                     torch.is_grad_enabled(), *[self._param(k) for k in USED_KEYS])

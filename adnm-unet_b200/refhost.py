@@ -1,0 +1,257 @@
+"""Host the UNMODIFIED reference network (kanyu369/ADNM-UNet) around the B200 drop-ins.
+
+The reference is pure Python; it is located at run time (never vendored into this package):
+  $ADNM_REFERENCE_ROOT  ->  <repo>/baseline/_ref (git-ignored copy made by baseline/fetch_ref.py, travels to the GPU box)
+  ->  /root/reference (build container only).
+What this module does, and nothing more:
+  * stand-ins for the three third-party packages the reference imports but this image lacks (`timm`, `pywt`,
+    `mamba_ssm`): exactly the names the reference uses (models/ADNMUNet.py:11-16,27-32, models/ADNssd.py:5-9,
+    models/model_untils.py:11-16, models/WTConv2d.py:4-5).  `mamba_ssm...layer_norm.RMSNorm` is the standalone class
+    the reference README tells users to substitute (README.md:22-30) - the variant BASELINE.json names;
+  * `Decoder.forward` hard-codes a 256 x 256 grid (models/ADNMUNet.py:634): for other image sizes the method is
+    re-compiled from its own source with the literal replaced by sqrt(L) (no reference file is edited);
+  * `build_adnm_unet(img_size, dropin)`: `VisionMamba` with the literals of `create_ADNMUNet(5, 20, 6)`
+    (models/ADNMUNet.py:906-940) and, when `dropin`, the two module globals rebound to the sm_100a modules
+    (SURVEY.md 8(b)): `models.ADNMUNet.Mamba2`, `models.model_untils.WTConv2d`;
+  * `reference_optimizer` / `reference_loss`: train_untils.py:29-43 without importing train_untils (it imports every
+    baseline model and builds two of them at import).
+"""
+import contextlib
+import importlib
+import inspect
+import math
+import os
+import sys
+import textwrap
+import types
+
+import torch
+import torch.nn as nn
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = (os.environ.get("ADNM_REFERENCE_ROOT"), os.path.join(_REPO, "baseline", "_ref"), "/root/reference")
+
+
+def reference_root():
+    for c in _CANDIDATES:
+        if c and os.path.isfile(os.path.join(c, "models", "ADNssd.py")):
+            return c
+    return None
+
+
+def reference_available() -> bool:
+    return reference_root() is not None
+
+
+class StandaloneRMSNorm(nn.Module):
+    """README.md:22-30 of the reference (the 'no mamba_ssm' variant)."""
+
+    def __init__(self, d_model: int, eps: float = 1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(d_model))
+
+    def forward(self, x):
+        output = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + self.eps)
+        return output * self.weight.to(x.dtype)
+
+
+def install_shims():
+    if "timm" in sys.modules and getattr(sys.modules["timm"], "_adnm_shim", False):
+        return
+
+    def _mod(name):
+        m = types.ModuleType(name)
+        m._adnm_shim = True
+        sys.modules[name] = m
+        return m
+
+    class DropPath(nn.Module):  # drop_path == 0 everywhere in ADNM-UNet -> identity
+        def __init__(self, drop_prob=0.0, *a, **k):
+            super().__init__()
+            self.drop_prob = drop_prob
+
+        def forward(self, x):
+            return x
+
+    def to_2tuple(x):
+        return tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+
+    def to_ntuple(n):
+        return lambda x: tuple(x) if isinstance(x, (tuple, list)) else tuple([x] * n)
+
+    def trunc_normal_(tensor, mean=0.0, std=1.0, a=-2.0, b=2.0):
+        return nn.init.trunc_normal_(tensor, mean=mean, std=std, a=a, b=b)
+
+    class _Unused(nn.Module):
+        def __init__(self, *a, **k):
+            raise RuntimeError("timm stand-in: symbol imported but never used by ADNM-UNet")
+
+    if "timm" not in sys.modules:
+        timm = _mod("timm")
+        layers = _mod("timm.layers")
+        models = _mod("timm.models")
+        vit = _mod("timm.models.vision_transformer")
+        timm.layers, timm.models, models.vision_transformer = layers, models, vit
+        layers.DropPath, layers.to_2tuple, layers.to_ntuple, layers.trunc_normal_ = DropPath, to_2tuple, to_ntuple, trunc_normal_
+        for n in ("AvgPool2dSame", "Mlp", "GlobalResponseNormMlp", "LayerNorm2d", "LayerNorm"):
+            setattr(layers, n, _Unused)
+        layers.create_conv2d = layers.get_act_layer = layers.make_divisible = lambda *a, **k: None
+        models.register_model = lambda f: f
+        vit._cfg = lambda **k: dict(k)
+        vit._load_weights = lambda *a, **k: None
+
+    if "pywt" not in sys.modules:
+        pywt = _mod("pywt")
+        _mod("pywt.data")
+        s = 1.0 / math.sqrt(2.0)
+
+        class Wavelet:  # db1 taps only (models/WTConv2d.py:10-12,20-21)
+            def __init__(self, name):
+                assert name in ("db1", "haar"), name
+                self.dec_lo, self.dec_hi = [s, s], [-s, s]
+                self.rec_lo, self.rec_hi = [s, s], [s, -s]
+
+        pywt.Wavelet = Wavelet
+
+    if "mamba_ssm" not in sys.modules:
+        ms = _mod("mamba_ssm")
+        ops = _mod("mamba_ssm.ops")
+        tri = _mod("mamba_ssm.ops.triton")
+        ms.ops, ops.triton = ops, tri
+
+        def _dead(*a, **k):
+            raise RuntimeError("mamba_ssm stand-in: dead symbol (linear_attn_duality=False branch)")
+
+        for sub, names in (("ssd_combined", ("mamba_chunk_scan_combined", "mamba_split_conv1d_scan_combined")),
+                           ("layernorm_gated", ("RMSNorm",)),
+                           ("selective_state_update", ("selective_state_update",))):
+            m = _mod("mamba_ssm.ops.triton." + sub)
+            setattr(tri, sub, m)
+            for n in names:
+                setattr(m, n, _dead)
+        ln = _mod("mamba_ssm.ops.triton.layer_norm")
+        tri.layer_norm = ln
+        ln.RMSNorm, ln.layer_norm_fn, ln.rms_norm_fn = StandaloneRMSNorm, _dead, _dead
+
+
+@contextlib.contextmanager
+def cuda_to_is_noop():
+    """Neutralise `.to('cuda')` of the index vectors (models/ADNssd.py:329-382) when running the reference on CPU."""
+    if torch.cuda.is_available():
+        yield
+        return
+    orig = torch.Tensor.to
+
+    def patched(self, *args, **kwargs):
+        if args and isinstance(args[0], str) and args[0].startswith("cuda"):
+            args = args[1:]
+            if not args and not kwargs:
+                return self
+        return orig(self, *args, **kwargs)
+
+    torch.Tensor.to = patched
+    try:
+        yield
+    finally:
+        torch.Tensor.to = orig
+
+
+_NS = None
+
+
+def load_reference():
+    """The reference `models` package as a namespace: .ADNssd .WTConv2d .ADNMUNet .model_untils .loss (imported once)."""
+    global _NS
+    if _NS is not None:
+        return _NS
+    root = reference_root()
+    if root is None:
+        raise FileNotFoundError("reference sources not found: run `python baseline/fetch_ref.py` in the build container "
+                                "(copies the needed .py files of /root/reference into git-ignored baseline/_ref/)")
+    install_shims()
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    ns = types.SimpleNamespace(root=root)
+    for name in ("WTConv2d", "model_untils", "ADNssd", "ADNMUNet", "loss"):
+        setattr(ns, name, importlib.import_module("models." + name))
+    ns.ref_Mamba2 = ns.ADNssd.Mamba2          # the reference's own classes, whatever the globals are rebound to later
+    ns.ref_WTConv2d = ns.WTConv2d.WTConv2d
+    _patch_decoder_size(ns.ADNMUNet)
+    _NS = ns
+    return ns
+
+
+def _patch_decoder_size(mod):
+    """models/ADNMUNet.py:634 `x.view(b,256,256,d)` -> sqrt(L): same code, the literal made size-generic."""
+    if getattr(mod.Decoder.forward, "_adnm_size_generic", False):
+        return
+    src = textwrap.dedent(inspect.getsource(mod.Decoder.forward))
+    lit = "x.view(b,256,256,d)"
+    if lit not in src:
+        raise RuntimeError("reference Decoder.forward changed: the 256-literal patch no longer applies")
+    src = src.replace(lit, "x.view(b,int(math.sqrt(l)),int(math.sqrt(l)),d)")
+    scope = {}
+    exec(compile(src, mod.__file__ + ":Decoder.forward[size-generic]", "exec"), mod.__dict__, scope)
+    fn = scope["forward"]
+    fn._adnm_size_generic = True
+    mod.Decoder.forward = fn
+
+
+@contextlib.contextmanager
+def _bound(ns, dropin, mixer=True, wtconv=True):
+    """Rebind (or restore) the two construction-time globals for the duration of a model build."""
+    old = (ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d)
+    if dropin:
+        from adnm_unet_b200.mixer import Mamba2
+        from adnm_unet_b200.wtconv import WTConv2d
+        if mixer:
+            ns.ADNMUNet.Mamba2 = Mamba2
+        if wtconv:
+            ns.model_untils.WTConv2d = WTConv2d
+    else:
+        ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d = ns.ref_Mamba2, ns.ref_WTConv2d
+    try:
+        yield
+    finally:
+        ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d = old
+
+
+def build_adnm_unet(img_size=256, dropin=True, input_frames=5, output_frames=20, seed=0, mixer=True, wtconv=True):
+    """`create_ADNMUNet(5, 20, 6)` (models/ADNMUNet.py:906-940) at `img_size`; seed -> identical init for both variants
+    (the drop-in constructors consume the RNG stream exactly like the reference's: tests/test_abi_cpu.py)."""
+    ns = load_reference()
+    if seed is not None:
+        torch.manual_seed(seed)
+    with _bound(ns, dropin, mixer, wtconv):
+        model = ns.ADNMUNet.VisionMamba(
+            img_size=img_size, depth=[1, 1, 1], refine_depth=[1, 1, 1, 1], refine_headdim=[4, 4, 4, 4],
+            refine_dim=[32, 32, 32, 32] if output_frames > 5 else [32, 32, 16, 16],
+            embed_dim=[32, 64, 128, 256, 512, 1024], headdim=4, channels=input_frames, out_channels=output_frames,
+            ssm_cfg=None, norm_epsilon=1e-6, initializer_cfg=None, kernel=[5, 5, 5], ratio=[2, 2, 2, 2, 2, 2],
+            wt_levels=[3, 2, 1], out_expand=2, InstanceNorm=True)
+    return model
+
+
+def build_block(dim, out_dim, dropin=True, headdim=4, seed=0):
+    """One `Block` as `create_block` builds it (models/ADNMUNet.py:243-292), for the Block-level parity tests."""
+    ns = load_reference()
+    if seed is not None:
+        torch.manual_seed(seed)
+    with _bound(ns, dropin):
+        blk = ns.ADNMUNet.create_block(dim, out_dim, headdim=headdim, norm_epsilon=1e-6, layer_idx=0)
+    return blk
+
+
+def reference_loss():
+    """train_untils.py:43"""
+    return load_reference().loss.enRainfallLoss(omega_t=0.57, alpha=0.25, gamma=0.)
+
+
+def reference_optimizer(model):
+    """train_untils.py:35-42"""
+    return torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-9, weight_decay=1e-2, amsgrad=False)
+
+
+ADAMW = dict(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-9, weight_decay=1e-2)     # train_untils.py:29-42
+CLIP_NORM = 0.025                                                              # train.py:79-94 (norm_max, epochs <= 4)

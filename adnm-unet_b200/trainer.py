@@ -1,0 +1,178 @@
+"""Batch-sharded data-parallel training step for ADNM-UNet: one process per GPU, NCCL all-reduce of the gradients only.
+
+Replaces the reference's `nn.DataParallel` wrap (train.py:99-102) and the tail of its step (train.py:140-145).  Every op
+of the network is per-sample and the loss is sum/numel over the local shard (models/loss.py:64-65), so
+equal shards + gradient averaging reproduce the single-GPU big-batch step exactly.
+
+What is B200-specific here:
+  * the 669 parameter tensors that actually receive a gradient (of 992; the other 307 + the 16 frozen Haar filters are
+    discovered on the first step and left alone - AdamW skips `grad is None`, so no decay is applied to them either)
+    live in ONE flat fp32 buffer, in the order their gradients become ready during backward; so do their gradients and
+    the two Adam moments;
+  * the gradient buffer is cut into buckets; a post-accumulate hook counts a bucket's tensors down and enqueues its
+    NCCL all-reduce (sum over NVLink / NVSwitch) as soon as the last one is written - the reduction of the refiner's
+    gradients overlaps the backward of the decoder and encoder;
+  * global grad-norm, clip (train.py:140), AdamW (train_untils.py:35-42) and zero_grad are two bandwidth-bound passes
+    over the flat buffers in the sm_100a library (include/adnb200.h: adn_sumsq_f32, adn_adamw_flat), with the 1/world
+    average folded in; no `.item()` host synchronisation per step (the reference has two, train.py:141,146).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from adnm_unet_b200 import _lib
+from adnm_unet_b200.refhost import ADAMW, CLIP_NORM
+
+
+def shard_range(global_batch: int, rank: int, world: int):
+    """Contiguous equal shards; the reference loss is sum/numel (models/loss.py:64-65), so shards must be equal-sized."""
+    if global_batch % world:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world}")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+def reference_lr(epoch: int, base_lr=1e-3, warmup_epochs=3, t_max=50, eta_min=5e-7):
+    """train_untils.py:44-46: LinearLR(start 0.01, 3 epochs) then CosineAnnealingLR(T_max 50, eta_min 5e-7); `epoch` counts
+    completed lr_scheduler.step() calls (train.py:187)."""
+    if epoch < warmup_epochs:
+        return base_lr * (0.01 + (1.0 - 0.01) * epoch / warmup_epochs)
+    e = epoch - warmup_epochs
+    return eta_min + (base_lr - eta_min) * (1 + math.cos(math.pi * e / t_max)) / 2
+
+
+def cuda_step_tail(p, g, m, v, ws, step, lr, grad_scale, clip_norm, hp):
+    """clip_grad_norm_ + AdamW.step + zero_grad on the flat buffers, in the sm_100a library.  No CPU implementation."""
+    _lib.require_cuda(p, "flat parameter buffer")
+    lib = _lib.load()
+    n = p.numel()
+    st = _lib.stream_ptr(p.device)
+    with _lib.on_device(p.device):
+        _lib.check(lib.adn_sumsq_f32(_lib.ptr(g), n, _lib.ptr(ws["partial"]), _lib.ptr(ws["sumsq"]), st), "adn_sumsq_f32")
+        _lib.check(lib.adn_adamw_flat(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), n, _lib.ptr(ws["sumsq"]),
+                                      _lib.ptr(ws["norm"]), lr, hp["beta1"], hp["beta2"], hp["eps"], hp["weight_decay"],
+                                      step, grad_scale, clip_norm if clip_norm else 0.0, st), "adn_adamw_flat")
+
+
+class DataParallelTrainer:
+    """model: the (drop-in hosting) network; loss_fn(outputs, targets) -> scalar.
+
+    step(imgs, targets, lr=None) runs forward, loss, backward (bucketed all-reduce overlapped), clip, AdamW, zero_grad and
+    returns the local loss as a device tensor.  The very first step also discovers which parameters are live and builds
+    the flat buffers (so it is slower and its all-reduce is not overlapped)."""
+
+    def __init__(self, model, loss_fn, group=None, clip_norm=CLIP_NORM, adamw=None, bucket_bytes=32 << 20,
+                 autocast_dtype=torch.bfloat16, step_tail=None):
+        self.model, self.loss_fn, self.group = model, loss_fn, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.clip_norm, self.hp = clip_norm, dict(ADAMW if adamw is None else adamw)
+        self.bucket_bytes, self.autocast_dtype = int(bucket_bytes), autocast_dtype
+        self.step_tail = cuda_step_tail if step_tail is None else step_tail
+        self.steps_done = 0
+        self.live = None            # parameters with gradients, in gradient-ready order
+        self.flat_p = self.flat_g = self.flat_m = self.flat_v = None
+        self.buckets = []           # (start, end) element ranges of flat_g
+        self._pending, self._works, self._ready_order = [], [], []
+        self._hooks = []
+
+    # ------------------------------------------------------------------ forward / backward
+    def _forward_loss(self, imgs, targets):
+        dev = imgs.device.type
+        if self.autocast_dtype is not None and dev == "cuda":
+            with torch.autocast("cuda", dtype=self.autocast_dtype):
+                out = self.model(imgs)
+            return self.loss_fn(out.float(), targets)
+        return self.loss_fn(self.model(imgs), targets)
+
+    # ------------------------------------------------------------------ discovery + flattening (first step)
+    def _discover_and_flatten(self, imgs, targets):
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        order = []
+        hooks = [p.register_post_accumulate_grad_hook(lambda p, order=order: order.append(p)) for p in params]
+        for p in params:
+            p.grad = None
+        loss = self._forward_loss(imgs, targets)
+        loss.backward()
+        for h in hooks:
+            h.remove()
+        live = [p for p in order if p.grad is not None]
+        # every rank must agree on the live set (it is structural: same model, any data) - checked, not assumed
+        index = {id(p): i for i, p in enumerate(params)}
+        mask = torch.zeros(len(params), device=imgs.device)
+        mask[[index[id(p)] for p in live]] = 1.0
+        if self.world > 1:
+            total = mask.clone()
+            dist.all_reduce(total, group=self.group)
+            if not torch.equal(total, mask * self.world):
+                raise RuntimeError("data-parallel ranks disagree on which parameters receive gradients")
+        if any(p.dtype != torch.float32 for p in live):
+            raise RuntimeError("the flat trainer keeps fp32 master weights; found a non-fp32 trainable parameter")
+        self.live = live
+        sizes = [(p.numel() + 3) // 4 * 4 for p in live]          # 16-byte aligned slots
+        n = sum(sizes)
+        dev = imgs.device
+        self.flat_p, self.flat_g = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        self.flat_m, self.flat_v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        self.ws = {"partial": torch.zeros(4096, device=dev), "sumsq": torch.zeros(1, device=dev), "norm": torch.zeros(1, device=dev)}
+        self.offsets, off = [], 0
+        with torch.no_grad():
+            for p, sz in zip(live, sizes):
+                k = p.numel()
+                self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
+                self.flat_g[off:off + k].copy_(p.grad.reshape(-1))
+                p.data = self.flat_p[off:off + k].view(p.shape)
+                p.grad = self.flat_g[off:off + k].view(p.shape)
+                self.offsets.append(off)
+                off += sz
+        # buckets: consecutive tensors (in ready order) up to bucket_bytes
+        self.buckets, self.bucket_of, start, count = [], [], 0, 0
+        for i, sz in enumerate(sizes):
+            self.bucket_of.append(len(self.buckets))
+            count += 1
+            end = self.offsets[i] + sz
+            if (end - start) * 4 >= self.bucket_bytes or i == len(sizes) - 1:
+                self.buckets.append((start, end, count))
+                start, count = end, 0
+        self._pending = [c for _, _, c in self.buckets]
+        for i, p in enumerate(live):
+            self._hooks.append(p.register_post_accumulate_grad_hook(lambda p, b=self.bucket_of[i]: self._grad_ready(b)))
+        self._overlap = False
+        return loss
+
+    def _grad_ready(self, b):
+        if not self._overlap:
+            return
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and self.world > 1:
+            s, e, _ = self.buckets[b]
+            self._works.append(dist.all_reduce(self.flat_g[s:e], group=self.group, async_op=True))
+
+    # ------------------------------------------------------------------ one training step (train.py:132-146)
+    def step(self, imgs, targets, lr=None):
+        self.model.train()
+        if self.live is None:
+            loss = self._discover_and_flatten(imgs, targets)
+            if self.world > 1:
+                dist.all_reduce(self.flat_g, group=self.group)
+        else:
+            self._pending = [c for _, _, c in self.buckets]
+            self._works, self._overlap = [], True
+            loss = self._forward_loss(imgs, targets)
+            loss.backward()
+            self._overlap = False
+            if self.world > 1 and any(self._pending):
+                raise RuntimeError("a live parameter received no gradient this step: the live set changed after discovery")
+            for w in self._works:
+                w.wait()            # stream-level wait (NCCL), not a host block
+        self.steps_done += 1
+        self.step_tail(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.ws, self.steps_done,
+                       self.hp["lr"] if lr is None else lr, 1.0 / self.world, self.clip_norm, self.hp)
+        return loss.detach()
+
+    def grad_norm(self):
+        """Unclipped global gradient norm of the last step (device tensor; what train.py:141 logs)."""
+        return self.ws["norm"]
+
+    def n_live_elements(self):
+        return sum(p.numel() for p in self.live) if self.live is not None else 0

@@ -14,6 +14,9 @@ def haar_filters(C, dtype=torch.float):
     return f, f.clone()
 
 
+STATS = {"forward_training": 0, "forward_inference": 0}
+
+
 def _structs(x, k, levels, base_w, base_b, base_s, conv_ws, scale_ws, cls):
     w = cls()
     w.base_conv_w = base_w.data_ptr()
@@ -29,7 +32,7 @@ class _WTConvFunction(torch.autograd.Function):
     """x, k, levels, has_bias, base_w, base_b (or None), base_scale, conv_w[0..levels), scale_w[0..levels)."""
 
     @staticmethod
-    def forward(ctx, x, k, levels, base_w, base_b, base_s, *rest):
+    def forward(ctx, x, k, levels, grad_mode, base_w, base_b, base_s, *rest):
         _lib.require_cuda(x, "x")
         lib = _lib.load()
         x = x.contiguous()
@@ -40,8 +43,9 @@ class _WTConvFunction(torch.autograd.Function):
         wts = _structs(x, k, levels, pw[0], pw[1], pw[2], pw[3:3 + levels], pw[3 + levels:], _lib.WtWeights)
         sv, fw, bw = (_lib.C.c_size_t() for _ in range(3))
         _lib.check(lib.wtconv_workspace_bytes(shape, sv, fw, bw), "wtconv_workspace_bytes")
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = bool(grad_mode) and any(ctx.needs_input_grad)   # needs_input_grad ignores torch.no_grad()
         saved = _lib.scratch(sv.value, x.device) if need_grad else None
+        STATS["forward_training" if need_grad else "forward_inference"] += 1
         ws = _lib.scratch(fw.value, x.device)
         y = torch.empty_like(x)
         with torch.cuda.device(x.device):
@@ -73,15 +77,15 @@ class _WTConvFunction(torch.autograd.Function):
             _lib.check(lib.wtconv_backward(shape, wts, _lib.ptr(x), _lib.ptr(saved), _lib.ptr(dy), _lib.ptr(dx), gst,
                                            _lib.ptr(ws), _lib.stream_ptr()), "wtconv_backward")
         pg = tuple(None if (g is None or not need) else g.to(p.dtype).reshape(p.shape)
-                   for g, p, need in zip(gr, ps, ctx.needs_input_grad[3:]))
-        return (dx if ctx.needs_input_grad[0] else None, None, None) + pg
+                   for g, p, need in zip(gr, ps, ctx.needs_input_grad[4:]))
+        return (dx if ctx.needs_input_grad[0] else None, None, None, None) + pg
 
 
 def wtconv2d(x, params, k, levels):
     """Functional form; `params` maps the reference's state_dict keys to tensors (Haar filter entries ignored)."""
     conv_ws = [params[f"wavelet_convs.{i}.weight"] for i in range(levels)]
     scale_ws = [params[f"wavelet_scale.{i}.weight"] for i in range(levels)]
-    return _WTConvFunction.apply(x, int(k), int(levels), params["base_conv.weight"], params.get("base_conv.bias"),
+    return _WTConvFunction.apply(x, int(k), int(levels), torch.is_grad_enabled(), params["base_conv.weight"], params.get("base_conv.bias"),
                                  params["base_scale.weight"], *conv_ws, *scale_ws)
 
 
@@ -121,8 +125,8 @@ class WTConv2d(nn.Module):
         self.do_stride = None
 
     def forward(self, x):
-        if torch.is_autocast_enabled():
-            x = x.to(torch.get_autocast_gpu_dtype())
-        return _WTConvFunction.apply(x, self.kernel_size, self.wt_levels, self.base_conv.weight, self.base_conv.bias,
+        if torch.is_autocast_enabled("cuda"):
+            x = x.to(torch.get_autocast_dtype("cuda"))
+        return _WTConvFunction.apply(x, self.kernel_size, self.wt_levels, torch.is_grad_enabled(), self.base_conv.weight, self.base_conv.bias,
                                      self.base_scale.weight, *[c.weight for c in self.wavelet_convs],
                                      *[s.weight for s in self.wavelet_scale])

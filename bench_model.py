@@ -1,0 +1,203 @@
+#!/usr/bin/env python
+"""Full-model legs of the benchmark (BASELINE.json configs[0], [2], [3]); imported by bench.py, runnable on its own.
+
+    python bench_model.py train  [--batch 32] [--img 128] [--steps 10] [--warmup 3] [--variant dropin|reference] [--fp32]
+    python bench_model.py infer  [--batch 64] [--img 256] [--steps 5]  [--warmup 2] [--variant dropin|reference]
+    python bench_model.py breakdown [--batch 32] [--img 128]          (torch.profiler kernel table of one training step)
+    torchrun --nproc-per-node N bench_model.py train ...               (batch-sharded DP, one process per GPU)
+
+train : one step = train.py:132-146 of the reference (forward, enRainfallLoss, backward, clip 0.025, AdamW, zero_grad) on a
+        synthetic Shanghai-shaped batch (B, 25, 1, img, img) -> 5 input / 20 target frames, bf16 autocast with fp32 master
+        weights, through adnm_unet_b200.trainer.DataParallelTrainer (bucketed NCCL all-reduce overlapped with backward).
+        seq/s = B * world / step time (CUDA events, max over ranks).
+infer : validate.py:96-106 minus its per-batch .cpu().numpy(): eval + no_grad forward of (B, 5, 1, img, img), then the
+        device threshold counts of the predictions (adn_threshold_counts) - the on-device evaluation path.
+The host network is the UNMODIFIED reference from git-ignored baseline/_ref (adnm_unet_b200.refhost); `--variant reference`
+runs the same step with the reference's own Mamba2 / WTConv2d (eager PyTorch on the B200: the like-for-like GPU baseline).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# full-model roofline per sample (probe numbers): unit-boundary activation traffic fwd+bwd and dense FLOPs
+TRAIN_BYTES_PER_SAMPLE = {128: 445e6, 256: 1.78e9}
+TRAIN_FLOP_PER_SAMPLE = {128: 46.4e9, 256: 188.1e9}
+
+
+def _dist_env():
+    return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def _timed(torch, dist, world, dev, fn, steps):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def train_bench(batch=32, img=128, steps=10, warmup=3, variant="dropin", bf16=True, e2e=True, init_dist=True, peaks=None):
+    """Returns a dict (rank 0) / None (other ranks).  The process group may already be initialised by the caller."""
+    import torch
+    import torch.distributed as dist
+    from adnm_unet_b200 import _lib, refhost
+    from adnm_unet_b200.trainer import DataParallelTrainer
+
+    world, rank, local = _dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized() and init_dist:
+        dist.init_process_group("nccl", device_id=dev)
+    model = refhost.build_adnm_unet(img, dropin=(variant == "dropin"), seed=0).to(dev)     # identical weights on every rank
+    trainer = DataParallelTrainer(model, refhost.reference_loss(), autocast_dtype=torch.bfloat16 if bf16 else None)
+    g = torch.Generator().manual_seed(1000 + rank)                                     # per-rank data shard
+    NSETS = 2
+    host = [torch.rand(batch, 25, 1, img, img, generator=g).pin_memory() for _ in range(NSETS)]
+    resident = [h.to(dev) for h in host]
+    losses = torch.zeros(max(steps, warmup, 3) + 1, device=dev)
+    host_loss = torch.zeros(1).pin_memory()
+
+    def step_resident(i):
+        d = resident[i % NSETS]
+        losses[i] = trainer.step(d[:, :5], d[:, 5:])
+
+    def step_e2e(i):
+        d = host[i % NSETS].to(dev, non_blocking=True)          # H2D of the step's batch from pinned memory
+        loss = trainer.step(d[:, :5], d[:, 5:])
+        host_loss.copy_(loss.reshape(1), non_blocking=True)     # D2H of the step's loss (what train.py:146 reads)
+
+    n0 = _lib.launch_count()
+    for i in range(max(warmup, 3)):
+        step_resident(i)
+    torch.cuda.synchronize()
+    launches_per_step = (_lib.launch_count() - n0) // max(warmup, 3)
+    mem = torch.cuda.max_memory_allocated(dev)
+    ms = _timed(torch, dist, world, dev, step_resident, steps)
+    ms_e2e = _timed(torch, dist, world, dev, step_e2e, steps) if e2e else None
+    final_loss = float(losses[steps - 1])
+    if rank != 0:
+        return None
+    step_ms = ms / steps
+    seq_s = batch * world * steps / (ms * 1e-3)
+    hbm, tf = peaks if peaks else (6524.9, 1400.6)
+    t_star = max(TRAIN_BYTES_PER_SAMPLE.get(img, 0) / (hbm * 1e9), TRAIN_FLOP_PER_SAMPLE.get(img, 0) / (tf * 1e12))
+    res = {
+        "metric": "adnm_unet_train_seq_per_s", "value": seq_s, "unit": "seq/s", "n_gpus": world, "ms_per_step": step_ms,
+        "steps": steps, "warmup": max(warmup, 3), "variant": variant, "dtype": "bf16 autocast, fp32 master weights" if bf16 else "f32",
+        "config": {"workload": f"ADNM-UNet training step (BASELINE configs[2]): B={batch}/GPU, 5->20 frames at {img}x{img}, "
+                               "enRainfallLoss, clip 0.025, AdamW", "global_batch": batch * world, "parallelism": f"dp{world}",
+                   "grad_allreduce": f"{len(trainer.buckets)} fp32 buckets ({trainer.n_live_elements()} live elements of "
+                                     f"{sum(p.numel() for p in model.parameters())}), NCCL sum overlapped with backward" if world > 1 else "none (1 GPU)"},
+        "live_param_tensors": len(trainer.live), "final_loss": final_loss, "grad_norm": float(trainer.grad_norm()),
+        "lib_launches_per_step": launches_per_step, "peak_mem_gb": mem / 2**30,
+        "roofline": {"per_sample_t_star_us": t_star * 1e6, "ceiling_seq_per_s_per_gpu": (1 / t_star) if t_star else None,
+                     "frac": (seq_s / world * t_star) if t_star else None,
+                     "note": "t* = max(445 MB / HBM, 46.4 GFLOP / bf16 sustained) per sample at 128^2 (SURVEY 8(d) full-model row)"},
+    }
+    if ms_e2e is not None:
+        res["e2e"] = {"value": batch * world * steps / (ms_e2e * 1e-3), "unit": "seq/s", "ms_per_step": ms_e2e / steps,
+                      "h2d_bytes_per_step": world * batch * 25 * img * img * 4, "d2h_bytes_per_step": world * 4}
+    return res
+
+
+def infer_bench(batch=64, img=256, steps=5, warmup=2, variant="dropin", bf16=True):
+    import torch
+    from adnm_unet_b200 import refhost, threshold_counts, csi_hss
+    world, rank, local = _dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    model = refhost.build_adnm_unet(img, dropin=(variant == "dropin"), seed=0).to(dev).eval()
+    g = torch.Generator().manual_seed(7 + rank)
+    x = torch.rand(batch, 5, 1, img, img, generator=g).to(dev)
+    tgt = torch.rand(batch, 20, img, img, generator=g).to(dev)
+    tables = []
+
+    def step(i):
+        with torch.no_grad():
+            if bf16:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    out = model(x)
+            else:
+                out = model(x)
+            tables.append(threshold_counts(out.squeeze(2).float(), tgt))
+
+    for i in range(warmup):
+        step(i)
+    tables.clear()
+    ms = _timed(torch, None, 1, dev, step, steps)
+    csi, hss = csi_hss(tables[-1])
+    return {"metric": "adnm_unet_infer_seq_per_s", "value": batch * steps / (ms * 1e-3), "unit": "seq/s", "ms_per_step": ms / steps,
+            "variant": variant, "dtype": "bf16 autocast" if bf16 else "f32",
+            "config": {"workload": f"ADNM-UNet inference (BASELINE configs[3], validate.py:96-106): B={batch}, 5->20 frames at {img}x{img}, "
+                                   "eval + no_grad forward + device threshold counts"},
+            "counts_table": tables[-1].cpu().tolist(), "csi": csi.cpu().tolist(), "hss": hss.cpu().tolist(),
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30}
+
+
+def breakdown(batch=32, img=128, variant="dropin", top=45):
+    """Kernel-time table of one training step (torch.profiler, CUDA activities), grouped by kernel name."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    from adnm_unet_b200 import refhost
+    from adnm_unet_b200.trainer import DataParallelTrainer
+    dev = torch.device("cuda", 0)
+    model = refhost.build_adnm_unet(img, dropin=(variant == "dropin"), seed=0).to(dev)
+    trainer = DataParallelTrainer(model, refhost.reference_loss())
+    d = torch.rand(batch, 25, 1, img, img).to(dev)
+    for _ in range(3):
+        trainer.step(d[:, :5], d[:, 5:])
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        trainer.step(d[:, :5], d[:, 5:])
+        torch.cuda.synchronize()
+    rows = []
+    for e in prof.key_averages():
+        t = getattr(e, "device_time_total", 0) or getattr(e, "cuda_time_total", 0)
+        if e.device_type == torch.autograd.DeviceType.CUDA and t > 0:
+            rows.append((e.key[:110], t, e.count))
+    rows.sort(key=lambda r: -r[1])
+    total = sum(r[1] for r in rows)
+    return {"variant": variant, "total_kernel_ms": total / 1e3, "n_kernel_names": len(rows), "n_launches": sum(r[2] for r in rows),
+            "top": [{"kernel": k, "ms": t / 1e3, "count": c, "share": t / total} for k, t, c in rows[:top]]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("mode", choices=["train", "infer", "breakdown"])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--img", type=int, default=None)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--variant", default="dropin", choices=["dropin", "reference"])
+    ap.add_argument("--fp32", action="store_true")
+    a = ap.parse_args()
+    if a.mode == "train":
+        r = train_bench(a.batch or 32, a.img or 128, a.steps, a.warmup, a.variant, not a.fp32)
+    elif a.mode == "infer":
+        r = infer_bench(a.batch or 64, a.img or 256, a.steps, a.warmup, a.variant, not a.fp32)
+    else:
+        r = breakdown(a.batch or 32, a.img or 128, a.variant)
+    if r is not None:
+        print(json.dumps(r))
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

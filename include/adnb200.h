@@ -10,6 +10,7 @@
  *   adnssd_forward / adnssd_backward   <- models/ADNssd.py:302-462  Mamba2.forward (+ its autograd)
  *   wtconv_forward / wtconv_backward   <- models/WTConv2d.py:100-153 WTConv2d.forward (+ its autograd)
  *   adn_threshold_counts               <- datasets/Shanghai_metrics.py:45-47,105-114 float2int + _cal_frame
+ *   adn_sumsq_f32 / adn_adamw_flat     <- train.py:140-145 clip_grad_norm_ + AdamW.step + zero_grad (train_untils.py:35-42)
  *
  * Conventions:
  *  - every pointer is a DEVICE pointer on the current CUDA device unless stated otherwise;
@@ -143,6 +144,24 @@ int wtconv_backward(const WtShape* s, const WtWeights* w, const void* x, const v
  * `thresholds` is a HOST pointer (n_thresholds <= 8); `table` is a DEVICE int64 buffer, overwritten. */
 int adn_threshold_counts(const float* obs, const float* sim, int64_t n, const int32_t* thresholds,
                          int32_t n_thresholds, float value_scale, int64_t* table, void* stream);
+
+/* ------------------------------------------------------------------ training-step tail ----- */
+
+/* Flat-buffer tail of one data-parallel training step, replacing train.py:140-145 of the reference
+ * (clip_grad_norm_ -> AdamW.step -> zero_grad; AdamW hyper-parameters of train_untils.py:35-42) for the batch-sharded
+ * trainer: all live parameters / gradients / moments are contiguous float32 buffers of n elements.
+ *
+ * adn_sumsq_f32: out[0] = sum(x[i]^2), deterministic (fixed reduction tree, no atomics) so that every rank derives the
+ *   same clip factor from the same all-reduced gradients.  partial_ws: adn_sumsq_workspace_floats() floats. */
+int adn_sumsq_workspace_floats(void);
+int adn_sumsq_f32(const float* x, int64_t n, float* partial_ws, float* out, void* stream);
+/* One pass: g_eff = g * grad_scale * min(1, max_norm / (sqrt(*sumsq) * grad_scale + 1e-6))  (max_norm <= 0: no clip;
+ *   grad_scale = 1 / world when the buffer holds the SUM over ranks), decoupled weight decay, Adam moments with bias
+ *   correction for step number `step` (>= 1), parameter update, and g <- 0.  If norm_out != NULL it receives the
+ *   unclipped global norm sqrt(*sumsq) * grad_scale (device float; what train.py:141 reads back with .item()). */
+int adn_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const float* sumsq, float* norm_out, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                   float max_norm, void* stream);
 
 /* ------------------------------------------------------------------ misc ------------------- */
 

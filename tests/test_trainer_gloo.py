@@ -1,0 +1,130 @@
+"""Host logic of the batch-sharded trainer (adnm_unet_b200.trainer) on CPU: world-size-2 gloo.
+
+Two ranks, each with half of the global batch, must end every step with the SAME parameters as one process running
+`clip_grad_norm_` + `torch.optim.AdamW` + `zero_grad` on the whole batch (train.py:132-146 semantics).  The per-step tail
+is injected as a plain-torch restatement (the product default is the CUDA library and refuses CPU tensors); what is under
+test is discovery of the live parameter set, flattening, bucketing, the overlapped all-reduce hooks and the 1/world scale.
+"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class Net(nn.Module):
+    """Small network with the two features that matter: a parameter that never gets a gradient and a shared one."""
+
+    def __init__(self):
+        super().__init__()
+        self.a = nn.Linear(6, 16)
+        self.b = nn.Linear(16, 16)
+        self.c = nn.Linear(16, 3)
+        self.unused = nn.Parameter(torch.ones(5))
+        self.beta = nn.Parameter(torch.tensor(0.7))
+
+    def forward(self, x):
+        h = torch.tanh(self.a(x))
+        h = self.beta * h + self.beta * torch.tanh(self.b(h))
+        return self.c(h)
+
+
+def torch_tail(p, g, m, v, ws, step, lr, grad_scale, clip_norm, hp):
+    """Plain-torch restatement of adn_sumsq_f32 + adn_adamw_flat (csrc/optim.cu)."""
+    with torch.no_grad():
+        norm = g.norm() * grad_scale
+        coef = grad_scale * (min(1.0, clip_norm / (norm.item() + 1e-6)) if clip_norm else 1.0)
+        ge = g * coef
+        m.mul_(hp["beta1"]).add_(ge, alpha=1 - hp["beta1"])
+        v.mul_(hp["beta2"]).addcmul_(ge, ge, value=1 - hp["beta2"])
+        p.mul_(1 - lr * hp["weight_decay"])
+        denom = v.sqrt() / (1 - hp["beta2"] ** step) ** 0.5 + hp["eps"]
+        p.addcdiv_(m, denom, value=-lr / (1 - hp["beta1"] ** step))
+        g.zero_()
+        ws["norm"].fill_(norm)
+
+
+def _loss(out, tgt):
+    return (out - tgt).abs().sum() / tgt.numel()
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from adnm_unet_b200.trainer import DataParallelTrainer, shard_range
+    from adnm_unet_b200.refhost import ADAMW
+    torch.manual_seed(0)
+    net = Net()
+    ref = Net()
+    ref.load_state_dict(net.state_dict())
+    hp = dict(ADAMW)
+    tr = DataParallelTrainer(net, _loss, clip_norm=0.05, adamw=hp, bucket_bytes=512, autocast_dtype=None,
+                             step_tail=torch_tail)
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(3, 8, 6, generator=g, dtype=torch.float32)
+    Y = torch.randn(3, 8, 3, generator=g, dtype=torch.float32)
+    opt = torch.optim.AdamW(ref.parameters(), lr=hp["lr"], betas=(hp["beta1"], hp["beta2"]), eps=hp["eps"],
+                            weight_decay=hp["weight_decay"])
+    a, b = shard_range(8, rank, world)
+    norms = []
+    for s in range(3):
+        tr.step(X[s, a:b], Y[s, a:b])
+        norms.append(float(tr.grad_norm()))
+        _loss(ref(X[s]), Y[s]).backward()
+        rn = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05)
+        opt.step()
+        opt.zero_grad()
+        norms[-1] = (norms[-1], float(rn))
+    err = max(float((p - q).abs().max()) for p, q in zip(net.parameters(), ref.parameters()))
+    if rank == 0:
+        ret["err"], ret["norms"] = err, norms
+        ret["unused_untouched"] = bool(torch.equal(net.unused, torch.ones(5))) and net.unused.grad is None
+        ret["buckets"], ret["live"] = len(tr.buckets), len(tr.live)
+    dist.destroy_process_group()
+
+
+def test_two_ranks_match_single_process_big_batch_training():
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret["err"] < 2e-6, ret["err"]
+    for mine, theirs in ret["norms"]:
+        assert abs(mine - theirs) / theirs < 1e-5
+    assert ret["unused_untouched"] and ret["live"] == 7 and ret["buckets"] >= 2
+
+
+def test_reference_lr_schedule_matches_torch_sequential_lr():
+    """train_untils.py:44-46"""
+    from adnm_unet_b200.trainer import reference_lr
+    p = [nn.Parameter(torch.zeros(1))]
+    opt = torch.optim.AdamW(p, lr=1e-3)
+    w = torch.optim.lr_scheduler.LinearLR(opt, start_factor=0.01, total_iters=3)
+    c = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=50, eta_min=5e-7)
+    sch = torch.optim.lr_scheduler.SequentialLR(opt, [w, c], [3])
+    for epoch in range(12):
+        assert abs(opt.param_groups[0]["lr"] - reference_lr(epoch)) < 1e-9, epoch
+        opt.step()
+        sch.step()
+
+
+def test_grad_allreducer_keeps_aliased_grads():
+    """a second call with the previous views still installed must not copy a slice onto itself."""
+    from adnm_unet_b200.dp import GradAllReducer
+    ps = [nn.Parameter(torch.randn(4, 3)), nn.Parameter(torch.randn(5))]
+    for p in ps:
+        p.grad = torch.ones_like(p)
+    red = GradAllReducer(ps)
+    red()
+    for p in ps:
+        p.grad.add_(1.0)          # accumulate into the views (set_to_none=False style)
+    red()
+    assert all(bool((p.grad == 2).all()) for p in ps)
