@@ -70,6 +70,11 @@ EXPORTS = {
     "adn_cta_times_read": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "adn_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "adn_selftest_umma_shift": (C.c_int, [C.c_int] * 6 + [C.c_void_p] * 5),
+    "adnssd_kernel_family": (C.c_int, [C.POINTER(AdnShape)]),
+    "adn_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "adn_selftest_gemm": (C.c_int, [C.c_int] * 6 + [C.c_void_p, C.c_longlong, C.c_longlong] * 4 +
+                          [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                           C.c_void_p, C.c_void_p]),
     "adn_bench_umma": (C.c_int, [C.c_int] * 6 + [C.c_void_p] * 2),
 }
 

@@ -100,6 +100,23 @@ __device__ __forceinline__ float silu_gradf_(float x) {
 // torch.nn.functional.softplus(beta=1, threshold=20)  (models/ADNssd.py:318)
 __device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : log1pf(__expf(x)); }
 
+// Storage-type dispatched math: the fp32 instantiation of the generic kernels IS the 1e-4 check mode, so it uses the
+// accurate expf (sums that cancel - scalar gates, per-head decay gradients - amplify the ~1e-6 error of __expf a hundred-
+// fold); the bf16 instantiations keep the fast intrinsics (their error is far below the bf16 rounding of the tensors).
+template <typename T> struct Math {
+  static __device__ __forceinline__ float exp(float x) { return __expf(x); }
+};
+template <> struct Math<float> {
+  static __device__ __forceinline__ float exp(float x) { return expf(x); }
+};
+template <typename T> __device__ __forceinline__ float sigmoid_t(float x) { return 1.f / (1.f + Math<T>::exp(-x)); }
+template <typename T> __device__ __forceinline__ float silu_t(float x) { return x * sigmoid_t<T>(x); }
+template <typename T> __device__ __forceinline__ float silu_grad_t(float x) {
+  const float s = sigmoid_t<T>(x);
+  return s * (1.f + x * (1.f - s));
+}
+template <typename T> __device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(Math<T>::exp(x)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

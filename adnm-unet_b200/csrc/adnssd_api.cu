@@ -7,6 +7,7 @@
 #include "adn_common.cuh"
 #include "adnssd_generic.cuh"
 #include "adnssd_sm100.cuh"
+#include "adnssd_wide.cuh"
 
 namespace adn {
 
@@ -30,8 +31,8 @@ int sm_count() {
   return n;
 }
 
-const EnvCfg& env() {
-  static const EnvCfg cfg = [] {
+static EnvCfg& env_mut() {
+  static EnvCfg cfg = [] {
     auto flag = [](const char* name, bool dflt) { const char* e = getenv(name); return e ? e[0] != '0' : dflt; };
     auto num = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; };
     EnvCfg c;
@@ -45,6 +46,7 @@ const EnvCfg& env() {
   }();
   return cfg;
 }
+const EnvCfg& env() { return env_mut(); }
 
 // ---- diagnostics: launch counter + optional per-launch CUDA-event timing
 constexpr int PROF_CAP = 4096;
@@ -150,6 +152,7 @@ int adnssd_workspace_bytes(const AdnShape* s, size_t* saved_bytes, size_t* fwd_w
     fw = fw > fw2 ? fw : fw2;
     bw = bw > bw2 ? bw : bw2;
     sv += sm100_saved_extra_bytes(d);
+    if (!sm100_supported(d) && wide::supported(d)) wide::workspace_bytes(d, &sv, &fw, &bw);
   }
   if (saved_bytes) *saved_bytes = sv;
   if (fwd_ws) *fwd_ws = fw;
@@ -168,6 +171,7 @@ int adnssd_forward(const AdnShape* s, const AdnWeights* w, const void* u, void* 
   cudaStream_t st = (cudaStream_t)stream;
   if (s->dtype == ADN_F32) return generic_forward<float>(d, *w, (const float*)u, (float*)out, saved, workspace, st);
   if (sm100_supported(d)) return sm100_forward(d, *w, (const bf16*)u, (bf16*)out, saved, workspace, st);
+  if (wide::supported(d)) return wide::forward(d, *w, (const bf16*)u, (bf16*)out, saved, workspace, st);
   return generic_forward<bf16>(d, *w, (const bf16*)u, (bf16*)out, saved, workspace, st);
 }
 
@@ -185,7 +189,51 @@ int adnssd_backward(const AdnShape* s, const AdnWeights* w, const void* u, const
     return generic_backward<float>(d, *w, (const float*)u, saved, (const float*)dout, (float*)du, *g, workspace, st);
   if (sm100_supported(d))
     return sm100_backward(d, *w, (const bf16*)u, saved, (const bf16*)dout, (bf16*)du, *g, workspace, st);
+  if (wide::supported(d))
+    return wide::backward(d, *w, (const bf16*)u, saved, (const bf16*)dout, (bf16*)du, *g, workspace, st);
   return generic_backward<bf16>(d, *w, (const bf16*)u, saved, (const bf16*)dout, (bf16*)du, *g, workspace, st);
+}
+
+
+// Diagnostics: flip a kernel-family switch between WHOLE forward + backward passes (the ADN_* environment variables are
+// only read once, at first use).  Not thread-safe; tests and profiling scripts only.
+int adn_set_option(const char* name, int value) {
+  ADN_REQUIRE(name != nullptr, ADN_ERR_NULL, "adn_set_option: NULL name");
+  EnvCfg& c = env_mut();
+  if (!strcmp(name, "rowconv")) c.rowconv = value != 0;
+  else if (!strcmp(name, "row_wide")) c.row_wide = value != 0;
+  else if (!strcmp(name, "bwd_ws")) c.bwd_ws = value != 0;
+  else if (!strcmp(name, "wide")) c.wide = value != 0;
+  else if (!strcmp(name, "rows_per_cta")) c.rows_per_cta = value;
+  else if (!strcmp(name, "du_dbg")) c.du_dbg = value;
+  else { set_error("adn_set_option: unknown option '%s'", name); return ADN_ERR_SHAPE; }
+  return ADN_OK;
+}
+
+// Which kernel family serves a shape: 0 generic CUDA-core (fp32 check mode, odd shapes), 1 tile kernels, 2 row kernels
+// (both d_model 32, tcgen05), 3 wide path (tcgen05 GEMMs + bf16 bandwidth kernels).  For the sweep / tests.
+int adnssd_kernel_family(const AdnShape* s) {
+  if (validate(s)) return -1;
+  MixerDims d = make_dims(*s);
+  if (s->dtype == ADN_F32) return 0;
+  if (sm100_supported(d)) return sm100_rowconv(d) ? 2 : 1;
+  return wide::supported(d) ? 3 : 0;
+}
+
+// Standalone entry to the general tcgen05 GEMM (tests/test_tcgemm_gpu.py): C[b] = alpha * (A0 B0 [+ A1 B1]).
+// a_mn / b_mn: 0 = operand stored [rows][K], 1 = stored [K][cols]; c_mode 0 bf16, 1 fp32, 2 fp32 atomic (C pre-zeroed).
+int adn_selftest_gemm(int M, int N, int K0, int K1, int a_mn, int b_mn, const void* A0, long long lda0, long long a_bs0,
+                      const void* B0, long long ldb0, long long b_bs0, const void* A1, long long lda1, long long a_bs1,
+                      const void* B1, long long ldb1, long long b_bs1, void* C, long long ldc, long long c_bs, int c_mode,
+                      int batches, int splitk, const float* alpha, int parity_mask, int* status, void* stream) {
+  tcg::Op a0{(const bf16*)A0, lda0, a_bs0, a_mn}, b0{(const bf16*)B0, ldb0, b_bs0, b_mn};
+  tcg::Op a1{(const bf16*)A1, lda1, a_bs1, a_mn}, b1{(const bf16*)B1, ldb1, b_bs1, b_mn};
+  if (K1 == 0) { a1 = tcg::NOOP; b1 = tcg::NOOP; a1.mn = a_mn; b1.mn = b_mn; }
+  int rc = tcg::gemm((cudaStream_t)stream, "tcgemm_selftest", M, N, K0, a0, b0, K1, a1, b1, tcg::Out{C, ldc, c_bs, c_mode}, batches,
+                     splitk, alpha, parity_mask, status);
+  if (rc) return rc;
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
 }
 
 }  // extern "C"

@@ -15,7 +15,8 @@ struct ConvWeightPtrs {
   const float *c13x1, *c31x1, *c13x2, *c31x2, *c13bc1, *c31bc1, *c13bc2, *c31bc2, *c2d, *c2dz;
 };
 
-__device__ __forceinline__ void assemble_conv_channel(const ConvWeightPtrs& w, float* __restrict__ Kc, int Di, int cc) {
+// out9[0..8] = the 3x3 kernel of channel cc
+__device__ __forceinline__ void assemble_conv_channel(const ConvWeightPtrs& w, float* __restrict__ out9, int Di, int cc) {
   float k[9];
   if (cc < Di) {
 #pragma unroll
@@ -43,12 +44,12 @@ __device__ __forceinline__ void assemble_conv_channel(const ConvWeightPtrs& w, f
     }
   }
 #pragma unroll
-  for (int t = 0; t < 9; ++t) Kc[cc * 9 + t] = k[t];
+  for (int t = 0; t < 9; ++t) out9[t] = k[t];
 }
 
 static __global__ void k_assemble_conv(ConvWeightPtrs w, float* __restrict__ Kc, int Di, int CC) {
   int cc = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cc < CC) assemble_conv_channel(w, Kc, Di, cc);
+  if (cc < CC) assemble_conv_channel(w, Kc + cc * 9, Di, cc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,7 +262,7 @@ k_conv_fwd(const T* __restrict__ raw, long long ldr, const float* __restrict__ K
     long long off = (((long long)b * H + y) * W + x) * CC + c0;
     if (pre) st4(pre + off, a);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = siluf_(a[i]);
+    for (int i = 0; i < 4; ++i) o[i] = silu_t<T>(a[i]);
     st4(act + off, o);
 #pragma unroll
     for (int s = 0; s < 3; ++s)
@@ -286,7 +287,7 @@ __device__ __forceinline__ void load_dpre_row3(const TW* __restrict__ dact, cons
       ld4(dact + off, g);
       ld4(pre + off, p);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) r[s][i] = g[i] * silu_gradf_(p[i]);
+      for (int i = 0; i < 4; ++i) r[s][i] = g[i] * silu_grad_t<T>(p[i]);
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) r[s][i] = 0.f;
@@ -377,7 +378,7 @@ __global__ void k_decay_wx(const T* __restrict__ raw, long long ldr, const T* __
   if (idx >= Ttok * nh) return;
   long long t = idx / nh;
   int h = (int)(idx % nh);
-  float w = softplusf_(ldf(raw + t * ldr + CC + h) + dt_bias[h]) * __expf(A_log[h]);
+  float w = softplus_t<T>(ldf(raw + t * ldr + CC + h) + dt_bias[h]) * Math<T>::exp(A_log[h]);
   if (wdec) wdec[idx] = w;
   int cb = 2 * P * (h >> 1) + (h & 1);
   for (int i = 0; i < P; ++i) {
@@ -492,7 +493,7 @@ k_bwd_heads(const T* __restrict__ raw, long long ldr, const T* __restrict__ act,
   const int h = blockIdx.x * 32 + threadIdx.x;
   float aD = 0.f, aA = 0.f, aB = 0.f;
   if (h < nh) {
-    const float Dh = Dp[h], eA = __expf(A_log[h]), bias = dt_bias[h];
+    const float Dh = Dp[h], eA = Math<T>::exp(A_log[h]), bias = dt_bias[h];
     const int cb = 2 * P * (h >> 1) + (h & 1);
     long long t0 = ((long long)blockIdx.y * 8 + threadIdx.y) * tokens_per_thread;
     for (long long t = t0; t < min(Ttok, t0 + tokens_per_thread); ++t) {
@@ -506,7 +507,7 @@ k_bwd_heads(const T* __restrict__ raw, long long ldr, const T* __restrict__ act,
         dw += x * G;
         aD += dy * x;
       }
-      float ddt = dw * eA * sigmoidf_(ldf(raw + t * ldr + CC + h) + bias);
+      float ddt = dw * eA * sigmoid_t<T>(ldf(raw + t * ldr + CC + h) + bias);
       stf(draw + t * ldr + CC + h, ddt);
       aA += dw * w;
       aB += ddt;

@@ -1496,7 +1496,7 @@ __global__ void k_prep(ConvWeightPtrs cw, float* __restrict__ Kc, int Di, int CC
     wt_hi[i] = h;
     wt_lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
   }
-  if (i < CC) assemble_conv_channel(cw, Kc, Di, i);
+  if (i < CC) assemble_conv_channel(cw, Kc + i * 9, Di, i);
   if (i < n_in) {
     const float v = win[i];
     const bf16 h = __float2bfloat16_rn(v);
@@ -1789,6 +1789,8 @@ static bool rowconv_supported(const MixerDims& d) {
   return d.D == 32 && d.Di == 64 && d.P == 4 && d.GN == 32 && d.dip == 208 && d.ldr == 208 &&
          (d.W == 128 || (wide && d.W % 128 == 0 && d.W <= 1024));
 }
+
+bool sm100_rowconv(const MixerDims& d) { return rowconv_supported(d); }
 
 bool sm100_supported(const MixerDims& d) {
   // instantiated tile shapes: d_model 32 (d_inner 64), headdim 4, ngroups*d_state in {32, 64, 128} (d_state 16, 32, 64)

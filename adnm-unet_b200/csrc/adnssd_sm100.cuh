@@ -4,6 +4,7 @@
 
 namespace adn {
 bool sm100_supported(const MixerDims& d);
+bool sm100_rowconv(const MixerDims& d);      // subset served by the conv-as-GEMM row kernels
 void sm100_workspace_bytes(const MixerDims& d, size_t* fwd, size_t* bwd);
 size_t sm100_saved_extra_bytes(const MixerDims& d);
 int sm100_forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* out, void* saved, void* ws,

@@ -1,0 +1,720 @@
+// "Wide" ADN-SSD mixer path (bf16): every shape the 32-wide row / tile kernels do not cover - the six encoder / decoder
+// mixers of ADNM-UNet (d_model 128 ... 1024, token grids 4 x 4 ... 32 x 32) and the d_state / d_model sweep corner.
+// All eleven contractions of the forward + backward run on the tensor cores through the general tcgen05 GEMM of
+// tcgemm.cuh (row-major operands in either orientation, two accumulating segments, per-sample batches, split-K); the
+// stages between them are bandwidth-bound bf16 kernels.  Stage split = oracle/adnssd_oracle.py (mixer_forward / _backward):
+//
+//   forward   raw  = u W_in^T                                   GEMM   (models/ADNssd.py:309)
+//             act  = SiLU(dwconv3x3(raw)), w, wx = w * xc        k_wconv_fwd                        (:329-390, :267-270)
+//             S'^T = mask . (wx^T Bc)            per sample      GEMM (MN-major x MN-major, K = L)  (:280)
+//             y    = Cc S' (hi + lo)             per sample      GEMM (two segments)                (:281)
+//             yn   = LayerNorm(y + D xc)                         k_wln_fwd                          (:283, :456)
+//             out  = alpha1 (yn W_y^T + zc W_z^T)                GEMM (two segments)                (:459-461)
+//   backward  g = dout W_out; y again; LayerNorm backward; dW_out = dout^T [yn | zc]; dS'^T = mask . (dy^T Cc);
+//             dCc = dy S'^T; G = Bc dS'; per-head dx / ddt / sums; dBc = wx dS'^T (each producer multiplies by SiLU'(pre), so
+//             dact holds the gradient w.r.t. the conv output's input); conv backward; du = draw W_in;
+//             dW_in = draw^T u; finalize (rank-1 chain rule of the 3x1 / 1x3 pairs).
+// bf16 operands, fp32 accumulation; fp32 where a difference of large numbers follows (y before LayerNorm, G, the states
+// as hi + lo pairs, every parameter-gradient accumulator).
+#pragma once
+#include "adn_common.cuh"
+#include "adnssd_generic.cuh"
+#include "tcgemm.cuh"
+
+namespace adn {
+namespace wide {
+using namespace adn::sm100;
+
+// ---------------------------------------------------------------- small kernels
+// One launch of per-call weight preparation: fp32 -> bf16 copies of W_in and W_out (tensor-core operands), the per-channel
+// expansion of the D skip (Dch[c] = D[hd(c)]: no integer division in the per-token kernels) and the per-channel 3x3 conv
+// kernels assembled from the ten conv weight tensors, stored tap-major Kt[9][CC] (one coalesced float4 per tap and thread).
+__global__ void k_prep_wide(const float* __restrict__ a, bf16* __restrict__ oa, long long na, const float* __restrict__ b,
+                            bf16* __restrict__ ob, long long nb, const float* __restrict__ Dp, float* __restrict__ Dch, int Di, int P,
+                            ConvWeightPtrs cw, float* __restrict__ Kt, int CC) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb + Di + CC; i += stride) {
+    if (i < na) oa[i] = __float2bfloat16_rn(a[i]);
+    else if (i < na + nb) ob[i - na] = __float2bfloat16_rn(b[i - na]);
+    else if (i < na + nb + Di) Dch[i - na - nb] = Dp[head_of_channel((int)(i - na - nb), P)];
+    else {
+      const int cc = (int)(i - na - nb - Di);
+      float k[9];
+      assemble_conv_channel(cw, k, Di, cc);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) Kt[t * CC + cc] = k[t];
+    }
+  }
+}
+
+// fp32 state -> bf16 hi + lo pair (hi = rn(s), lo = rn(s - hi)): the tensor cores then see the state to ~16 mantissa bits
+__global__ void k_split_hilo(const float* __restrict__ s, bf16* __restrict__ hi, bf16* __restrict__ lo, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = s[i];
+    const bf16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) { unpack8(*reinterpret_cast<const uint4*>(p), v); }
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) { *reinterpret_cast<uint4*>(p) = pack8(v); }
+
+// decay weight of (token, head) from the raw dt column: w = softplus(dt + bias) * exp(A_log), and sigmoid(dt + bias)
+__device__ __forceinline__ void decay_of(float v, float eA, float& w, float& sig) {
+  if (v > 20.f) { w = v * eA; sig = 1.f; return; }
+  const float e = __expf(v);
+  w = log1pf(e) * eA;
+  sig = e / (1.f + e);
+}
+
+// ---------------------------------------------------------------- depthwise 3x3 + SiLU (+ decay weighting), channels-last
+// thread = (4 channels, one column x, TWO rows y, y+1); the 32 lanes of a warp cover 128 consecutive channels (256 contiguous
+// bytes per token and tap).  ncu on the first versions (profiles/r02_wide_kernels.md): 890 instructions per thread for 8
+// outputs at 10 % of the DRAM throughput - the stage is bound by instruction issue (per-tap 64-bit address arithmetic and
+// bounds predicates), not by memory.  Hence: a zero-filled halo tile in shared memory (cp.async), compile-time offsets in
+// the compute phase, packed fp32 pair arithmetic (FFMA2: one instruction per two channels), sigmoid through tanh.approx
+// (one MUFU), shifts instead of the head-index division for power-of-two headdim, __logf instead of log1pf.
+typedef unsigned long long f32x2;      // two fp32 lanes in one 64-bit register pair: lane 0 = even channel
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// bf16x2 word -> fp32 pair (exact: a bf16 is the upper half of an fp32)
+__device__ __forceinline__ f32x2 bf2_to_f2(uint32_t w) { return ((f32x2)(w & 0xffff0000u) << 32) | (f32x2)(w << 16); }
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }   // |err| < 3e-4: below bf16 rounding
+__device__ __forceinline__ float silu_grad_fast(float x) { const float s = sigmoid_fast(x); return s * fmaf(x, 1.f - s, 1.f); }
+
+__device__ __forceinline__ void load_taps(const float* __restrict__ Kt, int CC, int c0, f32x2 (&k)[9][2]) {
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 v = *reinterpret_cast<const float4*>(Kt + t * CC + c0);
+    k[t][0] = pk2(v.x, v.y);
+    k[t][1] = pk2(v.z, v.w);
+  }
+}
+__device__ __forceinline__ void store4(bf16* p, float a, float b, float c, float d) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(a, b), pack_bf16(c, d));
+}
+
+// Halo tile in shared memory: (TY + 2) x (TX + 2) tokens x 128 channels (256 bytes per token) around the block's TY x TX
+// output tile, filled with 16-byte cp.async copies that zero-fill outside the image (and past the last channel).  The
+// compute phase then addresses it with compile-time offsets from one per-thread base: no per-tap address arithmetic, no
+// bounds predicates.
+constexpr int TY = 8, TX = 8, HT = (TY + 2) * (TX + 2), HALO_B = HT * 256;
+__device__ __forceinline__ void cp16z(uint32_t sdst, const void* gsrc, int nbytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(nbytes) : "memory");
+}
+// src: (sample, row 0, col 0, channel block) of a channels-last tensor with row pitch ld; tile origin (y0, x0)
+__device__ __forceinline__ void stage_halo(uint32_t stile, const bf16* __restrict__ src, int ld, int H, int W, int y0, int x0,
+                                           int ch_valid, int tid) {
+  for (int id = tid; id < HT * 16; id += 256) {
+    const int pos = id >> 4, piece = id & 15;
+    const int ty = pos / (TX + 2), tx = pos - ty * (TX + 2);
+    const int yy = y0 - 1 + ty, xx = x0 - 1 + tx;
+    const bool ok = (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W && piece * 8 < ch_valid;
+    const bf16* g = ok ? src + ((long long)yy * W + xx) * ld + piece * 8 : src;
+    cp16z(stile + id * 16, g, ok ? 16 : 0);
+  }
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void lds_vec(const uint8_t* p, f32x2 (&v)[2]) {
+  const uint2 w = *reinterpret_cast<const uint2*>(p);
+  v[0] = bf2_to_f2(w.x);
+  v[1] = bf2_to_f2(w.y);
+}
+
+// Stages (2) + (3) in one pass: pre = dwconv3x3(raw[:, :CC]; K), act = SiLU(pre), and for the x channels wx = w * xc.
+// block (32 lanes = 128 channels, TX columns); each thread walks the TY rows of the tile with a 3 x 3 register window.
+// grid (ceil(CC/128), ceil(W/TX), B * ceil(H/TY)).  pshift = log2(headdim) for power-of-two headdim >= 2, else -1.
+__global__ void __launch_bounds__(256)
+k_wconv_fwd(const bf16* __restrict__ raw, int ldr, const float* __restrict__ Kt, const float* __restrict__ dt_bias,
+            const float* __restrict__ A_log, bf16* __restrict__ pre, bf16* __restrict__ act, bf16* __restrict__ wx, int H, int W,
+            int CC, int Di, int P, int pshift) {
+  __shared__ __align__(16) uint8_t tile[HALO_B];
+  const int cblk = blockIdx.x * 128, c0 = cblk + threadIdx.x * 4;
+  const int x0 = blockIdx.y * TX, x = x0 + threadIdx.y;
+  const int ybl = (H + TY - 1) / TY;
+  const int b = blockIdx.z / ybl, y0 = (blockIdx.z - b * ybl) * TY;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const long long tok0 = (long long)b * H * W;
+  stage_halo(smem_u32(tile), raw + tok0 * ldr + cblk, ldr, H, W, y0, x0, CC - cblk, tid);
+  const bool live = c0 < CC && x < W;
+  f32x2 k[9][2];
+  const bool is_x = c0 >= Di && c0 < 2 * Di;
+  int hd[4] = {0, 0, 0, 0};
+  float eA[4], bias[4];
+  if (live) {
+    load_taps(Kt, CC, c0, k);
+    if (is_x) {
+      const int cx = c0 - Di;
+      if (pshift >= 1) {
+        hd[0] = 2 * ((cx >> 1) >> pshift); hd[1] = hd[0] + 1; hd[2] = hd[0]; hd[3] = hd[1];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hd[i] = head_of_channel(cx + i, P);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { eA[i] = __expf(A_log[hd[i]]); bias[i] = dt_bias[hd[i]]; }
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (!live) return;
+  const uint8_t* base = tile + threadIdx.y * 256 + threadIdx.x * 8;      // halo (row 0, col tx) of this thread's channels
+  f32x2 win[3][3][2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) lds_vec(base + (r * (TX + 2) + s) * 256, win[r][s]);
+#pragma unroll
+  for (int j = 0; j < TY; ++j) {
+#pragma unroll
+    for (int s = 0; s < 3; ++s) lds_vec(base + ((j + 2) * (TX + 2) + s) * 256, win[(j + 2) % 3][s]);
+    if (y0 + j < H) {
+      f32x2 a0 = 0ull, a1 = 0ull;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          a0 = ffma2(k[r * 3 + s][0], win[(j + r) % 3][s][0], a0);
+          a1 = ffma2(k[r * 3 + s][1], win[(j + r) % 3][s][1], a1);
+        }
+      float a[4], o[4];
+      upk2(a0, a[0], a[1]);
+      upk2(a1, a[2], a[3]);
+      const long long tok = tok0 + (long long)(y0 + j) * W + x;
+      if (pre) store4(pre + tok * CC + c0, a[0], a[1], a[2], a[3]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = a[i] * sigmoid_fast(a[i]);
+      store4(act + tok * CC + c0, o[0], o[1], o[2], o[3]);
+      if (is_x) {
+        float wv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i >= 2 && hd[i] == hd[i - 2]) { wv[i] = wv[i - 2]; continue; }
+          const float v = ldf(raw + tok * ldr + CC + hd[i]) + bias[i];
+          wv[i] = (v > 20.f ? v : __logf(1.f + __expf(v))) * eA[i];
+        }
+        store4(wx + tok * Di + (c0 - Di), o[0] * wv[0], o[1] * wv[1], o[2] * wv[2], o[3] * wv[3]);
+      }
+    }
+  }
+}
+
+// conv backward on dpre (the producers already multiplied by SiLU'(pre)): draw[:, :CC] = conv^T(dpre) and
+// dK[c][a][b] += raw[y, x, c] * dpre[y-a+1, x-b+1, c].  Same tiling as k_wconv_fwd (halo tile of dpre in shared memory);
+// blockIdx.z strides over the (sample, row block) work items so that a thread keeps its 36 dK partial sums in registers
+// across the whole pass: one shared-memory reduction and 1152 global atomics per BLOCK at the end (the generic kernel's ~5 M
+// contended atomics were 3.6 ms at d_model 128).
+__global__ void __launch_bounds__(256, 2)
+k_wconv_bwd(const bf16* __restrict__ dpre, const bf16* __restrict__ raw, int ldr, const float* __restrict__ Kt,
+            bf16* __restrict__ draw, float* __restrict__ dK, int Bn, int H, int W, int CC) {
+  __shared__ __align__(16) uint8_t tile[HALO_B];
+  __shared__ float red[32][37];
+  const int cblk = blockIdx.x * 128, c0 = cblk + threadIdx.x * 4;
+  const int x0 = blockIdx.y * TX, x = x0 + threadIdx.y;
+  const int ybl = (H + TY - 1) / TY;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int i = tid; i < 32 * 37; i += 256) (&red[0][0])[i] = 0.f;
+  const bool live = (c0 < CC && x < W);
+  f32x2 dk[9][2], k[9][2];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) dk[t][0] = dk[t][1] = k[t][0] = k[t][1] = 0ull;
+  if (live) load_taps(Kt, CC, c0, k);
+  const uint8_t* base = tile + threadIdx.y * 256 + threadIdx.x * 8;
+  for (int z = blockIdx.z; z < Bn * ybl; z += gridDim.z) {
+    const int b = z / ybl, y0 = (z - b * ybl) * TY;
+    const long long boff = (long long)b * H * W;
+    __syncthreads();                       // every thread is done with the previous tile
+    stage_halo(smem_u32(tile), dpre + boff * CC + cblk, CC, H, W, y0, x0, CC - cblk, tid);
+    cp_async_wait_all();
+    __syncthreads();
+    if (!live) continue;
+    f32x2 win[3][3][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) lds_vec(base + (r * (TX + 2) + s) * 256, win[r][s]);
+#pragma unroll
+    for (int j = 0; j < TY; ++j) {
+#pragma unroll
+      for (int s = 0; s < 3; ++s) lds_vec(base + ((j + 2) * (TX + 2) + s) * 256, win[(j + 2) % 3][s]);
+      if (y0 + j < H) {
+        const long long tok = boff + (long long)(y0 + j) * W + x;
+        const uint2 rv = *reinterpret_cast<const uint2*>(raw + tok * ldr + c0);
+        const f32x2 rc0 = bf2_to_f2(rv.x), rc1 = bf2_to_f2(rv.y);
+        f32x2 o0 = 0ull, o1 = 0ull;
+        // halo row j + r holds dpre row y0 + j - 1 + r: tap (a, b) reads dpre[y - a + 1][x - b + 1] = win row 2 - a, column 2 - b
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb) {
+            const f32x2 d0 = win[(j + 2 - a) % 3][2 - bb][0], d1 = win[(j + 2 - a) % 3][2 - bb][1];
+            o0 = ffma2(k[a * 3 + bb][0], d0, o0);
+            o1 = ffma2(k[a * 3 + bb][1], d1, o1);
+            dk[a * 3 + bb][0] = ffma2(rc0, d0, dk[a * 3 + bb][0]);
+            dk[a * 3 + bb][1] = ffma2(rc1, d1, dk[a * 3 + bb][1]);
+          }
+        float o[4];
+        upk2(o0, o[0], o[1]);
+        upk2(o1, o[2], o[3]);
+        store4(draw + tok * ldr + c0, o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  // reduce the column threads of the block (one warp each), warp after warp, then one atomic per (channel, tap)
+  for (int w = 0; w < TX; ++w) {
+    __syncthreads();
+    if ((int)threadIdx.y == w && live) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float v[4];
+        upk2(dk[t][0], v[0], v[1]);
+        upk2(dk[t][1], v[2], v[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[threadIdx.x][t * 4 + i] += v[i];
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 32 * 36; i += 256) {
+    const int v = i / 36, r = i % 36, t = r >> 2, ch = (blockIdx.x * 32 + v) * 4 + (r & 3);
+    if (ch < CC) atomicAdd(dK + ch * 9 + t, red[v][r]);
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm forward / backward
+// y = ygemm + Dch xc;  yn = LayerNorm(y) (biased variance, eps 1e-5, affine).  One warp per token, 8 channels per lane and
+// step; the row is re-read from L1 / L2 for the second and third pass (Di up to 4096).
+__global__ void __launch_bounds__(256)
+k_wln_fwd(const float* __restrict__ ygemm, const bf16* __restrict__ act, const float* __restrict__ Dch,
+          const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ yn, long long Ttok, int Di, int CC) {
+  const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= Ttok) return;
+  const float* yg = ygemm + t * Di;
+  const bf16* xc = act + t * CC + Di;
+  float s = 0.f;
+  for (int c = lane * 8; c < Di; c += 256) {
+    float a[8], x[8], dv[8];
+    load8(yg + c, a); load8(xc + c, x); load8(Dch + c, dv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += fmaf(dv[j], x[j], a[j]);
+  }
+  const float mu = warp_sum(s) / Di;
+  float v = 0.f;
+  for (int c = lane * 8; c < Di; c += 256) {
+    float a[8], x[8], dv[8];
+    load8(yg + c, a); load8(xc + c, x); load8(Dch + c, dv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = fmaf(dv[j], x[j], a[j]) - mu; v = fmaf(d, d, v); }
+  }
+  const float rstd = rsqrtf(warp_sum(v) / Di + 1e-5f);
+  for (int c = lane * 8; c < Di; c += 256) {
+    float a[8], x[8], dv[8], ga[8], be[8], o[8];
+    load8(yg + c, a); load8(xc + c, x); load8(Dch + c, dv); load8(gamma + c, ga); load8(beta + c, be);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (fmaf(dv[j], x[j], a[j]) - mu) * rstd * ga[j] + be[j];
+    store8(yn + t * Di + c, o);
+  }
+}
+
+// Backward of out = alpha1 [LN(y) | zc] W_out^T given g = dout W_out (fp32, no alpha1).  A warp owns `tpw` consecutive tokens.
+//   phase A (per token): LayerNorm statistics, yn (for dW_out), dzc * SiLU'(pre) -> z block of dact, d alpha1, and the row means
+//                        m1 = mean(dyh), m2 = mean(dyh * yhat) of the LayerNorm backward;
+//   phase B (per 8-channel chunk, tokens inner): dy -> x block of dact, with the chunk's d gamma / d beta partial sums in
+//                        registers across the warp's tokens (16 shared-memory atomics per chunk and warp, then one global
+//                        atomic per channel and BLOCK).
+constexpr int LNB_MAX_TPW = 16;
+__global__ void __launch_bounds__(256)
+k_wln_bwd(const float* __restrict__ ygemm, const bf16* __restrict__ act, const float* __restrict__ g,
+          const float* __restrict__ Dch, const float* __restrict__ gamma, const float* __restrict__ beta,
+          const float* __restrict__ alpha1p, const bf16* __restrict__ pre, bf16* __restrict__ yn, bf16* __restrict__ dact,
+          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dalpha1, long long Ttok, int tpw, int Di, int CC) {
+  extern __shared__ float sm[];  // [2*Di] block-local dgamma / dbeta
+  __shared__ float stats[8][LNB_MAX_TPW][4];
+  float* sg = sm;
+  float* sb = sm + Di;
+  for (int i = threadIdx.x; i < 2 * Di; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const float a1 = *alpha1p;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long t0 = ((long long)blockIdx.x * 8 + warp) * tpw;
+  const int nt = (int)max(0LL, min((long long)tpw, Ttok - t0));
+  float da = 0.f;
+  for (int ti = 0; ti < nt; ++ti) {
+    const long long t = t0 + ti;
+    const float* yg = ygemm + t * Di;
+    const bf16* zc = act + t * CC;
+    const bf16* xc = zc + Di;
+    const float* gy = g + t * 2 * Di;
+    const float* gz = gy + Di;
+    float s = 0.f;
+    for (int c = lane * 8; c < Di; c += 256) {
+      float a[8], x[8], dv[8];
+      load8(yg + c, a); load8(xc + c, x); load8(Dch + c, dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += fmaf(dv[j], x[j], a[j]);
+    }
+    const float mu = warp_sum(s) / Di;
+    float v = 0.f;
+    for (int c = lane * 8; c < Di; c += 256) {
+      float a[8], x[8], dv[8];
+      load8(yg + c, a); load8(xc + c, x); load8(Dch + c, dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = fmaf(dv[j], x[j], a[j]) - mu; v = fmaf(d, d, v); }
+    }
+    const float rstd = rsqrtf(warp_sum(v) / Di + 1e-5f);
+    float m1 = 0.f, m2 = 0.f;
+    for (int c = lane * 8; c < Di; c += 256) {
+      float a[8], x[8], dv[8], ga[8], be[8], gyv[8], gzv[8], z[8], ynv[8], dz[8], pz[8];
+      load8(yg + c, a); load8(xc + c, x); load8(Dch + c, dv); load8(gamma + c, ga); load8(beta + c, be);
+      load8(gy + c, gyv); load8(gz + c, gzv); load8(zc + c, z); load8(pre + t * CC + c, pz);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float yh = (fmaf(dv[j], x[j], a[j]) - mu) * rstd;
+        ynv[j] = fmaf(yh, ga[j], be[j]);
+        da += gyv[j] * ynv[j] + gzv[j] * z[j];
+        const float dyh = a1 * gyv[j] * ga[j];
+        m1 += dyh;
+        m2 = fmaf(dyh, yh, m2);
+        dz[j] = a1 * gzv[j] * silu_grad_fast(pz[j]);      // dpre of the z block
+      }
+      store8(yn + t * Di + c, ynv);
+      store8(dact + t * CC + c, dz);
+    }
+    m1 = warp_sum(m1) / Di;
+    m2 = warp_sum(m2) / Di;
+    if (lane == 0) { stats[warp][ti][0] = mu; stats[warp][ti][1] = rstd; stats[warp][ti][2] = m1; stats[warp][ti][3] = m2; }
+  }
+  __syncwarp();
+  for (int c = lane * 8; c < Di; c += 256) {
+    float dv[8], ga[8], dg[8] = {}, db[8] = {};
+    load8(Dch + c, dv); load8(gamma + c, ga);
+    for (int ti = 0; ti < nt; ++ti) {
+      const long long t = t0 + ti;
+      const float mu = stats[warp][ti][0], rstd = stats[warp][ti][1], m1 = stats[warp][ti][2], m2 = stats[warp][ti][3];
+      float a[8], x[8], gyv[8], o[8];
+      load8(ygemm + t * Di + c, a); load8(act + t * CC + Di + c, x); load8(g + t * 2 * Di + c, gyv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float yh = (fmaf(dv[j], x[j], a[j]) - mu) * rstd;
+        const float dyn = a1 * gyv[j];
+        dg[j] = fmaf(dyn, yh, dg[j]);
+        db[j] += dyn;
+        o[j] = rstd * (dyn * ga[j] - m1 - yh * m2);
+      }
+      store8(dact + t * CC + Di + c, o);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(sg + c + j, dg[j]); atomicAdd(sb + c + j, db[j]); }
+  }
+  da = warp_sum(da);
+  if (lane == 0 && da != 0.f) atomicAdd(dalpha1, da);
+  __syncthreads();
+  for (int i = threadIdx.x; i < Di; i += blockDim.x) {
+    atomicAdd(dgamma + i, sg[i]);
+    atomicAdd(dbeta + i, sb[i]);
+  }
+}
+
+// per (token, head): dpre_x = (D dy + w G) SiLU'(pre) (in place over the x block of dact), wx = w xc, ddt -> draw[:, CC + h];
+// accumulates dD, dA_log, ddt_bias.  The decay weight is recomputed from the saved dt column.   block (32 heads, 8 tokens)
+__global__ void __launch_bounds__(256)
+k_wbwd_heads(const bf16* __restrict__ raw, long long ldr, const bf16* __restrict__ act, const bf16* __restrict__ pre, const float* __restrict__ dt_bias,
+             const float* __restrict__ A_log, const float* __restrict__ Dp, bf16* __restrict__ dact, const float* __restrict__ G,
+             bf16* __restrict__ wx, bf16* __restrict__ draw, float* __restrict__ dD, float* __restrict__ dAlog,
+             float* __restrict__ ddtb, long long Ttok, int tokens_per_thread, int nh, int P, int Di, int CC) {
+  __shared__ float red[3][8][32];
+  const int h = blockIdx.x * 32 + threadIdx.x;
+  float aD = 0.f, aA = 0.f, aB = 0.f;
+  if (h < nh) {
+    const float Dh = Dp[h], eA = __expf(A_log[h]), bias = dt_bias[h];
+    const int cb = 2 * P * (h >> 1) + (h & 1);
+    const long long t0 = ((long long)blockIdx.y * 8 + threadIdx.y) * tokens_per_thread;
+    for (long long t = t0; t < min(Ttok, t0 + (long long)tokens_per_thread); ++t) {
+      float w, sig;
+      decay_of(ldf(raw + t * ldr + CC + h) + bias, eA, w, sig);
+      float dw = 0.f;
+      for (int i = 0; i < P; ++i) {
+        const int c = cb + 2 * i;
+        const float dy = ldf(dact + t * CC + Di + c), Gv = G[t * Di + c], x = ldf(act + t * CC + Di + c);
+        stf(dact + t * CC + Di + c, (Dh * dy + w * Gv) * silu_grad_fast(ldf(pre + t * CC + Di + c)));      // dpre of the x block
+        stf(wx + t * Di + c, w * x);
+        dw += x * Gv;
+        aD += dy * x;
+      }
+      const float ddt = dw * eA * sig;
+      stf(draw + t * ldr + CC + h, ddt);
+      aA += dw * w;
+      aB += ddt;
+    }
+  }
+  red[0][threadIdx.y][threadIdx.x] = aD;
+  red[1][threadIdx.y][threadIdx.x] = aA;
+  red[2][threadIdx.y][threadIdx.x] = aB;
+  __syncthreads();
+  if (threadIdx.y < 3 && h < nh) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += red[threadIdx.y][j][threadIdx.x];
+    float* dst = threadIdx.y == 0 ? dD : (threadIdx.y == 1 ? dAlog : ddtb);
+    atomicAdd(dst + h, s);
+  }
+}
+
+// Loud failure without a host sync: if a GEMM of this pass flagged a pipeline time-out, poison the pass's output.
+__global__ void k_poison_if(const int* __restrict__ status, bf16* __restrict__ out, int n) {
+  if (*status != 0 && threadIdx.x < n) out[threadIdx.x] = __float2bfloat16_rn(__int_as_float(0x7fc00000));
+}
+
+// ---------------------------------------------------------------- buffers
+struct SavedW {
+  bf16 *raw, *pre, *act;
+  float* ST;                   // S'^T [B][Di][GN] fp32 (masked)
+  bf16 *S_hi, *S_lo;
+  size_t bytes;
+  SavedW(const MixerDims& d, void* p) {
+    Carver c(p);
+    raw = c.take<bf16>((size_t)d.T * d.ldr);
+    pre = c.take<bf16>((size_t)d.T * d.CC);
+    act = c.take<bf16>((size_t)d.T * d.CC);
+    ST = c.take<float>((size_t)d.B * d.GN * d.Di);
+    S_hi = c.take<bf16>((size_t)d.B * d.GN * d.Di);
+    S_lo = c.take<bf16>((size_t)d.B * d.GN * d.Di);
+    bytes = c.off;
+  }
+};
+
+struct FwdW {
+  float *Kc, *Dch;
+  bf16 *Win, *Wout, *wx, *yn;
+  float* ygemm;
+  int* status;
+  SavedW tmp;      // used when the caller passes saved == NULL (inference)
+  size_t bytes;
+  FwdW(const MixerDims& d, void* p) : tmp(d, nullptr) {
+    Carver c(p);
+    Kc = c.take<float>((size_t)d.CC * 9);
+    Dch = c.take<float>(d.Di);
+    Win = c.take<bf16>((size_t)d.dip * d.D);
+    Wout = c.take<bf16>((size_t)d.D * 2 * d.Di);
+    wx = c.take<bf16>((size_t)d.T * d.Di);
+    yn = c.take<bf16>((size_t)d.T * d.Di);
+    ygemm = c.take<float>((size_t)d.T * d.Di);
+    status = c.take<int>(64);
+    const size_t here = c.off;
+    tmp = SavedW(d, p ? (char*)p + here : nullptr);
+    bytes = here + tmp.bytes;
+  }
+};
+
+struct BwdW {
+  float *Kc, *Dch;
+  bf16 *Win, *Wout;
+  float* zero_begin;
+  GradAcc acc;
+  int* status;
+  float* dST;
+  size_t zero_bytes;
+  bf16 *dS_hi, *dS_lo, *yn, *wx, *dact, *draw;
+  float* g;          // dout W_out, fp32
+  float* ybuf;       // y (readout recompute), then G
+  size_t bytes;
+  BwdW(const MixerDims& d, void* p) {
+    Carver c(p);
+    Kc = c.take<float>((size_t)d.CC * 9);
+    Dch = c.take<float>(d.Di);
+    Win = c.take<bf16>((size_t)d.dip * d.D);
+    Wout = c.take<bf16>((size_t)d.D * 2 * d.Di);
+    const size_t z0 = c.off;
+    zero_begin = p ? (float*)((char*)p + z0) : nullptr;
+    acc.dWin = c.take<float>((size_t)d.dip * d.D);
+    acc.dWin_part = nullptr; acc.dWin_parts = 0;
+    acc.dK_part = nullptr; acc.dK_parts = 0; acc.dK_stride = 0;
+    acc.head_part = nullptr; acc.head_parts = 0;
+    acc.dWout = c.take<float>((size_t)d.D * 2 * d.Di);
+    acc.dgamma = c.take<float>(d.Di);
+    acc.dbeta = c.take<float>(d.Di);
+    acc.dD = c.take<float>(d.nh);
+    acc.dAlog = c.take<float>(d.nh);
+    acc.ddtb = c.take<float>(d.nh);
+    acc.dalpha1 = c.take<float>(1);
+    acc.dK = c.take<float>((size_t)d.CC * 9);
+    acc.sync_counter = c.take<int>(64);
+    status = c.take<int>(64);
+    dST = c.take<float>((size_t)d.B * d.GN * d.Di);
+    zero_bytes = c.off - z0;
+    dS_hi = c.take<bf16>((size_t)d.B * d.GN * d.Di);
+    dS_lo = c.take<bf16>((size_t)d.B * d.GN * d.Di);
+    g = c.take<float>((size_t)d.T * 2 * d.Di);
+    yn = c.take<bf16>((size_t)d.T * d.Di);
+    wx = c.take<bf16>((size_t)d.T * d.Di);
+    dact = c.take<bf16>((size_t)d.T * d.CC);
+    draw = c.take<bf16>((size_t)d.T * d.ldr);
+    ybuf = c.take<float>((size_t)d.T * d.Di);
+    bytes = c.off;
+  }
+};
+
+// Shapes of the wide path: everything bf16 whose rows are whole 16-byte pieces (cp.async granularity) and whose state
+// width is a legal UMMA N.  The reference network's mixers all qualify (SURVEY.md 3.2 instance table).
+static inline bool supported(const MixerDims& d) {
+  return env().wide && d.D % 8 == 0 && d.Di % 8 == 0 && d.GN % 16 == 0 && d.GN <= 256 && d.dip % 8 == 0 && d.ldr == d.dip &&
+         d.CC % 8 == 0 && d.T < (1LL << 31) / 8;
+}
+
+static inline void workspace_bytes(const MixerDims& d, size_t* saved, size_t* fwd, size_t* bwd) {
+  *saved = SavedW(d, nullptr).bytes;
+  *fwd = FwdW(d, nullptr).bytes;
+  *bwd = BwdW(d, nullptr).bytes;
+}
+
+static inline int ew_grid(long long n) {
+  long long b = (n + 255) / 256;
+  long long cap = (long long)sm_count() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+#define WIDE_GEMM(...)              \
+  do {                              \
+    int _rc = tcg::gemm(__VA_ARGS__); \
+    if (_rc) return _rc;            \
+  } while (0)
+
+// ---------------------------------------------------------------- forward
+static int forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16* out, void* saved, void* ws, cudaStream_t st) {
+  using namespace tcg;
+  FwdW W(d, ws);
+  SavedW S = saved ? SavedW(d, saved) : W.tmp;
+  const bool training = saved != nullptr;
+  const int T = (int)d.T, L = d.L;
+  const long long sS = (long long)d.GN * d.Di;
+  ADN_CHECK_CUDA(cudaMemsetAsync(W.status, 0, 256, st));
+  { ADN_KERNEL("k_prep_wide", st); k_prep_wide<<<ew_grid((long long)d.dip * d.D + (long long)d.D * 2 * d.Di), 256, 0, st>>>(
+        w.in_proj_w, W.Win, (long long)d.dip * d.D, w.out_proj_w, W.Wout, (long long)d.D * 2 * d.Di, w.D, W.Dch, d.Di, d.P,
+        conv_ptrs(w), W.Kc, d.CC); }
+  // (1) raw = u W_in^T
+  WIDE_GEMM(st, "tcgemm_inproj", T, d.dip, d.D, kmaj(u, d.D), kmaj(W.Win, d.D), 0, NOOP, NOOP,
+            Out{S.raw, d.ldr, 0, C_BF16}, 1, 1, nullptr, 0, W.status);
+  // (2) depthwise 3x3 + SiLU over [z | x | B | C];  (3) decay weights and w * x
+  {
+    dim3 grid(cdiv(d.CC, 128), cdiv(d.W, TX), d.B * cdiv(d.H, TY)), block(32, TX);
+    ADN_REQUIRE(grid.z <= 65535, ADN_ERR_SHAPE, "wide path: B * ceil(H / %d) = %u exceeds the grid limit", TY, grid.z);
+    int pshift = -1;
+    for (int q = 1; q < 16; ++q) if ((1 << q) == d.P) pshift = q;
+    { ADN_KERNEL("k_wconv_fwd", st); k_wconv_fwd<<<grid, block, 0, st>>>(S.raw, d.ldr, W.Kc, w.dt_bias, w.A_log, training ? S.pre : nullptr,
+                                                                        S.act, W.wx, d.H, d.W, d.CC, d.Di, d.P, pshift); }
+  }
+  // (4a) S'^T[b] = mask . wx[b]^T Bc[b]   (M = Di, N = GN, K = L; both operands MN-major)
+  {
+    const int splitk = pick_splitk(cdiv(d.Di, BM) * cdiv(d.GN, pick_bn(d.GN)) * d.B, L);
+    if (splitk > 1) ADN_CHECK_CUDA(cudaMemsetAsync(S.ST, 0, (size_t)d.B * sS * sizeof(float), st));
+    WIDE_GEMM(st, "tcgemm_state", d.Di, d.GN, L, mnmaj(W.wx, d.Di, (long long)L * d.Di), mnmaj(S.act + 2 * d.Di, d.CC, (long long)L * d.CC),
+              0, NOOP, NOOP, Out{S.ST, d.GN, sS, splitk > 1 ? C_ATOMIC_F32 : C_F32}, d.B, splitk, nullptr, 1, W.status);
+    { ADN_KERNEL("k_split_hilo", st); k_split_hilo<<<ew_grid((long long)d.B * sS), 256, 0, st>>>(S.ST, S.S_hi, S.S_lo, (long long)d.B * sS); }
+  }
+  // (4b) y[b] = Cc[b] S'[b]   (M = L, N = Di, K = GN; B operand = S'^T [Di][GN], K-major, hi + lo)
+  WIDE_GEMM(st, "tcgemm_readout", L, d.Di, d.GN, kmaj(S.act + 2 * d.Di + d.GN, d.CC, (long long)L * d.CC), kmaj(S.S_hi, d.GN, sS),
+            d.GN, kmaj(S.act + 2 * d.Di + d.GN, d.CC, (long long)L * d.CC), kmaj(S.S_lo, d.GN, sS),
+            Out{W.ygemm, d.Di, (long long)L * d.Di, C_F32}, d.B, 1, nullptr, 0, W.status);
+  // (5) D-skip + LayerNorm, out = alpha1 (yn W_y^T + zc W_z^T)
+  { ADN_KERNEL("k_wln_fwd", st); k_wln_fwd<<<cdiv(T, 8), 256, 0, st>>>(W.ygemm, S.act, W.Dch, w.norm_w, w.norm_b, W.yn, T, d.Di, d.CC); }
+  WIDE_GEMM(st, "tcgemm_outproj", T, d.D, d.Di, kmaj(W.yn, d.Di), kmaj(W.Wout, 2 * d.Di), d.Di, kmaj(S.act, d.CC), kmaj(W.Wout + d.Di, 2 * d.Di),
+            Out{out, d.D, 0, C_BF16}, 1, 1, w.alpha1, 0, W.status);
+  { ADN_KERNEL("k_poison_if", st); k_poison_if<<<1, 32, 0, st>>>(W.status, out, 8); }
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
+// ---------------------------------------------------------------- backward
+static int backward(const MixerDims& d, const AdnWeights& w, const bf16* u, const void* saved, const bf16* dout, bf16* du,
+                    const AdnWeightGrads& g, void* ws, cudaStream_t st) {
+  using namespace tcg;
+  BwdW W(d, ws);
+  SavedW S(d, const_cast<void*>(saved));
+  const int T = (int)d.T, L = d.L;
+  const long long sS = (long long)d.GN * d.Di;
+  const long long bA = (long long)L * d.CC, bD = (long long)L * d.Di;
+  ADN_CHECK_CUDA(cudaMemsetAsync(W.zero_begin, 0, W.zero_bytes, st));
+  { ADN_KERNEL("k_prep_wide", st); k_prep_wide<<<ew_grid((long long)d.dip * d.D + (long long)d.D * 2 * d.Di), 256, 0, st>>>(
+        w.in_proj_w, W.Win, (long long)d.dip * d.D, w.out_proj_w, W.Wout, (long long)d.D * 2 * d.Di, w.D, W.Dch, d.Di, d.P,
+        conv_ptrs(w), W.Kc, d.CC); }
+  const bf16* Cc = S.act + 2 * d.Di + d.GN;
+  const bf16* Bc = S.act + 2 * d.Di;
+  // ---- phase B1
+  // g = dout W_out   (B stored [K = D][N = 2Di]: MN-major)
+  WIDE_GEMM(st, "tcgemm_g", T, 2 * d.Di, d.D, kmaj(dout, d.D), mnmaj(W.Wout, 2 * d.Di), 0, NOOP, NOOP,
+            Out{W.g, 2 * d.Di, 0, C_F32}, 1, 1, nullptr, 0, W.status);
+  WIDE_GEMM(st, "tcgemm_readout", L, d.Di, d.GN, kmaj(Cc, d.CC, bA), kmaj(S.S_hi, d.GN, sS), d.GN, kmaj(Cc, d.CC, bA), kmaj(S.S_lo, d.GN, sS),
+            Out{W.ybuf, d.Di, bD, C_F32}, d.B, 1, nullptr, 0, W.status);
+  {
+    // tokens per warp: enough warps to fill the machine twice over, at most LNB_MAX_TPW tokens each
+    int tpw = (int)(d.T / (16LL * sm_count()));
+    tpw = tpw < 1 ? 1 : (tpw > LNB_MAX_TPW ? LNB_MAX_TPW : tpw);
+    { ADN_KERNEL("k_wln_bwd", st); k_wln_bwd<<<cdiv(T, 8 * tpw), 256, 2 * d.Di * sizeof(float), st>>>(
+        W.ybuf, S.act, W.g, W.Dch, w.norm_w, w.norm_b, w.alpha1, S.pre, W.yn, W.dact, W.acc.dgamma, W.acc.dbeta, W.acc.dalpha1, T,
+        tpw, d.Di, d.CC); }
+  }
+  // dW_out = dout^T [yn | zc]   (reductions over all tokens: both operands MN-major, split-K, fp32 atomics)
+  {
+    const int splitk = pick_splitk(cdiv(d.D, BM) * cdiv(d.Di, pick_bn(d.Di)), T);
+    WIDE_GEMM(st, "tcgemm_dWout_y", d.D, d.Di, T, mnmaj(dout, d.D), mnmaj(W.yn, d.Di), 0, NOOP, NOOP,
+              Out{W.acc.dWout, 2 * d.Di, 0, C_ATOMIC_F32}, 1, splitk, nullptr, 0, W.status);
+    WIDE_GEMM(st, "tcgemm_dWout_z", d.D, d.Di, T, mnmaj(dout, d.D), mnmaj(S.act, d.CC), 0, NOOP, NOOP,
+              Out{W.acc.dWout + d.Di, 2 * d.Di, 0, C_ATOMIC_F32}, 1, splitk, nullptr, 0, W.status);
+  }
+  // dS'^T[b] = mask . dy[b]^T Cc[b]
+  {
+    const int splitk = pick_splitk(cdiv(d.Di, BM) * cdiv(d.GN, pick_bn(d.GN)) * d.B, L);
+    WIDE_GEMM(st, "tcgemm_dstate", d.Di, d.GN, L, mnmaj(W.dact + d.Di, d.CC, bA), mnmaj(Cc, d.CC, bA), 0, NOOP, NOOP,
+              Out{W.dST, d.GN, sS, C_ATOMIC_F32}, d.B, splitk, nullptr, 1, W.status);
+    { ADN_KERNEL("k_split_hilo", st); k_split_hilo<<<ew_grid((long long)d.B * sS), 256, 0, st>>>(W.dST, W.dS_hi, W.dS_lo, (long long)d.B * sS); }
+  }
+  // dCc[b] = dy[b] S'[b]^T   (B = S'^T [K = Di][N = GN]: MN-major, hi + lo) -> C block of dact
+  WIDE_GEMM(st, "tcgemm_dC", L, d.GN, d.Di, kmaj(W.dact + d.Di, d.CC, bA), mnmaj(S.S_hi, d.GN, sS), d.Di, kmaj(W.dact + d.Di, d.CC, bA),
+            mnmaj(S.S_lo, d.GN, sS), Out{W.dact + 2 * d.Di + d.GN, d.CC, bA, C_BF16}, d.B, 1, nullptr, 0, W.status,
+            Aux{S.pre + 2 * d.Di + d.GN, d.CC, bA});
+  // ---- phase B2
+  // G[b] = Bc[b] dS'[b]   (B = dS'^T [N = Di][K = GN]: K-major, hi + lo)
+  WIDE_GEMM(st, "tcgemm_G", L, d.Di, d.GN, kmaj(Bc, d.CC, bA), kmaj(W.dS_hi, d.GN, sS), d.GN, kmaj(Bc, d.CC, bA), kmaj(W.dS_lo, d.GN, sS),
+            Out{W.ybuf, d.Di, bD, C_F32}, d.B, 1, nullptr, 0, W.status);
+  {
+    const int tpt = 8;
+    dim3 grid(cdiv(d.nh, 32), cdiv(T, 8 * tpt)), block(32, 8);
+    { ADN_KERNEL("k_wbwd_heads", st); k_wbwd_heads<<<grid, block, 0, st>>>(S.raw, d.ldr, S.act, S.pre, w.dt_bias, w.A_log, w.D, W.dact, W.ybuf,
+                                                                            W.wx, W.draw, W.acc.dD, W.acc.dAlog, W.acc.ddtb, T, tpt, d.nh, d.P, d.Di, d.CC); }
+  }
+  // dBc[b] = wx[b] dS'[b]^T   (B = dS'^T [K = Di][N = GN]: MN-major, hi + lo) -> B block of dact
+  WIDE_GEMM(st, "tcgemm_dB", L, d.GN, d.Di, kmaj(W.wx, d.Di, bD), mnmaj(W.dS_hi, d.GN, sS), d.Di, kmaj(W.wx, d.Di, bD), mnmaj(W.dS_lo, d.GN, sS),
+            Out{W.dact + 2 * d.Di, d.CC, bA, C_BF16}, d.B, 1, nullptr, 0, W.status, Aux{S.pre + 2 * d.Di, d.CC, bA});
+  // ---- conv backward (dact now holds dpre: every producer above multiplied by SiLU'(pre)): draw[:, :CC] = conv^T(dpre); dK
+  {
+    const int gx = cdiv(d.CC, 128), gy = cdiv(d.W, TX), items = d.B * cdiv(d.H, TY);
+    int gz = cdiv(6LL * sm_count(), (long long)gx * gy);       // ~6 blocks per SM in total, each striding over the work items
+    gz = gz < 1 ? 1 : (gz > items ? items : gz);
+    dim3 grid(gx, gy, gz), block(32, TX);
+    { ADN_KERNEL("k_wconv_bwd", st); k_wconv_bwd<<<grid, block, 0, st>>>(W.dact, S.raw, d.ldr, W.Kc, W.draw, W.acc.dK, d.B, d.H, d.W, d.CC); }
+  }
+  // ---- in_proj backward: du = draw W_in (B stored [K = dip][N = D]: MN-major); dW_in = draw^T u
+  WIDE_GEMM(st, "tcgemm_du", T, d.D, d.dip, kmaj(W.draw, d.ldr), mnmaj(W.Win, d.D), 0, NOOP, NOOP, Out{du, d.D, 0, C_BF16}, 1, 1, nullptr, 0,
+            W.status);
+  {
+    const int splitk = pick_splitk(cdiv(d.dip, BM) * cdiv(d.D, pick_bn(d.D)), T);
+    WIDE_GEMM(st, "tcgemm_dWin", d.dip, d.D, T, mnmaj(W.draw, d.ldr), mnmaj(u, d.D), 0, NOOP, NOOP,
+              Out{W.acc.dWin, d.D, 0, C_ATOMIC_F32}, 1, splitk, nullptr, 0, W.status);
+  }
+  { ADN_KERNEL("k_finalize", st); k_finalize<<<sm_count(), 256, 0, st>>>(W.acc, w, g, d.D, d.Di, d.GN, d.nh, d.dip); }
+  { ADN_KERNEL("k_poison_if", st); k_poison_if<<<1, 32, 0, st>>>(W.status, du, 8); }
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
+}  // namespace wide
+}  // namespace adn

@@ -47,7 +47,8 @@ struct Args {
   int parity_mask;         // 1: keep only (m & 1) == (n & 1)   (the even/odd SSD split, models/ADNssd.py:397-404)
   int splitk, k_per_split; // split-K over segment 0 (nseg must be 1 when splitk > 1); k_per_split is a multiple of BK
   int* status;             // set to 1 on a pipeline time-out
-};
+  const bf16* aux; long long ld_aux, aux_bs;   // optional epilogue operand, indexed like C: C = acc * SiLU'(aux)   (conv backward:
+};                                            // the gradient w.r.t. the conv output becomes the gradient w.r.t. its input)
 
 __device__ __forceinline__ void cp16(uint32_t sdst, const void* gsrc, int nbytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(nbytes) : "memory");
@@ -113,18 +114,17 @@ k_tcgemm(const Args a) {
       if (it < nk) {
         const int s = it % STAGES;
         if (it >= STAGES) ok &= mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
-        const bool second = it >= nk0;
-        const Seg& sg = a.seg[second ? 1 : 0];
+        const bool second = it >= nk0;      // scalar selects (no dynamic indexing of the kernel parameter struct)
+        const long long lda = second ? a.seg[1].lda : a.seg[0].lda, ldb = second ? a.seg[1].ldb : a.seg[0].ldb;
         const int k0 = second ? (it - nk0) * BK : kb0 + it * BK;
-        const int kend = second ? sg.K : ke0;
-        const int kvalid = kend - k0;                       // > 0
-        const bf16* A = sg.A + (long long)batch * sg.a_bs;
-        const bf16* B = sg.B + (long long)batch * sg.b_bs;
+        const int kvalid = (second ? a.seg[1].K : ke0) - k0;                       // > 0
+        const bf16* A = second ? a.seg[1].A + (long long)batch * a.seg[1].a_bs : a.seg[0].A + (long long)batch * a.seg[0].a_bs;
+        const bf16* B = second ? a.seg[1].B + (long long)batch * a.seg[1].b_bs : a.seg[0].B + (long long)batch * a.seg[0].b_bs;
         const uint32_t sa = s0 + s * stage_b, sb = sa + A_TILE_B;
-        if (!a.a_mn) load_t8(sa, A + (long long)m0 * sg.lda + k0, sg.lda, BM, BM, BK / 8, a.M - m0, (kvalid + 7) >> 3, warp, lane);
-        else         load_t8(sa, A + (long long)k0 * sg.lda + m0, sg.lda, BK, BK, BM / 8, kvalid, (a.M - m0 + 7) >> 3, warp, lane);
-        if (!a.b_mn) load_t8(sb, B + (long long)n0 * sg.ldb + k0, sg.ldb, BN, BN, BK / 8, a.N - n0, (kvalid + 7) >> 3, warp, lane);
-        else         load_t8(sb, B + (long long)k0 * sg.ldb + n0, sg.ldb, BK, BK, BN / 8, kvalid, (a.N - n0 + 7) >> 3, warp, lane);
+        if (!a.a_mn) load_t8(sa, A + (long long)m0 * lda + k0, lda, BM, BM, BK / 8, a.M - m0, (kvalid + 7) >> 3, warp, lane);
+        else         load_t8(sa, A + (long long)k0 * lda + m0, lda, BK, BK, BM / 8, kvalid, (a.M - m0 + 7) >> 3, warp, lane);
+        if (!a.b_mn) load_t8(sb, B + (long long)n0 * ldb + k0, ldb, BN, BN, BK / 8, a.N - n0, (kvalid + 7) >> 3, warp, lane);
+        else         load_t8(sb, B + (long long)k0 * ldb + n0, ldb, BK, BK, BN / 8, kvalid, (a.N - n0 + 7) >> 3, warp, lane);
       }
       cp_commit();
       if (it >= LAG) {
@@ -151,6 +151,12 @@ k_tcgemm(const Args a) {
         if (a.parity_mask && ((m ^ (n + j)) & 1)) v[j] = 0.f;
       }
       const int nv = min(16, a.N - n);
+      if (a.aux != nullptr) {
+        const bf16* q = a.aux + (long long)batch * a.aux_bs + (long long)m * a.ld_aux + n;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nv) v[j] *= silu_gradf_(__bfloat162float(q[j]));
+      }
       if (a.c_mode == C_BF16) {
         bf16* p = (bf16*)a.C + (long long)batch * a.c_bs + (long long)m * a.ldc + n;
         if (nv == 16 && ((uintptr_t)p & 15) == 0) {
@@ -222,8 +228,13 @@ static inline int pick_bn(int N) {
 }
 
 // C = alpha * (A0 . B0 [+ A1 . B1]);  batches > 1: per-sample GEMMs;  splitk > 1: atomics into a ZEROED fp32 C.
+struct Aux {
+  const bf16* p; long long ld, bs;
+};
+static const Aux NOAUX = Aux{nullptr, 0, 0};
+
 static int gemm(cudaStream_t st, const char* name, int M, int N, int K0, Op A0, Op B0, int K1, Op A1, Op B1, Out C,
-                int batches, int splitk, const float* alpha, int parity_mask, int* status) {
+                int batches, int splitk, const float* alpha, int parity_mask, int* status, Aux aux = NOAUX) {
   ADN_REQUIRE(M > 0 && N > 0 && K0 > 0 && batches > 0, ADN_ERR_SHAPE, "tcgemm %s: empty problem", name);
   ADN_REQUIRE(K1 == 0 || (A1.mn == A0.mn && B1.mn == B0.mn), ADN_ERR_SHAPE, "tcgemm %s: segments must share orientation", name);
   ADN_REQUIRE(splitk == 1 || (K1 == 0 && C.mode == C_ATOMIC_F32), ADN_ERR_SHAPE, "tcgemm %s: split-K needs one segment and an atomic fp32 output", name);
@@ -243,6 +254,7 @@ static int gemm(cudaStream_t st, const char* name, int M, int N, int K0, Op A0, 
   a.k_per_split = (cdiv(cdiv(K0, a.splitk), BK)) * BK;
   a.splitk = cdiv(K0, a.k_per_split);
   a.status = status;
+  a.aux = aux.p; a.ld_aux = aux.ld; a.aux_bs = aux.bs;
   const size_t smem = (size_t)STAGES * (A_TILE_B + a.BN * BK * 2);
   static bool attr_done = false;
   if (!attr_done) {

@@ -200,6 +200,23 @@ int adn_selftest_umma(int mode, int N, int K, const void* A, const void* B, floa
 int adn_selftest_umma_shift(int mode, int N, int K, int pitch, int shiftA, int shiftB, const void* A, const void* B,
                             float* C, int* status, void* stream);
 
+/* Diagnostic kernel-family switches ("rowconv", "row_wide", "bwd_ws", "wide", "rows_per_cta", "du_dbg"): same meaning as the
+ * ADN_<NAME> environment variables, which are read once at first use.  Flip only between whole forward + backward passes. */
+int adn_set_option(const char* name, int value);
+/* Kernel family that serves a shape: 0 generic CUDA-core kernels (the fp32 check mode; bf16 shapes whose rows are not
+ * whole 16-byte pieces), 1 tile kernels and 2 row kernels (d_model 32, fused tcgen05), 3 wide path (d_model >= 64 or
+ * d_state 128: tcgen05 GEMMs + bf16 bandwidth kernels); -1 for an invalid shape. */
+int adnssd_kernel_family(const AdnShape* s);
+/* Standalone entry to the general tcgen05 GEMM of the wide path (bf16 operands, fp32 accumulation in TMEM):
+ *   C[b] = alpha * (A0[b] . B0[b] [+ A1[b] . B1[b]])      M x N, K0 (+ K1) deep, `batches` problems, optional split-K.
+ * a_mn / b_mn: 0 = operand stored row-major [M or N][K], 1 = stored [K][M or N]; row pitches ld*, batch strides *_bs (elements).
+ * c_mode 0: bf16 store, 1: fp32 store, 2: fp32 atomic add into a pre-zeroed C (required for splitk > 1).
+ * parity_mask 1 keeps only (m & 1) == (n & 1).  *status (device int, caller-zeroed) is set to 1 on a pipeline time-out. */
+int adn_selftest_gemm(int M, int N, int K0, int K1, int a_mn, int b_mn, const void* A0, long long lda0, long long a_bs0,
+                      const void* B0, long long ldb0, long long b_bs0, const void* A1, long long lda1, long long a_bs1,
+                      const void* B1, long long ldb1, long long b_bs1, void* C, long long ldc, long long c_bs, int c_mode,
+                      int batches, int splitk, const float* alpha, int parity_mask, int* status, void* stream);
+
 /* tcgen05.mma issue-rate probe: `ctas` CTAs each issue `iters` 128 x N x 16 bf16 MMAs (mode 0 K-major, 1 MN-major operands,
  * row pitch `pitch`, start shifted by `shift` rows); cycles[cta] (DEVICE int64) = SM clocks from first issue to completion. */
 int adn_bench_umma(int mode, int N, int pitch, int shift, int iters, int ctas, long long* cycles, void* stream);

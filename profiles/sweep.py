@@ -1,7 +1,7 @@
 """BASELINE configs[4] sweep (evidence, not a bench line): ADN-SSD mixer fwd+bwd over token grids 32^2..256^2 and d_state
 16..128 at a constant token count (B = 262144 / L), bf16, device-timed with CUDA events; and WTConv2d over the same grids.
-Writes profiles/r01_sweep.json.  Paths: W == 128, d_state 16 -> conv-as-GEMM row kernels; other L % 128 == 0 shapes of
-d_model 32 with d_state in {16, 64} -> halo-tile tcgen05 kernels; everything else -> generic CUDA-core path."""
+Writes gpurun_out/r02_sweep.json (copied to profiles/ when committed).  Paths: W == 128, d_state 16 -> conv-as-GEMM row kernels; other L % 128 == 0 shapes of
+d_model 32 with d_state in {16, 64} -> halo-tile tcgen05 kernels; d_model >= 64 and d_state 128 -> wide path (tcgen05 GEMMs, adnssd_wide.cuh)."""
 import json, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import adnm_unet_b200 as A
@@ -33,7 +33,7 @@ for D in (32, 128):
             with _lib.profile() as prof:
                 step()
             names = sorted({n for n, _ in prof.records})
-            path = "row" if "k_fconv" in names else ("tile" if "k_inproj" in names else "generic")
+            path = "row" if "k_fconv" in names else ("tile" if "k_inproj" in names else ("wide" if "tcgemm_inproj" in names else "generic"))
             ms = time_fn(step, 10 if path != "generic" else 3)
             rows.append({"op": "adnssd_fwd_bwd", "d_model": D, "d_state": N, "grid": g, "batch": B, "path": path, "ms": ms,
                          "tokens_per_s": TOK / (ms * 1e-3)})
@@ -56,6 +56,6 @@ for C in (32, 64):
         print(rows[-1], flush=True)
         del m, x, gy
         torch.cuda.empty_cache()
-out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out", "r01_sweep.json")
+out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out", "r02_sweep.json")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 json.dump({"note": "eager launches (host-bound below ~0.4 ms); see bench.py for the graph-replayed headline", "rows": rows}, open(out, "w"), indent=1)

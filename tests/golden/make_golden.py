@@ -69,6 +69,29 @@ def mixer_bf16_case(ref, name):
     save(name, **arrays)
 
 
+def mixer_corr_case(ref, name):
+    """128 x 128 goldens with a correlated upstream gradient (cases.MIXER_CORR_CASES); out / du stored subsampled."""
+    D, P, N, B, g, perturb = cases.MIXER_CORR_CASES[name]
+    p32 = adnssd_oracle.init_params(D, P, N, seed=17, perturb=perturb, dtype=torch.float32)
+    m = ref.ADNssd.Mamba2(d_model=D, headdim=P, d_state=N).double()
+    m.load_state_dict({k: v.double() for k, v in p32.items()}, strict=True)
+    u = cases.mixer_corr_u(name, torch.float32).double().requires_grad_(True)
+    with cuda_to_is_noop():
+        out = m(u, g, g)
+    dout = cases.mixer_corr_dout(name, out.detach())
+    # the tests rebuild dout from the ORACLE's forward: the two must agree far below fp32 resolution
+    o2 = adnssd_oracle.mixer_forward({k: v.double() for k, v in p32.items()}, u.detach(), g, g, P, N)
+    assert float((o2 - out.detach()).abs().max() / out.detach().abs().max()) < 1e-12
+    out.backward(dout.double())
+    s = cases.SUBSAMPLE_STRIDE
+    arrays = {"param/" + k: v.numpy() for k, v in p32.items()}
+    arrays.update(out=out.detach()[:, ::s].numpy(), du=u.grad[:, ::s].numpy())
+    for k, v in m.named_parameters():
+        if v.grad is not None:
+            arrays["grad/" + k] = v.grad.numpy()
+    save(name, **arrays)
+
+
 def wtconv_case(ref, name):
     C, k, L, B, H, W, bias = cases.WTCONV_CASES[name]
     p32 = wtconv_oracle.init_params(C, k, L, bias=bias, seed=21, dtype=torch.float32)
@@ -118,6 +141,9 @@ def main():
     for name in cases.MIXER_BF16_CASES:
         if not only or name in only:
             mixer_bf16_case(ref, name)
+    for name in cases.MIXER_CORR_CASES:
+        if not only or name in only:
+            mixer_corr_case(ref, name)
     for name in cases.WTCONV_CASES:
         if not only or name in only:
             wtconv_case(ref, name)

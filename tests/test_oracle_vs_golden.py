@@ -56,6 +56,23 @@ def test_mixer_oracle_matches_reference_model_scale(golden_dir, name):
         assert rel(og[k].reshape(ref.shape), ref) < 1e-6, k
 
 
+@pytest.mark.parametrize("name", sorted(cases.MIXER_CORR_CASES))
+def test_mixer_oracle_matches_reference_headline_shapes(golden_dir, name):
+    """128 x 128 goldens of the unmodified reference with a correlated upstream gradient (make_golden.mixer_corr_case)."""
+    D, P, N, B, g, _ = cases.MIXER_CORR_CASES[name]
+    z, params, grads = load(golden_dir, name)
+    p = {k: v.double() for k, v in params.items()}
+    u = cases.mixer_corr_u(name, torch.float32).double()
+    out = AO.mixer_forward(p, u, g, g, P, N)
+    dout = cases.mixer_corr_dout(name, out).double()
+    du, og = AO.mixer_backward(p, u, g, g, P, N, dout)
+    s = cases.SUBSAMPLE_STRIDE
+    assert rel(out[:, ::s], z["out"]) < 1e-12 and rel(du[:, ::s], z["du"]) < 1e-11
+    assert set(grads) == set(AO.PARAM_NAMES) - set(AO.UNUSED_PARAMS)
+    for k, ref in grads.items():
+        assert rel(og[k].reshape(ref.shape), ref) < 1e-10, k
+
+
 def test_mixer_oracle_explicit_backward_equals_autograd():
     D, P, N, g = 16, 4, 8, 5
     p = AO.init_params(D, P, N, seed=3, perturb=0.3, dtype=torch.float64)
