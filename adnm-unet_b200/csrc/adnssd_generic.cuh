@@ -432,7 +432,9 @@ k_ln_bwd(const TW* __restrict__ ygemm, const T* __restrict__ act, const TW* __re
   const float a1 = *alpha1p;
   const int lane = threadIdx.x & 31;
   long long t0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * tokens_per_warp;
-  float da = 0.f;
+  // d alpha1 = <g, [yn | zc]> is one scalar summed over every token and channel with heavy cancellation: accumulated in
+  // fp64 end to end (the 8-byte accumulator slot is read back as a double by finalize_body)
+  double da = 0.0;
   for (long long t = t0; t < min(Ttok, t0 + tokens_per_warp); ++t) {
     const TW* yg = ygemm + t * Di;
     const T* zc = act + t * CC;
@@ -454,7 +456,7 @@ k_ln_bwd(const TW* __restrict__ ygemm, const T* __restrict__ act, const TW* __re
       float gyc = ldf(gy + c), gzc = ldf(gz + c), z = ldf(zc + c);
       float ynv = yh * gamma[c] + beta[c];
       stf(yn + t * Di + c, ynv);
-      da += gyc * ynv + gzc * z;
+      da += (double)(gyc * ynv + gzc * z);
       float dyn = a1 * gyc;
       atomicAdd(sg + c, dyn * yh);
       atomicAdd(sb + c, dyn);
@@ -471,8 +473,9 @@ k_ln_bwd(const TW* __restrict__ ygemm, const T* __restrict__ act, const TW* __re
       stf(dact + t * CC + Di + c, rstd * (dyh - m1 - yh * m2));
     }
   }
-  da = warp_sum(da);
-  if (lane == 0 && da != 0.f) atomicAdd(dalpha1, da);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
+  if (lane == 0 && da != 0.0) atomicAdd(reinterpret_cast<double*>(dalpha1), da);
   __syncthreads();
   for (int i = threadIdx.x; i < Di; i += blockDim.x) {
     atomicAdd(dgamma + i, sg[i]);
@@ -532,6 +535,7 @@ k_bwd_heads(const T* __restrict__ raw, long long ldr, const T* __restrict__ act,
 // ------------------------------------------------------------------------------------------------
 struct GradAcc {
   float *dWin, *dWout, *dgamma, *dbeta, *dD, *dAlog, *ddtb, *dalpha1, *dK;
+  int dalpha1_f64;      // the dalpha1 slot (8 bytes) holds a double (generic k_ln_bwd) instead of a float
   // optional per-CTA partial sums of dW_in (the tcgen05 path writes one slab per CTA instead of contended atomics);
   // finalize adds dWin_parts slabs of dip*D floats starting at dWin_part to dWin
   const float* dWin_part;
@@ -570,7 +574,7 @@ __device__ __forceinline__ void finalize_body(const GradAcc& a, const AdnWeights
     if (g.norm_w) g.norm_w[i] = a.dgamma[i];
     if (g.norm_b) g.norm_b[i] = a.dbeta[i];
   }
-  if (i0 == 0 && g.alpha1) g.alpha1[0] = a.dalpha1[0];
+  if (i0 == 0 && g.alpha1) g.alpha1[0] = a.dalpha1_f64 ? (float)*reinterpret_cast<const double*>(a.dalpha1) : a.dalpha1[0];
   }
   for (long long i = i0; i < nh; i += stride) {
     float vD = __ldcg(a.dD + i), vA = __ldcg(a.dAlog + i), vB = __ldcg(a.ddtb + i);
@@ -705,7 +709,8 @@ struct BwdWs {
     acc.dD = c.take<float>(d.nh);
     acc.dAlog = c.take<float>(d.nh);
     acc.ddtb = c.take<float>(d.nh);
-    acc.dalpha1 = c.take<float>(1);
+    acc.dalpha1 = c.take<float>(2);
+    acc.dalpha1_f64 = 1;
     acc.dK = c.take<float>((size_t)d.CC * 9);
     acc.sync_counter = c.take<int>(64);
     status = c.take<int>(64);      // pipeline-fault word of the backward pass, zeroed with the accumulators

@@ -545,7 +545,8 @@ struct BwdW {
     acc.dD = c.take<float>(d.nh);
     acc.dAlog = c.take<float>(d.nh);
     acc.ddtb = c.take<float>(d.nh);
-    acc.dalpha1 = c.take<float>(1);
+    acc.dalpha1 = c.take<float>(2);
+    acc.dalpha1_f64 = 0;
     acc.dK = c.take<float>((size_t)d.CC * 9);
     acc.sync_counter = c.take<int>(64);
     status = c.take<int>(64);

@@ -136,9 +136,10 @@ def install_shims():
 
 
 @contextlib.contextmanager
-def cuda_to_is_noop():
-    """Neutralise `.to('cuda')` of the index vectors (models/ADNssd.py:329-382) when running the reference on CPU."""
-    if torch.cuda.is_available():
+def cuda_to_is_noop(force=False):
+    """Neutralise `.to('cuda')` of the index vectors (models/ADNssd.py:329-382) when running the reference on CPU.
+    force=True: also on a box that HAS a GPU (the CPU baseline legs of bench.py run the reference on the host cores there)."""
+    if torch.cuda.is_available() and not force:
         yield
         return
     orig = torch.Tensor.to

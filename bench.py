@@ -1,20 +1,25 @@
 #!/usr/bin/env python
-"""bench.py - ADN-SSD mixer fwd+bwd tokens/s (BASELINE.json configs[1]) on N B200s of one node.
+"""bench.py - ADN-SSD mixer fwd+bwd tokens/s (BASELINE.json configs[1]) on N B200s of one node, plus the full-model legs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--d-model 32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--d-model 32] [--no-model]
 
 One "step" = one forward + backward of one ADN-SSD mixer (models/ADNssd.py::Mamba2 of the reference) over a
 synthetic batch B=16 of 128x128 token grids (262 144 tokens per GPU), bf16 I/O, random-init weights.
-  value  : tokens/s with u / dout already resident in HBM (CUDA events, max over ranks)
-  e2e    : the same through the public module call (adnm_unet_b200.Mamba2) with HOST buffers: pinned-host u and
-           dout copied H2D and out / du copied D2H inside the timed region, every step
-  roofline : dominant kernel of the step, timed per launch with CUDA events inside the library
-           (adn_prof_*), algorithmic bytes / time vs MEASURED_PEAKS.json
-  cpu_baseline : the CPU oracle port (oracle/adnssd_oracle.py, PyTorch fp32, all host threads) on a bounded sample
-N > 1 (torchrun): batch-sharded data parallel, one process per GPU, weak scaling; the mixer's parameter
-gradients are all-reduced over NCCL every step (the only exchange the path has).
-`--impl reference` times the reference's CPU algorithm (the oracle port; the reference is pure Python and
-/root/reference does not exist on the GPU box) on the host cores for the same metric.
+  value    : tokens/s with u / dout already resident in HBM (CUDA events, max over ranks)
+  e2e      : the same through the public module call (adnm_unet_b200.Mamba2) with HOST buffers: pinned-host u and
+             dout copied H2D and out / du copied D2H inside the timed region, every step
+  roofline : SURVEY.md 8(d): the step's compulsory HBM traffic (10*D bytes per token) / the step time vs MEASURED_PEAKS.json
+             (`frac`), the tensor-or-HBM bound t* next to it, the per-step DRAM traffic of the committed ncu capture
+             (`traffic`), and the dominant kernel's own DRAM throughput under `dominant_kernel`
+  cpu_baseline : the UNMODIFIED reference Mamba2 (git-ignored baseline/_ref, shims of adnm_unet_b200.refhost) on the box's
+             host cores, fp32, bounded sample;  gpu_baseline : the same module eagerly on the B200 (fp32 and bf16 autocast)
+  train / infer : BASELINE configs[2] / [3] through bench_model.py - full ADNM-UNet training step (B=32/GPU at 128x128,
+             batch-sharded DP over all N ranks, bucketed NCCL all-reduce overlapped with backward) and, at N=1, the
+             validate.py-shaped inference at 256x256 with on-device threshold counts; each next to the eager reference model.
+N > 1 (torchrun): batch-sharded data parallel, one process per GPU, weak scaling; the mixer's parameter gradients are
+all-reduced over NCCL every step (the only exchange the path has), captured inside the step's CUDA graph.
+`--impl reference` times the reference's own CPU implementation of the path (the unmodified modules; the closed-form oracle
+port only if baseline/_ref is absent) on the host cores for the same metric and config, plus configs[0] (full model on CPU).
 """
 import argparse
 import json
@@ -85,7 +90,7 @@ class ClockSampler:
 
 
 def oracle_step_fn(d_model, batch, threads):
-    """The CPU algorithm of the reference (oracle port), fwd + autograd bwd, fp32."""
+    """The CPU algorithm of the reference (oracle port), fwd + autograd bwd, fp32.  Fallback when baseline/_ref is absent."""
     import torch
     from oracle import adnssd_oracle as AO
     torch.set_num_threads(threads)
@@ -102,19 +107,74 @@ def oracle_step_fn(d_model, batch, threads):
     return step
 
 
-def time_cpu(d_model, batch, steps, warmup):
+def reference_step_fn(d_model, batch, threads):
+    """The UNMODIFIED reference module models/ADNssd.py::Mamba2 on the host cores, fp32, fwd + autograd bwd."""
+    import torch
+    from adnm_unet_b200 import refhost
+    torch.set_num_threads(threads)
+    ns = refhost.load_reference()
+    torch.manual_seed(0)
+    m = ns.ref_Mamba2(d_model=d_model, headdim=HEADDIM, d_state=D_STATE)
+    g = torch.Generator().manual_seed(1234)
+    u = torch.randn(batch, GRID * GRID, d_model, generator=g).requires_grad_(True)
+    dout = torch.randn(batch, GRID * GRID, d_model, generator=g)
+
+    def step():
+        m.zero_grad(set_to_none=True)
+        u.grad = None
+        with refhost.cuda_to_is_noop(force=True):
+            m(u, GRID, GRID).backward(dout)
+    return step
+
+
+def cpu_kind():
+    from adnm_unet_b200 import refhost
+    return "reference" if refhost.reference_available() else "port"
+
+
+def time_cpu(d_model, batch, steps, warmup, budget_s=None):
+    """tokens/s of the CPU arm; with `budget_s` the timed loop stops early once the budget is spent (>= 2 steps)."""
     threads = os.cpu_count() or 1
-    step = oracle_step_fn(d_model, batch, threads)
+    kind = cpu_kind()
+    step = (reference_step_fn if kind == "reference" else oracle_step_fn)(d_model, batch, threads)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
+    done = 0
     for _ in range(steps):
         step()
-    dt = (time.perf_counter() - t0) / steps
-    return batch * GRID * GRID / dt, dt, threads
+        done += 1
+        if budget_s is not None and done >= 2 and time.perf_counter() - t0 > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / done
+    return batch * GRID * GRID / dt, dt, threads, kind, done
 
 
-CPU_BATCH = 4        # samples per CPU step (the GPU arm runs B=16 per GPU; tokens/s is per token, so the metric is comparable)
+def full_model_cpu(steps=3, warmup=1):
+    """BASELINE configs[0]: the unmodified ADNM-UNet fwd + enRainfallLoss + bwd on the host cores, B=1, 5->20 frames, 128x128."""
+    import torch
+    from adnm_unet_b200 import refhost
+    if not refhost.reference_available():
+        return None
+    torch.set_num_threads(os.cpu_count() or 1)
+    with refhost.cuda_to_is_noop(force=True):
+        model = refhost.build_adnm_unet(128, dropin=False, seed=0)
+        loss_fn = refhost.reference_loss()
+        data = torch.rand(1, 25, 1, 128, 128, generator=torch.Generator().manual_seed(0))
+        ts = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            model.zero_grad(set_to_none=True)
+            loss_fn(model(data[:, :5]), data[:, 5:]).backward()
+            ts.append(time.perf_counter() - t0)
+    ts = sorted(ts[warmup:])
+    med = ts[len(ts) // 2]
+    return {"metric": "adnm_unet_fwd_bwd_seq_per_s_cpu", "value": 1.0 / med, "unit": "seq/s", "s_per_step": med,
+            "cores": os.cpu_count() or 1, "config": {"workload": "ADNM-UNet fwd + enRainfallLoss + bwd on CPU (BASELINE configs[0]): B=1, "
+                                                                 "5->20 frames at 128x128, standalone RMSNorm, fp32, unmodified reference"}}
+
+
+CPU_BATCH = B_PER_GPU        # the CPU arm runs the SAME batch as one GPU (B=16): same config, per-token metric
 
 
 def run_reference(args):
@@ -122,20 +182,26 @@ def run_reference(args):
     if rank != 0:
         return
     batch = CPU_BATCH
-    steps, warmup = max(1, min(args.steps, 300)), max(1, min(args.warmup, 5))     # <= ~20 s of CPU work
-    val, dt, threads = time_cpu(args.d_model, batch, steps, warmup)
-    sample = f"oracle port (PyTorch fp32 CPU), B={batch} x {GRID}x{GRID} tokens per step, {steps} steps"
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+    steps, warmup = max(2, min(args.steps, 40)), max(1, min(args.warmup, 3))
+    val, dt, threads, kind, done = time_cpu(args.d_model, batch, steps, warmup, budget_s=90.0)     # a few minutes at most
+    what = "unmodified reference Mamba2 (baseline/_ref)" if kind == "reference" else "oracle port (baseline/_ref absent)"
+    sample = f"{what}, PyTorch fp32 CPU, B={batch} x {GRID}x{GRID} tokens per step, {done} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"ADN-SSD mixer fwd+bwd (BASELINE configs[1]): D={args.d_model}, headdim={HEADDIM}, d_state={D_STATE}, "
                                f"B={B_PER_GPU}/GPU, {GRID}x{GRID} tokens",
-                   "note": f"CPU arm: each step is a bounded sample of that workload, B={batch} of the {B_PER_GPU} samples"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                   "note": "CPU arm: the reference's own CPU path on all host cores, same batch as one GPU of the GPU arm"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }
+    if not args.no_model:
+        fm = full_model_cpu()
+        if fm is not None:
+            line["full_model_cpu"] = fm
+    print(json.dumps(line))
 
 
 def run_ours(args):
@@ -154,6 +220,7 @@ def run_ours(args):
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its banner there)
         dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(torch.zeros(1, device=dev))      # communicator fully set up before any CUDA-graph capture
     lib = _lib.load()
     assert lib.adn_device_supported() == 1
 
@@ -208,8 +275,12 @@ def run_ours(args):
         with torch.cuda.graph(graph, pool=pool):
             out = mixer(u_static, GRID, GRID)
             out.backward(g_static)
-        # the 18 parameter gradients are views of ONE flat fp32 buffer (adnm_unet_b200/mixer.py): all-reduce it in one call
-        flat = torch.empty(0, dtype=torch.float32, device=dev).set_(params[0].grad.untyped_storage())
+            # the 18 parameter gradients are views of ONE flat fp32 buffer (adnm_unet_b200/mixer.py): all-reduce it in one call
+            flat = torch.empty(0, dtype=torch.float32, device=dev).set_(params[0].grad.untyped_storage())
+            if world > 1 and args.graph_nccl:
+                # NCCL is capturable: the all-reduce becomes a node of the step graph, so a data-parallel step is ONE
+                # cudaGraphLaunch (round 1 issued graph replay + 2 event records + stream wait + NCCL enqueue from Python)
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
         assert flat.numel() == sum(p.numel() for p in params), "flat gradient buffer layout changed"
         return graph, out.detach(), u_static.grad, flat
 
@@ -231,16 +302,18 @@ def run_ours(args):
             dist.all_reduce(flat, op=dist.ReduceOp.AVG)
             ev_comm[k].record(s_comm)
 
+    side_allreduce = world > 1 and not args.graph_nccl
+
     def step_resident(i):
         if graphs is None:
             return step_eager(i)
         k = i % N_INPUT_SETS
         graph, out, du, flat = graphs[k]
         cur = torch.cuda.current_stream()
-        if world > 1:
+        if side_allreduce:
             cur.wait_event(ev_comm[k])        # the previous all-reduce of this graph's gradient buffer has finished
         graph.replay()
-        if world > 1:
+        if side_allreduce:
             allreduce_async(k, flat, cur)
         return out, du
 
@@ -284,9 +357,11 @@ def run_ours(args):
             res = (out.detach(), u.grad)
         else:
             graph, out, du, flat = slot_graphs[k]
+            if side_allreduce:
+                cur.wait_event(ev_comm[k])
             graph.replay()
-            if world > 1:
-                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            if side_allreduce:
+                allreduce_async(k, flat, cur)      # side stream, as in step_resident (round 1 blocked the compute stream here)
             res = (out, du)
         ev_done[k].record(cur)
         keep[k] = res
@@ -303,6 +378,8 @@ def run_ours(args):
         cur = torch.cuda.current_stream()
         for k in range(NSLOT):
             cur.wait_event(ev_out[k])
+        if side_allreduce:
+            cur.wait_stream(s_comm)
 
     def barrier():
         if world > 1:
@@ -324,12 +401,21 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for i in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 2 * N_INPUT_SETS)      # every captured graph / input set replayed at least twice before timing
+    for i in range(n_warm):
         step_resident(i)
         step_e2e(i)
+    # clocks / throttle reasons sampled DURING the timed region: nvidia-smi needs ~0.2 s to produce its first line, so it is
+    # started under load (a second warm-up burst) and stopped right after the timed steps
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        t_end = time.perf_counter() + 0.5
+        i = 0
+        while time.perf_counter() < t_end:
+            step_resident(i)
+            i += 1
+        torch.cuda.synchronize()
     ms = timed(step_resident, args.steps, drain_resident)
     launches = launches_per_step * args.steps      # kernels of this library per step (counted on an eager step) x steps
     clocks = sampler.stop() if sampler else None
@@ -353,37 +439,152 @@ def run_ours(args):
     step_ms = ms / args.steps
     kernels = {k: {"ms_per_step": v[0] / nprof, "launches_per_step": v[1] / nprof, "share": v[0] / tot} for k, v in per.items()}
 
+    # ---- H2D-only probe: what the host side can feed this rank while every other rank does the same (explains e2e scaling)
+    def h2d_only(i):
+        with torch.no_grad():
+            slot_u[i % NSLOT].copy_(host_u[i % N_INPUT_SETS], non_blocking=True)
+            slot_g[i % NSLOT].copy_(host_g[i % N_INPUT_SETS], non_blocking=True)
+    ms_h2d = timed(h2d_only, min(args.steps, 50))
+    h2d_gbs = 2 * tokens * D * 2 * min(args.steps, 50) / (ms_h2d * 1e-3) / 1e9      # per rank, max-over-ranks time
+
+    # ---- like-for-like GPU baseline: the UNMODIFIED reference module, eager PyTorch on this B200 (rank 0 of a 1-GPU run)
+    gpu_base = None
+    if world == 1 and not args.no_model:
+        gpu_base = eager_reference_on_gpu(torch, dev, D, B, L)
+
+    # ---- full-model legs (BASELINE configs[2] at N ranks, configs[3] at N = 1)
+    model_legs = {}
+    if not args.no_model:
+        del graphs, slot_graphs
+        torch.cuda.empty_cache()
+        model_legs = full_model_legs(world, rank, load_peaks())
+
     if rank == 0:
         top_ms = per[top][0] / per[top][1]
         # dominant kernel: achieved = bytes it must move per launch / its mean launch time
         top_bytes = KERNEL_ALG_BYTES.get(top, lambda D, T: None)(D, tokens)
-        roof = {"bound": "hbm", "kernel": top, "achieved": (top_bytes / (top_ms * 1e-3) / 1e9) if top_bytes else None,
-                "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": load_traffic(top),
-                "kernel_ms_per_launch": top_ms, "kernel_share_of_step": per[top][0] / tot,
-                "step_achieved": alg_bytes_step / (step_ms * 1e-3) / 1e9, "step_algorithmic_bytes": alg_bytes_step}
-        roof["frac"] = (roof["achieved"] / hbm_peak) if roof["achieved"] else None
-        roof["step_frac"] = roof["step_achieved"] / hbm_peak
+        # roofline.achieved = the step's compulsory HBM traffic (10*D bytes per token: u, out, dout, u, du in
+        # bf16) / the measured step time; t* = max(HBM time of those bytes, tensor time of 3*F_fwd flops per token)
+        Di, GN, nh, CC, dip = _dims(D)
+        f_fwd = 2 * D * dip + 2 * GN * Di + 4 * Di * D + 15 * (Di + 2 * GN) + 18 * Di
+        t_hbm, t_tc = alg_bytes_step / (hbm_peak * 1e9), 3 * f_fwd * tokens / (tf_peak * 1e12)
+        achieved = alg_bytes_step / (step_ms * 1e-3) / 1e9
+        traffic = load_step_traffic()
+        roof = {"bound": "hbm", "kernel": f"whole fwd+bwd chain ({launches_per_step} launches per step)", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "frac": achieved / hbm_peak,
+                "algorithmic_bytes": alg_bytes_step, "traffic": traffic,
+                "traffic_over_algorithmic": (traffic / alg_bytes_step) if traffic else None,
+                "t_star_us": max(t_hbm, t_tc) * 1e6, "t_star_bound": "tensor" if t_tc > t_hbm else "hbm",
+                "frac_of_t_star": max(t_hbm, t_tc) / (step_ms * 1e-3),
+                "dominant_kernel": {"name": top, "ms_per_launch": top_ms, "share_of_step": per[top][0] / tot,
+                                    "own_bytes_per_launch": top_bytes, "own_GBps": (top_bytes / (top_ms * 1e-3) / 1e9) if top_bytes else None,
+                                    "own_frac_of_hbm_peak": (top_bytes / (top_ms * 1e-3) / 1e9 / hbm_peak) if top_bytes else None,
+                                    "ncu_dram_bytes_per_launch": load_traffic(top),
+                                    "note": "DRAM throughput of the kernel on the bytes its own design moves - NOT the roofline fraction"}}
         # bounded CPU sample (~10 s): the oracle port on every host core, CPU_BATCH samples per step
-        cpu_val, cpu_dt, cpu_threads = time_cpu(D, CPU_BATCH, 150, 3) if world == 1 and not args.no_cpu else (None, None, None)
+        cpu_val = None
+        if world == 1 and not args.no_cpu:
+            cpu_val, cpu_dt, cpu_threads, cpu_kind_, cpu_done = time_cpu(D, CPU_BATCH, 40, 1, budget_s=20.0)
         line = {
             "metric": METRIC, "value": world * tokens * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+            "steps": args.steps, "warmup": n_warm, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"ADN-SSD mixer fwd+bwd (BASELINE configs[1]): D={D}, headdim={HEADDIM}, d_state={D_STATE}, "
                                    f"B={B}/GPU, {GRID}x{GRID} tokens", "global_batch": B * world, "tokens_per_step": tokens * world,
-                       "parallelism": f"dp{world}", "grad_allreduce": "NCCL AVG of one flat fp32 buffer per step on a side stream (overlaps the next step)" if world > 1 else "none (1 GPU)", "launch": "cuda_graph_replay" if args.graph else "eager", "l2": f"{N_INPUT_SETS} rotating input sets (> L2) + ~1 GB of intermediates rewritten per step"},
+                       "parallelism": f"dp{world}", "grad_allreduce": ("none (1 GPU)" if world == 1 else "NCCL AVG of one flat fp32 buffer per step, captured inside the step's CUDA graph" if (args.graph and args.graph_nccl) else "NCCL AVG of one flat fp32 buffer per step on a side stream (overlaps the next step)"), "launch": "cuda_graph_replay" if args.graph else "eager", "l2": f"{N_INPUT_SETS} rotating input sets (> L2) + ~1 GB of intermediates rewritten per step"},
             "e2e": {"value": world * tokens * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": world * 2 * tokens * D * 2, "d2h_bytes_per_step": world * 2 * tokens * D * 2,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "h2d_only_GBps_per_rank": h2d_gbs,
+                    "note": "bound by the 2 x 33.5 MB per step and rank that cross PCIe in each direction; h2d_only is the host->device "
+                            "rate one rank sustains while all ranks copy at once (host memory / PCIe root share)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
         }
         if cpu_val is not None:
-            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
-                                    "sample": f"oracle port (PyTorch fp32, fwd + autograd bwd), B={CPU_BATCH} x {GRID}x{GRID} tokens per step, "
-                                              f"150 steps after 3 warm-ups, {cpu_dt * 1e3:.1f} ms/step"}
+            what = "unmodified reference Mamba2 (baseline/_ref)" if cpu_kind_ == "reference" else "oracle port (baseline/_ref absent)"
+            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": cpu_kind_,
+                                    "sample": f"{what}, PyTorch fp32, fwd + autograd bwd, B={CPU_BATCH} x {GRID}x{GRID} tokens per step, "
+                                              f"{cpu_done} steps after 1 warm-up, {cpu_dt * 1e3:.1f} ms/step"}
+        if gpu_base is not None:
+            line["gpu_baseline"] = gpu_base
+        line.update(model_legs)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def eager_reference_on_gpu(torch, dev, D, B, L, steps=10):
+    """The unmodified reference Mamba2 run eagerly on the B200 (its ten `.to('cuda')` index uploads per forward are real
+    here): the like-for-like GPU baseline of SURVEY.md 8(d).  fp32 (what the reference trains in) and bf16 autocast."""
+    from adnm_unet_b200 import refhost
+    if not refhost.reference_available():
+        return {"unavailable": "baseline/_ref not on this box"}
+    ns = refhost.load_reference()
+    torch.manual_seed(0)
+    m = ns.ref_Mamba2(d_model=D, headdim=HEADDIM, d_state=D_STATE).to(dev)
+    u = torch.randn(B, L, D, device=dev, requires_grad=True)
+    g = torch.randn(B, L, D, device=dev)
+    res = {"unit": UNIT, "what": "unmodified reference models/ADNssd.py::Mamba2, eager PyTorch on the same B200, same shape"}
+    for name, ac in (("fp32", False), ("bf16_autocast", True)):
+        def step():
+            m.zero_grad(set_to_none=True)
+            u.grad = None
+            if ac:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    o = m(u, GRID, GRID)
+                o.float().backward(g)
+            else:
+                m(u, GRID, GRID).backward(g)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res[name] = {"value": B * L / (ms * 1e-3), "ms_per_step": ms}
+    del m, u, g
+    torch.cuda.empty_cache()
+    return res
+
+
+def full_model_legs(world, rank, peaks):
+    """BASELINE configs[2] (training step, all ranks) and configs[3] (inference, 1 GPU) through bench_model.py."""
+    import torch
+    import bench_model
+    from adnm_unet_b200 import refhost
+    if not refhost.reference_available():
+        return {"train": {"unavailable": "baseline/_ref not on this box (python baseline/fetch_ref.py in the build container)"}}
+    pk = (peaks[0], load_sustained_tf())
+    out = {}
+    tr = bench_model.train_bench(batch=32, img=128, steps=8, warmup=3, variant="dropin", peaks=pk, init_dist=False)
+    if rank == 0:
+        out["train"] = tr
+    torch.cuda.empty_cache()
+    if world == 1:
+        ref = bench_model.train_bench(batch=32, img=128, steps=4, warmup=3, variant="reference", e2e=False, peaks=pk)
+        out["train"]["gpu_baseline"] = {"value": ref["value"], "unit": "seq/s", "ms_per_step": ref["ms_per_step"],
+                                        "what": "the same step with the reference's own Mamba2 / WTConv2d (eager PyTorch, bf16 autocast) on the same B200"}
+        torch.cuda.empty_cache()
+        inf = bench_model.infer_bench(batch=64, img=256, steps=3, warmup=1, variant="dropin")
+        torch.cuda.empty_cache()
+        iref = bench_model.infer_bench(batch=64, img=256, steps=2, warmup=1, variant="reference")
+        inf["gpu_baseline"] = {"value": iref["value"], "unit": "seq/s", "ms_per_step": iref["ms_per_step"],
+                               "what": "the reference's own modules, eager PyTorch bf16 autocast, same B200"}
+        out["infer"] = inf
+        torch.cuda.empty_cache()
+    return out
+
+
+def load_sustained_tf():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f).get("bf16_tflops_sustained", 1400.0)
+    return 1400.0
 
 
 # algorithmic HBM bytes per launch of each kernel (bf16 elements = 2 bytes), D = d_model, T = tokens; see DESIGN.md
@@ -425,15 +626,28 @@ class _AlgBytes(dict):
 KERNEL_ALG_BYTES = _AlgBytes()
 
 
+def _ncu_summary():
+    for name in ("r02_mixer_kernels.json", "r01_mixer_kernels.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.isfile(p):
+            with open(p) as f:
+                return json.load(f)
+    return None
+
+
 def load_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full summary."""
-    p = os.path.join(ROOT, "profiles", "r01_mixer_kernels.json")
-    if not os.path.isfile(p):
-        return None
-    with open(p) as f:
-        d = json.load(f)
-    e = d.get("kernels", {}).get(kernel)
+    d = _ncu_summary()
+    e = d.get("kernels", {}).get(kernel) if d else None
     return (e["dram_read_bytes"] + e["dram_write_bytes"]) if e else None
+
+
+def load_step_traffic():
+    """Sum of the ncu DRAM bytes over every launch of one fwd+bwd step (same committed capture)."""
+    d = _ncu_summary()
+    if not d:
+        return None
+    return float(sum(e["dram_read_bytes"] + e["dram_write_bytes"] for e in d.get("kernels", {}).values()))
 
 
 def main():
@@ -446,6 +660,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="issue every step through Python / autograd instead of replaying a captured CUDA graph")
+    ap.add_argument("--no-graph-nccl", dest="graph_nccl", action="store_false",
+                    help="N > 1: all-reduce on a side stream after each graph replay instead of inside the captured graph")
+    ap.add_argument("--no-model", action="store_true", help="skip the full-model legs (train / infer / gpu_baseline / configs[0])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
