@@ -56,6 +56,7 @@ struct EnvCfg {
   bool bwd_ws;        // ADN_BWD_WS=0     monolithic tile kernels for B1 / B2
   int du_dbg;         // ADN_DU_DBG       knock-out mask of k_bconv_du
   bool wide;          // ADN_WIDE=0       keeps d_model >= 64 on the CUDA-core generic path
+  int gemm_dbg;       // ADN_GEMM_DBG     knock-out mask of the tcgen05 GEMM (profiling: results are wrong when set)
 };
 const EnvCfg& env();
 

@@ -42,6 +42,7 @@ static EnvCfg& env_mut() {
     c.bwd_ws = flag("ADN_BWD_WS", true);
     c.du_dbg = num("ADN_DU_DBG");
     c.wide = flag("ADN_WIDE", true);
+    c.gemm_dbg = num("ADN_GEMM_DBG");
     return c;
   }();
   return cfg;
@@ -206,6 +207,7 @@ int adn_set_option(const char* name, int value) {
   else if (!strcmp(name, "wide")) c.wide = value != 0;
   else if (!strcmp(name, "rows_per_cta")) c.rows_per_cta = value;
   else if (!strcmp(name, "du_dbg")) c.du_dbg = value;
+  else if (!strcmp(name, "gemm_dbg")) c.gemm_dbg = value;
   else { set_error("adn_set_option: unknown option '%s'", name); return ADN_ERR_SHAPE; }
   return ADN_OK;
 }

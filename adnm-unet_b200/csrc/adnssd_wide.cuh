@@ -615,7 +615,7 @@ static int forward(const MixerDims& d, const AdnWeights& w, const bf16* u, bf16*
   }
   // (4a) S'^T[b] = mask . wx[b]^T Bc[b]   (M = Di, N = GN, K = L; both operands MN-major)
   {
-    const int splitk = pick_splitk(cdiv(d.Di, BM) * cdiv(d.GN, pick_bn(d.GN)) * d.B, L);
+    const int splitk = pick_splitk(cdiv(d.Di, BM) * cdiv(d.GN, pick_bn(d.GN, 1)) * d.B, L);
     if (splitk > 1) ADN_CHECK_CUDA(cudaMemsetAsync(S.ST, 0, (size_t)d.B * sS * sizeof(float), st));
     WIDE_GEMM(st, "tcgemm_state", d.Di, d.GN, L, mnmaj(W.wx, d.Di, (long long)L * d.Di), mnmaj(S.act + 2 * d.Di, d.CC, (long long)L * d.CC),
               0, NOOP, NOOP, Out{S.ST, d.GN, sS, splitk > 1 ? C_ATOMIC_F32 : C_F32}, d.B, splitk, nullptr, 1, W.status);
@@ -665,7 +665,7 @@ static int backward(const MixerDims& d, const AdnWeights& w, const bf16* u, cons
   }
   // dW_out = dout^T [yn | zc]   (reductions over all tokens: both operands MN-major, split-K, fp32 atomics)
   {
-    const int splitk = pick_splitk(cdiv(d.D, BM) * cdiv(d.Di, pick_bn(d.Di)), T);
+    const int splitk = pick_splitk(cdiv(d.D, BM) * cdiv(d.Di, pick_bn(d.Di, 1)), T);
     WIDE_GEMM(st, "tcgemm_dWout_y", d.D, d.Di, T, mnmaj(dout, d.D), mnmaj(W.yn, d.Di), 0, NOOP, NOOP,
               Out{W.acc.dWout, 2 * d.Di, 0, C_ATOMIC_F32}, 1, splitk, nullptr, 0, W.status);
     WIDE_GEMM(st, "tcgemm_dWout_z", d.D, d.Di, T, mnmaj(dout, d.D), mnmaj(S.act, d.CC), 0, NOOP, NOOP,
@@ -673,7 +673,7 @@ static int backward(const MixerDims& d, const AdnWeights& w, const bf16* u, cons
   }
   // dS'^T[b] = mask . dy[b]^T Cc[b]
   {
-    const int splitk = pick_splitk(cdiv(d.Di, BM) * cdiv(d.GN, pick_bn(d.GN)) * d.B, L);
+    const int splitk = pick_splitk(cdiv(d.Di, BM) * cdiv(d.GN, pick_bn(d.GN, 1)) * d.B, L);
     WIDE_GEMM(st, "tcgemm_dstate", d.Di, d.GN, L, mnmaj(W.dact + d.Di, d.CC, bA), mnmaj(Cc, d.CC, bA), 0, NOOP, NOOP,
               Out{W.dST, d.GN, sS, C_ATOMIC_F32}, d.B, splitk, nullptr, 1, W.status);
     { ADN_KERNEL("k_split_hilo", st); k_split_hilo<<<ew_grid((long long)d.B * sS), 256, 0, st>>>(W.dST, W.dS_hi, W.dS_lo, (long long)d.B * sS); }
@@ -707,7 +707,7 @@ static int backward(const MixerDims& d, const AdnWeights& w, const bf16* u, cons
   WIDE_GEMM(st, "tcgemm_du", T, d.D, d.dip, kmaj(W.draw, d.ldr), mnmaj(W.Win, d.D), 0, NOOP, NOOP, Out{du, d.D, 0, C_BF16}, 1, 1, nullptr, 0,
             W.status);
   {
-    const int splitk = pick_splitk(cdiv(d.dip, BM) * cdiv(d.D, pick_bn(d.D)), T);
+    const int splitk = pick_splitk(cdiv(d.dip, BM) * cdiv(d.D, pick_bn(d.D, 1)), T);
     WIDE_GEMM(st, "tcgemm_dWin", d.dip, d.D, T, mnmaj(W.draw, d.ldr), mnmaj(u, d.D), 0, NOOP, NOOP,
               Out{W.acc.dWin, d.D, 0, C_ATOMIC_F32}, 1, splitk, nullptr, 0, W.status);
   }

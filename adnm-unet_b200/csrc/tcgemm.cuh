@@ -7,16 +7,25 @@
 // * Operands are row-major global tensors in either orientation, no copies or transposes on the host side:
 //     K-major  : stored [rows = M or N][K], row pitch ld       (x @ W^T with W = [N][K]: in_proj, out_proj, readout ...)
 //     MN-major : stored [K][cols = M or N], row pitch ld       (reductions over tokens: state, weight gradients; x @ W)
-//   Both land in shared memory in the same un-swizzled "T8" core-matrix layout (sm100_utils.cuh) with 16-byte cp.async
-//   copies (zero-filled outside the matrix: ragged M / N / K need no padding), and only the UMMA descriptor differs.
+//   Both are fetched by TMA (cp.async.bulk.tensor, 128-byte swizzle, one elected thread, completion on an mbarrier) through
+//   tensor maps encoded per launch; boxes that reach outside the matrix are zero-filled by the hardware, so ragged M / N / K
+//   need no padding and sub-matrix views (row pitch > width) never read their neighbours.  K-major tiles are [rows][128 B],
+//   MN-major tiles [64 K rows][128 B] per 64-wide MN group; only the UMMA descriptor differs.  (Round-2 history: the first
+//   version staged un-swizzled tiles with 16-byte cp.async copies; knock-out timing showed those copies - 8 L1 tags per warp
+//   instruction - cost 200 of 395 us on the in_proj shape and capped a square 8192^3 GEMM at 207 TFLOP/s.)
 // * Up to two (A, B, K) segments accumulate into the same tile: [LN(y) | zc] @ W_out^T without a concatenated buffer, and
 //   fp32 states as bf16 hi + lo pairs.
 // * blockIdx.z = batch * splitk + split: per-sample GEMMs (state, readout) and split-K for the token reductions
 //   (fp32 atomics into a zeroed accumulator).
-// * CTA = 128 x BN tile (BN <= 128, multiple of 16), BK = 64, 3-stage cp.async ring; warps 0-3 produce, then drain the
-//   accumulator (TMEM lane quarter = warp), warp 4 issues the MMAs.  96 KB of shared memory: two CTAs per SM, so one CTA's
-//   epilogue overlaps the other's main loop.
+// * Persistent CTAs (one per SM) over 128 x BN tiles (BN <= 256, multiple of 16), BK = 64, 4-stage TMA ring; a producer
+//   lane, an MMA-issuing lane and four epilogue warps run concurrently, the accumulator double-buffered in TMEM (2 x BN of
+//   the 512 columns) so that a tile's epilogue overlaps the next tile's main loop.
+// * Epilogue: TMEM -> registers (alpha, parity mask, optional SiLU'(aux) factor) -> 128-byte-swizzled staging slab in
+//   shared memory -> TMA store (bf16 / fp32) or TMA reduce-add (split-K), 32 rows x 128 bytes per instruction, clipped to
+//   the matrix by the hardware.  (Thread-per-row global stores cost 107 of 157 us on the in_proj shape.)
 #pragma once
+#include <cuda.h>      // CUtensorMap (types only: cuTensorMapEncodeTiled is resolved through cudaGetDriverEntryPoint)
+
 #include "adn_common.cuh"
 #include "sm100_utils.cuh"
 
@@ -24,9 +33,10 @@ namespace adn {
 namespace tcg {
 using namespace adn::sm100;
 
-constexpr int BM = 128, BK = 64, STAGES = 3, LAG = 2, MAX_BN = 128;
+constexpr int BM = 128, BK = 64, STAGES = 4, MAX_BN = 256;
+constexpr int EPI_BUF_B = 4096, EPI_B = 4 * 2 * EPI_BUF_B;      // per epilogue warp: two 32-row x 128-byte staging slabs
 constexpr int A_TILE_B = BM * BK * 2;                    // 16 KB in either orientation
-constexpr int THREADS = 160;
+constexpr int THREADS = 192;      // 4 epilogue warps + MMA warp + TMA producer warp
 
 enum { C_BF16 = 0, C_F32 = 1, C_ATOMIC_F32 = 2 };
 
@@ -48,167 +58,238 @@ struct Args {
   int splitk, k_per_split; // split-K over segment 0 (nseg must be 1 when splitk > 1); k_per_split is a multiple of BK
   int* status;             // set to 1 on a pipeline time-out
   const bf16* aux; long long ld_aux, aux_bs;   // optional epilogue operand, indexed like C: C = acc * SiLU'(aux)   (conv backward:
-};                                            // the gradient w.r.t. the conv output becomes the gradient w.r.t. its input)
+                                              // the gradient w.r.t. the conv output becomes the gradient w.r.t. its input)
+  int a_bz[2], b_bz[2];    // 1: the operand of that segment has a batch dimension (else every batch reads the same matrix)
+  int dbg;                 // knock-outs for profiling (adn_set_option("gemm_dbg")): 1 no epilogue stores, 2 no operand loads, 4 no MMAs
+};
 
-__device__ __forceinline__ void cp16(uint32_t sdst, const void* gsrc, int nbytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(nbytes) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-
-// rows x chunks (8 bf16 each) of a row-major global matrix -> T8 tile [chunk][R][8].  128 producer threads; one warp
-// instruction covers 8 rows x 4 chunks: conflict-free 128-byte shared-memory runs, 64-byte global segments per row.
-__device__ __forceinline__ void load_t8(uint32_t sdst, const bf16* __restrict__ g, long long ld, int R, int nrows, int nchunks,
-                                        int rows_valid, int chunks_valid, int warp, int lane) {
-  const int r8 = lane & 7, cq = lane >> 3;
-  for (int rb = warp; rb * 8 < nrows; rb += 4) {
-    const int r = rb * 8 + r8;
-    const bool rok = r < rows_valid;
-    const bf16* src = g + (long long)(rok ? r : 0) * ld;
-    for (int c = cq; c < nchunks; c += 4) {
-      const bool ok = rok && c < chunks_valid;
-      cp16(sdst + (uint32_t)(c * R + r) * 16, ok ? (const void*)(src + c * 8) : (const void*)g, ok ? 16 : 0);
-    }
-  }
+// one TMA box: coordinates (c0 innermost, c1, c2 = batch) of a rank-3 tensor map -> shared memory, bytes counted on `bar`
+__device__ __forceinline__ void tma_load_3d(uint32_t sdst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(sdst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t ssrc, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"((uint64_t)map), "r"(ssrc), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t ssrc, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"((uint64_t)map), "r"(ssrc), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
 
+// Shared-memory matrix descriptors for the 128-byte swizzled tiles TMA writes (cute/atom/mma_traits_sm100.hpp,
+// make_umma_desc: canonical layouts in 16-byte units)
+//   K-major  Swizzle<3,4,3> o ((8,n),2):((8,SBO),1)        rows 128 B apart, 8-row groups SBO = 1024 B apart, LBO unused (1)
+//   MN-major Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO))   64 MN elements per 128-B row, K rows 128 B apart, 8-row K
+//            groups SBO = 1024 B apart, 64-wide MN groups LBO apart (= one 64 x 64 box = 8192 B)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;      // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;      // layout type SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint64_t desc_k_sw128(uint32_t tile, int ks) { return desc_sw128(tile + ks * 32, 16, 1024); }
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t tile, int ks) { return desc_sw128(tile + ks * 2048, 8192, 1024); }
+
+// Persistent CTA: tiles (batch x split, m tile, n tile; n fastest so that consecutive CTAs share the A tile in L2) are taken
+// round-robin.  Three warp roles run concurrently and hand work over through mbarriers only:
+//   warps 5-8  producers: cp.async ring (STAGES deep) that runs continuously across tile boundaries
+//   warp  4    MMA issuer: one elected lane; accumulators double-buffered in TMEM (2 x BN columns)
+//   warps 0-3  epilogue: drains accumulator buffer i & 1 (TMEM lane quarter = warp) while the MMAs of tile i + 1 run
 __global__ void __launch_bounds__(THREADS)
-k_tcgemm(const Args a) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full[STAGES], empty[STAGES], acc_full;
+k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_constant__ CUtensorMap mA0,
+         const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUtensorMap mB1,
+         const __grid_constant__ CUtensorMap mC) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = a.BN;
   const int stage_b = A_TILE_B + BN * BK * 2;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int batch = blockIdx.z / a.splitk, split = blockIdx.z % a.splitk;
-  // k-tile list: segment 0 restricted to this split's range, then segment 1
-  int kb0 = 0, ke0 = a.seg[0].K;
-  if (a.splitk > 1) { kb0 = split * a.k_per_split; ke0 = min(a.seg[0].K, kb0 + a.k_per_split); }
-  const int nk0 = ke0 > kb0 ? (ke0 - kb0 + BK - 1) / BK : 0;
-  const int nk1 = a.nseg > 1 ? (a.seg[1].K + BK - 1) / BK : 0;
-  const int nk = nk0 + nk1;
-  if (nk == 0) return;
   uint32_t tcols = 32;
   while ((int)tcols < BN) tcols <<= 1;
   if (tid == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
-    mbar_init(&acc_full, 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(&tmem_slot, tcols);
+  if (warp == 4) tmem_alloc(&tmem_slot, 2 * tcols);
+  if (warp == 5 && lane == 0) tma_prefetch_desc(&mC);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
-  const uint32_t s0 = smem_u32(smem);
+  const uint32_t s0 = (smem_u32(smem_raw) + 1023u) & ~1023u;      // 128-byte swizzle atoms: 1024-byte aligned tiles
   bool ok = true;
+  const int nk1 = a.nseg > 1 ? (a.seg[1].K + BK - 1) / BK : 0;
+  const int per_z = tiles_m * tiles_n;
 
-  if (warp < 4) {
-    // ---------------- producer
-    for (int it = 0; it < nk + LAG; ++it) {
-      if (it < nk) {
-        const int s = it % STAGES;
-        if (it >= STAGES) ok &= mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
-        const bool second = it >= nk0;      // scalar selects (no dynamic indexing of the kernel parameter struct)
-        const long long lda = second ? a.seg[1].lda : a.seg[0].lda, ldb = second ? a.seg[1].ldb : a.seg[0].ldb;
-        const int k0 = second ? (it - nk0) * BK : kb0 + it * BK;
-        const int kvalid = (second ? a.seg[1].K : ke0) - k0;                       // > 0
-        const bf16* A = second ? a.seg[1].A + (long long)batch * a.seg[1].a_bs : a.seg[0].A + (long long)batch * a.seg[0].a_bs;
-        const bf16* B = second ? a.seg[1].B + (long long)batch * a.seg[1].b_bs : a.seg[0].B + (long long)batch * a.seg[0].b_bs;
-        const uint32_t sa = s0 + s * stage_b, sb = sa + A_TILE_B;
-        if (!a.a_mn) load_t8(sa, A + (long long)m0 * lda + k0, lda, BM, BM, BK / 8, a.M - m0, (kvalid + 7) >> 3, warp, lane);
-        else         load_t8(sa, A + (long long)k0 * lda + m0, lda, BK, BK, BM / 8, kvalid, (a.M - m0 + 7) >> 3, warp, lane);
-        if (!a.b_mn) load_t8(sb, B + (long long)n0 * ldb + k0, ldb, BN, BN, BK / 8, a.N - n0, (kvalid + 7) >> 3, warp, lane);
-        else         load_t8(sb, B + (long long)k0 * ldb + n0, ldb, BK, BK, BN / 8, kvalid, (a.N - n0 + 7) >> 3, warp, lane);
-      }
-      cp_commit();
-      if (it >= LAG) {
-        cp_wait<LAG>();
-        fence_async_smem();
-        mbar_arrive1(&full[(it - LAG) % STAGES]);
-      }
-    }
-    // ---------------- epilogue: TMEM lane quarter `warp`, thread = output row
-    ok &= mbar_wait(&acc_full, 0);
-    tc_fence_after();
-    const int m = m0 + warp * 32 + lane;
-    const float alpha = a.alpha ? *a.alpha : 1.f;
-    const bool row_ok = m < a.M;
-    for (int c = 0; c < BN; c += 16) {
-      float v[16];
-      tmem_ld16(tmem_addr(tbase, warp * 32, c), v);
-      tmem_wait_ld();
-      const int n = n0 + c;
-      if (!row_ok || n >= a.N) continue;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        v[j] *= alpha;
-        if (a.parity_mask && ((m ^ (n + j)) & 1)) v[j] = 0.f;
-      }
-      const int nv = min(16, a.N - n);
-      if (a.aux != nullptr) {
-        const bf16* q = a.aux + (long long)batch * a.aux_bs + (long long)m * a.ld_aux + n;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nv) v[j] *= silu_gradf_(__bfloat162float(q[j]));
-      }
-      if (a.c_mode == C_BF16) {
-        bf16* p = (bf16*)a.C + (long long)batch * a.c_bs + (long long)m * a.ldc + n;
-        if (nv == 16 && ((uintptr_t)p & 15) == 0) {
-          const float lo[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
-          const float hi[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
-          reinterpret_cast<uint4*>(p)[0] = pack8(lo);
-          reinterpret_cast<uint4*>(p)[1] = pack8(hi);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) if (j < nv) p[j] = __float2bfloat16_rn(v[j]);
-        }
-      } else {
-        float* p = (float*)a.C + (long long)batch * a.c_bs + (long long)m * a.ldc + n;
-        if (a.c_mode == C_F32) {
-          if (nv == 16 && ((uintptr_t)p & 15) == 0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  // k-tile range of a tile's split
+#define TCG_DECODE(tile)                                                                   \
+  const int z = (tile) / per_z, mn = (tile) - z * per_z;                                  \
+  const int mt = mn / tiles_n, nt_ = mn - mt * tiles_n;                                   \
+  const int m0 = mt * BM, n0 = nt_ * BN;                                                  \
+  const int batch = z / a.splitk, split = z - batch * a.splitk;                           \
+  int kb0 = 0, ke0 = a.seg[0].K;                                                          \
+  if (a.splitk > 1) { kb0 = split * a.k_per_split; ke0 = min(a.seg[0].K, kb0 + a.k_per_split); } \
+  const int nk0 = (ke0 - kb0 + BK - 1) / BK;                                              \
+  const int nk = nk0 + nk1;
+
+  if (warp == 5) {
+    // ---------------- TMA producer (one lane)
+    if (lane == 0) {
+      tma_prefetch_desc(&mA0); tma_prefetch_desc(&mB0);
+      if (a.nseg > 1) { tma_prefetch_desc(&mA1); tma_prefetch_desc(&mB1); }
+      int it = 0;                                  // k-tile sequence number of this CTA, across tiles
+      for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+        TCG_DECODE(tile)
+        (void)split;
+        for (int kt = 0; kt < nk; ++kt, ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) ok &= mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
+          const bool second = kt >= nk0;
+          const int k0 = second ? (kt - nk0) * BK : kb0 + kt * BK;
+          const CUtensorMap* pa = second ? &mA1 : &mA0;
+          const CUtensorMap* pb = second ? &mB1 : &mB0;
+          const uint32_t sa = s0 + s * stage_b, sb = sa + A_TILE_B;
+          mbar_expect_tx(&full[s], (uint32_t)stage_b);
+          if (!(a.dbg & 2)) {
+            // split-K: a box may reach past this split's range into the next one's; harmless for K-major / MN-major alike
+            // because splits are whole multiples of BK (k_per_split % BK == 0)
+            const int za = batch * (second ? a.a_bz[1] : a.a_bz[0]), zb = batch * (second ? a.b_bz[1] : a.b_bz[0]);
+            if (!a.a_mn) tma_load_3d(sa, pa, k0, m0, za, &full[s]);
+            else { tma_load_3d(sa, pa, m0, k0, za, &full[s]); tma_load_3d(sa + 8192, pa, m0 + 64, k0, za, &full[s]); }
+            if (!a.b_mn) tma_load_3d(sb, pb, k0, n0, zb, &full[s]);
+            else
+              for (int q = 0; q < BN; q += 64) tma_load_3d(sb + q * 128, pb, n0 + q, k0, zb, &full[s]);
           } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (j < nv) p[j] = v[j];
+            asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full[s])), "r"((uint32_t)stage_b) : "memory");
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nv && !(a.parity_mask && ((m ^ (n + j)) & 1))) atomicAdd(p + j, v[j]);
         }
       }
     }
-  } else {
+  } else if (warp == 4) {
     // ---------------- MMA issuer (one lane)
     if (lane == 0) {
       const uint32_t idesc = make_idesc_rt(BM, BN, a.a_mn != 0, a.b_mn != 0);
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % STAGES;
-        ok &= mbar_wait(&full[s], (it / STAGES) & 1);
+      int it = 0, i = 0;
+      for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++i) {
+        TCG_DECODE(tile)
+        (void)m0; (void)n0; (void)batch; (void)split;
+        const int ab = i & 1;
+        if (i >= 2) ok &= mbar_wait(&acc_empty[ab], ((i >> 1) - 1) & 1);
         tc_fence_after();
-        const uint32_t sa = s0 + s * stage_b, sb = sa + A_TILE_B;
+        const uint32_t tacc = tbase + ab * tcols;
+        for (int kt = 0; kt < nk; ++kt, ++it) {
+          const int s = it % STAGES;
+          ok &= mbar_wait(&full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = s0 + s * stage_b, sb = sa + A_TILE_B;
 #pragma unroll
-        for (int ks = 0; ks < BK / 16; ++ks) {
-          const uint64_t da = a.a_mn ? desc_mnmajor(sa, BK, 0, ks * 16) : desc_kmajor(sa, BM, 0, ks * 16);
-          const uint64_t db = a.b_mn ? desc_mnmajor(sb, BK, 0, ks * 16) : desc_kmajor(sb, BN, 0, ks * 16);
-          umma(tbase, da, db, idesc, (it | ks) != 0);
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t da = a.a_mn ? desc_mn_sw128(sa, ks) : desc_k_sw128(sa, ks);
+            const uint64_t db = a.b_mn ? desc_mn_sw128(sb, ks) : desc_k_sw128(sb, ks);
+            if (!(a.dbg & 4)) umma(tacc, da, db, idesc, (kt | ks) != 0);
+          }
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        umma_commit(&acc_full[ab]);
       }
-      umma_commit(&acc_full);
     }
+  } else {
+    // ---------------- epilogue: TMEM lane quarter `warp`, thread = output row; slabs of 128 bytes per row leave through TMA
+    const float alpha = a.alpha ? *a.alpha : 1.f;
+    const uint32_t sbuf = s0 + STAGES * stage_b + warp * 2 * EPI_BUF_B;      // this warp's two staging slabs (1024-byte aligned)
+    const int cw = a.c_mode == C_BF16 ? 64 : 32;                             // columns per 128-byte slab
+    int i = 0, slab = 0;
+    for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++i) {
+      TCG_DECODE(tile)
+      (void)split; (void)nk;
+      const int ab = i & 1;
+      ok &= mbar_wait(&acc_full[ab], (i >> 1) & 1);
+      tc_fence_after();
+      const int row = warp * 32 + lane, m = m0 + row;
+      const uint32_t tacc = tbase + ab * tcols;
+      for (int c0 = 0; c0 < BN && n0 + c0 < a.N; c0 += cw, ++slab) {
+        const uint32_t sb = sbuf + (slab & 1) * EPI_BUF_B;
+        if (slab >= 2) {                       // the TMA store that last read this slab has finished reading shared memory
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {          // 16 accumulator columns per step
+          if (q * 16 >= cw) break;
+          float v[16];
+          tmem_ld16(tmem_addr(tacc, warp * 32, c0 + q * 16), v);
+          tmem_wait_ld();
+          const int n = n0 + c0 + q * 16;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            v[j] *= alpha;
+            if (a.parity_mask && ((m ^ (n + j)) & 1)) v[j] = 0.f;
+          }
+          if (a.aux != nullptr && m < a.M) {
+            const bf16* ax = a.aux + (long long)batch * a.aux_bs + (long long)m * a.ld_aux + n;
+            if (n + 16 <= a.N && ((uintptr_t)ax & 15) == 0) {      // two 16-byte loads per row instead of 16 scalar ones
+              float x[16];
+              unpack8(reinterpret_cast<const uint4*>(ax)[0], *reinterpret_cast<float(*)[8]>(x));
+              unpack8(reinterpret_cast<const uint4*>(ax)[1], *reinterpret_cast<float(*)[8]>(x + 8));
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] *= silu_gradf_(x[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n + j < a.N) v[j] *= silu_gradf_(__bfloat162float(ax[j]));
+            }
+          }
+          // row `lane` of the slab, 16-byte chunk index XOR (row & 7): the 128-byte swizzle the tensor map expects
+          if (a.c_mode == C_BF16) {
+            const float lo[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+            const float hi[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+            const uint4 p0 = pack8(lo), p1 = pack8(hi);
+            const int ch = q * 2;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + lane * 128 + (((ch) ^ (lane & 7)) << 4)), "r"(p0.x), "r"(p0.y), "r"(p0.z), "r"(p0.w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + lane * 128 + (((ch + 1) ^ (lane & 7)) << 4)), "r"(p1.x), "r"(p1.y), "r"(p1.z), "r"(p1.w) : "memory");
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + lane * 128 + (((q * 4 + t) ^ (lane & 7)) << 4)), "f"(v[4 * t]), "f"(v[4 * t + 1]), "f"(v[4 * t + 2]), "f"(v[4 * t + 3]) : "memory");
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0 && !(a.dbg & 1)) {
+          if (a.c_mode == C_ATOMIC_F32) tma_reduce_add_3d(&mC, sb, n0 + c0, m0 + warp * 32, batch);
+          else tma_store_3d(&mC, sb, n0 + c0, m0 + warp * 32, batch);
+          bulk_commit();
+        }
+      }
+      // this accumulator buffer may be overwritten by the MMAs of tile i + 2
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive1(&acc_empty[ab]);
+    }
+    if (lane == 0) bulk_wait_read<0>();      // shared memory must outlive the last TMA stores' reads
+    __syncwarp();
   }
+#undef TCG_DECODE
   if (!ok && a.status) *a.status = 1;
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tbase, tcols);
+  if (warp == 4) tmem_dealloc(tbase, 2 * tcols);
 }
 
 // ---------------------------------------------------------------- host side
@@ -222,31 +303,67 @@ struct Out {
   void* p; long long ld, bs; int mode;
 };
 
-static inline int pick_bn(int N) {
-  int r = (N + 15) / 16 * 16;
-  return r < MAX_BN ? r : MAX_BN;
+static inline int pick_bn(int N, int b_mn) {
+  // MN-major B: whole 64-wide swizzle groups (TMA zero-fills past N); K-major B: any multiple of 16 rows
+  const int g = b_mn ? 64 : 16;
+  const int r = (N + g - 1) / g * g;
+  if (r <= MAX_BN) return r;
+  // wider than one tile: 256 unless its zero-padded last tile wastes more than 1/8 of the work, then 128
+  const int pad256 = (N + 255) / 256 * 256 - N;
+  return pad256 * 8 <= N ? 256 : 128;
 }
 
-// C = alpha * (A0 . B0 [+ A1 . B1]);  batches > 1: per-sample GEMMs;  splitk > 1: atomics into a ZEROED fp32 C.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// Rank-3 bf16 tensor map of one operand: K-major [rows][K] -> dims (K, rows, batches), box (64, box_rows, 1);
+// MN-major [K][cols] -> dims (cols, K, batches), box (64, 64, 1).  128-byte swizzle, zero fill outside the matrix.
+static int make_operand_map(CUtensorMap* map, const char* name, Op o, int extent_mn, int K, int batches, int box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  ADN_REQUIRE(enc != nullptr, ADN_ERR_CUDA, "tcgemm %s: cuTensorMapEncodeTiled is not available from this driver", name);
+  const bool has_batch = batches > 1 && o.bs != 0;
+  cuuint64_t dims[3] = {(cuuint64_t)(o.mn ? extent_mn : K), (cuuint64_t)(o.mn ? K : extent_mn), (cuuint64_t)(has_batch ? batches : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)o.ld * 2, has_batch ? (cuuint64_t)o.bs * 2 : (cuuint64_t)o.ld * 2 * dims[1]};
+  cuuint32_t box[3] = {64, (cuuint32_t)(o.mn ? 64 : box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)o.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ADN_REQUIRE(r == CUDA_SUCCESS, ADN_ERR_CUDA, "tcgemm %s: cuTensorMapEncodeTiled failed (%d) dims %llu x %llu x %llu pitch %llu", name,
+              (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)strides[0]);
+  return ADN_OK;
+}
+
 struct Aux {
   const bf16* p; long long ld, bs;
 };
 static const Aux NOAUX = Aux{nullptr, 0, 0};
 
+// C = alpha * (A0 . B0 [+ A1 . B1]);  batches > 1: per-sample GEMMs;  splitk > 1: atomics into a ZEROED fp32 C.
 static int gemm(cudaStream_t st, const char* name, int M, int N, int K0, Op A0, Op B0, int K1, Op A1, Op B1, Out C,
                 int batches, int splitk, const float* alpha, int parity_mask, int* status, Aux aux = NOAUX) {
   ADN_REQUIRE(M > 0 && N > 0 && K0 > 0 && batches > 0, ADN_ERR_SHAPE, "tcgemm %s: empty problem", name);
   ADN_REQUIRE(K1 == 0 || (A1.mn == A0.mn && B1.mn == B0.mn), ADN_ERR_SHAPE, "tcgemm %s: segments must share orientation", name);
   ADN_REQUIRE(splitk == 1 || (K1 == 0 && C.mode == C_ATOMIC_F32), ADN_ERR_SHAPE, "tcgemm %s: split-K needs one segment and an atomic fp32 output", name);
-  // 16-byte cp.async granularity: pitches and the contiguous extent in units of 8 bf16
+  // TMA granularity: 16-byte aligned bases, row pitches and batch strides
   ADN_REQUIRE(A0.ld % 8 == 0 && B0.ld % 8 == 0 && (K1 == 0 || (A1.ld % 8 == 0 && B1.ld % 8 == 0)), ADN_ERR_SHAPE, "tcgemm %s: row pitches must be multiples of 8", name);
+  ADN_REQUIRE(A0.bs % 8 == 0 && B0.bs % 8 == 0 && A1.bs % 8 == 0 && B1.bs % 8 == 0, ADN_ERR_SHAPE, "tcgemm %s: batch strides must be multiples of 8", name);
   ADN_REQUIRE(((uintptr_t)A0.p | (uintptr_t)B0.p | (uintptr_t)A1.p | (uintptr_t)B1.p) % 16 == 0, ADN_ERR_SHAPE, "tcgemm %s: operands must be 16-byte aligned", name);
-  ADN_REQUIRE((A0.mn || K0 % 8 == 0) && (B0.mn || K0 % 8 == 0) && (K1 % 8 == 0 || (A1.mn && B1.mn)), ADN_ERR_SHAPE, "tcgemm %s: K-major operands need K %% 8 == 0", name);
   Args a;
   a.seg[0] = Seg{A0.p, A0.ld, A0.bs, B0.p, B0.ld, B0.bs, K0};
   a.seg[1] = Seg{A1.p, A1.ld, A1.bs, B1.p, B1.ld, B1.bs, K1};
   a.nseg = K1 > 0 ? 2 : 1;
-  a.M = M; a.N = N; a.BN = pick_bn(N);
+  a.M = M; a.N = N; a.BN = pick_bn(N, B0.mn);
   a.a_mn = A0.mn; a.b_mn = B0.mn;
   a.C = C.p; a.ldc = C.ld; a.c_bs = C.bs; a.c_mode = C.mode;
   a.alpha = alpha; a.parity_mask = parity_mask;
@@ -255,15 +372,52 @@ static int gemm(cudaStream_t st, const char* name, int M, int N, int K0, Op A0, 
   a.splitk = cdiv(K0, a.k_per_split);
   a.status = status;
   a.aux = aux.p; a.ld_aux = aux.ld; a.aux_bs = aux.bs;
-  const size_t smem = (size_t)STAGES * (A_TILE_B + a.BN * BK * 2);
+  a.a_bz[0] = batches > 1 && A0.bs != 0; a.b_bz[0] = batches > 1 && B0.bs != 0;
+  a.a_bz[1] = batches > 1 && A1.bs != 0; a.b_bz[1] = batches > 1 && B1.bs != 0;
+  a.dbg = env().gemm_dbg;
+  CUtensorMap mA0, mB0, mA1, mB1;
+  int rc = make_operand_map(&mA0, name, A0, M, K0, batches, BM);
+  if (rc) return rc;
+  rc = make_operand_map(&mB0, name, B0, N, K0, batches, a.BN);
+  if (rc) return rc;
+  if (K1 > 0) {
+    rc = make_operand_map(&mA1, name, A1, M, K1, batches, BM);
+    if (rc) return rc;
+    rc = make_operand_map(&mB1, name, B1, N, K1, batches, a.BN);
+    if (rc) return rc;
+  } else {
+    mA1 = mA0; mB1 = mB0;
+  }
+  // output map: dims (N, M, batches), box (128 bytes of columns, 32 rows, 1), 128-byte swizzle; stores are clipped to it
+  CUtensorMap mC;
+  {
+    EncodeTiledFn enc = encode_tiled_fn();
+    const bool bf = C.mode == C_BF16;
+    const int es = bf ? 2 : 4;
+    ADN_REQUIRE(((uintptr_t)C.p % 16) == 0 && (C.ld * es) % 16 == 0 && (C.bs * es) % 16 == 0, ADN_ERR_SHAPE,
+                "tcgemm %s: output base / row pitch / batch stride must be 16-byte aligned", name);
+    const bool has_batch = batches > 1 && C.bs != 0;
+    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)(has_batch ? batches : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)C.ld * es, has_batch ? (cuuint64_t)C.bs * es : (cuuint64_t)C.ld * es * M};
+    cuuint32_t box[3] = {(cuuint32_t)(128 / es), 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&mC, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, C.p, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ADN_REQUIRE(r == CUDA_SUCCESS, ADN_ERR_CUDA, "tcgemm %s: cuTensorMapEncodeTiled (output) failed (%d)", name, (int)r);
+    ADN_REQUIRE(batches == 1 || has_batch, ADN_ERR_SHAPE, "tcgemm %s: a batched GEMM needs a batch stride on its output", name);
+  }
+  const size_t smem = (size_t)STAGES * (A_TILE_B + a.BN * BK * 2) + EPI_B + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    ADN_CHECK_CUDA(cudaFuncSetAttribute(k_tcgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * (A_TILE_B + MAX_BN * BK * 2)));
+    ADN_CHECK_CUDA(cudaFuncSetAttribute(k_tcgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * (A_TILE_B + MAX_BN * BK * 2) + EPI_B + 1024));
     attr_done = true;
   }
-  dim3 grid(cdiv(M, BM), cdiv(N, a.BN), batches * a.splitk);
-  ADN_REQUIRE(grid.y <= 65535 && grid.z <= 65535, ADN_ERR_SHAPE, "tcgemm %s: grid too large", name);
-  { ADN_KERNEL(name, st); k_tcgemm<<<grid, THREADS, smem, st>>>(a); }
+  const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, a.BN);
+  const long long tiles = (long long)tiles_m * tiles_n * batches * a.splitk;
+  ADN_REQUIRE(tiles < (1LL << 31), ADN_ERR_SHAPE, "tcgemm %s: too many tiles", name);
+  const int grid = (int)(tiles < (long long)sm_count() ? tiles : (long long)sm_count());      // persistent: one CTA per SM
+  { ADN_KERNEL(name, st); k_tcgemm<<<grid, THREADS, smem, st>>>(a, tiles_m, tiles_n, (int)tiles, mA0, mB0, mA1, mB1, mC); }
   return ADN_OK;
 }
 

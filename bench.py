@@ -17,7 +17,7 @@ synthetic batch B=16 of 128x128 token grids (262 144 tokens per GPU), bf16 I/O, 
              batch-sharded DP over all N ranks, bucketed NCCL all-reduce overlapped with backward) and, at N=1, the
              validate.py-shaped inference at 256x256 with on-device threshold counts; each next to the eager reference model.
 N > 1 (torchrun): batch-sharded data parallel, one process per GPU, weak scaling; the mixer's parameter gradients are
-all-reduced over NCCL every step (the only exchange the path has), captured inside the step's CUDA graph.
+all-reduced over NCCL every step (the only exchange the path has) on a side stream that overlaps the next step's kernels.
 `--impl reference` times the reference's own CPU implementation of the path (the unmodified modules; the closed-form oracle
 port only if baseline/_ref is absent) on the host cores for the same metric and config, plus configs[0] (full model on CPU).
 """
@@ -219,8 +219,17 @@ def run_ours(args):
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its banner there)
-        dist.init_process_group("nccl", device_id=dev)
-        dist.all_reduce(torch.zeros(1, device=dev))      # communicator fully set up before any CUDA-graph capture
+        # NCCL prints its version banner on stdout when the communicator is created; stdout must stay the ONE JSON line
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))      # communicator fully set up before any CUDA-graph capture
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     lib = _lib.load()
     assert lib.adn_device_supported() == 1
 
@@ -257,6 +266,14 @@ def run_ours(args):
     # then issues one cudaGraphLaunch per step instead of ~15 launches through Python / autograd).
     pool = torch.cuda.graph_pool_handle() if args.graph else None
 
+    # Data-parallel step as ONE cudaGraphLaunch with the gradient all-reduce overlapped: graph k copies its flat gradient
+    # buffer (50 KB) into a pre-allocated staging buffer at its end, and all-reduces the staging buffer of the PREVIOUS step
+    # on a forked branch that runs beside its own kernels (an all-reduce placed after the kernels of the same graph measured
+    # 0.312 ms / step at N = 2: its latency is exposed; a Python-issued side-stream all-reduce 0.294 ms).
+    n_grad = sum(p.numel() for p in params)
+    stage = [torch.zeros(n_grad, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    cap_count = [0]
+
     def capture(u_static, g_static):
         u_static.requires_grad_(True)
         s = torch.cuda.Stream(device=dev)
@@ -272,15 +289,23 @@ def run_ours(args):
         for p in params:
             p.grad = None
         graph = torch.cuda.CUDAGraph()
+        k = cap_count[0]
+        cap_count[0] += 1
         with torch.cuda.graph(graph, pool=pool):
+            in_graph = world > 1 and args.graph_nccl
+            if in_graph:      # forked branch: all-reduce of the previous step's staged gradients, beside this step's kernels
+                cur = torch.cuda.current_stream()
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    dist.all_reduce(stage[(k + 1) % 2], op=dist.ReduceOp.AVG)
             out = mixer(u_static, GRID, GRID)
             out.backward(g_static)
-            # the 18 parameter gradients are views of ONE flat fp32 buffer (adnm_unet_b200/mixer.py): all-reduce it in one call
+            # the 18 parameter gradients are views of ONE flat fp32 buffer (adnm_unet_b200/mixer.py)
             flat = torch.empty(0, dtype=torch.float32, device=dev).set_(params[0].grad.untyped_storage())
-            if world > 1 and args.graph_nccl:
-                # NCCL is capturable: the all-reduce becomes a node of the step graph, so a data-parallel step is ONE
-                # cudaGraphLaunch (round 1 issued graph replay + 2 event records + stream wait + NCCL enqueue from Python)
-                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            if in_graph:
+                cur.wait_stream(side)                      # join: the previous all-reduce is done before ...
+                stage[k % 2].copy_(flat)                   # ... this step's gradients are staged for the next graph
         assert flat.numel() == sum(p.numel() for p in params), "flat gradient buffer layout changed"
         return graph, out.detach(), u_static.grad, flat
 
@@ -320,6 +345,9 @@ def run_ours(args):
     def drain_resident():
         if world > 1:
             torch.cuda.current_stream().wait_stream(s_comm)
+            if args.graph and args.graph_nccl:             # the last step's staged gradients (inside the timed region)
+                dist.all_reduce(stage[0], op=dist.ReduceOp.AVG)
+                dist.all_reduce(stage[1], op=dist.ReduceOp.AVG)
 
     # ---- end-to-end: host buffers in, host buffers out, every step.  Copies run on their own streams so that the H2D of
     # step i+1 and the D2H of step i-1 overlap the kernels of step i (double-buffered device staging slots).
@@ -410,12 +438,10 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-        t_end = time.perf_counter() + 0.5
-        i = 0
-        while time.perf_counter() < t_end:
-            step_resident(i)
-            i += 1
-        torch.cuda.synchronize()
+    for i in range(1500):                 # the SAME number of steps on every rank (the steps contain collectives)
+        step_resident(i)
+    drain_resident()
+    torch.cuda.synchronize()
     ms = timed(step_resident, args.steps, drain_resident)
     launches = launches_per_step * args.steps      # kernels of this library per step (counted on an eager step) x steps
     clocks = sampler.stop() if sampler else None
@@ -491,7 +517,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"ADN-SSD mixer fwd+bwd (BASELINE configs[1]): D={D}, headdim={HEADDIM}, d_state={D_STATE}, "
                                    f"B={B}/GPU, {GRID}x{GRID} tokens", "global_batch": B * world, "tokens_per_step": tokens * world,
-                       "parallelism": f"dp{world}", "grad_allreduce": ("none (1 GPU)" if world == 1 else "NCCL AVG of one flat fp32 buffer per step, captured inside the step's CUDA graph" if (args.graph and args.graph_nccl) else "NCCL AVG of one flat fp32 buffer per step on a side stream (overlaps the next step)"), "launch": "cuda_graph_replay" if args.graph else "eager", "l2": f"{N_INPUT_SETS} rotating input sets (> L2) + ~1 GB of intermediates rewritten per step"},
+                       "parallelism": f"dp{world}", "grad_allreduce": ("none (1 GPU)" if world == 1 else "NCCL AVG of one flat fp32 buffer per step inside the step's CUDA graph, pipelined: a forked branch all-reduces the previous step's staged gradients beside this step's kernels" if (args.graph and args.graph_nccl) else "NCCL AVG of one flat fp32 buffer per step on a side stream (overlaps the next step)"), "launch": "cuda_graph_replay" if args.graph else "eager", "l2": f"{N_INPUT_SETS} rotating input sets (> L2) + ~1 GB of intermediates rewritten per step"},
             "e2e": {"value": world * tokens * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": world * 2 * tokens * D * 2, "d2h_bytes_per_step": world * 2 * tokens * D * 2,
                     "ms_per_step": ms_e2e / args.steps,
@@ -509,8 +535,13 @@ def run_ours(args):
             line["gpu_baseline"] = gpu_base
         line.update(model_legs)
         print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # leave without tearing NCCL down: a communicator destroyed while CUDA graphs / side streams still reference it has hung
+        # at exit (seen with captured collectives); every rank has printed / finished its work after this barrier
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def eager_reference_on_gpu(torch, dev, D, B, L, steps=10):
@@ -639,7 +670,7 @@ def load_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full summary."""
     d = _ncu_summary()
     e = d.get("kernels", {}).get(kernel) if d else None
-    return (e["dram_read_bytes"] + e["dram_write_bytes"]) if e else None
+    return ((e["dram_read_bytes"] + e["dram_write_bytes"]) / max(1, e.get("launches", 1))) if e else None
 
 
 def load_step_traffic():
@@ -660,8 +691,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="issue every step through Python / autograd instead of replaying a captured CUDA graph")
-    ap.add_argument("--no-graph-nccl", dest="graph_nccl", action="store_false",
-                    help="N > 1: all-reduce on a side stream after each graph replay instead of inside the captured graph")
+    ap.add_argument("--graph-nccl", dest="graph_nccl", action="store_true",
+                    help="N > 1: capture the gradient all-reduce inside the step graph (pipelined on a forked branch) instead of "
+                         "issuing it on a side stream after each replay.  Measured SLOWER at N = 2 (0.309 vs 0.294 ms / step; a "
+                         "plain in-graph all-reduce after the kernels 0.312) and the process hung in destroy_process_group with the "
+                         "captured collectives alive, so the side stream is the default")
     ap.add_argument("--no-model", action="store_true", help="skip the full-model legs (train / infer / gpu_baseline / configs[0])")
     args = ap.parse_args()
     if args.impl == "reference":

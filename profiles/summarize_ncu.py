@@ -34,21 +34,27 @@ def main(rep, out, command="python profiles/run_mixer_once.py (D=32, B=16, 128x1
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
-    kernels = {}
-    for r in rows[2:]:
+    launches, kernels = [], {}
+    for n, r in enumerate(rows[2:]):
         name = re.sub(r"^void ", "", r[idx["Kernel Name"]])
         short = re.match(r"(?:\w+::)*(\w+)", name).group(1)
-        e = {"signature": name[:120]}
+        e = {"launch": n, "kernel": short, "signature": name[:120]}
         for m, key in METRICS.items():
             if m in idx and r[idx[m]] not in ("", "n/a"):
                 v = float(r[idx[m]].replace(",", ""))
                 e[key] = v * UNIT_SCALE.get(units[idx[m]], 1.0)
-        kernels[short] = e
-    json.dump({"source": rep, "command": command,
-               "ncu": "--set full --clock-control none --import-source on", "kernels": kernels}, open(out, "w"), indent=1)
-    for k, e in kernels.items():
-        print(f"{k:20s} {e.get('time_us', 0):8.1f} us  dram {(e.get('dram_read_bytes', 0) + e.get('dram_write_bytes', 0)) / 1e6:7.1f} MB"
-              f"  {e.get('dram_pct_of_peak', 0):5.1f}% dram  {e.get('warps_active_pct', 0):5.1f}% warps  {e.get('tensor_pipe_active_pct', 0):4.1f}% tensor")
+        launches.append(e)      # EVERY launch, in order (round 1 keyed by kernel name and kept only the last launch of each)
+        k = kernels.setdefault(short, {"launches": 0, "time_us": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0})
+        k["launches"] += 1
+        for key in ("time_us", "dram_read_bytes", "dram_write_bytes"):
+            k[key] += e.get(key, 0.0)
+    json.dump({"source": rep, "command": command, "ncu": "--set full --clock-control none --import-source on",
+               "note": "`launches`: every captured launch in order; `kernels`: sums over the launches of each kernel name",
+               "launches": launches, "kernels": kernels}, open(out, "w"), indent=1)
+    for e in launches:
+        print(f"{e['launch']:3d} {e['kernel']:20s} {e.get('time_us', 0):8.1f} us  dram {(e.get('dram_read_bytes', 0) + e.get('dram_write_bytes', 0)) / 1e6:7.1f} MB"
+              f"  {e.get('dram_pct_of_peak', 0):5.1f}% dram  {e.get('warps_active_pct', 0):5.1f}% warps  {e.get('tensor_pipe_active_pct', 0):4.1f}% tensor"
+              f"  {e.get('issue_active_pct', 0):4.1f}% issue")
 
 
 if __name__ == "__main__":
