@@ -30,6 +30,17 @@ class AdnWeightGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in MIXER_FIELDS]
 
 
+class AdnFfnShape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "H", "W", "D", "C4", "dtype")]
+
+
+FFN_FIELDS = ("w_in", "b_in", "w_dw", "b_dw", "w_out", "b_out")
+
+
+class AdnFfnWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in FFN_FIELDS]
+
+
 class WtShape(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "C", "H", "W", "k", "levels", "has_bias", "dtype")]
 
@@ -58,6 +69,17 @@ EXPORTS = {
     "adn_sumsq_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "adn_adamw_flat": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 5 +
                        [C.c_int32, C.c_float, C.c_float, C.c_void_p]),
+    "adn_rmsnorm_forward": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "adn_rmsnorm_backward": (C.c_int, [C.c_void_p] * 9 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "adn_residual_forward": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "adn_residual_backward": (C.c_int, [C.c_void_p] * 12 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "adn_ffn_workspace_bytes": (C.c_int, [C.POINTER(AdnFfnShape)] + [C.POINTER(C.c_size_t)] * 3),
+    "adn_ffn_forward": (C.c_int, [C.POINTER(AdnFfnShape), C.POINTER(AdnFfnWeights)] + [C.c_void_p] * 5),
+    "adn_ffn_backward": (C.c_int, [C.POINTER(AdnFfnShape), C.POINTER(AdnFfnWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(AdnFfnWeights), C.c_void_p, C.c_void_p]),
+    "adn_linear_workspace_bytes": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "adn_linear_forward": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "adn_linear_backward": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "adn_last_error": (C.c_char_p, []),
     "adn_abi_version": (C.c_int, []),
     "adn_device_supported": (C.c_int, []),

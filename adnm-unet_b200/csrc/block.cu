@@ -1,0 +1,671 @@
+// The ADNM-UNet `Block` around the mixer (models/ADNMUNet.py:115-165), kept token-major (B, L, C) from end to end:
+//   x1 = beta1 x + beta2 mixer(scale1 RMSNorm(x) + shift1)              residual mix          (:149-152)
+//   x2 = (beta1 x1 + beta2 FFN(scale2 RMSNorm(x1) + shift2)) gamma      residual mix + gamma  (:155-161; beta3/4 alias beta1/2)
+//   out = x2 W_o^T + b_o  when dim != out_dim                            Linear                (:162-163)
+// FFN = FeedForward (models/model_untils.py:172-197): 1x1 conv D -> C4 = 4D, depthwise 3x3 (+bias, zero padding) on the C4
+// channels, gelu(first half) * sigmoid(second half), 1x1 conv C4/2 -> D.  The reference permutes to NCHW and back around it
+// (models/ADNMUNet.py:158); here the 1x1 convs are GEMMs over tokens and the depthwise conv runs channels-last, so no
+// layout change exists anywhere in the Block.
+// bf16 activations: the GEMMs (project_in / project_out / Linear and their data and weight gradients) run on the tensor
+// cores through the tcgen05 GEMM of tcgemm.cuh (bias in its epilogue); fp32 activations (the 1e-4 check mode) and shapes
+// whose rows are not whole 16-byte pieces use the CUDA-core GEMMs of adnssd_generic.cuh.  Same kernels between the GEMMs.
+#include "adn_common.cuh"
+#include "adnssd_generic.cuh"
+#include "tcgemm.cuh"
+
+namespace adn {
+namespace blk {
+
+static inline int ew_grid(long long n) {
+  long long b = (n + 255) / 256;
+  long long cap = (long long)sm_count() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ---------------------------------------------------------------- residual mix
+// out = (b1 x + b2 y) * gamma[c]      (gamma NULL: no channel scale)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_residual_fwd(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ b1p, const float* __restrict__ b2p,
+               const float* __restrict__ gamma, T* __restrict__ out, long long n4, int D) {
+  const float b1 = *b1p, b2 = *b2p;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float a[4], b[4], g[4] = {1.f, 1.f, 1.f, 1.f}, o[4];
+    ld4(x + i * 4, a);
+    ld4(y + i * 4, b);
+    if (gamma) ld4(gamma + (int)((i * 4) % D), g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = fmaf(b1, a[j], b2 * b[j]) * g[j];
+    st4(out + i * 4, o);
+  }
+}
+
+// dx = b1 gamma g, dy = b2 gamma g; d beta1 = <g gamma, x>, d beta2 = <g gamma, y> (accumulated in fp64: sums that cancel),
+// dgamma[c] = sum_t g (b1 x + b2 y).  A warp owns `tpw` consecutive tokens; lanes stride over channels, 4 at a time.
+constexpr int RES_DG_MAX = 4;      // dgamma partial sums live in registers for D <= 512, else shared-memory atomics per token
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_residual_bwd(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ g, const float* __restrict__ b1p,
+               const float* __restrict__ b2p, const float* __restrict__ gamma, T* __restrict__ dx, T* __restrict__ dy,
+               double* __restrict__ acc2, float* __restrict__ dgamma, long long Ttok, int tpw, int D) {
+  extern __shared__ float sg[];      // [D] block-local dgamma
+  if (gamma) {
+    for (int i = threadIdx.x; i < D; i += blockDim.x) sg[i] = 0.f;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float b1 = *b1p, b2 = *b2p;
+  const long long t0 = ((long long)blockIdx.x * 8 + warp) * tpw;
+  const bool regs = D <= 128 * RES_DG_MAX;
+  float dgr[RES_DG_MAX][4] = {};
+  double a1 = 0.0, a2 = 0.0;
+  for (long long t = t0; t < min(Ttok, t0 + (long long)tpw); ++t) {
+    float s1 = 0.f, s2 = 0.f;
+    int k = 0;
+    for (int c = lane * 4; c < D; c += 128, ++k) {
+      float xv[4], yv[4], gv[4], ga[4] = {1.f, 1.f, 1.f, 1.f}, ox[4], oy[4];
+      ld4(x + t * D + c, xv); ld4(y + t * D + c, yv); ld4(g + t * D + c, gv);
+      if (gamma) ld4(gamma + c, ga);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gg = gv[j] * ga[j];
+        ox[j] = b1 * gg;
+        oy[j] = b2 * gg;
+        s1 = fmaf(gg, xv[j], s1);
+        s2 = fmaf(gg, yv[j], s2);
+        if (gamma) {
+          const float dgv = gv[j] * fmaf(b1, xv[j], b2 * yv[j]);
+          if (regs) dgr[k < RES_DG_MAX ? k : 0][j] += dgv; else atomicAdd(&sg[c + j], dgv);
+        }
+      }
+      st4(dx + t * D + c, ox);
+      st4(dy + t * D + c, oy);
+    }
+    a1 += (double)s1;
+    a2 += (double)s2;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if (lane == 0) { atomicAdd(acc2, a1); atomicAdd(acc2 + 1, a2); }
+  if (gamma) {
+    if (regs) {
+      int k = 0;
+      for (int c = lane * 4; c < D; c += 128, ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&sg[c + j], dgr[k < RES_DG_MAX ? k : 0][j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x)
+      if (sg[i] != 0.f) atomicAdd(dgamma + i, sg[i]);
+  }
+}
+
+__global__ void k_store_acc2(const double* __restrict__ acc2, float* __restrict__ d1, float* __restrict__ d2) {
+  if (threadIdx.x == 0) { *d1 = (float)acc2[0]; *d2 = (float)acc2[1]; }
+}
+
+// ---------------------------------------------------------------- small helpers
+__global__ void k_to_bf16(const float* __restrict__ a, bf16* __restrict__ oa, long long na, const float* __restrict__ b,
+                          bf16* __restrict__ ob, long long nb) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += stride) {
+    if (i < na) oa[i] = __float2bfloat16_rn(a[i]);
+    else ob[i - na] = __float2bfloat16_rn(b[i - na]);
+  }
+}
+
+template <typename T>
+__global__ void k_bias_add(T* __restrict__ y, const float* __restrict__ bias, long long n, int N) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) stf(y + i, ldf(y + i) + bias[(int)(i % N)]);
+}
+
+// out[n] += sum_t X[t][n]   (out zeroed by the caller).  block = 8 warps x 32 lanes; lane -> 4 columns; grid (ceil(N/128), chunks)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_colsum(const T* __restrict__ X, long long ld, float* __restrict__ out, long long Ttok, int N, int tpb) {
+  __shared__ float red[8][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long t0 = (long long)blockIdx.y * tpb, t1 = min(Ttok, t0 + (long long)tpb);
+  if (c < N) {
+    for (long long t = t0 + warp; t < t1; t += 8) {
+      if (c + 4 <= N) {
+        float v[4];
+        ld4(X + t * ld + c, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] += v[j];
+      } else {
+        for (int j = 0; c + j < N; ++j) s[j] += ldf(X + t * ld + c + j);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[warp][lane * 4 + j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (cc < N && v != 0.f) atomicAdd(out + cc, v);
+  }
+}
+template <typename T>
+static inline void launch_colsum(cudaStream_t st, const T* X, long long ld, float* out, long long Ttok, int N) {
+  int chunks = cdiv(4LL * sm_count(), cdiv(N, 128));
+  long long tpb = (Ttok + chunks - 1) / chunks;
+  tpb = tpb < 64 ? 64 : tpb;
+  dim3 grid(cdiv(N, 128), cdiv(Ttok, tpb));
+  { ADN_KERNEL("k_colsum", st); k_colsum<T><<<grid, 256, 0, st>>>(X, ld, out, Ttok, N, (int)tpb); }
+}
+
+// ---------------------------------------------------------------- FeedForward: depthwise 3x3 + gate, channels-last
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+
+constexpr int FROWS = 8;
+// a = dwconv3x3(h1; K) + b_dw over all C4 channels; gated[t][c] = gelu(a[t][c]) * sigmoid(a[t][C2 + c]).
+// thread = (4 channels of the first half + the matching 4 of the second half, one column x), walks FROWS rows with two 3x3
+// register windows.  block (8 channel groups, 32 columns); grid (ceil(C2/32), ceil(W/32), B * ceil(H/FROWS)).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_ffn_conv_fwd(const T* __restrict__ h1, const float* __restrict__ Kc, const float* __restrict__ b_dw, T* __restrict__ a_out,
+               T* __restrict__ gated, int H, int W, int C4) {
+  const int C2 = C4 >> 1, CV = C2 >> 2;
+  const int cv = blockIdx.x * 8 + threadIdx.x;
+  const int x = blockIdx.y * 32 + threadIdx.y;
+  const int ybl = cdiv(H, FROWS);
+  const int b = blockIdx.z / ybl, y0 = (blockIdx.z % ybl) * FROWS;
+  if (cv >= CV || x >= W) return;
+  const int c0 = cv * 4;
+  float k1[9][4], k2[9][4], bi1[4], bi2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { k1[t][i] = Kc[(c0 + i) * 9 + t]; k2[t][i] = Kc[(C2 + c0 + i) * 9 + t]; }
+    bi1[i] = b_dw[c0 + i];
+    bi2[i] = b_dw[C2 + c0 + i];
+  }
+  const T* s1 = h1 + (long long)b * H * W * C4 + c0;
+  const T* s2 = s1 + C2;
+  float w1[3][3][4], w2[3][3][4];
+  load_row3(s1, C4, W, y0 - 1, H, x, w1[0]); load_row3(s2, C4, W, y0 - 1, H, x, w2[0]);
+  load_row3(s1, C4, W, y0, H, x, w1[1]); load_row3(s2, C4, W, y0, H, x, w2[1]);
+  const int y1 = min(H, y0 + FROWS);
+  for (int y = y0; y < y1; ++y) {
+    load_row3(s1, C4, W, y + 1, H, x, w1[2]); load_row3(s2, C4, W, y + 1, H, x, w2[2]);
+    float a1[4], a2[4], o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { a1[i] = bi1[i]; a2[i] = bi2[i]; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a1[i] = fmaf(k1[r * 3 + s][i], w1[r][s][i], a1[i]);
+          a2[i] = fmaf(k2[r * 3 + s][i], w2[r][s][i], a2[i]);
+        }
+    const long long tok = ((long long)b * H + y) * W + x;
+    if (a_out) { st4(a_out + tok * C4 + c0, a1); st4(a_out + tok * C4 + C2 + c0, a2); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = gelu_f(a1[i]) * sigmoid_t<T>(a2[i]);
+    st4(gated + tok * C2 + c0, o);
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        w1[0][s][i] = w1[1][s][i]; w1[1][s][i] = w1[2][s][i];
+        w2[0][s][i] = w2[1][s][i]; w2[1][s][i] = w2[2][s][i];
+      }
+  }
+}
+
+// da = dgated * d(gelu(a1) sigmoid(a2)) / d(a1, a2)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_ffn_gate_bwd(const T* __restrict__ a, const T* __restrict__ dg, T* __restrict__ da, long long Ttok, int C4) {
+  const int C2 = C4 >> 1, CV = C2 >> 2;
+  const long long n = Ttok * CV, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long t = i / CV;
+    const int c0 = (int)(i - t * CV) * 4;
+    float a1[4], a2[4], g[4], o1[4], o2[4];
+    ld4(a + t * C4 + c0, a1); ld4(a + t * C4 + C2 + c0, a2); ld4(dg + t * C2 + c0, g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float s = sigmoid_t<T>(a2[j]);
+      o1[j] = g[j] * s * gelu_grad_f(a1[j]);
+      o2[j] = g[j] * gelu_f(a1[j]) * s * (1.f - s);
+    }
+    st4(da + t * C4 + c0, o1);
+    st4(da + t * C4 + C2 + c0, o2);
+  }
+}
+
+// dh1 = conv^T(da);  dK[c][a][b] += h1[y, x, c] da[y-a+1, x-b+1, c];  db_dw[c] += da;  db_in[c] += dh1.
+// thread = (4 channels, one column); blockIdx.z strides over the (sample, row block) work items so that the 44 partial sums
+// of a thread stay in registers over the whole pass (one shared-memory reduction + 44 x 32 global atomics per block).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_ffn_conv_bwd(const T* __restrict__ da, const T* __restrict__ h1, const float* __restrict__ Kc, T* __restrict__ dh1,
+               float* __restrict__ dK, float* __restrict__ db_dw, float* __restrict__ db_in, int Bn, int H, int W, int C4) {
+  __shared__ float red[8][44];
+  const int CV = C4 >> 2;
+  const int cv = blockIdx.x * 8 + threadIdx.x;
+  const int x = blockIdx.y * 32 + threadIdx.y;
+  const int ybl = cdiv(H, FROWS);
+  const int tid = threadIdx.y * 8 + threadIdx.x;
+  for (int i = tid; i < 8 * 44; i += 256) (&red[0][0])[i] = 0.f;
+  __syncthreads();
+  const bool active = (cv < CV && x < W);
+  const int c0 = cv * 4;
+  float dk[9][4] = {}, sda[4] = {}, sdh[4] = {};
+  if (active) {
+    float k[9][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) k[t][i] = Kc[(c0 + i) * 9 + t];
+    for (int z = blockIdx.z; z < Bn * ybl; z += gridDim.z) {
+      const int b = z / ybl, y0 = (z - b * ybl) * FROWS;
+      const long long boff = (long long)b * H * W;
+      const T* g = da + boff * C4 + c0;
+      float win[3][3][4];
+      load_row3(g, C4, W, y0 - 1, H, x, win[0]);
+      load_row3(g, C4, W, y0, H, x, win[1]);
+      const int y1 = min(H, y0 + FROWS);
+      for (int y = y0; y < y1; ++y) {
+        load_row3(g, C4, W, y + 1, H, x, win[2]);
+        float rc[4], o[4] = {0.f, 0.f, 0.f, 0.f};
+        const long long tok = boff + (long long)y * W + x;
+        ld4(h1 + tok * C4 + c0, rc);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float d = win[2 - a][2 - bb][i];
+              o[i] = fmaf(k[a * 3 + bb][i], d, o[i]);
+              dk[a * 3 + bb][i] = fmaf(rc[i], d, dk[a * 3 + bb][i]);
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { sda[i] += win[1][1][i]; sdh[i] += o[i]; }
+        st4(dh1 + tok * C4 + c0, o);
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            win[0][s][i] = win[1][s][i];
+            win[1][s][i] = win[2][s][i];
+          }
+      }
+    }
+  }
+  // lanes of a warp = 4 columns x 8 channel groups: fold the columns, then the 8 warps through shared memory
+#pragma unroll
+  for (int t = 0; t < 11; ++t)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v = t < 9 ? dk[t < 9 ? t : 0][i] : (t == 9 ? sda[i] : sdh[i]);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((tid & 31) < 8) atomicAdd(&red[threadIdx.x][t * 4 + i], v);
+    }
+  __syncthreads();
+  for (int i = tid; i < 8 * 44; i += 256) {
+    const int v = i / 44, r = i % 44, t = r >> 2, ch = (blockIdx.x * 8 + v) * 4 + (r & 3);
+    if (ch >= C4) continue;
+    const float val = red[v][r];
+    if (t < 9) atomicAdd(dK + ch * 9 + t, val);
+    else if (t == 9) atomicAdd(db_dw + ch, val);
+    else atomicAdd(db_in + ch, val);
+  }
+}
+
+// Loud failure without a host sync: a GEMM of this pass flagged a pipeline time-out -> poison the pass's output.
+template <typename T>
+__global__ void k_poison_if(const int* __restrict__ status, T* __restrict__ out, int n) {
+  if (*status != 0 && threadIdx.x < n) stf(out + threadIdx.x, __int_as_float(0x7fc00000));
+}
+
+// ---------------------------------------------------------------- GEMM dispatch (tensor cores for bf16, CUDA cores otherwise)
+static inline bool tc_ok(int dtype, int K, int N) { return dtype == ADN_BF16 && K % 8 == 0 && N % 8 == 0 && env().wide; }
+
+#define BLK_GEMM(...)                   \
+  do {                                  \
+    int _rc = tcg::gemm(__VA_ARGS__);   \
+    if (_rc) return _rc;                \
+  } while (0)
+
+// y[T][N] = x[T][K] W[N][K]^T (+ bias)
+template <typename T>
+static int gemm_xwT(cudaStream_t st, const char* name, bool tc, const T* x, long long Ttok, int K, const float* w, const bf16* w_bf, int N,
+                    const float* bias, T* y, int* status) {
+  if (tc) {
+    using namespace tcg;
+    BLK_GEMM(st, name, (int)Ttok, N, K, kmaj((const bf16*)x, K), kmaj(w_bf, K), 0, NOOP, NOOP, Out{y, N, 0, C_BF16}, 1, 1, nullptr, 0,
+             status, NOAUX, bias);
+  } else {
+    launch_gemm<T, T, true>(st, x, K, 0, w, K, 0, y, N, 0, (int)Ttok, N, K, 1, nullptr, 0);
+    if (bias) { ADN_KERNEL("k_bias_add", st); k_bias_add<T><<<ew_grid(Ttok * N), 256, 0, st>>>(y, bias, Ttok * N, N); }
+  }
+  return ADN_OK;
+}
+// dx[T][K] = dy[T][N] W[N][K]
+template <typename T>
+static int gemm_xw(cudaStream_t st, const char* name, bool tc, const T* dy, long long Ttok, int N, const float* w, const bf16* w_bf, int K,
+                   T* dx, int* status) {
+  if (tc) {
+    using namespace tcg;
+    BLK_GEMM(st, name, (int)Ttok, K, N, kmaj((const bf16*)dy, N), mnmaj(w_bf, K), 0, NOOP, NOOP, Out{dx, K, 0, C_BF16}, 1, 1, nullptr, 0, status);
+  } else {
+    launch_gemm<T, T, false>(st, dy, N, 0, w, K, 0, dx, K, 0, (int)Ttok, K, N, 1, nullptr, 0);
+  }
+  return ADN_OK;
+}
+// dW[N][K] += dy[T][N]^T x[T][K]     (dW zeroed by the caller)
+template <typename T>
+static int gemm_wgrad(cudaStream_t st, const char* name, bool tc, const T* dy, long long Ttok, int N, const T* x, int K, float* dW, int* status) {
+  if (tc) {
+    using namespace tcg;
+    const int splitk = pick_splitk(cdiv(N, BM) * cdiv(K, pick_bn(K, 1)), (int)Ttok);
+    BLK_GEMM(st, name, N, K, (int)Ttok, mnmaj((const bf16*)dy, N), mnmaj((const bf16*)x, K), 0, NOOP, NOOP, Out{dW, K, 0, C_ATOMIC_F32}, 1, splitk,
+             nullptr, 0, status);
+  } else {
+    launch_reduce_gemm<T, T>(st, dy, N, x, K, dW, K, 0, N, K, (int)Ttok, 1, 0);
+  }
+  return ADN_OK;
+}
+
+// ---------------------------------------------------------------- FeedForward buffers
+struct FfnDims {
+  int B, H, W, D, C4, C2;
+  long long T;
+};
+template <typename T>
+struct FfnSaved {
+  T *h1, *a, *gated;
+  size_t bytes;
+  FfnSaved(const FfnDims& d, void* p) {
+    Carver c(p);
+    h1 = c.take<T>((size_t)d.T * d.C4);
+    a = c.take<T>((size_t)d.T * d.C4);
+    gated = c.take<T>((size_t)d.T * d.C2);
+    bytes = c.off;
+  }
+};
+template <typename T>
+struct FfnFwdW {
+  int* status;
+  bf16 *w_in, *w_out;
+  T *h1, *gated;      // inference: the two intermediates live here
+  size_t bytes;
+  FfnFwdW(const FfnDims& d, void* p) {
+    Carver c(p);
+    status = c.take<int>(64);
+    w_in = c.take<bf16>((size_t)d.C4 * d.D);
+    w_out = c.take<bf16>((size_t)d.D * d.C2);
+    h1 = c.take<T>((size_t)d.T * d.C4);
+    gated = c.take<T>((size_t)d.T * d.C2);
+    bytes = c.off;
+  }
+};
+template <typename T>
+struct FfnBwdW {
+  int* status;
+  bf16 *w_in, *w_out;
+  T *dgated, *da, *dh1;
+  size_t bytes;
+  FfnBwdW(const FfnDims& d, void* p) {
+    Carver c(p);
+    status = c.take<int>(64);
+    w_in = c.take<bf16>((size_t)d.C4 * d.D);
+    w_out = c.take<bf16>((size_t)d.D * d.C2);
+    dgated = c.take<T>((size_t)d.T * d.C2);
+    da = c.take<T>((size_t)d.T * d.C4);
+    dh1 = c.take<T>((size_t)d.T * d.C4);
+    bytes = c.off;
+  }
+};
+
+static int ffn_dims(const AdnFfnShape* s, FfnDims* d, const char* what) {
+  ADN_REQUIRE(s != nullptr, ADN_ERR_NULL, "%s: NULL shape", what);
+  ADN_REQUIRE(s->B > 0 && s->H > 0 && s->W > 0 && s->D > 0 && s->C4 > 0, ADN_ERR_SHAPE, "%s: non-positive extent", what);
+  ADN_REQUIRE(s->D % 4 == 0 && s->C4 % 8 == 0, ADN_ERR_SHAPE, "%s: D %% 4 == 0 and C4 %% 8 == 0 required (got D=%d, C4=%d)", what, s->D, s->C4);
+  ADN_REQUIRE(s->dtype == ADN_F32 || s->dtype == ADN_BF16, ADN_ERR_DTYPE, "%s: unsupported dtype %d", what, s->dtype);
+  d->B = s->B; d->H = s->H; d->W = s->W; d->D = s->D; d->C4 = s->C4; d->C2 = s->C4 / 2;
+  d->T = (long long)s->B * s->H * s->W;
+  ADN_REQUIRE(d->T < (1LL << 31) / 8, ADN_ERR_SHAPE, "%s: too many tokens (%lld)", what, d->T);
+  ADN_REQUIRE((long long)s->B * cdiv(s->H, FROWS) <= 65535, ADN_ERR_SHAPE, "%s: B * ceil(H / %d) exceeds the grid limit", what, FROWS);
+  return ADN_OK;
+}
+
+template <typename T>
+static int ffn_forward(const FfnDims& d, int dtype, const AdnFfnWeights& w, const T* x, T* y, void* saved, void* ws, cudaStream_t st) {
+  FfnFwdW<T> W(d, ws);
+  const bool training = saved != nullptr;
+  FfnSaved<T> S(d, saved);
+  T* h1 = training ? S.h1 : W.h1;
+  T* gated = training ? S.gated : W.gated;
+  const bool tc = tc_ok(dtype, d.D, d.C4) && d.C2 % 8 == 0;
+  ADN_CHECK_CUDA(cudaMemsetAsync(W.status, 0, 256, st));
+  if (tc) {
+    ADN_KERNEL("k_to_bf16", st);
+    k_to_bf16<<<ew_grid((long long)d.C4 * d.D + (long long)d.D * d.C2), 256, 0, st>>>((const float*)w.w_in, W.w_in, (long long)d.C4 * d.D,
+                                                                                       (const float*)w.w_out, W.w_out, (long long)d.D * d.C2);
+  }
+  int rc = gemm_xwT<T>(st, "ffn_project_in", tc, x, d.T, d.D, (const float*)w.w_in, W.w_in, d.C4, (const float*)w.b_in, h1, W.status);
+  if (rc) return rc;
+  {
+    dim3 grid(cdiv(d.C2 / 4, 8), cdiv(d.W, 32), d.B * cdiv(d.H, FROWS)), block(8, 32);
+    ADN_KERNEL("k_ffn_conv_fwd", st);
+    k_ffn_conv_fwd<T><<<grid, block, 0, st>>>(h1, (const float*)w.w_dw, (const float*)w.b_dw, training ? S.a : nullptr, gated, d.H, d.W, d.C4);
+  }
+  rc = gemm_xwT<T>(st, "ffn_project_out", tc, gated, d.T, d.C2, (const float*)w.w_out, W.w_out, d.D, (const float*)w.b_out, y, W.status);
+  if (rc) return rc;
+  { ADN_KERNEL("k_poison_if", st); k_poison_if<T><<<1, 32, 0, st>>>(W.status, y, 4); }
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
+template <typename T>
+static int ffn_backward(const FfnDims& d, int dtype, const AdnFfnWeights& w, const T* x, const void* saved, const T* dy, T* dx,
+                        const AdnFfnWeights& g, void* ws, cudaStream_t st) {
+  FfnBwdW<T> W(d, ws);
+  FfnSaved<T> S(d, const_cast<void*>(saved));
+  const bool tc = tc_ok(dtype, d.D, d.C4) && d.C2 % 8 == 0;
+  ADN_CHECK_CUDA(cudaMemsetAsync(W.status, 0, 256, st));
+  ADN_CHECK_CUDA(cudaMemsetAsync(g.w_in, 0, (size_t)d.C4 * d.D * sizeof(float), st));
+  ADN_CHECK_CUDA(cudaMemsetAsync(g.b_in, 0, (size_t)d.C4 * sizeof(float), st));
+  ADN_CHECK_CUDA(cudaMemsetAsync(g.w_dw, 0, (size_t)d.C4 * 9 * sizeof(float), st));
+  ADN_CHECK_CUDA(cudaMemsetAsync(g.b_dw, 0, (size_t)d.C4 * sizeof(float), st));
+  ADN_CHECK_CUDA(cudaMemsetAsync(g.w_out, 0, (size_t)d.D * d.C2 * sizeof(float), st));
+  ADN_CHECK_CUDA(cudaMemsetAsync(g.b_out, 0, (size_t)d.D * sizeof(float), st));
+  if (tc) {
+    ADN_KERNEL("k_to_bf16", st);
+    k_to_bf16<<<ew_grid((long long)d.C4 * d.D + (long long)d.D * d.C2), 256, 0, st>>>((const float*)w.w_in, W.w_in, (long long)d.C4 * d.D,
+                                                                                       (const float*)w.w_out, W.w_out, (long long)d.D * d.C2);
+  }
+  // project_out backward
+  int rc = gemm_xw<T>(st, "ffn_dgated", tc, dy, d.T, d.D, (const float*)w.w_out, W.w_out, d.C2, W.dgated, W.status);
+  if (rc) return rc;
+  rc = gemm_wgrad<T>(st, "ffn_dWout", tc, dy, d.T, d.D, S.gated, d.C2, (float*)g.w_out, W.status);
+  if (rc) return rc;
+  launch_colsum<T>(st, dy, d.D, (float*)g.b_out, d.T, d.D);
+  // gate + depthwise conv backward
+  { ADN_KERNEL("k_ffn_gate_bwd", st); k_ffn_gate_bwd<T><<<ew_grid(d.T * (d.C2 / 4)), 256, 0, st>>>(S.a, W.dgated, W.da, d.T, d.C4); }
+  {
+    const int gx = cdiv(d.C4 / 4, 8), gy = cdiv(d.W, 32), items = d.B * cdiv(d.H, FROWS);
+    int gz = cdiv(8LL * sm_count(), (long long)gx * gy);
+    gz = gz < 1 ? 1 : (gz > items ? items : gz);
+    dim3 grid(gx, gy, gz), block(8, 32);
+    ADN_KERNEL("k_ffn_conv_bwd", st);
+    k_ffn_conv_bwd<T><<<grid, block, 0, st>>>(W.da, S.h1, (const float*)w.w_dw, W.dh1, (float*)g.w_dw, (float*)g.b_dw, (float*)g.b_in, d.B, d.H,
+                                              d.W, d.C4);
+  }
+  // project_in backward
+  rc = gemm_xw<T>(st, "ffn_dx", tc, W.dh1, d.T, d.C4, (const float*)w.w_in, W.w_in, d.D, dx, W.status);
+  if (rc) return rc;
+  rc = gemm_wgrad<T>(st, "ffn_dWin", tc, W.dh1, d.T, d.C4, x, d.D, (float*)g.w_in, W.status);
+  if (rc) return rc;
+  { ADN_KERNEL("k_poison_if", st); k_poison_if<T><<<1, 32, 0, st>>>(W.status, dx, 4); }
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
+}  // namespace blk
+}  // namespace adn
+
+using namespace adn;
+using namespace adn::blk;
+
+extern "C" {
+
+int adn_residual_forward(const void* x, const void* y, const float* beta1, const float* beta2, const float* gamma, void* out,
+                         int64_t tokens, int32_t D, int32_t dtype, void* stream) {
+  ADN_REQUIRE(tokens > 0 && D > 0 && D % 4 == 0, ADN_ERR_SHAPE, "adn_residual_forward: tokens > 0 and D %% 4 == 0 required (got %lld, %d)",
+              (long long)tokens, D);
+  ADN_REQUIRE(dtype == ADN_F32 || dtype == ADN_BF16, ADN_ERR_DTYPE, "adn_residual_forward: unsupported dtype %d", dtype);
+  ADN_REQUIRE(x && y && beta1 && beta2 && out, ADN_ERR_NULL, "adn_residual_forward: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n4 = tokens * D / 4;
+  if (dtype == ADN_F32) { ADN_KERNEL("k_residual_fwd", st); k_residual_fwd<float><<<ew_grid(n4), 256, 0, st>>>((const float*)x, (const float*)y, beta1, beta2, gamma, (float*)out, n4, D); }
+  else { ADN_KERNEL("k_residual_fwd", st); k_residual_fwd<bf16><<<ew_grid(n4), 256, 0, st>>>((const bf16*)x, (const bf16*)y, beta1, beta2, gamma, (bf16*)out, n4, D); }
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
+int adn_residual_backward(const void* x, const void* y, const void* dout, const float* beta1, const float* beta2, const float* gamma,
+                          void* dx, void* dy, float* dbeta1, float* dbeta2, float* dgamma, void* ws, int64_t tokens, int32_t D,
+                          int32_t dtype, void* stream) {
+  ADN_REQUIRE(tokens > 0 && D > 0 && D % 4 == 0 && D <= 8192, ADN_ERR_SHAPE, "adn_residual_backward: tokens > 0, D %% 4 == 0, D <= 8192 required (got %lld, %d)",
+              (long long)tokens, D);
+  ADN_REQUIRE(dtype == ADN_F32 || dtype == ADN_BF16, ADN_ERR_DTYPE, "adn_residual_backward: unsupported dtype %d", dtype);
+  ADN_REQUIRE(x && y && dout && beta1 && beta2 && dx && dy && dbeta1 && dbeta2 && ws && (!gamma || dgamma), ADN_ERR_NULL,
+              "adn_residual_backward: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* acc2 = (double*)ws;
+  ADN_CHECK_CUDA(cudaMemsetAsync(acc2, 0, 2 * sizeof(double), st));
+  if (gamma) ADN_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)D * sizeof(float), st));
+  long long tpw = tokens / (16LL * sm_count());
+  tpw = tpw < 1 ? 1 : (tpw > 64 ? 64 : tpw);
+  const int grid = cdiv(tokens, 8 * tpw);
+  const size_t smem = (size_t)D * sizeof(float);
+  if (dtype == ADN_F32) { ADN_KERNEL("k_residual_bwd", st); k_residual_bwd<float><<<grid, 256, smem, st>>>((const float*)x, (const float*)y, (const float*)dout, beta1, beta2, gamma, (float*)dx, (float*)dy, acc2, dgamma, tokens, (int)tpw, D); }
+  else { ADN_KERNEL("k_residual_bwd", st); k_residual_bwd<bf16><<<grid, 256, smem, st>>>((const bf16*)x, (const bf16*)y, (const bf16*)dout, beta1, beta2, gamma, (bf16*)dx, (bf16*)dy, acc2, dgamma, tokens, (int)tpw, D); }
+  { ADN_KERNEL("k_store_acc2", st); k_store_acc2<<<1, 32, 0, st>>>(acc2, dbeta1, dbeta2); }
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
+int adn_ffn_workspace_bytes(const AdnFfnShape* s, size_t* saved, size_t* fwd_ws, size_t* bwd_ws) {
+  FfnDims d;
+  int rc = ffn_dims(s, &d, "adn_ffn_workspace_bytes");
+  if (rc) return rc;
+  if (s->dtype == ADN_F32) {
+    if (saved) *saved = FfnSaved<float>(d, nullptr).bytes;
+    if (fwd_ws) *fwd_ws = FfnFwdW<float>(d, nullptr).bytes;
+    if (bwd_ws) *bwd_ws = FfnBwdW<float>(d, nullptr).bytes;
+  } else {
+    if (saved) *saved = FfnSaved<bf16>(d, nullptr).bytes;
+    if (fwd_ws) *fwd_ws = FfnFwdW<bf16>(d, nullptr).bytes;
+    if (bwd_ws) *bwd_ws = FfnBwdW<bf16>(d, nullptr).bytes;
+  }
+  return ADN_OK;
+}
+
+int adn_ffn_forward(const AdnFfnShape* s, const AdnFfnWeights* w, const void* x, void* y, void* saved, void* ws, void* stream) {
+  FfnDims d;
+  int rc = ffn_dims(s, &d, "adn_ffn_forward");
+  if (rc) return rc;
+  ADN_REQUIRE(w && x && y && ws && w->w_in && w->b_in && w->w_dw && w->b_dw && w->w_out && w->b_out, ADN_ERR_NULL, "adn_ffn_forward: NULL argument");
+  if (s->dtype == ADN_F32) return ffn_forward<float>(d, s->dtype, *w, (const float*)x, (float*)y, saved, ws, (cudaStream_t)stream);
+  return ffn_forward<bf16>(d, s->dtype, *w, (const bf16*)x, (bf16*)y, saved, ws, (cudaStream_t)stream);
+}
+
+int adn_ffn_backward(const AdnFfnShape* s, const AdnFfnWeights* w, const void* x, const void* saved, const void* dy, void* dx,
+                     const AdnFfnWeights* grads, void* ws, void* stream) {
+  FfnDims d;
+  int rc = ffn_dims(s, &d, "adn_ffn_backward");
+  if (rc) return rc;
+  ADN_REQUIRE(w && x && saved && dy && dx && grads && ws && grads->w_in && grads->b_in && grads->w_dw && grads->b_dw && grads->w_out && grads->b_out,
+              ADN_ERR_NULL, "adn_ffn_backward: NULL argument");
+  if (s->dtype == ADN_F32) return ffn_backward<float>(d, s->dtype, *w, (const float*)x, saved, (const float*)dy, (float*)dx, *grads, ws, (cudaStream_t)stream);
+  return ffn_backward<bf16>(d, s->dtype, *w, (const bf16*)x, saved, (const bf16*)dy, (bf16*)dx, *grads, ws, (cudaStream_t)stream);
+}
+
+// ---- Linear (the Block's out_proj, models/ADNMUNet.py:108-110,162-163): y = x W^T + b over tokens
+static int linear_check(int64_t tokens, int32_t K, int32_t N, int32_t dtype, const char* what) {
+  ADN_REQUIRE(tokens > 0 && K > 0 && N > 0 && tokens < (1LL << 31) / 8, ADN_ERR_SHAPE, "%s: bad extents (%lld, %d, %d)", what, (long long)tokens, K, N);
+  ADN_REQUIRE(dtype == ADN_F32 || dtype == ADN_BF16, ADN_ERR_DTYPE, "%s: unsupported dtype %d", what, dtype);
+  return ADN_OK;
+}
+
+int adn_linear_workspace_bytes(int64_t tokens, int32_t K, int32_t N, int32_t dtype, size_t* ws) {
+  int rc = linear_check(tokens, K, N, dtype, "adn_linear_workspace_bytes");
+  if (rc) return rc;
+  if (ws) *ws = 256 + align_up((size_t)K * N * sizeof(bf16), 256);
+  return ADN_OK;
+}
+
+int adn_linear_forward(const void* x, const float* w, const float* bias, void* y, int64_t tokens, int32_t K, int32_t N, int32_t dtype,
+                       void* ws, void* stream) {
+  int rc = linear_check(tokens, K, N, dtype, "adn_linear_forward");
+  if (rc) return rc;
+  ADN_REQUIRE(x && w && y && ws, ADN_ERR_NULL, "adn_linear_forward: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* status = (int*)ws;
+  bf16* w_bf = (bf16*)((char*)ws + 256);
+  const bool tc = tc_ok(dtype, K, N);
+  ADN_CHECK_CUDA(cudaMemsetAsync(status, 0, 256, st));
+  if (tc) { ADN_KERNEL("k_to_bf16", st); k_to_bf16<<<ew_grid((long long)K * N), 256, 0, st>>>(w, w_bf, (long long)K * N, nullptr, nullptr, 0); }
+  if (dtype == ADN_F32) {
+    rc = gemm_xwT<float>(st, "linear_fwd", tc, (const float*)x, tokens, K, w, w_bf, N, bias, (float*)y, status);
+  } else {
+    rc = gemm_xwT<bf16>(st, "linear_fwd", tc, (const bf16*)x, tokens, K, w, w_bf, N, bias, (bf16*)y, status);
+    if (!rc) { ADN_KERNEL("k_poison_if", st); k_poison_if<bf16><<<1, 32, 0, st>>>(status, (bf16*)y, 4); }
+  }
+  if (rc) return rc;
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
+int adn_linear_backward(const void* x, const float* w, const void* dy, void* dx, float* dw, float* dbias, int64_t tokens, int32_t K,
+                        int32_t N, int32_t dtype, void* ws, void* stream) {
+  int rc = linear_check(tokens, K, N, dtype, "adn_linear_backward");
+  if (rc) return rc;
+  ADN_REQUIRE(x && w && dy && dx && dw && ws, ADN_ERR_NULL, "adn_linear_backward: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* status = (int*)ws;
+  bf16* w_bf = (bf16*)((char*)ws + 256);
+  const bool tc = tc_ok(dtype, K, N);
+  ADN_CHECK_CUDA(cudaMemsetAsync(status, 0, 256, st));
+  ADN_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * N * sizeof(float), st));
+  if (dbias) ADN_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)N * sizeof(float), st));
+  if (tc) { ADN_KERNEL("k_to_bf16", st); k_to_bf16<<<ew_grid((long long)K * N), 256, 0, st>>>(w, w_bf, (long long)K * N, nullptr, nullptr, 0); }
+  if (dtype == ADN_F32) {
+    rc = gemm_xw<float>(st, "linear_dx", tc, (const float*)dy, tokens, N, w, w_bf, K, (float*)dx, status);
+    if (!rc) rc = gemm_wgrad<float>(st, "linear_dW", tc, (const float*)dy, tokens, N, (const float*)x, K, dw, status);
+    if (!rc && dbias) launch_colsum<float>(st, (const float*)dy, N, dbias, tokens, N);
+  } else {
+    rc = gemm_xw<bf16>(st, "linear_dx", tc, (const bf16*)dy, tokens, N, w, w_bf, K, (bf16*)dx, status);
+    if (!rc) rc = gemm_wgrad<bf16>(st, "linear_dW", tc, (const bf16*)dy, tokens, N, (const bf16*)x, K, dw, status);
+    if (!rc && dbias) launch_colsum<bf16>(st, (const bf16*)dy, N, dbias, tokens, N);
+    if (!rc) { ADN_KERNEL("k_poison_if", st); k_poison_if<bf16><<<1, 32, 0, st>>>(status, (bf16*)dx, 4); }
+  }
+  if (rc) return rc;
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
+}  // extern "C"

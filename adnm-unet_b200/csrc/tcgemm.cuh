@@ -60,6 +60,7 @@ struct Args {
   const bf16* aux; long long ld_aux, aux_bs;   // optional epilogue operand, indexed like C: C = acc * SiLU'(aux)   (conv backward:
                                               // the gradient w.r.t. the conv output becomes the gradient w.r.t. its input)
   int a_bz[2], b_bz[2];    // 1: the operand of that segment has a batch dimension (else every batch reads the same matrix)
+  const float* bias;       // optional fp32 vector [N] added after alpha (1x1 conv / Linear bias)
   int dbg;                 // knock-outs for profiling (adn_set_option("gemm_dbg")): 1 no epilogue stores, 2 no operand loads, 4 no MMAs
 };
 
@@ -109,7 +110,7 @@ __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t tile, int ks) { retur
 //   warps 5-8  producers: cp.async ring (STAGES deep) that runs continuously across tile boundaries
 //   warp  4    MMA issuer: one elected lane; accumulators double-buffered in TMEM (2 x BN columns)
 //   warps 0-3  epilogue: drains accumulator buffer i & 1 (TMEM lane quarter = warp) while the MMAs of tile i + 1 run
-__global__ void __launch_bounds__(THREADS)
+static __global__ void __launch_bounds__(THREADS)
 k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_constant__ CUtensorMap mA0,
          const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUtensorMap mB1,
          const __grid_constant__ CUtensorMap mC) {
@@ -241,6 +242,11 @@ k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_c
             v[j] *= alpha;
             if (a.parity_mask && ((m ^ (n + j)) & 1)) v[j] = 0.f;
           }
+          if (a.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n + j < a.N) v[j] += __ldg(a.bias + n + j);
+          }
           if (a.aux != nullptr && m < a.M) {
             const bf16* ax = a.aux + (long long)batch * a.aux_bs + (long long)m * a.ld_aux + n;
             if (n + 16 <= a.N && ((uintptr_t)ax & 15) == 0) {      // two 16-byte loads per row instead of 16 scalar ones
@@ -351,7 +357,7 @@ static const Aux NOAUX = Aux{nullptr, 0, 0};
 
 // C = alpha * (A0 . B0 [+ A1 . B1]);  batches > 1: per-sample GEMMs;  splitk > 1: atomics into a ZEROED fp32 C.
 static int gemm(cudaStream_t st, const char* name, int M, int N, int K0, Op A0, Op B0, int K1, Op A1, Op B1, Out C,
-                int batches, int splitk, const float* alpha, int parity_mask, int* status, Aux aux = NOAUX) {
+                int batches, int splitk, const float* alpha, int parity_mask, int* status, Aux aux = NOAUX, const float* bias = nullptr) {
   ADN_REQUIRE(M > 0 && N > 0 && K0 > 0 && batches > 0, ADN_ERR_SHAPE, "tcgemm %s: empty problem", name);
   ADN_REQUIRE(K1 == 0 || (A1.mn == A0.mn && B1.mn == B0.mn), ADN_ERR_SHAPE, "tcgemm %s: segments must share orientation", name);
   ADN_REQUIRE(splitk == 1 || (K1 == 0 && C.mode == C_ATOMIC_F32), ADN_ERR_SHAPE, "tcgemm %s: split-K needs one segment and an atomic fp32 output", name);
@@ -372,6 +378,7 @@ static int gemm(cudaStream_t st, const char* name, int M, int N, int K0, Op A0, 
   a.splitk = cdiv(K0, a.k_per_split);
   a.status = status;
   a.aux = aux.p; a.ld_aux = aux.ld; a.aux_bs = aux.bs;
+  a.bias = bias;
   a.a_bz[0] = batches > 1 && A0.bs != 0; a.b_bz[0] = batches > 1 && B0.bs != 0;
   a.a_bz[1] = batches > 1 && A1.bs != 0; a.b_bz[1] = batches > 1 && B1.bs != 0;
   a.dbg = env().gemm_dbg;

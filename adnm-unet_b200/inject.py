@@ -1,12 +1,13 @@
-"""Make the unmodified reference network use the B200 kernels: rebind the two module globals the reference
-resolves at construction time: `models.ADNMUNet.Mamba2` (looked up inside `create_block`,
-models/ADNMUNet.py:277) and `models.model_untils.WTConv2d` (models/model_untils.py:17,101).  No reference file is
-edited; call this before `create_ADNMUNet(...)`."""
+"""Make the unmodified reference network use the B200 kernels: rebind the module globals the reference resolves at
+construction time: `models.ADNMUNet.Mamba2` (looked up inside `create_block`, models/ADNMUNet.py:277),
+`models.model_untils.WTConv2d` (models/model_untils.py:17,101) and - for the fused Block - the names
+`Block` / `RMSNorm` that `create_block` resolves (models/ADNMUNet.py:278-291).  No reference file is edited; call this
+before `create_ADNMUNet(...)`."""
 import importlib
 
 
 def install_into_reference(adnmunet_module="models.ADNMUNet", untils_module="models.model_untils",
-                           mixer=True, wtconv=True):
+                           mixer=True, wtconv=True, block=True):
     from adnm_unet_b200.mixer import Mamba2
     from adnm_unet_b200.wtconv import WTConv2d
     done = []
@@ -18,4 +19,10 @@ def install_into_reference(adnmunet_module="models.ADNMUNet", untils_module="mod
         m = importlib.import_module(untils_module)
         m.WTConv2d = WTConv2d
         done.append(untils_module + ".WTConv2d")
+    if block:
+        from adnm_unet_b200.block import Block
+        from adnm_unet_b200.rmsnorm import RMSNorm
+        m = importlib.import_module(adnmunet_module)
+        m.Block, m.RMSNorm = Block, RMSNorm
+        done += [adnmunet_module + ".Block", adnmunet_module + ".RMSNorm"]
     return done

@@ -178,6 +178,7 @@ def load_reference():
         setattr(ns, name, importlib.import_module("models." + name))
     ns.ref_Mamba2 = ns.ADNssd.Mamba2          # the reference's own classes, whatever the globals are rebound to later
     ns.ref_WTConv2d = ns.WTConv2d.WTConv2d
+    ns.ref_Block, ns.ref_RMSNorm = ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm
     _patch_decoder_size(ns.ADNMUNet)
     _NS = ns
     return ns
@@ -200,31 +201,37 @@ def _patch_decoder_size(mod):
 
 
 @contextlib.contextmanager
-def _bound(ns, dropin, mixer=True, wtconv=True):
-    """Rebind (or restore) the two construction-time globals for the duration of a model build."""
-    old = (ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d)
+def _bound(ns, dropin, mixer=True, wtconv=True, block=True):
+    """Rebind (or restore) the construction-time globals for the duration of a model build: the mixer and WTConv2d classes
+     and, with `block`, the `Block` / `RMSNorm` names `create_block` resolves (models/ADNMUNet.py:277-291)."""
+    old = (ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d, ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm)
     if dropin:
         from adnm_unet_b200.mixer import Mamba2
         from adnm_unet_b200.wtconv import WTConv2d
+        from adnm_unet_b200.block import Block
+        from adnm_unet_b200.rmsnorm import RMSNorm
         if mixer:
             ns.ADNMUNet.Mamba2 = Mamba2
         if wtconv:
             ns.model_untils.WTConv2d = WTConv2d
+        if block:
+            ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm = Block, RMSNorm
     else:
         ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d = ns.ref_Mamba2, ns.ref_WTConv2d
+        ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm = ns.ref_Block, ns.ref_RMSNorm
     try:
         yield
     finally:
-        ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d = old
+        ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d, ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm = old
 
 
-def build_adnm_unet(img_size=256, dropin=True, input_frames=5, output_frames=20, seed=0, mixer=True, wtconv=True):
+def build_adnm_unet(img_size=256, dropin=True, input_frames=5, output_frames=20, seed=0, mixer=True, wtconv=True, block=True):
     """`create_ADNMUNet(5, 20, 6)` (models/ADNMUNet.py:906-940) at `img_size`; seed -> identical init for both variants
     (the drop-in constructors consume the RNG stream exactly like the reference's: tests/test_abi_cpu.py)."""
     ns = load_reference()
     if seed is not None:
         torch.manual_seed(seed)
-    with _bound(ns, dropin, mixer, wtconv):
+    with _bound(ns, dropin, mixer, wtconv, block):
         model = ns.ADNMUNet.VisionMamba(
             img_size=img_size, depth=[1, 1, 1], refine_depth=[1, 1, 1, 1], refine_headdim=[4, 4, 4, 4],
             refine_dim=[32, 32, 32, 32] if output_frames > 5 else [32, 32, 16, 16],
@@ -234,12 +241,12 @@ def build_adnm_unet(img_size=256, dropin=True, input_frames=5, output_frames=20,
     return model
 
 
-def build_block(dim, out_dim, dropin=True, headdim=4, seed=0):
+def build_block(dim, out_dim, dropin=True, headdim=4, seed=0, block=True):
     """One `Block` as `create_block` builds it (models/ADNMUNet.py:243-292), for the Block-level parity tests."""
     ns = load_reference()
     if seed is not None:
         torch.manual_seed(seed)
-    with _bound(ns, dropin):
+    with _bound(ns, dropin, block=block):
         blk = ns.ADNMUNet.create_block(dim, out_dim, headdim=headdim, norm_epsilon=1e-6, layer_idx=0)
     return blk
 

@@ -163,6 +163,60 @@ int adn_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const floa
                    float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                    float max_norm, void* stream);
 
+/* ------------------------------------------------------------------ Block pre-norm -------- */
+
+/* Standalone RMSNorm of the reference README (README.md:22-30, the `norm_layer` of create_block, models/ADNMUNet.py:278) fused
+ * with the Block's scalar affine (models/ADNMUNet.py:149,155):
+ *     y = scale * (x * rsqrt(mean(x^2) + eps) * weight) + shift          per token over D
+ * x, y, dy, dx: [tokens][D] contiguous, dtype ADN_F32 or ADN_BF16; weight / scale / shift / rstd / gradients fp32.
+ * scale / shift may be NULL (1 and 0: the bare RMSNorm module).  rstd ([tokens], optional in forward) is what backward needs
+ * besides x.  dweight / dscale / dshift are OVERWRITTEN (dscale / dshift may be NULL).  D % 4 == 0, D <= 8192. */
+int adn_rmsnorm_forward(const void* x, const float* weight, const float* scale, const float* shift, void* y, float* rstd,
+                        int64_t tokens, int32_t D, float eps, int32_t dtype, void* stream);
+int adn_rmsnorm_backward(const void* x, const float* weight, const float* scale, const float* rstd, const void* dy, void* dx,
+                         float* dweight, float* dscale, float* dshift, int64_t tokens, int32_t D, int32_t dtype, void* stream);
+
+/* Residual mix of the Block (models/ADNMUNet.py:152,158,161): out = (beta1 * x + beta2 * y) * gamma[c]; gamma NULL = no
+ * per-channel scale.  x, y, out, dout, dx, dy: [tokens][D] contiguous (dtype); beta1 / beta2: device scalars; gamma (D) fp32.
+ * Backward OVERWRITES dx, dy, dbeta1, dbeta2 (scalars, accumulated in fp64 inside) and dgamma.  ws: 64 bytes of scratch. */
+int adn_residual_forward(const void* x, const void* y, const float* beta1, const float* beta2, const float* gamma, void* out,
+                         int64_t tokens, int32_t D, int32_t dtype, void* stream);
+int adn_residual_backward(const void* x, const void* y, const void* dout, const float* beta1, const float* beta2,
+                          const float* gamma, void* dx, void* dy, float* dbeta1, float* dbeta2, float* dgamma, void* ws,
+                          int64_t tokens, int32_t D, int32_t dtype, void* stream);
+
+/* FeedForward of the Block (models/model_untils.py:172-197) on TOKEN-MAJOR activations x, y: [B][H*W][D] - the layout the
+ * mixer uses, so that the NCHW round trip of models/ADNMUNet.py:158 disappears:
+ *   y = project_out( gelu(a[:, :C4/2]) * sigmoid(a[:, C4/2:]) ),  a = dwconv3x3(project_in(x)),  C4 = 4 * D in ADNM-UNet.
+ * Weights are the module's state_dict tensors, fp32, native layout (1x1 conv weights are [out][in]). */
+typedef struct AdnFfnShape {
+  int32_t B, H, W;   /* token grid                                        */
+  int32_t D;         /* dim, D % 4 == 0                                   */
+  int32_t C4;        /* project_in output channels (2 * hidden), C4 % 8 == 0 */
+  int32_t dtype;     /* ADN_F32 | ADN_BF16                                */
+} AdnFfnShape;
+typedef struct AdnFfnWeights {   /* also used for the gradients (same shapes, OVERWRITTEN) */
+  void* w_in;    /* project_in.conv.weight  (C4, D, 1, 1)   */
+  void* b_in;    /* project_in.conv.bias    (C4)            */
+  void* w_dw;    /* dwconv.conv.weight      (C4, 1, 3, 3)   */
+  void* b_dw;    /* dwconv.conv.bias        (C4)            */
+  void* w_out;   /* project_out.conv.weight (D, C4/2, 1, 1) */
+  void* b_out;   /* project_out.conv.bias   (D)             */
+} AdnFfnWeights;
+int adn_ffn_workspace_bytes(const AdnFfnShape* s, size_t* saved_bytes, size_t* fwd_workspace_bytes, size_t* bwd_workspace_bytes);
+/* saved may be NULL for inference. */
+int adn_ffn_forward(const AdnFfnShape* s, const AdnFfnWeights* w, const void* x, void* y, void* saved, void* workspace, void* stream);
+int adn_ffn_backward(const AdnFfnShape* s, const AdnFfnWeights* w, const void* x, const void* saved, const void* dy, void* dx,
+                     const AdnFfnWeights* grads, void* workspace, void* stream);
+
+/* Linear over tokens (the Block's out_proj, models/ADNMUNet.py:108-110,162-163): y[tokens][N] = x[tokens][K] W[N][K]^T + bias.
+ * bf16 activations with K % 8 == 0 and N % 8 == 0 run on the tcgen05 GEMM; dw / dbias are OVERWRITTEN (dbias may be NULL). */
+int adn_linear_workspace_bytes(int64_t tokens, int32_t K, int32_t N, int32_t dtype, size_t* workspace_bytes);
+int adn_linear_forward(const void* x, const float* w, const float* bias, void* y, int64_t tokens, int32_t K, int32_t N,
+                       int32_t dtype, void* workspace, void* stream);
+int adn_linear_backward(const void* x, const float* w, const void* dy, void* dx, float* dw, float* dbias, int64_t tokens,
+                        int32_t K, int32_t N, int32_t dtype, void* workspace, void* stream);
+
 /* ------------------------------------------------------------------ misc ------------------- */
 
 const char* adn_last_error(void);

@@ -1,0 +1,204 @@
+"""GPU parity of the Block-level kernels (RMSNorm + scalar affine, residual mix, token-major FeedForward, the whole Block)
+through the C ABI against the CPU oracle (oracle/block_oracle.py, pinned to the unmodified reference Block)."""
+import pytest
+import torch
+
+import cases
+from oracle import block_oracle as BO
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), torch.as_tensor(b).detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("cfg", [(3, 50, 32, True), (1, 7, 1024, True), (2, 129, 256, False), (5, 1000, 4, True), (1, 3, 640, True)],
+                         ids=lambda c: "B%d_L%d_D%d_affine%d" % c)
+def test_rmsnorm_affine_matches_oracle(cfg, dtype):
+    from adnm_unet_b200.rmsnorm import rmsnorm_affine
+    B, L, D, affine = cfg
+    dev = torch.device("cuda:0")
+    x = cases.rng_normal(11, (B, L, D), torch.float32) * 1.7
+    dy = cases.rng_normal(12, (B, L, D), torch.float32)
+    w = 1 + 0.3 * cases.rng_normal(13, (D,), torch.float32)
+    scale, shift = (torch.tensor(1.3), torch.tensor(-0.2)) if affine else (None, None)
+    xq = x.to(dtype).float()      # the oracle sees the same (rounded) input
+    leaves = [t.double().requires_grad_(True) for t in (xq, w)] + ([scale.double().requires_grad_(True), shift.double().requires_grad_(True)] if affine else [])
+    ref = BO.rmsnorm_affine(leaves[0], leaves[1], *(leaves[2:] if affine else (None, None)), eps=1e-6)
+    ref.backward(dy.to(dtype).double())
+    xd = x.to(dev, dtype).requires_grad_(True)
+    wd = w.to(dev).requires_grad_(True)
+    sd = [t.to(dev).requires_grad_(True) for t in (scale, shift)] if affine else [None, None]
+    y = rmsnorm_affine(xd, wd, sd[0], sd[1], eps=1e-6)
+    y.backward(dy.to(dev, dtype))
+    torch.cuda.synchronize()
+    errs = {"y": rel(y, ref), "dx": rel(xd.grad, leaves[0].grad), "dweight": rel(wd.grad, leaves[1].grad)}
+    if affine:
+        errs["dscale"] = rel(sd[0].grad, leaves[2].grad)
+        errs["dshift"] = rel(sd[1].grad, leaves[3].grad)
+    bad = {k: v for k, v in errs.items() if not v < TOL[dtype]}
+    assert not bad, bad
+
+
+def test_rmsnorm_module_is_a_drop_in():
+    from adnm_unet_b200.rmsnorm import RMSNorm
+    from adnm_unet_b200.refhost import StandaloneRMSNorm
+    dev = torch.device("cuda:0")
+    ref, new = StandaloneRMSNorm(96, eps=1e-6).to(dev), RMSNorm(96, eps=1e-6).to(dev)
+    with torch.no_grad():
+        ref.weight.copy_(1 + 0.2 * torch.randn(96, device=dev))
+    new.load_state_dict(ref.state_dict(), strict=True)
+    x = torch.randn(4, 33, 96, device=dev)
+    xr, xn = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    g = torch.randn_like(x)
+    ref(xr).backward(g)
+    new(xn).backward(g)
+    assert rel(new(x), ref(x)) < 1e-5 and rel(xn.grad, xr.grad) < 1e-5 and rel(new.weight.grad, ref.weight.grad) < 1e-5
+    with torch.no_grad():
+        assert new(x).shape == x.shape
+
+
+def _leaf(t, dev=None, dtype=None):
+    t = t.detach().clone()
+    if dev is not None:
+        t = t.to(dev, dtype) if dtype is not None else t.to(dev)
+    return t.requires_grad_(True)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("cfg", [(2, 77, 32, True), (1, 5, 1024, True), (3, 200, 64, False), (1, 9, 12, True)],
+                         ids=lambda c: "B%d_L%d_D%d_gamma%d" % c)
+def test_residual_mix_matches_formula(cfg, dtype):
+    """models/ADNMUNet.py:152,158,161: (beta1 x + beta2 y) * gamma."""
+    from adnm_unet_b200.block import residual_mix
+    B, L, D, has_gamma = cfg
+    dev = torch.device("cuda:0")
+    x, y, g = (cases.rng_normal(s, (B, L, D), torch.float32).to(dtype).float() for s in (21, 22, 23))
+    b1, b2 = torch.tensor(0.8), torch.tensor(-1.3)
+    gamma = 1 + 0.3 * cases.rng_normal(24, (D,), torch.float32) if has_gamma else None
+    ref_in = [_leaf(t.double()) for t in (x, y, b1, b2)] + ([_leaf(gamma.double())] if has_gamma else [])
+    ref = (ref_in[2] * ref_in[0] + ref_in[3] * ref_in[1]) * (ref_in[4] if has_gamma else 1.0)
+    ref.backward(g.double())
+    new_in = [_leaf(x, dev, dtype), _leaf(y, dev, dtype), _leaf(b1, dev), _leaf(b2, dev)] + ([_leaf(gamma, dev)] if has_gamma else [None])
+    out = residual_mix(*new_in)
+    out.backward(g.to(dev, dtype))
+    torch.cuda.synchronize()
+    errs = {"out": rel(out, ref)}
+    for n, a, b in zip(("dx", "dy", "dbeta1", "dbeta2", "dgamma"), new_in, ref_in):
+        errs[n] = rel(a.grad, b.grad)
+    bad = {k: v for k, v in errs.items() if not v < TOL[dtype]}
+    assert not bad, bad
+
+
+FFN_KEYS = ("project_in.conv.weight", "project_in.conv.bias", "dwconv.conv.weight", "dwconv.conv.bias",
+            "project_out.conv.weight", "project_out.conv.bias")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("cfg", [(2, 16, 16, 32), (1, 5, 9, 64), (3, 4, 4, 256), (1, 33, 40, 32), (2, 7, 7, 12), (1, 128, 128, 32)],
+                         ids=lambda c: "B%d_%dx%d_D%d" % c)
+def test_ffn_token_major_matches_oracle(cfg, dtype):
+    """FeedForward (models/model_untils.py:172-197) in token-major form, all six parameter gradients."""
+    from adnm_unet_b200.block import _FfnFunction
+    B, H, W, D = cfg
+    dev = torch.device("cuda:0")
+    p = BO.init_block_params(D, D, seed=9)
+    fp = {k: p["ffns.0." + k] for k in FFN_KEYS}
+    x = cases.rng_normal(41, (B, H * W, D), torch.float32).to(dtype).float()
+    dy = cases.rng_normal(42, (B, H * W, D), torch.float32).to(dtype).float()
+    ref_p = {"ffns.0." + k: _leaf(v) for k, v in fp.items()}
+    xr = _leaf(x.double())
+    ref = BO.ffn_forward(ref_p, xr, H, W)
+    ref.backward(dy.double())
+    new_p = [_leaf(fp[k].float(), dev) for k in FFN_KEYS]
+    xn = _leaf(x, dev, dtype)
+    y = _FfnFunction.apply(xn, H, W, True, *new_p)
+    y.backward(dy.to(dev, dtype))
+    torch.cuda.synchronize()
+    errs = {"out": rel(y, ref), "dx": rel(xn.grad, xr.grad)}
+    for k, t in zip(FFN_KEYS, new_p):
+        errs[k] = rel(t.grad, ref_p["ffns.0." + k].grad)
+    bad = {k: v for k, v in errs.items() if not v < TOL[dtype]}
+    assert not bad, bad
+    with torch.no_grad():      # inference variant (saved == NULL) gives the same output
+        y2 = _FfnFunction.apply(xn.detach(), H, W, False, *[t.detach() for t in new_p])
+    assert torch.equal(y2, y.detach())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("cfg", [(300, 128, 256, True), (16, 1024, 512, True), (1000, 32, 40, False), (7, 12, 20, True)],
+                         ids=lambda c: "T%d_K%d_N%d_bias%d" % c)
+def test_linear_tokens_matches_formula(cfg, dtype):
+    from adnm_unet_b200.block import linear_tokens
+    T, K, N, has_bias = cfg
+    dev = torch.device("cuda:0")
+    x = cases.rng_normal(51, (2, T, K), torch.float32).to(dtype).float()
+    w = cases.rng_normal(52, (N, K), torch.float32) / K ** 0.5
+    b = cases.rng_normal(53, (N,), torch.float32) if has_bias else None
+    dy = cases.rng_normal(54, (2, T, N), torch.float32).to(dtype).float()
+    wq = w.to(dtype).float() if dtype == torch.bfloat16 else w      # the tensor cores see bf16 weights
+    ref_in = [_leaf(x.double()), _leaf(wq.double())] + ([_leaf(b.double())] if has_bias else [])
+    ref = ref_in[0] @ ref_in[1].t() + (ref_in[2] if has_bias else 0.0)
+    ref.backward(dy.double())
+    new_in = [_leaf(x, dev, dtype), _leaf(w, dev)] + ([_leaf(b, dev)] if has_bias else [None])
+    y = linear_tokens(*new_in)
+    y.backward(dy.to(dev, dtype))
+    torch.cuda.synchronize()
+    errs = {"out": rel(y, ref)}
+    for n, a, r in zip(("dx", "dw", "db"), new_in, ref_in):
+        errs[n] = rel(a.grad, r.grad)
+    bad = {k: v for k, v in errs.items() if not v < TOL[dtype]}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("cfg", [(32, 32, 2, 16, False), (64, 128, 1, 8, False), (64, 32, 2, 8, True)],
+                         ids=lambda c: "dim%d_out%d_B%d_g%d_skip%d" % c)
+def test_block_matches_oracle(cfg, dtype):
+    """The whole Block (models/ADNMUNet.py:115-165) against the fp64 oracle: output, input gradients and every parameter
+    gradient; the same parameters are grad-less as in the reference (beta3, beta4, act.beta, the mixer's scale / shift / alpha2)."""
+    from adnm_unet_b200.block import make_block
+    dim, out_dim, B, g, skip = cfg
+    dev = torch.device("cuda:0")
+    p = BO.init_block_params(dim, out_dim, seed=13, perturb=0.1)
+    blk = make_block(dim, out_dim, headdim=4, d_state=16, norm_epsilon=1e-6)
+    blk.load_state_dict({k: v.float() for k, v in p.items()}, strict=True)
+    blk = blk.to(dev)
+    L = g * g
+    half = dim // 2 if skip else dim
+    x = cases.rng_normal(61, (B, L, half), torch.float32).to(dtype).float()
+    res = cases.rng_normal(62, (B, L, half), torch.float32).to(dtype).float() if skip else None
+    feat = cases.rng_normal(63, (B, L, half), torch.float32).to(dtype).float() if skip else None
+    rp = {k: _leaf(v) for k, v in p.items()}
+    xr = _leaf(x.double())
+    extra_r = [_leaf(t.double()) for t in (res, feat)] if skip else [None, None]
+    ref = BO.block_forward(rp, xr, g, g, 4, 16, residual=extra_r[0], features=extra_r[1])
+    dy = (ref.detach() / ref.detach().std() + 0.25 * cases.rng_normal(64, tuple(ref.shape), torch.float64)) / ref.numel()
+    dy = dy.to(dtype).double()
+    ref.backward(dy)
+    xn = _leaf(x, dev, dtype)
+    extra_n = [_leaf(t, dev, dtype) for t in (res, feat)] if skip else [None, None]
+    out = blk(xn, residual=extra_n[0], features=extra_n[1])
+    assert out.is_contiguous() and out.shape == ref.shape
+    out.backward(dy.to(dev, dtype))
+    torch.cuda.synchronize()
+    errs = {"out": rel(out, ref), "dx": rel(xn.grad, xr.grad)}
+    if skip:
+        errs["dresidual"], errs["dfeatures"] = rel(extra_n[0].grad, extra_r[0].grad), rel(extra_n[1].grad, extra_r[1].grad)
+    for k, v in blk.named_parameters():
+        r = rp[k].grad
+        if r is None or float(r.abs().max()) == 0.0:
+            assert v.grad is None or float(v.grad.abs().max()) == 0.0, k
+            continue
+        errs[k] = rel(v.grad, r)
+    # bf16: scalars and per-head vectors are sums over every token and channel that cancel (d scale1 = <dxn, norm(x)>, the
+    # decay parameters dt_bias / A_log: rounding noise of ~1e5 bf16 terms against a small total) - sanity-bounded at 1e-1
+    # like the perturbed mixer goldens (tests/test_mixer_gpu.py); every activation-sized or weight-matrix tensor at 2e-2.
+    nh = 2 * dim // 4
+    tol = {k: (1e-1 if dtype == torch.bfloat16 and k in rp and rp[k].numel() <= nh else TOL[dtype]) for k in errs}
+    bad = {k: v for k, v in errs.items() if not v < tol[k]}
+    assert not bad, bad
