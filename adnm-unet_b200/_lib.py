@@ -65,12 +65,14 @@ EXPORTS = {
                                   C.c_void_p, C.POINTER(WtWeightGrads), C.c_void_p, C.c_void_p]),
     "adn_threshold_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.c_int32, C.c_float,
                                        C.c_void_p, C.c_void_p]),
+    "adn_eval_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.POINTER(C.c_int32), C.c_int32, C.c_float,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "adn_sumsq_workspace_floats": (C.c_int, []),
     "adn_sumsq_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "adn_adamw_flat": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 5 +
                        [C.c_int32, C.c_float, C.c_float, C.c_void_p]),
     "adn_rmsnorm_forward": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
-    "adn_rmsnorm_backward": (C.c_int, [C.c_void_p] * 9 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "adn_rmsnorm_backward": (C.c_int, [C.c_void_p] * 10 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "adn_residual_forward": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "adn_residual_backward": (C.c_int, [C.c_void_p] * 12 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "adn_ffn_workspace_bytes": (C.c_int, [C.POINTER(AdnFfnShape)] + [C.POINTER(C.c_size_t)] * 3),
@@ -80,6 +82,8 @@ EXPORTS = {
     "adn_linear_workspace_bytes": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "adn_linear_forward": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "adn_linear_backward": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "adn_sdpa_forward": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_float, C.c_int32, C.c_void_p]),
+    "adn_sdpa_backward": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_float, C.c_int32, C.c_void_p]),
     "adn_last_error": (C.c_char_p, []),
     "adn_abi_version": (C.c_int, []),
     "adn_device_supported": (C.c_int, []),

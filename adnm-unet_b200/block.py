@@ -286,9 +286,10 @@ class Block(nn.Module):
             n1, n2 = self.norm1_layers[i], self.norm2_layers[i]
             b1, b2 = self.beta1[i], self.beta2[i]                  # beta3 / beta4 alias them (models/ADNMUNet.py:145-146)
             last = i == self.num_layers - 1
-            xn = rmsnorm_affine(x, n1.weight, self.scale1[i], self.shift1[i], n1.eps)
+            # x also feeds the residual mix: take it from the norm's pass-through output so that both gradients meet in one kernel
+            xn, x = rmsnorm_affine(x, n1.weight, self.scale1[i], self.shift1[i], n1.eps, passthrough=True)
             x = residual_mix(x, self.mixer_layers[i](xn, h, w), b1, b2)
-            xn = rmsnorm_affine(x, n2.weight, self.scale2[i], self.shift2[i], n2.eps)
+            xn, x = rmsnorm_affine(x, n2.weight, self.scale2[i], self.shift2[i], n2.eps, passthrough=True)
             x = residual_mix(x, self.ffns[i].forward_tokens(xn, h, w), b1, b2, self.gamma if last else None)
         if self.num_layers == 0:
             x = x * self.gamma.view(1, 1, -1)

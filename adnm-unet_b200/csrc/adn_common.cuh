@@ -57,6 +57,7 @@ struct EnvCfg {
   int du_dbg;         // ADN_DU_DBG       knock-out mask of k_bconv_du
   bool wide;          // ADN_WIDE=0       keeps d_model >= 64 on the CUDA-core generic path
   int gemm_dbg;       // ADN_GEMM_DBG     knock-out mask of the tcgen05 GEMM (profiling: results are wrong when set)
+  int variant;        // ADN_VARIANT      bit mask of kernel tuning variants under measurement (results identical)
 };
 const EnvCfg& env();
 

@@ -43,6 +43,7 @@ static EnvCfg& env_mut() {
     c.du_dbg = num("ADN_DU_DBG");
     c.wide = flag("ADN_WIDE", true);
     c.gemm_dbg = num("ADN_GEMM_DBG");
+    c.variant = num("ADN_VARIANT");
     return c;
   }();
   return cfg;
@@ -208,6 +209,7 @@ int adn_set_option(const char* name, int value) {
   else if (!strcmp(name, "rows_per_cta")) c.rows_per_cta = value;
   else if (!strcmp(name, "du_dbg")) c.du_dbg = value;
   else if (!strcmp(name, "gemm_dbg")) c.gemm_dbg = value;
+  else if (!strcmp(name, "variant")) c.variant = value;
   else { set_error("adn_set_option: unknown option '%s'", name); return ADN_ERR_SHAPE; }
   return ADN_OK;
 }

@@ -16,6 +16,20 @@
 namespace adn {
 namespace blk {
 
+__device__ __forceinline__ void ldg8(const bf16* p, float (&v)[8]) { sm100::unpack8(*reinterpret_cast<const uint4*>(p), v); }
+__device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void stg8(bf16* p, const float (&v)[8]) { *reinterpret_cast<uint4*>(p) = sm100::pack8(v); }
+__device__ __forceinline__ void stg8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+__device__ __forceinline__ void st2(bf16* p, float a, float b) { *reinterpret_cast<uint32_t*>(p) = sm100::pack_bf16(a, b); }
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+
 static inline int ew_grid(long long n) {
   long long b = (n + 255) / 256;
   long long cap = (long long)sm_count() * 16;
@@ -104,6 +118,70 @@ k_residual_bwd(const T* __restrict__ x, const T* __restrict__ y, const T* __rest
   }
 }
 
+// Same for D == 8 * G (G = 1 ... 32 lanes per token, 8 channels per lane; every width of ADNM-UNet up to 256): gamma and the
+// dgamma partial sums stay in registers for the whole pass (at D = 32 a warp handles 8 tokens per step).
+template <typename T, int G>
+__global__ void __launch_bounds__(256)
+k_residual_bwd_g(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ g, const float* __restrict__ b1p,
+                 const float* __restrict__ b2p, const float* __restrict__ gamma, T* __restrict__ dx, T* __restrict__ dy,
+                 double* __restrict__ acc2, float* __restrict__ dgamma, long long Ttok) {
+  constexpr int D = 8 * G, TPW = 32 / G;
+  __shared__ float sg[8][D];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = (lane % G) * 8;
+  const float b1 = *b1p, b2 = *b2p;
+  float ga[8], dgv[8] = {};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ga[i] = 1.f;
+  if (gamma) ldg8(gamma + c, ga);
+  double a1 = 0.0, a2 = 0.0;
+  const long long warps = (long long)gridDim.x * 8, gw = (long long)blockIdx.x * 8 + warp;
+  for (long long t0 = gw * TPW; t0 < Ttok; t0 += warps * TPW) {
+    const long long t = t0 + lane / G;
+    if (t < Ttok) {
+      float xv[8], yv[8], gv[8], ox[8], oy[8];
+      ldg8(x + t * D + c, xv); ldg8(y + t * D + c, yv); ldg8(g + t * D + c, gv);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float gg = gv[i] * ga[i];
+        ox[i] = b1 * gg;
+        oy[i] = b2 * gg;
+        s1 = fmaf(gg, xv[i], s1);
+        s2 = fmaf(gg, yv[i], s2);
+        dgv[i] = fmaf(gv[i], fmaf(b1, xv[i], b2 * yv[i]), dgv[i]);
+      }
+      stg8(dx + t * D + c, ox);
+      stg8(dy + t * D + c, oy);
+      a1 += (double)s1;
+      a2 += (double)s2;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if (lane == 0) { atomicAdd(acc2, a1); atomicAdd(acc2 + 1, a2); }
+  if (gamma) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int o = G; o < 32; o <<= 1) dgv[i] += __shfl_xor_sync(0xffffffffu, dgv[i], o);
+    }
+    if (lane < G) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sg[warp][c + i] = dgv[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v += sg[q][i];
+      if (v != 0.f) atomicAdd(dgamma + i, v);
+    }
+  }
+}
+
 __global__ void k_store_acc2(const double* __restrict__ acc2, float* __restrict__ d1, float* __restrict__ d2) {
   if (threadIdx.x == 0) { *d1 = (float)acc2[0]; *d2 = (float)acc2[1]; }
 }
@@ -167,65 +245,119 @@ static inline void launch_colsum(cudaStream_t st, const T* X, long long ld, floa
 
 // ---------------------------------------------------------------- FeedForward: depthwise 3x3 + gate, channels-last
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// bf16 storage: erf through Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below the bf16 rounding of the stored result) with
+// one fast exp, and the sigmoid through tanh.approx (one MUFU): the exact erff + expf pair made the gate the larger part of
+// k_ffn_conv_fwd's instruction stream.  fp32 storage (the 1e-4 check mode) keeps erff / expf.
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x), t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = 1.f - p * t * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <typename T> struct Gate {      // exact
+  static __device__ __forceinline__ float gelu(float x) { return gelu_f(x); }
+  static __device__ __forceinline__ float sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+};
+template <> struct Gate<bf16> {
+  static __device__ __forceinline__ float gelu(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f)); }
+  static __device__ __forceinline__ float sigmoid(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+};
 __device__ __forceinline__ float gelu_grad_f(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
 }
 
-constexpr int FROWS = 8;
+constexpr int FROWS = 4, FCOLS = 8;
+// Four channels of one token in storage form: loaded first (all taps of a thread's rows in flight together - the first
+// version converted and consumed row after row and was bound by one exposed memory latency per row: 388 us for 524 288
+// tokens x 128 channels, 9x its instruction-issue time), converted to fp32 when consumed.
+template <typename T> struct Raw4;
+template <> struct Raw4<bf16> {
+  uint2 v;
+  __device__ __forceinline__ void zero() { v = make_uint2(0u, 0u); }
+  __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ void get(float (&f)[4]) const {
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  }
+};
+template <> struct Raw4<float> {
+  float4 v;
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void get(float (&f)[4]) const { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+};
+// rows y0-1 .. y0+FROWS, columns x-1 .. x+1 of a channels-last tensor (row pitch ld), zero outside the image
+template <typename T>
+__device__ __forceinline__ void load_halo(const T* __restrict__ base, long long ld, int H, int W, int y0, int x, bool live,
+                                          Raw4<T> (&r)[FROWS + 2][3]) {
+#pragma unroll
+  for (int j = 0; j < FROWS + 2; ++j)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int yy = y0 - 1 + j, xx = x - 1 + s;
+      if (live && (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) r[j][s].load(base + ((long long)yy * W + xx) * ld);
+      else r[j][s].zero();
+    }
+}
+
 // a = dwconv3x3(h1; K) + b_dw over all C4 channels; gated[t][c] = gelu(a[t][c]) * sigmoid(a[t][C2 + c]).
-// thread = (4 channels of the first half + the matching 4 of the second half, one column x), walks FROWS rows with two 3x3
-// register windows.  block (8 channel groups, 32 columns); grid (ceil(C2/32), ceil(W/32), B * ceil(H/FROWS)).
+// A warp owns one column x and 64 + 64 channels: lanes 0-15 hold four channels each of the first half, lanes 16-31 the matching
+// channels of the second half (two 128-byte segments per token for bf16 - at C4 = 128 the whole 256-byte token), so the gate
+// partner of a lane sits 16 lanes away (one shuffle).  Each thread produces FROWS rows of its column.
+// block (32, FCOLS); grid (ceil(C2 / 64), ceil(W / FCOLS), B * ceil(H / FROWS)).
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_ffn_conv_fwd(const T* __restrict__ h1, const float* __restrict__ Kc, const float* __restrict__ b_dw, T* __restrict__ a_out,
                T* __restrict__ gated, int H, int W, int C4) {
-  const int C2 = C4 >> 1, CV = C2 >> 2;
-  const int cv = blockIdx.x * 8 + threadIdx.x;
-  const int x = blockIdx.y * 32 + threadIdx.y;
+  const int C2 = C4 >> 1;
+  const int lane = threadIdx.x, half = lane >> 4;
+  const int cl = (blockIdx.x * 16 + (lane & 15)) * 4;      // channel inside the half
+  const int x = blockIdx.y * FCOLS + threadIdx.y;
   const int ybl = cdiv(H, FROWS);
   const int b = blockIdx.z / ybl, y0 = (blockIdx.z % ybl) * FROWS;
-  if (cv >= CV || x >= W) return;
-  const int c0 = cv * 4;
-  float k1[9][4], k2[9][4], bi1[4], bi2[4];
+  const bool live = cl < C2 && x < W;
+  const int c0 = live ? half * C2 + cl : 0;
+  Raw4<T> raw[FROWS + 2][3];
+  load_halo<T>(h1 + (long long)b * H * W * C4 + c0, C4, H, W, y0, x, live, raw);
+  float k[9][4], bi[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
 #pragma unroll
-    for (int t = 0; t < 9; ++t) { k1[t][i] = Kc[(c0 + i) * 9 + t]; k2[t][i] = Kc[(C2 + c0 + i) * 9 + t]; }
-    bi1[i] = b_dw[c0 + i];
-    bi2[i] = b_dw[C2 + c0 + i];
+    for (int t = 0; t < 9; ++t) k[t][i] = Kc[(c0 + i) * 9 + t];
+    bi[i] = b_dw[c0 + i];
   }
-  const T* s1 = h1 + (long long)b * H * W * C4 + c0;
-  const T* s2 = s1 + C2;
-  float w1[3][3][4], w2[3][3][4];
-  load_row3(s1, C4, W, y0 - 1, H, x, w1[0]); load_row3(s2, C4, W, y0 - 1, H, x, w2[0]);
-  load_row3(s1, C4, W, y0, H, x, w1[1]); load_row3(s2, C4, W, y0, H, x, w2[1]);
-  const int y1 = min(H, y0 + FROWS);
-  for (int y = y0; y < y1; ++y) {
-    load_row3(s1, C4, W, y + 1, H, x, w1[2]); load_row3(s2, C4, W, y + 1, H, x, w2[2]);
-    float a1[4], a2[4], o[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { a1[i] = bi1[i]; a2[i] = bi2[i]; }
+  for (int j = 0; j < FROWS; ++j) {
+    float a[4], o[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = bi[i];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int s = 0; s < 3; ++s)
+      for (int s = 0; s < 3; ++s) {
+        float v[4];
+        raw[j + r][s].get(v);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          a1[i] = fmaf(k1[r * 3 + s][i], w1[r][s][i], a1[i]);
-          a2[i] = fmaf(k2[r * 3 + s][i], w2[r][s][i], a2[i]);
-        }
-    const long long tok = ((long long)b * H + y) * W + x;
-    if (a_out) { st4(a_out + tok * C4 + c0, a1); st4(a_out + tok * C4 + C2 + c0, a2); }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = gelu_f(a1[i]) * sigmoid_t<T>(a2[i]);
-    st4(gated + tok * C2 + c0, o);
-#pragma unroll
-    for (int s = 0; s < 3; ++s)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        w1[0][s][i] = w1[1][s][i]; w1[1][s][i] = w1[2][s][i];
-        w2[0][s][i] = w2[1][s][i]; w2[1][s][i] = w2[2][s][i];
+        for (int i = 0; i < 4; ++i) a[i] = fmaf(k[r * 3 + s][i], v[i], a[i]);
       }
+    // gate: the lower lane of a pair takes channels 0-1, the upper lane channels 2-3 (both halves of the warp busy)
+    //   lower needs a2[0..1] of the upper lane, upper needs a1[2..3] of the lower lane
+    const float s0 = half ? a[0] : a[2], s1 = half ? a[1] : a[3];
+    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+    const int y = y0 + j;
+    if (live && y < H) {
+      const long long tok = ((long long)b * H + y) * W + x;
+      if (a_out) st4(a_out + tok * C4 + c0, a);
+      const float g0 = half ? r0 : a[0], g1 = half ? r1 : a[1];      // first-half values (gelu side)
+      const float q0 = half ? a[2] : r0, q1 = half ? a[3] : r1;      // second-half values (sigmoid side)
+      o[0] = Gate<T>::gelu(g0) * Gate<T>::sigmoid(q0);
+      o[1] = Gate<T>::gelu(g1) * Gate<T>::sigmoid(q1);
+      st2(gated + tok * C2 + cl + 2 * half, o[0], o[1]);
+    }
   }
 }
 
@@ -252,22 +384,21 @@ k_ffn_gate_bwd(const T* __restrict__ a, const T* __restrict__ dg, T* __restrict_
 }
 
 // dh1 = conv^T(da);  dK[c][a][b] += h1[y, x, c] da[y-a+1, x-b+1, c];  db_dw[c] += da;  db_in[c] += dh1.
-// thread = (4 channels, one column); blockIdx.z strides over the (sample, row block) work items so that the 44 partial sums
-// of a thread stay in registers over the whole pass (one shared-memory reduction + 44 x 32 global atomics per block).
-template <typename T>
-__global__ void __launch_bounds__(256)
+// thread = (4 channels, one column): a warp covers 128 consecutive channels of one token (256 contiguous bytes for bf16);
+// blockIdx.z strides over the (sample, row block) work items so that the 44 partial sums of a thread stay in registers over
+// the whole pass (one shared-memory reduction over the FCOLS warps + 44 x 128 global atomics per block).  All loads of a
+// work item (da halo + h1 rows) are issued before the first use.
+template <typename T, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_ffn_conv_bwd(const T* __restrict__ da, const T* __restrict__ h1, const float* __restrict__ Kc, T* __restrict__ dh1,
                float* __restrict__ dK, float* __restrict__ db_dw, float* __restrict__ db_in, int Bn, int H, int W, int C4) {
-  __shared__ float red[8][44];
-  const int CV = C4 >> 2;
-  const int cv = blockIdx.x * 8 + threadIdx.x;
-  const int x = blockIdx.y * 32 + threadIdx.y;
+  __shared__ float red[32][45];
+  const int c0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int x = blockIdx.y * FCOLS + threadIdx.y;
   const int ybl = cdiv(H, FROWS);
-  const int tid = threadIdx.y * 8 + threadIdx.x;
-  for (int i = tid; i < 8 * 44; i += 256) (&red[0][0])[i] = 0.f;
-  __syncthreads();
-  const bool active = (cv < CV && x < W);
-  const int c0 = cv * 4;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int i = tid; i < 32 * 45; i += 256) (&red[0][0])[i] = 0.f;
+  const bool active = (c0 < C4 && x < W);
   float dk[9][4] = {}, sda[4] = {}, sdh[4] = {};
   if (active) {
     float k[9][4];
@@ -278,52 +409,55 @@ k_ffn_conv_bwd(const T* __restrict__ da, const T* __restrict__ h1, const float* 
     for (int z = blockIdx.z; z < Bn * ybl; z += gridDim.z) {
       const int b = z / ybl, y0 = (z - b * ybl) * FROWS;
       const long long boff = (long long)b * H * W;
-      const T* g = da + boff * C4 + c0;
-      float win[3][3][4];
-      load_row3(g, C4, W, y0 - 1, H, x, win[0]);
-      load_row3(g, C4, W, y0, H, x, win[1]);
-      const int y1 = min(H, y0 + FROWS);
-      for (int y = y0; y < y1; ++y) {
-        load_row3(g, C4, W, y + 1, H, x, win[2]);
+      Raw4<T> raw[FROWS + 2][3], rh[FROWS];
+      load_halo<T>(da + boff * C4 + c0, C4, H, W, y0, x, true, raw);
+#pragma unroll
+      for (int j = 0; j < FROWS; ++j) {
+        if (y0 + j < H) rh[j].load(h1 + (boff + (long long)(y0 + j) * W + x) * C4 + c0);
+        else rh[j].zero();
+      }
+#pragma unroll
+      for (int j = 0; j < FROWS; ++j) {
         float rc[4], o[4] = {0.f, 0.f, 0.f, 0.f};
-        const long long tok = boff + (long long)y * W + x;
-        ld4(h1 + tok * C4 + c0, rc);
+        rh[j].get(rc);
+        // halo row j + r holds da row y0 + j - 1 + r: tap (a, b) reads da[y - a + 1][x - b + 1] = halo row j + 2 - a, column 2 - b
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
-          for (int bb = 0; bb < 3; ++bb)
+          for (int bb = 0; bb < 3; ++bb) {
+            float d[4];
+            raw[j + 2 - a][2 - bb].get(d);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float d = win[2 - a][2 - bb][i];
-              o[i] = fmaf(k[a * 3 + bb][i], d, o[i]);
-              dk[a * 3 + bb][i] = fmaf(rc[i], d, dk[a * 3 + bb][i]);
+              o[i] = fmaf(k[a * 3 + bb][i], d[i], o[i]);
+              dk[a * 3 + bb][i] = fmaf(rc[i], d[i], dk[a * 3 + bb][i]);
             }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { sda[i] += win[1][1][i]; sdh[i] += o[i]; }
-        st4(dh1 + tok * C4 + c0, o);
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            win[0][s][i] = win[1][s][i];
-            win[1][s][i] = win[2][s][i];
           }
+        if (y0 + j < H) {
+          float ctr[4];
+          raw[j + 1][1].get(ctr);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { sda[i] += ctr[i]; sdh[i] += o[i]; }
+          st4(dh1 + (boff + (long long)(y0 + j) * W + x) * C4 + c0, o);
+        }
       }
     }
   }
-  // lanes of a warp = 4 columns x 8 channel groups: fold the columns, then the 8 warps through shared memory
+  // fold the FCOLS column warps of the block, one after the other, then one atomic per (channel, sum)
+  for (int w = 0; w < FCOLS; ++w) {
+    __syncthreads();
+    if ((int)threadIdx.y == w && active) {
 #pragma unroll
-  for (int t = 0; t < 11; ++t)
+      for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float v = t < 9 ? dk[t < 9 ? t : 0][i] : (t == 9 ? sda[i] : sdh[i]);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if ((tid & 31) < 8) atomicAdd(&red[threadIdx.x][t * 4 + i], v);
+        for (int i = 0; i < 4; ++i) red[threadIdx.x][t * 4 + i] += dk[t][i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { red[threadIdx.x][36 + i] += sda[i]; red[threadIdx.x][40 + i] += sdh[i]; }
     }
+  }
   __syncthreads();
-  for (int i = tid; i < 8 * 44; i += 256) {
-    const int v = i / 44, r = i % 44, t = r >> 2, ch = (blockIdx.x * 8 + v) * 4 + (r & 3);
+  for (int i = tid; i < 32 * 44; i += 256) {
+    const int v = i / 44, r = i % 44, t = r >> 2, ch = (blockIdx.x * 32 + v) * 4 + (r & 3);
     if (ch >= C4) continue;
     const float val = red[v][r];
     if (t < 9) atomicAdd(dK + ch * 9 + t, val);
@@ -467,7 +601,7 @@ static int ffn_forward(const FfnDims& d, int dtype, const AdnFfnWeights& w, cons
   int rc = gemm_xwT<T>(st, "ffn_project_in", tc, x, d.T, d.D, (const float*)w.w_in, W.w_in, d.C4, (const float*)w.b_in, h1, W.status);
   if (rc) return rc;
   {
-    dim3 grid(cdiv(d.C2 / 4, 8), cdiv(d.W, 32), d.B * cdiv(d.H, FROWS)), block(8, 32);
+    dim3 grid(cdiv(d.C2, 64), cdiv(d.W, FCOLS), d.B * cdiv(d.H, FROWS)), block(32, FCOLS);
     ADN_KERNEL("k_ffn_conv_fwd", st);
     k_ffn_conv_fwd<T><<<grid, block, 0, st>>>(h1, (const float*)w.w_dw, (const float*)w.b_dw, training ? S.a : nullptr, gated, d.H, d.W, d.C4);
   }
@@ -505,13 +639,17 @@ static int ffn_backward(const FfnDims& d, int dtype, const AdnFfnWeights& w, con
   // gate + depthwise conv backward
   { ADN_KERNEL("k_ffn_gate_bwd", st); k_ffn_gate_bwd<T><<<ew_grid(d.T * (d.C2 / 4)), 256, 0, st>>>(S.a, W.dgated, W.da, d.T, d.C4); }
   {
-    const int gx = cdiv(d.C4 / 4, 8), gy = cdiv(d.W, 32), items = d.B * cdiv(d.H, FROWS);
+    const int gx = cdiv(d.C4, 128), gy = cdiv(d.W, FCOLS), items = d.B * cdiv(d.H, FROWS);
     int gz = cdiv(8LL * sm_count(), (long long)gx * gy);
     gz = gz < 1 ? 1 : (gz > items ? items : gz);
-    dim3 grid(gx, gy, gz), block(8, 32);
+    dim3 grid(gx, gy, gz), block(32, FCOLS);
     ADN_KERNEL("k_ffn_conv_bwd", st);
-    k_ffn_conv_bwd<T><<<grid, block, 0, st>>>(W.da, S.h1, (const float*)w.w_dw, W.dh1, (float*)g.w_dw, (float*)g.b_dw, (float*)g.b_in, d.B, d.H,
-                                              d.W, d.C4);
+    if (env().variant & 1)
+      k_ffn_conv_bwd<T, 2><<<grid, block, 0, st>>>(W.da, S.h1, (const float*)w.w_dw, W.dh1, (float*)g.w_dw, (float*)g.b_dw, (float*)g.b_in, d.B,
+                                                   d.H, d.W, d.C4);
+    else
+      k_ffn_conv_bwd<T, 1><<<grid, block, 0, st>>>(W.da, S.h1, (const float*)w.w_dw, W.dh1, (float*)g.w_dw, (float*)g.b_dw, (float*)g.b_in, d.B,
+                                                   d.H, d.W, d.C4);
   }
   // project_in backward
   rc = gemm_xw<T>(st, "ffn_dx", tc, W.dh1, d.T, d.C4, (const float*)w.w_in, W.w_in, d.D, dx, W.status);
@@ -557,12 +695,24 @@ int adn_residual_backward(const void* x, const void* y, const void* dout, const 
   double* acc2 = (double*)ws;
   ADN_CHECK_CUDA(cudaMemsetAsync(acc2, 0, 2 * sizeof(double), st));
   if (gamma) ADN_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)D * sizeof(float), st));
-  long long tpw = tokens / (16LL * sm_count());
-  tpw = tpw < 1 ? 1 : (tpw > 64 ? 64 : tpw);
-  const int grid = cdiv(tokens, 8 * tpw);
-  const size_t smem = (size_t)D * sizeof(float);
-  if (dtype == ADN_F32) { ADN_KERNEL("k_residual_bwd", st); k_residual_bwd<float><<<grid, 256, smem, st>>>((const float*)x, (const float*)y, (const float*)dout, beta1, beta2, gamma, (float*)dx, (float*)dy, acc2, dgamma, tokens, (int)tpw, D); }
-  else { ADN_KERNEL("k_residual_bwd", st); k_residual_bwd<bf16><<<grid, 256, smem, st>>>((const bf16*)x, (const bf16*)y, (const bf16*)dout, beta1, beta2, gamma, (bf16*)dx, (bf16*)dy, acc2, dgamma, tokens, (int)tpw, D); }
+  if (D % 8 == 0 && D <= 256 && ((D / 8) & (D / 8 - 1)) == 0) {
+    const long long tpw = 32 / (D / 8), want = (tokens + 8 * tpw - 1) / (8 * tpw), cap = 4LL * sm_count();
+    const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    ADN_KERNEL("k_residual_bwd_g", st);
+#define RES_G(T, Gn) k_residual_bwd_g<T, Gn><<<grid, 256, 0, st>>>((const T*)x, (const T*)y, (const T*)dout, beta1, beta2, gamma, (T*)dx, (T*)dy, acc2, dgamma, tokens)
+#define RES_G_ALL(T) switch (D / 8) { case 1: RES_G(T, 1); break; case 2: RES_G(T, 2); break; case 4: RES_G(T, 4); break; case 8: RES_G(T, 8); break; \
+                                      case 16: RES_G(T, 16); break; default: RES_G(T, 32); break; }
+    if (dtype == ADN_F32) { RES_G_ALL(float) } else { RES_G_ALL(bf16) }
+#undef RES_G_ALL
+#undef RES_G
+  } else {
+    long long tpw = tokens / (16LL * sm_count());
+    tpw = tpw < 1 ? 1 : (tpw > 64 ? 64 : tpw);
+    const int grid = cdiv(tokens, 8 * tpw);
+    const size_t smem = (size_t)D * sizeof(float);
+    if (dtype == ADN_F32) { ADN_KERNEL("k_residual_bwd", st); k_residual_bwd<float><<<grid, 256, smem, st>>>((const float*)x, (const float*)y, (const float*)dout, beta1, beta2, gamma, (float*)dx, (float*)dy, acc2, dgamma, tokens, (int)tpw, D); }
+    else { ADN_KERNEL("k_residual_bwd", st); k_residual_bwd<bf16><<<grid, 256, smem, st>>>((const bf16*)x, (const bf16*)y, (const bf16*)dout, beta1, beta2, gamma, (bf16*)dx, (bf16*)dy, acc2, dgamma, tokens, (int)tpw, D); }
+  }
   { ADN_KERNEL("k_store_acc2", st); k_store_acc2<<<1, 32, 0, st>>>(acc2, dbeta1, dbeta2); }
   ADN_CHECK_LAUNCH();
   return ADN_OK;

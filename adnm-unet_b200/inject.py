@@ -23,6 +23,7 @@ def install_into_reference(adnmunet_module="models.ADNMUNet", untils_module="mod
         from adnm_unet_b200.block import Block
         from adnm_unet_b200.rmsnorm import RMSNorm
         m = importlib.import_module(adnmunet_module)
-        m.Block, m.RMSNorm = Block, RMSNorm
-        done += [adnmunet_module + ".Block", adnmunet_module + ".RMSNorm"]
+        from adnm_unet_b200.attention import StandardAttention
+        m.Block, m.RMSNorm, m.StandardAttention = Block, RMSNorm, StandardAttention
+        done += [adnmunet_module + ".Block", adnmunet_module + ".RMSNorm", adnmunet_module + ".StandardAttention"]
     return done

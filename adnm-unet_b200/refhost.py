@@ -179,6 +179,7 @@ def load_reference():
     ns.ref_Mamba2 = ns.ADNssd.Mamba2          # the reference's own classes, whatever the globals are rebound to later
     ns.ref_WTConv2d = ns.WTConv2d.WTConv2d
     ns.ref_Block, ns.ref_RMSNorm = ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm
+    ns.ref_StandardAttention = ns.ADNssd.StandardAttention
     _patch_decoder_size(ns.ADNMUNet)
     _NS = ns
     return ns
@@ -203,8 +204,9 @@ def _patch_decoder_size(mod):
 @contextlib.contextmanager
 def _bound(ns, dropin, mixer=True, wtconv=True, block=True):
     """Rebind (or restore) the construction-time globals for the duration of a model build: the mixer and WTConv2d classes
-     and, with `block`, the `Block` / `RMSNorm` names `create_block` resolves (models/ADNMUNet.py:277-291)."""
-    old = (ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d, ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm)
+     and, with `block`, the `Block` / `RMSNorm` names `create_block` resolves (models/ADNMUNet.py:277-291)
+    and the `StandardAttention` name `Attention` resolves (models/ADNMUNet.py:181)."""
+    old = (ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d, ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm, ns.ADNMUNet.StandardAttention)
     if dropin:
         from adnm_unet_b200.mixer import Mamba2
         from adnm_unet_b200.wtconv import WTConv2d
@@ -215,14 +217,15 @@ def _bound(ns, dropin, mixer=True, wtconv=True, block=True):
         if wtconv:
             ns.model_untils.WTConv2d = WTConv2d
         if block:
-            ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm = Block, RMSNorm
+            from adnm_unet_b200.attention import StandardAttention
+            ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm, ns.ADNMUNet.StandardAttention = Block, RMSNorm, StandardAttention
     else:
         ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d = ns.ref_Mamba2, ns.ref_WTConv2d
-        ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm = ns.ref_Block, ns.ref_RMSNorm
+        ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm, ns.ADNMUNet.StandardAttention = ns.ref_Block, ns.ref_RMSNorm, ns.ref_StandardAttention
     try:
         yield
     finally:
-        ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d, ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm = old
+        ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d, ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm, ns.ADNMUNet.StandardAttention = old
 
 
 def build_adnm_unet(img_size=256, dropin=True, input_frames=5, output_frames=20, seed=0, mixer=True, wtconv=True, block=True):

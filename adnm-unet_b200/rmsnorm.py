@@ -9,8 +9,13 @@ from adnm_unet_b200 import _lib
 
 
 class _RmsNormFunction(torch.autograd.Function):
+    """`passthrough`: also return x itself as a second output.  The Block feeds that alias to its residual mix
+    (models/ADNMUNet.py:152), so the gradient of the residual path arrives HERE and is added to the norm's own dx inside the
+    backward kernel - one pass and one rounding instead of autograd's separate accumulation of two bf16 tensors."""
+
     @staticmethod
-    def forward(ctx, x, weight, scale, shift, eps, grad_mode):
+    def forward(ctx, x, weight, scale, shift, eps, grad_mode, passthrough=False):
+        ctx.set_materialize_grads(False)
         _lib.require_cuda(x, "x")
         lib = _lib.load()
         x = x.contiguous()
@@ -26,32 +31,37 @@ class _RmsNormFunction(torch.autograd.Function):
         if need_grad:
             ctx.save_for_backward(x, w, scale, shift, rstd)
             ctx.wdtype = weight.dtype
-        return y
+        return (y, x.view_as(x)) if passthrough else y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dres=None):
         lib = _lib.load()
         x, w, scale, shift, rstd = ctx.saved_tensors
         D = x.shape[-1]
         tokens = x.numel() // D
+        if dy is None:                       # only the pass-through output was used
+            return (dres,) + (None,) * 6
         dy = dy.to(x.dtype).contiguous()
+        if dres is not None:
+            dres = dres.to(x.dtype).contiguous()
         dx = torch.empty_like(x)
         flat = torch.empty(D + 2, dtype=torch.float32, device=x.device)
         dw, dscale, dshift = flat[:D], flat[D:D + 1], flat[D + 1:]
         with _lib.on_device(x.device):
-            _lib.check(lib.adn_rmsnorm_backward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(scale), _lib.ptr(rstd), _lib.ptr(dy), _lib.ptr(dx),
-                                                _lib.ptr(dw), _lib.ptr(dscale) if scale is not None else None,
+            _lib.check(lib.adn_rmsnorm_backward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(scale), _lib.ptr(rstd), _lib.ptr(dy), _lib.ptr(dres),
+                                                _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(dscale) if scale is not None else None,
                                                 _lib.ptr(dshift) if shift is not None else None, tokens, D, _lib.dtype_code(x),
                                                 _lib.stream_ptr(x.device)), "adn_rmsnorm_backward")
         ni = ctx.needs_input_grad
         return (dx if ni[0] else None, dw.to(ctx.wdtype) if ni[1] else None,
                 dscale.reshape(scale.shape) if scale is not None and ni[2] else None,
-                dshift.reshape(shift.shape) if shift is not None and ni[3] else None, None, None)
+                dshift.reshape(shift.shape) if shift is not None and ni[3] else None, None, None, None)
 
 
-def rmsnorm_affine(x, weight, scale=None, shift=None, eps=1e-5):
-    """scale * (x * rsqrt(mean(x^2, -1) + eps) * weight) + shift; scale / shift are 0-dim fp32 tensors or None."""
-    return _RmsNormFunction.apply(x, weight, scale, shift, eps, torch.is_grad_enabled())
+def rmsnorm_affine(x, weight, scale=None, shift=None, eps=1e-5, passthrough=False):
+    """scale * (x * rsqrt(mean(x^2, -1) + eps) * weight) + shift; scale / shift are 0-dim fp32 tensors or None.
+    passthrough=True returns (y, x_alias): use x_alias for the residual branch (see _RmsNormFunction)."""
+    return _RmsNormFunction.apply(x, weight, scale, shift, eps, torch.is_grad_enabled(), passthrough)
 
 
 class RMSNorm(nn.Module):

@@ -145,6 +145,18 @@ int wtconv_backward(const WtShape* s, const WtWeights* w, const void* x, const v
 int adn_threshold_counts(const float* obs, const float* sim, int64_t n, const int32_t* thresholds,
                          int32_t n_thresholds, float value_scale, int64_t* table, void* stream);
 
+/* One batch of SimplifiedEvaluator.evaluate (datasets/Shanghai_metrics.py:49-103) on device, replacing the per-batch
+ * .cpu().numpy() + Python loops over batch x frame x threshold of validate.py:100-118:
+ *   true_batch, pred_batch: [batch][seq_len][frame_elems] float32 (declared argument order of evaluate, :49);
+ *   table[t*4 + {TP,FN,FP,TN}] += the counts of every frame (same quantisation as adn_threshold_counts), int64, ACCUMULATED
+ *     (zero it when the evaluator is reset);
+ *   mse_t[t] += sum_b mean((clip(pred)*scale - clip(true)*scale)^2) of frame (b, t)  (:116-121), fp64, ACCUMULATED: `done`
+ *     (:276) computes RMSE = mean_t sqrt(mse_t[t] / total_samples).
+ * `thresholds` is a HOST pointer; batch * seq_len <= 65535 per call. */
+int adn_eval_batch(const float* true_batch, const float* pred_batch, int64_t batch, int32_t seq_len, int64_t frame_elems,
+                   const int32_t* thresholds, int32_t n_thresholds, float value_scale, int64_t* table, double* mse_t,
+                   void* stream);
+
 /* ------------------------------------------------------------------ training-step tail ----- */
 
 /* Flat-buffer tail of one data-parallel training step, replacing train.py:140-145 of the reference
@@ -170,11 +182,14 @@ int adn_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const floa
  *     y = scale * (x * rsqrt(mean(x^2) + eps) * weight) + shift          per token over D
  * x, y, dy, dx: [tokens][D] contiguous, dtype ADN_F32 or ADN_BF16; weight / scale / shift / rstd / gradients fp32.
  * scale / shift may be NULL (1 and 0: the bare RMSNorm module).  rstd ([tokens], optional in forward) is what backward needs
- * besides x.  dweight / dscale / dshift are OVERWRITTEN (dscale / dshift may be NULL).  D % 4 == 0, D <= 8192. */
+ * besides x.  dweight / dscale / dshift are OVERWRITTEN (dscale / dshift may be NULL).  D % 4 == 0, D <= 8192.
+ * dres (optional, [tokens][D]) is added to dx: the gradient reaching x through the Block's residual path (ADNMUNet.py:152),
+ * so the sum of the two branches is formed in fp32 and rounded once. */
 int adn_rmsnorm_forward(const void* x, const float* weight, const float* scale, const float* shift, void* y, float* rstd,
                         int64_t tokens, int32_t D, float eps, int32_t dtype, void* stream);
-int adn_rmsnorm_backward(const void* x, const float* weight, const float* scale, const float* rstd, const void* dy, void* dx,
-                         float* dweight, float* dscale, float* dshift, int64_t tokens, int32_t D, int32_t dtype, void* stream);
+int adn_rmsnorm_backward(const void* x, const float* weight, const float* scale, const float* rstd, const void* dy,
+                         const void* dres, void* dx, float* dweight, float* dscale, float* dshift, int64_t tokens, int32_t D,
+                         int32_t dtype, void* stream);
 
 /* Residual mix of the Block (models/ADNMUNet.py:152,158,161): out = (beta1 * x + beta2 * y) * gamma[c]; gamma NULL = no
  * per-channel scale.  x, y, out, dout, dx, dy: [tokens][D] contiguous (dtype); beta1 / beta2: device scalars; gamma (D) fp32.
@@ -216,6 +231,18 @@ int adn_linear_forward(const void* x, const float* w, const float* bias, void* y
                        int32_t dtype, void* workspace, void* stream);
 int adn_linear_backward(const void* x, const float* w, const void* dy, void* dx, float* dw, float* dbias, int64_t tokens,
                         int32_t K, int32_t N, int32_t dtype, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------ fused attention --------- */
+
+/* Core of StandardAttention (models/ADNssd.py:41-46; the Attention bridges, models/ADNMUNet.py:172-238), SURVEY.md 8(f)3:
+ *   out[b][i][h*dh + d] = sum_j softmax_j(scale * q_i . k_j) v_j[d]      per sample b and head h
+ * qkv: [B][L][3 * heads * dh], the packed to_qkv output (q | k | v, each in '(h d)' order); out / dout: [B][L][heads * dh];
+ * dqkv: like qkv (OVERWRITTEN); lse: [B][heads][L] fp32, written by forward (may be NULL for inference), read by backward.
+ * dh in {4, 8, 16} (ADNM-UNet: 4).  The L x L score matrix is never materialised. */
+int adn_sdpa_forward(const void* qkv, void* out, float* lse, int32_t B, int32_t L, int32_t heads, int32_t dh, float scale,
+                     int32_t dtype, void* stream);
+int adn_sdpa_backward(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, int32_t B, int32_t L,
+                      int32_t heads, int32_t dh, float scale, int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------ misc ------------------- */
 

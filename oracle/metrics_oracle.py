@@ -37,3 +37,22 @@ def scores(table):
         return {"CSI": TP / (TP + FP + FN), "POD": TP / (TP + FN),
                 "HSS": (2 * (TP * TN - FP * FN)) / (FP ** 2 + FN ** 2 + 2 * TP * TN + (FP + FN) * (TP + TN)),
                 "FAR": FP / (TP + FP)}
+
+
+def evaluator_done(batches, thresholds=THRESHOLDS, value_scale=VALUE_SCALE):
+    """`SimplifiedEvaluator.evaluate` over `batches` = [(true_batch, pred_batch), ...] (declared argument order, :49) and
+    then `done` (:218-290), restated without the per-frame Python loops: threshold_metrics (TP/TN/FP/FN/CSI/POD/HSS), FAR and
+    RMSE = mean_t sqrt(mean_b mse[b][t]) with mse on the clipped frames times value_scale, fp32 like the reference (:116-121,276)."""
+    table = np.zeros((len(thresholds), 4), dtype=np.int64)
+    mse = []
+    for tb, pb in batches:
+        tb = np.clip(np.asarray(tb, dtype=np.float32), 0.0, 1.0)
+        pb = np.clip(np.asarray(pb, dtype=np.float32), 0.0, 1.0)
+        table += counts(tb, pb, thresholds, value_scale)
+        d = pb * np.float32(value_scale) - tb * np.float32(value_scale)
+        mse.append(np.mean(d.reshape(d.shape[0], d.shape[1], -1) ** 2, axis=2))
+    mse = np.concatenate(mse, axis=0)
+    sc = scores(table)
+    tm = {thr: {"TP": float(table[i, 0]), "TN": float(table[i, 3]), "FP": float(table[i, 2]), "FN": float(table[i, 1]),
+                "CSI": sc["CSI"][i], "POD": sc["POD"][i], "HSS": sc["HSS"][i]} for i, thr in enumerate(thresholds)}
+    return {"threshold_metrics": tm, "FAR": float(np.mean(sc["FAR"])), "RMSE": float(np.mean(np.sqrt(np.mean(mse, axis=0))))}

@@ -111,3 +111,28 @@ def corr_dout(out_ref, seed, frac=CORR_FRACTION):
 def mixer_corr_dout(name, out_ref):
     seed = 5500 + sorted(MIXER_CORR_CASES).index(name)
     return corr_dout(out_ref, seed)
+
+
+# Block goldens (SURVEY.md 8(c) golden (2)): the reference `Block` (models/ADNMUNet.py:49-165) as `create_block` builds it
+# (headdim 4, d_state 16, RMSNorm eps 1e-6), perturbed parameters (oracle.block_oracle.init_block_params), fp64.
+# name -> (dim, out_dim, batch, grid, skip): skip = called with `residual` and `features` (the decoder call, :124-129)
+BLOCK_CASES = {
+    "block_d32_o32_g16": (32, 32, 2, 16, False),
+    "block_d64_o128_g8": (64, 128, 1, 8, False),
+    "block_d64_o32_g8_skip": (64, 32, 2, 8, True),
+}
+
+
+def block_inputs(name, dtype=torch.float64):
+    dim, out_dim, B, g, skip = BLOCK_CASES[name]
+    seed = 6000 + 10 * sorted(BLOCK_CASES).index(name)
+    half = dim // 2 if skip else dim
+    x = bf16_exact(rng_normal(seed, (B, g * g, half), torch.float32)).to(dtype)
+    res = bf16_exact(rng_normal(seed + 1, (B, g * g, half), torch.float32)).to(dtype) if skip else None
+    feat = bf16_exact(rng_normal(seed + 2, (B, g * g, half), torch.float32)).to(dtype) if skip else None
+    return x, res, feat
+
+
+def block_dout(name, out_ref):
+    seed = 6500 + sorted(BLOCK_CASES).index(name)
+    return corr_dout(out_ref, seed, frac=1.0) / out_ref.numel()

@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 import cases  # noqa: E402
 from ref_loader import cuda_to_is_noop, load_reference  # noqa: E402
-from oracle import adnssd_oracle, wtconv_oracle  # noqa: E402
+from oracle import adnssd_oracle, block_oracle, wtconv_oracle  # noqa: E402
 
 
 def save(name, **arrays):
@@ -109,6 +109,27 @@ def wtconv_case(ref, name):
     save(name, **arrays)
 
 
+def block_case(ref, name):
+    """The unmodified reference Block (models/ADNMUNet.py:49-165) via create_block, fp64, CPU."""
+    dim, out_dim, B, g, skip = cases.BLOCK_CASES[name]
+    p32 = block_oracle.init_block_params(dim, out_dim, headdim=4, d_state=16, seed=23, perturb=0.1, dtype=torch.float32)
+    blk = ref.ADNMUNet.create_block(dim, out_dim, headdim=4, norm_epsilon=1e-6, layer_idx=0).double()
+    blk.load_state_dict({k: v.double() for k, v in p32.items()}, strict=True)
+    x, res, feat = (None if t is None else t.requires_grad_(True) for t in cases.block_inputs(name, torch.float64))
+    with cuda_to_is_noop():
+        out = blk(x, residual=res, features=feat)
+    dout = cases.block_dout(name, out.detach())
+    out.backward(dout.double())
+    arrays = {"param/" + k: v.numpy() for k, v in p32.items()}
+    arrays.update(out=out.detach().numpy(), dx=x.grad.numpy())
+    if skip:
+        arrays.update(dresidual=res.grad.numpy(), dfeatures=feat.grad.numpy())
+    for k, v in blk.named_parameters():
+        if v.grad is not None:
+            arrays["grad/" + k] = v.grad.numpy()
+    save(name, **arrays)
+
+
 def metrics_case():
     """Counts from the reference's own float2int / _cal_frame (datasets/Shanghai_metrics.py:45-47,105-114).
     The class constructor needs `lpips` (absent, downloads weights) so the two methods are called unbound."""
@@ -147,6 +168,9 @@ def main():
     for name in cases.WTCONV_CASES:
         if not only or name in only:
             wtconv_case(ref, name)
+    for name in cases.BLOCK_CASES:
+        if not only or name in only:
+            block_case(ref, name)
     if not only or cases.METRIC_CASE[0] in only:
         metrics_case()
 

@@ -8,6 +8,7 @@ import torch
 
 import cases
 from oracle import adnssd_oracle as AO
+from oracle import block_oracle as BO
 from oracle import metrics_oracle as MO
 from oracle import wtconv_oracle as WO
 
@@ -124,3 +125,86 @@ def test_metric_counts_match_reference(golden_dir):
     # CSI and HSS are symmetric under the FP<->FN swap the reference's call order introduces
     sw = MO.scores(table[:, [0, 2, 1, 3]])
     assert np.allclose(sw["CSI"], sc["CSI"]) and np.allclose(sw["HSS"], sc["HSS"])
+
+
+@pytest.mark.parametrize("name", sorted(cases.BLOCK_CASES))
+def test_block_oracle_matches_reference_fp64(golden_dir, name):
+    """oracle/block_oracle.py against the unmodified reference Block (goldens made by tests/golden/make_golden.py)."""
+    dim, out_dim, B, g, skip = cases.BLOCK_CASES[name]
+    z, params, grads = load(golden_dir, name)
+    p = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    x, res, feat = (None if t is None else t.requires_grad_(True) for t in cases.block_inputs(name, torch.float64))
+    out = BO.block_forward(p, x, g, g, 4, 16, residual=res, features=feat)
+    assert rel(out.detach(), z["out"]) < 1e-12
+    out.backward(cases.block_dout(name, torch.from_numpy(z["out"])).double())
+    assert rel(x.grad, z["dx"]) < 1e-11
+    if skip:
+        assert rel(res.grad, z["dresidual"]) < 1e-11 and rel(feat.grad, z["dfeatures"]) < 1e-11
+    live = {k for k, v in p.items() if v.grad is not None and float(v.grad.abs().max()) > 0}
+    assert live == set(grads), live ^ set(grads)
+    for k, ref in grads.items():
+        assert rel(p[k].grad, ref) < 1e-10, k
+
+
+def test_evaluator_oracle_matches_reference_evaluator():
+    """oracle.metrics_oracle.evaluator_done against the reference's own SimplifiedEvaluator.evaluate + done
+    (datasets/Shanghai_metrics.py:49-103,218-290; LPIPS stubbed out: it needs a pretrained AlexNet)."""
+    import importlib.util
+    import sys
+    import types
+    import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("reference sources not available")
+    sys.modules.setdefault("lpips", types.ModuleType("lpips"))
+    spec = importlib.util.spec_from_file_location("ref_shanghai_metrics", os.path.join(ref_loader.reference_root(), "datasets", "Shanghai_metrics.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    class Ev(mod.SimplifiedEvaluator):
+        def __init__(self, seq_len, value_scale, thresholds):
+            self.lpips_fn = None      # the constructor proper (:15-43) loads lpips.LPIPS(net='alex')
+            self.metrics, self.thresholds, self.seq_len, self.value_scale = {}, thresholds, seq_len, value_scale
+            self.TP, self.TN, self.FP, self.FN = [], [], [], []
+            mod.SimplifiedEvaluator.reset(self)
+
+        def _cal_batch_lpips(self, preds, trues):
+            return [[0.0] * preds.shape[1]] * preds.shape[0]
+
+    ev = Ev(6, 90, [20, 30, 35, 40])
+    rng = np.random.default_rng(5)
+    batches = [(rng.random((2, 6, 24, 24), dtype=np.float32) * 1.2 - 0.1, rng.random((2, 6, 24, 24), dtype=np.float32) * 1.2 - 0.1) for _ in range(2)]
+    for tb, pb in batches:
+        ev.evaluate(tb, pb)
+    ref = ev.done()
+    got = MO.evaluator_done(batches)
+    for thr in (20, 30, 35, 40):
+        for k in ("TP", "TN", "FP", "FN"):
+            assert got["threshold_metrics"][thr][k] == ref["threshold_metrics"][thr][k], (thr, k)
+        for k in ("CSI", "POD", "HSS"):
+            assert abs(got["threshold_metrics"][thr][k] - ref["threshold_metrics"][thr][k]) < 1e-12
+    assert abs(got["FAR"] - ref["FAR"]) < 1e-12 and abs(got["RMSE"] - ref["RMSE"]) < 1e-5 * ref["RMSE"]
+
+
+@pytest.mark.parametrize("cfg", [(32, 8, 4, 2, 25), (48, 6, 8, 1, 16)], ids=lambda c: "dim%d_h%d_dh%d_B%d_L%d" % c)
+def test_attention_oracle_matches_reference(cfg):
+    """oracle/attention_oracle.py against the unmodified reference StandardAttention (models/ADNssd.py:26-47), fp64."""
+    import ref_loader
+    from oracle import attention_oracle as AT
+    if not ref_loader.reference_available():
+        pytest.skip("reference sources not available")
+    dim, heads, dh, B, L = cfg
+    ref = ref_loader.load_reference()
+    m = ref.ADNssd.StandardAttention(dim, heads=heads, dim_head=dh, dropout=0.).double()
+    p = AT.init_params(dim, heads, dh, seed=3)
+    m.load_state_dict(p, strict=True)
+    x = cases.rng_normal(71, (B, L, dim)).requires_grad_(True)
+    dy = cases.rng_normal(72, (B, L, dim))
+    y = m(x, 5, 5)
+    y.backward(dy)
+    pp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    x2 = x.detach().clone().requires_grad_(True)
+    y2 = AT.attention_forward(pp, x2, heads, dh)
+    y2.backward(dy)
+    assert rel(y2.detach(), y.detach()) < 1e-12 and rel(x2.grad, x.grad) < 1e-12
+    for k, v in m.named_parameters():
+        assert rel(pp[k].grad, v.grad) < 1e-12, k
