@@ -24,14 +24,14 @@
 //   shared memory -> TMA store (bf16 / fp32) or TMA reduce-add (split-K), 32 rows x 128 bytes per instruction, clipped to
 //   the matrix by the hardware.  (Thread-per-row global stores cost 107 of 157 us on the in_proj shape.)
 #pragma once
-#include <cuda.h>      // CUtensorMap (types only: cuTensorMapEncodeTiled is resolved through cudaGetDriverEntryPoint)
-
 #include "adn_common.cuh"
 #include "sm100_utils.cuh"
+#include "tma_utils.cuh"
 
 namespace adn {
 namespace tcg {
 using namespace adn::sm100;
+using namespace adn::tma;
 
 constexpr int BM = 128, BK = 64, STAGES = 4, MAX_BN = 256;
 constexpr int EPI_BUF_B = 4096, EPI_B = 4 * 2 * EPI_BUF_B;      // per epilogue warp: two 32-row x 128-byte staging slabs
@@ -67,12 +67,6 @@ struct Args {
 __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// one TMA box: coordinates (c0 innermost, c1, c2 = batch) of a rank-3 tensor map -> shared memory, bytes counted on `bar`
-__device__ __forceinline__ void tma_load_3d(uint32_t sdst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-               ::"r"(sdst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t ssrc, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"((uint64_t)map), "r"(ssrc), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -84,10 +78,6 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
-}
-
 // Shared-memory matrix descriptors for the 128-byte swizzled tiles TMA writes (cute/atom/mma_traits_sm100.hpp,
 // make_umma_desc: canonical layouts in 16-byte units)
 //   K-major  Swizzle<3,4,3> o ((8,n),2):((8,SBO),1)        rows 128 B apart, 8-row groups SBO = 1024 B apart, LBO unused (1)
@@ -317,20 +307,6 @@ static inline int pick_bn(int N, int b_mn) {
   // wider than one tile: 256 unless its zero-padded last tile wastes more than 1/8 of the work, then 128
   const int pad256 = (N + 255) / 256 * 256 - N;
   return pad256 * 8 <= N ? 256 : 128;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
 }
 
 // Rank-3 bf16 tensor map of one operand: K-major [rows][K] -> dims (K, rows, batches), box (64, box_rows, 1);

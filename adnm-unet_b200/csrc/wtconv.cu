@@ -8,12 +8,14 @@
 //            (:118-127) are never materialised: each level kernel recomputes the Haar butterflies in shared memory.
 // Backward = the same two kernels on dy (the Haar pair is orthonormal, so adjoint(IDWT) = DWT and vice versa) with
 //            flipped taps, plus a correlation kernel per level for the weight / scale gradients.
+#include <string.h>
+
 #include "adn_common.cuh"
+#include "tma_utils.cuh"
 
 namespace adn {
+using namespace adn::sm100;
 
-constexpr int WT_TH = 16, WT_TW = 32;   // sub-band positions per CTA tile (=> 32 x 64 pixels of that level)
-constexpr int WT_MAXK = 7;
 
 struct LevelGeom { int h, w, h2, w2; };  // this level's input plane and its sub-band plane (h2 = ceil(h/2))
 
@@ -80,243 +82,492 @@ __global__ void k_haar_ll_vec(const TI* __restrict__ in, float* __restrict__ out
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused level kernel.  One CTA = one (plane, 16x32 sub-band tile); 128 threads, each a 1x4 strip of positions.
+// Fused level kernel.  One CTA = one (plane, 32 x 32 sub-band tile) = 64 x 64 pixels of that level; 64 threads, each a
+// 4 x 4 block of sub-band positions (8 x 8 pixels).
 //   sub  = DWT(pad(in))                       (in shared memory, with a k/2 halo)
 //   t    = scale[ch] * conv_k(sub; Wl[ch])    (taps flipped when FLIP: the transposed conv of the backward pass)
 //   t[LL] += coarse                           (nxt_{i+1} forward / dll_{i+1} backward; may be NULL)
 //   o    = crop(IDWT(t))
 //   if BASE: o += bscale[c] * (conv_k(in; Wb[c]) + bias[c])
+// The k x k taps make this stage FMA-bound, and the CUDA cores only reach their FMA rate when shared memory delivers less
+// than one word per four FMAs (128 FMA lanes, 32 banks per SM).  Round 1's 1 x 4 strips needed 13 words per 20 FMAs and ran
+// 3x off the FMA rate; a 2 x 4 block reads (2 + k - 1) rows of (4 + k - 1) values as aligned 16-byte vectors once per band
+// for 8 k^2 FMAs (k = 5: 48 words per 200 FMAs), with the k^2 taps of the band in registers.  (A 4 x 4 block has the better
+// ratio but halves the warps an SM can hold - 512 bytes of tile per thread - and measured slower: the tile staging, one
+// exposed HBM latency per CTA, then has too few other warps to hide behind.)
 // ---------------------------------------------------------------------------------------------
-template <typename TI, typename TO, int K, bool BASE, bool FLIP>
-__global__ void __launch_bounds__(128)
-k_wt_level(const TI* __restrict__ in, const float* __restrict__ coarse, TO* __restrict__ out,
+constexpr int WT_T = 32, WT_THREADS = 128, WT_BH = 2;      // sub-band tile edge; a thread owns WT_BH x 4 positions
+template <int K> struct WtTile {
+  static constexpr int R = K / 2, SH = WT_T + 2 * R;
+  static constexpr int VW = ((4 + K - 1) + 3) / 4 * 4;          // values a thread reads per row: whole 16-byte vectors
+  static constexpr int SP = ((WT_T - 4 + VW) + 3) / 4 * 4;      // row pitch of S (the last block's vectors stay inside the row)
+  static constexpr int POFF = (4 - R % 4) % 4;                  // column shift of the pixel tile: a block's first column is 16-byte aligned
+  static constexpr int PVW = ((8 + K - 1) + 3) / 4 * 4;
+  static constexpr int PW_WRITE = 2 * (WT_T + 2 * R) + POFF, PW_READ = 2 * (WT_T - 4) + R + POFF + PVW;
+  static constexpr int PH = 2 * SH, PP = ((PW_WRITE > PW_READ ? PW_WRITE : PW_READ) + 3) / 4 * 4;
+};
+
+// Halo tile staging.  TMA == true: the raw input tile (pixels of this level, storage dtype) arrives by ONE bulk tensor copy
+// (cp.async.bulk.tensor, zero fill outside the plane = the conv's zero padding AND the odd-size padding of the DWT) issued by
+// one thread and tracked by an mbarrier; the CTA is persistent and the copy of its NEXT tile is issued as soon as the current
+// raw tile has been transformed, so it lands while the FMAs of the current tile run.  TMA == false (row pitch or plane size
+// not a multiple of 16 bytes): the same tile is gathered with per-thread loads.
+template <typename TI, int K> struct WtRaw {
+  static constexpr int PER = 4 / (int)sizeof(TI);      // pixels per 32-bit TMA element
+  // The box must START on a 16-byte boundary of the row (measured: a bf16 tile whose first pixel is 8 bytes into a 16-byte
+  // unit faults with "illegal instruction" on the first copy; the fp32 tile, 16 bytes in, copies fine), so the tile is widened
+  // to the left by XOFF pixels, and its rows are whole 32-byte units.
+  static constexpr int APX = 16 / (int)sizeof(TI), XOFF = (APX - (2 * WtTile<K>::R) % APX) % APX;
+  static constexpr int PXQ = 32 / (int)sizeof(TI);
+  static constexpr int BH = 2 * WtTile<K>::SH, BW = (2 * (WT_T + 2 * WtTile<K>::R) + XOFF + PXQ - 1) / PXQ * PXQ;
+  static constexpr size_t BYTES = ((size_t)BH * BW * sizeof(TI) + 127) / 128 * 128;
+};
+
+template <typename TI, typename TO, int K, bool BASE, bool FLIP, bool TMA>
+__global__ void __launch_bounds__(WT_THREADS, 4)
+k_wt_level(const __grid_constant__ CUtensorMap map, const TI* __restrict__ in, const float* __restrict__ coarse, TO* __restrict__ out,
            const float* __restrict__ Wl, const float* __restrict__ scale, const float* __restrict__ Wb,
            const float* __restrict__ bias, const float* __restrict__ bscale, int C, LevelGeom g, int tiles_x,
-           int tiles_y) {
-  constexpr int R = K / 2, SH = WT_TH + 2 * R, SW = WT_TW + 2 * R, SWP = SW + 1;
-  __shared__ float S[4][SH][SWP];
-  __shared__ float Px[BASE ? 2 * SH : 1][BASE ? 2 * SW + 1 : 1];
+           int tiles_y, int total) {
+  using G = WtTile<K>;
+  using RW = WtRaw<TI, K>;
+  constexpr int R = G::R, SH = G::SH, SW = WT_T + 2 * R, SP = G::SP;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);      // TMA destinations: 128-byte aligned
+  TI* raw = reinterpret_cast<TI*>(smem_raw);                                          // [BH][BW]   (TMA only)
+  float* smem = reinterpret_cast<float*>(smem_raw + (TMA ? RW::BYTES : 0));
+  float (*S)[SH][SP] = reinterpret_cast<float (*)[SH][SP]>(smem);                    // [4][SH][SP]
+  float (*Px)[G::PP] = reinterpret_cast<float (*)[G::PP]>(smem + 4 * SH * SP);       // [PH][PP]   (BASE only)
   __shared__ float Wk[4][K * K];
   __shared__ float Wbk[K * K];
-  int bid = blockIdx.x;
-  const int tx = bid % tiles_x; bid /= tiles_x;
-  const int ty = bid % tiles_y;
-  const long long plane = bid / tiles_y;
-  const int c = (int)(plane % C);
-  const int sy0 = ty * WT_TH, sx0 = tx * WT_TW;
-  const TI* src = in + plane * (long long)g.h * g.w;
+  __shared__ uint64_t bar;
   const int tid = threadIdx.x;
-  const bool weven = (g.w & 1) == 0 && ((plane * (long long)g.h * g.w) & 1) == 0;
-  for (int i = tid; i < 4 * K * K; i += 128) {
-    int band = i / (K * K), t = i % (K * K);
-    Wk[band][FLIP ? K * K - 1 - t : t] = Wl[((long long)c * 4 + band) * K * K + t];
-  }
-  if (BASE)
-    for (int i = tid; i < K * K; i += 128) Wbk[FLIP ? K * K - 1 - i : i] = Wb[(long long)c * K * K + i];
-  for (int i = tid; i < SH * SW; i += 128) {
-    int sy = i / SW, sx = i % SW;
-    int gy = sy0 - R + sy, gx = sx0 - R + sx;
-    float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
-    if (gy >= 0 && gy < g.h2 && gx >= 0 && gx < g.w2) load_quad(src, g.h, g.w, 2 * gy, 2 * gx, weven, a, b, cc, d);
-    S[0][sy][sx] = 0.5f * (a + b + cc + d);
-    S[1][sy][sx] = 0.5f * (a + b - cc - d);
-    S[2][sy][sx] = 0.5f * (a - b + cc - d);
-    S[3][sy][sx] = 0.5f * (a - b - cc + d);
-    if (BASE) {
-      Px[2 * sy][2 * sx] = a; Px[2 * sy][2 * sx + 1] = b;
-      Px[2 * sy + 1][2 * sx] = cc; Px[2 * sy + 1][2 * sx + 1] = d;
+  const int per_plane = tiles_x * tiles_y;
+  if (TMA) {
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); tma::tma_prefetch_desc(&map); }
+    __syncthreads();
+    if (tid == 0 && (int)blockIdx.x < total) {
+      const int t0 = blockIdx.x, pl = t0 / per_plane, rem = t0 - pl * per_plane, tyy = rem / tiles_x, txx = rem - tyy * tiles_x;
+      mbar_expect_tx(&bar, (uint32_t)((size_t)RW::BH * RW::BW * sizeof(TI)));
+      tma::tma_load_3d(smem_u32(raw), &map, (2 * (txx * WT_T - R) - RW::XOFF) / RW::PER, 2 * (tyy * WT_T - R), pl, &bar);
     }
   }
-  __syncthreads();
-  const int py = tid >> 3, px = (tid & 7) * 4;  // strip origin inside the tile
-  const int gy = sy0 + py;
-  if (gy >= g.h2) return;
-  float t[4][4];
-#pragma unroll
-  for (int band = 0; band < 4; ++band) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int a = 0; a < K; ++a) {
-      float v[4 + K - 1], wv[K];
-#pragma unroll
-      for (int j = 0; j < 4 + K - 1; ++j) v[j] = S[band][py + a][px + j];
-#pragma unroll
-      for (int bb = 0; bb < K; ++bb) wv[bb] = Wk[band][a * K + bb];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int bb = 0; bb < K; ++bb) acc[j] = fmaf(wv[bb], v[j + bb], acc[j]);
+  uint32_t phase = 0;
+  const int py = (tid >> 3) * WT_BH, px = (tid & 7) * 4;  // block origin inside the tile
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int pl = tile / per_plane, rem = tile - pl * per_plane, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const long long plane = pl;
+    const int c = (int)(plane % C);
+    const int sy0 = ty * WT_T, sx0 = tx * WT_T;
+    for (int i = tid; i < 4 * K * K; i += WT_THREADS) {
+      int band = i / (K * K), t = i % (K * K);
+      Wk[band][FLIP ? K * K - 1 - t : t] = Wl[((long long)c * 4 + band) * K * K + t];
     }
-    const float sc = scale[c * 4 + band];
+    if (BASE)
+      for (int i = tid; i < K * K; i += WT_THREADS) Wbk[FLIP ? K * K - 1 - i : i] = Wb[(long long)c * K * K + i];
+    constexpr int NQ = (SH * SW + WT_THREADS - 1) / WT_THREADS;
+    if (TMA) {
+      if (!mbar_wait(&bar, phase)) __trap();      // a fault in the async pipe must be loud, not a hang
+      phase ^= 1;
+#pragma unroll 2
+      for (int u = 0; u < NQ; ++u) {
+        const int i = u * WT_THREADS + tid;
+        if (i >= SH * SW) break;
+        const int sy = i / SW, sx = i - sy * SW;
+        float a, b, cc, d;
+        load_quad(raw, RW::BH, RW::BW, 2 * sy, 2 * sx + RW::XOFF, true, a, b, cc, d);
+        S[0][sy][sx] = 0.5f * (a + b + cc + d);
+        S[1][sy][sx] = 0.5f * (a + b - cc - d);
+        S[2][sy][sx] = 0.5f * (a - b + cc - d);
+        S[3][sy][sx] = 0.5f * (a - b - cc + d);
+        if (BASE) {
+          Px[2 * sy][2 * sx + G::POFF] = a; Px[2 * sy][2 * sx + 1 + G::POFF] = b;
+          Px[2 * sy + 1][2 * sx + G::POFF] = cc; Px[2 * sy + 1][2 * sx + 1 + G::POFF] = d;
+        }
+      }
+    } else {
+      const TI* src = in + plane * (long long)g.h * g.w;
+      const bool weven = (g.w & 1) == 0 && ((plane * (long long)g.h * g.w) & 1) == 0;
+      // ALL of a thread's quads are loaded before the first is used (one exposed memory latency per tile)
+      float qa[NQ], qb[NQ], qc[NQ], qd[NQ];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) t[band][j] = sc * acc[j];
-  }
-  float o[2][8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    int gx = sx0 + px + j;
-    float ll = t[0][j];
-    if (coarse != nullptr && gx < g.w2) ll += coarse[(plane * g.h2 + gy) * g.w2 + gx];
-    float b1 = t[1][j], b2 = t[2][j], b3 = t[3][j];
-    o[0][2 * j] = 0.5f * (ll + b1 + b2 + b3);
-    o[0][2 * j + 1] = 0.5f * (ll + b1 - b2 - b3);
-    o[1][2 * j] = 0.5f * (ll - b1 + b2 - b3);
-    o[1][2 * j + 1] = 0.5f * (ll - b1 - b2 + b3);
-  }
-  if (BASE) {
-    const float bs = bscale[c], bi = bias ? bias[c] : 0.f;
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      float acc[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = bi;
-      // pixel (2*py + rr, 2*px + j) of the tile sits at Px[2*(py+R) + rr][2*(px+R) + j]
-#pragma unroll
-      for (int a = 0; a < K; ++a) {
-        float v[8 + K - 1], wv[K];
-#pragma unroll
-        for (int j = 0; j < 8 + K - 1; ++j) v[j] = Px[2 * (py + R) + rr + a - R][2 * (px + R) - R + j];
-#pragma unroll
-        for (int bb = 0; bb < K; ++bb) wv[bb] = Wbk[a * K + bb];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-          for (int bb = 0; bb < K; ++bb) acc[j] = fmaf(wv[bb], v[j + bb], acc[j]);
+      for (int u = 0; u < NQ; ++u) {
+        const int i = u * WT_THREADS + tid;
+        const int sy = i / SW, sx = i - sy * SW;
+        const int gy = sy0 - R + sy, gx = sx0 - R + sx;
+        qa[u] = qb[u] = qc[u] = qd[u] = 0.f;
+        if (i < SH * SW && gy >= 0 && gy < g.h2 && gx >= 0 && gx < g.w2) load_quad(src, g.h, g.w, 2 * gy, 2 * gx, weven, qa[u], qb[u], qc[u], qd[u]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[rr][j] += bs * acc[j];
+      for (int u = 0; u < NQ; ++u) {
+        const int i = u * WT_THREADS + tid;
+        if (i >= SH * SW) continue;
+        const int sy = i / SW, sx = i - sy * SW;
+        const float a = qa[u], b = qb[u], cc = qc[u], d = qd[u];
+        S[0][sy][sx] = 0.5f * (a + b + cc + d);
+        S[1][sy][sx] = 0.5f * (a + b - cc - d);
+        S[2][sy][sx] = 0.5f * (a - b + cc - d);
+        S[3][sy][sx] = 0.5f * (a - b - cc + d);
+        if (BASE) {
+          Px[2 * sy][2 * sx + G::POFF] = a; Px[2 * sy][2 * sx + 1 + G::POFF] = b;
+          Px[2 * sy + 1][2 * sx + G::POFF] = cc; Px[2 * sy + 1][2 * sx + 1 + G::POFF] = d;
+        }
+      }
     }
-  }
-  TO* dst = out + plane * (long long)g.h * g.w;
-  const int x0 = 2 * (sx0 + px);                      // multiple of 8
-  const bool vec = (g.w & 7) == 0 && x0 + 8 <= g.w;   // the strip's 8 outputs of a row: two 4-element vector stores
+    __syncthreads();                                        // S / Px / weights ready; the raw tile is consumed
+    if (TMA && tid == 0 && tile + (int)gridDim.x < total) {
+      const int t1 = tile + gridDim.x, pl1 = t1 / per_plane, rem1 = t1 - pl1 * per_plane, ty1 = rem1 / tiles_x, tx1 = rem1 - ty1 * tiles_x;
+      mbar_expect_tx(&bar, (uint32_t)((size_t)RW::BH * RW::BW * sizeof(TI)));
+      tma::tma_load_3d(smem_u32(raw), &map, (2 * (tx1 * WT_T - R) - RW::XOFF) / RW::PER, 2 * (ty1 * WT_T - R), pl1, &bar);
+    }
+    if (sy0 + py < g.h2 && sx0 + px < g.w2) {              // else: the whole block lies outside the plane
+      float t[4][WT_BH][4];                                  // [band][row][col]
 #pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    int y = 2 * gy + rr;
-    if (y >= g.h) continue;
-    if (vec) {
-      float lo[4] = {o[rr][0], o[rr][1], o[rr][2], o[rr][3]}, hi[4] = {o[rr][4], o[rr][5], o[rr][6], o[rr][7]};
-      st4(dst + (long long)y * g.w + x0, lo);
-      st4(dst + (long long)y * g.w + x0 + 4, hi);
-      continue;
-    }
+      for (int band = 0; band < 4; ++band) {
+        float wv[K * K];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int x = x0 + j;
-      if (x < g.w) stf(dst + (long long)y * g.w + x, o[rr][j]);
+        for (int i = 0; i < K * K; ++i) wv[i] = Wk[band][i];
+        float acc[WT_BH][4];
+#pragma unroll
+        for (int i = 0; i < WT_BH; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+        for (int r = 0; r < WT_BH + K - 1; ++r) {
+          float v[G::VW];
+#pragma unroll
+          for (int q = 0; q < G::VW; q += 4) {
+            const float4 f = *reinterpret_cast<const float4*>(&S[band][py + r][px + q]);
+            v[q] = f.x; v[q + 1] = f.y; v[q + 2] = f.z; v[q + 3] = f.w;
+          }
+#pragma unroll
+          for (int i = 0; i < WT_BH; ++i) {
+            const int a = r - i;                               // tap row that maps input row r to output row i
+            if (a < 0 || a >= K) continue;
+#pragma unroll
+            for (int bb = 0; bb < K; ++bb)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[a * K + bb], v[j + bb], acc[i][j]);
+          }
+        }
+        const float sc = scale[c * 4 + band];
+#pragma unroll
+        for (int i = 0; i < WT_BH; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) t[band][i][j] = sc * acc[i][j];
+      }
+      TO* dst = out + plane * (long long)g.h * g.w;
+      const float bs = BASE ? bscale[c] : 0.f, bi = (BASE && bias) ? bias[c] : 0.f;
+      const int x0 = 2 * (sx0 + px);                      // multiple of 8
+      const bool vec = (g.w & 7) == 0 && x0 + 8 <= g.w;   // the block's 8 outputs of a row: two 4-element vector stores
+      // two pixel rows (one sub-band row) at a time: IDWT, base conv, store
+#pragma unroll
+      for (int i = 0; i < WT_BH; ++i) {
+        const int gy = sy0 + py + i;
+        if (gy >= g.h2) break;
+        float o[2][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int gx = sx0 + px + j;
+          float ll = t[0][i][j];
+          if (coarse != nullptr && gx < g.w2) ll += coarse[(plane * g.h2 + gy) * g.w2 + gx];
+          const float b1 = t[1][i][j], b2 = t[2][i][j], b3 = t[3][i][j];
+          o[0][2 * j] = 0.5f * (ll + b1 + b2 + b3);
+          o[0][2 * j + 1] = 0.5f * (ll + b1 - b2 - b3);
+          o[1][2 * j] = 0.5f * (ll - b1 + b2 - b3);
+          o[1][2 * j + 1] = 0.5f * (ll - b1 - b2 + b3);
+        }
+        if (BASE) {
+          float wb[K * K];
+#pragma unroll
+          for (int q = 0; q < K * K; ++q) wb[q] = Wbk[q];
+          float acc[2][8];
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[rr][j] = bi;
+          // pixel (2 * (py + i) + rr, 2 * px + j) of the tile sits at Px[2 * (py + i + R) + rr][2 * (px + R) + j + POFF]; tap (a, bb)
+          // reads row + a - R, column + bb - R: rows 2 * (py + i) + R + rr + a, columns 2 * px + R + POFF + j + bb
+#pragma unroll
+          for (int r = 0; r < 2 + K - 1; ++r) {
+            float v[G::PVW];
+#pragma unroll
+            for (int q = 0; q < G::PVW; q += 4) {
+              const float4 f = *reinterpret_cast<const float4*>(&Px[2 * (py + i) + R + r][2 * px + R + G::POFF + q]);
+              v[q] = f.x; v[q + 1] = f.y; v[q + 2] = f.z; v[q + 3] = f.w;
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const int a = r - rr;
+              if (a < 0 || a >= K) continue;
+#pragma unroll
+              for (int bb = 0; bb < K; ++bb)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[rr][j] = fmaf(wb[a * K + bb], v[j + bb], acc[rr][j]);
+            }
+          }
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[rr][j] = fmaf(bs, acc[rr][j], o[rr][j]);
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int y = 2 * gy + rr;
+          if (y >= g.h) continue;
+          if (vec) {
+            float lo[4] = {o[rr][0], o[rr][1], o[rr][2], o[rr][3]}, hi[4] = {o[rr][4], o[rr][5], o[rr][6], o[rr][7]};
+            st4(dst + (long long)y * g.w + x0, lo);
+            st4(dst + (long long)y * g.w + x0 + 4, hi);
+            continue;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int x = x0 + j;
+            if (x < g.w) stf(dst + (long long)y * g.w + x, o[rr][j]);
+          }
+        }
+      }
     }
+    __syncthreads();                                        // S / Px / weights may be overwritten by the next tile
   }
+}
+template <typename TI, int K, bool BASE, bool TMA> static constexpr size_t wt_level_smem() {
+  using G = WtTile<K>;
+  return 128 + (TMA ? WtRaw<TI, K>::BYTES : 0) + sizeof(float) * (4 * (size_t)G::SH * G::SP + (BASE ? (size_t)G::PH * G::PP : 0));
 }
 
 // ---------------------------------------------------------------------------------------------
 // Correlations for the weight gradients of one level:
 //   NB == 4:  Rl[c*4+band][a][b] += sum dsub[band][y][x] * sub[band][y+a-R][x+b-R],  sub = DWT(pad(xin)), dsub = DWT(pad(gin))
 //   NB == 1:  Rb[c][a][b] += sum gin[y][x] * xin[y+a-R][x+b-R],  sumg[c] += sum gin            (base conv, pixel units)
-// thread = (band, tap row a, group of 2 tile rows): slides a K-wide window along x.
+// One CTA = one channel and a strided share of its (sample, 32 x 32 tile) work items; 128 threads, each a 2 x 4 block of
+// positions with ALL k^2 correlation sums of a band in registers (8 k^2 FMAs per 8 + (2 + k - 1)(4 + k - 1) shared-memory words),
+// carried across the work items and flushed once per CTA: shuffles, then one global atomic per (band, tap) and CTA.
+// (Round 1: one thread per tap row sliding along x - 2 shared-memory words per 5 FMAs - and a shared-memory atomic flush
+// per tile: 365 us of the 0.98 ms forward + backward at C = 32, 128^2, B = 64.)
 // ---------------------------------------------------------------------------------------------
-template <typename TX, typename TG, int K, int NB>
-__global__ void k_wt_wgrad(const TX* __restrict__ xin, const TG* __restrict__ gin, float* __restrict__ Rout,
-                           float* __restrict__ sumg, int C, LevelGeom g, int tiles_x, int tiles_y) {
-  // tile of the correlation domain: 16 x 32 sub-band positions (NB == 4) or 32 x 64 pixels (base conv: less halo, 4x fewer CTAs)
-  constexpr int TH = NB == 4 ? WT_TH : 2 * WT_TH, TW = NB == 4 ? WT_TW : 2 * WT_TW;
-  constexpr int R = K / 2, SH = TH + 2 * R, SW = TW + 2 * R, SWP = SW + 1;
-  __shared__ float S[NB][SH][SWP];
-  __shared__ float Dt[NB][TH][TW + 1];
-  __shared__ float red[NB * K * K];
-  __shared__ float redsum;
-  int bid = blockIdx.x;
-  const int tx = bid % tiles_x; bid /= tiles_x;
-  const int ty = bid % tiles_y;
-  const long long plane = bid / tiles_y;
-  const int c = (int)(plane % C);
-  const int sy0 = ty * TH, sx0 = tx * TW;
-  // extent of the tiled domain: sub-band plane (NB==4) or the pixel plane itself (NB==1)
-  const int dh = NB == 4 ? g.h2 : g.h, dw = NB == 4 ? g.w2 : g.w;
-  const TX* xs = xin + plane * (long long)g.h * g.w;
-  const TG* gs = gin + plane * (long long)g.h * g.w;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const bool weven = (g.w & 1) == 0 && ((plane * (long long)g.h * g.w) & 1) == 0;
-  for (int i = tid; i < NB * K * K; i += nt) red[i] = 0.f;
-  if (tid == 0) redsum = 0.f;
-  for (int i = tid; i < SH * SW; i += nt) {
-    int sy = i / SW, sx = i % SW;
-    int gy = sy0 - R + sy, gx = sx0 - R + sx;
-    bool in = gy >= 0 && gy < dh && gx >= 0 && gx < dw;
-    if (NB == 4) {
-      float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
-      if (in) load_quad(xs, g.h, g.w, 2 * gy, 2 * gx, weven, a, b, cc, d);
-      S[0][sy][sx] = 0.5f * (a + b + cc + d);
-      S[NB > 1 ? 1 : 0][sy][sx] = 0.5f * (a + b - cc - d);
-      S[NB > 2 ? 2 : 0][sy][sx] = 0.5f * (a - b + cc - d);
-      S[NB > 3 ? 3 : 0][sy][sx] = 0.5f * (a - b - cc + d);
-    } else {
-      S[0][sy][sx] = in ? ldf(xs + (long long)gy * g.w + gx) : 0.f;
-    }
-  }
+// raw tiles of the correlation kernel: `x` with the k/2 halo (pixels of the level for NB == 4, the correlation domain itself
+// for NB == 1), `g` without; same 16-byte origin / 32-byte row rules as WtRaw
+template <typename T, int K, int NB> struct WtRawX {
+  static constexpr int PER = 4 / (int)sizeof(T), APX = 16 / (int)sizeof(T), PXQ = 32 / (int)sizeof(T);
+  static constexpr int R = WtTile<K>::R, SW = WT_T + 2 * R;
+  static constexpr int LEFT = NB == 4 ? 2 * R : R;                               // halo pixels left of the tile origin
+  static constexpr int XOFF = (APX - LEFT % APX) % APX;
+  static constexpr int BH = (NB == 4 ? 2 : 1) * WtTile<K>::SH, BW = ((NB == 4 ? 2 : 1) * SW + XOFF + PXQ - 1) / PXQ * PXQ;
+  static constexpr size_t BYTES = ((size_t)BH * BW * sizeof(T) + 127) / 128 * 128;
+};
+template <typename T, int NB> struct WtRawG {
+  static constexpr int PER = 4 / (int)sizeof(T);
+  static constexpr int BH = (NB == 4 ? 2 : 1) * WT_T, BW = BH;
+  static constexpr size_t BYTES = ((size_t)BH * BW * sizeof(T) + 127) / 128 * 128;
+};
+
+template <typename TX, typename TG, int K, int NB, bool TMA>
+__global__ void __launch_bounds__(WT_THREADS, 4)
+k_wt_wgrad(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapg, const TX* __restrict__ xin,
+           const TG* __restrict__ gin, float* __restrict__ Rout, float* __restrict__ sumg, int C, int Bn, LevelGeom g, int tiles_x,
+           int tiles_y) {
+  using G = WtTile<K>;
+  using RX = WtRawX<TX, K, NB>;
+  using RG = WtRawG<TG, NB>;
+  constexpr int R = G::R, SH = G::SH, SW = WT_T + 2 * R, SP = G::SP, DP = WT_T + 4;
+  constexpr int MUL = NB == 4 ? 2 : 1;                   // raw pixels per correlation position along each axis
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+  TX* rawx = reinterpret_cast<TX*>(smem_raw);
+  TG* rawg = reinterpret_cast<TG*>(smem_raw + (TMA ? RX::BYTES : 0));
+  float* smem = reinterpret_cast<float*>(smem_raw + (TMA ? RX::BYTES + RG::BYTES : 0));
+  float (*S)[SH][SP] = reinterpret_cast<float (*)[SH][SP]>(smem);                       // [NB][SH][SP]
+  float (*Dt)[WT_T][DP] = reinterpret_cast<float (*)[WT_T][DP]>(smem + NB * SH * SP);   // [NB][WT_T][DP]
+  __shared__ float red[WT_THREADS / 32][NB * K * K + 1];
+  __shared__ uint64_t bar;
+  const int c = blockIdx.x;
+  const int dh = NB == 4 ? g.h2 : g.h, dw = NB == 4 ? g.w2 : g.w;      // extent of the correlation domain
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int py = (tid >> 3) * WT_BH, px = (tid & 7) * 4;
+  float acc[NB][K * K];
+#pragma unroll
+  for (int band = 0; band < NB; ++band)
+#pragma unroll
+    for (int q = 0; q < K * K; ++q) acc[band][q] = 0.f;
   float lsum = 0.f;
-  for (int i = tid; i < TH * TW; i += nt) {
-    int sy = i / TW, sx = i % TW;
-    int gy = sy0 + sy, gx = sx0 + sx;
-    bool in = gy < dh && gx < dw;
-    if (NB == 4) {
-      float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
-      if (in) load_quad(gs, g.h, g.w, 2 * gy, 2 * gx, weven, a, b, cc, d);
-      Dt[0][sy][sx] = 0.5f * (a + b + cc + d);
-      Dt[NB > 1 ? 1 : 0][sy][sx] = 0.5f * (a + b - cc - d);
-      Dt[NB > 2 ? 2 : 0][sy][sx] = 0.5f * (a - b + cc - d);
-      Dt[NB > 3 ? 3 : 0][sy][sx] = 0.5f * (a - b - cc + d);
-    } else {
-      float v = in ? ldf(gs + (long long)gy * g.w + gx) : 0.f;
-      Dt[0][sy][sx] = v;
-      lsum += v;
-    }
+  const int items = Bn * tiles_y * tiles_x;
+  constexpr uint32_t TX_BYTES = (uint32_t)((size_t)RX::BH * RX::BW * sizeof(TX) + (size_t)RG::BH * RG::BW * sizeof(TG));
+  auto issue = [&](int it) {
+    const int txi = it % tiles_x, tyi = (it / tiles_x) % tiles_y, b = it / (tiles_x * tiles_y);
+    const int plane = b * C + c;
+    mbar_expect_tx(&bar, TX_BYTES);
+    tma::tma_load_3d(smem_u32(rawx), &mapx, (MUL * (txi * WT_T - R) - RX::XOFF) / RX::PER, MUL * (tyi * WT_T - R), plane, &bar);
+    tma::tma_load_3d(smem_u32(rawg), &mapg, (MUL * txi * WT_T) / RG::PER, MUL * tyi * WT_T, plane, &bar);
+  };
+  if (TMA) {
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); tma::tma_prefetch_desc(&mapx); tma::tma_prefetch_desc(&mapg); }
+    __syncthreads();
+    if (tid == 0 && (int)blockIdx.y < items) issue(blockIdx.y);
   }
-  __syncthreads();
-  // roles: tid -> (row group rg, tap row a, band, x segment): slides a K-wide window along x for its tap row.  The window
-  // walk is fully unrolled (the shift is register renaming: 2 LDS + K FMA per position).  NB == 4: 8 groups of 2 rows over
-  // the whole tile width; NB == 1 (base conv): 32 single rows, so that all K * 32 threads work.
-  constexpr int XSEG = 1, XW = TW / XSEG, RPT = NB == 4 ? 2 : 1, NRG = TH / RPT;
-  const int role = tid;
-  if (role < NB * K * NRG * XSEG) {
-    const int rg = role % NRG, a = (role / NRG) % K, band = (role / (NRG * K)) % NB, x0 = (role / (NRG * K * NB)) * XW;
-    float acc[K];
+  uint32_t phase = 0;
+  constexpr int NQ = (SH * SW + WT_THREADS - 1) / WT_THREADS, NQD = WT_T * WT_T / WT_THREADS;
+  for (int it = blockIdx.y; it < items; it += gridDim.y) {
+    const int txi = it % tiles_x, tyi = (it / tiles_x) % tiles_y, b = it / (tiles_x * tiles_y);
+    const long long plane = (long long)b * C + c;
+    const int sy0 = tyi * WT_T, sx0 = txi * WT_T;
+    if (TMA) {
+      if (!mbar_wait(&bar, phase)) __trap();           // a fault in the async pipe must be loud, not a hang
+      phase ^= 1;
+#pragma unroll 2
+      for (int u = 0; u < NQ; ++u) {
+        const int i = u * WT_THREADS + tid;
+        if (i >= SH * SW) break;
+        const int sy = i / SW, sx = i - sy * SW;
+        if (NB == 4) {
+          float a, bq, cc, d;
+          load_quad(rawx, RX::BH, RX::BW, 2 * sy, 2 * sx + RX::XOFF, true, a, bq, cc, d);
+          S[0][sy][sx] = 0.5f * (a + bq + cc + d);
+          S[NB > 1 ? 1 : 0][sy][sx] = 0.5f * (a + bq - cc - d);
+          S[NB > 2 ? 2 : 0][sy][sx] = 0.5f * (a - bq + cc - d);
+          S[NB > 3 ? 3 : 0][sy][sx] = 0.5f * (a - bq - cc + d);
+        } else {
+          S[0][sy][sx] = ldf(rawx + sy * RX::BW + sx + RX::XOFF);
+        }
+      }
+#pragma unroll 2
+      for (int u = 0; u < NQD; ++u) {
+        const int i = u * WT_THREADS + tid;
+        const int sy = i / WT_T, sx = i - sy * WT_T;
+        if (NB == 4) {
+          float a, bq, cc, d;
+          load_quad(rawg, RG::BH, RG::BW, 2 * sy, 2 * sx, true, a, bq, cc, d);
+          Dt[0][sy][sx] = 0.5f * (a + bq + cc + d);
+          Dt[NB > 1 ? 1 : 0][sy][sx] = 0.5f * (a + bq - cc - d);
+          Dt[NB > 2 ? 2 : 0][sy][sx] = 0.5f * (a - bq + cc - d);
+          Dt[NB > 3 ? 3 : 0][sy][sx] = 0.5f * (a - bq - cc + d);
+        } else {
+          const float v = ldf(rawg + sy * RG::BW + sx);
+          Dt[0][sy][sx] = v;
+          lsum += v;
+        }
+      }
+    } else {
+      const TX* xs = xin + plane * (long long)g.h * g.w;
+      const TG* gs = gin + plane * (long long)g.h * g.w;
+      const bool weven = (g.w & 1) == 0 && ((plane * (long long)g.h * g.w) & 1) == 0;
+      {
+        float qa[NQ], qb[NQ], qc[NQ], qd[NQ];
 #pragma unroll
-    for (int bb = 0; bb < K; ++bb) acc[bb] = 0.f;
+        for (int u = 0; u < NQ; ++u) {
+          const int i = u * WT_THREADS + tid;
+          const int sy = i / SW, sx = i - sy * SW;
+          const int gy = sy0 - R + sy, gx = sx0 - R + sx;
+          const bool in = i < SH * SW && gy >= 0 && gy < dh && gx >= 0 && gx < dw;
+          qa[u] = qb[u] = qc[u] = qd[u] = 0.f;
+          if (in) {
+            if (NB == 4) load_quad(xs, g.h, g.w, 2 * gy, 2 * gx, weven, qa[u], qb[u], qc[u], qd[u]);
+            else qa[u] = ldf(xs + (long long)gy * g.w + gx);
+          }
+        }
 #pragma unroll
-    for (int yy = 0; yy < RPT; ++yy) {
-      const int y = rg * RPT + yy;
-      const float* srow = &S[band][y + a][x0];
-      const float* drow = &Dt[band][y][x0];
-      float win[K];
+        for (int u = 0; u < NQ; ++u) {
+          const int i = u * WT_THREADS + tid;
+          if (i >= SH * SW) continue;
+          const int sy = i / SW, sx = i - sy * SW;
+          if (NB == 4) {
+            const float a = qa[u], bq = qb[u], cc = qc[u], d = qd[u];
+            S[0][sy][sx] = 0.5f * (a + bq + cc + d);
+            S[NB > 1 ? 1 : 0][sy][sx] = 0.5f * (a + bq - cc - d);
+            S[NB > 2 ? 2 : 0][sy][sx] = 0.5f * (a - bq + cc - d);
+            S[NB > 3 ? 3 : 0][sy][sx] = 0.5f * (a - bq - cc + d);
+          } else {
+            S[0][sy][sx] = qa[u];
+          }
+        }
+      }
+      {
+        float qa[NQD], qb[NQD], qc[NQD], qd[NQD];
 #pragma unroll
-      for (int bb = 0; bb < K - 1; ++bb) win[bb + 1] = srow[bb];
+        for (int u = 0; u < NQD; ++u) {
+          const int i = u * WT_THREADS + tid;
+          const int sy = i / WT_T, sx = i - sy * WT_T;
+          const int gy = sy0 + sy, gx = sx0 + sx;
+          qa[u] = qb[u] = qc[u] = qd[u] = 0.f;
+          if (gy < dh && gx < dw) {
+            if (NB == 4) load_quad(gs, g.h, g.w, 2 * gy, 2 * gx, weven, qa[u], qb[u], qc[u], qd[u]);
+            else qa[u] = ldf(gs + (long long)gy * g.w + gx);
+          }
+        }
 #pragma unroll
-      for (int x = 0; x < XW; ++x) {
-#pragma unroll
-        for (int bb = 0; bb < K - 1; ++bb) win[bb] = win[bb + 1];
-        win[K - 1] = srow[x + K - 1];
-        const float dv = drow[x];
-#pragma unroll
-        for (int bb = 0; bb < K; ++bb) acc[bb] = fmaf(dv, win[bb], acc[bb]);
+        for (int u = 0; u < NQD; ++u) {
+          const int i = u * WT_THREADS + tid;
+          const int sy = i / WT_T, sx = i - sy * WT_T;
+          if (NB == 4) {
+            const float a = qa[u], bq = qb[u], cc = qc[u], d = qd[u];
+            Dt[0][sy][sx] = 0.5f * (a + bq + cc + d);
+            Dt[NB > 1 ? 1 : 0][sy][sx] = 0.5f * (a + bq - cc - d);
+            Dt[NB > 2 ? 2 : 0][sy][sx] = 0.5f * (a - bq + cc - d);
+            Dt[NB > 3 ? 3 : 0][sy][sx] = 0.5f * (a - bq - cc + d);
+          } else {
+            Dt[0][sy][sx] = qa[u];
+            lsum += qa[u];
+          }
+        }
       }
     }
-    // the NRG row groups of one (x segment, band, tap row) are consecutive lanes: add them up with shuffles (whole warps are
-    // inside this branch) so that one lane per tap issues the shared-memory atomic (a CAS loop for fp32: it must not contend)
+    __syncthreads();                                    // S / Dt ready; the raw tiles are consumed
+    if (TMA && tid == 0 && it + (int)gridDim.y < items) issue(it + gridDim.y);
 #pragma unroll
-    for (int bb = 0; bb < K; ++bb) {
-      float v = acc[bb];
+    for (int band = 0; band < NB; ++band) {
+      float dv[WT_BH][4];
 #pragma unroll
-      for (int m = 1; m < NRG; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-      if (rg == 0) atomicAdd(&red[(band * K + a) * K + bb], v);
+      for (int i = 0; i < WT_BH; ++i) {
+        const float4 f = *reinterpret_cast<const float4*>(&Dt[band][py + i][px]);
+        dv[i][0] = f.x; dv[i][1] = f.y; dv[i][2] = f.z; dv[i][3] = f.w;
+      }
+#pragma unroll
+      for (int r = 0; r < WT_BH + K - 1; ++r) {
+        float v[G::VW];
+#pragma unroll
+        for (int q = 0; q < G::VW; q += 4) {
+          const float4 f = *reinterpret_cast<const float4*>(&S[band][py + r][px + q]);
+          v[q] = f.x; v[q + 1] = f.y; v[q + 2] = f.z; v[q + 3] = f.w;
+        }
+#pragma unroll
+        for (int i = 0; i < WT_BH; ++i) {
+          const int a = r - i;
+          if (a < 0 || a >= K) continue;
+#pragma unroll
+          for (int bb = 0; bb < K; ++bb)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[band][a * K + bb] = fmaf(dv[i][j], v[j + bb], acc[band][a * K + bb]);
+        }
+      }
     }
+    __syncthreads();                                    // S / Dt may be overwritten by the next item
   }
+  // flush: warp shuffles, the warps through shared memory, one atomic per (band, tap)
+#pragma unroll
+  for (int band = 0; band < NB; ++band)
+#pragma unroll
+    for (int q = 0; q < K * K; ++q) {
+      const float v = warp_sum(acc[band][q]);
+      if (lane == 0) red[warp][band * K * K + q] = v;
+    }
   if (NB == 1) {
     lsum = warp_sum(lsum);
-    if ((tid & 31) == 0 && lsum != 0.f) atomicAdd(&redsum, lsum);
+    if (lane == 0) red[warp][NB * K * K] = lsum;
   }
   __syncthreads();
-  for (int i = tid; i < NB * K * K; i += nt) atomicAdd(Rout + (long long)c * NB * K * K + i, red[i]);
-  if (NB == 1 && tid == 0 && sumg) atomicAdd(sumg + c, redsum);
+  for (int i = tid; i < NB * K * K + 1; i += WT_THREADS) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < WT_THREADS / 32; ++q) v += red[q][i];
+    if (i < NB * K * K) { if (v != 0.f) atomicAdd(Rout + (long long)c * NB * K * K + i, v); }
+    else if (NB == 1 && sumg) atomicAdd(sumg + c, v);
+  }
+}
+template <typename TX, typename TG, int K, int NB, bool TMA> static constexpr size_t wt_wgrad_smem() {
+  using G = WtTile<K>;
+  return 128 + (TMA ? WtRawX<TX, K, NB>::BYTES + WtRawG<TG, NB>::BYTES : 0) +
+         sizeof(float) * ((size_t)NB * G::SH * G::SP + (size_t)NB * WT_T * (WT_T + 4));
 }
 
 // dW_i = scale_i * R_i ; dscale_i[ch] = sum_ab W_i R_i ; dW_b = bs * R_b ; dbs = sum W_b R_b + bias * sumdy ; dbias = bs * sumdy
@@ -417,18 +668,56 @@ static WtAcc carve_acc(float* base, const WtShape& s) {
   return a;
 }
 
+// Rank-3 tensor map [planes][h][w] of a contiguous NCHW tensor viewed as planes, box (box_w, box_h, 1), no swizzle, zero fill
+// outside the tensor.  Usable when row pitch and plane size are whole 16-byte units (TMA granularity).
+template <typename T> static inline bool wt_tma_ok(const T* base, int h, int w) {
+  return ((size_t)w * sizeof(T)) % 16 == 0 && ((size_t)w * h * sizeof(T)) % 16 == 0 && ((uintptr_t)base % 16) == 0;
+}
+template <typename T>
+static int wt_make_map(CUtensorMap* map, const T* base, long long planes, int h, int w, int box_w, int box_h) {
+  tma::EncodeTiledFn enc = tma::encode_tiled_fn();
+  ADN_REQUIRE(enc != nullptr, ADN_ERR_CUDA, "wtconv: cuTensorMapEncodeTiled is not available from this driver");
+  // bf16 planes are described as 32-bit words (two pixels per element; w, the box width and the box origin are even)
+  const int per = 4 / (int)sizeof(T);
+  cuuint64_t dims[3] = {(cuuint64_t)(w / per), (cuuint64_t)h, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)w * sizeof(T), (cuuint64_t)w * h * sizeof(T)};
+  cuuint32_t box[3] = {(cuuint32_t)(box_w / per), (cuuint32_t)box_h, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ADN_REQUIRE(r == CUDA_SUCCESS, ADN_ERR_CUDA, "wtconv: cuTensorMapEncodeTiled failed (%d) for a %lld x %d x %d tensor, box %d x %d", (int)r,
+              planes, h, w, box_w, box_h);
+  return ADN_OK;
+}
+static inline int wt_persistent_grid(long long total, size_t smem) {
+  long long per_sm = (long long)(227 * 1024) / (long long)(smem + 1024);
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  const long long cap = per_sm * sm_count();
+  return (int)(total < cap ? total : cap);
+}
+
 template <typename TI, typename TO, bool BASE, bool FLIP>
-static void launch_level(cudaStream_t st, int k, const TI* in, const float* coarse, TO* out, const float* Wl,
-                         const float* scale, const float* Wb, const float* bias, const float* bscale, int C,
-                         const LevelGeom& g, long long planes) {
-  int tx = cdiv(g.w2, WT_TW), ty = cdiv(g.h2, WT_TH);
+static int launch_level(cudaStream_t st, int k, const TI* in, const float* coarse, TO* out, const float* Wl,
+                        const float* scale, const float* Wb, const float* bias, const float* bscale, int C,
+                        const LevelGeom& g, long long planes) {
+  int tx = cdiv(g.w2, WT_T), ty = cdiv(g.h2, WT_T);
   long long blocks = planes * tx * ty;
-#define ADN_WT_LAUNCH(KK)                                                                                        \
+  ADN_REQUIRE(blocks < (1LL << 31) && planes < (1LL << 31), ADN_ERR_SHAPE, "wtconv: too many tiles");
+  const bool use_tma = wt_tma_ok(in, g.h, g.w) && !(env().variant & 2);
+#define ADN_WT_LAUNCH_T(KK, TMAF)                                                                                \
   {                                                                                                              \
+    constexpr size_t smem = wt_level_smem<TI, KK, BASE, TMAF>();                                                 \
+    static bool attr = false;                                                                                    \
+    if (!attr) { ADN_CHECK_CUDA(cudaFuncSetAttribute(k_wt_level<TI, TO, KK, BASE, FLIP, TMAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
+    CUtensorMap map;                                                                                             \
+    memset(&map, 0, sizeof(map));                                                                                \
+    if (TMAF) { int rc = wt_make_map<TI>(&map, in, planes, g.h, g.w, WtRaw<TI, KK>::BW, WtRaw<TI, KK>::BH); if (rc) return rc; } \
     ADN_KERNEL("k_wt_level", st);                                                                                \
-    k_wt_level<TI, TO, KK, BASE, FLIP><<<(unsigned)blocks, 128, 0, st>>>(in, coarse, out, Wl, scale, Wb, bias, bscale, C, \
-                                                                         g, tx, ty);                             \
+    k_wt_level<TI, TO, KK, BASE, FLIP, TMAF><<<wt_persistent_grid(blocks, smem), WT_THREADS, smem, st>>>(        \
+        map, in, coarse, out, Wl, scale, Wb, bias, bscale, C, g, tx, ty, (int)blocks);                           \
   }
+#define ADN_WT_LAUNCH(KK) if (use_tma) ADN_WT_LAUNCH_T(KK, true) else ADN_WT_LAUNCH_T(KK, false)
   switch (k) {
     case 1: ADN_WT_LAUNCH(1); break;
     case 3: ADN_WT_LAUNCH(3); break;
@@ -436,21 +725,41 @@ static void launch_level(cudaStream_t st, int k, const TI* in, const float* coar
     default: ADN_WT_LAUNCH(7); break;
   }
 #undef ADN_WT_LAUNCH
+#undef ADN_WT_LAUNCH_T
+  return ADN_OK;
 }
 
 template <typename TX, typename TG, int NB>
-static void launch_wgrad(cudaStream_t st, int k, const TX* xin, const TG* gin, float* Rout, float* sumg, int C,
-                         const LevelGeom& g, long long planes) {
+static int launch_wgrad(cudaStream_t st, int k, const TX* xin, const TG* gin, float* Rout, float* sumg, int C, int Bn,
+                        const LevelGeom& g) {
   int dh = NB == 4 ? g.h2 : g.h, dw = NB == 4 ? g.w2 : g.w;
-  int tx = cdiv(dw, NB == 4 ? WT_TW : 2 * WT_TW), ty = cdiv(dh, NB == 4 ? WT_TH : 2 * WT_TH);   // tile of k_wt_wgrad<.., NB>
-  long long blocks = planes * tx * ty;
-  int threads = (((NB == 4 ? 4 * k * 8 : k * 32) + 31) / 32) * 32;   // one thread per role of k_wt_wgrad
-  if (threads < 64) threads = 64;
-#define ADN_WT_LAUNCH(KK) \
-  {                                                                                                             \
-    ADN_KERNEL("k_wt_wgrad", st);                                                                               \
-    k_wt_wgrad<TX, TG, KK, NB><<<(unsigned)blocks, threads, 0, st>>>(xin, gin, Rout, sumg, C, g, tx, ty);        \
+  int tx = cdiv(dw, WT_T), ty = cdiv(dh, WT_T);
+  const long long items = (long long)Bn * tx * ty, planes = (long long)Bn * C;
+  ADN_REQUIRE(items < (1LL << 31) && planes < (1LL << 31), ADN_ERR_SHAPE, "wtconv: too many tiles");
+  const bool use_tma = wt_tma_ok(xin, g.h, g.w) && wt_tma_ok(gin, g.h, g.w) && !(env().variant & 2);
+#define ADN_WT_LAUNCH_T(KK, TMAF)                                                                                \
+  {                                                                                                              \
+    constexpr size_t smem = wt_wgrad_smem<TX, TG, KK, NB, TMAF>();                                               \
+    static bool attr = false;                                                                                    \
+    if (!attr) { ADN_CHECK_CUDA(cudaFuncSetAttribute(k_wt_wgrad<TX, TG, KK, NB, TMAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
+    long long per_sm = (long long)(227 * 1024) / (long long)(smem + 1024);                                       \
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);                                                         \
+    int split = cdiv(per_sm * sm_count(), C);      /* one resident wave of CTAs, each striding over its channel's work items */ \
+    split = split < 1 ? 1 : (split > items ? (int)items : split);                                                \
+    if (split > 65535) split = 65535;                                                                            \
+    dim3 grid(C, split);                                                                                         \
+    CUtensorMap mx, mg;                                                                                          \
+    memset(&mx, 0, sizeof(mx)); memset(&mg, 0, sizeof(mg));                                                      \
+    if (TMAF) {                                                                                                  \
+      int rc = wt_make_map<TX>(&mx, xin, planes, g.h, g.w, WtRawX<TX, KK, NB>::BW, WtRawX<TX, KK, NB>::BH);      \
+      if (rc) return rc;                                                                                         \
+      rc = wt_make_map<TG>(&mg, gin, planes, g.h, g.w, WtRawG<TG, NB>::BW, WtRawG<TG, NB>::BH);                  \
+      if (rc) return rc;                                                                                         \
+    }                                                                                                            \
+    ADN_KERNEL("k_wt_wgrad", st);                                                                                \
+    k_wt_wgrad<TX, TG, KK, NB, TMAF><<<grid, WT_THREADS, smem, st>>>(mx, mg, xin, gin, Rout, sumg, C, Bn, g, tx, ty); \
   }
+#define ADN_WT_LAUNCH(KK) if (use_tma) ADN_WT_LAUNCH_T(KK, true) else ADN_WT_LAUNCH_T(KK, false)
   switch (k) {
     case 1: ADN_WT_LAUNCH(1); break;
     case 3: ADN_WT_LAUNCH(3); break;
@@ -458,6 +767,8 @@ static void launch_wgrad(cudaStream_t st, int k, const TX* xin, const TG* gin, f
     default: ADN_WT_LAUNCH(7); break;
   }
 #undef ADN_WT_LAUNCH
+#undef ADN_WT_LAUNCH_T
+  return ADN_OK;
 }
 
 // Builds ll_1..ll_{L-1} of `src` into `pyr` and then runs the level kernels coarsest-first.
@@ -482,12 +793,14 @@ static int run_pass(const WtShape& s, const WtPlan& p, const WtWeights& w, const
   for (int i = p.L - 1; i >= 0; --i) {
     const float* coarse = (i == p.L - 1) ? nullptr : chain + p.pyr_off[i + 1];
     if (i == 0) {
-      launch_level<T, T, true, FLIP>(st, s.k, src, coarse, dst, w.wavelet_conv_w[0], w.wavelet_scale_w[0], w.base_conv_w,
-                                     FLIP ? nullptr : w.base_conv_b, w.base_scale_w, s.C, p.g[0], p.planes);
+      int rc = launch_level<T, T, true, FLIP>(st, s.k, src, coarse, dst, w.wavelet_conv_w[0], w.wavelet_scale_w[0], w.base_conv_w,
+                                              FLIP ? nullptr : w.base_conv_b, w.base_scale_w, s.C, p.g[0], p.planes);
+      if (rc) return rc;
     } else {
-      launch_level<float, float, false, FLIP>(st, s.k, pyr + p.pyr_off[i], coarse, chain + p.pyr_off[i],
-                                              w.wavelet_conv_w[i], w.wavelet_scale_w[i], nullptr, nullptr, nullptr, s.C,
-                                              p.g[i], p.planes);
+      int rc = launch_level<float, float, false, FLIP>(st, s.k, pyr + p.pyr_off[i], coarse, chain + p.pyr_off[i],
+                                                       w.wavelet_conv_w[i], w.wavelet_scale_w[i], nullptr, nullptr, nullptr, s.C,
+                                                       p.g[i], p.planes);
+      if (rc) return rc;
     }
   }
   ADN_CHECK_LAUNCH();
@@ -529,11 +842,14 @@ static int wt_backward(const WtShape& s, const WtWeights& w0, const T* x, const 
   int rc = run_pass<T, true>(s, p, w, dy, dx, gpyr, chain, st);
   if (rc) return rc;
   // weight-gradient correlations
-  launch_wgrad<T, T, 1>(st, s.k, x, dy, acc.Rb, acc.sumg, s.C, p.g[0], p.planes);
-  launch_wgrad<T, T, 4>(st, s.k, x, dy, acc.Rl[0], nullptr, s.C, p.g[0], p.planes);
-  for (int i = 1; i < p.L; ++i)
-    launch_wgrad<float, float, 4>(st, s.k, xpyr + p.pyr_off[i], gpyr + p.pyr_off[i], acc.Rl[i], nullptr, s.C, p.g[i],
-                                  p.planes);
+  rc = launch_wgrad<T, T, 1>(st, s.k, x, dy, acc.Rb, acc.sumg, s.C, s.B, p.g[0]);
+  if (rc) return rc;
+  rc = launch_wgrad<T, T, 4>(st, s.k, x, dy, acc.Rl[0], nullptr, s.C, s.B, p.g[0]);
+  if (rc) return rc;
+  for (int i = 1; i < p.L; ++i) {
+    rc = launch_wgrad<float, float, 4>(st, s.k, xpyr + p.pyr_off[i], gpyr + p.pyr_off[i], acc.Rl[i], nullptr, s.C, s.B, p.g[i]);
+    if (rc) return rc;
+  }
   WtFinalize f;
   for (int l = 0; l < ADN_WT_MAX_LEVELS; ++l) f.Rl[l] = l < s.levels ? acc.Rl[l] : nullptr;
   f.Rb = acc.Rb; f.sumg = acc.sumg;

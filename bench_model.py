@@ -115,9 +115,15 @@ def train_bench(batch=32, img=128, steps=10, warmup=3, variant="dropin", bf16=Tr
     return res
 
 
-def infer_bench(batch=64, img=256, steps=5, warmup=2, variant="dropin", bf16=True):
+def infer_bench(batch=64, img=256, steps=5, warmup=2, variant="dropin", bf16=True, cpu_eval_sample=2):
+    """validate.py:92-118 on the device: eval + no_grad forward, then SimplifiedEvaluator.evaluate of the predictions - the
+    on-device evaluation path (adn_eval_batch: threshold counts + per-lead-time MSE in one kernel, no .cpu().numpy()).
+    `eval_baseline`: the reference's own evaluator (float2int + the Python loops over batch x frame x threshold around
+    _cal_frame, datasets/Shanghai_metrics.py:61-80, LPIPS / SSIM skipped) timed on the host on `cpu_eval_sample` samples."""
+    import numpy as np
     import torch
-    from adnm_unet_b200 import refhost, threshold_counts, csi_hss
+    from adnm_unet_b200 import refhost
+    from adnm_unet_b200.evaluator import SimplifiedEvaluator
     world, rank, local = _dist_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -125,7 +131,8 @@ def infer_bench(batch=64, img=256, steps=5, warmup=2, variant="dropin", bf16=Tru
     g = torch.Generator().manual_seed(7 + rank)
     x = torch.rand(batch, 5, 1, img, img, generator=g).to(dev)
     tgt = torch.rand(batch, 20, img, img, generator=g).to(dev)
-    tables = []
+    ev = SimplifiedEvaluator(seq_len=20, value_scale=90, thresholds=[20, 30, 35, 40], device=dev)
+    last = {}
 
     def step(i):
         with torch.no_grad():
@@ -134,18 +141,39 @@ def infer_bench(batch=64, img=256, steps=5, warmup=2, variant="dropin", bf16=Tru
                     out = model(x)
             else:
                 out = model(x)
-            tables.append(threshold_counts(out.squeeze(2).float(), tgt))
+            last["out"] = out
+            ev.evaluate(tgt, out.squeeze(2).float())
 
     for i in range(warmup):
         step(i)
-    tables.clear()
+    ev.reset()
     ms = _timed(torch, None, 1, dev, step, steps)
-    csi, hss = csi_hss(tables[-1])
+    table = ev.counts().clone()
+    res = ev.done()
+    # the evaluation alone, device vs the reference's host loops
+    pred = last["out"].squeeze(2).float().contiguous()
+    ev.reset()
+    ms_eval = _timed(torch, None, 1, dev, lambda i: ev.evaluate(tgt, pred), 5) / 5
+    nb = min(cpu_eval_sample, batch)
+    p_np, t_np = pred[:nb].cpu().numpy(), tgt[:nb].cpu().numpy()
+    t0 = time.perf_counter()
+    pi, ti = (np.clip(p_np, 0.0, 1.0) * 90).astype(np.uint16), (np.clip(t_np, 0.0, 1.0) * 90).astype(np.uint16)
+    for thr in (20, 30, 35, 40):
+        for b in range(nb):
+            for f in range(20):
+                ob, sb = (ti[b][f] >= thr).astype(int), (pi[b][f] >= thr).astype(int)
+                _ = (np.sum((ob == 1) & (sb == 1)), np.sum((ob == 1) & (sb == 0)), np.sum((ob == 0) & (sb == 1)), np.sum((ob == 0) & (sb == 0)))
+    cpu_s = time.perf_counter() - t0
+    csi = [res["threshold_metrics"][t]["CSI"] for t in (20, 30, 35, 40)]
+    hss = [res["threshold_metrics"][t]["HSS"] for t in (20, 30, 35, 40)]
     return {"metric": "adnm_unet_infer_seq_per_s", "value": batch * steps / (ms * 1e-3), "unit": "seq/s", "ms_per_step": ms / steps,
             "variant": variant, "dtype": "bf16 autocast" if bf16 else "f32",
-            "config": {"workload": f"ADNM-UNet inference (BASELINE configs[3], validate.py:96-106): B={batch}, 5->20 frames at {img}x{img}, "
-                                   "eval + no_grad forward + device threshold counts"},
-            "counts_table": tables[-1].cpu().tolist(), "csi": csi.cpu().tolist(), "hss": hss.cpu().tolist(),
+            "config": {"workload": f"ADNM-UNet inference (BASELINE configs[3], validate.py:92-118): B={batch}, 5->20 frames at {img}x{img}, "
+                                   "eval + no_grad forward + on-device SimplifiedEvaluator (threshold counts + RMSE)"},
+            "counts_table": table.cpu().tolist(), "csi": csi, "hss": hss, "rmse": res["RMSE"], "far": res["FAR"],
+            "evaluator": {"device_ms_per_batch": ms_eval, "device_samples_per_s": batch / (ms_eval * 1e-3),
+                          "eval_baseline": {"kind": "reference loops (float2int + _cal_frame over batch x frame x threshold) on the host",
+                                            "samples": nb, "samples_per_s": nb / cpu_s}},
             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30}
 
 
