@@ -196,6 +196,21 @@ __global__ void k_to_bf16(const float* __restrict__ a, bf16* __restrict__ oa, lo
   }
 }
 
+// depthwise taps, state_dict layout [C4][9] -> tap-major Kt[9][C4]: one coalesced 16-byte load per tap and thread in the conv
+// kernels (the native layout costs 36 scalar loads per thread that each touch 32 different cache lines per warp - eight
+// times the sector traffic of the activations themselves)
+__global__ void k_ffn_taps(const float* __restrict__ w_dw, float* __restrict__ Kt, int C4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 9 * C4) { const int t = i / C4, c = i - t * C4; Kt[i] = w_dw[c * 9 + t]; }
+}
+__device__ __forceinline__ void load_taps4(const float* __restrict__ Kt, int C4, int c0, float (&k)[9][4]) {
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 v = *reinterpret_cast<const float4*>(Kt + t * C4 + c0);
+    k[t][0] = v.x; k[t][1] = v.y; k[t][2] = v.z; k[t][3] = v.w;
+  }
+}
+
 template <typename T>
 __global__ void k_bias_add(T* __restrict__ y, const float* __restrict__ bias, long long n, int N) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -205,7 +220,7 @@ __global__ void k_bias_add(T* __restrict__ y, const float* __restrict__ bias, lo
 // out[n] += sum_t X[t][n]   (out zeroed by the caller).  block = 8 warps x 32 lanes; lane -> 4 columns; grid (ceil(N/128), chunks)
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_colsum(const T* __restrict__ X, long long ld, float* __restrict__ out, long long Ttok, int N, int tpb) {
+k_colsum(const T* __restrict__ X, long long ld, float* __restrict__ out, long long Ttok, int N, int tpb, int fold) {
   __shared__ float red[8][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 128 + lane * 4;
@@ -231,20 +246,26 @@ k_colsum(const T* __restrict__ X, long long ld, float* __restrict__ out, long lo
 #pragma unroll
     for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
     const int cc = blockIdx.x * 128 + threadIdx.x;
-    if (cc < N && v != 0.f) atomicAdd(out + cc, v);
+    if (cc < N && v != 0.f) atomicAdd(out + (fold ? cc % fold : cc), v);
   }
 }
 template <typename T>
 static inline void launch_colsum(cudaStream_t st, const T* X, long long ld, float* out, long long Ttok, int N) {
+  // narrow matrices (N = 32: 8 of 32 lanes busy) are summed as [T * N / 128][128] and folded modulo N at the end
+  int fold = 0;
+  if (N < 128 && 128 % N == 0 && ld == N && (Ttok * N) % 128 == 0) { fold = N; Ttok = Ttok * N / 128; N = 128; ld = 128; }
   int chunks = cdiv(4LL * sm_count(), cdiv(N, 128));
   long long tpb = (Ttok + chunks - 1) / chunks;
   tpb = tpb < 64 ? 64 : tpb;
   dim3 grid(cdiv(N, 128), cdiv(Ttok, tpb));
-  { ADN_KERNEL("k_colsum", st); k_colsum<T><<<grid, 256, 0, st>>>(X, ld, out, Ttok, N, (int)tpb); }
+  { ADN_KERNEL("k_colsum", st); k_colsum<T><<<grid, 256, 0, st>>>(X, ld, out, Ttok, N, (int)tpb, fold); }
 }
 
 // ---------------------------------------------------------------- FeedForward: depthwise 3x3 + gate, channels-last
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
 // bf16 storage: erf through Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below the bf16 rounding of the stored result) with
 // one fast exp, and the sigmoid through tanh.approx (one MUFU): the exact erff + expf pair made the gate the larger part of
 // k_ffn_conv_fwd's instruction stream.  fp32 storage (the 1e-4 check mode) keeps erff / expf.
@@ -261,14 +282,24 @@ __device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.
 template <typename T> struct Gate {      // exact
   static __device__ __forceinline__ float gelu(float x) { return gelu_f(x); }
   static __device__ __forceinline__ float sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+  static __device__ __forceinline__ void gelu_both(float x, float& g, float& dg) { g = gelu_f(x); dg = gelu_grad_f(x); }
 };
 template <> struct Gate<bf16> {
   static __device__ __forceinline__ float gelu(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f)); }
   static __device__ __forceinline__ float sigmoid(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+  // gelu and gelu' share the exponential: Phi(x) = (1 + erf(x / sqrt 2)) / 2 needs exp(-x^2 / 2), and phi(x) is that times 1 / sqrt(2 pi)
+  static __device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
+    const float z = x * 0.70710678118654752f, az = fabsf(z), t = __fdividef(1.f, fmaf(0.3275911f, az, 1.f));
+    const float e = __expf(-az * az);
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float cdf = 0.5f * (1.f + copysignf(1.f - p * t * e, z));
+    g = x * cdf;
+    dg = fmaf(x * 0.3989422804014327f, e, cdf);
+  }
 };
-__device__ __forceinline__ float gelu_grad_f(float x) {
-  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
-}
 
 constexpr int FROWS = 4, FCOLS = 8;
 // Four channels of one token in storage form: loaded first (all taps of a thread's rows in flight together - the first
@@ -324,11 +355,10 @@ k_ffn_conv_fwd(const T* __restrict__ h1, const float* __restrict__ Kc, const flo
   Raw4<T> raw[FROWS + 2][3];
   load_halo<T>(h1 + (long long)b * H * W * C4 + c0, C4, H, W, y0, x, live, raw);
   float k[9][4], bi[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-#pragma unroll
-    for (int t = 0; t < 9; ++t) k[t][i] = Kc[(c0 + i) * 9 + t];
-    bi[i] = b_dw[c0 + i];
+  load_taps4(Kc, C4, c0, k);
+  {
+    const float4 v = *reinterpret_cast<const float4*>(b_dw + c0);
+    bi[0] = v.x; bi[1] = v.y; bi[2] = v.z; bi[3] = v.w;
   }
 #pragma unroll
   for (int j = 0; j < FROWS; ++j) {
@@ -374,9 +404,11 @@ k_ffn_gate_bwd(const T* __restrict__ a, const T* __restrict__ dg, T* __restrict_
     ld4(a + t * C4 + c0, a1); ld4(a + t * C4 + C2 + c0, a2); ld4(dg + t * C2 + c0, g);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float s = sigmoid_t<T>(a2[j]);
-      o1[j] = g[j] * s * gelu_grad_f(a1[j]);
-      o2[j] = g[j] * gelu_f(a1[j]) * s * (1.f - s);
+      const float s = Gate<T>::sigmoid(a2[j]);
+      float ge, dge;
+      Gate<T>::gelu_both(a1[j], ge, dge);
+      o1[j] = g[j] * s * dge;
+      o2[j] = g[j] * ge * s * (1.f - s);
     }
     st4(da + t * C4 + c0, o1);
     st4(da + t * C4 + C2 + c0, o2);
@@ -402,10 +434,7 @@ k_ffn_conv_bwd(const T* __restrict__ da, const T* __restrict__ h1, const float* 
   float dk[9][4] = {}, sda[4] = {}, sdh[4] = {};
   if (active) {
     float k[9][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int t = 0; t < 9; ++t) k[t][i] = Kc[(c0 + i) * 9 + t];
+    load_taps4(Kc, C4, c0, k);
     for (int z = blockIdx.z; z < Bn * ybl; z += gridDim.z) {
       const int b = z / ybl, y0 = (z - b * ybl) * FROWS;
       const long long boff = (long long)b * H * W;
@@ -541,12 +570,14 @@ struct FfnSaved {
 template <typename T>
 struct FfnFwdW {
   int* status;
+  float* Kt;
   bf16 *w_in, *w_out;
   T *h1, *gated;      // inference: the two intermediates live here
   size_t bytes;
   FfnFwdW(const FfnDims& d, void* p) {
     Carver c(p);
     status = c.take<int>(64);
+    Kt = c.take<float>((size_t)9 * d.C4);
     w_in = c.take<bf16>((size_t)d.C4 * d.D);
     w_out = c.take<bf16>((size_t)d.D * d.C2);
     h1 = c.take<T>((size_t)d.T * d.C4);
@@ -557,12 +588,14 @@ struct FfnFwdW {
 template <typename T>
 struct FfnBwdW {
   int* status;
+  float* Kt;
   bf16 *w_in, *w_out;
   T *dgated, *da, *dh1;
   size_t bytes;
   FfnBwdW(const FfnDims& d, void* p) {
     Carver c(p);
     status = c.take<int>(64);
+    Kt = c.take<float>((size_t)9 * d.C4);
     w_in = c.take<bf16>((size_t)d.C4 * d.D);
     w_out = c.take<bf16>((size_t)d.D * d.C2);
     dgated = c.take<T>((size_t)d.T * d.C2);
@@ -598,12 +631,13 @@ static int ffn_forward(const FfnDims& d, int dtype, const AdnFfnWeights& w, cons
     k_to_bf16<<<ew_grid((long long)d.C4 * d.D + (long long)d.D * d.C2), 256, 0, st>>>((const float*)w.w_in, W.w_in, (long long)d.C4 * d.D,
                                                                                        (const float*)w.w_out, W.w_out, (long long)d.D * d.C2);
   }
+  { ADN_KERNEL("k_ffn_taps", st); k_ffn_taps<<<cdiv(9 * d.C4, 256), 256, 0, st>>>((const float*)w.w_dw, W.Kt, d.C4); }
   int rc = gemm_xwT<T>(st, "ffn_project_in", tc, x, d.T, d.D, (const float*)w.w_in, W.w_in, d.C4, (const float*)w.b_in, h1, W.status);
   if (rc) return rc;
   {
     dim3 grid(cdiv(d.C2, 64), cdiv(d.W, FCOLS), d.B * cdiv(d.H, FROWS)), block(32, FCOLS);
     ADN_KERNEL("k_ffn_conv_fwd", st);
-    k_ffn_conv_fwd<T><<<grid, block, 0, st>>>(h1, (const float*)w.w_dw, (const float*)w.b_dw, training ? S.a : nullptr, gated, d.H, d.W, d.C4);
+    k_ffn_conv_fwd<T><<<grid, block, 0, st>>>(h1, W.Kt, (const float*)w.b_dw, training ? S.a : nullptr, gated, d.H, d.W, d.C4);
   }
   rc = gemm_xwT<T>(st, "ffn_project_out", tc, gated, d.T, d.C2, (const float*)w.w_out, W.w_out, d.D, (const float*)w.b_out, y, W.status);
   if (rc) return rc;
@@ -630,6 +664,7 @@ static int ffn_backward(const FfnDims& d, int dtype, const AdnFfnWeights& w, con
     k_to_bf16<<<ew_grid((long long)d.C4 * d.D + (long long)d.D * d.C2), 256, 0, st>>>((const float*)w.w_in, W.w_in, (long long)d.C4 * d.D,
                                                                                        (const float*)w.w_out, W.w_out, (long long)d.D * d.C2);
   }
+  { ADN_KERNEL("k_ffn_taps", st); k_ffn_taps<<<cdiv(9 * d.C4, 256), 256, 0, st>>>((const float*)w.w_dw, W.Kt, d.C4); }
   // project_out backward
   int rc = gemm_xw<T>(st, "ffn_dgated", tc, dy, d.T, d.D, (const float*)w.w_out, W.w_out, d.C2, W.dgated, W.status);
   if (rc) return rc;
@@ -645,10 +680,10 @@ static int ffn_backward(const FfnDims& d, int dtype, const AdnFfnWeights& w, con
     dim3 grid(gx, gy, gz), block(32, FCOLS);
     ADN_KERNEL("k_ffn_conv_bwd", st);
     if (env().variant & 1)
-      k_ffn_conv_bwd<T, 2><<<grid, block, 0, st>>>(W.da, S.h1, (const float*)w.w_dw, W.dh1, (float*)g.w_dw, (float*)g.b_dw, (float*)g.b_in, d.B,
+      k_ffn_conv_bwd<T, 2><<<grid, block, 0, st>>>(W.da, S.h1, W.Kt, W.dh1, (float*)g.w_dw, (float*)g.b_dw, (float*)g.b_in, d.B,
                                                    d.H, d.W, d.C4);
     else
-      k_ffn_conv_bwd<T, 1><<<grid, block, 0, st>>>(W.da, S.h1, (const float*)w.w_dw, W.dh1, (float*)g.w_dw, (float*)g.b_dw, (float*)g.b_in, d.B,
+      k_ffn_conv_bwd<T, 1><<<grid, block, 0, st>>>(W.da, S.h1, W.Kt, W.dh1, (float*)g.w_dw, (float*)g.b_dw, (float*)g.b_in, d.B,
                                                    d.H, d.W, d.C4);
   }
   // project_in backward

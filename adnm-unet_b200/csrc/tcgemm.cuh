@@ -220,12 +220,17 @@ k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_c
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
         }
+        // all TMEM loads of the slab are issued before the one wait (a wait per 16 columns exposed the TMEM latency 16 times
+        // per 128 x 256 tile: the skinny, epilogue-bound GEMMs of the mixer / FeedForward spent most of their time there)
+        float vv[4][16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q * 16 < cw) tmem_ld16(tmem_addr(tacc, warp * 32, c0 + q * 16), vv[q]);
+        tmem_wait_ld();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {          // 16 accumulator columns per step
           if (q * 16 >= cw) break;
-          float v[16];
-          tmem_ld16(tmem_addr(tacc, warp * 32, c0 + q * 16), v);
-          tmem_wait_ld();
+          float (&v)[16] = vv[q];
           const int n = n0 + c0 + q * 16;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
