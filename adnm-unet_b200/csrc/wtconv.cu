@@ -96,14 +96,17 @@ __global__ void k_haar_ll_vec(const TI* __restrict__ in, float* __restrict__ out
 // ratio but halves the warps an SM can hold - 512 bytes of tile per thread - and measured slower: the tile staging, one
 // exposed HBM latency per CTA, then has too few other warps to hide behind.)
 // ---------------------------------------------------------------------------------------------
-constexpr int WT_T = 32, WT_THREADS = 128, WT_BH = 2;      // sub-band tile edge; a thread owns WT_BH x 4 positions
-template <int K> struct WtTile {
-  static constexpr int R = K / 2, SH = WT_T + 2 * R;
+constexpr int WT_BH = 2;                                    // a thread owns WT_BH x 4 positions
+// sub-band tile edge TT: 32 (128 threads) for planes with more than 16 x 16 sub-band positions, else 16 (32 threads) - a
+// 32 x 32 plane of the model's deeper stages (16 x 16 positions per band) filled a quarter of the large tile
+__host__ __device__ constexpr int wt_threads(int TT) { return (TT / 4) * (TT / WT_BH); }
+template <int K, int TT> struct WtTile {
+  static constexpr int R = K / 2, SH = TT + 2 * R;
   static constexpr int VW = ((4 + K - 1) + 3) / 4 * 4;          // values a thread reads per row: whole 16-byte vectors
-  static constexpr int SP = ((WT_T - 4 + VW) + 3) / 4 * 4;      // row pitch of S (the last block's vectors stay inside the row)
+  static constexpr int SP = ((TT - 4 + VW) + 3) / 4 * 4;      // row pitch of S (the last block's vectors stay inside the row)
   static constexpr int POFF = (4 - R % 4) % 4;                  // column shift of the pixel tile: a block's first column is 16-byte aligned
   static constexpr int PVW = ((8 + K - 1) + 3) / 4 * 4;
-  static constexpr int PW_WRITE = 2 * (WT_T + 2 * R) + POFF, PW_READ = 2 * (WT_T - 4) + R + POFF + PVW;
+  static constexpr int PW_WRITE = 2 * (TT + 2 * R) + POFF, PW_READ = 2 * (TT - 4) + R + POFF + PVW;
   static constexpr int PH = 2 * SH, PP = ((PW_WRITE > PW_READ ? PW_WRITE : PW_READ) + 3) / 4 * 4;
 };
 
@@ -112,25 +115,26 @@ template <int K> struct WtTile {
 // one thread and tracked by an mbarrier; the CTA is persistent and the copy of its NEXT tile is issued as soon as the current
 // raw tile has been transformed, so it lands while the FMAs of the current tile run.  TMA == false (row pitch or plane size
 // not a multiple of 16 bytes): the same tile is gathered with per-thread loads.
-template <typename TI, int K> struct WtRaw {
+template <typename TI, int K, int TT> struct WtRaw {
   static constexpr int PER = 4 / (int)sizeof(TI);      // pixels per 32-bit TMA element
   // The box must START on a 16-byte boundary of the row (measured: a bf16 tile whose first pixel is 8 bytes into a 16-byte
   // unit faults with "illegal instruction" on the first copy; the fp32 tile, 16 bytes in, copies fine), so the tile is widened
   // to the left by XOFF pixels, and its rows are whole 32-byte units.
-  static constexpr int APX = 16 / (int)sizeof(TI), XOFF = (APX - (2 * WtTile<K>::R) % APX) % APX;
+  static constexpr int APX = 16 / (int)sizeof(TI), XOFF = (APX - (2 * WtTile<K, TT>::R) % APX) % APX;
   static constexpr int PXQ = 32 / (int)sizeof(TI);
-  static constexpr int BH = 2 * WtTile<K>::SH, BW = (2 * (WT_T + 2 * WtTile<K>::R) + XOFF + PXQ - 1) / PXQ * PXQ;
+  static constexpr int BH = 2 * WtTile<K, TT>::SH, BW = (2 * (TT + 2 * WtTile<K, TT>::R) + XOFF + PXQ - 1) / PXQ * PXQ;
   static constexpr size_t BYTES = ((size_t)BH * BW * sizeof(TI) + 127) / 128 * 128;
 };
 
-template <typename TI, typename TO, int K, bool BASE, bool FLIP, bool TMA>
-__global__ void __launch_bounds__(WT_THREADS, 4)
+template <typename TI, typename TO, int K, bool BASE, bool FLIP, bool TMA, int TT>
+__global__ void __launch_bounds__(wt_threads(TT), 4)
 k_wt_level(const __grid_constant__ CUtensorMap map, const TI* __restrict__ in, const float* __restrict__ coarse, TO* __restrict__ out,
            const float* __restrict__ Wl, const float* __restrict__ scale, const float* __restrict__ Wb,
            const float* __restrict__ bias, const float* __restrict__ bscale, int C, LevelGeom g, int tiles_x,
            int tiles_y, int total) {
-  using G = WtTile<K>;
-  using RW = WtRaw<TI, K>;
+  using G = WtTile<K, TT>;
+  using RW = WtRaw<TI, K, TT>;
+  constexpr int WT_T = TT, WT_THREADS = wt_threads(TT);
   constexpr int R = G::R, SH = G::SH, SW = WT_T + 2 * R, SP = G::SP;
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);      // TMA destinations: 128-byte aligned
@@ -153,7 +157,7 @@ k_wt_level(const __grid_constant__ CUtensorMap map, const TI* __restrict__ in, c
     }
   }
   uint32_t phase = 0;
-  const int py = (tid >> 3) * WT_BH, px = (tid & 7) * 4;  // block origin inside the tile
+  const int py = (tid / (WT_T / 4)) * WT_BH, px = (tid % (WT_T / 4)) * 4;  // block origin inside the tile
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const int pl = tile / per_plane, rem = tile - pl * per_plane, ty = rem / tiles_x, tx = rem - ty * tiles_x;
     const long long plane = pl;
@@ -332,9 +336,9 @@ k_wt_level(const __grid_constant__ CUtensorMap map, const TI* __restrict__ in, c
     __syncthreads();                                        // S / Px / weights may be overwritten by the next tile
   }
 }
-template <typename TI, int K, bool BASE, bool TMA> static constexpr size_t wt_level_smem() {
-  using G = WtTile<K>;
-  return 128 + (TMA ? WtRaw<TI, K>::BYTES : 0) + sizeof(float) * (4 * (size_t)G::SH * G::SP + (BASE ? (size_t)G::PH * G::PP : 0));
+template <typename TI, int K, bool BASE, bool TMA, int TT> static constexpr size_t wt_level_smem() {
+  using G = WtTile<K, TT>;
+  return 128 + (TMA ? WtRaw<TI, K, TT>::BYTES : 0) + sizeof(float) * (4 * (size_t)G::SH * G::SP + (BASE ? (size_t)G::PH * G::PP : 0));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -349,28 +353,29 @@ template <typename TI, int K, bool BASE, bool TMA> static constexpr size_t wt_le
 // ---------------------------------------------------------------------------------------------
 // raw tiles of the correlation kernel: `x` with the k/2 halo (pixels of the level for NB == 4, the correlation domain itself
 // for NB == 1), `g` without; same 16-byte origin / 32-byte row rules as WtRaw
-template <typename T, int K, int NB> struct WtRawX {
+template <typename T, int K, int NB, int TT> struct WtRawX {
   static constexpr int PER = 4 / (int)sizeof(T), APX = 16 / (int)sizeof(T), PXQ = 32 / (int)sizeof(T);
-  static constexpr int R = WtTile<K>::R, SW = WT_T + 2 * R;
+  static constexpr int R = WtTile<K, TT>::R, SW = TT + 2 * R;
   static constexpr int LEFT = NB == 4 ? 2 * R : R;                               // halo pixels left of the tile origin
   static constexpr int XOFF = (APX - LEFT % APX) % APX;
-  static constexpr int BH = (NB == 4 ? 2 : 1) * WtTile<K>::SH, BW = ((NB == 4 ? 2 : 1) * SW + XOFF + PXQ - 1) / PXQ * PXQ;
+  static constexpr int BH = (NB == 4 ? 2 : 1) * WtTile<K, TT>::SH, BW = ((NB == 4 ? 2 : 1) * SW + XOFF + PXQ - 1) / PXQ * PXQ;
   static constexpr size_t BYTES = ((size_t)BH * BW * sizeof(T) + 127) / 128 * 128;
 };
-template <typename T, int NB> struct WtRawG {
+template <typename T, int NB, int TT> struct WtRawG {
   static constexpr int PER = 4 / (int)sizeof(T);
-  static constexpr int BH = (NB == 4 ? 2 : 1) * WT_T, BW = BH;
+  static constexpr int BH = (NB == 4 ? 2 : 1) * TT, BW = BH;
   static constexpr size_t BYTES = ((size_t)BH * BW * sizeof(T) + 127) / 128 * 128;
 };
 
-template <typename TX, typename TG, int K, int NB, bool TMA>
-__global__ void __launch_bounds__(WT_THREADS, 4)
+template <typename TX, typename TG, int K, int NB, bool TMA, int TT>
+__global__ void __launch_bounds__(wt_threads(TT), 4)
 k_wt_wgrad(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapg, const TX* __restrict__ xin,
            const TG* __restrict__ gin, float* __restrict__ Rout, float* __restrict__ sumg, int C, int Bn, LevelGeom g, int tiles_x,
            int tiles_y) {
-  using G = WtTile<K>;
-  using RX = WtRawX<TX, K, NB>;
-  using RG = WtRawG<TG, NB>;
+  using G = WtTile<K, TT>;
+  using RX = WtRawX<TX, K, NB, TT>;
+  using RG = WtRawG<TG, NB, TT>;
+  constexpr int WT_T = TT, WT_THREADS = wt_threads(TT);
   constexpr int R = G::R, SH = G::SH, SW = WT_T + 2 * R, SP = G::SP, DP = WT_T + 4;
   constexpr int MUL = NB == 4 ? 2 : 1;                   // raw pixels per correlation position along each axis
   extern __shared__ uint8_t smem_dyn[];
@@ -380,12 +385,12 @@ k_wt_wgrad(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUt
   float* smem = reinterpret_cast<float*>(smem_raw + (TMA ? RX::BYTES + RG::BYTES : 0));
   float (*S)[SH][SP] = reinterpret_cast<float (*)[SH][SP]>(smem);                       // [NB][SH][SP]
   float (*Dt)[WT_T][DP] = reinterpret_cast<float (*)[WT_T][DP]>(smem + NB * SH * SP);   // [NB][WT_T][DP]
-  __shared__ float red[WT_THREADS / 32][NB * K * K + 1];
+  __shared__ float red[(WT_THREADS + 31) / 32][NB * K * K + 1];
   __shared__ uint64_t bar;
   const int c = blockIdx.x;
   const int dh = NB == 4 ? g.h2 : g.h, dw = NB == 4 ? g.w2 : g.w;      // extent of the correlation domain
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int py = (tid >> 3) * WT_BH, px = (tid & 7) * 4;
+  const int py = (tid / (WT_T / 4)) * WT_BH, px = (tid % (WT_T / 4)) * 4;
   float acc[NB][K * K];
 #pragma unroll
   for (int band = 0; band < NB; ++band)
@@ -559,15 +564,15 @@ k_wt_wgrad(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUt
   for (int i = tid; i < NB * K * K + 1; i += WT_THREADS) {
     float v = 0.f;
 #pragma unroll
-    for (int q = 0; q < WT_THREADS / 32; ++q) v += red[q][i];
+    for (int q = 0; q < (WT_THREADS + 31) / 32; ++q) v += red[q][i];
     if (i < NB * K * K) { if (v != 0.f) atomicAdd(Rout + (long long)c * NB * K * K + i, v); }
     else if (NB == 1 && sumg) atomicAdd(sumg + c, v);
   }
 }
-template <typename TX, typename TG, int K, int NB, bool TMA> static constexpr size_t wt_wgrad_smem() {
-  using G = WtTile<K>;
-  return 128 + (TMA ? WtRawX<TX, K, NB>::BYTES + WtRawG<TG, NB>::BYTES : 0) +
-         sizeof(float) * ((size_t)NB * G::SH * G::SP + (size_t)NB * WT_T * (WT_T + 4));
+template <typename TX, typename TG, int K, int NB, bool TMA, int TT> static constexpr size_t wt_wgrad_smem() {
+  using G = WtTile<K, TT>;
+  return 128 + (TMA ? WtRawX<TX, K, NB, TT>::BYTES + WtRawG<TG, NB, TT>::BYTES : 0) +
+         sizeof(float) * ((size_t)NB * G::SH * G::SP + (size_t)NB * TT * (TT + 4));
 }
 
 // dW_i = scale_i * R_i ; dscale_i[ch] = sum_ab W_i R_i ; dW_b = bs * R_b ; dbs = sum W_b R_b + bias * sumdy ; dbias = bs * sumdy
@@ -690,9 +695,9 @@ static int wt_make_map(CUtensorMap* map, const T* base, long long planes, int h,
               planes, h, w, box_w, box_h);
   return ADN_OK;
 }
-static inline int wt_persistent_grid(long long total, size_t smem) {
+static inline int wt_persistent_grid(long long total, size_t smem, int max_per_sm) {
   long long per_sm = (long long)(227 * 1024) / (long long)(smem + 1024);
-  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  per_sm = per_sm < 1 ? 1 : (per_sm > max_per_sm ? max_per_sm : per_sm);
   const long long cap = per_sm * sm_count();
   return (int)(total < cap ? total : cap);
 }
@@ -701,23 +706,26 @@ template <typename TI, typename TO, bool BASE, bool FLIP>
 static int launch_level(cudaStream_t st, int k, const TI* in, const float* coarse, TO* out, const float* Wl,
                         const float* scale, const float* Wb, const float* bias, const float* bscale, int C,
                         const LevelGeom& g, long long planes) {
-  int tx = cdiv(g.w2, WT_T), ty = cdiv(g.h2, WT_T);
+  const bool small = g.w2 <= 16 && g.h2 <= 16;
+  const int TTv = small ? 16 : 32;
+  int tx = cdiv(g.w2, TTv), ty = cdiv(g.h2, TTv);
   long long blocks = planes * tx * ty;
   ADN_REQUIRE(blocks < (1LL << 31) && planes < (1LL << 31), ADN_ERR_SHAPE, "wtconv: too many tiles");
   const bool use_tma = wt_tma_ok(in, g.h, g.w) && !(env().variant & 2);
-#define ADN_WT_LAUNCH_T(KK, TMAF)                                                                                \
+#define ADN_WT_LAUNCH_T(KK, TMAF, TTC)                                                                           \
   {                                                                                                              \
-    constexpr size_t smem = wt_level_smem<TI, KK, BASE, TMAF>();                                                 \
+    constexpr size_t smem = wt_level_smem<TI, KK, BASE, TMAF, TTC>();                                            \
     static bool attr = false;                                                                                    \
-    if (!attr) { ADN_CHECK_CUDA(cudaFuncSetAttribute(k_wt_level<TI, TO, KK, BASE, FLIP, TMAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
+    if (!attr) { ADN_CHECK_CUDA(cudaFuncSetAttribute(k_wt_level<TI, TO, KK, BASE, FLIP, TMAF, TTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
     CUtensorMap map;                                                                                             \
     memset(&map, 0, sizeof(map));                                                                                \
-    if (TMAF) { int rc = wt_make_map<TI>(&map, in, planes, g.h, g.w, WtRaw<TI, KK>::BW, WtRaw<TI, KK>::BH); if (rc) return rc; } \
+    if (TMAF) { int rc = wt_make_map<TI>(&map, in, planes, g.h, g.w, WtRaw<TI, KK, TTC>::BW, WtRaw<TI, KK, TTC>::BH); if (rc) return rc; } \
     ADN_KERNEL("k_wt_level", st);                                                                                \
-    k_wt_level<TI, TO, KK, BASE, FLIP, TMAF><<<wt_persistent_grid(blocks, smem), WT_THREADS, smem, st>>>(        \
+    k_wt_level<TI, TO, KK, BASE, FLIP, TMAF, TTC><<<wt_persistent_grid(blocks, smem, TTC == 16 ? 16 : 4), wt_threads(TTC), smem, st>>>( \
         map, in, coarse, out, Wl, scale, Wb, bias, bscale, C, g, tx, ty, (int)blocks);                           \
   }
-#define ADN_WT_LAUNCH(KK) if (use_tma) ADN_WT_LAUNCH_T(KK, true) else ADN_WT_LAUNCH_T(KK, false)
+#define ADN_WT_LAUNCH_S(KK, TTC) if (use_tma) ADN_WT_LAUNCH_T(KK, true, TTC) else ADN_WT_LAUNCH_T(KK, false, TTC)
+#define ADN_WT_LAUNCH(KK) if (small) { ADN_WT_LAUNCH_S(KK, 16) } else { ADN_WT_LAUNCH_S(KK, 32) }
   switch (k) {
     case 1: ADN_WT_LAUNCH(1); break;
     case 3: ADN_WT_LAUNCH(3); break;
@@ -725,6 +733,7 @@ static int launch_level(cudaStream_t st, int k, const TI* in, const float* coars
     default: ADN_WT_LAUNCH(7); break;
   }
 #undef ADN_WT_LAUNCH
+#undef ADN_WT_LAUNCH_S
 #undef ADN_WT_LAUNCH_T
   return ADN_OK;
 }
@@ -733,17 +742,20 @@ template <typename TX, typename TG, int NB>
 static int launch_wgrad(cudaStream_t st, int k, const TX* xin, const TG* gin, float* Rout, float* sumg, int C, int Bn,
                         const LevelGeom& g) {
   int dh = NB == 4 ? g.h2 : g.h, dw = NB == 4 ? g.w2 : g.w;
-  int tx = cdiv(dw, WT_T), ty = cdiv(dh, WT_T);
+  const bool small = dw <= 16 && dh <= 16;
+  const int TTv = small ? 16 : 32;
+  int tx = cdiv(dw, TTv), ty = cdiv(dh, TTv);
   const long long items = (long long)Bn * tx * ty, planes = (long long)Bn * C;
   ADN_REQUIRE(items < (1LL << 31) && planes < (1LL << 31), ADN_ERR_SHAPE, "wtconv: too many tiles");
   const bool use_tma = wt_tma_ok(xin, g.h, g.w) && wt_tma_ok(gin, g.h, g.w) && !(env().variant & 2);
-#define ADN_WT_LAUNCH_T(KK, TMAF)                                                                                \
+#define ADN_WT_LAUNCH_T(KK, TMAF, TTC)                                                                           \
   {                                                                                                              \
-    constexpr size_t smem = wt_wgrad_smem<TX, TG, KK, NB, TMAF>();                                               \
+    constexpr size_t smem = wt_wgrad_smem<TX, TG, KK, NB, TMAF, TTC>();                                          \
     static bool attr = false;                                                                                    \
-    if (!attr) { ADN_CHECK_CUDA(cudaFuncSetAttribute(k_wt_wgrad<TX, TG, KK, NB, TMAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
+    if (!attr) { ADN_CHECK_CUDA(cudaFuncSetAttribute(k_wt_wgrad<TX, TG, KK, NB, TMAF, TTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; } \
     long long per_sm = (long long)(227 * 1024) / (long long)(smem + 1024);                                       \
-    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);                                                         \
+    const long long cap_sm = TTC == 16 ? 16 : 4;                                                                 \
+    per_sm = per_sm < 1 ? 1 : (per_sm > cap_sm ? cap_sm : per_sm);                                               \
     int split = cdiv(per_sm * sm_count(), C);      /* one resident wave of CTAs, each striding over its channel's work items */ \
     split = split < 1 ? 1 : (split > items ? (int)items : split);                                                \
     if (split > 65535) split = 65535;                                                                            \
@@ -751,15 +763,16 @@ static int launch_wgrad(cudaStream_t st, int k, const TX* xin, const TG* gin, fl
     CUtensorMap mx, mg;                                                                                          \
     memset(&mx, 0, sizeof(mx)); memset(&mg, 0, sizeof(mg));                                                      \
     if (TMAF) {                                                                                                  \
-      int rc = wt_make_map<TX>(&mx, xin, planes, g.h, g.w, WtRawX<TX, KK, NB>::BW, WtRawX<TX, KK, NB>::BH);      \
+      int rc = wt_make_map<TX>(&mx, xin, planes, g.h, g.w, WtRawX<TX, KK, NB, TTC>::BW, WtRawX<TX, KK, NB, TTC>::BH); \
       if (rc) return rc;                                                                                         \
-      rc = wt_make_map<TG>(&mg, gin, planes, g.h, g.w, WtRawG<TG, NB>::BW, WtRawG<TG, NB>::BH);                  \
+      rc = wt_make_map<TG>(&mg, gin, planes, g.h, g.w, WtRawG<TG, NB, TTC>::BW, WtRawG<TG, NB, TTC>::BH);        \
       if (rc) return rc;                                                                                         \
     }                                                                                                            \
     ADN_KERNEL("k_wt_wgrad", st);                                                                                \
-    k_wt_wgrad<TX, TG, KK, NB, TMAF><<<grid, WT_THREADS, smem, st>>>(mx, mg, xin, gin, Rout, sumg, C, Bn, g, tx, ty); \
+    k_wt_wgrad<TX, TG, KK, NB, TMAF, TTC><<<grid, wt_threads(TTC), smem, st>>>(mx, mg, xin, gin, Rout, sumg, C, Bn, g, tx, ty); \
   }
-#define ADN_WT_LAUNCH(KK) if (use_tma) ADN_WT_LAUNCH_T(KK, true) else ADN_WT_LAUNCH_T(KK, false)
+#define ADN_WT_LAUNCH_S(KK, TTC) if (use_tma) ADN_WT_LAUNCH_T(KK, true, TTC) else ADN_WT_LAUNCH_T(KK, false, TTC)
+#define ADN_WT_LAUNCH(KK) if (small) { ADN_WT_LAUNCH_S(KK, 16) } else { ADN_WT_LAUNCH_S(KK, 32) }
   switch (k) {
     case 1: ADN_WT_LAUNCH(1); break;
     case 3: ADN_WT_LAUNCH(3); break;
@@ -767,6 +780,7 @@ static int launch_wgrad(cudaStream_t st, int k, const TX* xin, const TG* gin, fl
     default: ADN_WT_LAUNCH(7); break;
   }
 #undef ADN_WT_LAUNCH
+#undef ADN_WT_LAUNCH_S
 #undef ADN_WT_LAUNCH_T
   return ADN_OK;
 }
