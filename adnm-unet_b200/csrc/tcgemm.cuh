@@ -61,7 +61,11 @@ struct Args {
                                               // the gradient w.r.t. the conv output becomes the gradient w.r.t. its input)
   int a_bz[2], b_bz[2];    // 1: the operand of that segment has a batch dimension (else every batch reads the same matrix)
   const float* bias;       // optional fp32 vector [N] added after alpha (1x1 conv / Linear bias)
-  int dbg;                 // knock-outs for profiling (adn_set_option("gemm_dbg")): 1 no epilogue stores, 2 no operand loads, 4 no MMAs
+  int dbg;                 // knock-outs for profiling (adn_set_option("gemm_dbg")): 1 no epilogue stores, 2 no operand loads, 4 no MMAs,
+                           // 8 no proxy fence, 16 no epilogue math / staging, 32 no TMEM loads.  Measured (profiles/gemm_knockout.py,
+                           // gpurun_out/r3g): the bare barrier skeleton costs ~0.45 us per k-tile commit whatever the ring depth (4 ... 8
+                           // stages: no change) - 8192^3 is bound by it (785 of 892 us with loads, MMAs and stores all knocked out) - and on
+                           // the skinny GEMMs (K <= 128) the epilogue arithmetic + staging is another 40-50 % of the launch
 };
 
 __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
@@ -223,13 +227,15 @@ k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_c
         // all TMEM loads of the slab are issued before the one wait (a wait per 16 columns exposed the TMEM latency 16 times
         // per 128 x 256 tile: the skinny, epilogue-bound GEMMs of the mixer / FeedForward spent most of their time there)
         float vv[4][16];
+        if (!(a.dbg & 32)) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (q * 16 < cw) tmem_ld16(tmem_addr(tacc, warp * 32, c0 + q * 16), vv[q]);
-        tmem_wait_ld();
+          for (int q = 0; q < 4; ++q)
+            if (q * 16 < cw) tmem_ld16(tmem_addr(tacc, warp * 32, c0 + q * 16), vv[q]);
+          tmem_wait_ld();
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {          // 16 accumulator columns per step
-          if (q * 16 >= cw) break;
+          if (q * 16 >= cw || (a.dbg & 16)) break;
           float (&v)[16] = vv[q];
           const int n = n0 + c0 + q * 16;
 #pragma unroll
@@ -270,7 +276,7 @@ k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_c
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + lane * 128 + (((q * 4 + t) ^ (lane & 7)) << 4)), "f"(v[4 * t]), "f"(v[4 * t + 1]), "f"(v[4 * t + 2]), "f"(v[4 * t + 3]) : "memory");
           }
         }
-        fence_async_smem();
+        if (!(a.dbg & 8)) fence_async_smem();
         __syncwarp();
         if (lane == 0 && !(a.dbg & 1)) {
           if (a.c_mode == C_ATOMIC_F32) tma_reduce_add_3d(&mC, sb, n0 + c0, m0 + warp * 32, batch);
