@@ -678,7 +678,8 @@ def load_step_traffic():
     d = _ncu_summary()
     if not d:
         return None
-    return float(sum(e["dram_read_bytes"] + e["dram_write_bytes"] for e in d.get("kernels", {}).values()))
+    # every kernel of the chain launches once per step; a capture window may hold a second launch of one of them
+    return float(sum((e["dram_read_bytes"] + e["dram_write_bytes"]) / max(1, e.get("launches", 1)) for e in d.get("kernels", {}).values()))
 
 
 def main():
