@@ -27,6 +27,11 @@ int sm_count() {
     n = (cudaGetDevice(&dev) == cudaSuccess &&
          cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;
     cudaGetLastError();
+    // ADN_SM_RESERVE=k: size every persistent grid for (SMs - k).  Data-parallel runs set 1: the persistent kernels hold one CTA
+    // per SM with most of its shared memory, so a concurrently running NCCL all-reduce CTA would otherwise displace one of
+    // them and add a whole extra wave to that kernel (measured as the weak-scaling loss of round 1: 0.281 -> 0.337 ms at N = 8).
+    const char* e = getenv("ADN_SM_RESERVE");
+    if (e) { const int k = atoi(e); if (k > 0 && k < n) n -= k; }
   }
   return n;
 }

@@ -213,6 +213,9 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # leave one SM to the NCCL all-reduce that runs beside the persistent (one CTA per SM) kernels; read once by the library
+        os.environ.setdefault("ADN_SM_RESERVE", "1")
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

@@ -59,6 +59,8 @@ def train_bench(batch=32, img=128, steps=10, warmup=3, variant="dropin", bf16=Tr
     from adnm_unet_b200.trainer import DataParallelTrainer
 
     world, rank, local = _dist_env()
+    if world > 1:
+        os.environ.setdefault("ADN_SM_RESERVE", "1")      # one SM for the NCCL CTAs beside the persistent kernels (read once by the library)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1 and not dist.is_initialized() and init_dist:
