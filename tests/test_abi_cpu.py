@@ -99,3 +99,52 @@ def test_product_path_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_block_level_entry_points_validate_on_the_host(lib):
+    """The Block / attention / evaluator entry points reject bad shapes and dtypes before touching the device."""
+    from adnm_unet_b200 import _lib
+    assert C.sizeof(_lib.AdnFfnShape) == 24 and C.sizeof(_lib.AdnFfnWeights) == 6 * 8
+    a, b, c = (C.c_size_t() for _ in range(3))
+    ok = _lib.AdnFfnShape(B=32, H=128, W=128, D=32, C4=128, dtype=_lib.ADN_BF16)
+    assert lib.adn_ffn_workspace_bytes(ok, a, b, c) == 0
+    T = 32 * 128 * 128
+    assert a.value >= T * (128 + 128 + 64) * 2 and b.value > 0 and c.value >= T * (64 + 128 + 128) * 2
+    for field, val in (("D", 30), ("C4", 100), ("dtype", 5), ("B", 0)):
+        bad = _lib.AdnFfnShape(B=32, H=128, W=128, D=32, C4=128, dtype=_lib.ADN_BF16)
+        setattr(bad, field, val)
+        assert lib.adn_ffn_workspace_bytes(bad, a, b, c) != 0 and lib.adn_last_error()
+    one = C.c_void_p(256)      # never dereferenced: validation comes first
+    assert lib.adn_sdpa_forward(one, one, None, 2, 16, 8, 5, 0.5, _lib.ADN_BF16, None) != 0 and b"dim_head" in lib.adn_last_error()
+    assert lib.adn_sdpa_forward(one, one, None, 2, 16, 8, 4, 0.5, 9, None) != 0 and b"dtype" in lib.adn_last_error()
+    assert lib.adn_rmsnorm_forward(one, one, None, None, one, None, 10, 30, 1e-6, _lib.ADN_F32, None) != 0
+    assert lib.adn_residual_forward(one, one, one, one, None, one, 0, 32, _lib.ADN_F32, None) != 0
+    nb = C.c_size_t()
+    assert lib.adn_linear_workspace_bytes(100, 64, 32, _lib.ADN_BF16, nb) == 0 and nb.value >= 64 * 32 * 2
+    assert lib.adn_linear_workspace_bytes(0, 64, 32, _lib.ADN_BF16, nb) != 0
+    thr = (C.c_int32 * 4)(20, 30, 35, 40)
+    assert lib.adn_eval_batch(one, one, 4000, 20, 16, thr, 4, 90.0, one, one, None) != 0      # batch * seq_len > 65535
+
+
+def test_block_modules_mirror_reference_state_dict():
+    """Block / FeedForward / RMSNorm / StandardAttention: reference key names, shapes and registration order; same-seed
+    construction consumes the RNG stream like the reference classes (only checked where the reference is importable)."""
+    import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("reference not mounted")
+    from adnm_unet_b200 import refhost
+    for dim, out_dim in ((32, 32), (64, 128)):
+        a = refhost.build_block(dim, out_dim, dropin=False, seed=11).state_dict()
+        b = refhost.build_block(dim, out_dim, dropin=True, seed=11).state_dict()
+        assert list(a) == list(b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    import adnm_unet_b200 as A
+    ref = ref_loader.load_reference()
+    torch.manual_seed(5)
+    ra = ref.ADNssd.StandardAttention(64, heads=16, dim_head=4, dropout=0.).state_dict()
+    torch.manual_seed(5)
+    rb = A.StandardAttention(64, heads=16, dim_head=4, dropout=0.).state_dict()
+    assert list(ra) == list(rb) and all(torch.equal(ra[k], rb[k]) for k in ra)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        A.RMSNorm(16)(torch.zeros(2, 3, 16))
