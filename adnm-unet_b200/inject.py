@@ -25,5 +25,8 @@ def install_into_reference(adnmunet_module="models.ADNMUNet", untils_module="mod
         m = importlib.import_module(adnmunet_module)
         from adnm_unet_b200.attention import StandardAttention
         m.Block, m.RMSNorm, m.StandardAttention = Block, RMSNorm, StandardAttention
-        done += [adnmunet_module + ".Block", adnmunet_module + ".RMSNorm", adnmunet_module + ".StandardAttention"]
+        from adnm_unet_b200.block import FeedForward
+        importlib.import_module(untils_module).FeedForward = FeedForward      # the FeedForwards of the EncoderToDecoder bridges
+        done += [adnmunet_module + ".Block", adnmunet_module + ".RMSNorm", adnmunet_module + ".StandardAttention",
+                 untils_module + ".FeedForward"]
     return done

@@ -180,6 +180,7 @@ def load_reference():
     ns.ref_WTConv2d = ns.WTConv2d.WTConv2d
     ns.ref_Block, ns.ref_RMSNorm = ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm
     ns.ref_StandardAttention = ns.ADNssd.StandardAttention
+    ns.ref_FeedForward = ns.model_untils.FeedForward
     _patch_decoder_size(ns.ADNMUNet)
     _NS = ns
     return ns
@@ -206,7 +207,8 @@ def _bound(ns, dropin, mixer=True, wtconv=True, block=True):
     """Rebind (or restore) the construction-time globals for the duration of a model build: the mixer and WTConv2d classes
      and, with `block`, the `Block` / `RMSNorm` names `create_block` resolves (models/ADNMUNet.py:277-291)
     and the `StandardAttention` name `Attention` resolves (models/ADNMUNet.py:181)."""
-    old = (ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d, ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm, ns.ADNMUNet.StandardAttention)
+    old = (ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d, ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm, ns.ADNMUNet.StandardAttention,
+           ns.model_untils.FeedForward)
     if dropin:
         from adnm_unet_b200.mixer import Mamba2
         from adnm_unet_b200.wtconv import WTConv2d
@@ -218,14 +220,18 @@ def _bound(ns, dropin, mixer=True, wtconv=True, block=True):
             ns.model_untils.WTConv2d = WTConv2d
         if block:
             from adnm_unet_b200.attention import StandardAttention
+            from adnm_unet_b200.block import FeedForward
             ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm, ns.ADNMUNet.StandardAttention = Block, RMSNorm, StandardAttention
+            ns.model_untils.FeedForward = FeedForward      # the seven FeedForwards of the EncoderToDecoder bridges (model_untils.py:738)
     else:
         ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d = ns.ref_Mamba2, ns.ref_WTConv2d
         ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm, ns.ADNMUNet.StandardAttention = ns.ref_Block, ns.ref_RMSNorm, ns.ref_StandardAttention
+        ns.model_untils.FeedForward = ns.ref_FeedForward
     try:
         yield
     finally:
-        ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d, ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm, ns.ADNMUNet.StandardAttention = old
+        (ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d, ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm, ns.ADNMUNet.StandardAttention,
+         ns.model_untils.FeedForward) = old
 
 
 def build_adnm_unet(img_size=256, dropin=True, input_frames=5, output_frames=20, seed=0, mixer=True, wtconv=True, block=True):
