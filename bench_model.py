@@ -29,6 +29,15 @@ TRAIN_BYTES_PER_SAMPLE = {128: 445e6, 256: 1.78e9}
 TRAIN_FLOP_PER_SAMPLE = {128: 46.4e9, 256: 188.1e9}
 
 
+def _host_note(variant):
+    if variant != "dropin":
+        return "the unmodified reference network (baseline/_ref), eager PyTorch"
+    dead = os.environ.get("ADNM_KEEP_DEAD_BRIDGES", "0") != "1"
+    return ("unmodified reference network with Mamba2 / WTConv2d / Block / RMSNorm / FeedForward / StandardAttention bound to the "
+            "sm_100a modules" + ("; the four EncoderToDecoder bridges whose outputs never reach the network output (e2ds[3..6]) "
+                                 "are skipped - bit-identical outputs and gradients, refhost.prune_dead_bridges" if dead else ""))
+
+
 def _dist_env():
     return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -103,6 +112,7 @@ def train_bench(batch=32, img=128, steps=10, warmup=3, variant="dropin", bf16=Tr
         "steps": steps, "warmup": max(warmup, 3), "variant": variant, "dtype": "bf16 autocast, fp32 master weights" if bf16 else "f32",
         "config": {"workload": f"ADNM-UNet training step (BASELINE configs[2]): B={batch}/GPU, 5->20 frames at {img}x{img}, "
                                "enRainfallLoss, clip 0.025, AdamW", "global_batch": batch * world, "parallelism": f"dp{world}",
+                   "host": _host_note(variant),
                    "grad_allreduce": f"{len(trainer.buckets)} fp32 buckets ({trainer.n_live_elements()} live elements of "
                                      f"{sum(p.numel() for p in model.parameters())}), NCCL sum overlapped with backward" if world > 1 else "none (1 GPU)"},
         "live_param_tensors": len(trainer.live), "final_loss": final_loss, "grad_norm": float(trainer.grad_norm()),
@@ -171,7 +181,8 @@ def infer_bench(batch=64, img=256, steps=5, warmup=2, variant="dropin", bf16=Tru
     return {"metric": "adnm_unet_infer_seq_per_s", "value": batch * steps / (ms * 1e-3), "unit": "seq/s", "ms_per_step": ms / steps,
             "variant": variant, "dtype": "bf16 autocast" if bf16 else "f32",
             "config": {"workload": f"ADNM-UNet inference (BASELINE configs[3], validate.py:92-118): B={batch}, 5->20 frames at {img}x{img}, "
-                                   "eval + no_grad forward + on-device SimplifiedEvaluator (threshold counts + RMSE)"},
+                                   "eval + no_grad forward + on-device SimplifiedEvaluator (threshold counts + RMSE)",
+                       "host": _host_note(variant)},
             "counts_table": table.cpu().tolist(), "csi": csi, "hss": hss, "rmse": res["RMSE"], "far": res["FAR"],
             "evaluator": {"device_ms_per_batch": ms_eval, "device_samples_per_s": batch / (ms_eval * 1e-3),
                           "eval_baseline": {"kind": "reference loops (float2int + _cal_frame over batch x frame x threshold) on the host",

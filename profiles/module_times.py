@@ -16,10 +16,13 @@ def main():
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
     depth = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     variant = sys.argv[4] if len(sys.argv) > 4 else "dropin"
+    infer = len(sys.argv) > 5 and sys.argv[5] == "infer"      # eval + no_grad forward only (BASELINE configs[3])
     dev = torch.device("cuda", 0)
     model = refhost.build_adnm_unet(img, dropin=(variant == "dropin"), seed=0).to(dev)
     loss_fn = refhost.reference_loss()
     d = torch.rand(B, 25, 1, img, img).to(dev)
+    if infer:
+        model.eval()
     interesting = ("Block", "Mamba2", "FeedForward", "WTConv2d", "WTConvLayer", "Attention", "OutProj", "PatchEmbed", "WTLayer",
                    "EncoderToDecoder", "RMSNorm", "StandaloneRMSNorm")
     mods = {n: m for n, m in model.named_modules() if n and (n.count(".") < depth or type(m).__name__ in interesting)}
@@ -35,10 +38,15 @@ def main():
     for n, m in mods.items():
         m.register_forward_pre_hook(rec(n, "f0"))
         m.register_forward_hook(rec(n, "f1"))
-        m.register_full_backward_pre_hook(rec(n, "b0"))
-        m.register_full_backward_hook(rec(n, "b1"))
+        if not infer:
+            m.register_full_backward_pre_hook(rec(n, "b0"))
+            m.register_full_backward_hook(rec(n, "b1"))
 
     def step():
+        if infer:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                model(d[:, :5])
+            return
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = model(d[:, :5])
         loss = loss_fn(out.float(), d[:, 5:])

@@ -128,3 +128,25 @@ def test_grad_allreducer_keeps_aliased_grads():
         p.grad.add_(1.0)          # accumulate into the views (set_to_none=False style)
     red()
     assert all(bool((p.grad == 2).all()) for p in ps)
+
+
+def test_dead_bridge_pruning_is_bit_identical_on_cpu():
+    """refhost.prune_dead_bridges: e2ds[3..6] never reach the output (models/ADNMUNet.py:603-630, model_untils.py:407-408);
+    skipping them leaves output, every gradient and the set of grad-less parameters bit-identical (reference modules, CPU)."""
+    import torch
+    from adnm_unet_b200 import refhost
+    if not refhost.reference_available():
+        import pytest
+        pytest.skip("reference sources not available")
+    a = refhost.build_adnm_unet(128, dropin=False, seed=0)
+    b = refhost.build_adnm_unet(128, dropin=False, seed=0, prune_dead=True)
+    assert list(a.state_dict()) == list(b.state_dict())
+    x = torch.rand(1, 5, 1, 128, 128, generator=torch.Generator().manual_seed(3))
+    with refhost.cuda_to_is_noop():
+        ya, yb = a(x), b(x)
+        ya.square().sum().backward()
+        yb.square().sum().backward()
+    assert torch.equal(ya, yb)
+    ga, gb = ({k: p.grad for k, p in m.named_parameters()} for m in (a, b))
+    assert all((ga[k] is None) == (gb[k] is None) for k in ga)
+    assert all(torch.equal(ga[k], gb[k]) for k in ga if ga[k] is not None)
