@@ -41,6 +41,10 @@ class AdnFfnWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in FFN_FIELDS]
 
 
+class AdnConvShape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "H", "W", "Cin", "Cout", "dtype")]
+
+
 class WtShape(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "C", "H", "W", "k", "levels", "has_bias", "dtype")]
 
@@ -82,6 +86,18 @@ EXPORTS = {
     "adn_linear_workspace_bytes": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "adn_linear_forward": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "adn_linear_backward": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "adn_conv3x3_path": (C.c_int, [C.POINTER(AdnConvShape)]),
+    "adn_conv3x3_workspace_bytes": (C.c_int, [C.POINTER(AdnConvShape), C.POINTER(C.c_size_t)]),
+    "adn_conv3x3_forward": (C.c_int, [C.POINTER(AdnConvShape)] + [C.c_void_p] * 7),
+    "adn_conv3x3_backward": (C.c_int, [C.POINTER(AdnConvShape)] + [C.c_void_p] * 10),
+    "adn_nchw_pack_forward": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "adn_nchw_pack_backward": (C.c_int, [C.c_void_p] * 10 + [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "adn_plane_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_int32, C.c_void_p]),
+    "adn_plane_mix_forward": (C.c_int, [C.c_void_p] * 9 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "adn_plane_mix_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "adn_plane_mix_backward": (C.c_int, [C.c_void_p] * 14 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "adn_act_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "adn_act_backward": (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "adn_sdpa_forward": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_float, C.c_int32, C.c_void_p]),
     "adn_sdpa_backward": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_float, C.c_int32, C.c_void_p]),
     "adn_last_error": (C.c_char_p, []),

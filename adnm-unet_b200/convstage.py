@@ -1,0 +1,471 @@
+"""Drop-ins for the full-resolution conv stages of the reference: `WTLayer` (models/model_untils.py:358-426),
+`PatchEmbed` (:226-314) and `OutProj` (:799-892), with their `WTConvLayer` (:96-116), `Conv2dLayer` (:71-93) and `Mlp` (:52-68)
+containers.  Same constructors, sub-module / parameter names, shapes and registration order (a reference state_dict loads
+strictly; a same-seed construction consumes the RNG stream identically), same `forward` signatures and return layouts.
+
+The forward keeps every activation token-major (B, L, C) = channels-last except the planes that enter / leave the native
+WTConv2d, and runs every stage in the sm_100a library through the C ABI (include/adnb200.h):
+    (B, L, C) -> planes, gama1 / gama2 skip concat      adn_nchw_pack_forward / _backward
+    WTConv2d                                            wtconv_forward / _backward         (adnm_unet_b200.wtconv)
+    InstanceNorm2d * scale + shift [GELU], alpha / beta shortcut mix, planes -> (B, L, C)
+                                                        adn_plane_stats + adn_plane_mix_forward / _backward
+    Mlp fc1 / fc2, the 1 x 1 conv of OutProj            adn_linear_forward / _backward      (tcgen05 GEMM)
+    dense 3 x 3 conv (+ bias, layer-scale gamma folded into the weights)
+                                                        adn_conv3x3_forward / _backward     (tcgen05 implicit GEMM)
+    GELU / Swish                                        adn_act_forward / _backward
+PyTorch ops left: OutProj's `alpha1 * x + alpha2 * residual` on the 20-channel frame tensor (models/model_untils.py:887-889).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from adnm_unet_b200 import _lib
+from adnm_unet_b200.block import Swish, linear_tokens
+from adnm_unet_b200.wtconv import WTConv2d
+
+ACT_NONE, ACT_GELU, ACT_SWISH = 0, 1, 2
+IN_EPS = 1e-5          # nn.InstanceNorm2d default
+
+
+def _f32(p):
+    return None if p is None else (p if p.dtype == torch.float32 and p.is_contiguous() else p.detach().float().contiguous())
+
+
+def _autocast(x):
+    return x.to(torch.get_autocast_dtype("cuda")) if torch.is_autocast_enabled("cuda") else x
+
+
+def _scalar_grad(flat, i, like, need):
+    return flat[i].reshape(like.shape).to(like.dtype) if need else None
+
+
+# ---------------------------------------------------------------------------------------------- layout: tokens -> planes
+class _PackFunction(torch.autograd.Function):
+    """(B, L, C1) [+ (B, L, C2)] -> (B, C1 + C2, H, W): g1 * x | g2 * res, concatenated over channels."""
+
+    @staticmethod
+    def forward(ctx, x, res, g1, g2, H, W):
+        _lib.require_cuda(x, "x")
+        lib = _lib.load()
+        x = x.contiguous()
+        B, L, C1 = x.shape
+        if L != H * W:
+            raise RuntimeError(f"pack: L={L} != H*W={H * W}")
+        C2 = 0
+        if res is not None:
+            res = res.to(x.dtype).contiguous()
+            C2 = res.shape[-1]
+        g1f, g2f = _f32(g1), _f32(g2)
+        out = torch.empty(B, C1 + C2, H, W, dtype=x.dtype, device=x.device)
+        with _lib.on_device(x.device):
+            _lib.check(lib.adn_nchw_pack_forward(_lib.ptr(x), _lib.ptr(res), _lib.ptr(g1f), _lib.ptr(g2f), _lib.ptr(out), B, L, C1, C2,
+                                                 _lib.dtype_code(x), _lib.stream_ptr(x.device)), "adn_nchw_pack_forward")
+        ctx.save_for_backward(x, res, g1f, g2f)
+        ctx.likes = (g1, g2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        x, res, g1f, g2f = ctx.saved_tensors
+        g1, g2 = ctx.likes
+        B, L, C1 = x.shape
+        C2 = 0 if res is None else res.shape[-1]
+        ni = ctx.needs_input_grad
+        dout = dout.to(x.dtype).contiguous()
+        dx = torch.empty_like(x) if ni[0] else None
+        dres = torch.empty_like(res) if res is not None and ni[1] else None
+        flat = torch.empty(2, dtype=torch.float32, device=x.device)
+        ws = _lib.scratch(64, x.device)
+        want1, want2 = g1 is not None and ni[2], g2 is not None and ni[3]
+        with _lib.on_device(x.device):
+            _lib.check(lib.adn_nchw_pack_backward(_lib.ptr(x), _lib.ptr(res), _lib.ptr(g1f), _lib.ptr(g2f), _lib.ptr(dout), _lib.ptr(dx), _lib.ptr(dres),
+                                                  _lib.ptr(flat[0:1]) if want1 else None, _lib.ptr(flat[1:2]) if want2 else None, _lib.ptr(ws),
+                                                  B, L, C1, C2, _lib.dtype_code(x), _lib.stream_ptr(x.device)), "adn_nchw_pack_backward")
+        return (dx, dres, _scalar_grad(flat, 0, g1, want1) if want1 else None, _scalar_grad(flat, 1, g2, want2) if want2 else None, None, None)
+
+
+def pack_planes(x, H, W, res=None, g1=None, g2=None):
+    return _PackFunction.apply(x, res, g1, g2, int(H), int(W))
+
+
+# ---------------------------------------------------------------------------------------------- norm + shortcut mix: planes -> tokens
+class _MixFunction(torch.autograd.Function):
+    """out (B, L, C) = gamma * (alpha * act(u) + beta * xs),  u = scale * InstanceNorm(y) + shift (norm) or y."""
+
+    @staticmethod
+    def forward(ctx, y, xs, scale, shift, alpha, beta, gamma, norm, act):
+        _lib.require_cuda(y, "y")
+        lib = _lib.load()
+        y = y.contiguous()
+        xs = xs.to(y.dtype).contiguous()
+        B, C, H, W = y.shape
+        HW = H * W
+        code = _lib.dtype_code(y)
+        p = [_f32(t) for t in (scale, shift, alpha, beta, gamma)]
+        stats = None
+        out = torch.empty(B, HW, C, dtype=y.dtype, device=y.device)
+        with _lib.on_device(y.device):
+            st = _lib.stream_ptr(y.device)
+            if norm:
+                stats = torch.empty(B * C, 2, dtype=torch.float32, device=y.device)
+                _lib.check(lib.adn_plane_stats(_lib.ptr(y), _lib.ptr(stats), B * C, HW, IN_EPS, code, st), "adn_plane_stats")
+            _lib.check(lib.adn_plane_mix_forward(_lib.ptr(y), _lib.ptr(xs), _lib.ptr(stats), _lib.ptr(p[0]), _lib.ptr(p[1]), _lib.ptr(p[2]), _lib.ptr(p[3]),
+                                                 _lib.ptr(p[4]), _lib.ptr(out), B, C, HW, act, code, st), "adn_plane_mix_forward")
+        ctx.save_for_backward(y, xs, stats, *p)
+        ctx.cfg = (act, (scale, shift, alpha, beta, gamma))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        y, xs, stats, *p = ctx.saved_tensors
+        act, likes = ctx.cfg
+        B, C, H, W = y.shape
+        HW = H * W
+        ni = ctx.needs_input_grad
+        dout = dout.to(y.dtype).contiguous()
+        dy = torch.empty_like(y) if ni[0] else None
+        dxs = torch.empty_like(xs) if ni[1] else None
+        flat = torch.empty(4 + C, dtype=torch.float32, device=y.device)
+        nb = _lib.C.c_size_t()
+        _lib.check(lib.adn_plane_mix_workspace_bytes(B, C, nb), "adn_plane_mix_workspace_bytes")
+        ws = _lib.scratch(nb.value, y.device)
+        with _lib.on_device(y.device):
+            _lib.check(lib.adn_plane_mix_backward(_lib.ptr(y), _lib.ptr(xs), _lib.ptr(stats), _lib.ptr(p[0]), _lib.ptr(p[1]), _lib.ptr(p[2]), _lib.ptr(p[3]),
+                                                  _lib.ptr(p[4]), _lib.ptr(dout), _lib.ptr(dy), _lib.ptr(dxs), _lib.ptr(flat[:4]),
+                                                  _lib.ptr(flat[4:]) if p[4] is not None else None, _lib.ptr(ws), B, C, HW, act,
+                                                  _lib.dtype_code(y), _lib.stream_ptr(y.device)), "adn_plane_mix_backward")
+        scale, shift, alpha, beta, gamma = likes
+        return (dy, dxs,
+                _scalar_grad(flat, 0, scale, True) if scale is not None and ni[2] else None,
+                _scalar_grad(flat, 1, shift, True) if shift is not None and ni[3] else None,
+                _scalar_grad(flat, 2, alpha, True) if ni[4] else None,
+                _scalar_grad(flat, 3, beta, True) if ni[5] else None,
+                flat[4:].reshape(gamma.shape).to(gamma.dtype) if gamma is not None and ni[6] else None, None, None)
+
+
+def plane_mix(y, xs, alpha, beta, scale=None, shift=None, gamma=None, norm=False, act=ACT_NONE):
+    return _MixFunction.apply(y, xs, scale, shift, alpha, beta, gamma, bool(norm), int(act))
+
+
+# ---------------------------------------------------------------------------------------------- dense 3 x 3 convolution, channels-last
+_CONV_CACHE = {}
+
+
+def _conv_info(B, H, W, Cin, Cout, code):
+    key = (B, H, W, Cin, Cout, code)
+    hit = _CONV_CACHE.get(key)
+    if hit is None:
+        shape = _lib.AdnConvShape(B=B, H=H, W=W, Cin=Cin, Cout=Cout, dtype=code)
+        nb = _lib.C.c_size_t()
+        _lib.check(_lib.load().adn_conv3x3_workspace_bytes(shape, nb), "adn_conv3x3_workspace_bytes")
+        hit = _CONV_CACHE[key] = (shape, nb.value)
+    return hit
+
+
+class _Conv3x3Function(torch.autograd.Function):
+    """x (B, L, Cin) token-major, weight (Cout, Cin, 3, 3), bias (Cout) | None, gamma (Cin) | None -> (B, L, Cout)."""
+
+    @staticmethod
+    def forward(ctx, x, H, W, weight, bias, gamma):
+        _lib.require_cuda(x, "x")
+        lib = _lib.load()
+        x = x.contiguous()
+        B, L, Cin = x.shape
+        Cout = weight.shape[0]
+        if L != H * W or tuple(weight.shape[1:]) != (Cin, 3, 3):
+            raise RuntimeError(f"conv3x3: x {tuple(x.shape)} / weight {tuple(weight.shape)} / grid {H}x{W} do not match")
+        shape, nb = _conv_info(B, H, W, Cin, Cout, _lib.dtype_code(x))
+        w, b, g = _f32(weight), _f32(bias), _f32(gamma)
+        y = torch.empty(B, L, Cout, dtype=x.dtype, device=x.device)
+        ws = _lib.scratch(nb, x.device)
+        with _lib.on_device(x.device):
+            _lib.check(lib.adn_conv3x3_forward(shape, _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(g), _lib.ptr(y), _lib.ptr(ws),
+                                               _lib.stream_ptr(x.device)), "adn_conv3x3_forward")
+        ctx.save_for_backward(x, w, g)
+        ctx.cfg = (shape, nb, (weight, bias, gamma))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, w, g = ctx.saved_tensors
+        shape, nb, (weight, bias, gamma) = ctx.cfg
+        ni = ctx.needs_input_grad
+        Cout, Cin = w.shape[0], w.shape[1]
+        dy = dy.to(x.dtype).contiguous()
+        dx = torch.empty_like(x) if ni[0] else None
+        flat = torch.empty(w.numel() + Cout + Cin, dtype=torch.float32, device=x.device)
+        dw, db, dg = flat[:w.numel()], flat[w.numel():w.numel() + Cout], flat[w.numel() + Cout:]
+        ws = _lib.scratch(nb, x.device)
+        with _lib.on_device(x.device):
+            _lib.check(lib.adn_conv3x3_backward(shape, _lib.ptr(x), _lib.ptr(w), _lib.ptr(g), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(dw),
+                                                _lib.ptr(db) if bias is not None else None, _lib.ptr(dg) if g is not None else None, _lib.ptr(ws),
+                                                _lib.stream_ptr(x.device)), "adn_conv3x3_backward")
+        return (dx, None, None, dw.view(w.shape).to(weight.dtype) if ni[3] else None,
+                db.to(bias.dtype) if bias is not None and ni[4] else None,
+                dg.reshape(gamma.shape).to(gamma.dtype) if gamma is not None and ni[5] else None)
+
+
+def conv3x3_tokens(x, H, W, weight, bias=None, gamma=None):
+    return _Conv3x3Function.apply(x, int(H), int(W), weight, bias, gamma)
+
+
+# ---------------------------------------------------------------------------------------------- activations
+class _ActFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kind, beta):
+        _lib.require_cuda(x, "x")
+        lib = _lib.load()
+        x = x.contiguous()
+        bf = _f32(beta)
+        y = torch.empty_like(x)
+        with _lib.on_device(x.device):
+            _lib.check(lib.adn_act_forward(_lib.ptr(x), _lib.ptr(y), x.numel(), kind, _lib.ptr(bf), _lib.dtype_code(x), _lib.stream_ptr(x.device)),
+                       "adn_act_forward")
+        ctx.save_for_backward(x, bf)
+        ctx.cfg = (kind, beta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, bf = ctx.saved_tensors
+        kind, beta = ctx.cfg
+        dy = dy.to(x.dtype).contiguous()
+        dx = torch.empty_like(x)
+        flat = torch.empty(1, dtype=torch.float32, device=x.device)
+        ws = _lib.scratch(64, x.device)
+        want = beta is not None and ctx.needs_input_grad[2]
+        with _lib.on_device(x.device):
+            _lib.check(lib.adn_act_backward(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dx), x.numel(), kind, _lib.ptr(bf), _lib.ptr(flat) if want else None,
+                                            _lib.ptr(ws), _lib.dtype_code(x), _lib.stream_ptr(x.device)), "adn_act_backward")
+        return dx if ctx.needs_input_grad[0] else None, None, _scalar_grad(flat, 0, beta, want) if want else None
+
+
+def gelu_tokens(x):
+    return _ActFunction.apply(x, ACT_GELU, None)
+
+
+def swish_tokens(x, beta):
+    return _ActFunction.apply(x, ACT_SWISH, beta)
+
+
+# ---------------------------------------------------------------------------------------------- parameter containers
+class Mlp(nn.Module):
+    """models/model_untils.py:52-68: fc1 -> GELU -> fc2 (act2 is declared and never applied)."""
+
+    def __init__(self, in_features, out_features=None, hidden_features=None, act_func=nn.GELU, drop=0., bias=True):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features * 2
+        if act_func is not nn.GELU or drop != 0.:
+            raise NotImplementedError("adnb200 Mlp covers GELU without dropout (the configuration ADNM-UNet instantiates)")
+        self.fc1 = nn.Linear(in_features, hidden_features, bias=bias)
+        self.act1 = act_func()
+        self.fc2 = nn.Linear(hidden_features, out_features, bias=bias)
+        self.drop = nn.Dropout(drop)
+        self.act2 = act_func()
+
+    def forward(self, x):
+        x = _autocast(x)
+        return linear_tokens(gelu_tokens(linear_tokens(x, self.fc1.weight, self.fc1.bias)), self.fc2.weight, self.fc2.bias)
+
+
+def _act_kind(act_func):
+    if act_func is None:
+        return None, ACT_NONE
+    if act_func is nn.GELU:
+        return nn.GELU(), ACT_GELU
+    if act_func is Swish or getattr(act_func, "__name__", "") == "Swish":
+        return act_func(), ACT_SWISH
+    raise NotImplementedError(f"adnb200 conv stages cover GELU and Swish activations, not {act_func}")
+
+
+class Conv2dLayer(nn.Module):
+    """models/model_untils.py:71-93 as ADNM-UNet's conv stages instantiate it: a dense 3 x 3 (or 1 x 1) nn.Conv2d, stride 1,
+    'same' padding, no norm, optional activation.  `forward_tokens` takes / returns (B, L, C)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1), dilation=(1, 1), groups=1, bias=True,
+                 dropout=0, norm=None, act_func=None):
+        super().__init__()
+        if dropout > 0 or norm is not None or groups != 1:
+            raise NotImplementedError("adnb200 Conv2dLayer: no dropout / norm / groups (never used by WTLayer, PatchEmbed, OutProj)")
+        self.dropout = None
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias)
+        k, pd = self.conv.kernel_size, self.conv.padding
+        if self.conv.stride != (1, 1) or self.conv.dilation != (1, 1) or (k, pd) not in (((3, 3), (1, 1)), ((1, 1), (0, 0))):
+            raise NotImplementedError("adnb200 Conv2dLayer: 3x3 / padding 1 or 1x1 / padding 0, stride 1")
+        self.norm = None
+        self.act, self.act_kind = _act_kind(act_func)
+
+    def forward_tokens(self, x, H, W, gamma=None):
+        if self.conv.kernel_size == (3, 3):
+            y = conv3x3_tokens(x, H, W, self.conv.weight, self.conv.bias, gamma)
+        else:
+            if gamma is not None:
+                raise NotImplementedError("gamma folding is implemented for the 3x3 conv")
+            y = linear_tokens(x, self.conv.weight.view(self.conv.out_channels, self.conv.in_channels), self.conv.bias)
+        if self.act_kind == ACT_GELU:
+            y = gelu_tokens(y)
+        elif self.act_kind == ACT_SWISH:
+            y = swish_tokens(y, self.act.beta)
+        return y
+
+    def forward(self, x):
+        b, c, h, w = x.shape
+        x = _autocast(x)
+        y = self.forward_tokens(x.permute(0, 2, 3, 1).reshape(b, h * w, c), h, w)
+        return pack_planes(y, h, w)
+
+
+class WTConvLayer(nn.Module):
+    """models/model_untils.py:96-116: WTConv2d, then `scale * norm(x) + shift` (InstanceNorm2d) and / or an activation.
+    The norm / activation are applied by the caller's plane_mix (they fuse with the shortcut mix that always follows)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, wt_levels=2, bias=True, dropout=0, norm=None, act_func=None):
+        super().__init__()
+        if dropout > 0:
+            raise NotImplementedError("dropout is 0 everywhere in ADNM-UNet")
+        if norm is not None and not (isinstance(norm, nn.InstanceNorm2d) and not norm.affine and not norm.track_running_stats):
+            raise NotImplementedError("adnb200 WTConvLayer fuses nn.InstanceNorm2d (InstanceNorm=True, the create_ADNMUNet configuration)")
+        self.dropout = None
+        self.conv = WTConv2d(in_channels, out_channels, kernel_size, stride, bias, wt_levels=wt_levels)
+        self.norm = norm
+        self.act, self.act_kind = _act_kind(act_func)
+        if self.act_kind == ACT_SWISH:
+            raise NotImplementedError("WTConvLayer activations: None or GELU")
+        if norm:
+            self.scale = nn.Parameter(torch.tensor(1.))
+            self.shift = nn.Parameter(torch.tensor(0.))
+
+    def mix(self, xs, alpha, beta, gamma=None):
+        """tokens (B, L, C) = gamma * (alpha * self(xs) + beta * xs) for planes xs (B, C, H, W)."""
+        y = self.conv(xs)
+        if self.norm is not None:
+            return plane_mix(y, xs, alpha, beta, self.scale, self.shift, gamma, norm=True, act=self.act_kind)
+        return plane_mix(y, xs, alpha, beta, None, None, gamma, norm=False, act=self.act_kind)
+
+    def forward(self, x):
+        one = torch.ones((), dtype=torch.float32, device=x.device)
+        b, c, h, w = x.shape
+        x = _autocast(x).contiguous()
+        return pack_planes(self.mix(x, one, torch.zeros_like(one)), h, w)
+
+
+def _norm2d(dim, InstanceNorm, what):
+    if not InstanceNorm:
+        raise NotImplementedError(f"adnb200 {what}: InstanceNorm=True (the create_ADNMUNet configuration); GroupNorm is not built")
+    return nn.InstanceNorm2d(dim)
+
+
+# ---------------------------------------------------------------------------------------------- the three stages
+class WTLayer(nn.Module):
+    """models/model_untils.py:358-426."""
+
+    def __init__(self, this_dim=128, next_dim=256, kernel=5, bias=True, wt_levels=2, ls_init_value=1, act=nn.GELU, if_res=False, InstanceNorm=True):
+        super().__init__()
+        self.next_dim = next_dim
+        self.wtconv = WTConvLayer(in_channels=this_dim, out_channels=this_dim, kernel_size=kernel, stride=1, bias=bias, wt_levels=wt_levels,
+                                  norm=_norm2d(this_dim, InstanceNorm, "WTLayer"))
+        self.conv = Conv2dLayer(in_channels=this_dim, out_channels=next_dim, kernel_size=3, padding=1, stride=1, bias=True, act_func=nn.GELU)
+        self.mlp = Mlp(this_dim)
+        self.gamma = nn.Parameter(ls_init_value * torch.ones(this_dim)) if ls_init_value is not None else None
+        self.alpha = nn.Parameter(torch.tensor(1, dtype=torch.float))
+        self.beta = nn.Parameter(torch.tensor(1, dtype=torch.float))
+        self.gama1 = nn.Parameter(torch.tensor(1, dtype=torch.float))
+        self.gama2 = nn.Parameter(torch.tensor(1, dtype=torch.float))
+        self.gama3 = nn.Parameter(torch.tensor(1, dtype=torch.float))
+        self.gama4 = nn.Parameter(torch.tensor(1, dtype=torch.float))
+
+    def forward(self, x, residual=None, features=None):
+        x = _autocast(x)
+        b, l, _ = x.shape
+        h = w = int(math.sqrt(l))
+        if residual is not None:
+            # cat(gama1 x, gama2 residual); the reference also builds a cat of `features` here and discards it (:407-408)
+            xs = pack_planes(x, h, w, _autocast(residual), self.gama1, self.gama2)
+        else:
+            if features is not None:
+                x = x + self.gama3 * features
+            xs = pack_planes(x, h, w)
+        t = self.wtconv.mix(xs, self.alpha, self.beta)          # alpha * (scale * IN(wtconv(x)) + shift) + beta * shortcut, token-major
+        t = self.mlp(t)
+        return self.conv.forward_tokens(t, h, w, gamma=self.gamma)      # x.mul(gamma) folded into the conv weights; conv + bias, GELU
+
+
+class PatchEmbed(nn.Module):
+    """models/model_untils.py:226-314."""
+
+    def __init__(self, img_size=256, patch_size=2, in_channels=3, embed_dim=256, kernel=6, num_frames=5, target_frames=3, wt_levels=2,
+                 ls_init_value=1, act=nn.GELU, InstanceNorm=True):
+        super().__init__()
+        img_size = tuple(img_size) if isinstance(img_size, (tuple, list)) else (img_size, img_size)
+        patch_size = tuple(patch_size) if isinstance(patch_size, (tuple, list)) else (patch_size, patch_size)
+        self.patches_resolution = [img_size[0] // patch_size[0], img_size[1] // patch_size[1]]
+        self.img_size, self.patch_size = img_size, patch_size
+        self.num_patches = self.patches_resolution[0] * self.patches_resolution[1]
+        self.embed_dim, self.num_frames, self.target_frames = embed_dim, num_frames, target_frames
+        self.gamma = nn.Parameter(ls_init_value * torch.ones(embed_dim)) if ls_init_value is not None else None
+        self.conv1 = nn.Sequential(WTConvLayer(in_channels=in_channels, out_channels=in_channels, kernel_size=kernel, stride=1, bias=False,
+                                               wt_levels=wt_levels, act_func=nn.GELU))
+        self.conv2 = nn.Sequential(Conv2dLayer(in_channels=in_channels, out_channels=embed_dim, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1),
+                                               groups=1, bias=False, act_func=nn.GELU))
+        self.conv3 = nn.Sequential(WTConvLayer(in_channels=embed_dim, out_channels=embed_dim, kernel_size=kernel, stride=1, bias=False,
+                                               wt_levels=wt_levels, norm=_norm2d(embed_dim, InstanceNorm, "PatchEmbed")))
+        self.alpha1 = nn.Parameter(torch.tensor(1, dtype=torch.float))
+        self.beta1 = nn.Parameter(torch.tensor(1, dtype=torch.float))
+        self.alpha2 = nn.Parameter(torch.tensor(1, dtype=torch.float))
+        self.beta2 = nn.Parameter(torch.tensor(1, dtype=torch.float))
+
+    def forward(self, x):
+        b, l, d = x.shape
+        h = w = int(math.sqrt(l))
+        res = x.view(b, h, w, d).permute(0, 3, 1, 2)[:, -1, :, :]            # the last input frame, as the reference returns it
+        x = _autocast(x)
+        xt = x.transpose(1, 2)
+        # the Encoder hands over `frames.flatten(2).transpose(1, 2)` (models/ADNMUNet.py:438): a view of planes that already exist
+        xs = xt.reshape(b, d, h, w) if xt.is_contiguous() else pack_planes(x, h, w)
+        t = self.conv1[0].mix(xs, self.alpha1, self.beta1)                   # alpha1 GELU(wtconv(x)) + beta1 x
+        s = self.conv2[0].forward_tokens(t, h, w)                            # shortcut = GELU(conv(x)), token-major
+        out = self.conv3[0].mix(pack_planes(s, h, w), self.alpha2, self.beta2, self.gamma)
+        return out, res
+
+
+class OutProj(nn.Module):
+    """models/model_untils.py:799-892."""
+
+    def __init__(self, num_frames=3, embed_dim=256, img_size=[256, 256], act_func=Swish, wt_levels=2, ls_init_value=1, out_expand=2,
+                 InstanceNorm=True):
+        super().__init__()
+        self.img_size = img_size
+        self.embed_dim = embed_dim
+        self.activation = act_func
+        self.wtconv = WTConvLayer(in_channels=embed_dim, out_channels=embed_dim, kernel_size=5, stride=1, bias=False, wt_levels=3, act_func=nn.GELU,
+                                  norm=_norm2d(embed_dim, InstanceNorm, "OutProj"))
+        self.conv = nn.Sequential(
+            Conv2dLayer(in_channels=embed_dim, out_channels=embed_dim * out_expand, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1), bias=False,
+                        act_func=nn.GELU),
+            Conv2dLayer(in_channels=embed_dim * out_expand, out_channels=num_frames, kernel_size=(1, 1), stride=(1, 1), padding=(0, 0), bias=False,
+                        act_func=nn.GELU))
+        self.conv2 = Conv2dLayer(in_channels=num_frames, out_channels=num_frames, kernel_size=3, stride=1, bias=False, act_func=self.activation)
+        self.alpha1 = nn.Parameter(torch.tensor(1., dtype=torch.float))
+        self.alpha2 = nn.Parameter(torch.tensor(1., dtype=torch.float))
+        self.gamma = nn.Parameter(ls_init_value * torch.ones(embed_dim)) if ls_init_value is not None else None
+        self.alpha = nn.Parameter(torch.tensor(1., dtype=torch.float))
+        self.beta = nn.Parameter(torch.tensor(1., dtype=torch.float))
+
+    def forward(self, x, residual):
+        h, w = self.img_size[0], self.img_size[1]
+        x = _autocast(x)
+        b, l, d = x.shape
+        xs = pack_planes(x, h, w)
+        t = self.wtconv.mix(xs, self.alpha, self.beta)                       # alpha GELU(scale IN(wtconv(x)) + shift) + beta shortcut
+        t = self.conv[0].forward_tokens(t, h, w, gamma=self.gamma)           # x.mul(gamma) folded into the conv weights
+        t = self.conv[1].forward_tokens(t, h, w)
+        if residual is not None:
+            t = self.alpha1 * t + self.alpha2 * residual.reshape(b, l, 1).to(t.dtype)
+        t = self.conv2.forward_tokens(t, h, w)
+        return pack_planes(t, h, w)

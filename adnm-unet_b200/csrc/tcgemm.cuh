@@ -23,6 +23,12 @@
 // * Epilogue: TMEM -> registers (alpha, parity mask, optional SiLU'(aux) factor) -> 128-byte-swizzled staging slab in
 //   shared memory -> TMA store (bf16 / fp32) or TMA reduce-add (split-K), 32 rows x 128 bytes per instruction, clipped to
 //   the matrix by the hardware.  (Thread-per-row global stores cost 107 of 157 us on the in_proj shape.)
+// * Implicit-GEMM 3x3 convolution (`Conv`, dense convs of WTLayer / OutProj, models/model_untils.py:375-386,820-831): one
+//   operand is a channels-last image [B][H][W][C] read through a RANK-4 tensor map; a tile of 128 (or 64) consecutive tokens
+//   is a box of whole image rows, and tap (dy, dx) is the same box moved by (dx, dy) - rows / columns / samples that fall
+//   outside the image are zero-filled by the TMA unit, which IS the convolution's zero padding.  No im2col buffer exists.
+//     mode 1: A = image (tokens are M), K = 9 taps x cpad channels        forward and data gradient (flipped taps)
+//     mode 2: B = image (tokens are K), N = 9 taps x cpad channels        weight gradient (split-K over tokens)
 #pragma once
 #include "adn_common.cuh"
 #include "sm100_utils.cuh"
@@ -46,6 +52,13 @@ struct Seg {
   int K;
 };
 
+struct Conv {
+  int mode;          // 0: plain GEMM; 1: operand A is the image (K-major); 2: operand B is the image (MN-major)
+  int W, H;          // image size; L = W * H tokens per sample
+  int cpad;          // image channels rounded up to 64: tap t owns k (mode 1) / n (mode 2) range [t * cpad, (t + 1) * cpad)
+};
+static const Conv NOCONV = Conv{0, 0, 0, 0};
+
 struct Args {
   Seg seg[2];
   int nseg;
@@ -61,6 +74,7 @@ struct Args {
                                               // the gradient w.r.t. the conv output becomes the gradient w.r.t. its input)
   int a_bz[2], b_bz[2];    // 1: the operand of that segment has a batch dimension (else every batch reads the same matrix)
   const float* bias;       // optional fp32 vector [N] added after alpha (1x1 conv / Linear bias)
+  Conv conv;               // implicit-GEMM 3x3 convolution (mode 0: off)
   int dbg;                 // knock-outs for profiling (adn_set_option("gemm_dbg")): 1 no epilogue stores, 2 no operand loads, 4 no MMAs,
                            // 8 no proxy fence, 16 no epilogue math / staging, 32 no TMEM loads.  Measured (profiles/gemm_knockout.py,
                            // gpurun_out/r3g): the bare barrier skeleton costs ~0.45 us per k-tile commit whatever the ring depth (4 ... 8
@@ -82,6 +96,12 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// one box of a rank-4 tensor map (channels-last image: c, x, y, sample); out-of-range coordinates are zero-filled
+__device__ __forceinline__ void tma_load_4d(uint32_t sdst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(sdst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // Shared-memory matrix descriptors for the 128-byte swizzled tiles TMA writes (cute/atom/mma_traits_sm100.hpp,
 // make_umma_desc: canonical layouts in 16-byte units)
 //   K-major  Swizzle<3,4,3> o ((8,n),2):((8,SBO),1)        rows 128 B apart, 8-row groups SBO = 1024 B apart, LBO unused (1)
@@ -165,9 +185,22 @@ k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_c
             // split-K: a box may reach past this split's range into the next one's; harmless for K-major / MN-major alike
             // because splits are whole multiples of BK (k_per_split % BK == 0)
             const int za = batch * (second ? a.a_bz[1] : a.a_bz[0]), zb = batch * (second ? a.b_bz[1] : a.b_bz[0]);
-            if (!a.a_mn) tma_load_3d(sa, pa, k0, m0, za, &full[s]);
+            if (a.conv.mode == 1) {
+              // A tile = 128 consecutive tokens of the image starting at token m0, moved by this k-tile's tap
+              const int cpt = a.conv.cpad >> 6, tap = kt / cpt, c0 = (kt - tap * cpt) << 6;
+              const int L = a.conv.W * a.conv.H, b0 = m0 / L, r = m0 - b0 * L, y0 = r / a.conv.W, x0 = r - y0 * a.conv.W;
+              tma_load_4d(sa, pa, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0, &full[s]);
+            } else if (!a.a_mn) tma_load_3d(sa, pa, k0, m0, za, &full[s]);
             else { tma_load_3d(sa, pa, m0, k0, za, &full[s]); tma_load_3d(sa + 8192, pa, m0 + 64, k0, za, &full[s]); }
-            if (!a.b_mn) tma_load_3d(sb, pb, k0, n0, zb, &full[s]);
+            if (a.conv.mode == 2) {
+              // B tile = 64 consecutive tokens (the k range) x BN columns; every 64-column group belongs to one tap
+              const int L = a.conv.W * a.conv.H, b0 = k0 / L, r = k0 - b0 * L, y0 = r / a.conv.W, x0 = r - y0 * a.conv.W;
+              for (int q = 0; q < BN; q += 64) {
+                const int n = n0 + q, tap = n / a.conv.cpad;
+                if (tap < 9) tma_load_4d(sb + q * 128, pb, n - tap * a.conv.cpad, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0, &full[s]);
+                else tma_load_4d(sb + q * 128, pb, a.conv.cpad, 0, 0, 0, &full[s]);      // past the last tap: an all-zero box
+              }
+            } else if (!a.b_mn) tma_load_3d(sb, pb, k0, n0, zb, &full[s]);
             else
               for (int q = 0; q < BN; q += 64) tma_load_3d(sb + q * 128, pb, n0 + q, k0, zb, &full[s]);
           } else {
@@ -337,6 +370,40 @@ static int make_operand_map(CUtensorMap* map, const char* name, Op o, int extent
   return ADN_OK;
 }
 
+// Rank-4 bf16 tensor map of a channels-last image [B][H][W][C]: dims (C, W, H, B), box = (64 channels, bw, bh, bb) with
+// bw * bh * bb = tokens_per_box consecutive tokens (whole rows / whole samples), 128-byte swizzle, zero fill outside.
+struct Image {
+  const bf16* p; int B, H, W, C;
+};
+static int make_image_map(CUtensorMap* map, const char* name, Image im, int tokens_per_box) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  ADN_REQUIRE(enc != nullptr, ADN_ERR_CUDA, "tcgemm %s: cuTensorMapEncodeTiled is not available from this driver", name);
+  const int tpb = tokens_per_box;
+  ADN_REQUIRE(im.C % 8 == 0 && ((uintptr_t)im.p % 16) == 0, ADN_ERR_SHAPE, "tcgemm %s: image channels must be a multiple of 8 and the base 16-byte aligned", name);
+  ADN_REQUIRE(im.W >= tpb ? im.W % tpb == 0 : tpb % im.W == 0, ADN_ERR_SHAPE, "tcgemm %s: image width %d does not tile %d-token boxes", name, im.W, tpb);
+  const int bw = im.W < tpb ? im.W : tpb, rows = tpb / bw;
+  ADN_REQUIRE(im.H >= rows ? im.H % rows == 0 : rows % im.H == 0, ADN_ERR_SHAPE, "tcgemm %s: image height %d does not tile %d-row boxes", name, im.H, rows);
+  const int bh = im.H < rows ? im.H : rows, bb = rows / bh;
+  cuuint64_t dims[4] = {(cuuint64_t)im.C, (cuuint64_t)im.W, (cuuint64_t)im.H, (cuuint64_t)im.B};
+  cuuint64_t strides[3] = {(cuuint64_t)im.C * 2, (cuuint64_t)im.W * im.C * 2, (cuuint64_t)im.H * im.W * im.C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)im.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ADN_REQUIRE(r == CUDA_SUCCESS, ADN_ERR_CUDA, "tcgemm %s: cuTensorMapEncodeTiled (image) failed (%d) dims %d x %d x %d x %d box %d x %d x %d", name,
+              (int)r, im.C, im.W, im.H, im.B, bw, bh, bb);
+  return ADN_OK;
+}
+// can make_image_map() tile this image for both the 128-token (forward / data gradient) and 64-token (weight gradient) boxes?
+static inline bool image_tiles(int H, int W) {
+  for (int tpb = 64; tpb <= 128; tpb *= 2) {
+    if (!(W >= tpb ? W % tpb == 0 : tpb % W == 0)) return false;
+    const int rows = tpb / (W < tpb ? W : tpb);
+    if (!(H >= rows ? H % rows == 0 : rows % H == 0)) return false;
+  }
+  return true;
+}
+
 struct Aux {
   const bf16* p; long long ld, bs;
 };
@@ -344,7 +411,8 @@ static const Aux NOAUX = Aux{nullptr, 0, 0};
 
 // C = alpha * (A0 . B0 [+ A1 . B1]);  batches > 1: per-sample GEMMs;  splitk > 1: atomics into a ZEROED fp32 C.
 static int gemm(cudaStream_t st, const char* name, int M, int N, int K0, Op A0, Op B0, int K1, Op A1, Op B1, Out C,
-                int batches, int splitk, const float* alpha, int parity_mask, int* status, Aux aux = NOAUX, const float* bias = nullptr) {
+                int batches, int splitk, const float* alpha, int parity_mask, int* status, Aux aux = NOAUX, const float* bias = nullptr,
+                Conv conv = NOCONV, Image image = Image{nullptr, 0, 0, 0, 0}) {
   ADN_REQUIRE(M > 0 && N > 0 && K0 > 0 && batches > 0, ADN_ERR_SHAPE, "tcgemm %s: empty problem", name);
   ADN_REQUIRE(K1 == 0 || (A1.mn == A0.mn && B1.mn == B0.mn), ADN_ERR_SHAPE, "tcgemm %s: segments must share orientation", name);
   ADN_REQUIRE(splitk == 1 || (K1 == 0 && C.mode == C_ATOMIC_F32), ADN_ERR_SHAPE, "tcgemm %s: split-K needs one segment and an atomic fp32 output", name);
@@ -369,10 +437,17 @@ static int gemm(cudaStream_t st, const char* name, int M, int N, int K0, Op A0, 
   a.a_bz[0] = batches > 1 && A0.bs != 0; a.b_bz[0] = batches > 1 && B0.bs != 0;
   a.a_bz[1] = batches > 1 && A1.bs != 0; a.b_bz[1] = batches > 1 && B1.bs != 0;
   a.dbg = env().gemm_dbg;
+  a.conv = conv;
+  ADN_REQUIRE(conv.mode == 0 || (K1 == 0 && batches == 1 && conv.cpad % 64 == 0 && conv.cpad >= image.C), ADN_ERR_SHAPE,
+              "tcgemm %s: a convolution is one un-batched segment", name);
+  ADN_REQUIRE(conv.mode != 1 || (A0.mn == 0 && a.splitk == 1 && K0 == 9 * conv.cpad && (long long)image.B * image.H * image.W == M), ADN_ERR_SHAPE,
+              "tcgemm %s: inconsistent convolution (forward) extents", name);
+  ADN_REQUIRE(conv.mode != 2 || (B0.mn == 1 && N == 9 * conv.cpad && (long long)image.B * image.H * image.W == K0), ADN_ERR_SHAPE,
+              "tcgemm %s: inconsistent convolution (weight gradient) extents", name);
   CUtensorMap mA0, mB0, mA1, mB1;
-  int rc = make_operand_map(&mA0, name, A0, M, K0, batches, BM);
+  int rc = conv.mode == 1 ? make_image_map(&mA0, name, image, BM) : make_operand_map(&mA0, name, A0, M, K0, batches, BM);
   if (rc) return rc;
-  rc = make_operand_map(&mB0, name, B0, N, K0, batches, a.BN);
+  rc = conv.mode == 2 ? make_image_map(&mB0, name, image, BK) : make_operand_map(&mB0, name, B0, N, K0, batches, a.BN);
   if (rc) return rc;
   if (K1 > 0) {
     rc = make_operand_map(&mA1, name, A1, M, K1, batches, BM);

@@ -12,7 +12,8 @@ What this module does, and nothing more:
     re-compiled from its own source with the literal replaced by sqrt(L) (no reference file is edited);
   * `build_adnm_unet(img_size, dropin)`: `VisionMamba` with the literals of `create_ADNMUNet(5, 20, 6)`
     (models/ADNMUNet.py:906-940) and, when `dropin`, the two module globals rebound to the sm_100a modules
-    (SURVEY.md 8(b)): `models.ADNMUNet.Mamba2`, `models.model_untils.WTConv2d`;
+    (SURVEY.md 8(b)): `models.ADNMUNet.Mamba2`, `models.model_untils.WTConv2d`, plus the Block-level names and the conv
+    stages `models.ADNMUNet.WTLayer / PatchEmbed / OutProj` (SURVEY.md 8(f)1-3);
   * `reference_optimizer` / `reference_loss`: train_untils.py:29-43 without importing train_untils (it imports every
     baseline model and builds two of them at import).
 """
@@ -181,6 +182,7 @@ def load_reference():
     ns.ref_Block, ns.ref_RMSNorm = ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm
     ns.ref_StandardAttention = ns.ADNssd.StandardAttention
     ns.ref_FeedForward = ns.model_untils.FeedForward
+    ns.ref_stages = {n: getattr(ns.model_untils, n) for n in STAGE_NAMES}
     _patch_decoder_size(ns.ADNMUNet)
     _NS = ns
     return ns
@@ -202,13 +204,24 @@ def _patch_decoder_size(mod):
     mod.Decoder.forward = fn
 
 
+STAGE_NAMES = ("WTLayer", "PatchEmbed", "OutProj")      # SURVEY.md 8(f)2; resolved by Encoder / Decoder / Refiner from models.ADNMUNet's
+                                                        # globals (`from .model_untils import *`, models/ADNMUNet.py:33)
+
+
 @contextlib.contextmanager
-def _bound(ns, dropin, mixer=True, wtconv=True, block=True):
+def _bound(ns, dropin, mixer=True, wtconv=True, block=True, stages=True):
     """Rebind (or restore) the construction-time globals for the duration of a model build: the mixer and WTConv2d classes
      and, with `block`, the `Block` / `RMSNorm` names `create_block` resolves (models/ADNMUNet.py:277-291)
     and the `StandardAttention` name `Attention` resolves (models/ADNMUNet.py:181)."""
     old = (ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d, ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm, ns.ADNMUNet.StandardAttention,
            ns.model_untils.FeedForward)
+    old_stages = {n: getattr(ns.ADNMUNet, n) for n in STAGE_NAMES}
+    for n in STAGE_NAMES:
+        setattr(ns.ADNMUNet, n, ns.ref_stages[n])
+    if dropin and stages and wtconv:
+        from adnm_unet_b200 import convstage
+        for n in STAGE_NAMES:
+            setattr(ns.ADNMUNet, n, getattr(convstage, n))
     if dropin:
         from adnm_unet_b200.mixer import Mamba2
         from adnm_unet_b200.wtconv import WTConv2d
@@ -232,6 +245,8 @@ def _bound(ns, dropin, mixer=True, wtconv=True, block=True):
     finally:
         (ns.ADNMUNet.Mamba2, ns.model_untils.WTConv2d, ns.ADNMUNet.Block, ns.ADNMUNet.RMSNorm, ns.ADNMUNet.StandardAttention,
          ns.model_untils.FeedForward) = old
+        for n in STAGE_NAMES:
+            setattr(ns.ADNMUNet, n, old_stages[n])
 
 
 DEAD_BRIDGES = (3, 4, 5, 6)
@@ -257,13 +272,13 @@ def prune_dead_bridges(model):
 
 
 def build_adnm_unet(img_size=256, dropin=True, input_frames=5, output_frames=20, seed=0, mixer=True, wtconv=True, block=True,
-                    prune_dead=None):
+                    prune_dead=None, stages=True):
     """`create_ADNMUNet(5, 20, 6)` (models/ADNMUNet.py:906-940) at `img_size`; seed -> identical init for both variants
     (the drop-in constructors consume the RNG stream exactly like the reference's: tests/test_abi_cpu.py)."""
     ns = load_reference()
     if seed is not None:
         torch.manual_seed(seed)
-    with _bound(ns, dropin, mixer, wtconv, block):
+    with _bound(ns, dropin, mixer, wtconv, block, stages):
         model = ns.ADNMUNet.VisionMamba(
             img_size=img_size, depth=[1, 1, 1], refine_depth=[1, 1, 1, 1], refine_headdim=[4, 4, 4, 4],
             refine_dim=[32, 32, 32, 32] if output_frames > 5 else [32, 32, 16, 16],

@@ -244,6 +244,62 @@ int adn_sdpa_forward(const void* qkv, void* out, float* lse, int32_t B, int32_t 
 int adn_sdpa_backward(const void* qkv, const void* out, const float* lse, const void* dout, void* dqkv, int32_t B, int32_t L,
                       int32_t heads, int32_t dh, float scale, int32_t dtype, void* stream);
 
+/* ------------------------------------------------------------------ conv stages (WTLayer / PatchEmbed / OutProj) ---- */
+
+/* the full-resolution stages around the native WTConv2d - WTLayer (models/model_untils.py:358-426),
+ * PatchEmbed (:226-314), OutProj (:799-892).  All activations at this seam are token-major (B, L, C) = channels-last,
+ * except where a tensor feeds / leaves wtconv_forward (NCHW planes). */
+
+/* Dense 3x3 convolution, stride 1, zero padding 1 (Conv2dLayer.conv, models/model_untils.py:71-93) on channels-last
+ * activations: x (B, H*W, Cin) -> y (B, H*W, Cout).  w: nn.Conv2d weight (Cout, Cin, 3, 3) fp32; bias (Cout) or NULL;
+ * gamma (Cin) or NULL: per-input-channel scale applied to x before the conv (the layer scale of WTLayer :420-421 /
+ * OutProj :882-883), folded into the weights.  bf16 with Cin % 8 == 0, Cout % 8 == 0 (<= 256) and a grid that tiles into
+ * 64- / 128-token boxes runs as an implicit GEMM on tcgen05 (adn_conv3x3_path() == 1); everything else on CUDA cores. */
+typedef struct AdnConvShape {
+  int32_t B, H, W, Cin, Cout;
+  int32_t dtype; /* ADN_F32 | ADN_BF16 */
+} AdnConvShape;
+int adn_conv3x3_path(const AdnConvShape* s);
+int adn_conv3x3_workspace_bytes(const AdnConvShape* s, size_t* workspace_bytes);
+int adn_conv3x3_forward(const AdnConvShape* s, const void* x, const float* w, const float* bias, const float* gamma, void* y,
+                        void* workspace, void* stream);
+/* dx may be NULL (PatchEmbed: the input is data); dw is OVERWRITTEN; dbias / dgamma may be NULL. */
+int adn_conv3x3_backward(const AdnConvShape* s, const void* x, const float* w, const float* gamma, const void* dy, void* dx,
+                         float* dw, float* dbias, float* dgamma, void* workspace, void* stream);
+
+/* (B, L, C1) [+ (B, L, C2)] token-major -> (B, C1 + C2, H, W) planes: out[b][c][p] = g1 x[b][p][c] | g2 res[b][p][c - C1]
+ * (WTLayer :404-414: cat(gama1 x, gama2 residual) followed by the NCHW permute; g1 / g2 device scalars or NULL = 1). */
+int adn_nchw_pack_forward(const void* x, const void* res, const float* g1, const float* g2, void* out, int32_t B, int64_t HW,
+                          int32_t C1, int32_t C2, int32_t dtype, void* stream);
+/* workspace: 64 bytes.  dx / dres / dg1 / dg2 may be NULL. */
+int adn_nchw_pack_backward(const void* x, const void* res, const float* g1, const float* g2, const void* dout, void* dx, void* dres,
+                           float* dg1, float* dg2, void* workspace, int32_t B, int64_t HW, int32_t C1, int32_t C2, int32_t dtype,
+                           void* stream);
+
+/* nn.InstanceNorm2d statistics (eps, biased variance, no affine): stats[plane] = (mean, rstd) fp32, planes = B * C. */
+int adn_plane_stats(const void* y, float* stats, int64_t planes, int64_t HW, float eps, int32_t dtype, void* stream);
+
+/* out[b][p][c] = gamma[c] * (alpha * act(u) + beta * xs[b][c][p]),  u = scale * (y - mean) * rstd + shift (stats NULL: u = y).
+ * y, xs: (B, C, HW) planes; out: (B, HW, C) token-major; act 0 none, 1 GELU; scale / shift / gamma may be NULL.
+ *   WTLayer    :416       alpha * wtconv(x) + beta * shortcut  with WTConvLayer's scale * norm(x) + shift (:112-113)
+ *   PatchEmbed :303-307   alpha1 * GELU(wtconv(x)) + beta1 * x;  (alpha2 * IN(wtconv(s)) + beta2 * s) * gamma
+ *   OutProj    :880-883   (alpha * GELU(IN(wtconv(x))) + beta * shortcut) * gamma */
+int adn_plane_mix_forward(const void* y, const void* xs, const float* stats, const float* scale, const float* shift,
+                          const float* alpha, const float* beta, const float* gamma, void* out, int32_t B, int32_t C, int64_t HW,
+                          int32_t act, int32_t dtype, void* stream);
+int adn_plane_mix_workspace_bytes(int32_t B, int32_t C, size_t* workspace_bytes);
+/* dout: (B, HW, C); dy / dxs: (B, C, HW), either may be NULL; dscal[4] = (dscale, dshift, dalpha, dbeta); dgamma (C) or NULL. */
+int adn_plane_mix_backward(const void* y, const void* xs, const float* stats, const float* scale, const float* shift,
+                           const float* alpha, const float* beta, const float* gamma, const void* dout, void* dy, void* dxs,
+                           float* dscal, float* dgamma, void* workspace, int32_t B, int32_t C, int64_t HW, int32_t act,
+                           int32_t dtype, void* stream);
+
+/* Activation after a conv / Linear: kind 1 = GELU (erf form), 2 = Swish x * sigmoid(beta * x) (models/model_untils.py:162-169,
+ * beta a device scalar or NULL = 1).  Backward workspace: 64 bytes; dbeta may be NULL. */
+int adn_act_forward(const void* x, void* y, int64_t n, int32_t kind, const float* beta, int32_t dtype, void* stream);
+int adn_act_backward(const void* x, const void* dy, void* dx, int64_t n, int32_t kind, const float* beta, float* dbeta,
+                     void* workspace, int32_t dtype, void* stream);
+
 /* ------------------------------------------------------------------ misc ------------------- */
 
 const char* adn_last_error(void);

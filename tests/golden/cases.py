@@ -136,3 +136,36 @@ def block_inputs(name, dtype=torch.float64):
 def block_dout(name, out_ref):
     seed = 6500 + sorted(BLOCK_CASES).index(name)
     return corr_dout(out_ref, seed, frac=1.0) / out_ref.numel()
+
+
+# Conv-stage goldens: the reference `WTLayer`, `PatchEmbed`, `OutProj` (models/model_untils.py:226-426,799-892)
+# with InstanceNorm=True and perturbed parameters (oracle.convstage_oracle.perturb_params), fp64, bf16-representable inputs.
+# name -> (kind, ctor kwargs, batch, grid, skip)
+CONVSTAGE_CASES = {
+    "wtlayer_d32_o64_g16": ("WTLayer", dict(this_dim=32, next_dim=64, kernel=5, wt_levels=2), 2, 16, False),
+    "wtlayer_d64_o32_g16_skip": ("WTLayer", dict(this_dim=64, next_dim=32, kernel=5, wt_levels=3, if_res=True), 2, 16, True),
+    "patchembed_c5_e32_g32": ("PatchEmbed", dict(img_size=32, patch_size=2, in_channels=5, embed_dim=32, kernel=5, wt_levels=3), 2, 32, False),
+    "outproj_e32_f20_g32": ("OutProj", dict(num_frames=20, embed_dim=32, img_size=[32, 32], wt_levels=3, out_expand=2), 2, 32, False),
+}
+
+
+def convstage_inputs(name, dtype=torch.float64):
+    """(x, second): second = residual tokens (WTLayer skip), the residual frame (OutProj) or None."""
+    kind, kw, B, g, skip = CONVSTAGE_CASES[name]
+    seed = 7000 + 10 * sorted(CONVSTAGE_CASES).index(name)
+    if kind == "WTLayer":
+        c = kw["this_dim"] // 2 if skip else kw["this_dim"]
+        x = bf16_exact(rng_normal(seed, (B, g * g, c), torch.float32)).to(dtype)
+        second = bf16_exact(rng_normal(seed + 1, (B, g * g, c), torch.float32)).to(dtype) if skip else None
+    elif kind == "PatchEmbed":
+        x = bf16_exact(rng_uniform(seed, (B, g * g, kw["in_channels"]), torch.float32)).to(dtype)
+        second = None
+    else:
+        x = bf16_exact(rng_normal(seed, (B, g * g, kw["embed_dim"]), torch.float32)).to(dtype)
+        second = bf16_exact(rng_uniform(seed + 1, (B, g, g), torch.float32)).to(dtype)
+    return x, second
+
+
+def convstage_dout(name, out_ref):
+    seed = 7500 + sorted(CONVSTAGE_CASES).index(name)
+    return corr_dout(out_ref, seed, frac=1.0) / out_ref.numel()

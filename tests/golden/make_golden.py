@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 import cases  # noqa: E402
 from ref_loader import cuda_to_is_noop, load_reference  # noqa: E402
-from oracle import adnssd_oracle, block_oracle, wtconv_oracle  # noqa: E402
+from oracle import adnssd_oracle, block_oracle, convstage_oracle, wtconv_oracle  # noqa: E402
 
 
 def save(name, **arrays):
@@ -130,6 +130,39 @@ def block_case(ref, name):
     save(name, **arrays)
 
 
+def convstage_case(ref, name):
+    """The unmodified reference WTLayer / PatchEmbed / OutProj (models/model_untils.py:226-426,799-892), fp64, CPU."""
+    kind, kw, B, g, skip = cases.CONVSTAGE_CASES[name]
+    torch.manual_seed(31)
+    m = getattr(ref.model_untils, kind)(**kw)
+    p32 = convstage_oracle.perturb_params(m.state_dict(), seed=29)
+    m = m.double()
+    m.load_state_dict({k: v.double() for k, v in p32.items()}, strict=True)
+    x, second = cases.convstage_inputs(name, torch.float64)
+    x.requires_grad_(kind != "PatchEmbed")
+    if second is not None and kind == "WTLayer":
+        second.requires_grad_(True)
+    if kind == "WTLayer":
+        out = m(x, residual=second, features=second.detach() * 0.5 if skip else None)
+    elif kind == "PatchEmbed":
+        out, res = m(x)
+        assert torch.equal(res, x.view(B, g, g, -1)[..., -1])
+    else:
+        out = m(x, second)
+    dout = cases.convstage_dout(name, out.detach())
+    out.backward(dout.double())
+    arrays = {"param/" + k: v.numpy() for k, v in p32.items()}
+    arrays.update(out=out.detach().numpy())
+    if x.grad is not None:
+        arrays.update(dx=x.grad.numpy())
+    if second is not None and second.grad is not None:
+        arrays.update(dsecond=second.grad.numpy())
+    for k, v in m.named_parameters():
+        if v.grad is not None:
+            arrays["grad/" + k] = v.grad.numpy()
+    save(name, **arrays)
+
+
 def metrics_case():
     """Counts from the reference's own float2int / _cal_frame (datasets/Shanghai_metrics.py:45-47,105-114).
     The class constructor needs `lpips` (absent, downloads weights) so the two methods are called unbound."""
@@ -171,6 +204,9 @@ def main():
     for name in cases.BLOCK_CASES:
         if not only or name in only:
             block_case(ref, name)
+    for name in cases.CONVSTAGE_CASES:
+        if not only or name in only:
+            convstage_case(ref, name)
     if not only or cases.METRIC_CASE[0] in only:
         metrics_case()
 

@@ -148,3 +148,59 @@ def test_block_modules_mirror_reference_state_dict():
     assert list(ra) == list(rb) and all(torch.equal(ra[k], rb[k]) for k in ra)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         A.RMSNorm(16)(torch.zeros(2, 3, 16))
+
+
+def test_convstage_modules_mirror_reference_state_dict():
+    """WTLayer / PatchEmbed / OutProj: reference key names, shapes and registration order; a same-seed
+    construction consumes the RNG stream like the reference classes; the hosted network with the stages bound has the
+    reference's state_dict, key for key and bit for bit (only checked where the reference is importable)."""
+    import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("reference not mounted")
+    import cases
+    from adnm_unet_b200 import convstage, refhost
+    ref = ref_loader.load_reference()
+    for name, (kind, kw, B, g, skip) in cases.CONVSTAGE_CASES.items():
+        torch.manual_seed(17)
+        a = getattr(ref.model_untils, kind)(**kw)
+        torch.manual_seed(17)
+        b = getattr(convstage, kind)(**kw)
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb), name
+        assert [n for n, _ in a.named_parameters()] == [n for n, _ in b.named_parameters()], name
+        for k in sa:      # the frozen Haar filters: exact +-0.5 here, float32 (1/sqrt 2)^2 = 0.49999997 from the pywt taps there
+            assert torch.allclose(sa[k], sb[k], rtol=0, atol=1e-7) if k.endswith("wt_filter") else torch.equal(sa[k], sb[k]), (name, k)
+        assert torch.equal(torch.rand(3), (torch.manual_seed(17), getattr(ref.model_untils, kind)(**kw), torch.rand(3))[2])
+    a = refhost.build_adnm_unet(128, dropin=False, seed=0).state_dict()
+    m = refhost.build_adnm_unet(128, dropin=True, seed=0)
+    b = m.state_dict()
+    assert list(a) == list(b)
+    for k in a:
+        assert torch.allclose(a[k], b[k], rtol=0, atol=1e-7) if k.endswith("wt_filter") else torch.equal(a[k], b[k]), k
+    assert type(m.encoder.encoder1) is convstage.PatchEmbed and type(m.decoder.decoder6) is convstage.WTLayer
+    assert type(m.refiner.out_proj) is convstage.OutProj and type(m.encoder.encoder2) is convstage.WTLayer
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.encoder.encoder2(torch.zeros(1, 64, 32))
+
+
+def test_convstage_entry_points_validate_on_the_host(lib):
+    from adnm_unet_b200 import _lib
+    assert C.sizeof(_lib.AdnConvShape) == 24
+    nb = C.c_size_t()
+    ok = _lib.AdnConvShape(B=32, H=128, W=128, Cin=64, Cout=32, dtype=_lib.ADN_BF16)
+    assert lib.adn_conv3x3_workspace_bytes(ok, nb) == 0 and nb.value >= 32 * 9 * 64 * (2 + 4) + 64 * 9 * 64 * 2
+    assert lib.adn_conv3x3_path(ok) == 1                                    # tcgen05 implicit GEMM
+    assert lib.adn_conv3x3_path(_lib.AdnConvShape(B=32, H=128, W=128, Cin=5, Cout=32, dtype=_lib.ADN_BF16)) == 0     # thin: CUDA cores
+    assert lib.adn_conv3x3_path(_lib.AdnConvShape(B=2, H=24, W=24, Cin=64, Cout=32, dtype=_lib.ADN_BF16)) == 0      # 24 does not tile
+    assert lib.adn_conv3x3_path(_lib.AdnConvShape(B=2, H=16, W=16, Cin=64, Cout=32, dtype=_lib.ADN_F32)) == 0       # check mode
+    assert lib.adn_conv3x3_path(_lib.AdnConvShape(B=4, H=4, W=4, Cin=128, Cout=256, dtype=_lib.ADN_BF16)) == 1       # boxes span samples
+    for field, val in (("B", 0), ("Cin", 0), ("dtype", 3)):
+        bad = _lib.AdnConvShape(B=32, H=128, W=128, Cin=64, Cout=32, dtype=_lib.ADN_BF16)
+        setattr(bad, field, val)
+        assert lib.adn_conv3x3_workspace_bytes(bad, nb) != 0 and lib.adn_last_error()
+    one = C.c_void_p(256)      # never dereferenced: validation comes first
+    assert lib.adn_plane_stats(one, one, 0, 16, 1e-5, _lib.ADN_F32, None) != 0
+    assert lib.adn_plane_mix_forward(one, one, None, None, None, one, one, None, one, 2, 8, 64, 2, _lib.ADN_F32, None) != 0 and b"act" in lib.adn_last_error()
+    assert lib.adn_act_forward(one, one, 10, 3, None, _lib.ADN_F32, None) != 0 and b"kind" in lib.adn_last_error()
+    assert lib.adn_nchw_pack_forward(one, None, None, None, one, 2, 64, 8, 8, _lib.ADN_F32, None) != 0      # C2 > 0 without res
+    assert lib.adn_plane_mix_workspace_bytes(32, 64, nb) == 0 and nb.value >= 32 * 64 * 16

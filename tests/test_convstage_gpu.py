@@ -1,0 +1,254 @@
+"""GPU parity of the conv-stage kernels (dense 3x3 conv as a tcgen05 implicit GEMM, plane packing,
+InstanceNorm + shortcut mix, activations) and of the WTLayer / PatchEmbed / OutProj drop-ins, through the C ABI, against the
+CPU oracle (oracle/convstage_oracle.py) and goldens of the unmodified reference modules (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import convstage_oracle as CO
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+DT = [torch.float32, torch.bfloat16]
+IDS = ["fp32", "bf16"]
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), torch.as_tensor(b).detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def _leaf(t, dev=None, dtype=None):
+    t = t.detach().clone()
+    if dev is not None:
+        t = t.to(dev, dtype) if dtype is not None else t.to(dev)
+    return t.requires_grad_(True)
+
+
+# name -> (B, H, W, Cin, Cout, bias, gamma, expected path for bf16: 1 tcgen05 implicit GEMM, 0 CUDA cores)
+CONV_CASES = {
+    "tc_32_64_g16": (2, 16, 16, 32, 64, True, True, 1),
+    "tc_64_32_g128": (1, 128, 128, 64, 32, True, True, 1),        # decoder6 of the network at 128 x 128
+    "tc_256_64_g32": (2, 32, 32, 256, 64, True, False, 1),        # decoder4
+    "tc_128_256_g4": (4, 4, 4, 128, 256, False, True, 1),         # a 128-token box spans 8 samples
+    "tc_64_128_g8_b3": (3, 8, 8, 64, 128, True, True, 1),         # boxes span 2 samples; the last one is half outside the batch
+    "tc_32_64_g256x64": (1, 64, 256, 32, 64, False, True, 1),     # two 128-token boxes per image row
+    "tc_40_24_g16": (2, 16, 16, 40, 24, True, True, 1),           # channel counts that are multiples of 8 only
+    "thin_5_32_g16": (2, 16, 16, 5, 32, False, False, 0),         # PatchEmbed.conv2
+    "thin_20_20_g12": (1, 12, 12, 20, 20, False, False, 0),       # OutProj.conv2
+    "odd_64_32_g24": (2, 24, 24, 64, 32, True, True, 0),          # 24 does not tile into 64- / 128-token boxes
+}
+
+
+@pytest.mark.parametrize("dtype", DT, ids=IDS)
+@pytest.mark.parametrize("name", sorted(CONV_CASES))
+def test_conv3x3_matches_oracle(name, dtype):
+    from adnm_unet_b200 import _lib
+    from adnm_unet_b200.convstage import conv3x3_tokens
+    B, H, W, Cin, Cout, has_bias, has_gamma, path = CONV_CASES[name]
+    dev = torch.device("cuda:0")
+    seed = 8000 + 10 * sorted(CONV_CASES).index(name)
+    x = cases.bf16_exact(cases.rng_normal(seed, (B, H * W, Cin), torch.float32))
+    dy = cases.bf16_exact(cases.rng_normal(seed + 1, (B, H * W, Cout), torch.float32))
+    w = cases.rng_normal(seed + 2, (Cout, Cin, 3, 3), torch.float32) / (3 * Cin ** 0.5)
+    b = 0.3 * cases.rng_normal(seed + 3, (Cout,), torch.float32) if has_bias else None
+    g = 1 + 0.3 * cases.rng_normal(seed + 4, (Cin,), torch.float32) if has_gamma else None
+    shape = _lib.AdnConvShape(B=B, H=H, W=W, Cin=Cin, Cout=Cout, dtype=_lib.ADN_BF16 if dtype == torch.bfloat16 else _lib.ADN_F32)
+    assert _lib.load().adn_conv3x3_path(shape) == (path if dtype == torch.bfloat16 else 0)
+    leaves = [t.double().requires_grad_(True) if t is not None else None for t in (x, w, b, g)]
+    ref = CO.conv_tokens(leaves[0], H, W, leaves[1], leaves[2], leaves[3])
+    ref.backward(dy.double())
+    xd, wd = _leaf(x, dev, dtype), _leaf(w, dev)
+    bd = _leaf(b, dev) if has_bias else None
+    gd = _leaf(g, dev) if has_gamma else None
+    y = conv3x3_tokens(xd, H, W, wd, bd, gd)
+    y.backward(dy.to(dev, dtype))
+    torch.cuda.synchronize()
+    errs = {"y": rel(y, ref), "dx": rel(xd.grad, leaves[0].grad), "dw": rel(wd.grad, leaves[1].grad)}
+    if has_bias:
+        errs["dbias"] = rel(bd.grad, leaves[2].grad)
+    if has_gamma:
+        errs["dgamma"] = rel(gd.grad, leaves[3].grad)
+    bad = {k: v for k, v in errs.items() if not v < TOL[dtype]}
+    assert not bad, bad
+
+
+def test_conv3x3_without_input_gradient():
+    """PatchEmbed's conv reads data: dx is not requested (NULL at the ABI), the weight gradient still comes out."""
+    from adnm_unet_b200.convstage import conv3x3_tokens
+    dev = torch.device("cuda:0")
+    x = cases.bf16_exact(cases.rng_normal(1, (2, 256, 32), torch.float32)).to(dev, torch.bfloat16)
+    w = (cases.rng_normal(2, (64, 32, 3, 3), torch.float32) / 17).to(dev).requires_grad_(True)
+    dy = cases.bf16_exact(cases.rng_normal(3, (2, 256, 64), torch.float32))
+    y = conv3x3_tokens(x, 16, 16, w)
+    y.backward(dy.to(dev, torch.bfloat16))
+    xr, wr = x.double().cpu(), w.detach().double().cpu().requires_grad_(True)
+    CO.conv_tokens(xr, 16, 16, wr).backward(dy.double())
+    assert rel(w.grad, wr.grad) < 2e-2
+
+
+# (B, H, W, C1, C2, scalars)
+@pytest.mark.parametrize("dtype", DT, ids=IDS)
+@pytest.mark.parametrize("cfg", [(2, 16, 16, 32, 32, True), (3, 12, 12, 5, 0, False), (1, 33, 20, 24, 40, True), (2, 64, 64, 64, 0, False)],
+                         ids=lambda c: "B%d_%dx%d_C%d+%d_s%d" % c)
+def test_pack_planes_matches_oracle(cfg, dtype):
+    from adnm_unet_b200.convstage import pack_planes
+    B, H, W, C1, C2, scalars = cfg
+    dev = torch.device("cuda:0")
+    x = cases.bf16_exact(cases.rng_normal(21, (B, H * W, C1), torch.float32))
+    r = cases.bf16_exact(cases.rng_normal(22, (B, H * W, C2), torch.float32)) if C2 else None
+    dout = cases.bf16_exact(cases.rng_normal(23, (B, C1 + C2, H, W), torch.float32))
+    g1, g2 = (torch.tensor(1.3), torch.tensor(-0.7)) if scalars else (None, None)
+    lv = [None if t is None else t.double().requires_grad_(True) for t in (x, r, g1, g2)]
+    t = lv[0] if g1 is None else lv[2] * lv[0]
+    if C2:
+        t = torch.cat((t, lv[1] if g2 is None else lv[3] * lv[1]), dim=-1)
+    ref = CO.to_planes(t, H, W)
+    ref.backward(dout.double())
+    xd = _leaf(x, dev, dtype)
+    rd = _leaf(r, dev, dtype) if C2 else None
+    sd = [_leaf(s, dev) for s in (g1, g2)] if scalars else [None, None]
+    out = pack_planes(xd, H, W, rd, sd[0], sd[1] if C2 else None)
+    out.backward(dout.to(dev, dtype))
+    torch.cuda.synchronize()
+    assert out.shape == (B, C1 + C2, H, W) and out.is_contiguous()
+    errs = {"out": rel(out, ref), "dx": rel(xd.grad, lv[0].grad)}
+    if C2:
+        errs["dres"] = rel(rd.grad, lv[1].grad)
+    if scalars:
+        errs["dg1"] = rel(sd[0].grad, lv[2].grad)
+        if C2:
+            errs["dg2"] = rel(sd[1].grad, lv[3].grad)
+    bad = {k: v for k, v in errs.items() if not v < TOL[dtype]}
+    assert not bad, bad
+
+
+# (B, C, H, W, norm, act, gamma)
+@pytest.mark.parametrize("dtype", DT, ids=IDS)
+@pytest.mark.parametrize("cfg", [(2, 32, 16, 16, True, False, False), (2, 5, 16, 16, False, True, False), (3, 32, 12, 20, True, False, True),
+                                 (2, 40, 32, 32, True, True, True), (1, 64, 128, 128, True, False, False), (2, 7, 9, 11, False, False, True)],
+                         ids=lambda c: "B%d_C%d_%dx%d_norm%d_act%d_gamma%d" % c)
+def test_plane_mix_matches_oracle(cfg, dtype):
+    from adnm_unet_b200.convstage import plane_mix
+    B, C, H, W, norm, act, has_gamma = cfg
+    dev = torch.device("cuda:0")
+    y = cases.bf16_exact(1.5 * cases.rng_normal(31, (B, C, H, W), torch.float32) + 0.4)
+    xs = cases.bf16_exact(cases.rng_normal(32, (B, C, H, W), torch.float32))
+    dout = cases.bf16_exact(cases.rng_normal(33, (B, H * W, C), torch.float32))
+    sc = {"alpha": torch.tensor(0.8), "beta": torch.tensor(1.2)}
+    if norm:
+        sc.update(scale=torch.tensor(1.3), shift=torch.tensor(-0.2))
+    gamma = 1 + 0.3 * cases.rng_normal(34, (C,), torch.float32) if has_gamma else None
+    ly, lx = y.double().requires_grad_(True), xs.double().requires_grad_(True)
+    ls = {k: v.double().requires_grad_(True) for k, v in sc.items()}
+    lg = gamma.double().requires_grad_(True) if has_gamma else None
+    ref = CO.plane_mix(ly, lx, ls["alpha"], ls["beta"], ls.get("scale"), ls.get("shift"), lg, norm=norm, act=act)
+    ref.backward(dout.double())
+    yd, xd = _leaf(y, dev, dtype), _leaf(xs, dev, dtype)
+    sd = {k: _leaf(v, dev) for k, v in sc.items()}
+    gd = _leaf(gamma, dev) if has_gamma else None
+    out = plane_mix(yd, xd, sd["alpha"], sd["beta"], sd.get("scale"), sd.get("shift"), gd, norm=norm, act=int(act))
+    out.backward(dout.to(dev, dtype))
+    torch.cuda.synchronize()
+    assert out.shape == (B, H * W, C)
+    errs = {"out": rel(out, ref), "dy": rel(yd.grad, ly.grad), "dxs": rel(xd.grad, lx.grad)}
+    errs.update({"d" + k: rel(sd[k].grad, ls[k].grad) for k in sc})
+    if has_gamma:
+        errs["dgamma"] = rel(gd.grad, lg.grad)
+    # bf16: dy of the normalised planes is a difference of three terms; the 0-dim gates are sums over every element
+    tol = {k: (5e-2 if dtype == torch.bfloat16 and k in ("dscale", "dshift", "dalpha", "dbeta") else TOL[dtype]) for k in errs}
+    bad = {k: v for k, v in errs.items() if not v < tol[k]}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("dtype", DT, ids=IDS)
+@pytest.mark.parametrize("kind", ["gelu", "swish"])
+def test_activation_matches_oracle(kind, dtype):
+    from adnm_unet_b200.convstage import gelu_tokens, swish_tokens
+    dev = torch.device("cuda:0")
+    x = cases.bf16_exact(2.5 * cases.rng_normal(41, (3, 1001, 7), torch.float32))
+    dy = cases.bf16_exact(cases.rng_normal(42, (3, 1001, 7), torch.float32))
+    lx = x.double().requires_grad_(True)
+    lb = torch.tensor(1.4, dtype=torch.float64, requires_grad=True)
+    ref = torch.nn.functional.gelu(lx) if kind == "gelu" else lx * torch.sigmoid(lb * lx)
+    ref.backward(dy.double())
+    xd = _leaf(x, dev, dtype)
+    bd = _leaf(torch.tensor(1.4), dev)
+    out = gelu_tokens(xd) if kind == "gelu" else swish_tokens(xd, bd)
+    out.backward(dy.to(dev, dtype))
+    torch.cuda.synchronize()
+    errs = {"out": rel(out, ref), "dx": rel(xd.grad, lx.grad)}
+    if kind == "swish":
+        errs["dbeta"] = rel(bd.grad, lb.grad)
+    bad = {k: v for k, v in errs.items() if not v < TOL[dtype]}
+    assert not bad, bad
+
+
+# bf16: these modules chain 7-9 stages that each store a bf16 tensor (pack, WTConv2d, norm + mix, fc1, GELU, fc2, conv, GELU);
+# like the whole Block (tests/test_block_gpu.py) the INPUT gradients are held to 3e-2, outputs and weight gradients to 2e-2,
+# 0-dim gates and the bias that sits in front of an InstanceNorm (true gradient: zero) are sanity-bounded.
+CHAIN_BF16_TOL = 3e-2
+
+
+@pytest.mark.parametrize("dtype", DT, ids=IDS)
+@pytest.mark.parametrize("name", sorted(cases.CONVSTAGE_CASES))
+def test_stage_modules_match_reference_golden(golden_dir, name, dtype):
+    """Output, input gradients and parameter gradients of the UNMODIFIED reference WTLayer / PatchEmbed / OutProj (fp64, made by
+    tests/golden/make_golden.py) against the drop-ins through the C ABI."""
+    from adnm_unet_b200 import convstage
+    kind, kw, B, g, skip = cases.CONVSTAGE_CASES[name]
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    dev = torch.device("cuda:0")
+    m = getattr(convstage, kind)(**kw)
+    m.load_state_dict({k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")}, strict=True)
+    m = m.to(dev)
+    x, second = cases.convstage_inputs(name, torch.float32)
+    x = x.to(dev, dtype).requires_grad_(kind != "PatchEmbed")
+    if second is not None:
+        second = second.to(dev, dtype).requires_grad_(kind == "WTLayer")
+    if kind == "WTLayer":
+        out = m(x, residual=second, features=second.detach() * 0.5 if skip else None)
+    elif kind == "PatchEmbed":
+        out, res = m(x)
+        assert torch.equal(res, x.view(B, g, g, -1)[..., -1])
+    else:
+        out = m(x, second)
+    out.backward(cases.convstage_dout(name, torch.from_numpy(z["out"])).to(dev, dtype))
+    torch.cuda.synchronize()
+    assert out.shape == z["out"].shape
+    errs = {"out": rel(out, z["out"])}
+    if "dx" in z.files:
+        errs["dx"] = rel(x.grad, z["dx"])
+    if "dsecond" in z.files:
+        errs["dsecond"] = rel(second.grad, z["dsecond"])
+    grads = {k[5:]: z[k] for k in z.files if k.startswith("grad/")}
+    assert {k for k, v in m.named_parameters() if v.grad is not None} == set(grads)
+    null = [k for k, v in grads.items() if np.abs(v).max() < 1e-14]
+    scale = max(float(np.abs(v).max()) for v in grads.values())
+    for k, v in m.named_parameters():
+        if k in null:
+            assert float(v.grad.abs().max()) < (1e-2 if dtype == torch.bfloat16 else 1e-5) * scale, k
+        elif k in grads:
+            errs[k] = rel(v.grad, grads[k])
+    tol = {k: (1e-1 if dtype == torch.bfloat16 and k in grads and grads[k].size <= 1 else TOL[dtype]) for k in errs}
+    if dtype == torch.bfloat16:
+        tol.update({k: CHAIN_BF16_TOL for k in ("dx", "dsecond") if k in tol})
+    bad = {k: v for k, v in errs.items() if not v < tol[k]}
+    assert not bad, bad
+
+
+def test_stage_modules_inference_and_autocast():
+    """no_grad forward saves nothing; under bf16 autocast with fp32 inputs the stages compute in bf16 like the hosted network."""
+    from adnm_unet_b200 import convstage
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    m = convstage.WTLayer(this_dim=32, next_dim=64, kernel=5, wt_levels=2).to(dev)
+    x = torch.randn(2, 256, 32, device=dev)
+    with torch.no_grad():
+        a = m(x)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        b = m(x)
+    assert a.dtype == torch.float32 and b.dtype == torch.bfloat16 and rel(b, a) < 2e-2

@@ -208,3 +208,45 @@ def test_attention_oracle_matches_reference(cfg):
     assert rel(y2.detach(), y.detach()) < 1e-12 and rel(x2.grad, x.grad) < 1e-12
     for k, v in m.named_parameters():
         assert rel(pp[k].grad, v.grad) < 1e-12, k
+
+
+def convstage_oracle_run(name, params, x, second, dtype=torch.float64):
+    """Forward of oracle/convstage_oracle.py for a CONVSTAGE_CASES entry; returns (out, leaves) with autograd leaves."""
+    from oracle import convstage_oracle as CO
+    kind, kw, B, g, skip = cases.CONVSTAGE_CASES[name]
+    p = {k: (v.to(dtype).clone().requires_grad_(not k.endswith("wt_filter"))) for k, v in params.items()}
+    x = x.to(dtype).clone().requires_grad_(kind != "PatchEmbed")
+    if second is not None:
+        second = second.to(dtype).clone().requires_grad_(kind == "WTLayer")
+    if kind == "WTLayer":
+        out = CO.wtlayer_forward(p, x, kw["wt_levels"], residual=second, features=second.detach() * 0.5 if skip else None)
+    elif kind == "PatchEmbed":
+        out, res = CO.patchembed_forward(p, x, kw["wt_levels"])
+        assert torch.equal(res, x.view(B, g, g, -1)[..., -1])
+    else:
+        out = CO.outproj_forward(p, x, second, g, g)
+    return out, p, x, second
+
+
+@pytest.mark.parametrize("name", sorted(cases.CONVSTAGE_CASES))
+def test_convstage_oracle_matches_reference_fp64(golden_dir, name):
+    """oracle/convstage_oracle.py against goldens of the unmodified reference WTLayer / PatchEmbed / OutProj
+    (models/model_untils.py:226-426,799-892; tests/golden/make_golden.py::convstage_case)."""
+    z, params, grads = load(golden_dir, name)
+    x, second = cases.convstage_inputs(name, torch.float64)
+    out, p, x, second = convstage_oracle_run(name, params, x, second)
+    assert rel(out.detach(), z["out"]) < 1e-12
+    out.backward(cases.convstage_dout(name, torch.from_numpy(z["out"])).double())
+    if "dx" in z.files:
+        assert rel(x.grad, z["dx"]) < 1e-11
+    if "dsecond" in z.files:
+        assert rel(second.grad, z["dsecond"]) < 1e-11
+    assert grads, "golden holds no parameter gradients"
+    for k, g in grads.items():
+        assert p[k].grad is not None, k
+        if g.abs().max() < 1e-14:      # a bias in front of an InstanceNorm: its gradient is identically zero, both sides hold rounding noise
+            assert p[k].grad.abs().max() < 1e-14, k
+            continue
+        assert rel(p[k].grad, g) < 1e-10, k
+    unused = [k for k, v in p.items() if v.requires_grad and v.grad is None]
+    assert sorted(unused) == sorted(k for k in p if k not in grads and not k.endswith("wt_filter")), unused
