@@ -10,10 +10,12 @@ from adnm_unet_b200.rmsnorm import RMSNorm, rmsnorm_affine  # noqa: F401
 from adnm_unet_b200.block import Block, FeedForward, residual_mix, linear_tokens, make_block  # noqa: F401
 from adnm_unet_b200.attention import StandardAttention, sdpa_packed  # noqa: F401
 from adnm_unet_b200.evaluator import SimplifiedEvaluator  # noqa: F401
+from adnm_unet_b200.convstage import WTLayer, PatchEmbed, OutProj, conv3x3_tokens, plane_mix, pack_planes  # noqa: F401
 from adnm_unet_b200.inject import install_into_reference  # noqa: F401
 from adnm_unet_b200.dp import GradAllReducer, shard_range  # noqa: F401
 from adnm_unet_b200.graphed import graphed_mixer  # noqa: F401
 
 __all__ = ["Mamba2", "adnssd_mixer", "WTConv2d", "wtconv2d", "threshold_counts", "csi_hss", "install_into_reference",
            "graphed_mixer", "RMSNorm", "rmsnorm_affine", "Block", "FeedForward", "residual_mix", "linear_tokens", "make_block",
-           "StandardAttention", "sdpa_packed", "SimplifiedEvaluator"]
+           "StandardAttention", "sdpa_packed", "SimplifiedEvaluator", "WTLayer", "PatchEmbed", "OutProj", "conv3x3_tokens", "plane_mix",
+           "pack_planes"]

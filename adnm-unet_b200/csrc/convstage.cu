@@ -268,70 +268,123 @@ static int conv_backward(const ConvDims& d, const T* x, const float* w, const fl
 }
 
 // ================================================================ layout changes, InstanceNorm, shortcut mix
-// A 32 x 32 (pixels x channels) tile goes through shared memory: the token-major side is read / written with lanes along
-// the channels, the NCHW side with lanes along the pixels, so both sides move whole 64-byte (bf16) / 128-byte (fp32) segments.
-constexpr int TS = 32;
+// A (32 V) x (32 V) (pixels x channels) tile goes through shared memory: the token-major side is read / written with lanes along
+// the channels, the NCHW side with lanes along the pixels, V elements per lane: V = 2 (4-byte bf16x2 / 8-byte float2 accesses,
+// 128 / 256 contiguous bytes per warp row) when the channel counts and the plane size are even, V = 1 otherwise (C = 5).
+template <int V> __device__ __forceinline__ void ldv(const float* p, float* v) {
+  if constexpr (V == 1) { v[0] = *p; } else { const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
+}
+template <int V> __device__ __forceinline__ void ldv(const bf16* p, float* v) {
+  if constexpr (V == 1) { v[0] = __bfloat162float(*p); } else { sm100::unpack_bf16(*reinterpret_cast<const uint32_t*>(p), v[0], v[1]); }
+}
+template <int V> __device__ __forceinline__ void stv(float* p, const float* v) {
+  if constexpr (V == 1) { *p = v[0]; } else { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+}
+template <int V> __device__ __forceinline__ void stv(bf16* p, const float* v) {
+  if constexpr (V == 1) { *p = __float2bfloat16_rn(v[0]); } else { *reinterpret_cast<uint32_t*>(p) = sm100::pack_bf16(v[0], v[1]); }
+}
+// Thread (tx = lane, ty = warp of 8): token side -> pixel row ty + 8 j, channels V tx ..; plane side -> channel row ty + 8 j, pixels V tx ..
+#define TILE_DECL(V)                                                                         \
+  constexpr int TSV = 32 * V;                                                                \
+  __shared__ float tile[TSV][TSV + 1];                                                       \
+  const int b = blockIdx.z, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                    \
+  const int c0 = blockIdx.y * TSV;
 
 // out[b][c][p] = g1 x[b][p][c] (c < C1) | g2 res[b][p][c - C1]        (WTLayer :404-414: cat(gama1 x, gama2 residual), then NCHW)
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
 k_pack_fwd(const T* __restrict__ x, int C1, const T* __restrict__ res, int C2, const float* __restrict__ g1p, const float* __restrict__ g2p,
            T* __restrict__ out, long long HW) {
-  __shared__ float tile[TS][TS + 1];
-  const int C = C1 + C2, b = blockIdx.z, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const long long p0 = (long long)blockIdx.x * TS;
-  const int c0 = blockIdx.y * TS;
+  TILE_DECL(V)
+  const int C = C1 + C2;
+  const long long p0 = (long long)blockIdx.x * TSV;
   const float g1 = g1p ? *g1p : 1.f, g2 = g2p ? *g2p : 1.f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const long long p = p0 + ty + 8 * j;
-    const int c = c0 + tx;
-    float v = 0.f;
-    if (p < HW && c < C) v = c < C1 ? g1 * ldf(x + ((long long)b * HW + p) * C1 + c) : g2 * ldf(res + ((long long)b * HW + p) * C2 + (c - C1));
-    tile[ty + 8 * j][tx] = v;
+  for (int j = 0; j < 4 * V; ++j) {
+    const int pl = ty + 8 * j, c = c0 + V * tx;
+    const long long p = p0 + pl;
+    float v[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = 0.f;
+    if (p < HW && c < C) {
+      if (c < C1) ldv<V>(x + ((long long)b * HW + p) * C1 + c, v);
+      else ldv<V>(res + ((long long)b * HW + p) * C2 + (c - C1), v);
+      const float g = c < C1 ? g1 : g2;
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] *= g;
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) tile[pl][V * tx + e] = v[e];
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c0 + ty + 8 * j;
-    const long long p = p0 + tx;
-    if (p < HW && c < C) stf(out + ((long long)b * C + c) * HW + p, tile[tx][ty + 8 * j]);
+  for (int j = 0; j < 4 * V; ++j) {
+    const int cl = ty + 8 * j, c = c0 + cl;
+    const long long p = p0 + V * tx;
+    if (p < HW && c < C) {
+      float v[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] = tile[V * tx + e][cl];
+      stv<V>(out + ((long long)b * C + c) * HW + p, v);
+    }
   }
 }
 
 // dx = g1 dout^T, dres = g2 dout^T, acc[0] += <x, dout^T>, acc[1] += <res, dout^T>   (fp64 accumulators, zeroed by the caller)
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
 k_pack_bwd(const T* __restrict__ x, int C1, const T* __restrict__ res, int C2, const float* __restrict__ g1p, const float* __restrict__ g2p,
            const T* __restrict__ dout, T* __restrict__ dx, T* __restrict__ dres, double* __restrict__ acc, long long HW) {
-  __shared__ float tile[TS][TS + 1];
+  TILE_DECL(V)
   __shared__ float red[2][8];
-  const int C = C1 + C2, b = blockIdx.z, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const long long p0 = (long long)blockIdx.x * TS;
-  const int c0 = blockIdx.y * TS;
+  const int C = C1 + C2;
+  const long long p0 = (long long)blockIdx.x * TSV;
   const float g1 = g1p ? *g1p : 1.f, g2 = g2p ? *g2p : 1.f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c0 + ty + 8 * j;
-    const long long p = p0 + tx;
-    tile[tx][ty + 8 * j] = (p < HW && c < C) ? ldf(dout + ((long long)b * C + c) * HW + p) : 0.f;
+  for (int j = 0; j < 4 * V; ++j) {
+    const int cl = ty + 8 * j, c = c0 + cl;
+    const long long p = p0 + V * tx;
+    float v[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = 0.f;
+    if (p < HW && c < C) ldv<V>(dout + ((long long)b * C + c) * HW + p, v);
+#pragma unroll
+    for (int e = 0; e < V; ++e) tile[V * tx + e][cl] = v[e];
   }
   __syncthreads();
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const long long p = p0 + ty + 8 * j;
-    const int c = c0 + tx;
+  for (int j = 0; j < 4 * V; ++j) {
+    const int pl = ty + 8 * j, c = c0 + V * tx;
+    const long long p = p0 + pl;
     if (p < HW && c < C) {
-      const float g = tile[ty + 8 * j][tx];
+      float g[V], o[V], xv[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) g[e] = tile[pl][V * tx + e];
       if (c < C1) {
-        const long long o = ((long long)b * HW + p) * C1 + c;
-        if (acc && g1p) s1 = fmaf(g, ldf(x + o), s1);
-        if (dx) stf(dx + o, g1 * g);
+        const long long off = ((long long)b * HW + p) * C1 + c;
+        if (acc && g1p) {
+          ldv<V>(x + off, xv);
+#pragma unroll
+          for (int e = 0; e < V; ++e) s1 = fmaf(g[e], xv[e], s1);
+        }
+        if (dx) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) o[e] = g1 * g[e];
+          stv<V>(dx + off, o);
+        }
       } else {
-        const long long o = ((long long)b * HW + p) * C2 + (c - C1);
-        if (acc && g2p) s2 = fmaf(g, ldf(res + o), s2);
-        if (dres) stf(dres + o, g2 * g);
+        const long long off = ((long long)b * HW + p) * C2 + (c - C1);
+        if (acc && g2p) {
+          ldv<V>(res + off, xv);
+#pragma unroll
+          for (int e = 0; e < V; ++e) s2 = fmaf(g[e], xv[e], s2);
+        }
+        if (dres) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) o[e] = g2 * g[e];
+          stv<V>(dres + off, o);
+        }
       }
     }
   }
@@ -362,13 +415,13 @@ k_plane_stats(const T* __restrict__ y, float* __restrict__ stats, long long HW, 
   const T* p = y + (long long)blockIdx.x * HW;
   const float k = ldf(p);
   float s1 = 0.f, s2 = 0.f;
-  constexpr int V = 16 / (int)sizeof(T);            // elements per 16-byte load
-  if (HW % V == 0 && ((uintptr_t)y & 15) == 0) {
-    for (long long i = (long long)threadIdx.x * V; i < HW; i += 256 * V) {
-      float v[V];
+  constexpr int VV = 16 / (int)sizeof(T);            // elements per 16-byte load
+  if (HW % VV == 0 && ((uintptr_t)y & 15) == 0) {
+    for (long long i = (long long)threadIdx.x * VV; i < HW; i += 256 * VV) {
+      float v[VV];
       ldvec(p + i, v);
 #pragma unroll
-      for (int j = 0; j < V; ++j) { const float d = v[j] - k; s1 += d; s2 = fmaf(d, d, s2); }
+      for (int j = 0; j < VV; ++j) { const float d = v[j] - k; s1 += d; s2 = fmaf(d, d, s2); }
     }
   } else {
     for (long long i = threadIdx.x; i < HW; i += 256) {
@@ -398,83 +451,108 @@ struct MixP {
   const float *stats, *scale, *shift, *alpha, *beta, *gamma;
   int act;
 };
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
 k_mix_fwd(const T* __restrict__ y, const T* __restrict__ xs, MixP m, T* __restrict__ out, int C, long long HW) {
-  __shared__ float tile[TS][TS + 1];
-  const int b = blockIdx.z, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const long long p0 = (long long)blockIdx.x * TS;
-  const int c0 = blockIdx.y * TS;
+  TILE_DECL(V)
+  const long long p0 = (long long)blockIdx.x * TSV;
   const float sc = m.scale ? *m.scale : 1.f, sh = m.shift ? *m.shift : 0.f, al = *m.alpha, be = *m.beta;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c0 + ty + 8 * j;
-    const long long p = p0 + tx;
-    float v = 0.f;
+  for (int j = 0; j < 4 * V; ++j) {
+    const int cl = ty + 8 * j, c = c0 + cl;
+    const long long p = p0 + V * tx;
+    float v[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = 0.f;
     if (p < HW && c < C) {
       const long long plane = (long long)b * C + c, o = plane * HW + p;
-      float u = ldf(y + o);
-      if (m.stats) u = sc * (u - m.stats[2 * plane]) * m.stats[2 * plane + 1] + sh;
-      if (m.act) u = gelu_f(u);
-      v = (al * u + be * ldf(xs + o)) * (m.gamma ? m.gamma[c] : 1.f);
+      float u[V], s[V];
+      ldv<V>(y + o, u);
+      ldv<V>(xs + o, s);
+      const float ga = m.gamma ? m.gamma[c] : 1.f;
+      float mean = 0.f, rstd = 1.f;
+      if (m.stats) { mean = m.stats[2 * plane]; rstd = m.stats[2 * plane + 1]; }
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        float t = u[e];
+        if (m.stats) t = sc * (t - mean) * rstd + sh;
+        if (m.act) t = gelu_f(t);
+        v[e] = (al * t + be * s[e]) * ga;
+      }
     }
-    tile[tx][ty + 8 * j] = v;
+#pragma unroll
+    for (int e = 0; e < V; ++e) tile[V * tx + e][cl] = v[e];
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const long long p = p0 + ty + 8 * j;
-    const int c = c0 + tx;
-    if (p < HW && c < C) stf(out + ((long long)b * HW + p) * C + c, tile[ty + 8 * j][tx]);
+  for (int j = 0; j < 4 * V; ++j) {
+    const int pl = ty + 8 * j, c = c0 + V * tx;
+    const long long p = p0 + pl;
+    if (p < HW && c < C) {
+      float v[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] = tile[pl][V * tx + e];
+      stv<V>(out + ((long long)b * HW + p) * C + c, v);
+    }
   }
 }
 
 // Backward, pass 1: per-plane sums  S1 = sum e, S2 = sum e n, S3 = sum dout act(u), S4 = sum dout xs   with
-// n = (y - mean) rstd (or y), u = scale n + shift, e = dout act'(u).  A CTA owns 32 channels x `nsub` pixel tiles.
-template <typename T>
+// n = (y - mean) rstd (or y), u = scale n + shift, e = dout act'(u).  A CTA owns 32 V channels x `nsub` pixel tiles.
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
 k_mix_bwd_sums(const T* __restrict__ y, const T* __restrict__ xs, MixP m, const T* __restrict__ dout, float* __restrict__ sums, int C, long long HW,
                int nsub) {
-  __shared__ float tile[TS][TS + 1];
-  const int b = blockIdx.z, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c0 = blockIdx.y * TS;
+  TILE_DECL(V)
   const float sc = m.scale ? *m.scale : 1.f, sh = m.shift ? *m.shift : 0.f;
-  float acc[4][4];
+  float acc[4 * V][4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int j = 0; j < 4 * V; ++j)
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
   for (int sub = 0; sub < nsub; ++sub) {
-    const long long p0 = ((long long)blockIdx.x * nsub + sub) * TS;
+    const long long p0 = ((long long)blockIdx.x * nsub + sub) * TSV;
     if (p0 >= HW) break;
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const long long p = p0 + ty + 8 * j;
-      const int c = c0 + tx;
-      tile[ty + 8 * j][tx] = (p < HW && c < C) ? ldf(dout + ((long long)b * HW + p) * C + c) : 0.f;
+    for (int j = 0; j < 4 * V; ++j) {
+      const int pl = ty + 8 * j, c = c0 + V * tx;
+      const long long p = p0 + pl;
+      float v[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] = 0.f;
+      if (p < HW && c < C) ldv<V>(dout + ((long long)b * HW + p) * C + c, v);
+#pragma unroll
+      for (int e = 0; e < V; ++e) tile[pl][V * tx + e] = v[e];
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = c0 + ty + 8 * j;
-      const long long p = p0 + tx;
+    for (int j = 0; j < 4 * V; ++j) {
+      const int cl = ty + 8 * j, c = c0 + cl;
+      const long long p = p0 + V * tx;
       if (p < HW && c < C) {
         const long long plane = (long long)b * C + c, o = plane * HW + p;
-        const float g = tile[tx][ty + 8 * j];
-        float n = ldf(y + o);
-        if (m.stats) n = (n - m.stats[2 * plane]) * m.stats[2 * plane + 1];
-        const float u = m.stats ? sc * n + sh : n;
-        const float e = m.act ? g * gelu_grad_f(u) : g;
-        acc[j][0] += e;
-        acc[j][1] = fmaf(e, n, acc[j][1]);
-        acc[j][2] = fmaf(g, m.act ? gelu_f(u) : u, acc[j][2]);
-        acc[j][3] = fmaf(g, ldf(xs + o), acc[j][3]);
+        float yv[V], sv[V];
+        ldv<V>(y + o, yv);
+        ldv<V>(xs + o, sv);
+        float mean = 0.f, rstd = 1.f;
+        if (m.stats) { mean = m.stats[2 * plane]; rstd = m.stats[2 * plane + 1]; }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float g = tile[V * tx + e][cl];
+          const float n = m.stats ? (yv[e] - mean) * rstd : yv[e];
+          const float u = m.stats ? sc * n + sh : n;
+          const float ee = m.act ? g * gelu_grad_f(u) : g;
+          acc[j][0] += ee;
+          acc[j][1] = fmaf(ee, n, acc[j][1]);
+          acc[j][2] = fmaf(g, m.act ? gelu_f(u) : u, acc[j][2]);
+          acc[j][3] = fmaf(g, sv[e], acc[j][3]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 4 * V; ++j) {
     const int c = c0 + ty + 8 * j;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -520,42 +598,58 @@ k_mix_bwd_final(const float* __restrict__ sums, MixP m, float* __restrict__ dsca
 }
 
 // Backward, pass 2: dy = rstd scale alpha gamma (e - S1 / HW - n S2 / HW)   (no norm: alpha gamma e),  dxs = beta gamma dout
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
 k_mix_bwd_apply(const T* __restrict__ y, MixP m, const T* __restrict__ dout, const float* __restrict__ sums, T* __restrict__ dy, T* __restrict__ dxs,
                 int C, long long HW) {
-  __shared__ float tile[TS][TS + 1];
-  const int b = blockIdx.z, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const long long p0 = (long long)blockIdx.x * TS;
-  const int c0 = blockIdx.y * TS;
+  TILE_DECL(V)
+  const long long p0 = (long long)blockIdx.x * TSV;
   const float sc = m.scale ? *m.scale : 1.f, sh = m.shift ? *m.shift : 0.f, al = *m.alpha, be = *m.beta;
   const float inv = 1.f / (float)HW;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const long long p = p0 + ty + 8 * j;
-    const int c = c0 + tx;
-    tile[ty + 8 * j][tx] = (p < HW && c < C) ? ldf(dout + ((long long)b * HW + p) * C + c) : 0.f;
+  for (int j = 0; j < 4 * V; ++j) {
+    const int pl = ty + 8 * j, c = c0 + V * tx;
+    const long long p = p0 + pl;
+    float v[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = 0.f;
+    if (p < HW && c < C) ldv<V>(dout + ((long long)b * HW + p) * C + c, v);
+#pragma unroll
+    for (int e = 0; e < V; ++e) tile[pl][V * tx + e] = v[e];
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c0 + ty + 8 * j;
-    const long long p = p0 + tx;
+  for (int j = 0; j < 4 * V; ++j) {
+    const int cl = ty + 8 * j, c = c0 + cl;
+    const long long p = p0 + V * tx;
     if (p < HW && c < C) {
       const long long plane = (long long)b * C + c, o = plane * HW + p;
-      const float g = tile[tx][ty + 8 * j], ga = m.gamma ? m.gamma[c] : 1.f;
-      if (dxs) stf(dxs + o, be * ga * g);
+      const float ga = m.gamma ? m.gamma[c] : 1.f;
+      float g[V], r[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) g[e] = tile[V * tx + e][cl];
+      if (dxs) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) r[e] = be * ga * g[e];
+        stv<V>(dxs + o, r);
+      }
       if (dy) {
-        float n = ldf(y + o), r;
+        float yv[V];
+        ldv<V>(y + o, yv);
         if (m.stats) {
-          const float rstd = m.stats[2 * plane + 1];
-          n = (n - m.stats[2 * plane]) * rstd;
-          const float e = m.act ? g * gelu_grad_f(sc * n + sh) : g;
-          r = rstd * sc * al * ga * (e - inv * sums[plane * 4] - n * inv * sums[plane * 4 + 1]);
+          const float mean = m.stats[2 * plane], rstd = m.stats[2 * plane + 1];
+          const float k = rstd * sc * al * ga, a1 = inv * sums[plane * 4], a2 = inv * sums[plane * 4 + 1];
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            const float n = (yv[e] - mean) * rstd;
+            const float ee = m.act ? g[e] * gelu_grad_f(sc * n + sh) : g[e];
+            r[e] = k * (ee - a1 - n * a2);
+          }
         } else {
-          r = al * ga * (m.act ? g * gelu_grad_f(n) : g);
+#pragma unroll
+          for (int e = 0; e < V; ++e) r[e] = al * ga * (m.act ? g[e] * gelu_grad_f(yv[e]) : g[e]);
         }
-        stf(dy + o, r);
+        stv<V>(dy + o, r);
       }
     }
   }
@@ -649,6 +743,9 @@ int adn_conv3x3_backward(const AdnConvShape* s, const void* x, const float* w, c
                              : conv_backward<bf16>(d, (const bf16*)x, w, gamma, (const bf16*)dy, (bf16*)dx, dw, dbias, dgamma, ws, st);
 }
 
+// elements per lane of the tile kernels: 2 when every row of both layouts starts on a 2-element boundary
+static inline int tile_v(int C1, int C2, long long HW) { return (C1 % 2 == 0 && C2 % 2 == 0 && HW % 2 == 0) ? 2 : 1; }
+
 static int plane_check(int32_t B, int32_t C, int64_t HW, int32_t dtype, const char* what) {
   ADN_REQUIRE(B > 0 && C > 0 && HW > 0 && B <= 65535 && (long long)B * C * HW < (1LL << 40), ADN_ERR_SHAPE, "%s: bad extents (%d, %d, %lld)", what, B, C, (long long)HW);
   ADN_REQUIRE(dtype == ADN_F32 || dtype == ADN_BF16, ADN_ERR_DTYPE, "%s: unsupported dtype %d", what, dtype);
@@ -661,10 +758,13 @@ int adn_nchw_pack_forward(const void* x, const void* res, const float* g1, const
   if (rc) return rc;
   ADN_REQUIRE(x && out && C1 > 0 && C2 >= 0 && (C2 == 0 || res), ADN_ERR_NULL, "adn_nchw_pack_forward: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid(cdiv(HW, TS), cdiv(C1 + C2, TS), B);
+  const int V = tile_v(C1, C2, HW);
+  dim3 grid(cdiv(HW, 32 * V), cdiv(C1 + C2, 32 * V), B);
   ADN_KERNEL("k_pack_fwd", st);
-  if (dtype == ADN_F32) k_pack_fwd<float><<<grid, 256, 0, st>>>((const float*)x, C1, (const float*)res, C2, g1, g2, (float*)out, HW);
-  else k_pack_fwd<bf16><<<grid, 256, 0, st>>>((const bf16*)x, C1, (const bf16*)res, C2, g1, g2, (bf16*)out, HW);
+#define PACK_FWD(T, VV) k_pack_fwd<T, VV><<<grid, 256, 0, st>>>((const T*)x, C1, (const T*)res, C2, g1, g2, (T*)out, HW)
+  if (dtype == ADN_F32) { if (V == 2) PACK_FWD(float, 2); else PACK_FWD(float, 1); }
+  else { if (V == 2) PACK_FWD(bf16, 2); else PACK_FWD(bf16, 1); }
+#undef PACK_FWD
   ADN_CHECK_LAUNCH();
   return ADN_OK;
 }
@@ -678,13 +778,14 @@ int adn_nchw_pack_backward(const void* x, const void* res, const float* g1, cons
   cudaStream_t st = (cudaStream_t)stream;
   double* acc = (dg1 || dg2) ? (double*)ws : nullptr;
   if (acc) ADN_CHECK_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
-  dim3 grid(cdiv(HW, TS), cdiv(C1 + C2, TS), B);
+  const int V = tile_v(C1, C2, HW);
+  dim3 grid(cdiv(HW, 32 * V), cdiv(C1 + C2, 32 * V), B);
   {
     ADN_KERNEL("k_pack_bwd", st);
-    if (dtype == ADN_F32)
-      k_pack_bwd<float><<<grid, 256, 0, st>>>((const float*)x, C1, (const float*)res, C2, g1, g2, (const float*)dout, (float*)dx, (float*)dres, acc, HW);
-    else
-      k_pack_bwd<bf16><<<grid, 256, 0, st>>>((const bf16*)x, C1, (const bf16*)res, C2, g1, g2, (const bf16*)dout, (bf16*)dx, (bf16*)dres, acc, HW);
+#define PACK_BWD(T, VV) k_pack_bwd<T, VV><<<grid, 256, 0, st>>>((const T*)x, C1, (const T*)res, C2, g1, g2, (const T*)dout, (T*)dx, (T*)dres, acc, HW)
+    if (dtype == ADN_F32) { if (V == 2) PACK_BWD(float, 2); else PACK_BWD(float, 1); }
+    else { if (V == 2) PACK_BWD(bf16, 2); else PACK_BWD(bf16, 1); }
+#undef PACK_BWD
   }
   if (acc) { ADN_KERNEL("k_store_acc", st); k_store_acc<<<1, 32, 0, st>>>(acc, dg1, dg2); }
   ADN_CHECK_LAUNCH();
@@ -712,10 +813,13 @@ int adn_plane_mix_forward(const void* y, const void* xs, const float* stats, con
   ADN_REQUIRE(act == 0 || act == 1, ADN_ERR_SHAPE, "adn_plane_mix_forward: act must be 0 (none) or 1 (GELU)");
   cudaStream_t st = (cudaStream_t)stream;
   MixP m{stats, scale, shift, alpha, beta, gamma, act};
-  dim3 grid(cdiv(HW, TS), cdiv(C, TS), B);
+  const int V = tile_v(C, 0, HW);
+  dim3 grid(cdiv(HW, 32 * V), cdiv(C, 32 * V), B);
   ADN_KERNEL("k_mix_fwd", st);
-  if (dtype == ADN_F32) k_mix_fwd<float><<<grid, 256, 0, st>>>((const float*)y, (const float*)xs, m, (float*)out, C, HW);
-  else k_mix_fwd<bf16><<<grid, 256, 0, st>>>((const bf16*)y, (const bf16*)xs, m, (bf16*)out, C, HW);
+#define MIX_FWD(T, VV) k_mix_fwd<T, VV><<<grid, 256, 0, st>>>((const T*)y, (const T*)xs, m, (T*)out, C, HW)
+  if (dtype == ADN_F32) { if (V == 2) MIX_FWD(float, 2); else MIX_FWD(float, 1); }
+  else { if (V == 2) MIX_FWD(bf16, 2); else MIX_FWD(bf16, 1); }
+#undef MIX_FWD
   ADN_CHECK_LAUNCH();
   return ADN_OK;
 }
@@ -738,17 +842,23 @@ int adn_plane_mix_backward(const void* y, const void* xs, const float* stats, co
   MixP m{stats, scale, shift, alpha, beta, gamma, act};
   float* sums = (float*)ws;
   ADN_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * C * 4 * sizeof(float), st));
-  const int nsub = 8;
-  dim3 g1(cdiv(HW, (long long)TS * nsub), cdiv(C, TS), B), g2(cdiv(HW, TS), cdiv(C, TS), B);
-  if (dtype == ADN_F32) {
-    { ADN_KERNEL("k_mix_bwd_sums", st); k_mix_bwd_sums<float><<<g1, 256, 0, st>>>((const float*)y, (const float*)xs, m, (const float*)dout, sums, C, HW, nsub); }
-    { ADN_KERNEL("k_mix_bwd_final", st); k_mix_bwd_final<<<1, 256, 0, st>>>(sums, m, dscal, gamma ? dgamma : nullptr, B, C); }
-    if (dy || dxs) { ADN_KERNEL("k_mix_bwd_apply", st); k_mix_bwd_apply<float><<<g2, 256, 0, st>>>((const float*)y, m, (const float*)dout, sums, (float*)dy, (float*)dxs, C, HW); }
-  } else {
-    { ADN_KERNEL("k_mix_bwd_sums", st); k_mix_bwd_sums<bf16><<<g1, 256, 0, st>>>((const bf16*)y, (const bf16*)xs, m, (const bf16*)dout, sums, C, HW, nsub); }
-    { ADN_KERNEL("k_mix_bwd_final", st); k_mix_bwd_final<<<1, 256, 0, st>>>(sums, m, dscal, gamma ? dgamma : nullptr, B, C); }
-    if (dy || dxs) { ADN_KERNEL("k_mix_bwd_apply", st); k_mix_bwd_apply<bf16><<<g2, 256, 0, st>>>((const bf16*)y, m, (const bf16*)dout, sums, (bf16*)dy, (bf16*)dxs, C, HW); }
+  const int nsub = 8, V = tile_v(C, 0, HW);
+  dim3 g1(cdiv(HW, (long long)32 * V * nsub), cdiv(C, 32 * V), B), g2(cdiv(HW, 32 * V), cdiv(C, 32 * V), B);
+#define MIX_SUMS(T, VV) k_mix_bwd_sums<T, VV><<<g1, 256, 0, st>>>((const T*)y, (const T*)xs, m, (const T*)dout, sums, C, HW, nsub)
+#define MIX_APPLY(T, VV) k_mix_bwd_apply<T, VV><<<g2, 256, 0, st>>>((const T*)y, m, (const T*)dout, sums, (T*)dy, (T*)dxs, C, HW)
+  {
+    ADN_KERNEL("k_mix_bwd_sums", st);
+    if (dtype == ADN_F32) { if (V == 2) MIX_SUMS(float, 2); else MIX_SUMS(float, 1); }
+    else { if (V == 2) MIX_SUMS(bf16, 2); else MIX_SUMS(bf16, 1); }
   }
+  { ADN_KERNEL("k_mix_bwd_final", st); k_mix_bwd_final<<<1, 256, 0, st>>>(sums, m, dscal, gamma ? dgamma : nullptr, B, C); }
+  if (dy || dxs) {
+    ADN_KERNEL("k_mix_bwd_apply", st);
+    if (dtype == ADN_F32) { if (V == 2) MIX_APPLY(float, 2); else MIX_APPLY(float, 1); }
+    else { if (V == 2) MIX_APPLY(bf16, 2); else MIX_APPLY(bf16, 1); }
+  }
+#undef MIX_SUMS
+#undef MIX_APPLY
   ADN_CHECK_LAUNCH();
   return ADN_OK;
 }

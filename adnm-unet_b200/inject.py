@@ -1,13 +1,15 @@
 """Make the unmodified reference network use the B200 kernels: rebind the module globals the reference resolves at
 construction time: `models.ADNMUNet.Mamba2` (looked up inside `create_block`, models/ADNMUNet.py:277),
 `models.model_untils.WTConv2d` (models/model_untils.py:17,101) and - for the fused Block - the names
-`Block` / `RMSNorm` that `create_block` resolves (models/ADNMUNet.py:278-291).  No reference file is edited; call this
-before `create_ADNMUNet(...)`."""
+`Block` / `RMSNorm` that `create_block` resolves (models/ADNMUNet.py:278-291) and - for the conv stages -
+the names `WTLayer` / `PatchEmbed` / `OutProj` that `Encoder` / `Decoder` / `Refiner` resolve (models/ADNMUNet.py:369-397,
+542-567,702-709; star-imported from models.model_untils at :33).  No reference file is edited; call this before
+`create_ADNMUNet(...)`."""
 import importlib
 
 
 def install_into_reference(adnmunet_module="models.ADNMUNet", untils_module="models.model_untils",
-                           mixer=True, wtconv=True, block=True):
+                           mixer=True, wtconv=True, block=True, stages=True):
     from adnm_unet_b200.mixer import Mamba2
     from adnm_unet_b200.wtconv import WTConv2d
     done = []
@@ -29,4 +31,10 @@ def install_into_reference(adnmunet_module="models.ADNMUNet", untils_module="mod
         importlib.import_module(untils_module).FeedForward = FeedForward      # the FeedForwards of the EncoderToDecoder bridges
         done += [adnmunet_module + ".Block", adnmunet_module + ".RMSNorm", adnmunet_module + ".StandardAttention",
                  untils_module + ".FeedForward"]
+    if stages and wtconv:
+        from adnm_unet_b200 import convstage
+        m = importlib.import_module(adnmunet_module)
+        for n in ("WTLayer", "PatchEmbed", "OutProj"):
+            setattr(m, n, getattr(convstage, n))
+            done.append(adnmunet_module + "." + n)
     return done

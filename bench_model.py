@@ -33,7 +33,7 @@ def _host_note(variant):
     if variant != "dropin":
         return "the unmodified reference network (baseline/_ref), eager PyTorch"
     dead = os.environ.get("ADNM_KEEP_DEAD_BRIDGES", "0") != "1"
-    return ("unmodified reference network with Mamba2 / WTConv2d / Block / RMSNorm / FeedForward / StandardAttention bound to the "
+    return ("unmodified reference network with Mamba2 / WTConv2d / Block / RMSNorm / FeedForward / StandardAttention / WTLayer / PatchEmbed / OutProj bound to the "
             "sm_100a modules" + ("; the four EncoderToDecoder bridges whose outputs never reach the network output (e2ds[3..6]) "
                                  "are skipped - bit-identical outputs and gradients, refhost.prune_dead_bridges" if dead else ""))
 
