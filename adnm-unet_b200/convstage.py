@@ -19,6 +19,7 @@ import math
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from adnm_unet_b200 import _lib
 from adnm_unet_b200.block import Swish, linear_tokens
@@ -464,8 +465,16 @@ class OutProj(nn.Module):
         xs = pack_planes(x, h, w)
         t = self.wtconv.mix(xs, self.alpha, self.beta)                       # alpha GELU(scale IN(wtconv(x)) + shift) + beta shortcut
         t = self.conv[0].forward_tokens(t, h, w, gamma=self.gamma)           # x.mul(gamma) folded into the conv weights
-        t = self.conv[1].forward_tokens(t, h, w)
+        # The frame tensor has num_frames (20) channels: its rows are not whole 16-byte pieces.  The 1 x 1 conv writes it with
+        # the channel count rounded up to 8 (zero weight rows -> zero channels, GELU(0) = 0) and conv2 reads it through weights
+        # zero-padded over the input channels, so both stay on the tensor-core paths; the pads are tiny tensor ops on the weights.
+        c1, c2 = self.conv[1].conv, self.conv2.conv
+        nf = c1.out_channels
+        pad = (-nf) % 8
+        w1 = c1.weight.view(nf, c1.in_channels)
+        t = gelu_tokens(linear_tokens(t, F.pad(w1, (0, 0, 0, pad)) if pad else w1, None))
         if residual is not None:
             t = self.alpha1 * t + self.alpha2 * residual.reshape(b, l, 1).to(t.dtype)
-        t = self.conv2.forward_tokens(t, h, w)
+        t = conv3x3_tokens(t, h, w, F.pad(c2.weight, (0, 0, 0, 0, 0, pad)) if pad else c2.weight, c2.bias)
+        t = swish_tokens(t, self.conv2.act.beta) if self.conv2.act_kind == ACT_SWISH else gelu_tokens(t)
         return pack_planes(t, h, w)

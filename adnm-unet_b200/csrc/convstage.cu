@@ -37,7 +37,10 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 
 // ================================================================ dense 3x3 convolution
 struct ConvDims {
-  int B, H, W, Cin, Cout, cpi, cpo;      // cpi / cpo: channels rounded up to 64 (one swizzle group per tap chunk)
+  int B, H, W, Cin, Cout;
+  int ci8, co8;          // channel counts rounded up to 8: the tensor-core path needs 16-byte rows; thin tensors (PatchEmbed 5 -> 32,
+                         // OutProj 20 -> 20) are copied into zero-padded rows in the workspace on the way in and compacted on the way out
+  int cpi, cpo;          // channels rounded up to 64 (one swizzle group per tap chunk)
   long long T;
   bool tc;
 };
@@ -47,16 +50,18 @@ static int conv_dims(const AdnConvShape* s, ConvDims* d, const char* what) {
   ADN_REQUIRE(s->B > 0 && s->H > 0 && s->W > 0 && s->Cin > 0 && s->Cout > 0, ADN_ERR_SHAPE, "%s: bad extents", what);
   ADN_REQUIRE(s->dtype == ADN_F32 || s->dtype == ADN_BF16, ADN_ERR_DTYPE, "%s: unsupported dtype %d", what, s->dtype);
   d->B = s->B; d->H = s->H; d->W = s->W; d->Cin = s->Cin; d->Cout = s->Cout;
+  d->ci8 = (s->Cin + 7) / 8 * 8; d->co8 = (s->Cout + 7) / 8 * 8;
   d->cpi = (s->Cin + 63) / 64 * 64; d->cpo = (s->Cout + 63) / 64 * 64;
   d->T = (long long)s->B * s->H * s->W;
   ADN_REQUIRE(d->T < (1LL << 31) / 16, ADN_ERR_SHAPE, "%s: too many tokens", what);
-  d->tc = s->dtype == ADN_BF16 && s->Cin % 8 == 0 && s->Cout % 8 == 0 && s->Cin <= 256 && s->Cout <= 256 && tcg::image_tiles(s->H, s->W) && env().wide;
+  d->tc = s->dtype == ADN_BF16 && s->Cin <= 256 && s->Cout <= 256 && tcg::image_tiles(s->H, s->W) && env().wide;
   return ADN_OK;
 }
 
-// workspace layout (both passes): [status 256 B][Wf bf16 Cout x 9 cpi][Wd bf16 Cin x 9 cpo][dWt fp32 Cout x 9 cpi]
+// workspace layout (both passes): [status 256 B][Wf bf16 co8 x 9 cpi][Wd bf16 ci8 x 9 cpo][dWt fp32 co8 x 9 cpi][bias fp32 co8]
+//                                 [xp bf16 T x ci8][yp bf16 T x co8][dxp bf16 T x ci8]   (the last three only for padded channel counts)
 struct ConvWs {
-  int* status; bf16* Wf; bf16* Wd; float* dWt;
+  int* status; bf16* Wf; bf16* Wd; float* dWt; float* biasp; bf16 *xp, *yp, *dxp;
   size_t bytes;
 };
 static ConvWs conv_ws(const ConvDims& d, void* base) {
@@ -64,26 +69,48 @@ static ConvWs conv_ws(const ConvDims& d, void* base) {
   char* p = (char*)base;
   size_t off = 0;
   w.status = (int*)(p + off); off += 256;
-  w.Wf = (bf16*)(p + off); off += align_up((size_t)d.Cout * 9 * d.cpi * sizeof(bf16), 256);
-  w.Wd = (bf16*)(p + off); off += align_up((size_t)d.Cin * 9 * d.cpo * sizeof(bf16), 256);
-  w.dWt = (float*)(p + off); off += align_up((size_t)d.Cout * 9 * d.cpi * sizeof(float), 256);
+  w.Wf = (bf16*)(p + off); off += align_up((size_t)d.co8 * 9 * d.cpi * sizeof(bf16), 256);
+  w.Wd = (bf16*)(p + off); off += align_up((size_t)d.ci8 * 9 * d.cpo * sizeof(bf16), 256);
+  w.dWt = (float*)(p + off); off += align_up((size_t)d.co8 * 9 * d.cpi * sizeof(float), 256);
+  w.biasp = (float*)(p + off); off += align_up((size_t)d.co8 * sizeof(float), 256);
+  w.xp = w.yp = w.dxp = nullptr;
+  if (d.tc && d.ci8 != d.Cin) {
+    w.xp = (bf16*)(p + off); off += align_up((size_t)d.T * d.ci8 * sizeof(bf16), 256);
+    w.dxp = (bf16*)(p + off); off += align_up((size_t)d.T * d.ci8 * sizeof(bf16), 256);
+  }
+  if (d.tc && d.co8 != d.Cout) { w.yp = (bf16*)(p + off); off += align_up((size_t)d.T * d.co8 * sizeof(bf16), 256); }
   w.bytes = off;
   return w;
 }
 
-// weight images of the implicit GEMMs from the state_dict layout w[Cout][Cin][3][3] (gamma folded in, pad channels zero)
-__global__ void k_conv_wprep(const float* __restrict__ w, const float* __restrict__ gamma, bf16* __restrict__ Wf, bf16* __restrict__ Wd,
-                             int Cin, int Cout, int cpi, int cpo) {
-  const int nf = Cout * 9 * cpi, nd = Cin * 9 * cpo;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += gridDim.x * blockDim.x) {
+// dst[t][0 .. Cd) = src[t][0 .. min(Cs, Cd)), zero beyond Cs: pads thin rows to whole 16-byte pieces / compacts them again
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_copy_rows(const T* __restrict__ src, int Cs, T* __restrict__ dst, int Cd, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long t = i / Cd;
+    const int c = (int)(i - t * Cd);
+    dst[i] = c < Cs ? src[t * Cs + c] : T(0.f);
+  }
+}
+
+// weight images of the implicit GEMMs from the state_dict layout w[Cout][Cin][3][3] (gamma folded in, pad rows / channels zero)
+__global__ void k_conv_wprep(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ bias, bf16* __restrict__ Wf,
+                             bf16* __restrict__ Wd, float* __restrict__ biasp, int Cin, int Cout, int ci8, int co8, int cpi, int cpo) {
+  const int nf = co8 * 9 * cpi, nd = ci8 * 9 * cpo;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd + co8; i += gridDim.x * blockDim.x) {
     if (i < nf) {
       const int co = i / (9 * cpi), r = i - co * 9 * cpi, t = r / cpi, ci = r - t * cpi;
-      const float v = ci < Cin ? w[((long long)co * Cin + ci) * 9 + t] * (gamma ? gamma[ci] : 1.f) : 0.f;
+      const float v = (ci < Cin && co < Cout) ? w[((long long)co * Cin + ci) * 9 + t] * (gamma ? gamma[ci] : 1.f) : 0.f;
       Wf[i] = __float2bfloat16_rn(v);
-    } else {
+    } else if (i < nf + nd) {
       const int j = i - nf, ci = j / (9 * cpo), r = j - ci * 9 * cpo, t = r / cpo, co = r - t * cpo;
-      const float v = co < Cout ? w[((long long)co * Cin + ci) * 9 + (8 - t)] * (gamma ? gamma[ci] : 1.f) : 0.f;
+      const float v = (co < Cout && ci < Cin) ? w[((long long)co * Cin + ci) * 9 + (8 - t)] * (gamma ? gamma[ci] : 1.f) : 0.f;
       Wd[j] = __float2bfloat16_rn(v);
+    } else {
+      const int co = i - nf - nd;
+      biasp[co] = (bias && co < Cout) ? bias[co] : 0.f;
     }
   }
 }
@@ -196,17 +223,33 @@ __global__ void k_poison_if(const int* __restrict__ status, T* __restrict__ out,
   if (*status != 0 && threadIdx.x < n) stf(out + threadIdx.x, __int_as_float(0x7fc00000));
 }
 
+static inline void launch_wprep(const ConvDims& d, const ConvWs& ws, const float* w, const float* gamma, const float* bias, cudaStream_t st) {
+  ADN_KERNEL("k_conv_wprep", st);
+  k_conv_wprep<<<ew_grid((long long)d.co8 * 9 * d.cpi + (long long)d.ci8 * 9 * d.cpo + d.co8), 256, 0, st>>>(
+      w, gamma, bias, ws.Wf, ws.Wd, ws.biasp, d.Cin, d.Cout, d.ci8, d.co8, d.cpi, d.cpo);
+}
+template <typename T>
+static inline void launch_copy_rows(const T* src, int Cs, T* dst, int Cd, long long Ttok, cudaStream_t st) {
+  ADN_KERNEL("k_copy_rows", st);
+  k_copy_rows<T><<<ew_grid(Ttok * Cd), 256, 0, st>>>(src, Cs, dst, Cd, Ttok * Cd);
+}
+
 template <typename T>
 static int conv_forward(const ConvDims& d, const T* x, const float* w, const float* bias, const float* gamma, T* y, void* wsp, cudaStream_t st) {
   ConvWs ws = conv_ws(d, wsp);
   if (d.tc) {
     using namespace tcg;
     ADN_CHECK_CUDA(cudaMemsetAsync(ws.status, 0, 256, st));
-    { ADN_KERNEL("k_conv_wprep", st); k_conv_wprep<<<ew_grid((long long)d.Cout * 9 * d.cpi + (long long)d.Cin * 9 * d.cpo), 256, 0, st>>>(w, gamma, ws.Wf, ws.Wd, d.Cin, d.Cout, d.cpi, d.cpo); }
-    int rc = gemm(st, "conv3x3_fwd", (int)d.T, d.Cout, 9 * d.cpi, kmaj((const bf16*)x, d.Cin), kmaj(ws.Wf, 9 * d.cpi), 0, NOOP, NOOP,
-                  Out{y, d.Cout, 0, C_BF16}, 1, 1, nullptr, 0, ws.status, NOAUX, bias, Conv{1, d.W, d.H, d.cpi},
-                  Image{(const bf16*)x, d.B, d.H, d.W, d.Cin});
+    launch_wprep(d, ws, w, gamma, bias, st);
+    const bf16* xe = (const bf16*)x;
+    bf16* ye = (bf16*)y;
+    if (ws.xp) { launch_copy_rows<bf16>((const bf16*)x, d.Cin, ws.xp, d.ci8, d.T, st); xe = ws.xp; }
+    if (ws.yp) ye = ws.yp;
+    int rc = gemm(st, "conv3x3_fwd", (int)d.T, d.co8, 9 * d.cpi, kmaj(xe, d.ci8), kmaj(ws.Wf, 9 * d.cpi), 0, NOOP, NOOP,
+                  Out{ye, d.co8, 0, C_BF16}, 1, 1, nullptr, 0, ws.status, NOAUX, bias ? ws.biasp : nullptr, Conv{1, d.W, d.H, d.cpi, 0},
+                  Image{xe, d.B, d.H, d.W, d.ci8});
     if (rc) return rc;
+    if (ws.yp) launch_copy_rows<bf16>(ws.yp, d.co8, (bf16*)y, d.Cout, d.T, st);
     { ADN_KERNEL("k_poison_if", st); k_poison_if<T><<<1, 32, 0, st>>>(ws.status, y, 4); }
   } else {
     const long long n = d.T * d.Cout;
@@ -222,24 +265,29 @@ static int conv_backward(const ConvDims& d, const T* x, const float* w, const fl
                          float* dgamma, void* wsp, cudaStream_t st) {
   ConvWs ws = conv_ws(d, wsp);
   ADN_CHECK_CUDA(cudaMemsetAsync(ws.status, 0, 256, st));
-  ADN_CHECK_CUDA(cudaMemsetAsync(ws.dWt, 0, (size_t)d.Cout * 9 * d.cpi * sizeof(float), st));
+  ADN_CHECK_CUDA(cudaMemsetAsync(ws.dWt, 0, (size_t)d.co8 * 9 * d.cpi * sizeof(float), st));
   if (dgamma) ADN_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)d.Cin * sizeof(float), st));
   if (dbias) ADN_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)d.Cout * sizeof(float), st));
   if (d.tc) {
     using namespace tcg;
     int rc = ADN_OK;
+    const bf16 *xe = (const bf16*)x, *dye = (const bf16*)dy;
+    if (ws.xp) { launch_copy_rows<bf16>((const bf16*)x, d.Cin, ws.xp, d.ci8, d.T, st); xe = ws.xp; }
+    if (ws.yp) { launch_copy_rows<bf16>((const bf16*)dy, d.Cout, ws.yp, d.co8, d.T, st); dye = ws.yp; }
     if (dx) {
-      { ADN_KERNEL("k_conv_wprep", st); k_conv_wprep<<<ew_grid((long long)d.Cout * 9 * d.cpi + (long long)d.Cin * 9 * d.cpo), 256, 0, st>>>(w, gamma, ws.Wf, ws.Wd, d.Cin, d.Cout, d.cpi, d.cpo); }
-      rc = gemm(st, "conv3x3_dgrad", (int)d.T, d.Cin, 9 * d.cpo, kmaj((const bf16*)dy, d.Cout), kmaj(ws.Wd, 9 * d.cpo), 0, NOOP, NOOP,
-                Out{dx, d.Cin, 0, C_BF16}, 1, 1, nullptr, 0, ws.status, NOAUX, nullptr, Conv{1, d.W, d.H, d.cpo},
-                Image{(const bf16*)dy, d.B, d.H, d.W, d.Cout});
+      launch_wprep(d, ws, w, gamma, nullptr, st);
+      bf16* dxe = ws.dxp ? ws.dxp : (bf16*)dx;
+      rc = gemm(st, "conv3x3_dgrad", (int)d.T, d.ci8, 9 * d.cpo, kmaj(dye, d.co8), kmaj(ws.Wd, 9 * d.cpo), 0, NOOP, NOOP,
+                Out{dxe, d.ci8, 0, C_BF16}, 1, 1, nullptr, 0, ws.status, NOAUX, nullptr, Conv{1, d.W, d.H, d.cpo, 0},
+                Image{dye, d.B, d.H, d.W, d.co8});
       if (rc) return rc;
+      if (ws.dxp) launch_copy_rows<bf16>(ws.dxp, d.ci8, (bf16*)dx, d.Cin, d.T, st);
     }
-    const int N = 9 * d.cpi;
-    const int splitk = pick_splitk(cdiv(d.Cout, BM) * cdiv(N, pick_bn(N, 1)), (int)d.T);
-    rc = gemm(st, "conv3x3_wgrad", d.Cout, N, (int)d.T, mnmaj((const bf16*)dy, d.Cout), mnmaj((const bf16*)x, d.Cin), 0, NOOP, NOOP,
-              Out{ws.dWt, N, 0, C_ATOMIC_F32}, 1, splitk, nullptr, 0, ws.status, NOAUX, nullptr, Conv{2, d.W, d.H, d.cpi},
-              Image{(const bf16*)x, d.B, d.H, d.W, d.Cin});
+    const int N = 9 * d.cpi, bn = N >= 256 ? 256 : 0;
+    const int splitk = pick_splitk(cdiv(d.co8, BM) * cdiv(N, bn ? bn : pick_bn(N, 1)), (int)d.T);
+    rc = gemm(st, "conv3x3_wgrad", d.co8, N, (int)d.T, mnmaj(dye, d.co8), mnmaj(xe, d.ci8), 0, NOOP, NOOP,
+              Out{ws.dWt, N, 0, C_ATOMIC_F32}, 1, splitk, nullptr, 0, ws.status, NOAUX, nullptr, Conv{2, d.W, d.H, d.cpi, bn},
+              Image{xe, d.B, d.H, d.W, d.ci8});
     if (rc) return rc;
   } else {
     if (dx) {
@@ -656,34 +704,51 @@ k_mix_bwd_apply(const T* __restrict__ y, MixP m, const T* __restrict__ dout, con
 }
 
 // ---- activations after the convs: kind 1 GELU (erf form, nn.GELU default), kind 2 Swish x sigmoid(beta x) (model_untils.py:162-169)
+// 16-byte accesses (8 bf16 / 4 fp32 per thread and step); the tail of a length that is not a multiple runs element-wise.
+__device__ __forceinline__ void stvec(float* p, const float (&v)[4]) { st4(p, v); }
+__device__ __forceinline__ void stvec(bf16* p, const float (&v)[8]) { *reinterpret_cast<uint4*>(p) = sm100::pack8(v); }
+__device__ __forceinline__ float act_f(float v, int kind, float be) { return kind == 1 ? gelu_f(v) : v / (1.f + expf(-be * v)); }
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_act_fwd(const T* __restrict__ x, T* __restrict__ y, long long n, int kind, const float* __restrict__ betap) {
+  constexpr int VV = 16 / (int)sizeof(T);
   const float be = betap ? *betap : 1.f;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float v = ldf(x + i);
-    stf(y + i, kind == 1 ? gelu_f(v) : v / (1.f + expf(-be * v)));
+  const long long stride = (long long)gridDim.x * blockDim.x, nv = n / VV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    float v[VV];
+    ldvec(x + i * VV, v);
+#pragma unroll
+    for (int j = 0; j < VV; ++j) v[j] = act_f(v[j], kind, be);
+    stvec(y + i * VV, v);
   }
+  for (long long i = nv * VV + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) stf(y + i, act_f(ldf(x + i), kind, be));
+}
+__device__ __forceinline__ float act_bwd_f(float v, float g, int kind, float be, float& db) {
+  if (kind == 1) return g * gelu_grad_f(v);
+  const float s = 1.f / (1.f + expf(-be * v)), ds = s * (1.f - s);
+  db = fmaf(g, v * v * ds, db);
+  return g * (s + v * be * ds);
 }
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_act_bwd(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long long n, int kind, const float* __restrict__ betap,
           double* __restrict__ dbeta_acc) {
   __shared__ float red[8];
+  constexpr int VV = 16 / (int)sizeof(T);
   const float be = betap ? *betap : 1.f;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long stride = (long long)gridDim.x * blockDim.x, nv = n / VV;
   float db = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float v = ldf(x + i), g = ldf(dy + i);
-    if (kind == 1) {
-      stf(dx + i, g * gelu_grad_f(v));
-    } else {
-      const float s = 1.f / (1.f + expf(-be * v)), ds = s * (1.f - s);
-      stf(dx + i, g * (s + v * be * ds));
-      db = fmaf(g, v * v * ds, db);
-    }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    float v[VV], g[VV];
+    ldvec(x + i * VV, v);
+    ldvec(dy + i * VV, g);
+#pragma unroll
+    for (int j = 0; j < VV; ++j) v[j] = act_bwd_f(v[j], g[j], kind, be, db);
+    stvec(dx + i * VV, v);
   }
+  for (long long i = nv * VV + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    stf(dx + i, act_bwd_f(ldf(x + i), ldf(dy + i), kind, be, db));
   if (dbeta_acc) {
     db = warp_sum(db);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = db;
@@ -869,8 +934,9 @@ int adn_act_forward(const void* x, void* y, int64_t n, int32_t kind, const float
   ADN_REQUIRE(dtype == ADN_F32 || dtype == ADN_BF16, ADN_ERR_DTYPE, "adn_act_forward: unsupported dtype %d", dtype);
   cudaStream_t st = (cudaStream_t)stream;
   ADN_KERNEL("k_act_fwd", st);
-  if (dtype == ADN_F32) k_act_fwd<float><<<ew_grid(n), 256, 0, st>>>((const float*)x, (float*)y, n, kind, beta);
-  else k_act_fwd<bf16><<<ew_grid(n), 256, 0, st>>>((const bf16*)x, (bf16*)y, n, kind, beta);
+  ADN_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 15) == 0, ADN_ERR_SHAPE, "adn_act_forward: buffers must be 16-byte aligned");
+  if (dtype == ADN_F32) k_act_fwd<float><<<ew_grid(n / 4 + 1), 256, 0, st>>>((const float*)x, (float*)y, n, kind, beta);
+  else k_act_fwd<bf16><<<ew_grid(n / 8 + 1), 256, 0, st>>>((const bf16*)x, (bf16*)y, n, kind, beta);
   ADN_CHECK_LAUNCH();
   return ADN_OK;
 }
@@ -880,14 +946,15 @@ int adn_act_backward(const void* x, const void* dy, void* dx, int64_t n, int32_t
                      void* stream) {
   ADN_REQUIRE(x && dy && dx && ws, ADN_ERR_NULL, "adn_act_backward: NULL argument");
   ADN_REQUIRE(n > 0 && (kind == 1 || kind == 2), ADN_ERR_SHAPE, "adn_act_backward: kind must be 1 (GELU) or 2 (Swish)");
+  ADN_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0, ADN_ERR_SHAPE, "adn_act_backward: buffers must be 16-byte aligned");
   ADN_REQUIRE(dtype == ADN_F32 || dtype == ADN_BF16, ADN_ERR_DTYPE, "adn_act_backward: unsupported dtype %d", dtype);
   cudaStream_t st = (cudaStream_t)stream;
   double* acc = (kind == 2 && dbeta) ? (double*)ws : nullptr;
   if (acc) ADN_CHECK_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
   {
     ADN_KERNEL("k_act_bwd", st);
-    if (dtype == ADN_F32) k_act_bwd<float><<<ew_grid(n), 256, 0, st>>>((const float*)x, (const float*)dy, (float*)dx, n, kind, beta, acc);
-    else k_act_bwd<bf16><<<ew_grid(n), 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, n, kind, beta, acc);
+    if (dtype == ADN_F32) k_act_bwd<float><<<ew_grid(n / 4 + 1), 256, 0, st>>>((const float*)x, (const float*)dy, (float*)dx, n, kind, beta, acc);
+    else k_act_bwd<bf16><<<ew_grid(n / 8 + 1), 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, n, kind, beta, acc);
   }
   if (acc) { ADN_KERNEL("k_store_acc", st); k_store_acc<<<1, 32, 0, st>>>(acc, dbeta, nullptr); }
   ADN_CHECK_LAUNCH();

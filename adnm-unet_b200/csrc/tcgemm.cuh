@@ -56,8 +56,10 @@ struct Conv {
   int mode;          // 0: plain GEMM; 1: operand A is the image (K-major); 2: operand B is the image (MN-major)
   int W, H;          // image size; L = W * H tokens per sample
   int cpad;          // image channels rounded up to 64: tap t owns k (mode 1) / n (mode 2) range [t * cpad, (t + 1) * cpad)
+  int bn;            // tile width override (0: pick_bn).  The weight gradient is bound by the number of k-tile hand-offs per CTA
+                     // (the token reduction is long, the tiles are few): 256-wide tiles even when the last one is mostly padding
 };
-static const Conv NOCONV = Conv{0, 0, 0, 0};
+static const Conv NOCONV = Conv{0, 0, 0, 0, 0};
 
 struct Args {
   Seg seg[2];
@@ -424,7 +426,7 @@ static int gemm(cudaStream_t st, const char* name, int M, int N, int K0, Op A0, 
   a.seg[0] = Seg{A0.p, A0.ld, A0.bs, B0.p, B0.ld, B0.bs, K0};
   a.seg[1] = Seg{A1.p, A1.ld, A1.bs, B1.p, B1.ld, B1.bs, K1};
   a.nseg = K1 > 0 ? 2 : 1;
-  a.M = M; a.N = N; a.BN = pick_bn(N, B0.mn);
+  a.M = M; a.N = N; a.BN = conv.bn > 0 ? conv.bn : pick_bn(N, B0.mn);
   a.a_mn = A0.mn; a.b_mn = B0.mn;
   a.C = C.p; a.ldc = C.ld; a.c_bs = C.bs; a.c_mode = C.mode;
   a.alpha = alpha; a.parity_mask = parity_mask;

@@ -190,7 +190,9 @@ def test_convstage_entry_points_validate_on_the_host(lib):
     ok = _lib.AdnConvShape(B=32, H=128, W=128, Cin=64, Cout=32, dtype=_lib.ADN_BF16)
     assert lib.adn_conv3x3_workspace_bytes(ok, nb) == 0 and nb.value >= 32 * 9 * 64 * (2 + 4) + 64 * 9 * 64 * 2
     assert lib.adn_conv3x3_path(ok) == 1                                    # tcgen05 implicit GEMM
-    assert lib.adn_conv3x3_path(_lib.AdnConvShape(B=32, H=128, W=128, Cin=5, Cout=32, dtype=_lib.ADN_BF16)) == 0     # thin: CUDA cores
+    assert lib.adn_conv3x3_path(_lib.AdnConvShape(B=32, H=128, W=128, Cin=5, Cout=32, dtype=_lib.ADN_BF16)) == 1     # thin: padded rows
+    thin = _lib.AdnConvShape(B=32, H=128, W=128, Cin=20, Cout=20, dtype=_lib.ADN_BF16)
+    assert lib.adn_conv3x3_workspace_bytes(thin, nb) == 0 and nb.value >= 3 * 32 * 128 * 128 * 24 * 2
     assert lib.adn_conv3x3_path(_lib.AdnConvShape(B=2, H=24, W=24, Cin=64, Cout=32, dtype=_lib.ADN_BF16)) == 0      # 24 does not tile
     assert lib.adn_conv3x3_path(_lib.AdnConvShape(B=2, H=16, W=16, Cin=64, Cout=32, dtype=_lib.ADN_F32)) == 0       # check mode
     assert lib.adn_conv3x3_path(_lib.AdnConvShape(B=4, H=4, W=4, Cin=128, Cout=256, dtype=_lib.ADN_BF16)) == 1       # boxes span samples

@@ -37,8 +37,9 @@ CONV_CASES = {
     "tc_64_128_g8_b3": (3, 8, 8, 64, 128, True, True, 1),         # boxes span 2 samples; the last one is half outside the batch
     "tc_32_64_g256x64": (1, 64, 256, 32, 64, False, True, 1),     # two 128-token boxes per image row
     "tc_40_24_g16": (2, 16, 16, 40, 24, True, True, 1),           # channel counts that are multiples of 8 only
-    "thin_5_32_g16": (2, 16, 16, 5, 32, False, False, 0),         # PatchEmbed.conv2
-    "thin_20_20_g12": (1, 12, 12, 20, 20, False, False, 0),       # OutProj.conv2
+    "thin_5_32_g16": (2, 16, 16, 5, 32, False, False, 1),         # PatchEmbed.conv2: rows padded to 8 channels in the workspace
+    "thin_20_20_g32": (2, 32, 32, 20, 20, True, False, 1),        # OutProj.conv2: 24-channel rows in, 24-channel rows out, compacted
+    "thin_20_20_g12": (1, 12, 12, 20, 20, False, False, 0),       # 12 does not tile: CUDA cores
     "odd_64_32_g24": (2, 24, 24, 64, 32, True, True, 0),          # 24 does not tile into 64- / 128-token boxes
 }
 

@@ -200,8 +200,15 @@ def test_full_model_fp32_forward_loss_backward_matches_reference(full_model):
     # and the bulk of the 669 tensors meets 1e-4 outright.  Measured (profiles/fullmodel_errs.py, B200): the reference's own
     # fp32 run has 46-51 tensors beyond 1e-4 of the fp64 truth, the drop-in model 115 (135 before the Block was fused): its
     # reductions use other summation orders (split-K tensor-core / atomic accumulation) than cuDNN / cuBLAS.
+    # With the conv stages native as well (WTLayer / PatchEmbed / OutProj - now every full-resolution stage of the
+    # network sums in another order than cuDNN / cuBLAS) the count is 228-235 against 47-61 for the reference's own run, and
+    # none of them is far out: the worst non-degenerate tensor sits at 1e-3 (scalar gates; `wtconv.conv.base_conv.bias` in front
+    # of an InstanceNorm has a true gradient of zero and is noise in BOTH runs).  Each stage meets 1e-4 on every tensor by itself
+    # (tests/test_convstage_gpu.py, tests/test_block_gpu.py, tests/test_mixer_gpu.py); the bound here guards against a broken
+    # stage (which moves hundreds of tensors by orders of magnitude), not against fp32 summation order.
     n_new, n_ref = (sum(1 for v in e.values() if v > FP32_TOL) for e in (e_new, e_ref))
-    assert n_new <= max(3 * n_ref, 60), (n_new, n_ref)
+    assert n_new <= max(6 * n_ref, 240), (n_new, n_ref)
+    assert sum(1 for v in e_new.values() if v > 10 * FP32_TOL) <= max(2 * sum(1 for v in e_ref.values() if v > 10 * FP32_TOL), 12)
 
 
 def test_full_model_bf16_autocast_matches_reference(full_model):
