@@ -14,7 +14,13 @@ What is B200-specific here:
     gradients overlaps the backward of the decoder and encoder;
   * global grad-norm, clip (train.py:140), AdamW (train_untils.py:35-42) and zero_grad are two bandwidth-bound passes
     over the flat buffers in the sm_100a library (include/adnb200.h: adn_sumsq_f32, adn_adamw_flat), with the 1/world
-    average folded in; no `.item()` host synchronisation per step (the reference has two, train.py:141,146).
+    average folded in; no `.item()` host synchronisation per step (the reference has two, train.py:141,146);
+  * `graph=True`: forward + loss + backward are captured ONCE into a CUDA graph (every library entry point enqueues on the
+    caller's stream without allocation or synchronisation, and the hosted reference modules are plain tensor ops) and
+    replayed per step on static input buffers - the ~1000 library launches + ~2000 tensor-op launches of a step then cost
+    one `cudaGraphLaunch` instead of ~20 ms of host time, which is what bounds the eager step at B = 32 per GPU.  The
+    all-reduce (bucketed, NCCL) and the two clip / AdamW kernels stay outside the graph: the step counter and the learning
+    rate are host scalars that change every step.
 """
 import math
 
@@ -63,7 +69,7 @@ class DataParallelTrainer:
     the flat buffers (so it is slower and its all-reduce is not overlapped)."""
 
     def __init__(self, model, loss_fn, group=None, clip_norm=CLIP_NORM, adamw=None, bucket_bytes=32 << 20,
-                 autocast_dtype=torch.bfloat16, step_tail=None):
+                 autocast_dtype=torch.bfloat16, step_tail=None, graph=False):
         self.model, self.loss_fn, self.group = model, loss_fn, group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.clip_norm, self.hp = clip_norm, dict(ADAMW if adamw is None else adamw)
@@ -75,6 +81,9 @@ class DataParallelTrainer:
         self.buckets = []           # (start, end) element ranges of flat_g
         self._pending, self._works, self._ready_order = [], [], []
         self._hooks = []
+        self.graph = bool(graph)      # capture forward + loss + backward into a CUDA graph after the discovery step
+        self._graph, self._static, self._eager_after_discovery = None, None, 0
+        self.graph_error = None       # why the capture was abandoned (the trainer then stays eager), for the bench line
 
     # ------------------------------------------------------------------ forward / backward
     def _forward_loss(self, imgs, targets):
@@ -148,14 +157,56 @@ class DataParallelTrainer:
             s, e, _ = self.buckets[b]
             self._works.append(dist.all_reduce(self.flat_g[s:e], group=self.group, async_op=True))
 
+    # ------------------------------------------------------------------ CUDA-graph capture of forward + loss + backward
+    def _capture(self, imgs, targets):
+        """Static input buffers, one warm-up pass on a side stream (so that every lazily initialised handle and every
+        autograd buffer exists before capture), then the capture itself.  The gradients accumulate in place into the views of
+        `flat_g` (zeroed by the optimizer kernel at the end of every step), inside the graph as outside."""
+        dev = imgs.device
+        st_imgs, st_tgt = imgs.detach().clone(), targets.detach().clone()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._forward_loss(st_imgs, st_tgt).backward()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.flat_g.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self._forward_loss(st_imgs, st_tgt)
+            loss.backward()
+        self._graph, self._static = graph, (st_imgs, st_tgt, loss.detach())
+
+    def _graph_step(self, imgs, targets):
+        if self._graph is None:
+            try:
+                self._capture(imgs, targets)
+            except Exception as ex:      # an op of the hosted network that cannot be captured: stay eager, say so
+                self.graph, self.graph_error = False, f"{type(ex).__name__}: {ex}"[:300]
+                torch.cuda.synchronize()
+                self.flat_g.zero_()
+                return None
+        st_imgs, st_tgt, st_loss = self._static
+        st_imgs.copy_(imgs, non_blocking=True)
+        st_tgt.copy_(targets, non_blocking=True)
+        self._graph.replay()
+        if self.world > 1:
+            works = [dist.all_reduce(self.flat_g[s:e], group=self.group, async_op=True) for s, e, _ in self.buckets]
+            for w in works:
+                w.wait()
+        return st_loss
+
     # ------------------------------------------------------------------ one training step (train.py:132-146)
     def step(self, imgs, targets, lr=None):
         self.model.train()
+        loss = None
         if self.live is None:
             loss = self._discover_and_flatten(imgs, targets)
             if self.world > 1:
                 dist.all_reduce(self.flat_g, group=self.group)
-        else:
+        elif self.graph and imgs.is_cuda and self._eager_after_discovery >= 1:
+            loss = self._graph_step(imgs, targets)
+        if loss is None:
+            self._eager_after_discovery += 1
             self._pending = [c for _, _, c in self.buckets]
             self._works, self._overlap = [], True
             loss = self._forward_loss(imgs, targets)

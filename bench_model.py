@@ -75,12 +75,13 @@ def train_bench(batch=32, img=128, steps=10, warmup=3, variant="dropin", bf16=Tr
     if world > 1 and not dist.is_initialized() and init_dist:
         dist.init_process_group("nccl", device_id=dev)
     model = refhost.build_adnm_unet(img, dropin=(variant == "dropin"), seed=0).to(dev)     # identical weights on every rank
-    trainer = DataParallelTrainer(model, refhost.reference_loss(), autocast_dtype=torch.bfloat16 if bf16 else None)
+    use_graph = variant == "dropin" and os.environ.get("ADNM_TRAIN_GRAPH", "1") != "0"
+    trainer = DataParallelTrainer(model, refhost.reference_loss(), autocast_dtype=torch.bfloat16 if bf16 else None, graph=use_graph)
     g = torch.Generator().manual_seed(1000 + rank)                                     # per-rank data shard
     NSETS = 2
     host = [torch.rand(batch, 25, 1, img, img, generator=g).pin_memory() for _ in range(NSETS)]
     resident = [h.to(dev) for h in host]
-    losses = torch.zeros(max(steps, warmup, 3) + 1, device=dev)
+    losses = torch.zeros(max(steps, warmup, 3) + 3, device=dev)
     host_loss = torch.zeros(1).pin_memory()
 
     def step_resident(i):
@@ -92,11 +93,14 @@ def train_bench(batch=32, img=128, steps=10, warmup=3, variant="dropin", bf16=Tr
         loss = trainer.step(d[:, :5], d[:, 5:])
         host_loss.copy_(loss.reshape(1), non_blocking=True)     # D2H of the step's loss (what train.py:146 reads)
 
+    step_resident(0)                       # discovery step (flat buffers), always eager
     n0 = _lib.launch_count()
-    for i in range(max(warmup, 3)):
+    step_resident(1)                       # one eager step on the flat buffers: the library launches a step consists of
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - n0
+    for i in range(2, max(warmup, 3) + 2):  # capture (graph mode) + warm replays
         step_resident(i)
     torch.cuda.synchronize()
-    launches_per_step = (_lib.launch_count() - n0) // max(warmup, 3)
     mem = torch.cuda.max_memory_allocated(dev)
     ms = _timed(torch, dist, world, dev, step_resident, steps)
     ms_e2e = _timed(torch, dist, world, dev, step_e2e, steps) if e2e else None
@@ -113,8 +117,11 @@ def train_bench(batch=32, img=128, steps=10, warmup=3, variant="dropin", bf16=Tr
         "config": {"workload": f"ADNM-UNet training step (BASELINE configs[2]): B={batch}/GPU, 5->20 frames at {img}x{img}, "
                                "enRainfallLoss, clip 0.025, AdamW", "global_batch": batch * world, "parallelism": f"dp{world}",
                    "host": _host_note(variant),
+                   "launch": ("cuda_graph_replay: forward + loss + backward captured once (static input buffers), gradient all-reduce and the "
+                              "clip / AdamW kernels launched per step" if trainer._graph is not None else
+                              "eager" + (f" (graph capture abandoned: {trainer.graph_error})" if trainer.graph_error else "")),
                    "grad_allreduce": f"{len(trainer.buckets)} fp32 buckets ({trainer.n_live_elements()} live elements of "
-                                     f"{sum(p.numel() for p in model.parameters())}), NCCL sum overlapped with backward" if world > 1 else "none (1 GPU)"},
+                                     f"{sum(p.numel() for p in model.parameters())}), NCCL sum " + ("after the replayed backward" if trainer._graph is not None else "overlapped with backward") if world > 1 else "none (1 GPU)"},
         "live_param_tensors": len(trainer.live), "final_loss": final_loss, "grad_norm": float(trainer.grad_norm()),
         "lib_launches_per_step": launches_per_step, "peak_mem_gb": mem / 2**30,
         "roofline": {"per_sample_t_star_us": t_star * 1e6, "ceiling_seq_per_s_per_gpu": (1 / t_star) if t_star else None,
@@ -146,18 +153,43 @@ def infer_bench(batch=64, img=256, steps=5, warmup=2, variant="dropin", bf16=Tru
     ev = SimplifiedEvaluator(seq_len=20, value_scale=90, thresholds=[20, 30, 35, 40], device=dev)
     last = {}
 
-    def step(i):
+    def fwd():
         with torch.no_grad():
             if bf16:
                 with torch.autocast("cuda", dtype=torch.bfloat16):
-                    out = model(x)
-            else:
-                out = model(x)
-            last["out"] = out
+                    return model(x)
+            return model(x)
+
+    graph, graph_note = None, "eager"
+
+    def step(i):
+        if graph is not None:
+            graph.replay()
+            out = last["static_out"]
+        else:
+            out = fwd()
+        last["out"] = out
+        with torch.no_grad():
             ev.evaluate(tgt, out.squeeze(2).float())
 
     for i in range(warmup):
         step(i)
+    if variant == "dropin" and os.environ.get("ADNM_INFER_GRAPH", "1") != "0":
+        # the eval forward captured once into a CUDA graph (static input buffer `x`), replayed per batch; the evaluator kernel stays eager
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                fwd()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                last["static_out"] = fwd()
+            graph, graph_note = g_, "cuda_graph_replay of the eval forward (static input buffer); evaluator kernel launched per batch"
+            step(0)
+        except Exception as ex:
+            graph, graph_note = None, f"eager (graph capture abandoned: {type(ex).__name__}: {ex})"[:300]
+            torch.cuda.synchronize()
     ev.reset()
     ms = _timed(torch, None, 1, dev, step, steps)
     table = ev.counts().clone()
@@ -182,7 +214,7 @@ def infer_bench(batch=64, img=256, steps=5, warmup=2, variant="dropin", bf16=Tru
             "variant": variant, "dtype": "bf16 autocast" if bf16 else "f32",
             "config": {"workload": f"ADNM-UNet inference (BASELINE configs[3], validate.py:92-118): B={batch}, 5->20 frames at {img}x{img}, "
                                    "eval + no_grad forward + on-device SimplifiedEvaluator (threshold counts + RMSE)",
-                       "host": _host_note(variant)},
+                       "host": _host_note(variant), "launch": graph_note},
             "counts_table": table.cpu().tolist(), "csi": csi, "hss": hss, "rmse": res["RMSE"], "far": res["FAR"],
             "evaluator": {"device_ms_per_batch": ms_eval, "device_samples_per_s": batch / (ms_eval * 1e-3),
                           "eval_baseline": {"kind": "reference loops (float2int + _cal_frame over batch x frame x threshold) on the host",
