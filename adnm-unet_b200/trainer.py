@@ -82,7 +82,7 @@ class DataParallelTrainer:
         self._pending, self._works, self._ready_order = [], [], []
         self._hooks = []
         self.graph = bool(graph)      # capture forward + loss + backward into a CUDA graph after the discovery step
-        self._graph, self._static, self._eager_after_discovery = None, None, 0
+        self._graph, self._static, self._eager_after_discovery, self._stream = None, None, 0, None
         self.graph_error = None       # why the capture was abandoned (the trainer then stays eager), for the bench line
 
     # ------------------------------------------------------------------ forward / backward
@@ -159,19 +159,14 @@ class DataParallelTrainer:
 
     # ------------------------------------------------------------------ CUDA-graph capture of forward + loss + backward
     def _capture(self, imgs, targets):
-        """Static input buffers, one warm-up pass on a side stream (so that every lazily initialised handle and every
-        autograd buffer exists before capture), then the capture itself.  The gradients accumulate in place into the views of
-        `flat_g` (zeroed by the optimizer kernel at the end of every step), inside the graph as outside."""
-        dev = imgs.device
+        """Static input buffers, then the capture on the trainer's own stream - the stream every earlier step of this trainer
+        ran on, so the parameters' AccumulateGrad nodes (created on first use, kept alive by the gradient hooks) belong to the
+        capturing stream; a node that lives on the legacy default stream would invalidate the capture.  The gradients
+        accumulate in place into the views of `flat_g` (zeroed by the optimizer kernel at the end of every step), inside the
+        graph as outside; the eager steps before this call have warmed every lazily initialised handle."""
         st_imgs, st_tgt = imgs.detach().clone(), targets.detach().clone()
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            self._forward_loss(st_imgs, st_tgt).backward()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        self.flat_g.zero_()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=self._stream):
             loss = self._forward_loss(st_imgs, st_tgt)
             loss.backward()
         self._graph, self._static = graph, (st_imgs, st_tgt, loss.detach())
@@ -197,6 +192,19 @@ class DataParallelTrainer:
 
     # ------------------------------------------------------------------ one training step (train.py:132-146)
     def step(self, imgs, targets, lr=None):
+        if self.graph and imgs.is_cuda:
+            # graph mode: every step of this trainer runs on ONE non-default stream (see _capture)
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(imgs.device)
+            cur = torch.cuda.current_stream(imgs.device)
+            self._stream.wait_stream(cur)
+            with torch.cuda.stream(self._stream):
+                loss = self._step(imgs, targets, lr)
+            cur.wait_stream(self._stream)
+            return loss
+        return self._step(imgs, targets, lr)
+
+    def _step(self, imgs, targets, lr=None):
         self.model.train()
         loss = None
         if self.live is None:

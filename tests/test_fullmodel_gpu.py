@@ -308,14 +308,16 @@ def test_trainer_tail_matches_torch_adamw_and_clip():
 
 def test_trainer_graph_mode_matches_eager():
     """DataParallelTrainer(graph=True): forward + loss + backward of the hosted network replayed from ONE captured CUDA graph
-    give the same losses and gradient norms, step for step, as the eager trainer on the same batches."""
+    give the same losses and gradient norms, step for step, as the eager trainer on the same batches.  fp32 (check mode): under
+    bf16 autocast the gradient norm of a B = 2 step is dominated by 0-dim gates whose sums cancel (measured: two EAGER bf16 runs
+    differ by 30 % in the norm of the same step while their losses agree to 1e-4), so bf16 cannot tell the two modes apart."""
     host = _host()
     from adnm_unet_b200.trainer import DataParallelTrainer
     dev = torch.device("cuda:0")
     runs = {}
     for graph in (False, True):
         model = host.build_adnm_unet(128, dropin=True, seed=0).to(dev)
-        tr = DataParallelTrainer(model, host.reference_loss(), graph=graph)
+        tr = DataParallelTrainer(model, host.reference_loss(), graph=graph, autocast_dtype=None)
         log = []
         for i in range(5):
             d = torch.rand(2, 25, 1, 128, 128, generator=torch.Generator().manual_seed(50 + i)).to(dev)
@@ -325,4 +327,4 @@ def test_trainer_graph_mode_matches_eager():
         if graph:
             assert tr._graph is not None, tr.graph_error
     for (le, ne), (lg, ng) in zip(runs[False], runs[True]):
-        assert abs(le - lg) <= 2e-2 * abs(le) and abs(ne - ng) <= 5e-2 * abs(ne), (runs[False], runs[True])
+        assert abs(le - lg) <= 1e-3 * abs(le) and abs(ne - ng) <= 2e-2 * abs(ne), (runs[False], runs[True])
