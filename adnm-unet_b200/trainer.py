@@ -166,7 +166,8 @@ class DataParallelTrainer:
         graph as outside; the eager steps before this call have warmed every lazily initialised handle."""
         st_imgs, st_tgt = imgs.detach().clone(), targets.detach().clone()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=self._stream):
+        # thread_local: CUDA calls of OTHER threads (NCCL watchdog, a data loader pinning memory) must not invalidate the capture
+        with torch.cuda.graph(graph, stream=self._stream, capture_error_mode="thread_local"):
             loss = self._forward_loss(st_imgs, st_tgt)
             loss.backward()
         self._graph, self._static = graph, (st_imgs, st_tgt, loss.detach())
