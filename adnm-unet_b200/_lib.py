@@ -98,6 +98,8 @@ EXPORTS = {
     "adn_plane_mix_backward": (C.c_int, [C.c_void_p] * 14 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "adn_act_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "adn_act_backward": (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "adn_gconv4_forward": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 7 + [C.c_void_p]),
+    "adn_gconv4_backward": (C.c_int, [C.c_void_p] * 6 + [C.c_int32] * 7 + [C.c_void_p]),
     "adn_sdpa_forward": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_float, C.c_int32, C.c_void_p]),
     "adn_sdpa_backward": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_float, C.c_int32, C.c_void_p]),
     "adn_last_error": (C.c_char_p, []),

@@ -478,3 +478,70 @@ class OutProj(nn.Module):
         t = conv3x3_tokens(t, h, w, F.pad(c2.weight, (0, 0, 0, 0, 0, pad)) if pad else c2.weight, c2.bias)
         t = swish_tokens(t, self.conv2.act.beta) if self.conv2.act_kind == ACT_SWISH else gelu_tokens(t)
         return pack_planes(t, h, w)
+
+
+# ---------------------------------------------------------------------------------------------- grouped conv of the bridges
+class _GConv4Function(torch.autograd.Function):
+    """x (B, L, C) channels-last, weight (C, 4, kh, kw), bias (C) | None -> (B, L, C): nn.Conv2d(C, C, (kh, kw), padding 'same',
+    groups = C / 4) of the EncoderToDecoder bridges (models/model_untils.py:621-675)."""
+
+    @staticmethod
+    def forward(ctx, x, H, W, weight, bias):
+        _lib.require_cuda(x, "x")
+        lib = _lib.load()
+        x = x.contiguous()
+        B, L, Cc = x.shape
+        kh, kw = int(weight.shape[2]), int(weight.shape[3])
+        if L != H * W or weight.shape[0] != Cc or weight.shape[1] != 4:
+            raise RuntimeError(f"gconv4: x {tuple(x.shape)} / weight {tuple(weight.shape)} / grid {H}x{W} do not match")
+        w, b = _f32(weight), _f32(bias)
+        y = torch.empty_like(x)
+        with _lib.on_device(x.device):
+            _lib.check(lib.adn_gconv4_forward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), B, H, W, Cc, kh, kw, _lib.dtype_code(x),
+                                              _lib.stream_ptr(x.device)), "adn_gconv4_forward")
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (H, W, weight, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, w = ctx.saved_tensors
+        H, W, weight, bias = ctx.cfg
+        B, L, Cc = x.shape
+        kh, kw = int(w.shape[2]), int(w.shape[3])
+        ni = ctx.needs_input_grad
+        dy = dy.to(x.dtype).contiguous()
+        dx = torch.empty_like(x) if ni[0] else None
+        flat = torch.empty(w.numel() + Cc, dtype=torch.float32, device=x.device)
+        dw, db = flat[:w.numel()], flat[w.numel():]
+        with _lib.on_device(x.device):
+            _lib.check(lib.adn_gconv4_backward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db) if bias is not None else None,
+                                               B, H, W, Cc, kh, kw, _lib.dtype_code(x), _lib.stream_ptr(x.device)), "adn_gconv4_backward")
+        return (dx, None, None, dw.view(w.shape).to(weight.dtype) if ni[3] else None, db.to(bias.dtype) if bias is not None and ni[4] else None)
+
+
+def gconv4_tokens(x, H, W, weight, bias=None):
+    return _GConv4Function.apply(x, int(H), int(W), weight, bias)
+
+
+def make_bridge_conv_layer(ref_conv2d_layer):
+    """Subclass of the reference's own `Conv2dLayer` (models/model_untils.py:71-93; same constructor, parameters and state_dict by
+    inheritance) whose forward sends the `groups = channels / 4` convolutions of the EncoderToDecoder bridges (:621-675) to
+    adn_gconv4_*; every other configuration runs the reference's forward unchanged.  Bound as `models.model_untils.Conv2dLayer` by
+    refhost while the network is built (the bridges are outside SURVEY.md section 8; this only removes ~2 400 cuDNN launches)."""
+
+    class Conv2dLayer(ref_conv2d_layer):
+        def forward(self, x):
+            c = self.conv
+            kh, kw = c.kernel_size
+            if (x.is_cuda and self.dropout is None and not self.norm and c.groups * 4 == c.in_channels == c.out_channels
+                    and c.stride == (1, 1) and c.dilation == (1, 1) and kh in (1, 3) and kw in (1, 3) and c.padding == (kh // 2, kw // 2)
+                    and c.padding_mode == "zeros"):
+                b, ch, h, w = x.shape
+                y = gconv4_tokens(_autocast(x).permute(0, 2, 3, 1).reshape(b, h * w, ch), h, w, c.weight, c.bias)
+                y = y.view(b, h, w, ch).permute(0, 3, 1, 2)
+                return self.act(y) if self.act else y
+            return super().forward(x)
+
+    return Conv2dLayer

@@ -315,6 +315,142 @@ static int conv_backward(const ConvDims& d, const T* x, const float* w, const fl
   return ADN_OK;
 }
 
+// ================================================================ grouped convolution, 4 channels per group
+// The `groups = dim / 4` convolutions of the EncoderToDecoder bridges (models/model_untils.py:621-675: 1x3, 3x1 and 3x3 kernels,
+// stride 1, 'same' zero padding, bias) on channels-last activations (B, H*W, C).  cuDNN runs them as one launch PER GROUP plus
+// two layout conversions per launch (256 groups at dim 1024: ~1 300 launches and 2 ms per bridge and step); here a conv is a
+// 4 x 4 x taps stencil per output element: one launch forward, two backward.  w: (C, 4, kh, kw) fp32, state_dict layout.
+// Thread mapping of all three kernels: lane = channel (32 consecutive channels = 8 groups per CTA: a warp reads / writes 64
+// contiguous bytes of a bf16 token row), the 8 warps of a CTA stride over the CTA's `tps` tokens; a thread keeps the 4 x taps
+// weights that involve its channel in registers.  grid = (ceil(C / 32), ceil(tokens / tps)).
+constexpr int GC_MAXK = 9;
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gconv4_fwd(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ y, int H, int W, int C,
+             int kh, int kw, long long Ttok, int tps) {
+  const int K = kh * kw, ph = kh / 2, pw = kw / 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int co = blockIdx.x * 32 + lane, g4 = co & ~3;
+  if (co >= C) return;
+  float wr[4][GC_MAXK];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int t = 0; t < GC_MAXK; ++t) wr[j][t] = t < K ? w[((long long)co * 4 + j) * K + t] : 0.f;
+  const float b0 = bias ? bias[co] : 0.f;
+  int tdy[GC_MAXK], tdx[GC_MAXK];      // tap offsets: constant over the token loop (no division per tap and token)
+#pragma unroll
+  for (int t = 0; t < GC_MAXK; ++t) { tdy[t] = t / kw - ph; tdx[t] = t % kw - pw; }
+  const int t0 = blockIdx.y * tps, t1 = (int)min(Ttok, (long long)t0 + tps);
+  for (int p = t0 + warp; p < t1; p += 8) {
+    const int row = p / W, xx = p - row * W, yy = row % H;
+    float acc = b0;
+#pragma unroll
+    for (int t = 0; t < GC_MAXK; ++t) {
+      if (t < K) {
+        const int dy = tdy[t], dx = tdx[t];
+        if (yy + dy >= 0 && yy + dy < H && xx + dx >= 0 && xx + dx < W) {
+          float v[4];
+          ld4(x + (long long)(p + dy * W + dx) * C + g4, v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc = fmaf(v[j], wr[j][t], acc);
+        }
+      }
+    }
+    stf(y + (long long)p * C + co, acc);
+  }
+}
+// dx[p][4g + j] = sum_t sum_{co in group} dy[p - delta_t][4g + co] w[4g + co][j][t]
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gconv4_dgrad(const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx, int H, int W, int C, int kh, int kw, long long Ttok,
+               int tps) {
+  const int K = kh * kw, ph = kh / 2, pw = kw / 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ci = blockIdx.x * 32 + lane, g4 = ci & ~3, j = ci & 3;
+  if (ci >= C) return;
+  float wr[4][GC_MAXK];
+#pragma unroll
+  for (int co = 0; co < 4; ++co)
+#pragma unroll
+    for (int t = 0; t < GC_MAXK; ++t) wr[co][t] = t < K ? w[((long long)(g4 + co) * 4 + j) * K + t] : 0.f;
+  int tdy[GC_MAXK], tdx[GC_MAXK];
+#pragma unroll
+  for (int t = 0; t < GC_MAXK; ++t) { tdy[t] = t / kw - ph; tdx[t] = t % kw - pw; }
+  const int t0 = blockIdx.y * tps, t1 = (int)min(Ttok, (long long)t0 + tps);
+  for (int p = t0 + warp; p < t1; p += 8) {
+    const int row = p / W, xx = p - row * W, yy = row % H;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < GC_MAXK; ++t) {
+      if (t < K) {
+        const int dyy = tdy[t], dxx = tdx[t];
+        if (yy - dyy >= 0 && yy - dyy < H && xx - dxx >= 0 && xx - dxx < W) {
+          float v[4];
+          ld4(dy + (long long)(p - dyy * W - dxx) * C + g4, v);
+#pragma unroll
+          for (int co = 0; co < 4; ++co) acc = fmaf(v[co], wr[co][t], acc);
+        }
+      }
+    }
+    stf(dx + (long long)p * C + ci, acc);
+  }
+}
+// dw[co][j][t] += sum_p dy[p][co] x[p + delta_t][4g + j],  dbias[co] += sum_p dy[p][co]: 4 x taps + 1 partial sums per thread over
+// its tokens, summed over the 8 warps through shared memory, one atomic per entry and CTA (dw / dbias zeroed by the caller)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gconv4_wgrad(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, float* __restrict__ dbias, int H, int W, int C,
+               int kh, int kw, long long Ttok, int tps) {
+  __shared__ float red[8][4 * GC_MAXK + 1][32];
+  const int K = kh * kw, ph = kh / 2, pw = kw / 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int co = blockIdx.x * 32 + lane, g4 = co & ~3;
+  float acc[4][GC_MAXK], ab = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int t = 0; t < GC_MAXK; ++t) acc[j][t] = 0.f;
+  int tdy[GC_MAXK], tdx[GC_MAXK];
+#pragma unroll
+  for (int t = 0; t < GC_MAXK; ++t) { tdy[t] = t / kw - ph; tdx[t] = t % kw - pw; }
+  const int t0 = blockIdx.y * tps, t1 = (int)min(Ttok, (long long)t0 + tps);
+  if (co < C) {
+    for (int p = t0 + warp; p < t1; p += 8) {
+      const int row = p / W, xx = p - row * W, yy = row % H;
+      const float g = ldf(dy + (long long)p * C + co);
+      ab += g;
+#pragma unroll
+      for (int t = 0; t < GC_MAXK; ++t) {
+        if (t < K) {
+          const int dyy = tdy[t], dxx = tdx[t];
+          if (yy + dyy >= 0 && yy + dyy < H && xx + dxx >= 0 && xx + dxx < W) {
+            float v[4];
+            ld4(x + (long long)(p + dyy * W + dxx) * C + g4, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][t] = fmaf(g, v[j], acc[j][t]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int t = 0; t < GC_MAXK; ++t) red[warp][j * GC_MAXK + t][lane] = acc[j][t];
+  red[warp][4 * GC_MAXK][lane] = ab;
+  __syncthreads();
+  for (int e = threadIdx.x; e < (4 * GC_MAXK + 1) * 32; e += 256) {
+    const int q = e >> 5, l = e & 31, c = blockIdx.x * 32 + l;
+    float v = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) v += red[wq][q][l];
+    if (c >= C || v == 0.f) continue;
+    if (q == 4 * GC_MAXK) { if (dbias) atomicAdd(dbias + c, v); }
+    else {
+      const int j = q / GC_MAXK, t = q - j * GC_MAXK;
+      if (t < K) atomicAdd(dw + ((long long)c * 4 + j) * K + t, v);
+    }
+  }
+}
+
 // ================================================================ layout changes, InstanceNorm, shortcut mix
 // A (32 V) x (32 V) (pixels x channels) tile goes through shared memory: the token-major side is read / written with lanes along
 // the channels, the NCHW side with lanes along the pixels, V elements per lane: V = 2 (4-byte bf16x2 / 8-byte float2 accesses,
@@ -957,6 +1093,53 @@ int adn_act_backward(const void* x, const void* dy, void* dx, int64_t n, int32_t
     else k_act_bwd<bf16><<<ew_grid(n / 8 + 1), 256, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, n, kind, beta, acc);
   }
   if (acc) { ADN_KERNEL("k_store_acc", st); k_store_acc<<<1, 32, 0, st>>>(acc, dbeta, nullptr); }
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
+static int gconv_check(int32_t B, int32_t H, int32_t W, int32_t C, int32_t kh, int32_t kw, int32_t dtype, const char* what) {
+  ADN_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && (long long)B * H * W < (1LL << 30), ADN_ERR_SHAPE,
+              "%s: bad extents (B %d, %d x %d, C %d: C must be a multiple of 4)", what, B, H, W, C);
+  ADN_REQUIRE((kh == 1 || kh == 3) && (kw == 1 || kw == 3), ADN_ERR_SHAPE, "%s: kernel %d x %d (1 or 3 per side)", what, kh, kw);
+  ADN_REQUIRE(dtype == ADN_F32 || dtype == ADN_BF16, ADN_ERR_DTYPE, "%s: unsupported dtype %d", what, dtype);
+  return ADN_OK;
+}
+
+int adn_gconv4_forward(const void* x, const float* w, const float* bias, void* y, int32_t B, int32_t H, int32_t W, int32_t C, int32_t kh,
+                       int32_t kw, int32_t dtype, void* stream) {
+  int rc = gconv_check(B, H, W, C, kh, kw, dtype, "adn_gconv4_forward");
+  if (rc) return rc;
+  ADN_REQUIRE(x && w && y, ADN_ERR_NULL, "adn_gconv4_forward: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long Ttok = (long long)B * H * W;
+  const int tps = 128;
+  dim3 grid(cdiv(C, 32), cdiv(Ttok, tps));
+  ADN_KERNEL("k_gconv4_fwd", st);
+  if (dtype == ADN_F32) k_gconv4_fwd<float><<<grid, 256, 0, st>>>((const float*)x, w, bias, (float*)y, H, W, C, kh, kw, Ttok, tps);
+  else k_gconv4_fwd<bf16><<<grid, 256, 0, st>>>((const bf16*)x, w, bias, (bf16*)y, H, W, C, kh, kw, Ttok, tps);
+  ADN_CHECK_LAUNCH();
+  return ADN_OK;
+}
+
+/* dx may be NULL; dw (C, 4, kh, kw) and dbias (C, may be NULL) are OVERWRITTEN. */
+int adn_gconv4_backward(const void* x, const float* w, const void* dy, void* dx, float* dw, float* dbias, int32_t B, int32_t H, int32_t W,
+                        int32_t C, int32_t kh, int32_t kw, int32_t dtype, void* stream) {
+  int rc = gconv_check(B, H, W, C, kh, kw, dtype, "adn_gconv4_backward");
+  if (rc) return rc;
+  ADN_REQUIRE(x && w && dy && dw, ADN_ERR_NULL, "adn_gconv4_backward: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long Ttok = (long long)B * H * W;
+  ADN_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)C * 4 * kh * kw * sizeof(float), st));
+  if (dbias) ADN_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)C * sizeof(float), st));
+  const int tps = 128;
+  dim3 grid(cdiv(C, 32), cdiv(Ttok, tps));
+  if (dtype == ADN_F32) {
+    if (dx) { ADN_KERNEL("k_gconv4_dgrad", st); k_gconv4_dgrad<float><<<grid, 256, 0, st>>>((const float*)dy, w, (float*)dx, H, W, C, kh, kw, Ttok, tps); }
+    { ADN_KERNEL("k_gconv4_wgrad", st); k_gconv4_wgrad<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)dy, dw, dbias, H, W, C, kh, kw, Ttok, tps); }
+  } else {
+    if (dx) { ADN_KERNEL("k_gconv4_dgrad", st); k_gconv4_dgrad<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, w, (bf16*)dx, H, W, C, kh, kw, Ttok, tps); }
+    { ADN_KERNEL("k_gconv4_wgrad", st); k_gconv4_wgrad<bf16><<<grid, 256, 0, st>>>((const bf16*)x, (const bf16*)dy, dw, dbias, H, W, C, kh, kw, Ttok, tps); }
+  }
   ADN_CHECK_LAUNCH();
   return ADN_OK;
 }

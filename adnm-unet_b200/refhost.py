@@ -183,6 +183,7 @@ def load_reference():
     ns.ref_StandardAttention = ns.ADNssd.StandardAttention
     ns.ref_FeedForward = ns.model_untils.FeedForward
     ns.ref_stages = {n: getattr(ns.model_untils, n) for n in STAGE_NAMES}
+    ns.ref_Conv2dLayer = ns.model_untils.Conv2dLayer
     _patch_decoder_size(ns.ADNMUNet)
     _NS = ns
     return ns
@@ -218,10 +219,16 @@ def _bound(ns, dropin, mixer=True, wtconv=True, block=True, stages=True):
     old_stages = {n: getattr(ns.ADNMUNet, n) for n in STAGE_NAMES}
     for n in STAGE_NAMES:
         setattr(ns.ADNMUNet, n, ns.ref_stages[n])
+    old_conv_layer = ns.model_untils.Conv2dLayer
+    ns.model_untils.Conv2dLayer = ns.ref_Conv2dLayer
     if dropin and stages and wtconv:
         from adnm_unet_b200 import convstage
         for n in STAGE_NAMES:
             setattr(ns.ADNMUNet, n, getattr(convstage, n))
+        # the bridges' grouped convs: the reference's own Conv2dLayer, subclassed (EncoderToDecoder resolves the name at :623-673)
+        if getattr(ns, "bridge_Conv2dLayer", None) is None:
+            ns.bridge_Conv2dLayer = convstage.make_bridge_conv_layer(ns.ref_Conv2dLayer)
+        ns.model_untils.Conv2dLayer = ns.bridge_Conv2dLayer
     if dropin:
         from adnm_unet_b200.mixer import Mamba2
         from adnm_unet_b200.wtconv import WTConv2d
@@ -247,6 +254,7 @@ def _bound(ns, dropin, mixer=True, wtconv=True, block=True, stages=True):
          ns.model_untils.FeedForward) = old
         for n in STAGE_NAMES:
             setattr(ns.ADNMUNet, n, old_stages[n])
+        ns.model_untils.Conv2dLayer = old_conv_layer
 
 
 DEAD_BRIDGES = (3, 4, 5, 6)

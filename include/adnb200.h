@@ -300,6 +300,15 @@ int adn_act_forward(const void* x, void* y, int64_t n, int32_t kind, const float
 int adn_act_backward(const void* x, const void* dy, void* dx, int64_t n, int32_t kind, const float* beta, float* dbeta,
                      void* workspace, int32_t dtype, void* stream);
 
+/* Grouped convolution with 4 channels per group (the `groups = dim / 4` convs of the EncoderToDecoder bridges,
+ * models/model_untils.py:621-675; cuDNN runs them as one launch per group): x, y (B, H*W, C) channels-last, w (C, 4, kh, kw) fp32 in
+ * nn.Conv2d's layout, bias (C) or NULL, kh / kw in {1, 3}, stride 1, zero padding kh/2, kw/2.  Backward: dx may be NULL, dw and
+ * dbias (may be NULL) are OVERWRITTEN. */
+int adn_gconv4_forward(const void* x, const float* w, const float* bias, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
+                       int32_t kh, int32_t kw, int32_t dtype, void* stream);
+int adn_gconv4_backward(const void* x, const float* w, const void* dy, void* dx, float* dw, float* dbias, int32_t B, int32_t H,
+                        int32_t W, int32_t C, int32_t kh, int32_t kw, int32_t dtype, void* stream);
+
 /* ------------------------------------------------------------------ misc ------------------- */
 
 const char* adn_last_error(void);

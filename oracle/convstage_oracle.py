@@ -135,3 +135,10 @@ def perturb_params(module_state, seed, scale=0.1):
         sd = scale if v.dim() < 2 else 0.3 * float(v.double().abs().mean().clamp_min(1e-3))
         out[k] = (v.double() + sd * torch.randn(v.shape, generator=g, dtype=torch.float64)).float()
     return out
+
+
+def gconv4_tokens(x, H, W, weight, bias=None):
+    """nn.Conv2d(C, C, (kh, kw), padding (kh // 2, kw // 2), groups = C / 4) of the EncoderToDecoder bridges
+    (models/model_untils.py:621-675) on token-major x (B, L, C)."""
+    kh, kw = weight.shape[2], weight.shape[3]
+    return to_tokens(F.conv2d(to_planes(x, H, W), weight, bias, padding=(kh // 2, kw // 2), groups=weight.shape[0] // 4))

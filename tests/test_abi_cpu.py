@@ -206,3 +206,5 @@ def test_convstage_entry_points_validate_on_the_host(lib):
     assert lib.adn_act_forward(one, one, 10, 3, None, _lib.ADN_F32, None) != 0 and b"kind" in lib.adn_last_error()
     assert lib.adn_nchw_pack_forward(one, None, None, None, one, 2, 64, 8, 8, _lib.ADN_F32, None) != 0      # C2 > 0 without res
     assert lib.adn_plane_mix_workspace_bytes(32, 64, nb) == 0 and nb.value >= 32 * 64 * 16
+    assert lib.adn_gconv4_forward(one, one, None, one, 2, 4, 4, 30, 3, 3, _lib.ADN_BF16, None) != 0 and b"multiple of 4" in lib.adn_last_error()
+    assert lib.adn_gconv4_forward(one, one, None, one, 2, 4, 4, 32, 5, 3, _lib.ADN_BF16, None) != 0 and b"kernel" in lib.adn_last_error()

@@ -302,3 +302,58 @@ def test_wtlayer_step_is_cuda_graph_capturable():
     for n, p in m.named_parameters():
         if p.grad is not None and n != "wtconv.conv.base_conv.bias":      # true gradient zero (InstanceNorm follows): noise
             assert rel(g_par[n], p.grad) < 5e-3, n      # atomically accumulated reductions: summation order differs run to run
+
+
+@pytest.mark.parametrize("dtype", DT, ids=IDS)
+@pytest.mark.parametrize("cfg", [(2, 4, 4, 1024, 1, 3, True), (2, 8, 8, 512, 3, 1, True), (3, 16, 16, 256, 3, 3, True), (1, 5, 7, 12, 3, 3, False)],
+                         ids=lambda c: "B%d_%dx%d_C%d_k%dx%d_bias%d" % c)
+def test_grouped_conv4_matches_oracle(cfg, dtype):
+    """The `groups = C / 4` convolutions of the EncoderToDecoder bridges (models/model_untils.py:621-675) through adn_gconv4_*."""
+    from adnm_unet_b200.convstage import gconv4_tokens
+    B, H, W, C, kh, kw, has_bias = cfg
+    dev = torch.device("cuda:0")
+    x = cases.bf16_exact(cases.rng_normal(51, (B, H * W, C), torch.float32))
+    dy = cases.bf16_exact(cases.rng_normal(52, (B, H * W, C), torch.float32))
+    w = cases.rng_normal(53, (C, 4, kh, kw), torch.float32) / (2 * (kh * kw) ** 0.5)
+    b = 0.3 * cases.rng_normal(54, (C,), torch.float32) if has_bias else None
+    lv = [None if t is None else t.double().requires_grad_(True) for t in (x, w, b)]
+    ref = CO.gconv4_tokens(lv[0], H, W, lv[1], lv[2])
+    ref.backward(dy.double())
+    xd, wd = _leaf(x, dev, dtype), _leaf(w, dev)
+    bd = _leaf(b, dev) if has_bias else None
+    y = gconv4_tokens(xd, H, W, wd, bd)
+    y.backward(dy.to(dev, dtype))
+    torch.cuda.synchronize()
+    errs = {"y": rel(y, ref), "dx": rel(xd.grad, lv[0].grad), "dw": rel(wd.grad, lv[1].grad)}
+    if has_bias:
+        errs["dbias"] = rel(bd.grad, lv[2].grad)
+    bad = {k: v for k, v in errs.items() if not v < TOL[dtype]}
+    assert not bad, bad
+
+
+def test_bridge_conv_layer_is_the_reference_layer():
+    """refhost binds a SUBCLASS of the reference's Conv2dLayer for the bridges: same parameters, same result as the reference
+    forward (cuDNN grouped conv + GELU) on the same GPU, and other configurations fall through to the reference code."""
+    from adnm_unet_b200 import convstage, refhost
+    if not refhost.reference_available():
+        pytest.skip("reference sources not on this box")
+    ns = refhost.load_reference()
+    cls = convstage.make_bridge_conv_layer(ns.ref_Conv2dLayer)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2)
+    new = cls(in_channels=64, out_channels=64, kernel_size=(1, 3), stride=(1, 1), padding=(0, 1), bias=True, groups=16, act_func=torch.nn.GELU).to(dev)
+    torch.manual_seed(2)
+    ref = ns.ref_Conv2dLayer(in_channels=64, out_channels=64, kernel_size=(1, 3), stride=(1, 1), padding=(0, 1), bias=True, groups=16,
+                             act_func=torch.nn.GELU).to(dev)
+    assert all(torch.equal(a, b) for a, b in zip(new.state_dict().values(), ref.state_dict().values()))
+    x = torch.randn(2, 8 * 8, 64, device=dev).view(2, 8, 8, 64).permute(0, 3, 1, 2)       # the bridges' NCHW view of token-major memory
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    g = torch.randn(2, 64, 8, 8, device=dev)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False      # the reference side is a cuDNN fp32 conv: keep it out of TF32
+    ya, yb = new(xa), ref(xb)
+    ya.backward(g); yb.backward(g)
+    torch.backends.cudnn.allow_tf32 = old
+    assert rel(ya, yb) < 1e-5 and rel(xa.grad, xb.grad) < 1e-5 and rel(new.conv.weight.grad, ref.conv.weight.grad) < 1e-4
+    dense = cls(in_channels=8, out_channels=16, kernel_size=3, padding=1).to(dev)                # not a 4-channel-group conv: reference path
+    assert dense(torch.randn(1, 8, 6, 6, device=dev)).shape == (1, 16, 6, 6)
