@@ -34,6 +34,24 @@ __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff
 __device__ __forceinline__ float gelu_grad_f(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
 }
+// Storage-type dispatched GELU: fp32 (the 1e-4 check mode) keeps erff / expf; bf16 uses Abramowitz-Stegun 7.1.26
+// (|error| < 1.5e-7 on erf, far below the bf16 rounding of the stored result) with ONE fast exponential shared between erf and the
+// Gaussian of the derivative (exp(-z^2) with z = x / sqrt 2 is exp(-x^2 / 2)): the exact pair kept k_act_* at 88 % issue slots.
+template <typename T> struct Act {
+  static __device__ __forceinline__ float gelu(float x) { return gelu_f(x); }
+  static __device__ __forceinline__ float gelu_grad(float x) { return gelu_grad_f(x); }
+};
+__device__ __forceinline__ void erf_as(float x, float& erf_z, float& gauss) {      // erf(x / sqrt 2), exp(-x^2 / 2)
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  gauss = __expf(-z * z);
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  erf_z = copysignf(1.f - poly * gauss, x);
+}
+template <> struct Act<bf16> {
+  static __device__ __forceinline__ float gelu(float x) { float e, g; erf_as(x, e, g); return 0.5f * x * (1.f + e); }
+  static __device__ __forceinline__ float gelu_grad(float x) { float e, g; erf_as(x, e, g); return 0.5f * (1.f + e) + x * 0.3989422804014327f * g; }
+};
 
 // ================================================================ dense 3x3 convolution
 struct ConvDims {
@@ -660,7 +678,7 @@ k_mix_fwd(const T* __restrict__ y, const T* __restrict__ xs, MixP m, T* __restri
       for (int e = 0; e < V; ++e) {
         float t = u[e];
         if (m.stats) t = sc * (t - mean) * rstd + sh;
-        if (m.act) t = gelu_f(t);
+        if (m.act) t = Act<T>::gelu(t);
         v[e] = (al * t + be * s[e]) * ga;
       }
     }
@@ -726,10 +744,10 @@ k_mix_bwd_sums(const T* __restrict__ y, const T* __restrict__ xs, MixP m, const 
           const float g = tile[V * tx + e][cl];
           const float n = m.stats ? (yv[e] - mean) * rstd : yv[e];
           const float u = m.stats ? sc * n + sh : n;
-          const float ee = m.act ? g * gelu_grad_f(u) : g;
+          const float ee = m.act ? g * Act<T>::gelu_grad(u) : g;
           acc[j][0] += ee;
           acc[j][1] = fmaf(ee, n, acc[j][1]);
-          acc[j][2] = fmaf(g, m.act ? gelu_f(u) : u, acc[j][2]);
+          acc[j][2] = fmaf(g, m.act ? Act<T>::gelu(u) : u, acc[j][2]);
           acc[j][3] = fmaf(g, sv[e], acc[j][3]);
         }
       }
@@ -826,12 +844,12 @@ k_mix_bwd_apply(const T* __restrict__ y, MixP m, const T* __restrict__ dout, con
 #pragma unroll
           for (int e = 0; e < V; ++e) {
             const float n = (yv[e] - mean) * rstd;
-            const float ee = m.act ? g[e] * gelu_grad_f(sc * n + sh) : g[e];
+            const float ee = m.act ? g[e] * Act<T>::gelu_grad(sc * n + sh) : g[e];
             r[e] = k * (ee - a1 - n * a2);
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < V; ++e) r[e] = al * ga * (m.act ? g[e] * gelu_grad_f(yv[e]) : g[e]);
+          for (int e = 0; e < V; ++e) r[e] = al * ga * (m.act ? g[e] * Act<T>::gelu_grad(yv[e]) : g[e]);
         }
         stv<V>(dy + o, r);
       }
@@ -843,7 +861,7 @@ k_mix_bwd_apply(const T* __restrict__ y, MixP m, const T* __restrict__ dout, con
 // 16-byte accesses (8 bf16 / 4 fp32 per thread and step); the tail of a length that is not a multiple runs element-wise.
 __device__ __forceinline__ void stvec(float* p, const float (&v)[4]) { st4(p, v); }
 __device__ __forceinline__ void stvec(bf16* p, const float (&v)[8]) { *reinterpret_cast<uint4*>(p) = sm100::pack8(v); }
-__device__ __forceinline__ float act_f(float v, int kind, float be) { return kind == 1 ? gelu_f(v) : v / (1.f + expf(-be * v)); }
+template <typename T> __device__ __forceinline__ float act_f(float v, int kind, float be) { return kind == 1 ? Act<T>::gelu(v) : v / (1.f + expf(-be * v)); }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -855,13 +873,13 @@ k_act_fwd(const T* __restrict__ x, T* __restrict__ y, long long n, int kind, con
     float v[VV];
     ldvec(x + i * VV, v);
 #pragma unroll
-    for (int j = 0; j < VV; ++j) v[j] = act_f(v[j], kind, be);
+    for (int j = 0; j < VV; ++j) v[j] = act_f<T>(v[j], kind, be);
     stvec(y + i * VV, v);
   }
-  for (long long i = nv * VV + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) stf(y + i, act_f(ldf(x + i), kind, be));
+  for (long long i = nv * VV + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) stf(y + i, act_f<T>(ldf(x + i), kind, be));
 }
-__device__ __forceinline__ float act_bwd_f(float v, float g, int kind, float be, float& db) {
-  if (kind == 1) return g * gelu_grad_f(v);
+template <typename T> __device__ __forceinline__ float act_bwd_f(float v, float g, int kind, float be, float& db) {
+  if (kind == 1) return g * Act<T>::gelu_grad(v);
   const float s = 1.f / (1.f + expf(-be * v)), ds = s * (1.f - s);
   db = fmaf(g, v * v * ds, db);
   return g * (s + v * be * ds);
@@ -880,11 +898,11 @@ k_act_bwd(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
     ldvec(x + i * VV, v);
     ldvec(dy + i * VV, g);
 #pragma unroll
-    for (int j = 0; j < VV; ++j) v[j] = act_bwd_f(v[j], g[j], kind, be, db);
+    for (int j = 0; j < VV; ++j) v[j] = act_bwd_f<T>(v[j], g[j], kind, be, db);
     stvec(dx + i * VV, v);
   }
   for (long long i = nv * VV + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    stf(dx + i, act_bwd_f(ldf(x + i), ldf(dy + i), kind, be, db));
+    stf(dx + i, act_bwd_f<T>(ldf(x + i), ldf(dy + i), kind, be, db));
   if (dbeta_acc) {
     db = warp_sum(db);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = db;
