@@ -212,8 +212,9 @@ class DataParallelTrainer:
             loss = self._discover_and_flatten(imgs, targets)
             if self.world > 1:
                 dist.all_reduce(self.flat_g, group=self.group)
-        elif self.graph and imgs.is_cuda and self._eager_after_discovery >= 1:
-            loss = self._graph_step(imgs, targets)
+        elif (self.graph and imgs.is_cuda and self._eager_after_discovery >= 1
+              and (self._static is None or (imgs.shape == self._static[0].shape and targets.shape == self._static[1].shape))):
+            loss = self._graph_step(imgs, targets)      # a batch of another shape (the last one of an epoch) runs eagerly below
         if loss is None:
             self._eager_after_discovery += 1
             self._pending = [c for _, _, c in self.buckets]
