@@ -40,9 +40,10 @@ using namespace adn::sm100;
 using namespace adn::tma;
 
 constexpr int BM = 128, BK = 64, STAGES = 4, MAX_BN = 256;
-constexpr int EPI_BUF_B = 4096, EPI_B = 4 * 2 * EPI_BUF_B;      // per epilogue warp: two 32-row x 128-byte staging slabs
+constexpr int EPI_BUF_B = 4096, EPI_B = 4 * 2 * EPI_BUF_B;      // per TMEM lane quarter (a PAIR of epilogue warps): two 32-row x 128-byte staging slabs
 constexpr int A_TILE_B = BM * BK * 2;                    // 16 KB in either orientation
-constexpr int THREADS = 192;      // 4 epilogue warps + MMA warp + TMA producer warp
+constexpr int THREADS = 320;      // 8 epilogue warps (two per TMEM lane quarter, splitting each slab's columns) + MMA warp + TMA producer warp
+constexpr int W_MMA = 8, W_TMA = 9;
 
 enum { C_BF16 = 0, C_F32 = 1, C_ATOMIC_F32 = 2 };
 
@@ -123,9 +124,13 @@ __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t tile, int ks) { retur
 
 // Persistent CTA: tiles (batch x split, m tile, n tile; n fastest so that consecutive CTAs share the A tile in L2) are taken
 // round-robin.  Three warp roles run concurrently and hand work over through mbarriers only:
-//   warps 5-8  producers: cp.async ring (STAGES deep) that runs continuously across tile boundaries
-//   warp  4    MMA issuer: one elected lane; accumulators double-buffered in TMEM (2 x BN columns)
-//   warps 0-3  epilogue: drains accumulator buffer i & 1 (TMEM lane quarter = warp) while the MMAs of tile i + 1 run
+//   warp  9    producer: TMA ring (STAGES deep) that runs continuously across tile boundaries
+//   warp  8    MMA issuer: one elected lane; accumulators double-buffered in TMEM (2 x BN columns)
+//   warps 0-7  epilogue: drain accumulator buffer i & 1 while the MMAs of tile i + 1 run.  Warps w and w + 4 share TMEM lane
+//              quarter w & 3 and split the column groups of every 128-byte slab (the skinny GEMMs of the mixer / FeedForward /
+//              Mlp / conv stages have ONE or two k-tiles per tile and were bound by four epilogue warps: knock-out timing in
+//              DESIGN.md, and GELU in the epilogue made inference slower); the pair shares the staging slabs and meets at a
+//              64-thread named barrier before the slab leaves through TMA
 static __global__ void __launch_bounds__(THREADS)
 k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_constant__ CUtensorMap mA0,
          const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUtensorMap mB1,
@@ -140,11 +145,11 @@ k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_c
   while ((int)tcols < BN) tcols <<= 1;
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(&tmem_slot, 2 * tcols);
-  if (warp == 5 && lane == 0) tma_prefetch_desc(&mC);
+  if (warp == W_MMA) tmem_alloc(&tmem_slot, 2 * tcols);
+  if (warp == W_TMA && lane == 0) tma_prefetch_desc(&mC);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -165,7 +170,7 @@ k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_c
   const int nk0 = (ke0 - kb0 + BK - 1) / BK;                                              \
   const int nk = nk0 + nk1;
 
-  if (warp == 5) {
+  if (warp == W_TMA) {
     // ---------------- TMA producer (one lane)
     if (lane == 0) {
       tma_prefetch_desc(&mA0); tma_prefetch_desc(&mB0);
@@ -211,7 +216,7 @@ k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_c
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == W_MMA) {
     // ---------------- MMA issuer (one lane)
     if (lane == 0) {
       const uint32_t idesc = make_idesc_rt(BM, BN, a.a_mn != 0, a.b_mn != 0);
@@ -240,10 +245,14 @@ k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_c
       }
     }
   } else {
-    // ---------------- epilogue: TMEM lane quarter `warp`, thread = output row; slabs of 128 bytes per row leave through TMA
+    // ---------------- epilogue: TMEM lane quarter `qd`, thread = output row; slabs of 128 bytes per row leave through TMA.
+    // Column groups of 16 accumulator columns: a slab holds 4 (bf16) or 2 (fp32) of them, half of which belong to this warp.
     const float alpha = a.alpha ? *a.alpha : 1.f;
-    const uint32_t sbuf = s0 + STAGES * stage_b + warp * 2 * EPI_BUF_B;      // this warp's two staging slabs (1024-byte aligned)
+    const int qd = warp & 3, half = warp >> 2;
+    const uint32_t sbuf = s0 + STAGES * stage_b + qd * 2 * EPI_BUF_B;      // the pair's two staging slabs (1024-byte aligned)
     const int cw = a.c_mode == C_BF16 ? 64 : 32;                             // columns per 128-byte slab
+    const int gpw = cw >> 5;                                                 // column groups per warp and slab: 2 (bf16) or 1 (fp32)
+#define TCG_PAIR_SYNC() asm volatile("bar.sync %0, 64;" ::"r"(qd + 1) : "memory")
     int i = 0, slab = 0;
     for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++i) {
       TCG_DECODE(tile)
@@ -251,27 +260,27 @@ k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_c
       const int ab = i & 1;
       ok &= mbar_wait(&acc_full[ab], (i >> 1) & 1);
       tc_fence_after();
-      const int row = warp * 32 + lane, m = m0 + row;
+      const int row = qd * 32 + lane, m = m0 + row;
       const uint32_t tacc = tbase + ab * tcols;
       for (int c0 = 0; c0 < BN && n0 + c0 < a.N; c0 += cw, ++slab) {
         const uint32_t sb = sbuf + (slab & 1) * EPI_BUF_B;
         if (slab >= 2) {                       // the TMA store that last read this slab has finished reading shared memory
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
+          if (half == 0 && lane == 0) bulk_wait_read<1>();
+          TCG_PAIR_SYNC();
         }
-        // all TMEM loads of the slab are issued before the one wait (a wait per 16 columns exposed the TMEM latency 16 times
-        // per 128 x 256 tile: the skinny, epilogue-bound GEMMs of the mixer / FeedForward spent most of their time there)
-        float vv[4][16];
+        // all TMEM loads of the warp's share of the slab are issued before the one wait
+        float vv[2][16];
         if (!(a.dbg & 32)) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (q * 16 < cw) tmem_ld16(tmem_addr(tacc, warp * 32, c0 + q * 16), vv[q]);
+          for (int gi = 0; gi < 2; ++gi)
+            if (gi < gpw) tmem_ld16(tmem_addr(tacc, qd * 32, c0 + (half * gpw + gi) * 16), vv[gi]);
           tmem_wait_ld();
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {          // 16 accumulator columns per step
-          if (q * 16 >= cw || (a.dbg & 16)) break;
-          float (&v)[16] = vv[q];
+        for (int gi = 0; gi < 2; ++gi) {          // 16 accumulator columns per step
+          if (gi >= gpw || (a.dbg & 16)) break;
+          const int q = half * gpw + gi;           // column group inside the slab
+          float (&v)[16] = vv[gi];
           const int n = n0 + c0 + q * 16;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -312,10 +321,10 @@ k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_c
           }
         }
         if (!(a.dbg & 8)) fence_async_smem();
-        __syncwarp();
-        if (lane == 0 && !(a.dbg & 1)) {
-          if (a.c_mode == C_ATOMIC_F32) tma_reduce_add_3d(&mC, sb, n0 + c0, m0 + warp * 32, batch);
-          else tma_store_3d(&mC, sb, n0 + c0, m0 + warp * 32, batch);
+        TCG_PAIR_SYNC();                       // both warps of the quarter have written (and fenced) their columns
+        if (half == 0 && lane == 0 && !(a.dbg & 1)) {
+          if (a.c_mode == C_ATOMIC_F32) tma_reduce_add_3d(&mC, sb, n0 + c0, m0 + qd * 32, batch);
+          else tma_store_3d(&mC, sb, n0 + c0, m0 + qd * 32, batch);
           bulk_commit();
         }
       }
@@ -324,14 +333,15 @@ k_tcgemm(const Args a, int tiles_m, int tiles_n, int tiles_total, const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive1(&acc_empty[ab]);
     }
-    if (lane == 0) bulk_wait_read<0>();      // shared memory must outlive the last TMA stores' reads
+    if (half == 0 && lane == 0) bulk_wait_read<0>();      // shared memory must outlive the last TMA stores' reads
     __syncwarp();
+#undef TCG_PAIR_SYNC
   }
 #undef TCG_DECODE
   if (!ok && a.status) *a.status = 1;
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tbase, 2 * tcols);
+  if (warp == W_MMA) tmem_dealloc(tbase, 2 * tcols);
 }
 
 // ---------------------------------------------------------------- host side
