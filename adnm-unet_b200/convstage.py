@@ -532,6 +532,8 @@ def make_bridge_conv_layer(ref_conv2d_layer):
     refhost while the network is built (the bridges are outside SURVEY.md section 8; this only removes ~2 400 cuDNN launches)."""
 
     class Conv2dLayer(ref_conv2d_layer):
+        _adnb200_bridge = True
+
         def forward(self, x):
             c = self.conv
             kh, kw = c.kernel_size

@@ -37,4 +37,10 @@ def install_into_reference(adnmunet_module="models.ADNMUNet", untils_module="mod
         for n in ("WTLayer", "PatchEmbed", "OutProj"):
             setattr(m, n, getattr(convstage, n))
             done.append(adnmunet_module + "." + n)
+        # the grouped convs of the EncoderToDecoder bridges: a subclass of the reference's own Conv2dLayer (models/model_untils.py:71-93),
+        # resolved by EncoderToDecoder.__init__ from models.model_untils' globals (:623-673)
+        u = importlib.import_module(untils_module)
+        if not getattr(u.Conv2dLayer, "_adnb200_bridge", False):
+            u.Conv2dLayer = convstage.make_bridge_conv_layer(u.Conv2dLayer)
+        done.append(untils_module + ".Conv2dLayer")
     return done
