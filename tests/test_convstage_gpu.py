@@ -357,3 +357,42 @@ def test_bridge_conv_layer_is_the_reference_layer():
     assert rel(ya, yb) < 1e-5 and rel(xa.grad, xb.grad) < 1e-5 and rel(new.conv.weight.grad, ref.conv.weight.grad) < 1e-4
     dense = cls(in_channels=8, out_channels=16, kernel_size=3, padding=1).to(dev)                # not a 4-channel-group conv: reference path
     assert dense(torch.randn(1, 8, 6, 6, device=dev)).shape == (1, 16, 6, 6)
+
+
+def test_container_nchw_entry_points_match_reference_layers():
+    """`WTConvLayer.forward` / `Conv2dLayer.forward` with the reference's NCHW signature (the stage modules call their token-major
+    forms; these are the containers' own entry points) against the unmodified reference layers on the same GPU, fp32."""
+    from adnm_unet_b200 import convstage, refhost
+    if not refhost.reference_available():
+        pytest.skip("reference sources not on this box")
+    ns = refhost.load_reference()
+    dev = torch.device("cuda:0")
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        x = torch.randn(2, 16, 12, 20, device=dev)
+        g = torch.randn(2, 16, 12, 20, device=dev)
+        for norm, act in ((True, None), (False, torch.nn.GELU), (True, torch.nn.GELU)):
+            kw = dict(in_channels=16, out_channels=16, kernel_size=5, stride=1, bias=True, wt_levels=2, act_func=act)
+            torch.manual_seed(4)
+            new = convstage.WTConvLayer(norm=torch.nn.InstanceNorm2d(16) if norm else None, **kw).to(dev)
+            ref = ns.model_untils.WTConvLayer(norm=torch.nn.InstanceNorm2d(16) if norm else None, **kw)
+            # the reference resolves the global WTConv2d at construction: whatever is bound, its state_dict layout is the same
+            ref.load_state_dict(new.state_dict(), strict=True)
+            ref = ref.to(dev)
+            xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+            ya, yb = new(xa), ref(xb)
+            ya.backward(g); yb.backward(g)
+            assert ya.shape == yb.shape and rel(ya, yb) < 1e-4 and rel(xa.grad, xb.grad) < 1e-4, (norm, act, rel(ya, yb), rel(xa.grad, xb.grad))
+        torch.manual_seed(5)
+        new = convstage.Conv2dLayer(16, 24, kernel_size=3, padding=1, bias=True, act_func=torch.nn.GELU).to(dev)
+        ref = ns.ref_Conv2dLayer(16, 24, kernel_size=3, padding=1, bias=True, act_func=torch.nn.GELU)
+        ref.load_state_dict(new.state_dict(), strict=True)
+        ref = ref.to(dev)
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        ya, yb = new(xa), ref(xb)
+        g2 = torch.randn_like(yb)
+        ya.backward(g2); yb.backward(g2)
+        assert rel(ya, yb) < 1e-4 and rel(xa.grad, xb.grad) < 1e-4 and rel(new.conv.weight.grad, ref.conv.weight.grad) < 1e-4
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
