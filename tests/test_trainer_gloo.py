@@ -150,3 +150,44 @@ def test_dead_bridge_pruning_is_bit_identical_on_cpu():
     ga, gb = ({k: p.grad for k, p in m.named_parameters()} for m in (a, b))
     assert all((ga[k] is None) == (gb[k] is None) for k in ga)
     assert all(torch.equal(ga[k], gb[k]) for k in ga if ga[k] is not None)
+
+
+def test_graph_mode_is_eager_on_cpu_tensors():
+    """DataParallelTrainer(graph=True) only captures CUDA steps: on host tensors (this container) the same trainer runs eagerly
+    and reproduces the graph=False trainer exactly - the switch cannot change results where no graph exists."""
+    from adnm_unet_b200.trainer import DataParallelTrainer
+    from adnm_unet_b200.refhost import ADAMW
+    g = torch.Generator().manual_seed(9)
+    X, Y = torch.randn(4, 8, 6, generator=g), torch.randn(4, 8, 3, generator=g)
+    finals = []
+    for graph in (False, True):
+        torch.manual_seed(0)
+        net = Net()
+        tr = DataParallelTrainer(net, _loss, clip_norm=0.05, adamw=dict(ADAMW), bucket_bytes=512, autocast_dtype=None, step_tail=torch_tail,
+                                 graph=graph)
+        losses = [float(tr.step(X[s], Y[s])) for s in range(4)]
+        assert tr._graph is None and tr.graph_error is None
+        finals.append((losses, tr.flat_p.clone()))
+    assert finals[0][0] == finals[1][0] and torch.equal(finals[0][1], finals[1][1])
+    # a batch of another shape after the first steps is simply another eager step
+    losses = float(tr.step(X[0, :5], Y[0, :5]))
+    assert losses == losses
+
+
+def test_bridge_conv_layer_falls_through_on_cpu():
+    """The Conv2dLayer subclass bound for the EncoderToDecoder bridges runs the reference's own forward for CPU tensors (and for any
+    configuration that is not a 4-channel-group conv): same parameters, same output."""
+    import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("reference not mounted")
+    from adnm_unet_b200 import convstage
+    ns = ref_loader.load_reference()
+    cls = convstage.make_bridge_conv_layer(ns.ref_Conv2dLayer)
+    kw = dict(in_channels=32, out_channels=32, kernel_size=(3, 1), stride=(1, 1), padding=(1, 0), bias=True, groups=8, act_func=nn.GELU)
+    torch.manual_seed(1)
+    a = cls(**kw)
+    torch.manual_seed(1)
+    b = ns.ref_Conv2dLayer(**kw)
+    assert list(a.state_dict()) == list(b.state_dict()) and all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
+    x = torch.randn(2, 32, 6, 6)
+    assert torch.equal(a(x), b(x)) and issubclass(cls, ns.ref_Conv2dLayer)
